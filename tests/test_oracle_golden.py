@@ -1,0 +1,80 @@
+"""Pin the oracle (oracle/vit_oracle.py) against golden vectors produced by the UNMODIFIED
+reference (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+
+CASES = ["tiny6_b4", "tiny6_b4_proto", "tiny6_b3_lowbnd", "p8s8_b2"]
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def load_case(golden_dir, name):
+    g = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    cfg = O.VitConfig(**g["cfg"])
+    sd = g.get("state_dict") or O.init_state_dict(cfg, seed=g["seed"])
+    for k, v in g["state_dict_checksum"].items():
+        assert abs(float(sd[k].double().abs().sum()) - v) <= 1e-9 * max(1.0, abs(v)), f"weight regen drift: {k}"
+    return g, cfg, {k: v.clone() for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(golden_dir, name):
+    g, cfg, sd = load_case(golden_dir, name)
+    hp = g["hp"]
+    kw = {}
+    if hp.get("use_proto"):
+        kw = dict(prototypes=g["prototypes"], w_pf=hp["w_pf"], w_pr=hp["w_pr"], BND_pro=hp["BND_pro"])
+    state = {}
+    for rec in g["steps"]:
+        out, grads = O.unlearn_step(sd, cfg, state, g["img_r"], g["lab_r"], g["img_f"], g["lab_f"],
+                                    lr=hp["lr"], wd=hp["wd"], beta=hp["beta"], alpha=hp["alpha"], BND=hp["BND"], **kw)
+        assert rel(out["logits_r"], rec["logits_r"]) < 2e-6
+        assert rel(out["logits_f"], rec["logits_f"]) < 2e-6
+        assert rel(out["emb_r"], rec["emb_r"]) < 2e-6
+        for key in ("loss_remain", "ce_forget", "loss_forget", "structure", "total", "proto_forget", "proto_remain"):
+            assert abs(float(out[key]) - rec[key]) <= 2e-5 * max(1.0, abs(rec[key])), key
+        sub = (lambda t: t.flatten()[::37]) if name == "p8s8_b2" else (lambda t: t)
+        for n in O.lora_param_list(cfg):
+            ref = rec["grads"][n]
+            assert (sub(grads[n]).double() - ref.double()).norm() <= 2e-5 * ref.double().norm() + 1e-9, n
+            assert rel(sub(sd[n]), rec["params_after"][n]) < 1e-5, n
+    l2 = O.norm_of_lora(sd, cfg, "L2")
+    l1 = O.norm_of_lora(sd, cfg, "L1")
+    for a, b in zip(l2, g["norm_of_lora_L2"]):
+        assert abs(float(a) - b) < 1e-4 * abs(b)
+    for a, b in zip(l1, g["norm_of_lora_L1"]):
+        assert abs(float(a) - b) < 1e-4 * abs(b)
+
+
+def test_lowbnd_gate_closed(golden_dir):
+    g, cfg, sd = load_case(golden_dir, "tiny6_b3_lowbnd")
+    assert g["steps"][0]["loss_forget"] == 0.0      # relu(BND - CE) closed => no forget gradient
+
+
+def test_merge_semantics_eval_forward(golden_dir):
+    """loralib eval(): W += B@A/r ; merged forward == unmerged forward."""
+    g, cfg, sd = load_case(golden_dir, "tiny6_b4")
+    # replay the two optimizer steps so sd matches the golden model's final state
+    hp = g["hp"]
+    state = {}
+    for _ in g["steps"]:
+        O.unlearn_step(sd, cfg, state, g["img_r"], g["lab_r"], g["img_f"], g["lab_f"], lr=hp["lr"], wd=hp["wd"],
+                       beta=hp["beta"], alpha=hp["alpha"], BND=hp["BND"])
+    with torch.no_grad():
+        logits, _ = O.vit_forward(sd, cfg, g["img_r"], g["lab_r"])
+    assert rel(logits, g["eval_logits_r"]) < 1e-5
+    n0 = O.blk(0, "1.fn.fn.net.0.")
+    merged = sd[n0 + "weight"] + (sd[n0 + "lora_B"] @ sd[n0 + "lora_A"]) * cfg.lora_scaling
+    assert rel(merged[:4, :8], g["eval_merged_fc1_w0"]) < 1e-6
+
+
+def test_flop_table_matches_baseline_md():
+    f = O.flops_per_image(O.P8S8)
+    assert abs(f["fwd"] / 1e9 - 8.049) < 0.01
+    assert abs(f["bwd"] / 1e9 - 7.599) < 0.01
