@@ -1,0 +1,473 @@
+// gslora-b200: the frozen-weight GEMM family of the GS-LoRA hot path on tcgen05 tensor cores.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )      A, B fp16 K-major, fp32 accumulation in TMEM
+//
+// This one kernel template serves every dense contraction of the reference's step
+// (vit_pytorch_face/vit_face.py:326-379 forward, autograd's dX GEMMs in engine_cl.py:124):
+//   QKV / attention-out / patch-embed projections, FFN fc1 (+bias +GELU) and fc2 (+bias +residual),
+//   and the backward dX GEMMs through the frozen weights (with the GELU' epilogue).
+// The LoRA branch  s*(x A^T) B^T  of loralib.Linear.forward rides along as an extra K = 16 MMA step:
+// the activation buffers carry the rank-r intermediate T = x A^T in 16 trailing columns and the
+// cached fp16 weight carries s*B in 16 trailing columns, so  [x | T] [W | sB]^T = x W^T + s T B^T
+// is produced by the same TMA pipeline and the same accumulator (K = in_features + 16).
+//
+// Structure (persistent, warp specialised, 192 threads):
+//   warp 0    TMA producer      cp.async.bulk.tensor 128B-swizzled A/B tiles -> smem ring (mbarrier full/empty)
+//   warp 1    MMA issuer        one lane issues tcgen05.mma (cta_group::1 or ::2), accumulators in TMEM,
+//                               tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2-5 epilogue          tcgen05.ld TMEM -> registers -> fused math -> swizzled smem -> TMA store,
+//                               auxiliary input tiles (residual / pre-GELU H) arrive by TMA, double buffered
+// Two TMEM accumulator buffers (2 x BLOCK_N columns) overlap the epilogue of tile i with the MMAs of tile i+1.
+#include "gsl_common.cuh"
+#include "gsl_kernels.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace gsl {
+
+static constexpr int BLOCK_M = 128;   // rows per CTA (UMMA M = 128 * CTA_GROUP)
+static constexpr int BLOCK_K = 64;    // 64 fp16 = one 128-byte swizzle row
+static constexpr int SMEM_LIMIT = 232448;
+static constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+    int M, N, K;
+    int num_m_tiles;      // super-tiles of 128 * CTA_GROUP rows
+    int num_n_tiles;
+    const float* bias;    // [N] or nullptr
+    const float* table;   // EPI_PERIODIC_F32: fp32 [period, ld_table]
+    int period, ld_table;
+    int has_out1;         // EPI_RES_F32 / EPI_F32: also emit an fp16 copy through tmO1
+};
+
+template <int EPI> struct EpiTraits;
+//                                                          out0 bytes/elem, out1?, aux bytes/elem (0 = none)
+template <> struct EpiTraits<EPI_F16>          { static constexpr int O0 = 2, O1 = 0, AUX = 0; };
+template <> struct EpiTraits<EPI_F32>          { static constexpr int O0 = 4, O1 = 2, AUX = 0; };
+template <> struct EpiTraits<EPI_GELU>         { static constexpr int O0 = 2, O1 = 2, AUX = 0; };
+template <> struct EpiTraits<EPI_GELU_BWD>     { static constexpr int O0 = 2, O1 = 0, AUX = 2; };
+template <> struct EpiTraits<EPI_RES_F32>      { static constexpr int O0 = 4, O1 = 2, AUX = 4; };
+template <> struct EpiTraits<EPI_PERIODIC_F32> { static constexpr int O0 = 4, O1 = 0, AUX = 0; };
+
+template <int CG, int BN, int EPI>
+struct GemmCfg {
+    using T = EpiTraits<EPI>;
+    static constexpr int A_STAGE = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_STAGE = (BN / CG) * BLOCK_K * 2;
+    static constexpr int STAGE = A_STAGE + B_STAGE;
+    // per epilogue warp: 32 rows x 32 columns per chunk, two buffers per tensor
+    static constexpr int O0_BUF = 32 * 32 * T::O0;
+    static constexpr int O1_BUF = 32 * 32 * T::O1;
+    static constexpr int AUX_BUF = 32 * 32 * T::AUX;
+    static constexpr int EPI_WARP = 2 * (O0_BUF + O1_BUF + AUX_BUF);
+    static constexpr int EPI_TOTAL = 4 * EPI_WARP;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - EPI_TOTAL - BAR_BYTES) / STAGE;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE + EPI_TOTAL + BAR_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static_assert(STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+    static_assert(EPI_WARP % 1024 == 0, "staging must keep 1024-byte alignment");
+};
+
+template <int CG, int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+                    const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+    using Cfg = GemmCfg<CG, BN, EPI>;
+    using T = EpiTraits<EPI>;
+    constexpr int S = Cfg::STAGES;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t sA = smem_base;
+    const uint32_t sB = sA + S * Cfg::A_STAGE;
+    const uint32_t sEpi = sB + S * Cfg::B_STAGE;
+    const uint32_t sBar = sEpi + Cfg::EPI_TOTAL;
+    auto full_bar = [&](int i) { return sBar + 8u * i; };
+    auto empty_bar = [&](int i) { return sBar + 8u * (S + i); };
+    auto tfull_bar = [&](int i) { return sBar + 8u * (2 * S + i); };
+    auto tempty_bar = [&](int i) { return sBar + 8u * (2 * S + 2 + i); };
+    auto aux_bar = [&](int w, int i) { return sBar + 8u * (2 * S + 4 + 2 * w + i); };
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (sBar - smem_base) + 8 * (2 * S + 4 + 8));
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+
+    if (CG == 2) cluster_sync_all();   // both CTAs of the pair are resident before the paired TMEM allocation
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO0);
+        if (T::O1) tma_prefetch_desc(&tmO1);
+        if (T::AUX) tma_prefetch_desc(&tmAux);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < S; ++i) {
+                mbar_init(full_bar(i), CG);     // producer arrivals (leader + peer), tx bytes from both CTAs
+                mbar_init(empty_bar(i), 1);     // one tcgen05.commit
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(tfull_bar(i), 1);             // one tcgen05.commit
+                mbar_init(tempty_bar(i), CG * 128);     // every epilogue thread of the pair
+            }
+            for (int w = 0; w < 4; ++w)
+                for (int i = 0; i < 2; ++i) mbar_init(aux_bar(w, i), 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<CG>(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
+    }
+    tcgen05_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_clusters = gridDim.x / CG;
+    const int cluster_id = blockIdx.x / CG;
+    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+                const int mt = t / p.num_n_tiles, nt = t % p.num_n_tiles;
+                const int m_base = (mt * CG + (int)cta_rank) * BLOCK_M;
+                const int n_base = nt * BN + (int)cta_rank * (BN / CG);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE * CG);
+                    tma_load_2d<CG>(&tmA, full_bar(stage), sA + stage * Cfg::A_STAGE, kb * BLOCK_K, m_base);
+                    tma_load_2d<CG>(&tmB, full_bar(stage), sB + stage * Cfg::B_STAGE, kb * BLOCK_K, n_base);
+                    if (!leader) mbar_arrive_cluster(full_bar(stage), 0);
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (leader CTA of the pair only)
+        if (leader) {
+            constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M * CG, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters, ++iter) {
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (iter >> 1) & 1;
+                if (CG == 2) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1); else mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (CG == 2) mbar_wait_cluster(full_bar(stage), phase); else mbar_wait(full_bar(stage), phase);
+                    tcgen05_fence_after();
+                    if (lane == 0) {
+                        const uint64_t da = umma_desc_sw128(sA + stage * Cfg::A_STAGE);
+                        const uint64_t db = umma_desc_sw128(sB + stage * Cfg::B_STAGE);
+                        const int krem = p.K - kb * BLOCK_K;
+                        const int nk = krem >= BLOCK_K ? BLOCK_K / 16 : (krem + 15) / 16;   // ragged last k-block (LoRA K+16)
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 16; ++k) {
+                            if (k < nk) umma_f16<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        umma_commit<CG>(empty_bar(stage));                 // smem stage free once these MMAs retire
+                        if (kb == num_kb - 1) umma_commit<CG>(tfull_bar(acc));   // accumulator complete
+                    }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps
+        const uint32_t quarter = warp & 3;              // TMEM lane quarter this warp may access
+        const uint32_t ew = warp - 2;
+        const uint32_t stg = sEpi + ew * Cfg::EPI_WARP;
+        // ordered large -> small so every buffer keeps the alignment its swizzle mode needs
+        uint32_t off = 0;
+        uint32_t o0_buf[2], o1_buf[2], aux_buf[2];
+        if (T::O0 == 4) { o0_buf[0] = stg + off; o0_buf[1] = stg + off + Cfg::O0_BUF; off += 2 * Cfg::O0_BUF; }
+        if (T::AUX == 4) { aux_buf[0] = stg + off; aux_buf[1] = stg + off + Cfg::AUX_BUF; off += 2 * Cfg::AUX_BUF; }
+        if (T::O0 == 2) { o0_buf[0] = stg + off; o0_buf[1] = stg + off + Cfg::O0_BUF; off += 2 * Cfg::O0_BUF; }
+        if (T::O1 == 2) { o1_buf[0] = stg + off; o1_buf[1] = stg + off + Cfg::O1_BUF; off += 2 * Cfg::O1_BUF; }
+        if (T::AUX == 2) { aux_buf[0] = stg + off; aux_buf[1] = stg + off + Cfg::AUX_BUF; off += 2 * Cfg::AUX_BUF; }
+        const bool write_o1 = (EPI == EPI_GELU) || ((EPI == EPI_RES_F32 || EPI == EPI_F32) && p.has_out1);
+
+        int iter = 0;
+        uint32_t aux_it = 0;     // aux chunks consumed so far (buffer = aux_it & 1, parity = (aux_it >> 1) & 1)
+        uint32_t st_it = 0;      // store chunks issued so far (staging buffer = st_it & 1)
+        for (int t = cluster_id; t < total_tiles; t += num_clusters, ++iter) {
+            const int mt = t / p.num_n_tiles, nt = t % p.num_n_tiles;
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int row0 = (mt * CG + (int)cta_rank) * BLOCK_M + (int)quarter * 32;
+            const int n_base = nt * BN;
+            const int n_rem = p.N - n_base;
+            const int nchunks = (n_rem >= BN ? BN : n_rem + 31) / 32;
+            const bool rows_live = row0 < p.M;     // warp-uniform
+
+            if (T::AUX && rows_live && lane == 0) {
+                const uint32_t b = aux_it & 1;
+                mbar_arrive_expect_tx(aux_bar(ew, b), Cfg::AUX_BUF);
+                tma_load_2d<1>(&tmAux, aux_bar(ew, b), aux_buf[b], n_base, row0);
+            }
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + acc * BN + c * 32, v);
+                if (T::AUX && rows_live && lane == 0 && c + 1 < nchunks) {
+                    const uint32_t b = (aux_it + 1) & 1;
+                    mbar_arrive_expect_tx(aux_bar(ew, b), Cfg::AUX_BUF);
+                    tma_load_2d<1>(&tmAux, aux_bar(ew, b), aux_buf[b], n_base + (c + 1) * 32, row0);
+                }
+                tmem_ld_wait();
+                if (c == nchunks - 1) {
+                    // all TMEM reads of this accumulator are in registers: hand the buffer back to the MMA warp
+                    tcgen05_fence_before();
+                    if (CG == 2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+                }
+                if (!rows_live) continue;
+
+                const int n0 = n_base + c * 32;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (n0 + j < p.N) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                        }
+                    }
+                }
+                if (T::AUX) {
+                    const uint32_t b = aux_it & 1;
+                    mbar_wait(aux_bar(ew, b), (aux_it >> 1) & 1);
+                    if (T::AUX == 4) {          // fp32 residual tile, 128-byte rows
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 r;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(aux_buf[b] + sw128_off(lane, j)));
+                            f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+                        }
+                    } else {                    // fp16 pre-activation tile H, 64-byte rows: dH = dG * gelu'(H)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t h0, h1, h2, h3;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(aux_buf[b] + sw64_off(lane, j)));
+                            const uint32_t hh[4] = {h0, h1, h2, h3};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 h = unpack_half2(hh[q]);
+                                f[8 * j + 2 * q] *= gelu_grad_f(h.x);
+                                f[8 * j + 2 * q + 1] *= gelu_grad_f(h.y);
+                            }
+                        }
+                    }
+                    __syncwarp();      // every lane has consumed the aux buffer before it is refilled
+                    ++aux_it;
+                }
+                if (EPI == EPI_PERIODIC_F32) {
+                    const int r = row0 + (int)lane;
+                    if (r < p.M) {
+                        const float* trow = p.table + (size_t)(r % p.period) * p.ld_table + n0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (n0 + j < p.N) {
+                                const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + j));
+                                f[j] += t4.x; f[j + 1] += t4.y; f[j + 2] += t4.z; f[j + 3] += t4.w;
+                            }
+                        }
+                    }
+                }
+
+                // staging buffer reuse: the TMA store issued two chunks ago must have finished reading smem
+                const uint32_t sb = st_it & 1;
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+
+                if (T::O0 == 4) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                                     ::"r"(o0_buf[sb] + sw128_off(lane, j)), "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                     ::"r"(o0_buf[sb] + sw64_off(lane, j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
+                                       "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
+                }
+                if (T::O1 && write_o1) {
+                    if (EPI == EPI_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_f(f[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                     ::"r"(o1_buf[sb] + sw64_off(lane, j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
+                                       "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmO0, o0_buf[sb], n0, row0);
+                    if (T::O1 && write_o1) tma_store_2d(&tmO1, o1_buf[sb], n0, row0);
+                    tma_store_commit();
+                }
+                ++st_it;
+            }
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+
+    // ===================================================== teardown
+    tcgen05_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static int load_encode() {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    });
+    return g_encode ? 0 : -1;
+}
+
+// 2-D row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols]
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
+                 int box_rows, int box_cols) {
+    GSL_REQUIRE(load_encode() == 0, "cuTensorMapEncodeTiled entry point not available");
+    GSL_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base pointer must be 16-byte aligned (%p)", ptr);
+    GSL_REQUIRE((ld * elem_bytes) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (ld=%lld)", (long long)ld);
+    const int inner_bytes = box_cols * elem_bytes;
+    CUtensorMapSwizzle sw;
+    if (inner_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    else if (inner_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+    else if (inner_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+    else { set_last_error("unsupported TMA box width %d bytes", inner_bytes); return -1; }
+    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)(ld * elem_bytes)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GSL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r,
+                (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
+    return 0;
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+template <int CG, int BN, int EPI>
+static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+    using Cfg = GemmCfg<CG, BN, EPI>;
+    using T = EpiTraits<EPI>;
+    CUtensorMap tmA, tmB, tmO0, tmO1, tmAux;
+    int rc;
+    if ((rc = make_tmap_2d(&tmA, a.A, 2, a.M, a.K, a.lda, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = make_tmap_2d(&tmB, a.B, 2, a.N, a.K, a.ldb, BN / CG, BLOCK_K))) return rc;
+    if ((rc = make_tmap_2d(&tmO0, a.out0, T::O0, a.M, a.N, a.ld0, 32, 32))) return rc;
+    const bool has_o1 = (EPI == EPI_GELU) || (T::O1 && a.out1 != nullptr);
+    if (has_o1) { if ((rc = make_tmap_2d(&tmO1, a.out1, 2, a.M, a.N, a.ld1, 32, 32))) return rc; } else tmO1 = tmO0;
+    if (T::AUX) { if ((rc = make_tmap_2d(&tmAux, a.aux, T::AUX, a.M, a.N, a.ldaux, 32, 32))) return rc; } else tmAux = tmO0;
+
+    GemmParams p;
+    p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K;
+    p.num_m_tiles = (int)((a.M + BLOCK_M * CG - 1) / (BLOCK_M * CG));
+    p.num_n_tiles = (int)((a.N + BN - 1) / BN);
+    p.bias = a.bias;
+    p.table = (EPI == EPI_PERIODIC_F32) ? reinterpret_cast<const float*>(a.aux) : nullptr;
+    p.period = (int)a.aux_period; p.ld_table = (int)a.ldaux;
+    p.has_out1 = has_o1 ? 1 : 0;
+
+    auto kern = gemm_tcgen05_kernel<CG, BN, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GSL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int sms = device_sm_count();
+    const int total = p.num_m_tiles * p.num_n_tiles;
+    int clusters = sms / CG;
+    if (clusters > total) clusters = total;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CG);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    GSL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO0, tmO1, tmAux, p));
+    return 0;
+}
+
+template <int CG, int BN>
+static int dispatch_epi(const GemmArgs& a, cudaStream_t s) {
+    switch (a.epi) {
+        case EPI_F16: return launch_gemm<CG, BN, EPI_F16>(a, s);
+        case EPI_F32: return launch_gemm<CG, BN, EPI_F32>(a, s);
+        case EPI_GELU: return launch_gemm<CG, BN, EPI_GELU>(a, s);
+        case EPI_GELU_BWD: return launch_gemm<CG, BN, EPI_GELU_BWD>(a, s);
+        case EPI_RES_F32: return launch_gemm<CG, BN, EPI_RES_F32>(a, s);
+        case EPI_PERIODIC_F32: return launch_gemm<CG, BN, EPI_PERIODIC_F32>(a, s);
+        default: set_last_error("unknown GEMM epilogue %d", a.epi); return -1;
+    }
+}
+
+static int g_default_cta_group = 2;
+void gemm_set_default_cta_group(int cg) { g_default_cta_group = (cg == 1) ? 1 : 2; }
+
+int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
+    GSL_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "empty GEMM %lldx%lldx%lld", (long long)a.M, (long long)a.N, (long long)a.K);
+    GSL_REQUIRE(a.K % 16 == 0 && a.N % 8 == 0, "GEMM needs K %% 16 == 0 and N %% 8 == 0 (N=%lld K=%lld)", (long long)a.N, (long long)a.K);
+    GSL_REQUIRE(a.A && a.B && a.out0, "null GEMM operand");
+    if (a.epi == EPI_GELU) GSL_REQUIRE(a.out1 != nullptr, "EPI_GELU needs out1");
+    if (a.epi == EPI_GELU_BWD || a.epi == EPI_RES_F32 || a.epi == EPI_PERIODIC_F32) GSL_REQUIRE(a.aux != nullptr, "epilogue %d needs aux", a.epi);
+    if (a.epi == EPI_PERIODIC_F32) GSL_REQUIRE(a.aux_period > 0, "EPI_PERIODIC_F32 needs aux_period > 0");
+    const int cg = a.cta_group ? a.cta_group : g_default_cta_group;
+    const int bn = a.block_n ? a.block_n : ((a.N % 256 == 0 || a.N > 1024) ? 256 : 128);
+    if (cg == 2) return bn == 256 ? dispatch_epi<2, 256>(a, stream) : dispatch_epi<2, 128>(a, stream);
+    return bn == 256 ? dispatch_epi<1, 256>(a, stream) : dispatch_epi<1, 128>(a, stream);
+}
+
+}  // namespace gsl

@@ -1,0 +1,109 @@
+// gslora-b200: internal C++ launcher interface shared by the engine and the C-ABI (include/gslora.h).
+// Every launcher is asynchronous on `stream`, returns 0 on success (else a cudaError_t / -1 with text in
+// gsl_last_error()), allocates nothing and never synchronises.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gsl {
+
+enum GemmEpi {
+    EPI_F16 = 0,           // out0(fp16) = acc + bias
+    EPI_F32 = 1,           // out0(fp32) = acc + bias                    [+ out1(fp16) copy]
+    EPI_GELU = 2,          // out0(fp16) = h = acc + bias ; out1(fp16) = gelu(h)          (FFN fc1)
+    EPI_GELU_BWD = 3,      // out0(fp16) = acc * gelu'(aux(fp16))                          (dH = dG * gelu'(H))
+    EPI_RES_F32 = 4,       // out0(fp32) = acc + bias + aux(fp32)        [+ out1(fp16) copy] (residual adds)
+    EPI_PERIODIC_F32 = 5,  // out0(fp32) = acc + aux_table(fp32)[row % period]             (patch embed + pos/cls)
+};
+
+struct GemmArgs {
+    const __half* A = nullptr; int64_t lda = 0;     // [M, K] row-major
+    const __half* B = nullptr; int64_t ldb = 0;     // [N, K] row-major (a torch Linear weight)
+    int64_t M = 0, N = 0, K = 0;
+    int epi = EPI_F16;
+    const float* bias = nullptr;
+    void* out0 = nullptr; int64_t ld0 = 0;
+    void* out1 = nullptr; int64_t ld1 = 0;
+    const void* aux = nullptr; int64_t ldaux = 0; int64_t aux_period = 0;
+    int cta_group = 0;   // 0 = library default, 1 or 2
+    int block_n = 0;     // 0 = auto, 128 or 256
+};
+int gemm_f16(const GemmArgs& a, cudaStream_t stream);
+void gemm_set_default_cta_group(int cg);
+int device_sm_count();
+
+// ---- elementwise / normalisation (gsl_rowops.cu)
+// img [B,C,S,S] fp32 NCHW -> patches fp16 [B*(P+1), ld] with a zero row at token 0 of every image;
+// order 0: (p1 p2 c) channel fastest (vit_face.py:530); order 1: (c p1 p2) (torchvision conv_proj)
+int patchify_f16(const float* img, __half* out, int64_t ld, int B, int C, int S, int patch, int order, cudaStream_t s);
+// y = LN(x) * gamma + beta -> fp16 [M, ldy] ; saves mean/rstd ; optionally T = y * A^T (r <= 16) into y[:, D:D+16]
+int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, __half* y, int64_t ldy,
+                  float* mean, float* rstd, const __half* loraA, int r, int64_t M, int D, cudaStream_t s);
+// dx = dres + LNbwd(dy) ; writes fp32 dx and an fp16 copy (GEMM operand for the next dX GEMM)
+int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                  const float* gamma, const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16,
+                  int64_t M, int D, cudaStream_t s);
+// T[M, 0:16] = X[M, K] * A16[16, K]^T  (fp16 in, fp32 accumulate, fp16 out at out[:, 0:16], row pitch ldo)
+int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __half* out, int64_t ldo, int64_t M, int K, cudaStream_t s);
+// dW[R, 16-ish] style skinny reductions over M (split-M partials + deterministic second pass):
+//   out[n, j] = scale * sum_m  L[m, n] * Rm[m, j]   n < N, j < r    (L fp16 [M, ldl], Rm fp16 [M, ldr])
+//   optional elementwise GELU applied to L on load (dA2 = s * U2^T * gelu(H))
+int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float* out, int64_t ldo, int transpose_out,
+              float scale, int64_t M, int N, int r, int gelu_on_load, float* workspace, size_t workspace_bytes, cudaStream_t s);
+size_t skinny_tn_workspace(int64_t M, int N, int r);
+// fp32 -> fp16 casts with optional scale / transpose / column placement (weight cache building, LoRA operand packing)
+int cast_f32_to_f16(const float* src, int64_t lds, __half* dst, int64_t ldd, int64_t rows, int64_t cols, float scale,
+                    int transpose, cudaStream_t s);
+int fill_zero(void* ptr, size_t bytes, cudaStream_t s);
+
+// ---- attention (gsl_attention.cu); qkv fp16 [B*N, ld] with q|k|v column blocks of heads*64
+int attention_fwd(const __half* qkv, int64_t ld, __half* out, int64_t ldo, float* lse, int B, int N, int heads, float scale, cudaStream_t s);
+int attention_bwd(const __half* qkv, int64_t ld, const __half* out, int64_t ldo, const __half* dout, int64_t lddo, const float* lse,
+                  __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s);
+
+// ---- head / losses (gsl_head.cu)
+struct HeadArgs {
+    const float* x; int64_t ldx;      // final residual stream [B*N, D]; cls row = b * tokens
+    int tokens;
+    const float* gamma; const float* beta; float eps;    // mlp_head LayerNorm
+    const float* W;                   // [C, D] CosFace weight (loss.weight)
+    const int64_t* labels;            // [B]
+    float cos_s, cos_m;
+    int B, D, C;
+    float* emb;                       // [B, D]
+    float* logits;                    // [B, C]
+    float* ce;                        // [B] per-sample cross entropy
+    int* correct;                     // [B] argmax == label
+    float* xhat;                      // [B, D] saved normalised cls rows
+    float* rstd;                      // [B]
+};
+int head_fwd(const HeadArgs& a, cudaStream_t s);
+// d logits / d emb (either may be null) -> gradient wrt the cls rows of the final residual stream, scaled by gscale;
+// writes dx (fp32 [B*N, D], only cls rows touched) and dx16
+struct HeadBwdArgs {
+    const float* dlogits;             // [B, C] or null
+    const float* demb;                // [B, D] or null
+    const float* emb; const float* W; const int64_t* labels; const float* xhat; const float* rstd; const float* gamma;
+    float cos_s; int B, D, C, tokens;
+    float gscale;
+    float* dx; int64_t lddx; __half* dx16; int64_t lddx16;
+};
+int head_bwd(const HeadBwdArgs& a, cudaStream_t s);
+// dlogits[b, :] = coef * (softmax(logits[b]) - onehot) / B_total ; coef read from device (gate applied by caller)
+int ce_grad(const float* logits, const int64_t* labels, const float* coef_dev, float scale, float* dlogits, int B, int C, cudaStream_t s);
+
+// ---- optimizer (gsl_optim.cu)
+struct OptimArgs {
+    float* params; const float* grads; float* m; float* v;   // flat fp32 buffers, `n` elements
+    const int* group_offsets;   // device [G + 1] element offsets of the group-lasso groups in the flat buffer
+    int num_groups; int64_t n;
+    float lr, wd, beta1, beta2, eps, alpha, grad_scale;      // grad_scale multiplies grads (1 / loss scale / world)
+    int step;                                                // 1-based
+    float* group_norms;         // device [G] : sqrt(sum p^2) per group, pre-update (structure loss terms)
+};
+int grouplasso_adamw_step(const OptimArgs& a, cudaStream_t s);
+// per tensor Frobenius / L1 norms for util.cal_norm.get_norm_of_lora: out[t] = ||P_t||_F (type 0) or ||P_t||_1 (type 1)
+int tensor_norms(const float* params, const int* tensor_offsets, int num_tensors, int type, float* out, cudaStream_t s);
+
+}  // namespace gsl

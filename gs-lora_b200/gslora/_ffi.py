@@ -1,0 +1,69 @@
+"""ctypes binding of libgslora.so (include/gslora.h).  The library is built in-tree by
+`__graft_entry__.build()` / `make -C gs-lora_b200/csrc`; there is NO fallback: if the shared object is
+missing or a call fails, an exception is raised."""
+import ctypes
+import os
+
+import torch
+
+_LIB = None
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgslora.so")
+
+c_void_p, c_int, c_int64, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+
+
+class GslError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise GslError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(gslora-b200 has no CPU / PyTorch fallback)")
+        _LIB = ctypes.CDLL(LIB_PATH)
+        _declare(_LIB)
+    return _LIB
+
+
+def _declare(L):
+    L.gsl_last_error.restype = ctypes.c_char_p
+    L.gsl_version.restype = c_int
+    L.gsl_set_gemm_cta_group.argtypes = [c_int]
+    L.gsl_gemm_f16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p,
+                               c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]
+    L.gsl_gemm_f16.restype = c_int
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().gsl_last_error().decode(errors="replace")
+        raise GslError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "gslora-b200 operates on CUDA tensors only (no CPU fallback)"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+EPI_F16, EPI_F32, EPI_GELU, EPI_GELU_BWD, EPI_RES_F32, EPI_PERIODIC_F32 = range(6)
+
+
+def gemm_f16(A, B, *, epi=EPI_F16, bias=None, out0, out1=None, aux=None, aux_period=0, K=None, N=None, M=None,
+             cta_group=0, block_n=0):
+    """out = epi(A[:, :K] @ B[:, :K].T); A, B fp16 row-major 2-D (possibly column-sliced views)."""
+    M = A.shape[0] if M is None else M
+    K = A.shape[1] if K is None else K
+    N = B.shape[0] if N is None else N
+    rc = lib().gsl_gemm_f16(ptr(A), A.stride(0), ptr(B), B.stride(0), M, N, K, epi, ptr(bias),
+                            ptr(out0), out0.stride(0), ptr(out1), out1.stride(0) if out1 is not None else 0,
+                            ptr(aux), aux.stride(0) if aux is not None else 0, aux_period, cta_group, block_n, cur_stream())
+    check(rc, "gsl_gemm_f16")
