@@ -1,6 +1,6 @@
 // gslora-b200: extern "C" surface declared in include/gslora.h.
 #include "../../include/gslora.h"
-#include "gsl_kernels.h"
+#include "gsl_engine.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -33,6 +33,97 @@ int gsl_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
     a.aux = aux; a.ldaux = ldaux; a.aux_period = aux_period;
     a.cta_group = cta_group; a.block_n = block_n;
     return gemm_f16(a, (cudaStream_t)stream);
+}
+
+
+#define ST(x) ((cudaStream_t)(x))
+
+int gsl_patchify_f16(const float* img, void* out, int64_t ld, int B, int C, int S, int patch, int order, void* stream) {
+    return patchify_f16(img, (__half*)out, ld, B, C, S, patch, order, ST(stream));
+}
+int gsl_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y16, int64_t ldy, float* mean,
+                      float* rstd, int64_t M, int D, void* stream) {
+    return layernorm_fwd(x, ldx, gamma, beta, eps, (__half*)y16, ldy, mean, rstd, M, D, ST(stream));
+}
+int gsl_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+                      const float* dres, int64_t lddres, float* dx, int64_t lddx, void* dx16, int64_t lddx16, int64_t M, int D, void* stream) {
+    return layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__half*)dx16, lddx16, M, D, ST(stream));
+}
+int gsl_lora_down(const void* X16, int64_t ldx, const void* A16, int64_t lda, void* out16, int64_t ldo, int64_t M, int K, int r, void* stream) {
+    return lora_down((const __half*)X16, ldx, (const __half*)A16, lda, (__half*)out16, ldo, M, K, r, ST(stream));
+}
+size_t gsl_skinny_tn_workspace(int64_t M, int N, int r) { return skinny_tn_workspace(M, N, r); }
+int gsl_skinny_tn(const void* L16, int64_t ldl, const void* R16, int64_t ldr, float* out, int64_t ldo, int transpose_out, float scale,
+                  int accumulate, int64_t M, int N, int r, float* workspace, size_t workspace_bytes, void* stream) {
+    return skinny_tn((const __half*)L16, ldl, (const __half*)R16, ldr, out, ldo, transpose_out, scale, accumulate, M, N, r, workspace,
+                     workspace_bytes, ST(stream));
+}
+int gsl_attention_fwd(const void* qkv16, int64_t ld, void* out16, int64_t ldo, float* lse, int B, int N, int heads, float scale, void* stream) {
+    return attention_fwd((const __half*)qkv16, ld, (__half*)out16, ldo, lse, B, N, heads, scale, ST(stream));
+}
+int gsl_attention_bwd(const void* qkv16, int64_t ld, const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
+                      void* dqkv16, int64_t lddqkv, int B, int N, int heads, float scale, void* stream) {
+    return attention_bwd((const __half*)qkv16, ld, (const __half*)out16, ldo, (const __half*)dout16, lddo, lse, (__half*)dqkv16, lddqkv, B, N,
+                         heads, scale, ST(stream));
+}
+int gsl_cast_f32_to_f16(const float* src, int64_t lds, void* dst16, int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose,
+                        void* stream) {
+    return cast_f32_to_f16(src, lds, (__half*)dst16, ldd, rows, cols, scale, transpose, ST(stream));
+}
+int gsl_grouplasso_adamw_step(float* params, const float* grads, float* m, float* v, const int32_t* group_offsets, int num_groups, int64_t n,
+                              float lr, float wd, float beta1, float beta2, float eps, float alpha, float grad_scale, int step,
+                              float* group_norms, void* stream) {
+    OptimArgs a;
+    a.params = params; a.grads = grads; a.m = m; a.v = v; a.group_offsets = group_offsets; a.num_groups = num_groups; a.n = n;
+    a.lr = lr; a.wd = wd; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.alpha = alpha; a.grad_scale = grad_scale; a.step = step;
+    a.group_norms = group_norms;
+    return grouplasso_adamw_step(a, ST(stream));
+}
+int gsl_tensor_norms(const float* params, const int32_t* tensor_offsets, int num_tensors, int type, float* out, void* stream) {
+    return tensor_norms(params, tensor_offsets, num_tensors, type, out, ST(stream));
+}
+
+size_t gsl_engine_workspace_bytes(const GslConfig* cfg) { return Engine::workspace_bytes(*cfg); }
+int gsl_engine_create(const GslConfig* cfg, void* workspace, size_t workspace_bytes, void** handle_out) {
+    Engine* e = new Engine();
+    int rc = e->init(*cfg, workspace, workspace_bytes);
+    if (rc) { delete e; *handle_out = nullptr; return rc; }
+    *handle_out = e;
+    return 0;
+}
+void gsl_engine_destroy(void* handle) { delete (Engine*)handle; }
+int gsl_engine_bind_params(void* handle, const void* const* frozen_ptrs, int num_ptrs, float* lora_flat, float* grad_flat) {
+    return ((Engine*)handle)->bind_params(frozen_ptrs, num_ptrs, lora_flat, grad_flat);
+}
+int gsl_engine_refresh_frozen(void* handle, void* stream) { return ((Engine*)handle)->refresh_frozen(ST(stream)); }
+int gsl_engine_refresh_lora(void* handle, void* stream) { return ((Engine*)handle)->refresh_lora(ST(stream)); }
+int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* labels, int B, int use_lora, void* stream) {
+    return ((Engine*)handle)->forward(slot, img, labels, B, use_lora, ST(stream));
+}
+int gsl_engine_backward(void* handle, int slot, const float* dlogits, const float* demb, int accumulate, void* stream) {
+    return ((Engine*)handle)->backward(slot, dlogits, demb, accumulate, ST(stream));
+}
+void* gsl_engine_slot_ptr(void* handle, int slot, int what) {
+    Engine* e = (Engine*)handle;
+    if (slot < 0 || slot >= (int)e->slots.size()) return nullptr;
+    Slot& s = e->slots[slot];
+    switch (what) {
+        case GSL_SLOT_EMB: return s.emb;
+        case GSL_SLOT_LOGITS: return s.logits;
+        case GSL_SLOT_CE: return s.ce;
+        case GSL_SLOT_CORRECT: return s.correct;
+        case GSL_SLOT_XFINAL: return s.x.back();
+        default: return nullptr;
+    }
+}
+int64_t gsl_engine_lora_offset(void* handle, int block, int which) { return ((Engine*)handle)->lora_offset(block, which); }
+int64_t gsl_engine_lora_numel(void* handle) { Engine* e = (Engine*)handle; return e->cfg.depth * e->lora_block_elems(); }
+int gsl_loss_sums(const float* ce, const int32_t* correct, int n_remain, int B, float* sums, void* stream) {
+    return loss_sums(ce, correct, n_remain, B, sums, ST(stream));
+}
+int gsl_unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C, float beta, float BND,
+                        float* dlogits, void* stream) {
+    return unlearn_ce_grad(logits, labels, sums, n_remain_local, B, C, beta, BND, dlogits, ST(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,431 @@
+// gslora-b200: engine -- orchestrates the sm_100a kernels into ViT_face.forward (vit_face.py:523-548) and the
+// selective backward autograd builds for engine_cl.py:124 (gradients for lora_A / lora_B only; dX flows through
+// the frozen layers from the head down to block 0's FFN, nothing below that has a trainable ancestor).
+//
+// Memory: the caller hands over ONE workspace (a torch uint8 tensor); carve() lays out
+//   fp16 operand caches of the frozen weights  [W | s*B] and transposes [W^T | s*A^T]  (K-extension for LoRA)
+//   `num_slots` activation sets (what the backward needs: residual snapshots, LN stats, q/k/v, O, LSE,
+//    [LN2(x) | T1], pre-GELU H, [G | T2])
+//   transient gradient buffers shared by all slots.
+#include "gsl_engine.h"
+#include "gsl_common.cuh"
+
+namespace gsl {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int64_t Engine::lora_block_elems() const {
+    const int64_t r = cfg.lora_rank, D = cfg.dim, H = cfg.mlp_dim;
+    return r * D + H * r + r * H + D * r;
+}
+int64_t Engine::lora_offset(int block, int which) const {
+    const int64_t r = cfg.lora_rank, D = cfg.dim, H = cfg.mlp_dim;
+    int64_t off = block * lora_block_elems();
+    if (which >= 1) off += r * D;
+    if (which >= 2) off += H * r;
+    if (which >= 3) off += r * H;
+    return off;
+}
+
+// One pass computes sizes (assign = false) or assigns pointers (assign = true); both walk the same sequence.
+size_t Engine::carve(bool assign) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> uint8_t* {
+        off = align_up(off, 1024);
+        uint8_t* p = assign ? ws + off : nullptr;
+        off += bytes;
+        return p;
+    };
+    const int64_t D = cfg.dim, H = cfg.mlp_dim, L = cfg.depth, C = cfg.num_class, Bm = cfg.max_batch;
+    const int64_t inner = (int64_t)cfg.heads * 64;
+    const int64_t M = Bm * tokens;
+    auto* pw = (__half*)take((size_t)D * patch_dim * 2);
+    auto* pb = (float*)take((size_t)tokens * D * 4);
+    if (assign) { patch_w16 = pw; posb = pb; cache.assign(L, BlockCache()); }
+    for (int l = 0; l < L; ++l) {
+        BlockCache c;
+        c.qkv_w16 = (__half*)take((size_t)3 * inner * D * 2);
+        c.qkv_wT16 = (__half*)take((size_t)D * 3 * inner * 2);
+        c.out_w16 = (__half*)take((size_t)D * inner * 2);
+        c.out_wT16 = (__half*)take((size_t)inner * D * 2);
+        c.fc1_cat = (__half*)take((size_t)H * (D + 16) * 2);
+        c.fc1T_cat = (__half*)take((size_t)D * (H + 16) * 2);
+        c.fc2_cat = (__half*)take((size_t)D * (H + 16) * 2);
+        c.fc2T_cat = (__half*)take((size_t)H * (D + 16) * 2);
+        c.A1h = (__half*)take((size_t)16 * D * 2);
+        c.A2h = (__half*)take((size_t)16 * H * 2);
+        c.B1T = (__half*)take((size_t)16 * H * 2);
+        c.B2T = (__half*)take((size_t)16 * D * 2);
+        if (assign) cache[l] = c;
+    }
+    if (assign) slots.assign(cfg.num_slots, Slot());
+    for (int s = 0; s < cfg.num_slots; ++s) {
+        Slot sl;
+        for (int i = 0; i < 2 * L + 1; ++i) sl.x.push_back((float*)take((size_t)M * D * 4));
+        for (int l = 0; l < L; ++l) {
+            BlockActs a;
+            a.ln1_mean = (float*)take((size_t)M * 4); a.ln1_rstd = (float*)take((size_t)M * 4);
+            a.ln2_mean = (float*)take((size_t)M * 4); a.ln2_rstd = (float*)take((size_t)M * 4);
+            a.lse = (float*)take((size_t)Bm * cfg.heads * tokens * 4);
+            a.qkv16 = (__half*)take((size_t)M * 3 * inner * 2);
+            a.o16 = (__half*)take((size_t)M * inner * 2);
+            a.xn2cat16 = (__half*)take((size_t)M * (D + 16) * 2);
+            a.h16 = (__half*)take((size_t)M * H * 2);
+            a.gcat16 = (__half*)take((size_t)M * (H + 16) * 2);
+            sl.blk.push_back(a);
+        }
+        sl.emb = (float*)take((size_t)Bm * D * 4);
+        sl.logits = (float*)take((size_t)Bm * C * 4);
+        sl.ce = (float*)take((size_t)Bm * 4);
+        sl.xhat = (float*)take((size_t)Bm * D * 4);
+        sl.head_rstd = (float*)take((size_t)Bm * 4);
+        sl.correct = (int*)take((size_t)Bm * 4);
+        if (assign) slots[s] = sl;
+    }
+    auto* t_patches = (__half*)take((size_t)M * patch_dim * 2);
+    auto* t_xn = (__half*)take((size_t)M * D * 2);
+    auto* t_dxcat = (__half*)take((size_t)M * (D + 16) * 2);
+    auto* t_dhcat = (__half*)take((size_t)M * (H + 16) * 2);
+    auto* t_do = (__half*)take((size_t)M * inner * 2);
+    auto* t_dqkv = (__half*)take((size_t)M * 3 * inner * 2);
+    auto* t_dx32 = (float*)take((size_t)M * D * 4);
+    auto* t_dxn32 = (float*)take((size_t)M * D * 4);
+    const size_t sk = skinny_tn_workspace(M, (int)(H > D ? H : D), cfg.lora_rank);
+    auto* t_sk = (float*)take(sk);
+    auto* t_go = (int*)take((size_t)(L + 1) * 4);
+    auto* t_to = (int*)take((size_t)(4 * L + 1) * 4);
+    auto* t_gn = (float*)take((size_t)L * 4);
+    auto* t_tn = (float*)take((size_t)4 * L * 4);
+    if (assign) {
+        patches16 = t_patches; xn16 = t_xn; dxcat16 = t_dxcat; dhcat16 = t_dhcat; do16 = t_do; dqkv16 = t_dqkv;
+        dx32 = t_dx32; dxn32 = t_dxn32; skinny_ws = t_sk; skinny_ws_bytes = sk;
+        group_offsets_dev = t_go; tensor_offsets_dev = t_to; group_norms_dev = t_gn; tensor_norms_dev = t_tn;
+    }
+    return align_up(off, 1024);
+}
+
+static int validate(const GslConfig& c) {
+    GSL_REQUIRE(c.image_size % c.patch_size == 0, "image_size %% patch_size != 0");
+    GSL_REQUIRE(c.dim % 128 == 0 && c.dim <= 1024, "dim=%d must be a multiple of 128 and <= 1024", c.dim);
+    GSL_REQUIRE(c.mlp_dim % 64 == 0, "mlp_dim=%d must be a multiple of 64", c.mlp_dim);
+    GSL_REQUIRE(c.heads * 64 == c.dim || c.heads > 0, "bad heads");
+    GSL_REQUIRE(c.lora_rank == 8 || c.lora_rank == 16, "lora_rank=%d: this build supports r in {8, 16}", c.lora_rank);
+    GSL_REQUIRE((c.channels * c.patch_size * c.patch_size) % 16 == 0, "patch_dim must be a multiple of 16");
+    GSL_REQUIRE(c.max_batch >= 1 && c.num_slots >= 1 && c.depth >= 1, "bad max_batch / num_slots / depth");
+    const int tokens = (c.image_size / c.patch_size) * (c.image_size / c.patch_size) + 1;
+    GSL_REQUIRE(tokens <= 208, "tokens=%d > 208 not supported by the attention kernel", tokens);
+    GSL_REQUIRE(c.num_class <= 1024, "num_class=%d > 1024", c.num_class);
+    return 0;
+}
+
+size_t Engine::workspace_bytes(const GslConfig& c) {
+    if (validate(c) != 0) return 0;
+    Engine e;
+    e.cfg = c;
+    e.tokens = (c.image_size / c.patch_size) * (c.image_size / c.patch_size) + 1;
+    e.patch_dim = c.channels * c.patch_size * c.patch_size;
+    return e.carve(false);
+}
+
+int Engine::init(const GslConfig& c, void* workspace, size_t bytes) {
+    int rc = validate(c);
+    if (rc) return rc;
+    cfg = c;
+    tokens = (c.image_size / c.patch_size) * (c.image_size / c.patch_size) + 1;
+    patch_dim = c.channels * c.patch_size * c.patch_size;
+    M_max = c.max_batch * tokens;
+    const size_t need = carve(false);
+    GSL_REQUIRE(bytes >= need, "workspace too small: %zu < %zu bytes", bytes, need);
+    GSL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
+    ws = (uint8_t*)workspace; ws_bytes = bytes;
+    carve(true);
+    // offsets of groups / tensors in the flat LoRA buffer
+    std::vector<int> go(c.depth + 1), to(4 * c.depth + 1);
+    for (int l = 0; l <= c.depth; ++l) go[l] = (int)(l * lora_block_elems());
+    for (int l = 0; l < c.depth; ++l)
+        for (int w = 0; w < 4; ++w) to[4 * l + w] = (int)lora_offset(l, w);
+    to[4 * c.depth] = (int)(c.depth * lora_block_elems());
+    GSL_CHECK_CUDA(cudaMemcpy(group_offsets_dev, go.data(), go.size() * 4, cudaMemcpyHostToDevice));
+    GSL_CHECK_CUDA(cudaMemcpy(tensor_offsets_dev, to.data(), to.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int Engine::bind_params(const void* const* p, int n, float* lora, float* grads) {
+    GSL_REQUIRE(n == GSL_NUM_GLOBAL_PARAMS + GSL_NUM_BLOCK_PARAMS * cfg.depth, "expected %d parameter pointers, got %d",
+                GSL_NUM_GLOBAL_PARAMS + GSL_NUM_BLOCK_PARAMS * cfg.depth, n);
+    pos_embedding = (const float*)p[0]; cls_token = (const float*)p[1]; patch_w = (const float*)p[2]; patch_b = (const float*)p[3];
+    head_ln_w = (const float*)p[4]; head_ln_b = (const float*)p[5]; loss_w = (const float*)p[6];
+    frozen.assign(cfg.depth, BlockFrozen());
+    for (int l = 0; l < cfg.depth; ++l) {
+        const void* const* q = p + GSL_NUM_GLOBAL_PARAMS + GSL_NUM_BLOCK_PARAMS * l;
+        BlockFrozen& f = frozen[l];
+        f.ln1_w = (const float*)q[0]; f.ln1_b = (const float*)q[1]; f.qkv_w = (const float*)q[2]; f.qkv_b = (const float*)q[3];
+        f.out_w = (const float*)q[4]; f.out_b = (const float*)q[5]; f.ln2_w = (const float*)q[6]; f.ln2_b = (const float*)q[7];
+        f.fc1_w = (const float*)q[8]; f.fc1_b = (const float*)q[9]; f.fc2_w = (const float*)q[10]; f.fc2_b = (const float*)q[11];
+        GSL_REQUIRE(f.ln1_w && f.ln1_b && f.qkv_w && f.out_w && f.out_b && f.ln2_w && f.ln2_b && f.fc1_w && f.fc1_b && f.fc2_w && f.fc2_b,
+                    "null frozen parameter in block %d", l);
+    }
+    GSL_REQUIRE(pos_embedding && cls_token && patch_w && patch_b && head_ln_w && head_ln_b, "null global parameter");
+    GSL_REQUIRE(lora != nullptr, "lora_flat is null");
+    lora_flat = lora; grad_flat = grads;
+    params_bound = true;
+    return 0;
+}
+
+// posb[n, :] = pos[n] + (n == 0 ? cls : patch_bias)   (vit_face.py:531-536 folded into the patch-embed epilogue)
+__global__ void posb_kernel(const float* __restrict__ pos, const float* __restrict__ cls, const float* __restrict__ pbias, float* __restrict__ out,
+                            int tokens, int D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tokens * D) return;
+    const int n = i / D, d = i % D;
+    out[i] = pos[i] + (n == 0 ? cls[d] : pbias[d]);
+}
+
+int Engine::refresh_frozen(cudaStream_t s) {
+    GSL_REQUIRE(params_bound, "bind_params first");
+    const int D = cfg.dim, H = cfg.mlp_dim, inner = cfg.heads * 64;
+    int rc;
+    if ((rc = cast_f32_to_f16(patch_w, patch_dim, patch_w16, patch_dim, D, patch_dim, 1.f, 0, s))) return rc;
+    posb_kernel<<<(tokens * D + 255) / 256, 256, 0, s>>>(pos_embedding, cls_token, patch_b, posb, tokens, D);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    for (int l = 0; l < cfg.depth; ++l) {
+        const BlockFrozen& f = frozen[l];
+        BlockCache& c = cache[l];
+        if ((rc = cast_f32_to_f16(f.qkv_w, D, c.qkv_w16, D, 3 * inner, D, 1.f, 0, s))) return rc;
+        if ((rc = cast_f32_to_f16(f.qkv_w, D, c.qkv_wT16, 3 * inner, 3 * inner, D, 1.f, 1, s))) return rc;
+        if ((rc = cast_f32_to_f16(f.out_w, inner, c.out_w16, inner, D, inner, 1.f, 0, s))) return rc;
+        if ((rc = cast_f32_to_f16(f.out_w, inner, c.out_wT16, D, D, inner, 1.f, 1, s))) return rc;
+        if ((rc = fill_zero(c.fc1_cat, (size_t)H * (D + 16) * 2, s))) return rc;
+        if ((rc = fill_zero(c.fc1T_cat, (size_t)D * (H + 16) * 2, s))) return rc;
+        if ((rc = fill_zero(c.fc2_cat, (size_t)D * (H + 16) * 2, s))) return rc;
+        if ((rc = fill_zero(c.fc2T_cat, (size_t)H * (D + 16) * 2, s))) return rc;
+        if ((rc = cast_f32_to_f16(f.fc1_w, D, c.fc1_cat, D + 16, H, D, 1.f, 0, s))) return rc;
+        if ((rc = cast_f32_to_f16(f.fc1_w, D, c.fc1T_cat, H + 16, H, D, 1.f, 1, s))) return rc;
+        if ((rc = cast_f32_to_f16(f.fc2_w, H, c.fc2_cat, H + 16, D, H, 1.f, 0, s))) return rc;
+        if ((rc = cast_f32_to_f16(f.fc2_w, H, c.fc2T_cat, D + 16, D, H, 1.f, 1, s))) return rc;
+    }
+    return refresh_lora(s);
+}
+
+int Engine::refresh_lora(cudaStream_t s) {
+    GSL_REQUIRE(params_bound, "bind_params first");
+    const int D = cfg.dim, H = cfg.mlp_dim, r = cfg.lora_rank;
+    const float sc = cfg.lora_scaling;
+    int rc;
+    for (int l = 0; l < cfg.depth; ++l) {
+        BlockCache& c = cache[l];
+        const float* A1 = lora_flat + lora_offset(l, 0);   // [r, D]
+        const float* B1 = lora_flat + lora_offset(l, 1);   // [H, r]
+        const float* A2 = lora_flat + lora_offset(l, 2);   // [r, H]
+        const float* B2 = lora_flat + lora_offset(l, 3);   // [D, r]
+        if (r < 16) {
+            if ((rc = fill_zero(c.A1h, (size_t)16 * D * 2, s))) return rc;
+            if ((rc = fill_zero(c.A2h, (size_t)16 * H * 2, s))) return rc;
+            if ((rc = fill_zero(c.B1T, (size_t)16 * H * 2, s))) return rc;
+            if ((rc = fill_zero(c.B2T, (size_t)16 * D * 2, s))) return rc;
+        }
+        if ((rc = cast_f32_to_f16(A1, D, c.A1h, D, r, D, 1.f, 0, s))) return rc;
+        if ((rc = cast_f32_to_f16(A2, H, c.A2h, H, r, H, 1.f, 0, s))) return rc;
+        if ((rc = cast_f32_to_f16(B1, r, c.B1T, H, H, r, 1.f, 1, s))) return rc;
+        if ((rc = cast_f32_to_f16(B2, r, c.B2T, D, D, r, 1.f, 1, s))) return rc;
+        // K-extension columns of the concatenated operands (columns [r, 16) stay zero from refresh_frozen)
+        if ((rc = cast_f32_to_f16(B1, r, c.fc1_cat + D, D + 16, H, r, sc, 0, s))) return rc;       // s*B1   -> fc1_cat[:, D:D+r]
+        if ((rc = cast_f32_to_f16(B2, r, c.fc2_cat + H, H + 16, D, r, sc, 0, s))) return rc;       // s*B2   -> fc2_cat[:, H:H+r]
+        if ((rc = cast_f32_to_f16(A1, D, c.fc1T_cat + H, H + 16, r, D, sc, 1, s))) return rc;      // s*A1^T -> fc1T_cat[:, H:H+r]
+        if ((rc = cast_f32_to_f16(A2, H, c.fc2T_cat + D, D + 16, r, H, sc, 1, s))) return rc;      // s*A2^T -> fc2T_cat[:, D:D+r]
+    }
+    return 0;
+}
+
+int Engine::forward(int slot, const float* img, const int64_t* labels, int B, int use_lora, cudaStream_t s) {
+    GSL_REQUIRE(params_bound, "bind_params first");
+    GSL_REQUIRE(slot >= 0 && slot < cfg.num_slots, "slot %d out of range", slot);
+    GSL_REQUIRE(B >= 1 && B <= cfg.max_batch, "batch %d outside [1, %d]", B, cfg.max_batch);
+    const int D = cfg.dim, H = cfg.mlp_dim, L = cfg.depth, inner = cfg.heads * 64, r = cfg.lora_rank;
+    const int64_t M = (int64_t)B * tokens;
+    const int kx = use_lora ? 16 : 0;
+    Slot& S = slots[slot];
+    S.batch = B; S.used_lora = use_lora;
+    int rc;
+    if ((rc = patchify_f16(img, patches16, patch_dim, B, cfg.channels, cfg.image_size, cfg.patch_size, cfg.patch_order, s))) return rc;
+    {   // patch_to_embedding + cls token + pos_embedding (vit_face.py:531-536)
+        GemmArgs g;
+        g.A = patches16; g.lda = patch_dim; g.B = patch_w16; g.ldb = patch_dim; g.M = M; g.N = D; g.K = patch_dim;
+        g.epi = EPI_PERIODIC_F32; g.out0 = S.x[0]; g.ld0 = D; g.aux = posb; g.ldaux = D; g.aux_period = tokens;
+        if ((rc = gemm_f16(g, s))) return rc;
+    }
+    for (int l = 0; l < L; ++l) {
+        const BlockFrozen& f = frozen[l];
+        const BlockCache& c = cache[l];
+        BlockActs& a = S.blk[l];
+        float* x_in = S.x[2 * l];
+        float* x_mid = S.x[2 * l + 1];
+        float* x_out = S.x[2 * l + 2];
+        // ---- x = Attention(LN(x)) + x
+        if ((rc = layernorm_fwd(x_in, D, f.ln1_w, f.ln1_b, cfg.ln_eps, xn16, D, a.ln1_mean, a.ln1_rstd, M, D, s))) return rc;
+        {
+            GemmArgs g;
+            g.A = xn16; g.lda = D; g.B = c.qkv_w16; g.ldb = D; g.M = M; g.N = 3 * inner; g.K = D;
+            g.epi = EPI_F16; g.bias = f.qkv_b; g.out0 = a.qkv16; g.ld0 = 3 * inner;
+            if ((rc = gemm_f16(g, s))) return rc;
+        }
+        if ((rc = attention_fwd(a.qkv16, 3 * inner, a.o16, inner, a.lse, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
+        {
+            GemmArgs g;
+            g.A = a.o16; g.lda = inner; g.B = c.out_w16; g.ldb = inner; g.M = M; g.N = D; g.K = inner;
+            g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = x_mid; g.ld0 = D; g.aux = x_in; g.ldaux = D;
+            if ((rc = gemm_f16(g, s))) return rc;
+        }
+        // ---- x = FeedForward(LN(x)) + x, loralib.Linear on both projections
+        if ((rc = layernorm_fwd(x_mid, D, f.ln2_w, f.ln2_b, cfg.ln_eps, a.xn2cat16, D + 16, a.ln2_mean, a.ln2_rstd, M, D, s))) return rc;
+        if (use_lora && (rc = lora_down(a.xn2cat16, D + 16, c.A1h, D, a.xn2cat16 + D, D + 16, M, D, r, s))) return rc;      // T1
+        {
+            GemmArgs g;
+            g.A = a.xn2cat16; g.lda = D + 16; g.B = c.fc1_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + kx;
+            g.epi = EPI_GELU; g.bias = f.fc1_b; g.out0 = a.h16; g.ld0 = H; g.out1 = a.gcat16; g.ld1 = H + 16;
+            if ((rc = gemm_f16(g, s))) return rc;
+        }
+        if (use_lora && (rc = lora_down(a.gcat16, H + 16, c.A2h, H, a.gcat16 + H, H + 16, M, H, r, s))) return rc;          // T2
+        {
+            GemmArgs g;
+            g.A = a.gcat16; g.lda = H + 16; g.B = c.fc2_cat; g.ldb = H + 16; g.M = M; g.N = D; g.K = H + kx;
+            g.epi = EPI_RES_F32; g.bias = f.fc2_b; g.out0 = x_out; g.ld0 = D; g.aux = x_mid; g.ldaux = D;
+            if ((rc = gemm_f16(g, s))) return rc;
+        }
+    }
+    HeadArgs h;
+    h.x = S.x[2 * L]; h.ldx = D; h.tokens = tokens; h.gamma = head_ln_w; h.beta = head_ln_b; h.eps = cfg.ln_eps;
+    h.W = labels ? loss_w : nullptr; h.labels = labels; h.cos_s = cfg.cos_s; h.cos_m = cfg.cos_m; h.B = B; h.D = D; h.C = cfg.num_class;
+    h.emb = S.emb; h.logits = S.logits; h.ce = S.ce; h.correct = S.correct; h.xhat = S.xhat; h.rstd = S.head_rstd;
+    if (labels) GSL_REQUIRE(loss_w != nullptr, "labelled forward needs loss.weight");
+    return head_fwd(h, s);
+}
+
+int Engine::backward(int slot, const float* dlogits, const float* demb, int accumulate, cudaStream_t s) {
+    GSL_REQUIRE(params_bound && grad_flat != nullptr, "bind_params (with a gradient buffer) first");
+    GSL_REQUIRE(slot >= 0 && slot < cfg.num_slots, "slot %d out of range", slot);
+    Slot& S = slots[slot];
+    GSL_REQUIRE(S.batch > 0, "slot %d holds no forward", slot);
+    GSL_REQUIRE(S.used_lora, "backward needs a forward run with use_lora = 1 (train mode, unmerged)");
+    GSL_REQUIRE(dlogits || demb, "backward needs d logits and/or d emb");
+    const int B = S.batch, D = cfg.dim, H = cfg.mlp_dim, L = cfg.depth, inner = cfg.heads * 64, r = cfg.lora_rank;
+    const int64_t M = (int64_t)B * tokens;
+    const float gs = cfg.grad_scale;
+    const float wscale = cfg.lora_scaling / gs;     // dA, dB carry the LoRA scaling and undo the loss scale
+    int rc;
+    // gradient wrt the final residual stream: zero except the cls rows
+    if ((rc = fill_zero(dx32, (size_t)M * D * 4, s))) return rc;
+    if ((rc = fill_zero(dxcat16, (size_t)M * (D + 16) * 2, s))) return rc;
+    HeadBwdArgs hb;
+    hb.dlogits = dlogits; hb.demb = demb; hb.emb = S.emb; hb.W = loss_w; hb.labels = nullptr; hb.xhat = S.xhat; hb.rstd = S.head_rstd;
+    hb.gamma = head_ln_w; hb.cos_s = cfg.cos_s; hb.B = B; hb.D = D; hb.C = cfg.num_class; hb.tokens = tokens; hb.gscale = gs;
+    hb.dx = dx32; hb.lddx = D; hb.dx16 = dxcat16; hb.lddx16 = D + 16;
+    if ((rc = head_bwd(hb, s))) return rc;
+
+    for (int l = L - 1; l >= 0; --l) {
+        const BlockFrozen& f = frozen[l];
+        const BlockCache& c = cache[l];
+        BlockActs& a = S.blk[l];
+        float* gA1 = grad_flat + lora_offset(l, 0);
+        float* gB1 = grad_flat + lora_offset(l, 1);
+        float* gA2 = grad_flat + lora_offset(l, 2);
+        float* gB2 = grad_flat + lora_offset(l, 3);
+        // ---------------- FFN: y = fc2(gelu(fc1(LN2(x)))) + x   (SURVEY Appendix C closed forms)
+        if ((rc = lora_down(dxcat16, D + 16, c.B2T, D, dxcat16 + D, D + 16, M, D, r, s))) return rc;                         // U2 = dY2 B2
+        if ((rc = skinny_tn(dxcat16, D + 16, a.gcat16 + H, H + 16, gB2, r, 0, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // dB2 = s dY2^T T2
+        if ((rc = skinny_tn(a.gcat16, H + 16, dxcat16 + D, D + 16, gA2, H, 1, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // dA2 = s U2^T G
+        {   // dH = (dY2 W2 + s U2 A2) * gelu'(H)
+            GemmArgs g;
+            g.A = dxcat16; g.lda = D + 16; g.B = c.fc2T_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + 16;
+            g.epi = EPI_GELU_BWD; g.out0 = dhcat16; g.ld0 = H + 16; g.aux = a.h16; g.ldaux = H;
+            if ((rc = gemm_f16(g, s))) return rc;
+        }
+        if ((rc = lora_down(dhcat16, H + 16, c.B1T, H, dhcat16 + H, H + 16, M, H, r, s))) return rc;                         // U1 = dH B1
+        if ((rc = skinny_tn(dhcat16, H + 16, a.xn2cat16 + D, D + 16, gB1, r, 0, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc; // dB1 = s dH^T T1
+        if ((rc = skinny_tn(a.xn2cat16, D + 16, dhcat16 + H, H + 16, gA1, D, 1, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc; // dA1 = s U1^T LN2(x)
+        if (l == 0) break;      // nothing trainable below block 0's FFN
+        {   // dLN2 = dH W1 + s U1 A1
+            GemmArgs g;
+            g.A = dhcat16; g.lda = H + 16; g.B = c.fc1T_cat; g.ldb = H + 16; g.M = M; g.N = D; g.K = H + 16;
+            g.epi = EPI_F32; g.out0 = dxn32; g.ld0 = D;
+            if ((rc = gemm_f16(g, s))) return rc;
+        }
+        if ((rc = layernorm_bwd(dxn32, D, S.x[2 * l + 1], D, a.ln2_mean, a.ln2_rstd, f.ln2_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, s))) return rc;
+        // ---------------- attention: y = to_out(attn(to_qkv(LN1(x)))) + x
+        {   // dO = dY Wo
+            GemmArgs g;
+            g.A = dxcat16; g.lda = D + 16; g.B = c.out_wT16; g.ldb = D; g.M = M; g.N = inner; g.K = D;
+            g.epi = EPI_F16; g.out0 = do16; g.ld0 = inner;
+            if ((rc = gemm_f16(g, s))) return rc;
+        }
+        if ((rc = attention_bwd(a.qkv16, 3 * inner, a.o16, inner, do16, inner, a.lse, dqkv16, 3 * inner, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
+        {   // dLN1 = dQKV Wqkv
+            GemmArgs g;
+            g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
+            g.epi = EPI_F32; g.out0 = dxn32; g.ld0 = D;
+            if ((rc = gemm_f16(g, s))) return rc;
+        }
+        if ((rc = layernorm_bwd(dxn32, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, s))) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ step-loss helpers
+__global__ void loss_sums_kernel(const float* __restrict__ ce, const int* __restrict__ correct, int n_remain, int B, float* __restrict__ sums) {
+    __shared__ float red[6][32];
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        if (b < n_remain) { v[0] += ce[b]; v[1] += 1.f; v[4] += correct ? (float)correct[b] : 0.f; }
+        else { v[2] += ce[b]; v[3] += 1.f; v[5] += correct ? (float)correct[b] : 0.f; }
+    }
+    for (int k = 0; k < 6; ++k) {
+        v[k] = warp_sum(v[k]);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[threadIdx.x][i];
+        sums[threadIdx.x] = t;
+    }
+}
+
+int loss_sums(const float* ce, const int* correct, int n_remain, int B, float* sums, cudaStream_t s) {
+    loss_sums_kernel<<<1, 1024, 0, s>>>(ce, correct, n_remain, B, sums);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// loss = CE_r + beta * relu(BND - CE_f)  (engine_cl.py:65-80,118-120): d/dlogits per sample
+__global__ void unlearn_ce_grad_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const float* __restrict__ sums,
+                                       int n_remain_local, int B, int C, float beta, float BND, float* __restrict__ dlogits) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float w;
+    if (b < n_remain_local) w = sums[1] > 0.f ? 1.0f / sums[1] : 0.f;
+    else {
+        const float mean_f = sums[3] > 0.f ? sums[2] / sums[3] : 0.f;
+        w = (sums[3] > 0.f && mean_f < BND) ? -beta / sums[3] : 0.f;      // relu'(BND - CE_f) = [CE_f < BND]
+    }
+    const float* lr = logits + (int64_t)b * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lr[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += __expf(lr[c] - mx);
+    se = warp_sum(se);
+    const float inv = 1.0f / se;
+    const int label = (int)labels[b];
+    for (int c = lane; c < C; c += 32) dlogits[(int64_t)b * C + c] = w * (__expf(lr[c] - mx) * inv - (c == label ? 1.f : 0.f));
+}
+
+int unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C, float beta, float BND,
+                    float* dlogits, cudaStream_t s) {
+    const int warps = 4;
+    unlearn_ce_grad_kernel<<<(B + warps - 1) / warps, warps * 32, 0, s>>>(logits, labels, sums, n_remain_local, B, C, beta, BND, dlogits);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gsl

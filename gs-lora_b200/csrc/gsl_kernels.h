@@ -37,20 +37,20 @@ int device_sm_count();
 // img [B,C,S,S] fp32 NCHW -> patches fp16 [B*(P+1), ld] with a zero row at token 0 of every image;
 // order 0: (p1 p2 c) channel fastest (vit_face.py:530); order 1: (c p1 p2) (torchvision conv_proj)
 int patchify_f16(const float* img, __half* out, int64_t ld, int B, int C, int S, int patch, int order, cudaStream_t s);
-// y = LN(x) * gamma + beta -> fp16 [M, ldy] ; saves mean/rstd ; optionally T = y * A^T (r <= 16) into y[:, D:D+16]
+// y = LN(x) * gamma + beta -> fp16 [M, ldy] ; saves mean/rstd
 int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, __half* y, int64_t ldy,
-                  float* mean, float* rstd, const __half* loraA, int r, int64_t M, int D, cudaStream_t s);
+                  float* mean, float* rstd, int64_t M, int D, cudaStream_t s);
 // dx = dres + LNbwd(dy) ; writes fp32 dx and an fp16 copy (GEMM operand for the next dX GEMM)
 int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                   const float* gamma, const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16,
                   int64_t M, int D, cudaStream_t s);
 // T[M, 0:16] = X[M, K] * A16[16, K]^T  (fp16 in, fp32 accumulate, fp16 out at out[:, 0:16], row pitch ldo)
-int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __half* out, int64_t ldo, int64_t M, int K, cudaStream_t s);
+int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __half* out, int64_t ldo, int64_t M, int K, int r, cudaStream_t s);
 // dW[R, 16-ish] style skinny reductions over M (split-M partials + deterministic second pass):
 //   out[n, j] = scale * sum_m  L[m, n] * Rm[m, j]   n < N, j < r    (L fp16 [M, ldl], Rm fp16 [M, ldr])
-//   optional elementwise GELU applied to L on load (dA2 = s * U2^T * gelu(H))
+//   accumulate != 0 adds into `out` (second data stream / gradient accumulation)
 int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float* out, int64_t ldo, int transpose_out,
-              float scale, int64_t M, int N, int r, int gelu_on_load, float* workspace, size_t workspace_bytes, cudaStream_t s);
+              float scale, int accumulate, int64_t M, int N, int r, float* workspace, size_t workspace_bytes, cudaStream_t s);
 size_t skinny_tn_workspace(int64_t M, int N, int r);
 // fp32 -> fp16 casts with optional scale / transpose / column placement (weight cache building, LoRA operand packing)
 int cast_f32_to_f16(const float* src, int64_t lds, __half* dst, int64_t ldd, int64_t rows, int64_t cols, float scale,
@@ -92,6 +92,9 @@ struct HeadBwdArgs {
 int head_bwd(const HeadBwdArgs& a, cudaStream_t s);
 // dlogits[b, :] = coef * (softmax(logits[b]) - onehot) / B_total ; coef read from device (gate applied by caller)
 int ce_grad(const float* logits, const int64_t* labels, const float* coef_dev, float scale, float* dlogits, int B, int C, cudaStream_t s);
+int loss_sums(const float* ce, const int* correct, int n_remain, int B, float* sums, cudaStream_t s);
+int unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C, float beta, float BND,
+                    float* dlogits, cudaStream_t s);
 
 // ---- optimizer (gsl_optim.cu)
 struct OptimArgs {

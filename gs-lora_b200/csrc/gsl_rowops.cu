@@ -1,0 +1,392 @@
+// gslora-b200: HBM-bound row kernels around the GEMMs -- patchify, LayerNorm forward/backward,
+// the skinny LoRA contractions (T = X A^T, U = dY B, dA/dB reductions over the token dimension),
+// and the fp32->fp16 weight-cache casts.  All are sized by bytes moved, not FLOPs: 16-byte vector
+// loads, one warp per row (or per 16 rows for the mma-based skinny products), fp32 arithmetic.
+#include "gsl_common.cuh"
+#include "gsl_kernels.h"
+
+namespace gsl {
+
+// ------------------------------------------------------------------------------------------------ patchify
+// Reference: einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (vit_pytorch_face/vit_face.py:530) and, for the
+// torchvision family, conv_proj's implicit (c p1 p2) patch vector.  Token 0 (cls slot) is a zero row so that the
+// patch-embedding GEMM's rows line up 1:1 with the [B, tokens, D] residual stream.
+__global__ void patchify_kernel(const float* __restrict__ img, __half* __restrict__ out, int64_t ld, int B, int C, int S,
+                                int patch, int order) {
+    const int w = S / patch;
+    const int P = w * w;
+    const int64_t total = (int64_t)B * C * S * S;
+    const int pd = C * patch * patch;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % S);
+        const int y = (int)((i / S) % S);
+        const int c = (int)((i / ((int64_t)S * S)) % C);
+        const int b = (int)(i / ((int64_t)S * S * C));
+        const int ph = y / patch, p1 = y % patch, pw = x / patch, p2 = x % patch;
+        const int tok = 1 + ph * w + pw;
+        const int e = order == 0 ? (p1 * patch + p2) * C + c : (c * patch + p1) * patch + p2;
+        out[((int64_t)b * (P + 1) + tok) * ld + e] = __float2half_rn(img[i]);
+    }
+    // zero the cls-slot rows
+    const int64_t ztotal = (int64_t)B * pd;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ztotal; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / pd), e = (int)(i % pd);
+        out[(int64_t)b * (P + 1) * ld + e] = __float2half_rn(0.f);
+    }
+}
+
+int patchify_f16(const float* img, __half* out, int64_t ld, int B, int C, int S, int patch, int order, cudaStream_t s) {
+    GSL_REQUIRE(S % patch == 0, "image size %d not divisible by patch %d", S, patch);
+    const int64_t total = (int64_t)B * C * S * S;
+    const int threads = 256;
+    int blocks = (int)((total + threads - 1) / threads);
+    const int cap = device_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    patchify_kernel<<<blocks, threads, 0, s>>>(img, out, ld, B, C, S, patch, order);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm forward
+// nn.LayerNorm(dim) of PreNorm (vit_face.py:316-323): y = (x - mean) * rstd * gamma + beta, biased variance.
+// One warp per row, VEC float4 per lane (D = 128 * VEC); writes fp16 (the next GEMM's A operand) + row stats.
+template <int VEC>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, __half* __restrict__ y,
+                                                            int64_t ldy, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int64_t M) {
+    constexpr int D = VEC * 128;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+    float4 v[VEC];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        v[i] = xr[lane + 32 * i];
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(sum) * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+    uint2* yr = reinterpret_cast<uint2*>(y + row * ldy);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+        uint2 o;
+        o.x = pack_half2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+        o.y = pack_half2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+        yr[lane + 32 * i] = o;
+    }
+}
+
+int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, __half* y, int64_t ldy,
+                  float* mean, float* rstd, int64_t M, int D, cudaStream_t s) {
+    GSL_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
+    GSL_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "layernorm: leading dimensions must be multiples of 4");
+    const int warps = 8;
+    const int blocks = (int)((M + warps - 1) / warps);
+#define GSL_LN_CASE(V) case V: layernorm_fwd_kernel<V><<<blocks, warps * 32, 0, s>>>(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M); break;
+    switch (D / 128) {
+        GSL_LN_CASE(1) GSL_LN_CASE(2) GSL_LN_CASE(3) GSL_LN_CASE(4) GSL_LN_CASE(5) GSL_LN_CASE(6) GSL_LN_CASE(7) GSL_LN_CASE(8)
+    }
+#undef GSL_LN_CASE
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm backward
+// dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd.
+// (autograd's native_layer_norm_backward for the frozen-affine case: gamma/beta get no gradient because
+//  lora.mark_only_lora_as_trainable froze them, train_own_forget_cl.py:316.)
+// Emits the fp32 gradient stream and its fp16 copy (A operand of the next dX GEMM).
+template <int VEC>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
+                                                            const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                            const float* __restrict__ gamma, const float* __restrict__ dres, int64_t lddres,
+                                                            float* __restrict__ dx, int64_t lddx, __half* __restrict__ dx16, int64_t lddx16,
+                                                            int64_t M) {
+    constexpr int D = VEC * 128;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+    const float4* dyr = reinterpret_cast<const float4*>(dy + row * lddy);
+    float4 xh[VEC], g[VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float4 xv = xr[lane + 32 * i];
+        const float4 dv = dyr[lane + 32 * i];
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+    }
+    const float mg = warp_sum(s1) * (1.0f / D);
+    const float mgx = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        float4 o;
+        o.x = rstd * (g[i].x - mg - xh[i].x * mgx);
+        o.y = rstd * (g[i].y - mg - xh[i].y * mgx);
+        o.z = rstd * (g[i].z - mg - xh[i].z * mgx);
+        o.w = rstd * (g[i].w - mg - xh[i].w * mgx);
+        if (dres) {
+            const float4 r = reinterpret_cast<const float4*>(dres + row * lddres)[lane + 32 * i];
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (dx) reinterpret_cast<float4*>(dx + row * lddx)[lane + 32 * i] = o;
+        if (dx16) {
+            uint2 h;
+            h.x = pack_half2(o.x, o.y);
+            h.y = pack_half2(o.z, o.w);
+            reinterpret_cast<uint2*>(dx16 + row * lddx16)[lane + 32 * i] = h;
+        }
+    }
+}
+
+int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+                  const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16, int64_t M, int D,
+                  cudaStream_t s) {
+    GSL_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm_bwd: D=%d must be a multiple of 128 and <= 1024", D);
+    const int warps = 8;
+    const int blocks = (int)((M + warps - 1) / warps);
+#define GSL_LN_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M); break;
+    switch (D / 128) {
+        GSL_LN_CASE(1) GSL_LN_CASE(2) GSL_LN_CASE(3) GSL_LN_CASE(4) GSL_LN_CASE(5) GSL_LN_CASE(6) GSL_LN_CASE(7) GSL_LN_CASE(8)
+    }
+#undef GSL_LN_CASE
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ skinny X * A^T
+// T[m, j] = sum_k X[m, k] * A[j, k],  j < 16  -- the rank-r projections of loralib.Linear:
+//   forward  T = x A^T  (loralib Linear.forward),   backward  U = dY B  (A := B^T).
+// mma.sync m16n8k16 with a K permutation chosen so that every lane's operand loads are contiguous
+// 16-byte vectors straight from global memory (no smem): within a 64-wide k chunk lane (g = lane/4,
+// t = lane%4) owns k in [16t, 16t+16) of rows g and g+8; mma step s consumes its halves [4s, 4s+4).
+// One warp = 16 rows; HBM-bound (reads X once).
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int NT>   // NT n-tiles of 8 (r = 8 -> 1, r = 16 -> 2)
+__global__ void __launch_bounds__(128) lora_down_kernel(const __half* __restrict__ X, int64_t ldx, const __half* __restrict__ A, int64_t lda,
+                                                        __half* __restrict__ out, int64_t ldo, int64_t M, int K) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t row_base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 16;
+    if (row_base >= M) return;
+    const int64_t r0 = row_base + g, r1 = row_base + g + 8;
+    const bool ok0 = r0 < M, ok1 = r1 < M;
+    const __half* x0 = X + (ok0 ? r0 : row_base) * ldx + 16 * t;
+    const __half* x1 = X + (ok1 ? r1 : row_base) * ldx + 16 * t;
+    float acc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    const int nchunks = K / 64;
+#pragma unroll 2
+    for (int c = 0; c < nchunks; ++c) {
+        const uint4 p0 = *reinterpret_cast<const uint4*>(x0 + c * 64);
+        const uint4 p1 = *reinterpret_cast<const uint4*>(x0 + c * 64 + 8);
+        const uint4 q0 = *reinterpret_cast<const uint4*>(x1 + c * 64);
+        const uint4 q1 = *reinterpret_cast<const uint4*>(x1 + c * 64 + 8);
+        const uint32_t xa[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        const uint32_t xb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const __half* ar = A + (int64_t)(8 * n + g) * lda + c * 64 + 16 * t;
+            const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(ar));
+            const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(ar + 8));
+            const uint32_t wb[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) mma_16816(acc[n], xa[2 * s], xb[2 * s], xa[2 * s + 1], xb[2 * s + 1], wb[2 * s], wb[2 * s + 1]);
+        }
+    }
+    // K tail (K % 64 in {16, 32, 48}): same scheme on 16-wide pieces, lanes t >= pieces contribute zeros
+    const int tail = K - nchunks * 64;
+    if (tail > 0) {
+        const int pieces = tail / 16;
+        uint32_t xa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (t < pieces) {
+            const uint4 p0 = *reinterpret_cast<const uint4*>(x0 + nchunks * 64);
+            const uint4 p1 = *reinterpret_cast<const uint4*>(x0 + nchunks * 64 + 8);
+            const uint4 q0 = *reinterpret_cast<const uint4*>(x1 + nchunks * 64);
+            const uint4 q1 = *reinterpret_cast<const uint4*>(x1 + nchunks * 64 + 8);
+            xa[0] = p0.x; xa[1] = p0.y; xa[2] = p0.z; xa[3] = p0.w; xa[4] = p1.x; xa[5] = p1.y; xa[6] = p1.z; xa[7] = p1.w;
+            xb[0] = q0.x; xb[1] = q0.y; xb[2] = q0.z; xb[3] = q0.w; xb[4] = q1.x; xb[5] = q1.y; xb[6] = q1.z; xb[7] = q1.w;
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            uint32_t wb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (t < pieces) {
+                const __half* ar = A + (int64_t)(8 * n + g) * lda + nchunks * 64 + 16 * t;
+                const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(ar));
+                const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(ar + 8));
+                wb[0] = w0.x; wb[1] = w0.y; wb[2] = w0.z; wb[3] = w0.w; wb[4] = w1.x; wb[5] = w1.y; wb[6] = w1.z; wb[7] = w1.w;
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) mma_16816(acc[n], xa[2 * s], xb[2 * s], xa[2 * s + 1], xb[2 * s + 1], wb[2 * s], wb[2 * s + 1]);
+        }
+    }
+    // c0,c1 -> (row g, cols 2t, 2t+1) ; c2,c3 -> (row g+8, ...) ; columns [8*NT, 16) are zero padding
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+        const uint32_t v0 = n < NT ? pack_half2(acc[n < NT ? n : 0][0], acc[n < NT ? n : 0][1]) : 0u;
+        const uint32_t v1 = n < NT ? pack_half2(acc[n < NT ? n : 0][2], acc[n < NT ? n : 0][3]) : 0u;
+        if (ok0) *reinterpret_cast<uint32_t*>(out + r0 * ldo + 8 * n + 2 * t) = v0;
+        if (ok1) *reinterpret_cast<uint32_t*>(out + r1 * ldo + 8 * n + 2 * t) = v1;
+    }
+}
+
+int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __half* out, int64_t ldo, int64_t M, int K, int r,
+              cudaStream_t s) {
+    GSL_REQUIRE(K % 16 == 0 && ldx % 8 == 0 && lda % 8 == 0 && ldo % 2 == 0, "lora_down: K %% 16, ldx %% 8, lda %% 8 required (K=%d)", K);
+    GSL_REQUIRE(r == 8 || r == 16, "lora_down: rank must be 8 or 16 (got %d)", r);
+    const int warps = 4;
+    const int64_t groups = (M + 15) / 16;
+    const int blocks = (int)((groups + warps - 1) / warps);
+    if (r == 8) lora_down_kernel<1><<<blocks, warps * 32, 0, s>>>(X, ldx, A16, lda, out, ldo, M, K);
+    else lora_down_kernel<2><<<blocks, warps * 32, 0, s>>>(X, ldx, A16, lda, out, ldo, M, K);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ skinny L^T * R over tokens
+// P[n, j] = scale * sum_m L[m, n] * R[m, j]   (n < N, j < r):  dB = s * dY^T T,  dA^T = s * X^T U  (SURVEY Appendix C).
+// Split-M partial sums (each CTA owns a 256-column block and an m-range, lanes walk columns so L is read
+// coalesced; the r-wide R rows are broadcast from shared memory), then a deterministic second pass.
+template <int R>
+__global__ void __launch_bounds__(128) skinny_tn_partial_kernel(const __half* __restrict__ L, int64_t ldl, const __half* __restrict__ Rm, int64_t ldr,
+                                                                float* __restrict__ partial, int64_t M, int N, int rows_per_split) {
+    __shared__ __align__(16) float rs[64][R];
+    const int col = blockIdx.x * 256 + threadIdx.x * 2;
+    const int split = blockIdx.y;
+    const int64_t m0 = (int64_t)split * rows_per_split;
+    const int64_t m1 = (m0 + rows_per_split < M) ? m0 + rows_per_split : M;
+    float acc0[R], acc1[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc0[j] = acc1[j] = 0.f;
+    const bool col_ok = col < N;
+    for (int64_t mb = m0; mb < m1; mb += 64) {
+        const int cnt = (int)((m1 - mb < 64) ? (m1 - mb) : 64);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 64 * R; i += 128) {
+            const int mm = i / R, j = i % R;
+            rs[mm][j] = mm < cnt ? __half2float(Rm[(mb + mm) * ldr + j]) : 0.f;
+        }
+        __syncthreads();
+        if (col_ok) {
+            const __half* lp = L + mb * ldl + col;
+#pragma unroll 8
+            for (int mm = 0; mm < cnt; ++mm) {
+                const float2 l = unpack_half2(*reinterpret_cast<const uint32_t*>(lp + (int64_t)mm * ldl));
+#pragma unroll
+                for (int j = 0; j < R; j += 4) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(&rs[mm][j]);
+                    acc0[j] += l.x * r4.x; acc0[j + 1] += l.x * r4.y; acc0[j + 2] += l.x * r4.z; acc0[j + 3] += l.x * r4.w;
+                    acc1[j] += l.y * r4.x; acc1[j + 1] += l.y * r4.y; acc1[j + 2] += l.y * r4.z; acc1[j + 3] += l.y * r4.w;
+                }
+            }
+        }
+    }
+    if (col_ok) {
+        float* p = partial + ((int64_t)split * N + col) * R;
+#pragma unroll
+        for (int j = 0; j < R; ++j) { p[j] = acc0[j]; p[R + j] = acc1[j]; }
+    }
+}
+
+template <int R>
+__global__ void skinny_tn_reduce_kernel(const float* __restrict__ partial, int splits, int N, float scale, float* __restrict__ out, int64_t ldo,
+                                        int transpose_out, int r_out, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * R) return;
+    const int n = i / R, j = i % R;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * N * R + i];
+    if (j < r_out) {
+        float* o = transpose_out ? out + (int64_t)j * ldo + n : out + (int64_t)n * ldo + j;
+        *o = (accumulate ? *o : 0.f) + s * scale;
+    }
+}
+
+static int skinny_splits(int64_t M, int N) {
+    const int colblocks = (N + 255) / 256;
+    int splits = (device_sm_count() * 4 + colblocks - 1) / colblocks;
+    const int64_t max_splits = (M + 63) / 64;
+    if (splits > max_splits) splits = (int)max_splits;
+    if (splits < 1) splits = 1;
+    return splits;
+}
+
+size_t skinny_tn_workspace(int64_t M, int N, int r) {
+    const int R = r <= 8 ? 8 : 16;
+    return (size_t)skinny_splits(M, N) * N * R * sizeof(float);
+}
+
+int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float* out, int64_t ldo, int transpose_out, float scale,
+              int accumulate, int64_t M, int N, int r, float* workspace, size_t workspace_bytes, cudaStream_t s) {
+    GSL_REQUIRE(r == 8 || r == 16, "skinny_tn: rank must be 8 or 16 (got %d)", r);
+    GSL_REQUIRE(N % 2 == 0 && ldl % 2 == 0, "skinny_tn: N and ldl must be even");
+    GSL_REQUIRE(workspace_bytes >= skinny_tn_workspace(M, N, r), "skinny_tn: workspace too small");
+    const int splits = skinny_splits(M, N);
+    int rows_per_split = (int)((M + splits - 1) / splits);
+    rows_per_split = (rows_per_split + 63) / 64 * 64;
+    dim3 grid((N + 255) / 256, splits);
+    if (r == 8) {
+        skinny_tn_partial_kernel<8><<<grid, 128, 0, s>>>(L, ldl, Rm, ldr, workspace, M, N, rows_per_split);
+        skinny_tn_reduce_kernel<8><<<(N * 8 + 255) / 256, 256, 0, s>>>(workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate);
+    } else {
+        skinny_tn_partial_kernel<16><<<grid, 128, 0, s>>>(L, ldl, Rm, ldr, workspace, M, N, rows_per_split);
+        skinny_tn_reduce_kernel<16><<<(N * 16 + 255) / 256, 256, 0, s>>>(workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate);
+    }
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ casts
+__global__ void cast_kernel(const float* __restrict__ src, int64_t lds, __half* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols,
+                            float scale, int transpose) {
+    const int64_t total = rows * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i % cols;
+        const __half h = __float2half_rn(src[r * lds + c] * scale);
+        if (transpose) dst[c * ldd + r] = h; else dst[r * ldd + c] = h;
+    }
+}
+
+int cast_f32_to_f16(const float* src, int64_t lds, __half* dst, int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose,
+                    cudaStream_t s) {
+    const int64_t total = rows * cols;
+    if (total == 0) return 0;
+    int blocks = (int)((total + 255) / 256);
+    const int cap = device_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    cast_kernel<<<blocks, 256, 0, s>>>(src, lds, dst, ldd, rows, cols, scale, transpose);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fill_zero(void* ptr, size_t bytes, cudaStream_t s) {
+    GSL_CHECK_CUDA(cudaMemsetAsync(ptr, 0, bytes, s));
+    return 0;
+}
+
+}  // namespace gsl

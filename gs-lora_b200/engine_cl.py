@@ -1,0 +1,344 @@
+"""gslora-b200 `engine_cl` -- drop-in for the reference's continual-forgetting inner loop (engine_cl.py of
+bjzhb666/GS-LoRA): `train_one_epoch` (engine_cl.py:12-244), `evaluate` (:247), `eval_data` (:318),
+`get_structure_loss` (:349) and `get_prototype_loss` (:571) with the reference's signatures and return values.
+
+One unlearning step (engine_cl.py:59-125) is executed as ONE fused pass of the native engine:
+  remain and forget batches are concatenated -> one forward -> device-side CE sums and the bounded-forget gate
+  relu(BND - CE_f) -> one selective backward (LoRA gradients only) -> [flat NCCL allreduce of the LoRA gradient
+  buffer under torch.distributed] -> fused group-Lasso + AdamW kernel -> ONE device-to-host copy of the scalars the
+  reference fetches with >= 8 `.item()` calls.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F_t
+
+from gslora import _ffi as F
+
+try:  # logging is host-side orchestration; keep the reference's wandb calls when wandb is importable
+    import wandb
+except Exception:  # pragma: no cover
+    class _NoWandb:
+        @staticmethod
+        def log(*a, **k):
+            return None
+    wandb = _NoWandb()
+
+try:
+    from util.utils import AverageMeter, get_time  # the reference's own helpers when its tree is on sys.path
+except Exception:
+    import datetime
+
+    class AverageMeter:
+        def __init__(self):
+            self.reset()
+
+        def reset(self):
+            self.val = self.avg = self.sum = self.count = 0
+
+        def update(self, val, n=1):
+            self.val = val
+            self.sum += val * n
+            self.count += n
+            self.avg = self.sum / self.count
+
+    def get_time():
+        return (str(datetime.datetime.now())[:-10]).replace(" ", "-").replace(":", "-")
+
+
+def _unwrap(model):
+    return model.module if isinstance(model, (torch.nn.DataParallel, torch.nn.parallel.DistributedDataParallel)) else model
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
+
+
+def _adamw_hparams(optimizer, params):
+    ids = {id(p) for p in params}
+    for g in optimizer.param_groups:
+        if any(id(p) in ids for p in g["params"]):
+            if not isinstance(optimizer, (torch.optim.AdamW,)):
+                raise NotImplementedError("gslora-b200 fused step implements torch.optim.AdamW (what timm create_optimizer builds for the reference)")
+            return dict(lr=g["lr"], wd=g["weight_decay"], betas=tuple(g["betas"]), eps=g["eps"])
+    raise RuntimeError("optimizer does not hold the model's LoRA parameters")
+
+
+def _prototype_tensor(prototype_dict, num_class, dim, device):
+    if torch.is_tensor(prototype_dict):
+        return prototype_dict.to(device)
+    t = torch.zeros(num_class, dim, device=device)
+    for k, v in prototype_dict.items():
+        t[int(k)] = v.to(device)
+    return t
+
+
+def get_prototype_loss(output, labels, prototype_dict, distance="kl"):
+    """engine_cl.get_prototype_loss (engine_cl.py:571-603) without the per-sample `.item()` loop: the prototypes are
+    gathered on device.  (The KL itself is a [B, dim] torch expression; a fused kernel is SURVEY 8f-1.)"""
+    if torch.is_tensor(prototype_dict):
+        pt = prototype_dict[labels.long()].to(output.device)
+    else:
+        table = _prototype_tensor(prototype_dict, max(int(k) for k in prototype_dict) + 1, output.shape[1], output.device)
+        pt = table[labels.long()]
+    if distance == "l2":
+        return torch.mean((output - pt) ** 2)
+    return F_t.kl_div(F_t.log_softmax(output, dim=1), F_t.log_softmax(pt, dim=1), reduction="batchmean", log_target=True)
+
+
+class _StructureLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, *lora_params):
+        eng = model._engine
+        norms = torch.empty(eng.spec.depth, dtype=torch.float32, device=eng.device)
+        F.check(F.lib().gsl_tensor_norms(F.ptr(eng.lora_flat), F.ptr(eng.group_offsets), eng.spec.depth, 0, F.ptr(norms), F.cur_stream()),
+                "gsl_tensor_norms")
+        ctx.model, ctx.norms = model, norms
+        return norms.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        eng = ctx.model._engine
+        inv = torch.where(ctx.norms > 0, 1.0 / ctx.norms, torch.zeros_like(ctx.norms))
+        flat = (eng.lora_flat.view(eng.spec.depth, -1) * inv[:, None] * g).view(-1)
+        out = [eng.lora_view(flat, l, w) for l in range(eng.spec.depth) for w in range(4)]
+        return (None, *out)
+
+
+def get_structure_loss(model: torch.nn.Module, imagenet=False):
+    """engine_cl.get_structure_loss (engine_cl.py:349-432): sum over Transformer blocks of the L2 norm of the block's four
+    LoRA matrices.  Differentiable w.r.t. the LoRA parameters (gradient P / ||g||, 0 at ||g|| = 0 where the reference NaNs)."""
+    m = _unwrap(model)
+    if imagenet:
+        raise NotImplementedError("gslora-b200: the torchvision ViT-B/16 family (config 4) is not built yet")
+    m.ensure_engine(1)
+    m.sync_engine()
+    return _StructureLossFn.apply(m, *m.lora_parameters())
+
+
+def unlearn_step(model, inputs_remain, labels_remain, inputs_forget, labels_forget, *, beta: float, alpha: float, BND: float,
+                 optimizer=None, hparams: Optional[dict] = None, use_prototype: bool = False, prototype_dict=None,
+                 prototype_weight_forget: float = 0.0, prototype_weight_remain: float = 0.0, BND_pro: float = 0.0) -> Dict[str, float]:
+    """One step of engine_cl.train_one_epoch (engine_cl.py:59-125), fused.  Returns the scalars the reference logs."""
+    m = _unwrap(model)
+    Br, Bf = int(inputs_remain.shape[0]), int(inputs_forget.shape[0])
+    B = Br + Bf
+    dev = inputs_remain.device
+    img = torch.cat([inputs_remain.float(), inputs_forget.float()], dim=0).contiguous()
+    lab = torch.cat([labels_remain.to(torch.int64), labels_forget.to(torch.int64)], dim=0).contiguous()
+    eng = m.ensure_engine(B)
+    m.sync_engine()
+    if m._merged():
+        raise RuntimeError("unlearn_step needs model.train() (un-merged LoRA)")
+    slot = m._take_slot()
+    eng.forward(img, lab, slot, use_lora=True)
+    sums = eng.loss_sums(slot, Br, B)
+    dist = _dist()
+    world = 1
+    if dist is not None:
+        world = dist.get_world_size()
+        dist.all_reduce(sums)                                   # global CE sums / counts / hits (<= 8 floats)
+    dlogits = torch.empty(B, eng.spec.num_class, dtype=torch.float32, device=dev)
+    eng.unlearn_ce_grad(slot, lab, Br, B, beta, BND, dlogits)
+    demb = None
+    proto_vals = None
+    if use_prototype:
+        table = _prototype_tensor(prototype_dict, eng.spec.num_class, eng.spec.dim, dev)
+        emb = eng.slot_tensor(slot, F.SLOT_EMB, B).detach().clone().requires_grad_(True)
+        pr = get_prototype_loss(emb[:Br], lab[:Br], table)
+        pf = get_prototype_loss(emb[Br:], lab[Br:], table)
+        proto = prototype_weight_forget * F_t.relu(BND_pro - pf) + prototype_weight_remain * pr      # engine_cl.py:97-101
+        proto.backward()
+        demb = (emb.grad / world).contiguous()
+        proto_vals = torch.stack([pf.detach(), pr.detach()])
+    eng.backward(slot, dlogits, demb, accumulate=False)
+    if dist is not None:
+        dist.all_reduce(eng.grad_flat)                          # the one flat LoRA-gradient allreduce (0.98 MB for ViT-P8S8 r=8)
+    hp = hparams if hparams is not None else _adamw_hparams(optimizer, m.lora_parameters())
+    eng.optimizer_step(lr=hp["lr"], wd=hp["wd"], alpha=alpha, betas=hp.get("betas", (0.9, 0.999)), eps=hp.get("eps", 1e-8))
+    m.mark_lora_updated_by_engine()
+    # one D2H copy for everything the reference reads with .item()
+    pieces = [sums[:6], eng.group_norms.sum().view(1)]
+    if proto_vals is not None:
+        pieces.append(proto_vals)
+    host = torch.cat(pieces).cpu().tolist()
+    s_ce_r, n_r, s_ce_f, n_f, hit_r, hit_f, structure = host[:7]
+    loss_remain = s_ce_r / max(n_r, 1.0)
+    ce_forget = s_ce_f / max(n_f, 1.0)
+    loss_forget = max(BND - ce_forget, 0.0)
+    pf_v, pr_v = (host[7], host[8]) if proto_vals is not None else (0.0, 0.0)
+    proto_total = prototype_weight_forget * max(BND_pro - pf_v, 0.0) + prototype_weight_remain * pr_v if use_prototype else 0.0
+    return dict(loss_remain=loss_remain, ce_forget=ce_forget, loss_forget=loss_forget, structure=structure,
+                top1_remain=100.0 * hit_r / max(n_r, 1.0), top1_forget=100.0 * hit_f / max(n_f, 1.0),
+                proto_forget=pf_v, proto_remain=pr_v,
+                total=beta * loss_forget + loss_remain + alpha * structure + proto_total)
+
+
+def sync_optimizer_state(model, optimizer):
+    """Expose the engine's fused AdamW moments through `optimizer.state` (views, no copies) so state_dict()/resume see them."""
+    m = _unwrap(model)
+    eng = m._engine
+    if eng is None or optimizer is None:
+        return
+    i = 0
+    for l in range(eng.spec.depth):
+        for w, p in zip(range(4), m.lora_parameters()[4 * l:4 * l + 4]):
+            optimizer.state[p] = {"step": torch.tensor(float(eng.opt_step)), "exp_avg": eng.lora_view(eng.exp_avg, l, w),
+                                  "exp_avg_sq": eng.lora_view(eng.exp_avg_sq, l, w)}
+            i += 1
+
+
+class _Prefetcher:
+    """Side-stream H2D prefetch of the forget loader (the reference's util/data_prefetcher.py:10-58 behaviour)."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = iter(loader), device
+        self.stream = torch.cuda.Stream(device=device)
+        self._preload()
+
+    def _preload(self):
+        try:
+            s, t = next(self.loader)
+        except StopIteration:
+            self.s = self.t = None
+            return
+        with torch.cuda.stream(self.stream):
+            self.s, self.t = s.to(self.device, non_blocking=True), t.to(self.device, non_blocking=True)
+
+    def next(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+        s, t = self.s, self.t
+        if s is not None:
+            s.record_stream(torch.cuda.current_stream())
+            t.record_stream(torch.cuda.current_stream())
+        self._preload()
+        return s, t
+
+
+def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criterion, optimizer, epoch, losses_forget, losses_remain,
+                    losses_total, losses_structure, top1_forget, top1_remain, beta, alpha, BND, batch, testloader_forget, testloader_remain,
+                    forget_acc_before, highest_H_mean, cfg, task_i, use_prototype, prototype_dict, prototype_weight_forget,
+                    prototype_weight_remain, losses_prototype_forget, losses_prototype_remain, dataloader_open=None):
+    """Same contract as engine_cl.train_one_epoch (engine_cl.py:12-244); `criterion` must be nn.CrossEntropyLoss (mean)."""
+    model.train()
+    criterion.train()
+    m = _unwrap(model)
+    if engine_fresh_optimizer(m, optimizer):
+        m.ensure_engine(1)
+        m._engine.reset_optimizer()
+    prefetcher = _Prefetcher(dataloader_forget, device)
+    inputs_forget, labels_forget = prefetcher.next()
+    DISP_FREQ, VER_FREQ = 5, 100
+    rank0 = _dist() is None or _dist().get_rank() == 0
+    for inputs_remain, labels_remain in iter(dataloader_remain):
+        inputs_remain = inputs_remain.to(device)
+        labels_remain = labels_remain.to(device)
+        out = unlearn_step(model, inputs_remain, labels_remain, inputs_forget, labels_forget, beta=beta, alpha=alpha, BND=BND,
+                           optimizer=optimizer, use_prototype=use_prototype, prototype_dict=prototype_dict,
+                           prototype_weight_forget=prototype_weight_forget, prototype_weight_remain=prototype_weight_remain,
+                           BND_pro=cfg.get("BND_pro", 0.0) if use_prototype else 0.0)
+        nr, nf = inputs_remain.size(0), inputs_forget.size(0)
+        losses_remain.update(out["loss_remain"], nr)
+        top1_remain.update(out["top1_remain"], nr)
+        losses_forget.update(beta * out["loss_forget"], nf)
+        top1_forget.update(out["top1_forget"], nf)
+        losses_structure.update(alpha * out["structure"], nr)
+        losses_prototype_forget.update(prototype_weight_forget * max(cfg.get("BND_pro", 0.0) - out["proto_forget"], 0.0) if use_prototype else 0.0, nr)
+        losses_prototype_remain.update(out["proto_remain"] * prototype_weight_remain, nr)
+        losses_total.update(out["total"], nr)
+
+        if ((batch + 1) % DISP_FREQ == 0) and batch != 0:
+            if rank0:
+                wandb.log({
+                    "epoch_loss_forget-{}".format(task_i): losses_forget.avg, "epoch_loss_remain-{}".format(task_i): losses_remain.avg,
+                    "epoch_acc_forget-{}".format(task_i): top1_forget.avg, "epoch_acc_remain-{}".format(task_i): top1_remain.avg,
+                    "epoch_loss_total-{}".format(task_i): losses_total.avg, "epoch_loss_structure-{}".format(task_i): losses_structure.avg,
+                    "epoch_loss_prototype_forget-{}".format(task_i): losses_prototype_forget.avg,
+                    "epoch_loss_prototype_remain-{}".format(task_i): losses_prototype_remain.avg})
+                print("Task {} Epoch {} Batch {}\t"
+                      "Training forget Loss {lf.val:.4f} ({lf.avg:.4f})\tTraining remain Loss {lr.val:.4f} ({lr.avg:.4f})\t"
+                      "Training forget prototype Loss {pf.val:.4f}\tTraining remain prototype Loss {pr.val:.4f}\t"
+                      "Training structure Loss {ls.val:.4f} ({ls.avg:.4f})\tTraining total Loss {lt.val:.4f} ({lt.avg:.4f})\t"
+                      "Training forget Prec@1 {tf.val:.3f} ({tf.avg:.3f})\tTraining remain Prec@1 {tr.val:.3f} ({tr.avg:.3f})".format(
+                          task_i, epoch + 1, batch + 1, lf=losses_forget, lr=losses_remain, pf=losses_prototype_forget,
+                          pr=losses_prototype_remain, ls=losses_structure, lt=losses_total, tf=top1_forget, tr=top1_remain))
+            losses_forget, losses_remain, top1_forget, top1_remain = AverageMeter(), AverageMeter(), AverageMeter(), AverageMeter()
+            losses_total, losses_structure = AverageMeter(), AverageMeter()
+            losses_prototype_forget, losses_prototype_remain = AverageMeter(), AverageMeter()
+
+        with torch.no_grad():
+            if ((batch + 1) % VER_FREQ == 0) and batch != 0:
+                highest_H_mean = evaluate(model, testloader_forget=testloader_forget, testloader_remain=testloader_remain, device=device,
+                                          batch=batch, epoch=epoch, task_i=task_i, forget_acc_before=forget_acc_before,
+                                          highest_H_mean=highest_H_mean, cfg=cfg, optimizer=optimizer, testloader_open=dataloader_open)
+                model.train()
+        batch += 1
+        inputs_forget, labels_forget = prefetcher.next()
+        if inputs_forget is None:
+            prefetcher = _Prefetcher(dataloader_forget, device)
+            inputs_forget, labels_forget = prefetcher.next()
+    sync_optimizer_state(model, optimizer)
+    return (batch, highest_H_mean, losses_forget, losses_remain, top1_forget, top1_remain, losses_total, losses_structure,
+            losses_prototype_forget, losses_prototype_remain)
+
+
+def engine_fresh_optimizer(m, optimizer) -> bool:
+    """A new torch optimizer object (the driver re-creates it per task, train_own_forget_cl.py:811-813) resets the fused moments."""
+    key = id(optimizer)
+    if getattr(m, "_gsl_optimizer_id", None) != key:
+        m._gsl_optimizer_id = key
+        return True
+    return False
+
+
+def evaluate(model, testloader_forget, testloader_remain, device, batch, epoch, forget_acc_before, highest_H_mean, cfg, optimizer, task_i,
+             testloader_open=None):
+    """engine_cl.evaluate (engine_cl.py:247-315): eval-mode (merged) accuracies, H-mean, rolling best checkpoint."""
+    model.eval()
+    lr = optimizer.param_groups[0]["lr"]
+    print("current learning rate:{:.7f}".format(lr))
+    print("Perfom evaluation on test set and save checkpoints...")
+    forget_acc = eval_data(model, testloader_forget, device, "forget-{}".format(task_i), batch)
+    remain_acc = eval_data(model, testloader_remain, device, "remain-{}".format(task_i), batch)
+    if testloader_open is not None:
+        eval_data(model, testloader_open, device, "open-{}".format(task_i), batch)
+    forget_drop = forget_acc_before - forget_acc
+    Hmean = 2 * forget_drop * remain_acc / (forget_drop + remain_acc + 1e-8)
+    rank0 = _dist() is None or _dist().get_rank() == 0
+    if Hmean > highest_H_mean:
+        highest_H_mean = Hmean
+        if rank0:
+            path = os.path.join(cfg["WORK_PATH"], "Backbone_{}_Epoch_{}_Batch_{}_Time_{}_checkpoint.pth".format(
+                cfg["BACKBONE_NAME"], epoch + 1, batch + 1, get_time()))
+            torch.save(_unwrap(model).state_dict(), path)     # written in eval mode: `weight` holds the merged LoRA delta, as in the reference
+            if len(os.listdir(cfg["WORK_PATH"])) >= 4:
+                ckpts = sorted((f for f in os.listdir(cfg["WORK_PATH"]) if f.endswith(".pth")),
+                               key=lambda f: os.path.getmtime(os.path.join(cfg["WORK_PATH"], f)))
+                os.remove(os.path.join(cfg["WORK_PATH"], ckpts[0]))
+    return highest_H_mean
+
+
+def eval_data(model, dataloader, device, mode: str, batch: int = 0):
+    """engine_cl.eval_data (engine_cl.py:318-346): top-1 accuracy (0-100) in eval mode; hits are counted by the head kernel."""
+    m = _unwrap(model)
+    hits = torch.zeros((), dtype=torch.int64, device=device)
+    total = 0
+    model.eval()
+    with torch.no_grad():
+        for images, labels in dataloader:
+            images = images.to(device).float().contiguous()
+            labels = labels.to(device).long().contiguous()
+            eng = m.ensure_engine(images.shape[0])
+            m.sync_engine()
+            slot = m._take_slot()
+            B = eng.forward(images, labels, slot, use_lora=not m._merged())
+            hits += eng.slot_tensor(slot, F.SLOT_CORRECT, B).sum()
+            total += labels.size(0)
+    accuracy = 100 * int(hits.item()) / max(total, 1)
+    print("Test {} Accuracy:{:2f}%".format(mode, accuracy))
+    wandb.log({"Test {} Accuracy".format(mode): accuracy})
+    return accuracy

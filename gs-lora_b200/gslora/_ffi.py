@@ -28,6 +28,16 @@ def lib():
     return _LIB
 
 
+class GslConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("image_size", "patch_size", "channels", "dim", "depth", "heads", "mlp_dim", "num_class",
+                                              "lora_rank", "max_batch", "num_slots", "patch_order")] + \
+               [(n, ctypes.c_float) for n in ("attn_scale", "ln_eps", "cos_s", "cos_m", "lora_scaling", "grad_scale")]
+
+
+SLOT_EMB, SLOT_LOGITS, SLOT_CE, SLOT_CORRECT, SLOT_XFINAL = range(5)
+NUM_GLOBAL_PARAMS, NUM_BLOCK_PARAMS = 7, 12
+
+
 def _declare(L):
     L.gsl_last_error.restype = ctypes.c_char_p
     L.gsl_version.restype = c_int
@@ -35,6 +45,51 @@ def _declare(L):
     L.gsl_gemm_f16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p,
                                c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]
     L.gsl_gemm_f16.restype = c_int
+    P = c_void_p
+    sigs = {
+        "gsl_patchify_f16": [P, P, c_int64, c_int, c_int, c_int, c_int, c_int, P],
+        "gsl_layernorm_fwd": [P, c_int64, P, P, c_float, P, c_int64, P, P, c_int64, c_int, P],
+        "gsl_layernorm_bwd": [P, c_int64, P, c_int64, P, P, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int, P],
+        "gsl_lora_down": [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int, c_int, P],
+        "gsl_skinny_tn": [P, c_int64, P, c_int64, P, c_int64, c_int, c_float, c_int, c_int64, c_int, c_int, P, c_size_t, P],
+        "gsl_attention_fwd": [P, c_int64, P, c_int64, P, c_int, c_int, c_int, c_float, P],
+        "gsl_attention_bwd": [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, c_int, c_int, c_float, P],
+        "gsl_cast_f32_to_f16": [P, c_int64, P, c_int64, c_int64, c_int64, c_float, c_int, P],
+        "gsl_grouplasso_adamw_step": [P, P, P, P, P, c_int, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P, P],
+        "gsl_tensor_norms": [P, P, c_int, c_int, P, P],
+        "gsl_engine_create": [ctypes.POINTER(GslConfig), P, c_size_t, ctypes.POINTER(P)],
+        "gsl_engine_bind_params": [P, ctypes.POINTER(P), c_int, P, P],
+        "gsl_engine_refresh_frozen": [P, P],
+        "gsl_engine_refresh_lora": [P, P],
+        "gsl_engine_forward": [P, c_int, P, P, c_int, c_int, P],
+        "gsl_engine_backward": [P, c_int, P, P, c_int, P],
+        "gsl_loss_sums": [P, P, c_int, c_int, P, P],
+        "gsl_unlearn_ce_grad": [P, P, P, c_int, c_int, c_int, c_float, c_float, P, P],
+    }
+    for name, args in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    L.gsl_skinny_tn_workspace.argtypes = [c_int64, c_int, c_int]
+    L.gsl_skinny_tn_workspace.restype = c_size_t
+    L.gsl_engine_workspace_bytes.argtypes = [ctypes.POINTER(GslConfig)]
+    L.gsl_engine_workspace_bytes.restype = c_size_t
+    L.gsl_engine_destroy.argtypes = [P]
+    L.gsl_engine_destroy.restype = None
+    L.gsl_engine_slot_ptr.argtypes = [P, c_int, c_int]
+    L.gsl_engine_slot_ptr.restype = P
+    L.gsl_engine_lora_offset.argtypes = [P, c_int, c_int]
+    L.gsl_engine_lora_offset.restype = c_int64
+    L.gsl_engine_lora_numel.argtypes = [P]
+    L.gsl_engine_lora_numel.restype = c_int64
+
+
+EXPORTS = ["gsl_last_error", "gsl_version", "gsl_set_gemm_cta_group", "gsl_gemm_f16", "gsl_patchify_f16", "gsl_layernorm_fwd",
+           "gsl_layernorm_bwd", "gsl_lora_down", "gsl_skinny_tn_workspace", "gsl_skinny_tn", "gsl_attention_fwd", "gsl_attention_bwd",
+           "gsl_cast_f32_to_f16", "gsl_grouplasso_adamw_step", "gsl_tensor_norms", "gsl_engine_workspace_bytes", "gsl_engine_create",
+           "gsl_engine_destroy", "gsl_engine_bind_params", "gsl_engine_refresh_frozen", "gsl_engine_refresh_lora", "gsl_engine_forward",
+           "gsl_engine_backward", "gsl_engine_slot_ptr", "gsl_engine_lora_offset", "gsl_engine_lora_numel", "gsl_loss_sums",
+           "gsl_unlearn_ce_grad"]
 
 
 def check(rc, what=""):

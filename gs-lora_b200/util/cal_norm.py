@@ -1,0 +1,38 @@
+"""`util.cal_norm.get_norm_of_lora` of the reference (util/cal_norm.py:4-146) for the gslora-b200 model.
+
+Per group the SUM of the per-matrix norms ||P||_F (type 'L2') or ||P||_1 ('L1') -- a different quantity from the
+group-lasso norm sqrt(sum ||P||_F^2) used by the structure loss.  For an engine-backed ViT_face with the block / lora /
+matrix FFN groupings the 4*depth per-tensor norms come from one CUDA kernel (gsl_tensor_norms) and are summed per group."""
+import torch
+
+
+def _ffn_groups(group_num, group_type):
+    a1, b1, a2, b2 = 0, 1, 2, 3
+    if group_type == "block":
+        return [[(i, a1), (i, b1), (i, a2), (i, b2)] for i in range(group_num)]
+    if group_type == "lora":
+        return [[(i, a1), (i, b1)] for i in range(group_num)] + [[(i, a2), (i, b2)] for i in range(group_num)]
+    if group_type == "matrix":
+        return ([[(i, a1)] for i in range(group_num)] + [[(i, b1)] for i in range(group_num)] +
+                [[(i, a2)] for i in range(group_num)] + [[(i, b2)] for i in range(group_num)])
+    raise ValueError("group_type should be block, lora or matrix")
+
+
+_NAMES = ["transformer.layers.{}.1.fn.fn.net.0.lora_A", "transformer.layers.{}.1.fn.fn.net.0.lora_B",
+          "transformer.layers.{}.1.fn.fn.net.3.lora_A", "transformer.layers.{}.1.fn.fn.net.3.lora_B"]
+
+
+def get_norm_of_lora(model, type="L2", group_num=6, group_type: str = "block", group_pos: str = "FFN", imagenet: bool = False):
+    if type not in ("L1", "L2"):
+        raise ValueError("type should be L1 or L2")
+    if group_pos != "FFN" or imagenet:
+        raise NotImplementedError("gslora-b200: get_norm_of_lora is built for the ViT_face FFN groupings (SURVEY.md 8f-2 lists the rest)")
+    groups = _ffn_groups(group_num, group_type)
+    print("\033[31mgroup_layers_names\033[0m\n", [[_NAMES[w].format(i) for i, w in g] for g in groups])
+    with torch.no_grad():
+        eng = getattr(model, "_engine", None)
+        if eng is None and hasattr(model, "ensure_engine"):
+            eng = model.ensure_engine(1)
+        model.sync_engine()
+        per_tensor = eng.tensor_norms(type)          # [4 * depth] on device
+        return [sum(per_tensor[4 * i + w] for i, w in g) for g in groups]

@@ -1,0 +1,288 @@
+"""gslora-b200 `ViT_face` -- the reference's module surface (vit_pytorch_face/vit_face.py:449-548 of bjzhb666/GS-LoRA)
+on top of the native sm_100a engine.
+
+The module tree, constructor keywords, `forward(img, label=None, mask=None)` contract and every `state_dict` key are
+the reference's, so `train/train_own_forget_cl.py` can build, load, freeze, wrap and checkpoint this
+model unchanged.  The sub-modules are *parameter holders*: `ViT_face.forward` hands the whole computation
+(patch-embed -> [LN, QKV, attention, out-proj, LN, fc1+LoRA, GELU, fc2+LoRA] x depth -> LN -> CosFace) to
+libgslora.so, and the backward is the engine's selective backward wired in through one `torch.autograd.Function`
+whose only differentiable leaves are the LoRA matrices.  There is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+import loralib as lora
+from gslora import _ffi as F
+from gslora.engine import EngineSpec, VitEngine
+
+MIN_NUM_PATCHES = 16
+
+
+def _holder_forward(self, *a, **k):
+    raise RuntimeError(f"gslora-b200: {type(self).__name__} is a parameter holder; it is executed by the fused engine via ViT_face.forward")
+
+
+class Residual(nn.Module):
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+    forward = _holder_forward
+
+
+class PreNorm(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+    forward = _holder_forward
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, hidden_dim, dropout=0.0, lora_rank=8):
+        super().__init__()
+        self.net = nn.Sequential(lora.Linear(dim, hidden_dim, r=lora_rank), nn.GELU(), nn.Dropout(dropout),
+                                 lora.Linear(hidden_dim, dim, r=lora_rank), nn.Dropout(dropout))
+    forward = _holder_forward
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0.0, lora_rank=0):
+        super().__init__()
+        inner_dim = dim_head * heads
+        self.heads = heads
+        self.scale = dim ** -0.5          # the reference scales by dim, not dim_head (vit_face.py:346)
+        self.to_qkv = lora.MergedLinear(in_features=dim, out_features=inner_dim * 3, r=lora_rank, enable_lora=[True, True, True], bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout))
+    forward = _holder_forward
+
+
+class Transformer(nn.Module):
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout, lora_rank, up=False, lora_pos: str = "FFN"):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                Residual(PreNorm(dim, Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout,
+                                                lora_rank=(lora_rank if lora_pos == "Attention" else 0)))),
+                Residual(PreNorm(dim, FeedForward(dim, mlp_dim, dropout=dropout, lora_rank=lora_rank if lora_pos == "FFN" else 0))),
+            ]))
+        self.up = up
+        self.depth = depth
+    forward = _holder_forward
+
+
+class CosFace(nn.Module):
+    """s * (cos(theta) - m * onehot)  (vit_face.py:146-208).  Parameter holder: evaluated by the engine's head kernel."""
+
+    def __init__(self, in_features, out_features, device_id, s=64.0, m=0.35):
+        super().__init__()
+        self.in_features, self.out_features, self.device_id, self.s, self.m = in_features, out_features, device_id, s, m
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        nn.init.xavier_uniform_(self.weight)
+    forward = _holder_forward
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(in_features={self.in_features}, out_features={self.out_features}, s={self.s}, m={self.m})"
+
+
+class _EngineFn(torch.autograd.Function):
+    """One autograd node for the whole network: inputs are the LoRA matrices, outputs (logits, emb)."""
+
+    @staticmethod
+    def forward(ctx, model, img, label, *lora_params):
+        eng = model._engine
+        slot = model._take_slot()
+        B = eng.forward(img, label, slot, use_lora=True)
+        ctx.model, ctx.slot, ctx.B, ctx.stamp = model, slot, B, model._slot_stamp[slot]
+        emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
+        if label is None:
+            return emb
+        return eng.slot_tensor(slot, F.SLOT_LOGITS, B).clone(), emb
+
+    @staticmethod
+    def backward(ctx, *grads):
+        model, eng, slot = ctx.model, ctx.model._engine, ctx.slot
+        if model._slot_stamp[slot] != ctx.stamp:
+            raise RuntimeError("gslora-b200: the activations of this forward were overwritten by later forwards; raise "
+                               "GSLORA_SLOTS (activation sets kept alive) or call backward sooner")
+        if len(grads) == 2:
+            dlogits, demb = grads
+        else:
+            dlogits, demb = None, grads[0]
+        dlogits = dlogits.contiguous().float() if dlogits is not None else None
+        demb = demb.contiguous().float() if demb is not None else None
+        eng.backward(slot, dlogits, demb, accumulate=False)
+        out = [eng.lora_view(eng.grad_flat, l, w).clone() for l in range(eng.spec.depth) for w in range(4)]
+        return (None, None, None, *out)
+
+
+class ViT_face(nn.Module):
+    def __init__(self, *, loss_type, GPU_ID, num_class, image_size, patch_size, dim, depth, heads, mlp_dim, pool="cls", channels=3,
+                 dim_head=64, dropout=0.0, emb_dropout=0.0, lora_rank=8, lora_pos: str = "FFN"):
+        super().__init__()
+        assert image_size % patch_size == 0, "Image dimensions must be divisible by the patch size."
+        num_patches = (image_size // patch_size) ** 2
+        patch_dim = channels * patch_size ** 2
+        assert num_patches > MIN_NUM_PATCHES, f"your number of patches ({num_patches}) is way too small for attention to be effective (at least 16). Try decreasing your patch size"
+        assert pool in {"cls", "mean"}, "pool type must be either cls (cls token) or mean (mean pooling)"
+        if pool != "cls" or lora_pos != "FFN" or dim_head != 64 or heads * dim_head != dim:
+            raise NotImplementedError("gslora-b200 builds the GS-LoRA configuration: pool='cls', lora_pos='FFN', dim_head=64, heads*64 == dim")
+        self.patch_size, self.image_size, self.channels = patch_size, image_size, channels
+        self.dim, self.depth, self.heads, self.mlp_dim, self.num_class, self.lora_rank = dim, depth, heads, mlp_dim, num_class, lora_rank
+        self.dropout_p, self.emb_dropout_p = float(dropout), float(emb_dropout)
+
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, dim))
+        self.patch_to_embedding = nn.Linear(patch_dim, dim)
+        self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.dropout = nn.Dropout(emb_dropout)
+        self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout, lora_rank, lora_pos=lora_pos)
+        self.pool = pool
+        self.to_latent = nn.Identity()
+        self.mlp_head = nn.Sequential(nn.LayerNorm(dim))
+        self.loss_type = loss_type
+        self.GPU_ID = GPU_ID
+        if loss_type == "None":
+            print("no loss for vit_face")
+        elif loss_type == "CosFace":
+            self.loss = CosFace(in_features=dim, out_features=num_class, device_id=GPU_ID)
+        else:
+            raise NotImplementedError(f"gslora-b200 builds the CosFace head only (every GS-LoRA script uses -head CosFace); got {loss_type}")
+        # engine state (not parameters / buffers: never part of state_dict)
+        self._engine: Optional[VitEngine] = None
+        self._frozen_sig = None
+        self._lora_sig = None
+        self._slot_next = 0
+        self._slot_stamp: List[int] = []
+
+    # ------------------------------------------------------------------ module plumbing
+    def __deepcopy__(self, memo):
+        import copy
+        eng, self._engine = self._engine, None
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            for k, v in self.__dict__.items():
+                setattr(new, k, copy.deepcopy(v, memo))
+        finally:
+            self._engine = eng
+        new._engine, new._frozen_sig, new._lora_sig = None, None, None
+        return new
+
+    def lora_layers(self):
+        for attn, ff in self.transformer.layers:
+            yield ff.fn.fn.net[0], ff.fn.fn.net[3]
+
+    def lora_parameters(self) -> List[nn.Parameter]:
+        out = []
+        for fc1, fc2 in self.lora_layers():
+            out += [fc1.lora_A, fc1.lora_B, fc2.lora_A, fc2.lora_B]
+        return out
+
+    def _frozen_tensors(self):
+        t = [self.pos_embedding, self.cls_token, self.patch_to_embedding.weight, self.patch_to_embedding.bias,
+             self.mlp_head[0].weight, self.mlp_head[0].bias, self.loss.weight if hasattr(self, "loss") else None]
+        for attn, ff in self.transformer.layers:
+            a, f = attn.fn, ff.fn
+            t += [a.norm.weight, a.norm.bias, a.fn.to_qkv.weight, a.fn.to_qkv.bias, a.fn.to_out[0].weight, a.fn.to_out[0].bias,
+                  f.norm.weight, f.norm.bias, f.fn.net[0].weight, f.fn.net[0].bias, f.fn.net[3].weight, f.fn.net[3].bias]
+        return t
+
+    def engine_spec(self) -> EngineSpec:
+        return EngineSpec(image_size=self.image_size, patch_size=self.patch_size, channels=self.channels, dim=self.dim, depth=self.depth,
+                          heads=self.heads, mlp_dim=self.mlp_dim, num_class=self.num_class, lora_rank=self.lora_rank,
+                          attn_scale=self.dim ** -0.5, ln_eps=self.mlp_head[0].eps,
+                          cos_s=getattr(getattr(self, "loss", None), "s", 64.0), cos_m=getattr(getattr(self, "loss", None), "m", 0.35),
+                          grad_scale=float(os.environ.get("GSLORA_GRAD_SCALE", "1024")))
+
+    def ensure_engine(self, batch: int, slots: Optional[int] = None) -> VitEngine:
+        dev = self.pos_embedding.device
+        if dev.type != "cuda":
+            raise F.GslError("gslora-b200: ViT_face executes on a CUDA device (sm_100a) only; there is no CPU fallback")
+        slots = slots or int(os.environ.get("GSLORA_SLOTS", "2"))
+        e = self._engine
+        if e is None or e.device != dev or e.max_batch < batch or e.num_slots < slots:
+            old = e
+            cap = max(batch, old.max_batch if old is not None and old.device == dev else 0)
+            self._engine = None
+            del old, e
+            self._engine = VitEngine(self.engine_spec(), dev, cap, slots)
+            self._frozen_sig = self._lora_sig = None
+            self._slot_stamp = [0] * slots
+            self._slot_next = 0
+        return self._engine
+
+    def sync_engine(self, force_lora: bool = False):
+        """Re-link parameters into the engine and refresh its fp16 operand caches if anything changed."""
+        eng = self._engine
+        relinked = False
+        for l, (fc1, fc2) in enumerate(self.lora_layers()):
+            for w, p in enumerate((fc1.lora_A, fc1.lora_B, fc2.lora_A, fc2.lora_B)):
+                view = eng.lora_view(eng.lora_flat, l, w)
+                if p.data_ptr() != view.data_ptr():
+                    view.copy_(p.data)
+                    p.data = view
+                    relinked = True
+        params = self._frozen_tensors()
+        frozen = [None if t is None else t.data for t in params]
+        for t in frozen:
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+                raise F.GslError("gslora-b200: frozen parameters must be contiguous fp32")
+        sig = tuple((0, 0) if q is None else (q.data_ptr(), q._version) for q in params)
+        sig += tuple(m._gsl_generation for pair in self.lora_layers() for m in pair)
+        if sig != self._frozen_sig:
+            eng.bind(frozen)
+            eng.refresh_frozen()
+            self._frozen_sig = sig
+            self._lora_sig = None
+        lsig = tuple(p._version for p in self.lora_parameters()) + (eng.opt_step,)
+        if relinked or force_lora or lsig != self._lora_sig:
+            eng.refresh_lora()
+            self._lora_sig = lsig
+
+    def mark_lora_updated_by_engine(self):
+        self._lora_sig = tuple(p._version for p in self.lora_parameters()) + (self._engine.opt_step,)
+
+    def _take_slot(self) -> int:
+        s = self._slot_next
+        self._slot_next = (s + 1) % self._engine.num_slots
+        self._slot_stamp[s] += 1
+        return s
+
+    def _merged(self) -> bool:
+        states = {m.merged for pair in self.lora_layers() for m in pair}
+        if len(states) != 1:
+            raise RuntimeError("gslora-b200: LoRA layers are in mixed merged / un-merged states")
+        return states.pop()
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, img, label=None, mask=None):
+        """:return: (logits, emb) if `label` is given else emb -- as vit_face.py:523-548"""
+        if mask is not None:
+            raise NotImplementedError("gslora-b200: attention masks are not used by any GS-LoRA script and are not built")
+        if self.training and (self.dropout_p > 0.0 or self.emb_dropout_p > 0.0) and os.environ.get("GSLORA_DROPOUT", "error") != "off":
+            raise NotImplementedError("gslora-b200 round 1: dropout > 0 in train mode is not built yet; construct with dropout=0 / "
+                                      "emb_dropout=0 or set GSLORA_DROPOUT=off to run the step without dropout")
+        img = img.float().contiguous()
+        if label is not None:
+            label = label.to(device=img.device, dtype=torch.int64).contiguous()
+            if not hasattr(self, "loss"):
+                raise RuntimeError("labelled forward needs loss_type='CosFace'")
+        eng = self.ensure_engine(img.shape[0])
+        self.sync_engine()
+        merged = self._merged()
+        lora_params = self.lora_parameters()
+        need_grad = torch.is_grad_enabled() and not merged and any(p.requires_grad for p in lora_params)
+        if need_grad:
+            return _EngineFn.apply(self, img, label, *lora_params)
+        slot = self._take_slot()
+        B = eng.forward(img, label, slot, use_lora=not merged)
+        emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
+        if label is None:
+            return emb
+        return eng.slot_tensor(slot, F.SLOT_LOGITS, B).clone(), emb

@@ -41,6 +41,96 @@ int gsl_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
                  int epi, const float* bias, void* out0, int64_t ld0, void* out1, int64_t ld1,
                  const void* aux, int64_t ldaux, int64_t aux_period, int cta_group, int block_n, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------
+ * Op-level entry points (each one kernel family; used by the engine and by the parity tests)
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (vit_face.py:530) -> fp16 [B*(P+1), ld], zero row at token 0.
+ * order 0 = (p1 p2 c) ViT_face, 1 = (c p1 p2) torchvision conv_proj. */
+int gsl_patchify_f16(const float* img, void* out, int64_t ld, int B, int C, int S, int patch, int order, void* stream);
+/* nn.LayerNorm forward (vit_face.py:316-323): fp32 in, fp16 out, row mean / rstd saved. */
+int gsl_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y16, int64_t ldy,
+                      float* mean, float* rstd, int64_t M, int D, void* stream);
+/* LayerNorm backward w.r.t. the input (frozen affine) fused with the residual-gradient add. */
+int gsl_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                      const float* gamma, const float* dres, int64_t lddres, float* dx, int64_t lddx, void* dx16, int64_t lddx16,
+                      int64_t M, int D, void* stream);
+/* T[M, 0:16] = X[M,K] * A16[r,K]^T   (loralib Linear.forward's  x @ A^T ; backward U = dY @ B with A16 = B^T). r in {8,16}. */
+int gsl_lora_down(const void* X16, int64_t ldx, const void* A16, int64_t lda, void* out16, int64_t ldo, int64_t M, int K, int r, void* stream);
+/* out[n, j] (or out[j, n] if transpose_out) (+)= scale * sum_m L[m, n] * R[m, j]  -- dB = s dY^T T, dA = s U^T X. */
+size_t gsl_skinny_tn_workspace(int64_t M, int N, int r);
+int gsl_skinny_tn(const void* L16, int64_t ldl, const void* R16, int64_t ldr, float* out, int64_t ldo, int transpose_out, float scale,
+                  int accumulate, int64_t M, int N, int r, float* workspace, size_t workspace_bytes, void* stream);
+/* Attention.forward (vit_face.py:358-379) on qkv fp16 [B*N, ld] (q | k | v blocks of heads*64 columns). */
+int gsl_attention_fwd(const void* qkv16, int64_t ld, void* out16, int64_t ldo, float* lse, int B, int N, int heads, float scale, void* stream);
+int gsl_attention_bwd(const void* qkv16, int64_t ld, const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
+                      void* dqkv16, int64_t lddqkv, int B, int N, int heads, float scale, void* stream);
+/* fp32 -> fp16 cast (optional scale / transpose) used to build the frozen-weight operand caches. */
+int gsl_cast_f32_to_f16(const float* src, int64_t lds, void* dst16, int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose, void* stream);
+
+/* Fused group-Lasso + AdamW (engine_cl.get_structure_loss engine_cl.py:349-432 + torch.optim.AdamW as built by
+ * timm create_optimizer, train_own_forget_cl.py:811-813).  group_offsets: device int32 [G+1] element offsets.
+ * group_norms (device [G], optional) receives the pre-update sqrt(sum p^2) of each group. */
+int gsl_grouplasso_adamw_step(float* params, const float* grads, float* m, float* v, const int32_t* group_offsets, int num_groups,
+                              int64_t n, float lr, float wd, float beta1, float beta2, float eps, float alpha, float grad_scale,
+                              int step, float* group_norms, void* stream);
+/* util.cal_norm.get_norm_of_lora (util/cal_norm.py:121-143): out[t] = ||P_t||_F (type 0) or ||P_t||_1 (type 1). */
+int gsl_tensor_norms(const float* params, const int32_t* tensor_offsets, int num_tensors, int type, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Engine: ViT_face forward / selective backward on caller-owned memory (vit_pytorch_face/vit_face.py:449-548,
+ * engine_cl.py:59-125).  One engine per model instance and device.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct GslConfig {
+  int32_t image_size, patch_size, channels, dim, depth, heads, mlp_dim, num_class, lora_rank;
+  int32_t max_batch;     /* images per forward call */
+  int32_t num_slots;     /* activation sets kept alive at once (autograd: one per un-backwarded forward) */
+  int32_t patch_order;   /* 0 = (p1 p2 c) ViT_face */
+  float attn_scale;      /* dim ** -0.5 for ViT_face (vit_face.py:346) */
+  float ln_eps;          /* 1e-5 */
+  float cos_s, cos_m;    /* CosFace s = 64, m = 0.35 (vit_face.py:158) */
+  float lora_scaling;    /* lora_alpha / r = 1 / r */
+  float grad_scale;      /* power-of-two loss scale of the fp16 gradient stream (unscaled again in dA/dB) */
+} GslConfig;
+
+/* Frozen parameter pointer table order for gsl_engine_bind_params (fp32 device pointers, reference state_dict names):
+ *   [0] pos_embedding  [1] cls_token  [2] patch_to_embedding.weight  [3] patch_to_embedding.bias
+ *   [4] mlp_head.0.weight  [5] mlp_head.0.bias  [6] loss.weight
+ *   then per block i (12 entries): 0.fn.norm.{weight,bias}, 0.fn.fn.to_qkv.{weight, bias(NULL for ViT_face)},
+ *   0.fn.fn.to_out.0.{weight,bias}, 1.fn.norm.{weight,bias}, 1.fn.fn.net.0.{weight,bias}, 1.fn.fn.net.3.{weight,bias}
+ * lora_flat / grad_flat: fp32 [depth][ lora_A(net.0) r*D | lora_B(net.0) H*r | lora_A(net.3) r*H | lora_B(net.3) D*r ]  */
+#define GSL_NUM_GLOBAL_PARAMS 7
+#define GSL_NUM_BLOCK_PARAMS 12
+
+size_t gsl_engine_workspace_bytes(const GslConfig* cfg);
+int gsl_engine_create(const GslConfig* cfg, void* workspace, size_t workspace_bytes, void** handle_out);
+void gsl_engine_destroy(void* handle);
+int gsl_engine_bind_params(void* handle, const void* const* frozen_ptrs, int num_ptrs, float* lora_flat, float* grad_flat);
+/* rebuild the fp16 frozen-weight caches (after load_state_dict / loralib merge or unmerge mutated `weight`) */
+int gsl_engine_refresh_frozen(void* handle, void* stream);
+/* repack the fp16 LoRA operands (after any update of lora_A / lora_B) */
+int gsl_engine_refresh_lora(void* handle, void* stream);
+/* ViT_face.forward(img, label): img fp32 [B,C,S,S], labels int64 [B] (may be NULL: emb only).  use_lora = 0 runs the
+ * merged / r == 0 form (F.linear only).  Results stay in the slot: see gsl_engine_slot_ptr. */
+int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* labels, int B, int use_lora, void* stream);
+/* selective backward of engine_cl.py:124: upstream d logits [B,C] and/or d emb [B,D] (fp32, may be NULL) ->
+ * LoRA gradients written (accumulate = 0) or added (accumulate = 1) into grad_flat. */
+int gsl_engine_backward(void* handle, int slot, const float* dlogits, const float* demb, int accumulate, void* stream);
+enum { GSL_SLOT_EMB = 0, GSL_SLOT_LOGITS = 1, GSL_SLOT_CE = 2, GSL_SLOT_CORRECT = 3, GSL_SLOT_XFINAL = 4 };
+void* gsl_engine_slot_ptr(void* handle, int slot, int what);
+int64_t gsl_engine_lora_offset(void* handle, int block, int which);   /* which: 0 A(net.0) 1 B(net.0) 2 A(net.3) 3 B(net.3) */
+int64_t gsl_engine_lora_numel(void* handle);
+
+/* Step losses of engine_cl.train_one_epoch (engine_cl.py:65-80) on device, no host sync:
+ *   sums[0..5] = { sum CE_remain, n_remain, sum CE_forget, n_forget, hits_remain, hits_forget } over ce/correct[0:B],
+ *   samples [0, n_remain) are the remain batch, [n_remain, B) the forget batch.  (Allreduce `sums` for data parallel.) */
+int gsl_loss_sums(const float* ce, const int32_t* correct, int n_remain, int B, float* sums, void* stream);
+/* dlogits[b] = w_b * (softmax(logits[b]) - onehot(label_b)) with w_b = 1/n_remain (remain) or
+ *   -beta * [CE_forget_mean < BND] / n_forget (forget), counts and means taken from `sums` (device). */
+int gsl_unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C,
+                        float beta, float BND, float* dlogits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

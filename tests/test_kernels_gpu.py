@@ -1,0 +1,156 @@
+"""Kernel-level parity (GPU): each C-ABI op against a plain PyTorch fp32 restatement of the same op on identical
+inputs.  Tolerances are for fp16 operands with fp32 accumulation."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    from gslora import _ffi
+    _ffi.lib()
+    return _ffi
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+GEMM_CASES = [
+    # M, N, K, epi, cta_group, block_n
+    (256, 256, 128, 0, 1, 128), (512, 512, 512, 0, 2, 256), (1000, 384, 528, 0, 1, 128), (1000, 1536, 528, 0, 2, 256),
+    (300, 512, 2064, 1, 2, 256), (520, 2048, 528, 2, 1, 256), (520, 2048, 528, 2, 2, 256), (520, 2048, 528, 3, 2, 256),
+    (777, 512, 2064, 4, 2, 256), (777, 128, 272, 4, 2, 128), (26 * 5, 128, 192, 5, 1, 128), (197 * 3, 512, 192, 5, 2, 256),
+    (9456, 512, 2064, 4, 0, 0), (9456, 2048, 528, 2, 0, 0),
+]
+
+
+@pytest.mark.parametrize("M,N,K,epi,cg,bn", GEMM_CASES)
+def test_gemm_epilogues(F, M, N, K, epi, cg, bn):
+    torch.manual_seed(M + N + K + epi)
+    dev = "cuda"
+    A = (torch.randn(M, K, device=dev) * 0.5).half()
+    B = (torch.randn(N, K, device=dev) * 0.05).half()
+    bias = torch.randn(N, device=dev)
+    acc = A.float() @ B.float().t()
+    out1 = aux = None
+    period = 0
+    want1 = None
+    if epi == F.EPI_F16:
+        out0 = torch.empty(M, N, device=dev, dtype=torch.half); want0 = acc + bias
+    elif epi == F.EPI_F32:
+        out0 = torch.empty(M, N, device=dev); out1 = torch.empty(M, N, device=dev, dtype=torch.half); want0 = want1 = acc + bias
+    elif epi == F.EPI_GELU:
+        out0 = torch.empty(M, N, device=dev, dtype=torch.half); out1 = torch.empty(M, N, device=dev, dtype=torch.half)
+        want0 = acc + bias; want1 = torch.nn.functional.gelu(want0)
+    elif epi == F.EPI_GELU_BWD:
+        aux = torch.randn(M, N, device=dev).half(); out0 = torch.empty(M, N, device=dev, dtype=torch.half)
+        h = aux.float().requires_grad_(True); torch.nn.functional.gelu(h).sum().backward()
+        bias = None; want0 = acc * h.grad
+    elif epi == F.EPI_RES_F32:
+        aux = torch.randn(M, N, device=dev); out0 = torch.empty(M, N, device=dev); out1 = torch.empty(M, N, device=dev, dtype=torch.half)
+        want0 = want1 = acc + bias + aux
+    else:
+        period = 26 if M % 26 == 0 else 197
+        aux = torch.randn(period, N, device=dev); out0 = torch.empty(M, N, device=dev); bias = None
+        want0 = acc + aux.repeat(M // period, 1)
+    F.gemm_f16(A, B, epi=epi, bias=bias, out0=out0, out1=out1, aux=aux, aux_period=period, cta_group=cg, block_n=bn)
+    torch.cuda.synchronize()
+    tol0 = 2e-3 if out0.dtype == torch.half else 2e-5      # fp16 output rounding vs fp32 output
+    assert (out0.float() - want0).abs().max() <= tol0 * want0.abs().max() + 1e-3 * (out0.dtype == torch.half)
+    if want1 is not None:
+        assert (out1.float() - want1).abs().max() <= 2e-3 * want1.abs().max() + 1e-3
+
+
+@pytest.mark.parametrize("M,D", [(197 * 3, 512), (1000, 128), (77, 768), (64, 1024)])
+def test_layernorm_fwd_bwd(F, M, D):
+    torch.manual_seed(0)
+    x = torch.randn(M, D, device="cuda") * 2 + 0.5
+    g = 1 + 0.1 * torch.randn(D, device="cuda"); b = 0.1 * torch.randn(D, device="cuda")
+    y16 = torch.zeros(M, D + 16, device="cuda", dtype=torch.half)
+    mean = torch.empty(M, device="cuda"); rstd = torch.empty(M, device="cuda")
+    F.check(F.lib().gsl_layernorm_fwd(F.ptr(x), D, F.ptr(g), F.ptr(b), 1e-5, F.ptr(y16), D + 16, F.ptr(mean), F.ptr(rstd), M, D, F.cur_stream()))
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), g, b, 1e-5)
+    assert (y16[:, :D].float() - ref).abs().max() < 4e-3
+    assert (y16[:, D:] == 0).all()
+    dy = torch.randn(M, D, device="cuda"); dres = torch.randn(M, D, device="cuda")
+    ref.backward(dy)
+    dx = dres.clone(); dx16 = torch.empty(M, D + 16, device="cuda", dtype=torch.half)
+    F.check(F.lib().gsl_layernorm_bwd(F.ptr(dy), D, F.ptr(x), D, F.ptr(mean), F.ptr(rstd), F.ptr(g), F.ptr(dx), D, F.ptr(dx), D, F.ptr(dx16), D + 16, M, D, F.cur_stream()))
+    want = xr.grad + dres
+    assert rel(dx, want) < 1e-5
+    assert rel(dx16[:, :D].float(), want) < 1e-3
+
+
+@pytest.mark.parametrize("M,K,r", [(1000, 512, 8), (197 * 5, 2048, 8), (333, 1024, 16), (50, 128, 8), (100, 272 - 16, 8)])
+def test_lora_down(F, M, K, r):
+    torch.manual_seed(1)
+    X = torch.randn(M, K + 16, device="cuda").half()
+    A = torch.zeros(16, K, device="cuda", dtype=torch.half); A[:r] = (torch.randn(r, K, device="cuda") * 0.05).half()
+    X[:, K:] = 7.0
+    F.check(F.lib().gsl_lora_down(F.ptr(X), K + 16, F.ptr(A), K, F.ptr(X[:, K:]), K + 16, M, K, r, F.cur_stream()))
+    want = X[:, :K].float() @ A.float().t()
+    assert (X[:, K:].float() - want).abs().max() <= 2e-3 * want.abs().max() + 1e-4
+    assert (X[:, K + r:] == 0).all()
+
+
+@pytest.mark.parametrize("M,N,r,tr", [(1000, 512, 8, 0), (197 * 7, 2048, 8, 1), (300, 256, 16, 1), (65, 128, 8, 0)])
+def test_skinny_tn(F, M, N, r, tr):
+    torch.manual_seed(2)
+    L = torch.randn(M, N + 16, device="cuda").half(); R = torch.randn(M, 16, device="cuda").half()
+    nb = F.lib().gsl_skinny_tn_workspace(M, N, r)
+    ws = torch.empty(nb // 4 + 16, device="cuda")
+    out = torch.full((r, N) if tr else (N, r), 0.5, device="cuda")
+    want = 0.25 * (L[:, :N].float().t() @ R[:, :r].float())
+    for acc in (0, 1):
+        F.check(F.lib().gsl_skinny_tn(F.ptr(L), N + 16, F.ptr(R), 16, F.ptr(out), N if tr else r, tr, 0.25, acc, M, N, r, F.ptr(ws), nb, F.cur_stream()))
+        got = out.t() if tr else out
+        assert rel(got, want * (1 + acc)) < 1e-5
+
+
+@pytest.mark.parametrize("B,N,heads,scale", [(3, 197, 8, 512 ** -0.5), (2, 26, 2, 128 ** -0.5), (1, 197, 12, 0.125), (5, 50, 4, 0.2)])
+def test_attention_fwd_bwd(F, B, N, heads, scale):
+    torch.manual_seed(3)
+    D = heads * 64
+    qkv = torch.randn(B * N, 3 * D, device="cuda").half()
+    out = torch.empty(B * N, D, device="cuda", dtype=torch.half); lse = torch.empty(B * heads * N, device="cuda")
+    F.check(F.lib().gsl_attention_fwd(F.ptr(qkv), 3 * D, F.ptr(out), D, F.ptr(lse), B, N, heads, scale, F.cur_stream()))
+    q32 = qkv.float().requires_grad_(True)
+    q, k, v = [t.reshape(B, N, heads, 64).permute(0, 2, 1, 3) for t in q32.chunk(3, dim=-1)]
+    dots = torch.einsum("bhid,bhjd->bhij", q, k) * scale
+    ref = torch.einsum("bhij,bhjd->bhid", dots.softmax(-1), v).permute(0, 2, 1, 3).reshape(B * N, D)
+    assert rel(out.float(), ref) < 2e-3
+    assert (lse.view(B, heads, N) - torch.logsumexp(dots, -1)).abs().max() < 2e-3
+    dout = torch.randn(B * N, D, device="cuda").half()
+    ref.backward(dout.float())
+    dqkv = torch.empty(B * N, 3 * D, device="cuda", dtype=torch.half)
+    F.check(F.lib().gsl_attention_bwd(F.ptr(qkv), 3 * D, F.ptr(out), D, F.ptr(dout), D, F.ptr(lse), F.ptr(dqkv), 3 * D, B, N, heads, scale, F.cur_stream()))
+    for i, name in enumerate("qkv"):
+        assert rel(dqkv[:, i * D:(i + 1) * D].float(), q32.grad[:, i * D:(i + 1) * D]) < 4e-3, name
+
+
+def test_grouplasso_adamw_matches_torch(F):
+    torch.manual_seed(4)
+    G, n_per = 6, 40960
+    p = torch.randn(G * n_per, device="cuda") * 0.05
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref], lr=1e-2, weight_decay=0.05)
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    offs = (torch.arange(G + 1, device="cuda", dtype=torch.int32) * n_per).contiguous()
+    norms = torch.empty(G, device="cuda")
+    alpha = 1e-2
+    for step in range(1, 4):
+        g = torch.randn_like(p) * 1e-3
+        opt.zero_grad()
+        loss = (ref * g).sum() + alpha * ref.view(G, -1).norm(dim=1).sum()
+        loss.backward(); opt.step()
+        F.check(F.lib().gsl_grouplasso_adamw_step(F.ptr(p), F.ptr(g), F.ptr(m), F.ptr(v), F.ptr(offs), G, p.numel(), 1e-2, 0.05, 0.9, 0.999,
+                                                  1e-8, alpha, 1.0, step, F.ptr(norms), F.cur_stream()))
+        assert rel(p, ref.detach()) < 2e-6
+    tn = torch.empty(G, device="cuda")
+    F.check(F.lib().gsl_tensor_norms(F.ptr(p), F.ptr(offs), G, 1, F.ptr(tn), F.cur_stream()))
+    assert rel(tn, p.view(G, -1).abs().sum(1)) < 1e-5
