@@ -68,7 +68,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
@@ -243,6 +243,42 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
     const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
     const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
     return cdf + x * pdf;
+}
+
+// Cheap erf-GELU for the GEMM epilogues (budget: ~16 issue slots per element): Abramowitz-Stegun 7.1.26
+//   erfc(z) ~= t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),  t = 1 / (1 + p z),  z = |x| / sqrt(2)   (|err| < 1.5e-7)
+// so Phi(x) = 0.5 erfc(-x / sqrt 2) and exp(-z^2) = exp(-x^2 / 2) is shared with the Gaussian pdf of the derivative.
+// Max abs error vs the exact erf form: 4.3e-7 (gelu), 3.0e-7 (gelu') over [-12, 12] -- far below the fp16 store rounding.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// hq = 0.5 - 0.5 * erfc(|x| / sqrt 2)  in [0, 0.5]  (so Phi(x) = 0.5 + sign(x) * hq);  e = exp(-x^2 / 2)
+__device__ __forceinline__ void gelu_parts(float x, float& hq, float& e) {
+    const float t = rcp_approx(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.0f));
+    float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);     // 0.5 folded into the coefficients
+    poly = fmaf(poly, t, 0.5f * 1.421413741f);
+    poly = fmaf(poly, t, 0.5f * -0.284496736f);
+    poly = fmaf(poly, t, 0.5f * 0.254829592f);
+    e = ex2_approx(x * x * -0.72134752044448170f);                       // exp(-x^2 / 2) = 2^(-x^2 * log2(e) / 2)
+    hq = fmaf(-poly * t, e, 0.5f);
+}
+__device__ __forceinline__ float gelu_fast(float x) {                     // x * Phi(x) = 0.5 x + |x| * hq
+    float hq, e;
+    gelu_parts(x, hq, e);
+    return fmaf(fabsf(x), hq, 0.5f * x);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {                // Phi(x) + x * pdf(x)
+    float hq, e;
+    gelu_parts(x, hq, e);
+    const float cdf = 0.5f + copysignf(hq, x);
+    return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

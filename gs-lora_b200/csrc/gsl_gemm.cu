@@ -29,7 +29,6 @@ namespace gsl {
 static constexpr int BLOCK_M = 128;   // rows per CTA (UMMA M = 128 * CTA_GROUP)
 static constexpr int BLOCK_K = 64;    // 64 fp16 = one 128-byte swizzle row
 static constexpr int SMEM_LIMIT = 232448;
-static constexpr int GEMM_THREADS = 192;
 
 struct GemmParams {
     int M, N, K;
@@ -38,17 +37,20 @@ struct GemmParams {
     const float* bias;    // [N] or nullptr
     const float* table;   // EPI_PERIODIC_F32: fp32 [period, ld_table]
     int period, ld_table;
-    int has_out1;         // EPI_RES_F32 / EPI_F32: also emit an fp16 copy through tmO1
+    int has_out1;         // EPI_F32: also emit an fp16 copy through tmO1
 };
 
 template <int EPI> struct EpiTraits;
-//                                                          out0 bytes/elem, out1?, aux bytes/elem (0 = none)
+//                                                          out0 bytes/elem, out1 bytes/elem (0 = none), aux bytes/elem (0 = none)
 template <> struct EpiTraits<EPI_F16>          { static constexpr int O0 = 2, O1 = 0, AUX = 0; };
 template <> struct EpiTraits<EPI_F32>          { static constexpr int O0 = 4, O1 = 2, AUX = 0; };
 template <> struct EpiTraits<EPI_GELU>         { static constexpr int O0 = 2, O1 = 2, AUX = 0; };
 template <> struct EpiTraits<EPI_GELU_BWD>     { static constexpr int O0 = 2, O1 = 0, AUX = 2; };
-template <> struct EpiTraits<EPI_RES_F32>      { static constexpr int O0 = 4, O1 = 2, AUX = 4; };
+template <> struct EpiTraits<EPI_RES_F32>      { static constexpr int O0 = 4, O1 = 0, AUX = 4; };
 template <> struct EpiTraits<EPI_PERIODIC_F32> { static constexpr int O0 = 4, O1 = 0, AUX = 0; };
+
+static constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of a stripe's columns
+static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 template <int CG, int BN, int EPI>
 struct GemmCfg {
@@ -56,12 +58,14 @@ struct GemmCfg {
     static constexpr int A_STAGE = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_STAGE = (BN / CG) * BLOCK_K * 2;
     static constexpr int STAGE = A_STAGE + B_STAGE;
-    // per epilogue warp: 32 rows x 32 columns per chunk, two buffers per tensor
-    static constexpr int O0_BUF = 32 * 32 * T::O0;
-    static constexpr int O1_BUF = 32 * 32 * T::O1;
-    static constexpr int AUX_BUF = 32 * 32 * T::AUX;
-    static constexpr int EPI_WARP = 2 * (O0_BUF + O1_BUF + AUX_BUF);
-    static constexpr int EPI_TOTAL = 4 * EPI_WARP;
+    // the epilogue works on stripes of the 128 x BN accumulator: 64 columns when every output is fp16, 32 columns when
+    // the main output is fp32 -- either way one 128-byte swizzle row per accumulator row, one TMA store per stripe.
+    static constexpr int STRIPE = T::O0 == 2 ? 64 : 32;
+    static constexpr int CW = STRIPE / 2;                 // columns per epilogue warp
+    static constexpr int O0_BUF = BLOCK_M * STRIPE * T::O0;
+    static constexpr int O1_BUF = BLOCK_M * STRIPE * T::O1;
+    static constexpr int AUX_BUF = BLOCK_M * STRIPE * T::AUX;
+    static constexpr int EPI_TOTAL = 2 * (O0_BUF + O1_BUF + AUX_BUF);
     static constexpr int BAR_BYTES = 1024;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - EPI_TOTAL - BAR_BYTES) / STAGE;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -69,8 +73,32 @@ struct GemmCfg {
     static constexpr int TMEM_COLS = 2 * BN;
     static_assert(STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
-    static_assert(EPI_WARP % 1024 == 0, "staging must keep 1024-byte alignment");
+    static_assert(O0_BUF % 1024 == 0 && (O1_BUF % 1024 == 0) && (AUX_BUF % 1024 == 0), "staging must keep 1024-byte alignment");
 };
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+
+// load CW fp32 accumulator columns of this warp's 32 TMEM lanes
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&f)[CW]) {
+    if constexpr (CW == 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    } else {
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr) : "memory");
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+    }
+}
 
 template <int CG, int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -92,8 +120,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto empty_bar = [&](int i) { return sBar + 8u * (S + i); };
     auto tfull_bar = [&](int i) { return sBar + 8u * (2 * S + i); };
     auto tempty_bar = [&](int i) { return sBar + 8u * (2 * S + 2 + i); };
-    auto aux_bar = [&](int w, int i) { return sBar + 8u * (2 * S + 4 + 2 * w + i); };
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (sBar - smem_base) + 8 * (2 * S + 4 + 8));
+    auto aux_bar = [&](int i) { return sBar + 8u * (2 * S + 4 + i); };
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (sBar - smem_base) + 8 * (2 * S + 4 + 2));
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
@@ -117,10 +145,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(tfull_bar(i), 1);             // one tcgen05.commit
-                mbar_init(tempty_bar(i), CG * 128);     // every epilogue thread of the pair
+                mbar_init(tempty_bar(i), CG * EPI_WARPS * 32);     // every epilogue thread of the pair
             }
-            for (int w = 0; w < 4; ++w)
-                for (int i = 0; i < 2; ++i) mbar_init(aux_bar(w, i), 1);
+            for (int i = 0; i < 2; ++i) mbar_init(aux_bar(i), 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -165,11 +192,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int t = cluster_id; t < total_tiles; t += num_clusters, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
-                if (CG == 2) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1); else mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    if (CG == 2) mbar_wait_cluster(full_bar(stage), phase); else mbar_wait(full_bar(stage), phase);
+                    mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
                     if (lane == 0) {
                         const uint64_t da = umma_desc_sw128(sA + stage * Cfg::A_STAGE);
@@ -189,64 +216,62 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        // ===================================================== epilogue warps
+        // ===================================================== epilogue warps (8 warps = 256 threads)
+        constexpr int STRIPE = Cfg::STRIPE, CW = Cfg::CW;
         const uint32_t quarter = warp & 3;              // TMEM lane quarter this warp may access
         const uint32_t ew = warp - 2;
-        const uint32_t stg = sEpi + ew * Cfg::EPI_WARP;
-        // ordered large -> small so every buffer keeps the alignment its swizzle mode needs
-        uint32_t off = 0;
+        const uint32_t half = ew >> 2;                  // which half of the stripe's columns
+        const uint32_t row = quarter * 32 + lane;       // row of the 128-row tile owned by this thread
+        const bool elected = (ew == 0 && lane == 0);
         uint32_t o0_buf[2], o1_buf[2], aux_buf[2];
-        if (T::O0 == 4) { o0_buf[0] = stg + off; o0_buf[1] = stg + off + Cfg::O0_BUF; off += 2 * Cfg::O0_BUF; }
-        if (T::AUX == 4) { aux_buf[0] = stg + off; aux_buf[1] = stg + off + Cfg::AUX_BUF; off += 2 * Cfg::AUX_BUF; }
-        if (T::O0 == 2) { o0_buf[0] = stg + off; o0_buf[1] = stg + off + Cfg::O0_BUF; off += 2 * Cfg::O0_BUF; }
-        if (T::O1 == 2) { o1_buf[0] = stg + off; o1_buf[1] = stg + off + Cfg::O1_BUF; off += 2 * Cfg::O1_BUF; }
-        if (T::AUX == 2) { aux_buf[0] = stg + off; aux_buf[1] = stg + off + Cfg::AUX_BUF; off += 2 * Cfg::AUX_BUF; }
-        const bool write_o1 = (EPI == EPI_GELU) || ((EPI == EPI_RES_F32 || EPI == EPI_F32) && p.has_out1);
+        {
+            uint32_t off = sEpi;
+            o0_buf[0] = off; o0_buf[1] = off + Cfg::O0_BUF; off += 2 * Cfg::O0_BUF;
+            aux_buf[0] = off; aux_buf[1] = off + Cfg::AUX_BUF; off += 2 * Cfg::AUX_BUF;
+            o1_buf[0] = off; o1_buf[1] = off + Cfg::O1_BUF;
+        }
+        const bool write_o1 = (EPI == EPI_GELU) || (EPI == EPI_F32 && p.has_out1);
 
         int iter = 0;
-        uint32_t aux_it = 0;     // aux chunks consumed so far (buffer = aux_it & 1, parity = (aux_it >> 1) & 1)
-        uint32_t st_it = 0;      // store chunks issued so far (staging buffer = st_it & 1)
+        uint32_t aux_it = 0;     // aux stripes consumed so far (buffer = aux_it & 1, parity = (aux_it >> 1) & 1)
+        uint32_t st_it = 0;      // stripes stored so far (staging buffer = st_it & 1)
         for (int t = cluster_id; t < total_tiles; t += num_clusters, ++iter) {
             const int mt = t / p.num_n_tiles, nt = t % p.num_n_tiles;
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
-            const int row0 = (mt * CG + (int)cta_rank) * BLOCK_M + (int)quarter * 32;
+            const int m_base = (mt * CG + (int)cta_rank) * BLOCK_M;
             const int n_base = nt * BN;
             const int n_rem = p.N - n_base;
-            const int nchunks = (n_rem >= BN ? BN : n_rem + 31) / 32;
-            const bool rows_live = row0 < p.M;     // warp-uniform
+            const int nstripes = ((n_rem >= BN ? BN : n_rem) + STRIPE - 1) / STRIPE;
+            const bool tile_live = m_base < p.M;     // CTA-uniform (the second CTA of a pair can be past the M tail)
 
-            if (T::AUX && rows_live && lane == 0) {
+            if (T::AUX && tile_live && elected) {
                 const uint32_t b = aux_it & 1;
-                mbar_arrive_expect_tx(aux_bar(ew, b), Cfg::AUX_BUF);
-                tma_load_2d<1>(&tmAux, aux_bar(ew, b), aux_buf[b], n_base, row0);
+                mbar_arrive_expect_tx(aux_bar(b), Cfg::AUX_BUF);
+                tma_load_2d<1>(&tmAux, aux_bar(b), aux_buf[b], n_base, m_base);
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
 
-            for (int c = 0; c < nchunks; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + acc * BN + c * 32, v);
-                if (T::AUX && rows_live && lane == 0 && c + 1 < nchunks) {
+            for (int sidx = 0; sidx < nstripes; ++sidx) {
+                const int n0 = n_base + sidx * STRIPE + (int)half * CW;      // first column of this warp
+                float f[CW];
+                if (T::AUX && tile_live && elected && sidx + 1 < nstripes) {
                     const uint32_t b = (aux_it + 1) & 1;
-                    mbar_arrive_expect_tx(aux_bar(ew, b), Cfg::AUX_BUF);
-                    tma_load_2d<1>(&tmAux, aux_bar(ew, b), aux_buf[b], n_base + (c + 1) * 32, row0);
+                    mbar_arrive_expect_tx(aux_bar(b), Cfg::AUX_BUF);
+                    tma_load_2d<1>(&tmAux, aux_bar(b), aux_buf[b], n_base + (sidx + 1) * STRIPE, m_base);
                 }
-                tmem_ld_wait();
-                if (c == nchunks - 1) {
+                tmem_ld_cols<CW>(tmem_base + ((quarter * 32u) << 16) + acc * BN + sidx * STRIPE + half * CW, f);
+                if (sidx == nstripes - 1) {
                     // all TMEM reads of this accumulator are in registers: hand the buffer back to the MMA warp
                     tcgen05_fence_before();
                     if (CG == 2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
                 }
-                if (!rows_live) continue;
+                if (!tile_live) continue;
 
-                const int n0 = n_base + c * 32;
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 if (p.bias != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
+                    for (int j = 0; j < CW; j += 4) {
                         if (n0 + j < p.N) {
                             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
                             f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
@@ -255,39 +280,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 if (T::AUX) {
                     const uint32_t b = aux_it & 1;
-                    mbar_wait(aux_bar(ew, b), (aux_it >> 1) & 1);
-                    if (T::AUX == 4) {          // fp32 residual tile, 128-byte rows
+                    mbar_wait(aux_bar(b), (aux_it >> 1) & 1);
+                    if (T::AUX == 4) {          // fp32 residual stripe [128 x 32]: this warp's 16 columns = chunks half*4 .. +3
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int j = 0; j < 4; ++j) {
                             float4 r;
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(aux_buf[b] + sw128_off(lane, j)));
+                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(aux_buf[b] + sw128_off(row, half * 4 + j)));
                             f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
                         }
-                    } else {                    // fp16 pre-activation tile H, 64-byte rows: dH = dG * gelu'(H)
+                    } else {                    // fp16 pre-activation stripe H [128 x 64]: dH = dG * gelu'(H)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint32_t h0, h1, h2, h3;
                             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(aux_buf[b] + sw64_off(lane, j)));
+                                         : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(aux_buf[b] + sw128_off(row, half * 4 + j)));
                             const uint32_t hh[4] = {h0, h1, h2, h3};
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const float2 h = unpack_half2(hh[q]);
-                                f[8 * j + 2 * q] *= gelu_grad_f(h.x);
-                                f[8 * j + 2 * q + 1] *= gelu_grad_f(h.y);
+                                f[8 * j + 2 * q] *= gelu_grad_fast(h.x);
+                                f[8 * j + 2 * q + 1] *= gelu_grad_fast(h.y);
                             }
                         }
                     }
-                    __syncwarp();      // every lane has consumed the aux buffer before it is refilled
                     ++aux_it;
                 }
                 if (EPI == EPI_PERIODIC_F32) {
-                    const int r = row0 + (int)lane;
+                    const int r = m_base + (int)row;
                     if (r < p.M) {
                         const float* trow = p.table + (size_t)(r % p.period) * p.ld_table + n0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
+                        for (int j = 0; j < CW; j += 4) {
                             if (n0 + j < p.N) {
                                 const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + j));
                                 f[j] += t4.x; f[j + 1] += t4.y; f[j + 2] += t4.z; f[j + 3] += t4.w;
@@ -296,45 +320,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
 
-                // staging buffer reuse: the TMA store issued two chunks ago must have finished reading smem
+                // staging buffer reuse: the TMA store issued two stripes ago must have finished reading smem
                 const uint32_t sb = st_it & 1;
-                if (lane == 0) tma_store_wait_read<1>();
-                __syncwarp();
+                if (elected) tma_store_wait_read<1>();
+                epi_bar_sync();
 
-                if (T::O0 == 4) {
+                if (T::O0 == 4) {   // fp32 [128 x 32] stripe: this warp's 16 columns = 16-byte chunks half*4 .. +3
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
+                    for (int j = 0; j < 4; ++j)
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-                                     ::"r"(o0_buf[sb] + sw128_off(lane, j)), "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
-                } else {
+                                     ::"r"(o0_buf[sb] + sw128_off(row, half * 4 + j)), "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
+                } else {            // fp16 [128 x 64] stripe: this warp's 32 columns = chunks half*4 .. +3
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                     ::"r"(o0_buf[sb] + sw64_off(lane, j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
+                                     ::"r"(o0_buf[sb] + sw128_off(row, half * 4 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
                                        "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
                 }
                 if (T::O1 && write_o1) {
-                    if (EPI == EPI_GELU) {
+                    if (EPI == EPI_GELU) {      // second output G = gelu(h), fp16 [128 x 64]
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = gelu_f(f[j]);
+                        for (int j = 0; j < CW; ++j) f[j] = gelu_fast(f[j]);
+#pragma unroll
+                        for (int j = 0; j < CW / 8; ++j)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                         ::"r"(o1_buf[sb] + sw128_off(row, half * 4 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
+                                           "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
+                    } else {                    // fp16 copy of an fp32 stripe, [128 x 32] = 64-byte rows: this warp's 16 columns = chunks half*2 .. +1
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                         ::"r"(o1_buf[sb] + sw64_off(row, half * 2 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
+                                           "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                     ::"r"(o1_buf[sb] + sw64_off(lane, j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
-                                       "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
                 }
                 fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&tmO0, o0_buf[sb], n0, row0);
-                    if (T::O1 && write_o1) tma_store_2d(&tmO1, o1_buf[sb], n0, row0);
+                epi_bar_sync();
+                if (elected) {
+                    tma_store_2d(&tmO0, o0_buf[sb], n_base + sidx * STRIPE, m_base);
+                    if (T::O1 && write_o1) tma_store_2d(&tmO1, o1_buf[sb], n_base + sidx * STRIPE, m_base);
                     tma_store_commit();
                 }
                 ++st_it;
             }
         }
-        if (lane == 0) tma_store_wait_all();
+        if (elected) tma_store_wait_all();
     }
 
     // ===================================================== teardown
@@ -386,6 +416,21 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int64_t rows
     return 0;
 }
 
+// 3-D view [B, N, cols] of a row-major [B*N, ld] fp16 matrix; box = [1, npad, 64 cols] with 128B swizzle.  Rows in
+// [N, npad) are out of bounds in dimension 1 and arrive as zeros (attention slabs).
+int make_tmap_qkv(CUtensorMap* map, const void* ptr, int64_t ld, int B, int N, int cols, int npad) {
+    GSL_REQUIRE(load_encode() == 0, "cuTensorMapEncodeTiled entry point not available");
+    GSL_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, "attention TMA: pointer / pitch must be 16-byte aligned");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)(ld * 2), (cuuint64_t)((int64_t)N * ld * 2)};
+    cuuint32_t box[3] = {64, (cuuint32_t)npad, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GSL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (attention) failed (%d)", (int)r);
+    return 0;
+}
+
 int device_sm_count() {
     static int sms = 0;
     if (sms == 0) {
@@ -404,10 +449,10 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     int rc;
     if ((rc = make_tmap_2d(&tmA, a.A, 2, a.M, a.K, a.lda, BLOCK_M, BLOCK_K))) return rc;
     if ((rc = make_tmap_2d(&tmB, a.B, 2, a.N, a.K, a.ldb, BN / CG, BLOCK_K))) return rc;
-    if ((rc = make_tmap_2d(&tmO0, a.out0, T::O0, a.M, a.N, a.ld0, 32, 32))) return rc;
+    if ((rc = make_tmap_2d(&tmO0, a.out0, T::O0, a.M, a.N, a.ld0, BLOCK_M, Cfg::STRIPE))) return rc;
     const bool has_o1 = (EPI == EPI_GELU) || (T::O1 && a.out1 != nullptr);
-    if (has_o1) { if ((rc = make_tmap_2d(&tmO1, a.out1, 2, a.M, a.N, a.ld1, 32, 32))) return rc; } else tmO1 = tmO0;
-    if (T::AUX) { if ((rc = make_tmap_2d(&tmAux, a.aux, T::AUX, a.M, a.N, a.ldaux, 32, 32))) return rc; } else tmAux = tmO0;
+    if (has_o1) { if ((rc = make_tmap_2d(&tmO1, a.out1, 2, a.M, a.N, a.ld1, BLOCK_M, Cfg::STRIPE))) return rc; } else tmO1 = tmO0;
+    if (T::AUX) { if ((rc = make_tmap_2d(&tmAux, a.aux, T::AUX, a.M, a.N, a.ldaux, BLOCK_M, Cfg::STRIPE))) return rc; } else tmAux = tmO0;
 
     GemmParams p;
     p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K;

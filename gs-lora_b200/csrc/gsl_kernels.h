@@ -13,7 +13,7 @@ enum GemmEpi {
     EPI_F32 = 1,           // out0(fp32) = acc + bias                    [+ out1(fp16) copy]
     EPI_GELU = 2,          // out0(fp16) = h = acc + bias ; out1(fp16) = gelu(h)          (FFN fc1)
     EPI_GELU_BWD = 3,      // out0(fp16) = acc * gelu'(aux(fp16))                          (dH = dG * gelu'(H))
-    EPI_RES_F32 = 4,       // out0(fp32) = acc + bias + aux(fp32)        [+ out1(fp16) copy] (residual adds)
+    EPI_RES_F32 = 4,       // out0(fp32) = acc + bias + aux(fp32)                            (residual adds)
     EPI_PERIODIC_F32 = 5,  // out0(fp32) = acc + aux_table(fp32)[row % period]             (patch embed + pos/cls)
 };
 

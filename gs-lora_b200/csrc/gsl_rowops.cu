@@ -270,46 +270,107 @@ int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __ha
 
 // ------------------------------------------------------------------------------------------------ skinny L^T * R over tokens
 // P[n, j] = scale * sum_m L[m, n] * R[m, j]   (n < N, j < r):  dB = s * dY^T T,  dA^T = s * X^T U  (SURVEY Appendix C).
-// Split-M partial sums (each CTA owns a 256-column block and an m-range, lanes walk columns so L is read
-// coalesced; the r-wide R rows are broadcast from shared memory), then a deterministic second pass.
+// HBM-bound (reads L once).  Split-M: CTA (col-block of 256, m-range) streams [64 m x 256 n] tiles of L and [64 m x 16] tiles
+// of R through a 3-stage cp.async ring; each warp owns 32 columns and contracts over m with mma.sync m16n8k16 -- both
+// operands are "transposed" views of row-major tiles, fetched with ldmatrix.trans (no explicit transpose anywhere).
+// Partials go to a workspace and a second tiny kernel reduces them in a fixed order (deterministic, no atomics).
+static constexpr int SK_COLS = 256, SK_ROWS = 64, SK_STAGES = 3, SK_THREADS = 256;
+static constexpr int SK_L_BYTES = SK_ROWS * SK_COLS * 2;   // 32 KB
+static constexpr int SK_R_BYTES = SK_ROWS * 16 * 2;        //  2 KB
+static constexpr int SK_STAGE_BYTES = SK_L_BYTES + SK_R_BYTES;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
 template <int R>
-__global__ void __launch_bounds__(128) skinny_tn_partial_kernel(const __half* __restrict__ L, int64_t ldl, const __half* __restrict__ Rm, int64_t ldr,
-                                                                float* __restrict__ partial, int64_t M, int N, int rows_per_split) {
-    __shared__ __align__(16) float rs[64][R];
-    const int col = blockIdx.x * 256 + threadIdx.x * 2;
+__global__ void __launch_bounds__(SK_THREADS, 2) skinny_tn_partial_kernel(const __half* __restrict__ L, int64_t ldl, const __half* __restrict__ Rm, int64_t ldr,
+                                                                         float* __restrict__ partial, int64_t M, int N, int rows_per_split) {
+    extern __shared__ __align__(128) uint8_t sk_smem[];
+    const uint32_t sbase = smem_u32(sk_smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int col0 = blockIdx.x * SK_COLS;
     const int split = blockIdx.y;
     const int64_t m0 = (int64_t)split * rows_per_split;
     const int64_t m1 = (m0 + rows_per_split < M) ? m0 + rows_per_split : M;
-    float acc0[R], acc1[R];
+    const int nchunks = m1 > m0 ? (int)((m1 - m0 + SK_ROWS - 1) / SK_ROWS) : 0;
+
+    auto load_chunk = [&](int c, int stage) {
+        const int64_t mb = m0 + (int64_t)c * SK_ROWS;
+        const uint32_t sL = sbase + stage * SK_STAGE_BYTES, sR = sL + SK_L_BYTES;
 #pragma unroll
-    for (int j = 0; j < R; ++j) acc0[j] = acc1[j] = 0.f;
-    const bool col_ok = col < N;
-    for (int64_t mb = m0; mb < m1; mb += 64) {
-        const int cnt = (int)((m1 - mb < 64) ? (m1 - mb) : 64);
-        __syncthreads();
-        for (int i = threadIdx.x; i < 64 * R; i += 128) {
-            const int mm = i / R, j = i % R;
-            rs[mm][j] = mm < cnt ? __half2float(Rm[(mb + mm) * ldr + j]) : 0.f;
+        for (int i = 0; i < (SK_ROWS * SK_COLS / 8) / SK_THREADS; ++i) {
+            const int idx = tid + i * SK_THREADS;
+            const int row = idx >> 5, chunk = idx & 31;
+            const bool ok = (mb + row < m1) && (col0 + chunk * 8 < N);
+            const __half* src = L + (ok ? (mb + row) * ldl + col0 + chunk * 8 : 0);
+            cp_async16(sL + row * 512 + (((chunk & ~7) | ((chunk ^ row) & 7)) << 4), src, ok);
         }
-        __syncthreads();
-        if (col_ok) {
-            const __half* lp = L + mb * ldl + col;
-#pragma unroll 8
-            for (int mm = 0; mm < cnt; ++mm) {
-                const float2 l = unpack_half2(*reinterpret_cast<const uint32_t*>(lp + (int64_t)mm * ldl));
+        if (tid < SK_ROWS * 2) {
+            const int row = tid >> 1, chunk = tid & 1;
+            const bool ok = (mb + row < m1);
+            const __half* src = Rm + (ok ? (mb + row) * ldr + chunk * 8 : 0);
+            cp_async16(sR + row * 32 + chunk * 16, src, ok);
+        }
+    };
+
+    constexpr int NJ = R / 8;
+    float acc[2][NJ][4];
 #pragma unroll
-                for (int j = 0; j < R; j += 4) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(&rs[mm][j]);
-                    acc0[j] += l.x * r4.x; acc0[j + 1] += l.x * r4.y; acc0[j + 2] += l.x * r4.z; acc0[j + 3] += l.x * r4.w;
-                    acc1[j] += l.y * r4.x; acc1[j + 1] += l.y * r4.y; acc1[j + 2] += l.y * r4.z; acc1[j + 3] += l.y * r4.w;
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[a][j][0] = acc[a][j][1] = acc[a][j][2] = acc[a][j][3] = 0.f;
+
+    for (int c = 0; c < SK_STAGES - 1; ++c) {
+        if (c < nchunks) load_chunk(c, c);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(SK_STAGES - 2) : "memory");
+        __syncthreads();
+        if (c + SK_STAGES - 1 < nchunks) load_chunk(c + SK_STAGES - 1, (c + SK_STAGES - 1) % SK_STAGES);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const uint32_t sL = sbase + (c % SK_STAGES) * SK_STAGE_BYTES, sR = sL + SK_L_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < SK_ROWS / 16; ++ks) {
+            // B fragments: R tile rows m (k), columns j (n), transposed load
+            uint32_t bf[NJ][2];
+            {
+                const int row = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                if (NJ == 1) {
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(bf[0][0]), "=r"(bf[0][1]) : "r"(sR + row * 32));
+                } else {
+                    uint32_t r4[4];
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r4[0]), "=r"(r4[1]), "=r"(r4[2]), "=r"(r4[3]) : "r"(sR + row * 32 + (lane >> 4) * 16));
+                    bf[0][0] = r4[0]; bf[0][1] = r4[1]; bf[NJ - 1][0] = r4[2]; bf[NJ - 1][1] = r4[3];
                 }
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                // A fragment (rows = n, k = m) from the [m][n] tile: transposed load
+                const int row = ks * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+                const int chunk = warp * 4 + a * 2 + ((lane >> 3) & 1);
+                uint32_t af[4];
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3])
+                             : "r"(sL + row * 512 + (((chunk & ~7) | ((chunk ^ row) & 7)) << 4)));
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) mma_16816(acc[a][j], af[0], af[1], af[2], af[3], bf[j][0], bf[j][1]);
             }
         }
     }
-    if (col_ok) {
-        float* p = partial + ((int64_t)split * N + col) * R;
+    // c0,c1 -> (n = g, j = 2t, 2t+1) ; c2,c3 -> (n = g + 8)
+    const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-        for (int j = 0; j < R; ++j) { p[j] = acc0[j]; p[R + j] = acc1[j]; }
+    for (int a = 0; a < 2; ++a) {
+        const int n = col0 + warp * 32 + a * 16 + g;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if (n < N) *reinterpret_cast<float2*>(partial + ((int64_t)split * N + n) * R + j * 8 + 2 * t) = make_float2(acc[a][j][0], acc[a][j][1]);
+            if (n + 8 < N) *reinterpret_cast<float2*>(partial + ((int64_t)split * N + n + 8) * R + j * 8 + 2 * t) = make_float2(acc[a][j][2], acc[a][j][3]);
+        }
     }
 }
 
@@ -328,9 +389,9 @@ __global__ void skinny_tn_reduce_kernel(const float* __restrict__ partial, int s
 }
 
 static int skinny_splits(int64_t M, int N) {
-    const int colblocks = (N + 255) / 256;
-    int splits = (device_sm_count() * 4 + colblocks - 1) / colblocks;
-    const int64_t max_splits = (M + 63) / 64;
+    const int colblocks = (N + SK_COLS - 1) / SK_COLS;
+    int splits = (device_sm_count() * 2 + colblocks - 1) / colblocks;
+    const int64_t max_splits = (M + SK_ROWS - 1) / SK_ROWS;
     if (splits > max_splits) splits = (int)max_splits;
     if (splits < 1) splits = 1;
     return splits;
@@ -344,17 +405,24 @@ size_t skinny_tn_workspace(int64_t M, int N, int r) {
 int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float* out, int64_t ldo, int transpose_out, float scale,
               int accumulate, int64_t M, int N, int r, float* workspace, size_t workspace_bytes, cudaStream_t s) {
     GSL_REQUIRE(r == 8 || r == 16, "skinny_tn: rank must be 8 or 16 (got %d)", r);
-    GSL_REQUIRE(N % 2 == 0 && ldl % 2 == 0, "skinny_tn: N and ldl must be even");
+    GSL_REQUIRE(N % 8 == 0 && ldl % 8 == 0 && ldr % 8 == 0, "skinny_tn: N, ldl, ldr must be multiples of 8");
     GSL_REQUIRE(workspace_bytes >= skinny_tn_workspace(M, N, r), "skinny_tn: workspace too small");
     const int splits = skinny_splits(M, N);
     int rows_per_split = (int)((M + splits - 1) / splits);
     rows_per_split = (rows_per_split + 63) / 64 * 64;
-    dim3 grid((N + 255) / 256, splits);
+    dim3 grid((N + SK_COLS - 1) / SK_COLS, splits);
+    const int smem = SK_STAGES * SK_STAGE_BYTES;
+    static bool attr = false;
+    if (!attr) {
+        GSL_CHECK_CUDA(cudaFuncSetAttribute(skinny_tn_partial_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GSL_CHECK_CUDA(cudaFuncSetAttribute(skinny_tn_partial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
     if (r == 8) {
-        skinny_tn_partial_kernel<8><<<grid, 128, 0, s>>>(L, ldl, Rm, ldr, workspace, M, N, rows_per_split);
+        skinny_tn_partial_kernel<8><<<grid, SK_THREADS, smem, s>>>(L, ldl, Rm, ldr, workspace, M, N, rows_per_split);
         skinny_tn_reduce_kernel<8><<<(N * 8 + 255) / 256, 256, 0, s>>>(workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate);
     } else {
-        skinny_tn_partial_kernel<16><<<grid, 128, 0, s>>>(L, ldl, Rm, ldr, workspace, M, N, rows_per_split);
+        skinny_tn_partial_kernel<16><<<grid, SK_THREADS, smem, s>>>(L, ldl, Rm, ldr, workspace, M, N, rows_per_split);
         skinny_tn_reduce_kernel<16><<<(N * 16 + 255) / 256, 256, 0, s>>>(workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate);
     }
     GSL_CHECK_CUDA(cudaGetLastError());

@@ -65,9 +65,8 @@ def run_case(name):
     elif epi == 4:
         aux = torch.randn(M, N, device=dev)
         out0 = torch.empty(M, N, device=dev)
-        out1 = torch.empty(M, N, device=dev, dtype=torch.half)
         want0 = ref + aux
-        want1 = want0
+        want1 = None
     elif epi == 5:
         period = 26 if M % 26 == 0 else 197
         aux = torch.randn(period, N, device=dev)

@@ -1,0 +1,52 @@
+"""Dev harness (GPU box): launch each hot kernel once at the config-2 shape (for ncu captures)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "gs-lora_b200"), ROOT]
+import torch
+from gslora import _ffi as F
+dev = "cuda"
+B, N, heads = int(os.environ.get("B", "1024")), 197, 8
+M, D, H = B * N, 512, 2048
+torch.manual_seed(0)
+what = sys.argv[1:] or ["gelu", "res", "f16", "attn", "skinny"]
+reps = int(os.environ.get("REPS", "1"))
+def timeit(fn, name, flops=None, bytes_=None):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    extra = (f" {flops/ms/1e9:.0f} TFLOP/s" if flops else "") + (f" {bytes_/ms/1e6:.0f} GB/s" if bytes_ else "")
+    print(f"{name}: {ms:.3f} ms{extra}", flush=True)
+if "gelu" in what:
+    A = (torch.randn(M, D + 16, device=dev) * 0.5).half(); W = (torch.randn(H, D + 16, device=dev) * 0.05).half(); bias = torch.randn(H, device=dev)
+    o0 = torch.empty(M, H, device=dev, dtype=torch.half); o1 = torch.empty(M, H + 16, device=dev, dtype=torch.half)
+    timeit(lambda: F.gemm_f16(A, W, epi=F.EPI_GELU, bias=bias, out0=o0, out1=o1, N=H), "fc1 GELU gemm", flops=2.0 * M * H * (D + 16))
+    dy = (torch.randn(M, D + 16, device=dev) * 0.5).half(); WT = (torch.randn(H, D + 16, device=dev) * 0.05).half()
+    timeit(lambda: F.gemm_f16(dy, WT, epi=F.EPI_GELU_BWD, out0=o1, aux=o0, N=H), "dH GELU' gemm", flops=2.0 * M * H * (D + 16))
+    del A, W, o0, o1, dy, WT
+if "res" in what:
+    G = (torch.randn(M, H + 16, device=dev) * 0.5).half(); W2 = (torch.randn(D, H + 16, device=dev) * 0.05).half(); bias = torch.randn(D, device=dev)
+    x = torch.randn(M, D, device=dev); y = torch.empty(M, D, device=dev)
+    timeit(lambda: F.gemm_f16(G, W2, epi=F.EPI_RES_F32, bias=bias, out0=y, aux=x), "fc2 RES gemm", flops=2.0 * M * D * (H + 16))
+    timeit(lambda: F.gemm_f16(G, W2, epi=F.EPI_F32, out0=y), "dXn F32 gemm (K=2064)", flops=2.0 * M * D * (H + 16))
+    del G, W2, x, y
+if "f16" in what:
+    xn = (torch.randn(M, D, device=dev) * 0.5).half(); Wq = (torch.randn(3 * D, D, device=dev) * 0.05).half()
+    qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.half)
+    timeit(lambda: F.gemm_f16(xn, Wq, epi=F.EPI_F16, out0=qkv), "QKV F16 gemm", flops=2.0 * M * 3 * D * D)
+    del xn, Wq, qkv
+if "attn" in what:
+    qkv = torch.randn(M, 3 * D, device=dev).half(); out = torch.empty(M, D, device=dev, dtype=torch.half); lse = torch.empty(B * heads * N, device=dev)
+    sc = 512 ** -0.5
+    timeit(lambda: F.check(F.lib().gsl_attention_fwd(F.ptr(qkv), 3 * D, F.ptr(out), D, F.ptr(lse), B, N, heads, sc, F.cur_stream())), "attention fwd", flops=4.0 * B * heads * N * N * 64)
+    dout = torch.randn(M, D, device=dev).half(); dqkv = torch.empty(M, 3 * D, device=dev, dtype=torch.half)
+    timeit(lambda: F.check(F.lib().gsl_attention_bwd(F.ptr(qkv), 3 * D, F.ptr(out), D, F.ptr(dout), D, F.ptr(lse), F.ptr(dqkv), 3 * D, B, N, heads, sc, F.cur_stream())), "attention bwd", flops=14.0 * B * heads * N * N * 64)
+    del qkv, out, dout, dqkv
+if "skinny" in what:
+    L = torch.randn(M, H + 16, device=dev).half(); R = torch.randn(M, 16, device=dev).half()
+    nb = F.lib().gsl_skinny_tn_workspace(M, H, 8); ws = torch.empty(nb // 4 + 16, device=dev); out = torch.zeros(H, 8, device=dev)
+    timeit(lambda: F.check(F.lib().gsl_skinny_tn(F.ptr(L), H + 16, F.ptr(R), 16, F.ptr(out), 8, 0, 1.0, 0, M, H, 8, F.ptr(ws), nb, F.cur_stream())), "skinny_tn N=2048", bytes_=M * H * 2.0)
+    A16 = torch.randn(16, H, device=dev).half()
+    timeit(lambda: F.check(F.lib().gsl_lora_down(F.ptr(L), H + 16, F.ptr(A16), H, F.ptr(L[:, H:]), H + 16, M, H, 8, F.cur_stream())), "lora_down K=2048", bytes_=M * H * 2.0)
