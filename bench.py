@@ -1,0 +1,286 @@
+"""bench.py -- GS-LoRA unlearning step throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # gslora-b200 arm
+    python bench.py --impl reference [...]                         # reference arm (CPU, oracle port of the reference)
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload ("p8s8_bs512"): BASELINE.json configs[1] -- ViT-P8S8 (112 px, patch 8, dim 512, depth 6, heads 8, mlp 2048), CASIA-100 head,
+LoRA r = 8 on every FFN Linear; one step = engine_cl.py:59-125: forward(remain 512) + forward(forget 512) -> CE, relu(BND - CE_f),
+group-lasso structure loss -> selective backward (LoRA grads only) -> [NCCL allreduce of the flat LoRA gradient] -> AdamW.
+Synthetic data (torch.rand images, random labels), seeded synthetic weights.  images/s = (512 + 512) * N / t_step.
+`value`: inputs resident in HBM.  `e2e`: the same step through the public API (engine_cl.unlearn_step) from pinned HOST
+buffers: the H2D copy of both batches and the D2H read of the step's loss scalars are inside the timed region.
+Dropout: the reference trains ViT-P8S8 with dropout 0.1; the round-1 kernels run the step with dropout 0 (stated in `config`).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "gs-lora_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+BATCH = 512          # per stream (remain and forget each) per GPU
+HP = dict(lr=1e-2, wd=0.05, beta=0.15, alpha=1e-4, BND=105.0)      # scripts/run_cl_forget.sh:225-233
+METRIC = "unlearn-step images/sec ViT-P8S8 112px bs512"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], burst=d["bf16_tflops"], sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max((float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=0.0)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(self.rows))
+
+
+FLOPS_PER_IMAGE = 15.648e9     # fwd 8.049 G + selective bwd 7.599 G, ViT-P8S8 d6 r8 (2mnk per GEMM)
+
+
+class P8S8:
+    image_size, patch_size, dim, depth, heads, mlp_dim, num_class, lora_rank, tokens = 112, 8, 512, 6, 8, 2048, 100, 8, 197
+
+
+def build_model(device):
+    """ViT-P8S8 with module-default random init under SEED 1337 (config.py:8); lora_B ~ N(0, 0.02) so both LoRA factors are live."""
+    import loralib as lora
+    from vit_pytorch_face import ViT_face
+    torch.manual_seed(1337)
+    m = ViT_face(loss_type="CosFace", GPU_ID=[0], num_class=100, image_size=112, patch_size=8, dim=512, depth=6, heads=8, mlp_dim=2048,
+                 dropout=0.0, emb_dropout=0.0, lora_rank=8)
+    with torch.no_grad():
+        m.pos_embedding.mul_(0.02)
+        m.cls_token.mul_(0.02)
+        for fc1, fc2 in m.lora_layers():
+            fc1.lora_B.normal_(0, 0.02)
+            fc2.lora_B.normal_(0, 0.02)
+    lora.mark_only_lora_as_trainable(m)
+    return m.to(device).train(), P8S8
+
+
+def run_gslora(args):
+    import torch.distributed as dist
+    import engine_cl
+    from gslora import _ffi as F
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- gslora-b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model, cfg = build_model(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    S = cfg.image_size
+    host = [torch.rand(BATCH, 3, S, S, generator=g).pin_memory(), torch.randint(0, 100, (BATCH,), generator=g).pin_memory(),
+            torch.rand(BATCH, 3, S, S, generator=g).pin_memory(), torch.randint(0, 100, (BATCH,), generator=g).pin_memory()]
+    devt = [t.to(dev) for t in host]
+    step_kw = dict(beta=HP["beta"], alpha=HP["alpha"], BND=HP["BND"], hparams=dict(lr=HP["lr"], wd=HP["wd"]))
+
+    def step_resident():
+        return engine_cl.unlearn_step(model, devt[0], devt[1], devt[2], devt[3], **step_kw)
+
+    def step_e2e():
+        xr, yr, xf, yf = [t.to(dev, non_blocking=True) for t in host]
+        return engine_cl.unlearn_step(model, xr, yr, xf, yf, **step_kw)     # ends with the D2H copy of the loss scalars
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = F.lib().gsl_launch_count()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = (F.lib().gsl_launch_count() - n0) // steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, out
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches, out = timed(step_resident, args.steps, args.warmup)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+
+    images = 2 * BATCH * world
+    value = images / ms * 1e3
+    e2e_value = images / ms_e2e * 1e3
+    result = None
+    if rank == 0:
+        peaks = load_peaks()
+        step_tflops = value * FLOPS_PER_IMAGE / 1e12 / world
+        roof = kernel_roofline(dev, cfg, peaks)
+        roof["step"] = dict(achieved=round(step_tflops, 1), peak=peaks["sustained"], unit="TFLOP/s", frac=round(step_tflops / peaks["sustained"], 4),
+                            note="whole step, algorithmic FLOPs per image 15.648 G (BASELINE.md section 3) vs sustained bf16 peak (" + peaks["source"] + ")")
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        result = {
+            "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": "p8s8_bs512", "model": "ViT-P8S8 depth 6 dim 512 heads 8 mlp 2048, 112x112, LoRA r=8 on FFN, CosFace 100 classes",
+                       "per_gpu_batch": "512 remain + 512 forget", "global_batch": images, "parallelism": f"dp{world}",
+                       "arithmetic": "fp16 operands, fp32 accumulate / residual stream / loss", "dropout": 0.0,
+                       "cache": "inputs_larger_than_l2 (154 MB images + >20 GB activations per step vs 126 MB L2)",
+                       "loss": out["total"]},
+            "clocks": sampler.summary(),
+            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(ms_e2e, 3), "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 7 * 4},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline(sample_batch=16, steps=2)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+
+
+def kernel_roofline(dev, cfg, peaks):
+    """Fused FFN+LoRA GEMM pair (fc1: [x | T1][W1 | sB1]^T + b1 -> H, gelu(H); fc2: [G | T2][W2 | sB2]^T + b2 + x), timed live with CUDA
+    events on the launching stream at the step's own shape (M = 1024 * 197 rows).  Algorithmic FLOPs per launch pair:
+    2 * M * (D*H*2 + 2r(D+H)); peak = measured cuBLAS bf16 burst."""
+    from gslora import _ffi as F
+    M, D, H, r = 2 * BATCH * cfg.tokens, cfg.dim, cfg.mlp_dim, cfg.lora_rank
+    x = (torch.randn(M, D + 16, device=dev) * 0.5).half()
+    w1 = (torch.randn(H, D + 16, device=dev) * 0.05).half()
+    w2 = (torch.randn(D, H + 16, device=dev) * 0.02).half()
+    b1, b2 = torch.randn(H, device=dev), torch.randn(D, device=dev)
+    h = torch.empty(M, H, device=dev, dtype=torch.half)
+    gcat = torch.empty(M, H + 16, device=dev, dtype=torch.half)
+    res = torch.randn(M, D, device=dev)
+    y = torch.empty(M, D, device=dev)
+
+    def pair():
+        F.gemm_f16(x, w1, epi=F.EPI_GELU, bias=b1, out0=h, out1=gcat, N=H)
+        F.gemm_f16(gcat, w2, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=res)
+    for _ in range(3):
+        pair()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        pair()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * M * (D * H * 2 + 2 * r * (D + H))
+    ach = flops / ms / 1e9
+    return dict(bound="tensor", kernel="gemm_tcgen05_kernel<2,256,EPI_GELU> + <2,256,EPI_RES_F32> (fused FFN+LoRA pair)", achieved=round(ach, 1),
+                peak=peaks["burst"], unit="TFLOP/s", frac=round(ach / peaks["burst"], 4), traffic=None, ms_per_launch_pair=round(ms, 4),
+                peak_source=peaks["source"] + " cuBLAS bf16 burst")
+
+
+def cpu_baseline(sample_batch=16, steps=2):
+    """The reference's CPU path (oracle port: oracle/vit_oracle.py restates vit_face.py / engine_cl.py:59-125; the reference tree itself
+    does not travel to the GPU box) on all host cores, bounded sample: bs `sample_batch`+`sample_batch`, FP32."""
+    from oracle import vit_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.P8S8
+    sd = O.init_state_dict(cfg, seed=1337)
+    g = torch.Generator().manual_seed(3)
+    B = sample_batch
+    xr, xf = torch.rand(B, 3, 112, 112, generator=g), torch.rand(B, 3, 112, 112, generator=g)
+    yr, yf = torch.randint(0, 100, (B,), generator=g), torch.randint(0, 100, (B,), generator=g)
+    state = {}
+    O.unlearn_step(sd, cfg, state, xr, yr, xf, yf, lr=HP["lr"], wd=HP["wd"], beta=HP["beta"], alpha=HP["alpha"], BND=HP["BND"])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.unlearn_step(sd, cfg, state, xr, yr, xf, yf, lr=HP["lr"], wd=HP["wd"], beta=HP["beta"], alpha=HP["alpha"], BND=HP["BND"])
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=round(2 * B / dt, 2), unit="images/s", cores=cores, kind="port",
+                sample=f"oracle port of the reference step (PyTorch FP32 eager, dropout 0), bs {B}+{B}, 1 warm-up + {steps} timed steps, {dt:.2f} s/step")
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, via the oracle port, on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 16
+    steps = max(1, min(args.steps, 3))
+    cb = cpu_baseline(sample_batch=B, steps=steps)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+           "warmup": 1, "ms_per_step": round(2 * B / cb["value"] * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "p8s8_bs512", "sample": f"bs {B}+{B} per step (bounded sample of the 512+512 workload)", "device": "host CPU"},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gslora", choices=["gslora", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "gslora":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gslora(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,7 +5,10 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <atomic>
+
 namespace gsl {
+std::atomic<long long> g_launches{0};
 static thread_local char g_err[1024] = "";
 void set_last_error(const char* fmt, ...) {
     va_list ap;
@@ -21,6 +24,7 @@ extern "C" {
 
 const char* gsl_last_error(void) { return g_err; }
 int gsl_version(void) { return 100; }
+long long gsl_launch_count(void) { return g_launches.load(); }
 void gsl_set_gemm_cta_group(int cta_group) { gemm_set_default_cta_group(cta_group); }
 
 int gsl_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K, int epi,

@@ -217,6 +217,7 @@ int attention_fwd(const __half* qkv, int64_t ld, __half* out, int64_t ldo, float
         attr = true;
     }
     attention_fwd_kernel<<<attention_grid(B * heads), ATT_WARPS * 32, smem, s>>>(tm, out, ldo, lse, B, N, heads, scale);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -464,6 +465,7 @@ int attention_bwd(const __half* qkv, int64_t ld, const __half* out, int64_t ldo,
         attr = true;
     }
     attention_bwd_kernel<<<attention_grid(B * heads), ATT_WARPS * 32, smem, s>>>(tq, td, out, ldo, lse, dqkv, lddqkv, B, N, heads, scale);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -16,6 +16,11 @@ namespace gsl {
 
 // ---------------------------------------------------------------- host-side error plumbing
 void set_last_error(const char* fmt, ...);
+}  // namespace gsl
+#include <atomic>
+namespace gsl {
+extern std::atomic<long long> g_launches;     // kernels launched by this library (gsl_launch_count)
+#define GSL_COUNT_LAUNCH(n) gsl::g_launches.fetch_add(n, std::memory_order_relaxed)
 #define GSL_CHECK_CUDA(expr)                                                                     \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \

@@ -187,6 +187,7 @@ int Engine::refresh_frozen(cudaStream_t s) {
     int rc;
     if ((rc = cast_f32_to_f16(patch_w, patch_dim, patch_w16, patch_dim, D, patch_dim, 1.f, 0, s))) return rc;
     posb_kernel<<<(tokens * D + 255) / 256, 256, 0, s>>>(pos_embedding, cls_token, patch_b, posb, tokens, D);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     for (int l = 0; l < cfg.depth; ++l) {
         const BlockFrozen& f = frozen[l];
@@ -392,6 +393,7 @@ __global__ void loss_sums_kernel(const float* __restrict__ ce, const int* __rest
 
 int loss_sums(const float* ce, const int* correct, int n_remain, int B, float* sums, cudaStream_t s) {
     loss_sums_kernel<<<1, 1024, 0, s>>>(ce, correct, n_remain, B, sums);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -424,6 +426,7 @@ int unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sum
                     float* dlogits, cudaStream_t s) {
     const int warps = 4;
     unlearn_ce_grad_kernel<<<(B + warps - 1) / warps, warps * 32, 0, s>>>(logits, labels, sums, n_remain_local, B, C, beta, BND, dlogits);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -483,6 +483,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     GSL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO0, tmO1, tmAux, p));
+    GSL_COUNT_LAUNCH(1);
     return 0;
 }
 

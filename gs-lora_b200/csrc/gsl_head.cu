@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(HeadArgs a) {
 int head_fwd(const HeadArgs& a, cudaStream_t s) {
     GSL_REQUIRE(a.D <= HEAD_MAX_D && a.C <= HEAD_MAX_C, "head: D=%d C=%d exceed limits", a.D, a.C);
     head_fwd_kernel<<<a.B, HEAD_THREADS, 0, s>>>(a);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -112,6 +113,7 @@ __global__ void ce_grad_kernel(const float* __restrict__ logits, const int64_t* 
 int ce_grad(const float* logits, const int64_t* labels, const float* coef_dev, float scale, float* dlogits, int B, int C, cudaStream_t s) {
     const int warps = 4;
     ce_grad_kernel<<<(B + warps - 1) / warps, warps * 32, 0, s>>>(logits, labels, coef_dev, scale, dlogits, B, C);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_bwd_kernel(HeadBwdArgs a) {
 int head_bwd(const HeadBwdArgs& a, cudaStream_t s) {
     GSL_REQUIRE(a.D <= HEAD_MAX_D && a.C <= HEAD_MAX_C, "head_bwd: D=%d C=%d exceed limits", a.D, a.C);
     head_bwd_kernel<<<a.B, HEAD_THREADS, 0, s>>>(a);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -53,6 +53,7 @@ int grouplasso_adamw_step(const OptimArgs& a, cudaStream_t s) {
     const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step);
     const double bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
     grouplasso_adamw_kernel<<<a.num_groups, 1024, 0, s>>>(a, (float)bc1, (float)sqrt(bc2));
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) tensor_norms_kernel(const float* __restri
 
 int tensor_norms(const float* params, const int* tensor_offsets, int num_tensors, int type, float* out, cudaStream_t s) {
     tensor_norms_kernel<<<num_tensors, 256, 0, s>>>(params, tensor_offsets, type, out);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -43,6 +43,7 @@ int patchify_f16(const float* img, __half* out, int64_t ld, int B, int C, int S,
     const int cap = device_sm_count() * 16;
     if (blocks > cap) blocks = cap;
     patchify_kernel<<<blocks, threads, 0, s>>>(img, out, ld, B, C, S, patch, order);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -102,6 +103,7 @@ int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* 
         GSL_LN_CASE(1) GSL_LN_CASE(2) GSL_LN_CASE(3) GSL_LN_CASE(4) GSL_LN_CASE(5) GSL_LN_CASE(6) GSL_LN_CASE(7) GSL_LN_CASE(8)
     }
 #undef GSL_LN_CASE
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -170,6 +172,7 @@ int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, co
         GSL_LN_CASE(1) GSL_LN_CASE(2) GSL_LN_CASE(3) GSL_LN_CASE(4) GSL_LN_CASE(5) GSL_LN_CASE(6) GSL_LN_CASE(7) GSL_LN_CASE(8)
     }
 #undef GSL_LN_CASE
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -264,6 +267,7 @@ int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __ha
     const int blocks = (int)((groups + warps - 1) / warps);
     if (r == 8) lora_down_kernel<1><<<blocks, warps * 32, 0, s>>>(X, ldx, A16, lda, out, ldo, M, K);
     else lora_down_kernel<2><<<blocks, warps * 32, 0, s>>>(X, ldx, A16, lda, out, ldo, M, K);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -420,10 +424,14 @@ int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float
     }
     if (r == 8) {
         skinny_tn_partial_kernel<8><<<grid, SK_THREADS, smem, s>>>(L, ldl, Rm, ldr, workspace, M, N, rows_per_split);
+        GSL_COUNT_LAUNCH(1);
         skinny_tn_reduce_kernel<8><<<(N * 8 + 255) / 256, 256, 0, s>>>(workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate);
+        GSL_COUNT_LAUNCH(1);
     } else {
         skinny_tn_partial_kernel<16><<<grid, SK_THREADS, smem, s>>>(L, ldl, Rm, ldr, workspace, M, N, rows_per_split);
+        GSL_COUNT_LAUNCH(1);
         skinny_tn_reduce_kernel<16><<<(N * 16 + 255) / 256, 256, 0, s>>>(workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate);
+        GSL_COUNT_LAUNCH(1);
     }
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -448,6 +456,7 @@ int cast_f32_to_f16(const float* src, int64_t lds, __half* dst, int64_t ldd, int
     const int cap = device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     cast_kernel<<<blocks, 256, 0, s>>>(src, lds, dst, ldd, rows, cols, scale, transpose);
+    GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -41,6 +41,7 @@ NUM_GLOBAL_PARAMS, NUM_BLOCK_PARAMS = 7, 12
 def _declare(L):
     L.gsl_last_error.restype = ctypes.c_char_p
     L.gsl_version.restype = c_int
+    L.gsl_launch_count.restype = ctypes.c_longlong
     L.gsl_set_gemm_cta_group.argtypes = [c_int]
     L.gsl_gemm_f16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p,
                                c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]
@@ -84,7 +85,7 @@ def _declare(L):
     L.gsl_engine_lora_numel.restype = c_int64
 
 
-EXPORTS = ["gsl_last_error", "gsl_version", "gsl_set_gemm_cta_group", "gsl_gemm_f16", "gsl_patchify_f16", "gsl_layernorm_fwd",
+EXPORTS = ["gsl_last_error", "gsl_version", "gsl_launch_count", "gsl_set_gemm_cta_group", "gsl_gemm_f16", "gsl_patchify_f16", "gsl_layernorm_fwd",
            "gsl_layernorm_bwd", "gsl_lora_down", "gsl_skinny_tn_workspace", "gsl_skinny_tn", "gsl_attention_fwd", "gsl_attention_bwd",
            "gsl_cast_f32_to_f16", "gsl_grouplasso_adamw_step", "gsl_tensor_norms", "gsl_engine_workspace_bytes", "gsl_engine_create",
            "gsl_engine_destroy", "gsl_engine_bind_params", "gsl_engine_refresh_frozen", "gsl_engine_refresh_lora", "gsl_engine_forward",

@@ -19,6 +19,8 @@ extern "C" {
 
 const char* gsl_last_error(void);
 int gsl_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+long long gsl_launch_count(void);
 /* default tcgen05 cta_group (1 or 2) for the GEMM family */
 void gsl_set_gemm_cta_group(int cta_group);
 

@@ -1,0 +1,146 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/gslora.h declares, the drop-in module
+surface matches the reference's (state_dict names, loralib merge semantics, freezing), and the data-parallel formulation
+(all-reduced loss sums -> per-sample weights -> summed LoRA gradients) equals the single-process step, checked with
+two gloo ranks."""
+import copy
+import os
+import re
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import vit_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    from gslora import _ffi
+    L = _ffi.lib()
+    header = open(os.path.join(ROOT, "include", "gslora.h")).read()
+    declared = set(re.findall(r"\b(gsl_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"libgslora.so does not export {name}"
+    assert set(_ffi.EXPORTS) == declared
+    assert L.gsl_version() >= 100
+    # workspace sizing is host arithmetic and must work without a device
+    import ctypes
+    cfg = _ffi.GslConfig(image_size=112, patch_size=8, channels=3, dim=512, depth=6, heads=8, mlp_dim=2048, num_class=100, lora_rank=8,
+                         max_batch=64, num_slots=2, patch_order=0, attn_scale=512 ** -0.5, ln_eps=1e-5, cos_s=64, cos_m=0.35,
+                         lora_scaling=0.125, grad_scale=1024)
+    assert L.gsl_engine_workspace_bytes(ctypes.byref(cfg)) > 1 << 28
+    bad = _ffi.GslConfig(image_size=112, patch_size=8, channels=3, dim=500, depth=6, heads=8, mlp_dim=2048, num_class=100, lora_rank=8,
+                         max_batch=64, num_slots=2)
+    assert L.gsl_engine_workspace_bytes(ctypes.byref(bad)) == 0 and b"dim" in L.gsl_last_error()
+
+
+def make_model(cfg=O.TINY, **kw):
+    from vit_pytorch_face import ViT_face
+    return ViT_face(loss_type="CosFace", GPU_ID=[0], num_class=cfg.num_class, image_size=cfg.image_size, patch_size=cfg.patch_size,
+                    dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp_dim=cfg.mlp_dim, lora_rank=cfg.lora_rank, **kw)
+
+
+def test_state_dict_names_and_counts_match_reference_surface():
+    import loralib as lora
+    m = make_model(O.P8S8, dropout=0.1, emb_dropout=0.1)
+    sd = O.init_state_dict(O.P8S8)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    assert sum(p.numel() for p in m.parameters()) == 19403264                 # SURVEY 8b [probed]
+    lora.mark_only_lora_as_trainable(m)
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 245760  # train_own_forget_cl.py:483 ratio
+    assert all(("lora_" in n) == p.requires_grad for n, p in m.named_parameters())
+    assert m.load_state_dict(sd, strict=True).missing_keys == []
+
+
+def test_loralib_merge_unmerge_semantics():
+    import loralib as lora
+    torch.manual_seed(0)
+    lin = lora.Linear(32, 48, r=8)
+    assert lin.scaling == 1 / 8 and not lin.weight.requires_grad and lin.lora_A.shape == (8, 32) and lin.lora_B.shape == (48, 8)
+    assert torch.count_nonzero(lin.lora_B) == 0                                # loralib init: B = 0, A kaiming
+    with torch.no_grad():
+        lin.lora_B.normal_()
+    w0 = lin.weight.detach().clone()
+    gen = lin._gsl_generation
+    lin.eval()
+    assert lin.merged and torch.allclose(lin.weight, w0 + (lin.lora_B @ lin.lora_A) / 8, atol=1e-6) and lin._gsl_generation == gen + 1
+    lin.eval()
+    assert lin._gsl_generation == gen + 1                                      # idempotent
+    lin.train()
+    assert not lin.merged and torch.allclose(lin.weight, w0, atol=1e-6)
+    ml = lora.MergedLinear(32, 96, r=0, enable_lora=[True, True, True], bias=False)
+    assert ml.bias is None and not hasattr(ml, "lora_A")
+    with pytest.raises(NotImplementedError):
+        lora.MergedLinear(32, 96, r=8, enable_lora=[True, True, True])
+
+
+def test_model_is_a_regular_module_and_refuses_cpu_execution():
+    from gslora import _ffi
+    m = make_model()
+    c = copy.deepcopy(m)
+    assert c is not m and c._engine is None
+    assert "ViT_face" in repr(m) and "CosFace" in repr(m)
+    m.eval(); m.train()
+    with pytest.raises(_ffi.GslError):
+        m(torch.rand(2, 3, 40, 40))
+    with pytest.raises(RuntimeError):
+        m.transformer(torch.rand(1, 26, 128))
+
+
+def test_cal_norm_groupings():
+    from util import cal_norm
+    assert len(cal_norm._ffn_groups(6, "block")) == 6 and len(cal_norm._ffn_groups(6, "lora")) == 12 and len(cal_norm._ffn_groups(6, "matrix")) == 24
+    assert cal_norm._ffn_groups(2, "block")[1] == [(1, 0), (1, 1), (1, 2), (1, 3)]
+
+
+# ---------------------------------------------------------------------------------------------- data parallel (gloo, 2 ranks)
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    import torch.nn.functional as Fn
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    cfg = O.TINY
+    sd = O.init_state_dict(cfg, seed=21)
+    g = torch.Generator().manual_seed(22)
+    Bg = 6
+    xr, xf = torch.rand(Bg, 3, 40, 40, generator=g), torch.rand(Bg, 3, 40, 40, generator=g)
+    yr, yf = torch.randint(0, 10, (Bg,), generator=g), torch.randint(0, 10, (Bg,), generator=g)
+    beta, BND = 0.15, 105.0
+    sl = slice(rank, Bg, world)                                  # rank-strided slices of the global batches
+    names = O.lora_param_list(cfg)
+    work = {k: v.clone() for k, v in sd.items()}
+    for n in names:
+        work[n].requires_grad_(True)
+    lr_, _ = O.vit_forward(work, cfg, xr[sl], yr[sl])
+    lf_, _ = O.vit_forward(work, cfg, xf[sl], yf[sl])
+    ce_r, ce_f = Fn.cross_entropy(lr_, yr[sl], reduction="none"), Fn.cross_entropy(lf_, yf[sl], reduction="none")
+    sums = torch.tensor([ce_r.sum().item(), float(len(ce_r)), ce_f.sum().item(), float(len(ce_f))])
+    dist.all_reduce(sums)                                        # what engine_cl.unlearn_step does with gsl_loss_sums' output
+    gate = 1.0 if sums[2] / sums[3] < BND else 0.0
+    local = ce_r.sum() / sums[1] - beta * gate * ce_f.sum() / sums[3]   # per-sample weights of gsl_unlearn_ce_grad
+    grads = torch.autograd.grad(local, [work[n] for n in names])
+    flat = torch.cat([t.flatten() for t in grads])
+    dist.all_reduce(flat)                                        # the one flat LoRA-gradient allreduce
+    if rank == 0:
+        _, ref = O.unlearn_grads(sd, cfg, xr, yr, xf, yf, beta, 0.0, BND, include_structure=False)
+        want = torch.cat([ref[n].flatten() for n in names])
+        ret["rel"] = float((flat - want).norm() / want.norm())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_formulation_two_gloo_ranks():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dp_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret["rel"] < 1e-5, ret["rel"]
