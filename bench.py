@@ -184,7 +184,7 @@ def run_gslora(args):
             "roofline": roof,
         }
         if world == 1 and not args.no_cpu_baseline:
-            result["cpu_baseline"] = cpu_baseline(sample_batch=16, steps=2)
+            result["cpu_baseline"] = cpu_baseline(sample_batch=96, steps=3)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -255,7 +255,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = 16
+    B = 96
     steps = max(1, min(args.steps, 3))
     cb = cpu_baseline(sample_batch=B, steps=steps)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
