@@ -11,6 +11,7 @@
 //   pass A  per 16-query tile : S, P, dP = dO V^T, dS = P (dP - delta)      -> dQ = scale * dS K
 //   pass B  per 16-key tile   : S^T, P^T, dP^T                              -> dV = P^T dO, dK = scale * dS^T Q
 #include "gsl_common.cuh"
+#include <stdlib.h>
 #include <cuda.h>
 #include "gsl_kernels.h"
 
@@ -203,7 +204,17 @@ static int attention_grid(int nwork) {
     return nwork < sms ? nwork : sms;
 }
 
+int attention_fwd_tc(const __half* qkv, int64_t ld, __half* out, int64_t ldo, float* lse, int B, int N, int heads, float scale, cudaStream_t s);
+
+// GSLORA_ATTN=mma selects the mma.sync kernels below; the default is the tcgen05 forward (gsl_attention_tc.cu)
+static bool attention_use_tc() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("GSLORA_ATTN"); mode = (e && e[0] == 'm') ? 0 : 1; }
+    return mode == 1;
+}
+
 int attention_fwd(const __half* qkv, int64_t ld, __half* out, int64_t ldo, float* lse, int B, int N, int heads, float scale, cudaStream_t s) {
+    if (attention_use_tc()) return attention_fwd_tc(qkv, ld, out, ldo, lse, B, N, heads, scale, s);
     GSL_REQUIRE(N >= 1 && N <= ATT_MAX_TOKENS, "attention: tokens=%d outside [1, %d]", N, ATT_MAX_TOKENS);
     GSL_REQUIRE(ld % 8 == 0 && ldo % 2 == 0, "attention: qkv pitch must be a multiple of 8 halves");
     const int npad = (N + 15) & ~15;
@@ -448,8 +459,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   }
 }
 
+int attention_bwd_tc(const __half* qkv, int64_t ld, const __half* out, int64_t ldo, const __half* dout, int64_t lddo, const float* lse,
+                     __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s);
+
 int attention_bwd(const __half* qkv, int64_t ld, const __half* out, int64_t ldo, const __half* dout, int64_t lddo, const float* lse,
                   __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s) {
+    if (attention_use_tc()) return attention_bwd_tc(qkv, ld, out, ldo, dout, lddo, lse, dqkv, lddqkv, B, N, heads, scale, s);
     GSL_REQUIRE(N >= 1 && N <= ATT_MAX_TOKENS, "attention_bwd: tokens=%d outside [1, %d]", N, ATT_MAX_TOKENS);
     GSL_REQUIRE(ld % 8 == 0 && lddo % 8 == 0 && ldo % 2 == 0 && lddqkv % 2 == 0, "attention_bwd: pitches must be multiples of 8 halves");
     const int npad = (N + 15) & ~15;
