@@ -10,7 +10,7 @@ group-lasso structure loss -> selective backward (LoRA grads only) -> [NCCL allr
 Synthetic data (torch.rand images, random labels), seeded synthetic weights.  images/s = (512 + 512) * N / t_step.
 `value`: inputs resident in HBM.  `e2e`: the same step through the public API (engine_cl.unlearn_step) from pinned HOST
 buffers: the H2D copy of both batches and the D2H read of the step's loss scalars are inside the timed region.
-Dropout: the reference trains ViT-P8S8 with dropout 0.1; the round-1 kernels run the step with dropout 0 (stated in `config`).
+Dropout 0.1 / emb_dropout 0.1 as in the reference's ViT-P8S8 construction (train/train_own_forget_cl.py:217-218), train mode.
 """
 import argparse
 import json
@@ -28,6 +28,7 @@ for p in (os.path.join(ROOT, "gs-lora_b200"), ROOT):
 import torch  # noqa: E402
 
 BATCH = 512          # per stream (remain and forget each) per GPU
+DROPOUT = 0.1        # train/train_own_forget_cl.py:217-218
 HP = dict(lr=1e-2, wd=0.05, beta=0.15, alpha=1e-4, BND=105.0)      # scripts/run_cl_forget.sh:225-233
 METRIC = "unlearn-step images/sec ViT-P8S8 112px bs512"
 
@@ -86,7 +87,7 @@ def build_model(device):
     from vit_pytorch_face import ViT_face
     torch.manual_seed(1337)
     m = ViT_face(loss_type="CosFace", GPU_ID=[0], num_class=100, image_size=112, patch_size=8, dim=512, depth=6, heads=8, mlp_dim=2048,
-                 dropout=0.0, emb_dropout=0.0, lora_rank=8)
+                 dropout=DROPOUT, emb_dropout=DROPOUT, lora_rank=8)
     with torch.no_grad():
         m.pos_embedding.mul_(0.02)
         m.cls_token.mul_(0.02)
@@ -174,7 +175,7 @@ def run_gslora(args):
             "data": "synthetic",
             "config": {"workload": "p8s8_bs512", "model": "ViT-P8S8 depth 6 dim 512 heads 8 mlp 2048, 112x112, LoRA r=8 on FFN, CosFace 100 classes",
                        "per_gpu_batch": "512 remain + 512 forget", "global_batch": images, "parallelism": f"dp{world}",
-                       "arithmetic": "fp16 operands, fp32 accumulate / residual stream / loss", "dropout": 0.0,
+                       "arithmetic": "fp16 operands, fp32 accumulate / residual stream / loss", "dropout": DROPOUT,
                        "cache": "inputs_larger_than_l2 (154 MB images + >20 GB activations per step vs 126 MB L2)",
                        "loss": out["total"]},
             "clocks": sampler.summary(),

@@ -29,13 +29,13 @@ void gsl_set_gemm_cta_group(int cta_group) { gemm_set_default_cta_group(cta_grou
 
 int gsl_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K, int epi,
                  const float* bias, void* out0, int64_t ld0, void* out1, int64_t ld1, const void* aux, int64_t ldaux,
-                 int64_t aux_period, int cta_group, int block_n, void* stream) {
+                 int64_t aux_period, int cta_group, int block_n, float drop_p, uint32_t drop_seed, void* stream) {
     GemmArgs a;
     a.A = (const __half*)A; a.lda = lda; a.B = (const __half*)B; a.ldb = ldb;
     a.M = M; a.N = N; a.K = K; a.epi = epi; a.bias = bias;
     a.out0 = out0; a.ld0 = ld0; a.out1 = out1; a.ld1 = ld1;
     a.aux = aux; a.ldaux = ldaux; a.aux_period = aux_period;
-    a.cta_group = cta_group; a.block_n = block_n;
+    a.cta_group = cta_group; a.block_n = block_n; a.drop_p = drop_p; a.drop_seed = drop_seed;
     return gemm_f16(a, (cudaStream_t)stream);
 }
 
@@ -51,7 +51,7 @@ int gsl_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const flo
 }
 int gsl_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
                       const float* dres, int64_t lddres, float* dx, int64_t lddx, void* dx16, int64_t lddx16, int64_t M, int D, void* stream) {
-    return layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__half*)dx16, lddx16, M, D, ST(stream));
+    return layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__half*)dx16, lddx16, M, D, 0.f, 0u, ST(stream));
 }
 int gsl_lora_down(const void* X16, int64_t ldx, const void* A16, int64_t lda, void* out16, int64_t ldo, int64_t M, int K, int r, void* stream) {
     return lora_down((const __half*)X16, ldx, (const __half*)A16, lda, (__half*)out16, ldo, M, K, r, ST(stream));
@@ -101,8 +101,9 @@ int gsl_engine_bind_params(void* handle, const void* const* frozen_ptrs, int num
 }
 int gsl_engine_refresh_frozen(void* handle, void* stream) { return ((Engine*)handle)->refresh_frozen(ST(stream)); }
 int gsl_engine_refresh_lora(void* handle, void* stream) { return ((Engine*)handle)->refresh_lora(ST(stream)); }
-int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* labels, int B, int use_lora, void* stream) {
-    return ((Engine*)handle)->forward(slot, img, labels, B, use_lora, ST(stream));
+int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* labels, int B, int use_lora, uint64_t dropout_seed,
+                       void* stream) {
+    return ((Engine*)handle)->forward(slot, img, labels, B, use_lora, dropout_seed, ST(stream));
 }
 int gsl_engine_backward(void* handle, int slot, const float* dlogits, const float* demb, int accumulate, void* stream) {
     return ((Engine*)handle)->backward(slot, dlogits, demb, accumulate, ST(stream));

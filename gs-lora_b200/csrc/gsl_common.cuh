@@ -286,6 +286,22 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {                // Phi
     return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
+// Counter-based dropout mask (nn.Dropout of the reference: vit_face.py:332,334,356,489).  One 32-bit hash per PAIR of
+// consecutive elements (murmur3 finalizer of pair index ^ seed), 16 bits each: keep iff bits >= p * 65536.  The forward and the
+// backward regenerate the same mask from (seed, row * width + col); nothing is stored.  torch's Philox stream cannot be
+// reproduced bit-for-bit, so parity tests replay this hash on the host (tests/dropout_ref.py) and feed the masks to the oracle.
+__device__ __host__ __forceinline__ uint32_t drop_hash(uint32_t pair, uint32_t seed) {
+    uint32_t h = pair * 0x9E3779B1u ^ seed;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+// scale factors (0 or 1/(1-p)) for elements e and e+1, e even
+__device__ __forceinline__ void drop_pair(uint32_t e, uint32_t seed, uint32_t thresh16, float keep_scale, float& s0, float& s1) {
+    const uint32_t h = drop_hash(e >> 1, seed);
+    s0 = (h & 0xFFFFu) >= thresh16 ? keep_scale : 0.f;
+    s1 = (h >> 16) >= thresh16 ? keep_scale : 0.f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -96,10 +96,11 @@ size_t Engine::carve(bool assign) {
     auto* t_to = (int*)take((size_t)(4 * L + 1) * 4);
     auto* t_gn = (float*)take((size_t)L * 4);
     auto* t_tn = (float*)take((size_t)4 * L * 4);
+    auto* t_pp = (void*)take((size_t)L * 8 * sizeof(void*));
     if (assign) {
         patches16 = t_patches; xn16 = t_xn; dxcat16 = t_dxcat; dhcat16 = t_dhcat; do16 = t_do; dqkv16 = t_dqkv;
         dx32 = t_dx32; dxn32 = t_dxn32; skinny_ws = t_sk; skinny_ws_bytes = sk;
-        group_offsets_dev = t_go; tensor_offsets_dev = t_to; group_norms_dev = t_gn; tensor_norms_dev = t_tn;
+        group_offsets_dev = t_go; tensor_offsets_dev = t_to; group_norms_dev = t_gn; tensor_norms_dev = t_tn; pack_ptrs_dev = t_pp;
     }
     return align_up(off, 1024);
 }
@@ -147,6 +148,13 @@ int Engine::init(const GslConfig& c, void* workspace, size_t bytes) {
     to[4 * c.depth] = (int)(c.depth * lora_block_elems());
     GSL_CHECK_CUDA(cudaMemcpy(group_offsets_dev, go.data(), go.size() * 4, cudaMemcpyHostToDevice));
     GSL_CHECK_CUDA(cudaMemcpy(tensor_offsets_dev, to.data(), to.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<void*> pp;
+    for (int l = 0; l < c.depth; ++l) {
+        const BlockCache& bc = cache[l];
+        void* row[8] = {bc.A1h, bc.A2h, bc.B1T, bc.B2T, bc.fc1_cat, bc.fc1T_cat, bc.fc2_cat, bc.fc2T_cat};
+        pp.insert(pp.end(), row, row + 8);
+    }
+    GSL_CHECK_CUDA(cudaMemcpy(pack_ptrs_dev, pp.data(), pp.size() * sizeof(void*), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -196,6 +204,10 @@ int Engine::refresh_frozen(cudaStream_t s) {
         if ((rc = cast_f32_to_f16(f.qkv_w, D, c.qkv_wT16, 3 * inner, 3 * inner, D, 1.f, 1, s))) return rc;
         if ((rc = cast_f32_to_f16(f.out_w, inner, c.out_w16, inner, D, inner, 1.f, 0, s))) return rc;
         if ((rc = cast_f32_to_f16(f.out_w, inner, c.out_wT16, D, D, inner, 1.f, 1, s))) return rc;
+        if ((rc = fill_zero(c.A1h, (size_t)16 * D * 2, s))) return rc;
+        if ((rc = fill_zero(c.A2h, (size_t)16 * H * 2, s))) return rc;
+        if ((rc = fill_zero(c.B1T, (size_t)16 * H * 2, s))) return rc;
+        if ((rc = fill_zero(c.B2T, (size_t)16 * D * 2, s))) return rc;
         if ((rc = fill_zero(c.fc1_cat, (size_t)H * (D + 16) * 2, s))) return rc;
         if ((rc = fill_zero(c.fc1T_cat, (size_t)D * (H + 16) * 2, s))) return rc;
         if ((rc = fill_zero(c.fc2_cat, (size_t)D * (H + 16) * 2, s))) return rc;
@@ -208,37 +220,63 @@ int Engine::refresh_frozen(cudaStream_t s) {
     return refresh_lora(s);
 }
 
+// One launch repacks every fp16 LoRA operand of every block from the flat fp32 parameter buffer:
+//   A1h/A2h = lora_A, B1T/B2T = lora_B^T (skinny products), and the K-extension columns  s*B -> [W | sB],  s*A^T -> [W^T | sA^T].
+struct LoraPackPtrs {
+    __half *A1h, *A2h, *B1T, *B2T, *fc1_cat, *fc1T_cat, *fc2_cat, *fc2T_cat;
+};
+__global__ void lora_pack_kernel(const float* __restrict__ flat, const LoraPackPtrs* __restrict__ ptrs, int D, int H, int r, float sc, int per_block) {
+    const int l = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per_block) return;
+    const LoraPackPtrs p = ptrs[l];
+    const float v = flat[(int64_t)l * per_block + i];
+    const __half hv = __float2half_rn(v), hs = __float2half_rn(v * sc);
+    int k = i;
+    if (k < r * D) {                       // lora_A(net.0) [r, D]
+        const int j = k / D, d = k % D;
+        p.A1h[(int64_t)j * D + d] = hv;
+        p.fc1T_cat[(int64_t)d * (H + 16) + H + j] = hs;
+        return;
+    }
+    k -= r * D;
+    if (k < H * r) {                       // lora_B(net.0) [H, r]
+        const int h = k / r, j = k % r;
+        p.B1T[(int64_t)j * H + h] = hv;
+        p.fc1_cat[(int64_t)h * (D + 16) + D + j] = hs;
+        return;
+    }
+    k -= H * r;
+    if (k < r * H) {                       // lora_A(net.3) [r, H]
+        const int j = k / H, h = k % H;
+        p.A2h[(int64_t)j * H + h] = hv;
+        p.fc2T_cat[(int64_t)h * (D + 16) + D + j] = hs;
+        return;
+    }
+    k -= r * H;
+    {                                      // lora_B(net.3) [D, r]
+        const int d = k / r, j = k % r;
+        p.B2T[(int64_t)j * D + d] = hv;
+        p.fc2_cat[(int64_t)d * (H + 16) + H + j] = hs;
+    }
+}
+
 int Engine::refresh_lora(cudaStream_t s) {
     GSL_REQUIRE(params_bound, "bind_params first");
-    const int D = cfg.dim, H = cfg.mlp_dim, r = cfg.lora_rank;
-    const float sc = cfg.lora_scaling;
-    int rc;
-    for (int l = 0; l < cfg.depth; ++l) {
-        BlockCache& c = cache[l];
-        const float* A1 = lora_flat + lora_offset(l, 0);   // [r, D]
-        const float* B1 = lora_flat + lora_offset(l, 1);   // [H, r]
-        const float* A2 = lora_flat + lora_offset(l, 2);   // [r, H]
-        const float* B2 = lora_flat + lora_offset(l, 3);   // [D, r]
-        if (r < 16) {
-            if ((rc = fill_zero(c.A1h, (size_t)16 * D * 2, s))) return rc;
-            if ((rc = fill_zero(c.A2h, (size_t)16 * H * 2, s))) return rc;
-            if ((rc = fill_zero(c.B1T, (size_t)16 * H * 2, s))) return rc;
-            if ((rc = fill_zero(c.B2T, (size_t)16 * D * 2, s))) return rc;
-        }
-        if ((rc = cast_f32_to_f16(A1, D, c.A1h, D, r, D, 1.f, 0, s))) return rc;
-        if ((rc = cast_f32_to_f16(A2, H, c.A2h, H, r, H, 1.f, 0, s))) return rc;
-        if ((rc = cast_f32_to_f16(B1, r, c.B1T, H, H, r, 1.f, 1, s))) return rc;
-        if ((rc = cast_f32_to_f16(B2, r, c.B2T, D, D, r, 1.f, 1, s))) return rc;
-        // K-extension columns of the concatenated operands (columns [r, 16) stay zero from refresh_frozen)
-        if ((rc = cast_f32_to_f16(B1, r, c.fc1_cat + D, D + 16, H, r, sc, 0, s))) return rc;       // s*B1   -> fc1_cat[:, D:D+r]
-        if ((rc = cast_f32_to_f16(B2, r, c.fc2_cat + H, H + 16, D, r, sc, 0, s))) return rc;       // s*B2   -> fc2_cat[:, H:H+r]
-        if ((rc = cast_f32_to_f16(A1, D, c.fc1T_cat + H, H + 16, r, D, sc, 1, s))) return rc;      // s*A1^T -> fc1T_cat[:, H:H+r]
-        if ((rc = cast_f32_to_f16(A2, H, c.fc2T_cat + D, D + 16, r, H, sc, 1, s))) return rc;      // s*A2^T -> fc2T_cat[:, D:D+r]
-    }
+    const int per_block = (int)lora_block_elems();
+    dim3 grid((per_block + 255) / 256, cfg.depth);
+    lora_pack_kernel<<<grid, 256, 0, s>>>(lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, cfg.lora_scaling, per_block);
+    GSL_COUNT_LAUNCH(1);
+    GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-int Engine::forward(int slot, const float* img, const int64_t* labels, int B, int use_lora, cudaStream_t s) {
+// per-site dropout seeds: site 0 emb (block index = depth), 1 attention to_out, 2 after GELU, 3 after fc2
+static inline uint32_t site_seed(uint64_t base, int block, int site) {
+    return drop_hash((uint32_t)(block * 4 + site + 1), (uint32_t)base ^ (uint32_t)(base >> 32));
+}
+
+int Engine::forward(int slot, const float* img, const int64_t* labels, int B, int use_lora, uint64_t dropout_seed, cudaStream_t s) {
     GSL_REQUIRE(params_bound, "bind_params first");
     GSL_REQUIRE(slot >= 0 && slot < cfg.num_slots, "slot %d out of range", slot);
     GSL_REQUIRE(B >= 1 && B <= cfg.max_batch, "batch %d outside [1, %d]", B, cfg.max_batch);
@@ -246,13 +284,15 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
     const int64_t M = (int64_t)B * tokens;
     const int kx = use_lora ? 16 : 0;
     Slot& S = slots[slot];
-    S.batch = B; S.used_lora = use_lora;
+    S.batch = B; S.used_lora = use_lora; S.drop_seed = dropout_seed;
+    const float pdrop = dropout_seed ? cfg.dropout : 0.f, pemb = dropout_seed ? cfg.emb_dropout : 0.f;
     int rc;
     if ((rc = patchify_f16(img, patches16, patch_dim, B, cfg.channels, cfg.image_size, cfg.patch_size, cfg.patch_order, s))) return rc;
     {   // patch_to_embedding + cls token + pos_embedding (vit_face.py:531-536)
         GemmArgs g;
         g.A = patches16; g.lda = patch_dim; g.B = patch_w16; g.ldb = patch_dim; g.M = M; g.N = D; g.K = patch_dim;
         g.epi = EPI_PERIODIC_F32; g.out0 = S.x[0]; g.ld0 = D; g.aux = posb; g.ldaux = D; g.aux_period = tokens;
+        g.drop_p = pemb; g.drop_seed = site_seed(dropout_seed, L, 0);
         if ((rc = gemm_f16(g, s))) return rc;
     }
     for (int l = 0; l < L; ++l) {
@@ -275,6 +315,7 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
             GemmArgs g;
             g.A = a.o16; g.lda = inner; g.B = c.out_w16; g.ldb = inner; g.M = M; g.N = D; g.K = inner;
             g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = x_mid; g.ld0 = D; g.aux = x_in; g.ldaux = D;
+            g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
         }
         // ---- x = FeedForward(LN(x)) + x, loralib.Linear on both projections
@@ -284,6 +325,7 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
             GemmArgs g;
             g.A = a.xn2cat16; g.lda = D + 16; g.B = c.fc1_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + kx;
             g.epi = EPI_GELU; g.bias = f.fc1_b; g.out0 = a.h16; g.ld0 = H; g.out1 = a.gcat16; g.ld1 = H + 16;
+            g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 2);
             if ((rc = gemm_f16(g, s))) return rc;
         }
         if (use_lora && (rc = lora_down(a.gcat16, H + 16, c.A2h, H, a.gcat16 + H, H + 16, M, H, r, s))) return rc;          // T2
@@ -291,6 +333,7 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
             GemmArgs g;
             g.A = a.gcat16; g.lda = H + 16; g.B = c.fc2_cat; g.ldb = H + 16; g.M = M; g.N = D; g.K = H + kx;
             g.epi = EPI_RES_F32; g.bias = f.fc2_b; g.out0 = x_out; g.ld0 = D; g.aux = x_mid; g.ldaux = D;
+            g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 3);
             if ((rc = gemm_f16(g, s))) return rc;
         }
     }
@@ -313,6 +356,8 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
     const int64_t M = (int64_t)B * tokens;
     const float gs = cfg.grad_scale;
     const float wscale = cfg.lora_scaling / gs;     // dA, dB carry the LoRA scaling and undo the loss scale
+    const uint64_t dseed = S.drop_seed;
+    const float pdrop = dseed ? cfg.dropout : 0.f;
     int rc;
     // gradient wrt the final residual stream: zero except the cls rows
     if ((rc = fill_zero(dx32, (size_t)M * D * 4, s))) return rc;
@@ -321,6 +366,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
     hb.dlogits = dlogits; hb.demb = demb; hb.emb = S.emb; hb.W = loss_w; hb.labels = nullptr; hb.xhat = S.xhat; hb.rstd = S.head_rstd;
     hb.gamma = head_ln_w; hb.cos_s = cfg.cos_s; hb.B = B; hb.D = D; hb.C = cfg.num_class; hb.tokens = tokens; hb.gscale = gs;
     hb.dx = dx32; hb.lddx = D; hb.dx16 = dxcat16; hb.lddx16 = D + 16;
+    hb.drop_p = pdrop; hb.drop_seed = site_seed(dseed, L - 1, 3);
     if ((rc = head_bwd(hb, s))) return rc;
 
     for (int l = L - 1; l >= 0; --l) {
@@ -339,6 +385,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
             GemmArgs g;
             g.A = dxcat16; g.lda = D + 16; g.B = c.fc2T_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + 16;
             g.epi = EPI_GELU_BWD; g.out0 = dhcat16; g.ld0 = H + 16; g.aux = a.h16; g.ldaux = H;
+            g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 2);
             if ((rc = gemm_f16(g, s))) return rc;
         }
         if ((rc = lora_down(dhcat16, H + 16, c.B1T, H, dhcat16 + H, H + 16, M, H, r, s))) return rc;                         // U1 = dH B1
@@ -351,7 +398,8 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
             g.epi = EPI_F32; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
-        if ((rc = layernorm_bwd(dxn32, D, S.x[2 * l + 1], D, a.ln2_mean, a.ln2_rstd, f.ln2_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, s))) return rc;
+        if ((rc = layernorm_bwd(dxn32, D, S.x[2 * l + 1], D, a.ln2_mean, a.ln2_rstd, f.ln2_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, pdrop,
+                                site_seed(dseed, l, 1), s))) return rc;
         // ---------------- attention: y = to_out(attn(to_qkv(LN1(x)))) + x
         {   // dO = dY Wo
             GemmArgs g;
@@ -366,7 +414,8 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
             g.epi = EPI_F32; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
-        if ((rc = layernorm_bwd(dxn32, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, s))) return rc;
+        if ((rc = layernorm_bwd(dxn32, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, pdrop,
+                                site_seed(dseed, l - 1, 3), s))) return rc;
     }
     return 0;
 }

@@ -34,6 +34,7 @@ struct Slot {
     int* correct;
     int batch = 0;
     int used_lora = 0;
+    uint64_t drop_seed = 0;
 };
 
 class Engine {
@@ -54,6 +55,7 @@ public:
     __half *patches16, *xn16, *dxcat16, *dhcat16, *do16, *dqkv16;
     float *dx32, *dxn32, *skinny_ws;
     size_t skinny_ws_bytes = 0;
+    void* pack_ptrs_dev = nullptr;
     int* group_offsets_dev = nullptr; int* tensor_offsets_dev = nullptr; float* group_norms_dev = nullptr; float* tensor_norms_dev = nullptr;
     bool params_bound = false;
 
@@ -62,7 +64,7 @@ public:
     int bind_params(const void* const* ptrs, int n, float* lora, float* grads);
     int refresh_frozen(cudaStream_t s);
     int refresh_lora(cudaStream_t s);
-    int forward(int slot, const float* img, const int64_t* labels, int B, int use_lora, cudaStream_t s);
+    int forward(int slot, const float* img, const int64_t* labels, int B, int use_lora, uint64_t dropout_seed, cudaStream_t s);
     int backward(int slot, const float* dlogits, const float* demb, int accumulate, cudaStream_t s);
     int64_t lora_block_elems() const;
     int64_t lora_offset(int block, int which) const;   // which: 0 A1, 1 B1, 2 A2, 3 B2

@@ -38,6 +38,9 @@ struct GemmParams {
     const float* table;   // EPI_PERIODIC_F32: fp32 [period, ld_table]
     int period, ld_table;
     int has_out1;         // EPI_F32: also emit an fp16 copy through tmO1
+    uint32_t drop_thresh; // p * 65536 (0 = no dropout)
+    uint32_t drop_seed;
+    float drop_scale;     // 1 / (1 - p)
 };
 
 template <int EPI> struct EpiTraits;
@@ -278,6 +281,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                     }
                 }
+                if ((EPI == EPI_RES_F32) && p.drop_thresh) {       // Dropout(to_out / fc2 output) before the residual add
+                    const uint32_t e0 = (uint32_t)(m_base + (int)row) * (uint32_t)p.N + (uint32_t)n0;
+#pragma unroll
+                    for (int j = 0; j < CW; j += 2) {
+                        float s0, s1;
+                        drop_pair(e0 + j, p.drop_seed, p.drop_thresh, p.drop_scale, s0, s1);
+                        f[j] *= s0; f[j + 1] *= s1;
+                    }
+                }
                 if (T::AUX) {
                     const uint32_t b = aux_it & 1;
                     mbar_wait(aux_bar(b), (aux_it >> 1) & 1);
@@ -306,6 +318,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     ++aux_it;
                 }
+                if ((EPI == EPI_GELU_BWD) && p.drop_thresh) {       // backward of Dropout(gelu(h)): same mask as the forward
+                    const uint32_t e0 = (uint32_t)(m_base + (int)row) * (uint32_t)p.N + (uint32_t)n0;
+#pragma unroll
+                    for (int j = 0; j < CW; j += 2) {
+                        float s0, s1;
+                        drop_pair(e0 + j, p.drop_seed, p.drop_thresh, p.drop_scale, s0, s1);
+                        f[j] *= s0; f[j + 1] *= s1;
+                    }
+                }
                 if (EPI == EPI_PERIODIC_F32) {
                     const int r = m_base + (int)row;
                     if (r < p.M) {
@@ -316,6 +337,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + j));
                                 f[j] += t4.x; f[j + 1] += t4.y; f[j + 2] += t4.z; f[j + 3] += t4.w;
                             }
+                        }
+                    }
+                    if (p.drop_thresh) {                            // emb_dropout after the pos-embedding add
+                        const uint32_t e0 = (uint32_t)r * (uint32_t)p.N + (uint32_t)n0;
+#pragma unroll
+                        for (int j = 0; j < CW; j += 2) {
+                            float s0, s1;
+                            drop_pair(e0 + j, p.drop_seed, p.drop_thresh, p.drop_scale, s0, s1);
+                            f[j] *= s0; f[j + 1] *= s1;
                         }
                     }
                 }
@@ -341,6 +371,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (EPI == EPI_GELU) {      // second output G = gelu(h), fp16 [128 x 64]
 #pragma unroll
                         for (int j = 0; j < CW; ++j) f[j] = gelu_fast(f[j]);
+                        if (p.drop_thresh) {                        // Dropout(gelu(h)): G is stored already masked and scaled
+                            const uint32_t e0 = (uint32_t)(m_base + (int)row) * (uint32_t)p.N + (uint32_t)n0;
+#pragma unroll
+                            for (int j = 0; j < CW; j += 2) {
+                                float s0, s1;
+                                drop_pair(e0 + j, p.drop_seed, p.drop_thresh, p.drop_scale, s0, s1);
+                                f[j] *= s0; f[j + 1] *= s1;
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < CW / 8; ++j)
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
@@ -462,6 +501,9 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.table = (EPI == EPI_PERIODIC_F32) ? reinterpret_cast<const float*>(a.aux) : nullptr;
     p.period = (int)a.aux_period; p.ld_table = (int)a.ldaux;
     p.has_out1 = has_o1 ? 1 : 0;
+    p.drop_thresh = a.drop_p > 0.f ? (uint32_t)(a.drop_p * 65536.0f + 0.5f) : 0u;
+    p.drop_seed = a.drop_seed;
+    p.drop_scale = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
 
     auto kern = gemm_tcgen05_kernel<CG, BN, EPI>;
     static bool attr_set = false;
@@ -507,6 +549,7 @@ int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
     GSL_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "empty GEMM %lldx%lldx%lld", (long long)a.M, (long long)a.N, (long long)a.K);
     GSL_REQUIRE(a.K % 16 == 0 && a.N % 8 == 0, "GEMM needs K %% 16 == 0 and N %% 8 == 0 (N=%lld K=%lld)", (long long)a.N, (long long)a.K);
     GSL_REQUIRE(a.A && a.B && a.out0, "null GEMM operand");
+    GSL_REQUIRE(a.drop_p >= 0.f && a.drop_p < 1.f && (a.drop_p == 0.f || a.M * a.N < (int64_t)4294967296LL), "bad dropout p / tensor too large for the 32-bit mask counter");
     if (a.epi == EPI_GELU) GSL_REQUIRE(a.out1 != nullptr, "EPI_GELU needs out1");
     if (a.epi == EPI_GELU_BWD || a.epi == EPI_RES_F32 || a.epi == EPI_PERIODIC_F32) GSL_REQUIRE(a.aux != nullptr, "epilogue %d needs aux", a.epi);
     if (a.epi == EPI_PERIODIC_F32) GSL_REQUIRE(a.aux_period > 0, "EPI_PERIODIC_F32 needs aux_period > 0");

@@ -28,6 +28,8 @@ struct GemmArgs {
     const void* aux = nullptr; int64_t ldaux = 0; int64_t aux_period = 0;
     int cta_group = 0;   // 0 = library default, 1 or 2
     int block_n = 0;     // 0 = auto, 128 or 256
+    float drop_p = 0.f;  // dropout on the produced value (before the residual add; on G for EPI_GELU; times gelu' for EPI_GELU_BWD)
+    uint32_t drop_seed = 0;
 };
 int gemm_f16(const GemmArgs& a, cudaStream_t stream);
 void gemm_set_default_cta_group(int cg);
@@ -43,7 +45,7 @@ int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* 
 // dx = dres + LNbwd(dy) ; writes fp32 dx and an fp16 copy (GEMM operand for the next dX GEMM)
 int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                   const float* gamma, const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16,
-                  int64_t M, int D, cudaStream_t s);
+                  int64_t M, int D, float drop_p, uint32_t drop_seed, cudaStream_t s);   // dropout mask applies to the fp16 copy only
 // T[M, 0:16] = X[M, K] * A16[16, K]^T  (fp16 in, fp32 accumulate, fp16 out at out[:, 0:16], row pitch ldo)
 int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __half* out, int64_t ldo, int64_t M, int K, int r, cudaStream_t s);
 // dW[R, 16-ish] style skinny reductions over M (split-M partials + deterministic second pass):
@@ -88,6 +90,7 @@ struct HeadBwdArgs {
     float cos_s; int B, D, C, tokens;
     float gscale;
     float* dx; int64_t lddx; __half* dx16; int64_t lddx16;
+    float drop_p = 0.f; uint32_t drop_seed = 0;      // mask of the last block's fc2-output dropout, applied to dx16 only
 };
 int head_bwd(const HeadBwdArgs& a, cudaStream_t s);
 // dlogits[b, :] = coef * (softmax(logits[b]) - onehot) / B_total ; coef read from device (gate applied by caller)

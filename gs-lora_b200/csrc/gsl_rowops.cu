@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                             const float* __restrict__ gamma, const float* __restrict__ dres, int64_t lddres,
                                                             float* __restrict__ dx, int64_t lddx, __half* __restrict__ dx16, int64_t lddx16,
-                                                            int64_t M) {
+                                                            int64_t M, uint32_t drop_thresh, uint32_t drop_seed, float drop_scale) {
     constexpr int D = VEC * 128;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -153,6 +153,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         }
         if (dx) reinterpret_cast<float4*>(dx + row * lddx)[lane + 32 * i] = o;
         if (dx16) {
+            if (drop_thresh) {      // the fp16 copy feeds a branch that sits behind a Dropout: apply that site's mask
+                const uint32_t e0 = (uint32_t)row * (uint32_t)D + (uint32_t)(lane + 32 * i) * 4u;
+                float s0, s1, s2, s3;
+                drop_pair(e0, drop_seed, drop_thresh, drop_scale, s0, s1);
+                drop_pair(e0 + 2, drop_seed, drop_thresh, drop_scale, s2, s3);
+                o.x *= s0; o.y *= s1; o.z *= s2; o.w *= s3;
+            }
             uint2 h;
             h.x = pack_half2(o.x, o.y);
             h.y = pack_half2(o.z, o.w);
@@ -163,11 +170,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 
 int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16, int64_t M, int D,
-                  cudaStream_t s) {
+                  float drop_p, uint32_t drop_seed, cudaStream_t s) {
+    const uint32_t dth = drop_p > 0.f ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
+    const float dsc = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     GSL_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm_bwd: D=%d must be a multiple of 128 and <= 1024", D);
     const int warps = 8;
     const int blocks = (int)((M + warps - 1) / warps);
-#define GSL_LN_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M); break;
+#define GSL_LN_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc); break;
     switch (D / 128) {
         GSL_LN_CASE(1) GSL_LN_CASE(2) GSL_LN_CASE(3) GSL_LN_CASE(4) GSL_LN_CASE(5) GSL_LN_CASE(6) GSL_LN_CASE(7) GSL_LN_CASE(8)
     }

@@ -122,7 +122,8 @@ def get_structure_loss(model: torch.nn.Module, imagenet=False):
 
 def unlearn_step(model, inputs_remain, labels_remain, inputs_forget, labels_forget, *, beta: float, alpha: float, BND: float,
                  optimizer=None, hparams: Optional[dict] = None, use_prototype: bool = False, prototype_dict=None,
-                 prototype_weight_forget: float = 0.0, prototype_weight_remain: float = 0.0, BND_pro: float = 0.0) -> Dict[str, float]:
+                 prototype_weight_forget: float = 0.0, prototype_weight_remain: float = 0.0, BND_pro: float = 0.0,
+                 dropout_seed: Optional[int] = None) -> Dict[str, float]:
     """One step of engine_cl.train_one_epoch (engine_cl.py:59-125), fused.  Returns the scalars the reference logs."""
     m = _unwrap(model)
     Br, Bf = int(inputs_remain.shape[0]), int(inputs_forget.shape[0])
@@ -135,7 +136,7 @@ def unlearn_step(model, inputs_remain, labels_remain, inputs_forget, labels_forg
     if m._merged():
         raise RuntimeError("unlearn_step needs model.train() (un-merged LoRA)")
     slot = m._take_slot()
-    eng.forward(img, lab, slot, use_lora=True)
+    eng.forward(img, lab, slot, use_lora=True, dropout_seed=m.dropout_seed() if dropout_seed is None else dropout_seed)
     sums = eng.loss_sums(slot, Br, B)
     dist = _dist()
     world = 1

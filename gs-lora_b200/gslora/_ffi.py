@@ -31,7 +31,7 @@ def lib():
 class GslConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("image_size", "patch_size", "channels", "dim", "depth", "heads", "mlp_dim", "num_class",
                                               "lora_rank", "max_batch", "num_slots", "patch_order")] + \
-               [(n, ctypes.c_float) for n in ("attn_scale", "ln_eps", "cos_s", "cos_m", "lora_scaling", "grad_scale")]
+               [(n, ctypes.c_float) for n in ("attn_scale", "ln_eps", "cos_s", "cos_m", "lora_scaling", "grad_scale", "dropout", "emb_dropout")]
 
 
 SLOT_EMB, SLOT_LOGITS, SLOT_CE, SLOT_CORRECT, SLOT_XFINAL = range(5)
@@ -44,7 +44,7 @@ def _declare(L):
     L.gsl_launch_count.restype = ctypes.c_longlong
     L.gsl_set_gemm_cta_group.argtypes = [c_int]
     L.gsl_gemm_f16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p,
-                               c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]
+                               c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_float, ctypes.c_uint32, c_void_p]
     L.gsl_gemm_f16.restype = c_int
     P = c_void_p
     sigs = {
@@ -62,7 +62,7 @@ def _declare(L):
         "gsl_engine_bind_params": [P, ctypes.POINTER(P), c_int, P, P],
         "gsl_engine_refresh_frozen": [P, P],
         "gsl_engine_refresh_lora": [P, P],
-        "gsl_engine_forward": [P, c_int, P, P, c_int, c_int, P],
+        "gsl_engine_forward": [P, c_int, P, P, c_int, c_int, ctypes.c_uint64, P],
         "gsl_engine_backward": [P, c_int, P, P, c_int, P],
         "gsl_loss_sums": [P, P, c_int, c_int, P, P],
         "gsl_unlearn_ce_grad": [P, P, P, c_int, c_int, c_int, c_float, c_float, P, P],
@@ -114,12 +114,13 @@ EPI_F16, EPI_F32, EPI_GELU, EPI_GELU_BWD, EPI_RES_F32, EPI_PERIODIC_F32 = range(
 
 
 def gemm_f16(A, B, *, epi=EPI_F16, bias=None, out0, out1=None, aux=None, aux_period=0, K=None, N=None, M=None,
-             cta_group=0, block_n=0):
+             cta_group=0, block_n=0, drop_p=0.0, drop_seed=0):
     """out = epi(A[:, :K] @ B[:, :K].T); A, B fp16 row-major 2-D (possibly column-sliced views)."""
     M = A.shape[0] if M is None else M
     K = A.shape[1] if K is None else K
     N = B.shape[0] if N is None else N
     rc = lib().gsl_gemm_f16(ptr(A), A.stride(0), ptr(B), B.stride(0), M, N, K, epi, ptr(bias),
                             ptr(out0), out0.stride(0), ptr(out1), out1.stride(0) if out1 is not None else 0,
-                            ptr(aux), aux.stride(0) if aux is not None else 0, aux_period, cta_group, block_n, cur_stream())
+                            ptr(aux), aux.stride(0) if aux is not None else 0, aux_period, cta_group, block_n, float(drop_p), int(drop_seed),
+                            cur_stream())
     check(rc, "gsl_gemm_f16")

@@ -30,6 +30,8 @@ class EngineSpec:
     cos_m: float = 0.35
     patch_order: int = 0
     grad_scale: float = 1024.0
+    dropout: float = 0.0
+    emb_dropout: float = 0.0
 
     @property
     def tokens(self) -> int:
@@ -54,7 +56,8 @@ class VitEngine:
                                depth=spec.depth, heads=spec.heads, mlp_dim=spec.mlp_dim, num_class=spec.num_class,
                                lora_rank=spec.lora_rank, max_batch=self.max_batch, num_slots=self.num_slots,
                                patch_order=spec.patch_order, attn_scale=spec.attn_scale, ln_eps=spec.ln_eps, cos_s=spec.cos_s,
-                               cos_m=spec.cos_m, lora_scaling=1.0 / spec.lora_rank, grad_scale=spec.grad_scale)
+                               cos_m=spec.cos_m, lora_scaling=1.0 / spec.lora_rank, grad_scale=spec.grad_scale,
+                               dropout=spec.dropout, emb_dropout=spec.emb_dropout)
         L = F.lib()
         nbytes = L.gsl_engine_workspace_bytes(ctypes.byref(self.cfg))
         if nbytes == 0:
@@ -143,12 +146,12 @@ class VitEngine:
             return self._view(p, (B * s.tokens, s.dim), torch.float32)
         raise ValueError(what)
 
-    def forward(self, img: torch.Tensor, labels: Optional[torch.Tensor], slot: int = 0, use_lora: bool = True):
+    def forward(self, img: torch.Tensor, labels: Optional[torch.Tensor], slot: int = 0, use_lora: bool = True, dropout_seed: int = 0):
         assert img.is_cuda and img.dtype == torch.float32 and img.is_contiguous()
         B = img.shape[0]
         if labels is not None:
             assert labels.is_cuda and labels.dtype == torch.int64 and labels.is_contiguous()
-        F.check(F.lib().gsl_engine_forward(self.handle, slot, F.ptr(img), F.ptr(labels), B, 1 if use_lora else 0, F.cur_stream()),
+        F.check(F.lib().gsl_engine_forward(self.handle, slot, F.ptr(img), F.ptr(labels), B, 1 if use_lora else 0, int(dropout_seed), F.cur_stream()),
                 "gsl_engine_forward")
         return B
 

@@ -97,7 +97,7 @@ class _EngineFn(torch.autograd.Function):
     def forward(ctx, model, img, label, *lora_params):
         eng = model._engine
         slot = model._take_slot()
-        B = eng.forward(img, label, slot, use_lora=True)
+        B = eng.forward(img, label, slot, use_lora=True, dropout_seed=model.dropout_seed())
         ctx.model, ctx.slot, ctx.B, ctx.stamp = model, slot, B, model._slot_stamp[slot]
         emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
         if label is None:
@@ -198,7 +198,7 @@ class ViT_face(nn.Module):
                           heads=self.heads, mlp_dim=self.mlp_dim, num_class=self.num_class, lora_rank=self.lora_rank,
                           attn_scale=self.dim ** -0.5, ln_eps=self.mlp_head[0].eps,
                           cos_s=getattr(getattr(self, "loss", None), "s", 64.0), cos_m=getattr(getattr(self, "loss", None), "m", 0.35),
-                          grad_scale=float(os.environ.get("GSLORA_GRAD_SCALE", "1024")))
+                          grad_scale=float(os.environ.get("GSLORA_GRAD_SCALE", "1024")), dropout=self.dropout_p, emb_dropout=self.emb_dropout_p)
 
     def ensure_engine(self, batch: int, slots: Optional[int] = None) -> VitEngine:
         dev = self.pos_embedding.device
@@ -254,6 +254,13 @@ class ViT_face(nn.Module):
         self._slot_stamp[s] += 1
         return s
 
+    def dropout_seed(self) -> int:
+        """Non-zero seed for the engine's counter-based dropout masks in train mode (drawn from torch's CPU generator, so
+        torch.manual_seed makes runs reproducible); 0 (= no dropout) in eval mode or when both probabilities are 0."""
+        if not self.training or (self.dropout_p <= 0.0 and self.emb_dropout_p <= 0.0) or os.environ.get("GSLORA_DROPOUT", "on") == "off":
+            return 0
+        return int(torch.randint(1, 2 ** 62, (1,)).item())
+
     def _merged(self) -> bool:
         states = {m.merged for pair in self.lora_layers() for m in pair}
         if len(states) != 1:
@@ -265,9 +272,6 @@ class ViT_face(nn.Module):
         """:return: (logits, emb) if `label` is given else emb -- as vit_face.py:523-548"""
         if mask is not None:
             raise NotImplementedError("gslora-b200: attention masks are not used by any GS-LoRA script and are not built")
-        if self.training and (self.dropout_p > 0.0 or self.emb_dropout_p > 0.0) and os.environ.get("GSLORA_DROPOUT", "error") != "off":
-            raise NotImplementedError("gslora-b200 round 1: dropout > 0 in train mode is not built yet; construct with dropout=0 / "
-                                      "emb_dropout=0 or set GSLORA_DROPOUT=off to run the step without dropout")
         img = img.float().contiguous()
         if label is not None:
             label = label.to(device=img.device, dtype=torch.int64).contiguous()
@@ -281,7 +285,7 @@ class ViT_face(nn.Module):
         if need_grad:
             return _EngineFn.apply(self, img, label, *lora_params)
         slot = self._take_slot()
-        B = eng.forward(img, label, slot, use_lora=not merged)
+        B = eng.forward(img, label, slot, use_lora=not merged, dropout_seed=self.dropout_seed())
         emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
         if label is None:
             return emb

@@ -38,10 +38,13 @@ enum {
  * Replaces torch.nn.functional.linear / loralib.Linear.forward on the hot path
  * (vit_pytorch_face/vit_face.py:330-334,360,377,531; loralib Linear.forward: the LoRA term is an extra
  * K = 16 step when A carries T = x*A^T and B carries s*lora_B in 16 trailing columns) and the dX GEMMs
- * autograd builds for engine_cl.py:124. */
+ * autograd builds for engine_cl.py:124.  drop_p > 0 applies a counter-based nn.Dropout mask (seed drop_seed, element index
+ * row * N + col) to the produced value: before the residual add (RES), after the table add (PERIODIC), on out1 (GELU), and as a
+ * factor in GELU_BWD. */
 int gsl_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                  int epi, const float* bias, void* out0, int64_t ld0, void* out1, int64_t ld1,
-                 const void* aux, int64_t ldaux, int64_t aux_period, int cta_group, int block_n, void* stream);
+                 const void* aux, int64_t ldaux, int64_t aux_period, int cta_group, int block_n, float drop_p, uint32_t drop_seed,
+                 void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------------
@@ -94,6 +97,8 @@ typedef struct GslConfig {
   float cos_s, cos_m;    /* CosFace s = 64, m = 0.35 (vit_face.py:158) */
   float lora_scaling;    /* lora_alpha / r = 1 / r */
   float grad_scale;      /* power-of-two loss scale of the fp16 gradient stream (unscaled again in dA/dB) */
+  float dropout;         /* nn.Dropout p of to_out / after GELU / after fc2 (vit_face.py:332,334,356), applied when dropout_seed != 0 */
+  float emb_dropout;     /* nn.Dropout p after the pos-embedding add (vit_face.py:489,537) */
 } GslConfig;
 
 /* Frozen parameter pointer table order for gsl_engine_bind_params (fp32 device pointers, reference state_dict names):
@@ -114,8 +119,10 @@ int gsl_engine_refresh_frozen(void* handle, void* stream);
 /* repack the fp16 LoRA operands (after any update of lora_A / lora_B) */
 int gsl_engine_refresh_lora(void* handle, void* stream);
 /* ViT_face.forward(img, label): img fp32 [B,C,S,S], labels int64 [B] (may be NULL: emb only).  use_lora = 0 runs the
- * merged / r == 0 form (F.linear only).  Results stay in the slot: see gsl_engine_slot_ptr. */
-int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* labels, int B, int use_lora, void* stream);
+ * merged / r == 0 form (F.linear only).  dropout_seed != 0 = train mode: the four nn.Dropout sites draw counter-based masks from
+ * it (the backward of the same slot regenerates them).  Results stay in the slot: see gsl_engine_slot_ptr. */
+int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* labels, int B, int use_lora, uint64_t dropout_seed,
+                       void* stream);
 /* selective backward of engine_cl.py:124: upstream d logits [B,C] and/or d emb [B,D] (fp32, may be NULL) ->
  * LoRA gradients written (accumulate = 0) or added (accumulate = 1) into grad_flat. */
 int gsl_engine_backward(void* handle, int slot, const float* dlogits, const float* demb, int accumulate, void* stream);

@@ -175,3 +175,47 @@ def test_no_cpu_fallback():
     model = build_model(cfg, sd, device="cpu")
     with pytest.raises(_ffi.GslError):
         model(torch.rand(2, 3, 40, 40))
+
+
+def test_dropout_step_matches_oracle_with_replayed_masks():
+    """Train-mode dropout (p = 0.1 at all four sites, the reference's ViT-P8S8 setting): the engine's counter-based masks are
+    replayed on the host and fed to the oracle; logits and every LoRA gradient must agree as in the p = 0 case."""
+    import loralib as lora
+    from vit_pytorch_face import ViT_face
+    from dropout_ref import engine_masks
+    cfg = O.VitConfig(image_size=112, patch_size=8, dim=512, depth=3, heads=8, mlp_dim=2048, num_class=100, lora_rank=8)
+    sd = O.init_state_dict(cfg, seed=41)
+    gen = torch.Generator().manual_seed(42)
+    B, p = 6, 0.1
+    x = torch.rand(B, 3, 112, 112, generator=gen).cuda()
+    y = torch.randint(0, 100, (B,), generator=gen).cuda()
+    m = ViT_face(loss_type="CosFace", GPU_ID=[0], num_class=100, image_size=112, patch_size=8, dim=512, depth=3, heads=8, mlp_dim=2048,
+                 dropout=p, emb_dropout=p, lora_rank=8)
+    m.load_state_dict(sd, strict=True)
+    lora.mark_only_lora_as_trainable(m)
+    m = m.cuda().train()
+    seed = 0x1234ABCD5678
+    m.dropout_seed = lambda: seed
+    logits, emb = m(x, y)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    # oracle with the same masks
+    masks = {k: v.cuda() for k, v in engine_masks(cfg, B, seed, p, p).items()}
+    work = {k: v.cuda() for k, v in sd.items()}
+    names = O.lora_param_list(cfg)
+    for n in names:
+        work[n].requires_grad_(True)
+    ref_logits, _ = O.vit_forward(work, cfg, x, y, masks=masks)
+    ref_loss = torch.nn.functional.cross_entropy(ref_logits, y)
+    ref_grads = torch.autograd.grad(ref_loss, [work[n] for n in names])
+    assert rel(logits, ref_logits) < TOL_LOGITS
+    got = torch.cat([m.get_parameter(n).grad.flatten() for n in names])
+    want = torch.cat([g.flatten() for g in ref_grads])
+    assert rel(got, want) < 1.5e-3
+    # the masks really drop ~p of the activations and eval mode is deterministic / mask-free
+    assert abs(float((masks[("gelu", 0)] == 0).float().mean()) - p) < 5e-3
+    m.eval()
+    with torch.no_grad():
+        l1, _ = m(x, y)
+        l2, _ = m(x, y)
+    assert torch.equal(l1, l2)
