@@ -11,12 +11,13 @@
 // cached fp16 weight carries s*B in 16 trailing columns, so  [x | T] [W | sB]^T = x W^T + s T B^T
 // is produced by the same TMA pipeline and the same accumulator (K = in_features + 16).
 //
-// Structure (persistent, warp specialised, 192 threads):
+// Structure (persistent, warp specialised, 576 threads):
 //   warp 0    TMA producer      cp.async.bulk.tensor 128B-swizzled A/B tiles -> smem ring (mbarrier full/empty)
 //   warp 1    MMA issuer        one lane issues tcgen05.mma (cta_group::1 or ::2), accumulators in TMEM,
 //                               tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2-5 epilogue          tcgen05.ld TMEM -> registers -> fused math -> swizzled smem -> TMA store,
-//                               auxiliary input tiles (residual / pre-GELU H) arrive by TMA, double buffered
+//   warps 2-17 epilogue         two groups of 8 warps on alternate 128 x 64 (fp16) / 128 x 32 (fp32) stripes of the accumulator:
+//                               tcgen05.ld TMEM -> registers -> fused math -> swizzled smem -> one TMA store per stripe;
+//                               auxiliary input stripes (residual / pre-GELU H) arrive by TMA
 // Two TMEM accumulator buffers (2 x BLOCK_N columns) overlap the epilogue of tile i with the MMAs of tile i+1.
 #include "gsl_common.cuh"
 #include "gsl_kernels.h"
@@ -52,8 +53,10 @@ template <> struct EpiTraits<EPI_GELU_BWD>     { static constexpr int O0 = 2, O1
 template <> struct EpiTraits<EPI_RES_F32>      { static constexpr int O0 = 4, O1 = 0, AUX = 4; };
 template <> struct EpiTraits<EPI_PERIODIC_F32> { static constexpr int O0 = 4, O1 = 0, AUX = 0; };
 
-static constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of a stripe's columns
-static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+static constexpr int EPI_GROUPS = 2;                      // two independent epilogue groups work on alternate stripes
+static constexpr int EPI_GROUP_WARPS = 8;                 // per group: two warps per TMEM lane quarter, each takes half of a stripe's columns
+static constexpr int EPI_WARPS = EPI_GROUPS * EPI_GROUP_WARPS;
+static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 
 template <int CG, int BN, int EPI>
 struct GemmCfg {
@@ -68,7 +71,7 @@ struct GemmCfg {
     static constexpr int O0_BUF = BLOCK_M * STRIPE * T::O0;
     static constexpr int O1_BUF = BLOCK_M * STRIPE * T::O1;
     static constexpr int AUX_BUF = BLOCK_M * STRIPE * T::AUX;
-    static constexpr int EPI_TOTAL = 2 * (O0_BUF + O1_BUF + AUX_BUF);
+    static constexpr int EPI_TOTAL = EPI_GROUPS * (O0_BUF + O1_BUF + AUX_BUF);   // one staging set per group (the groups alternate)
     static constexpr int BAR_BYTES = 1024;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - EPI_TOTAL - BAR_BYTES) / STAGE;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -79,7 +82,7 @@ struct GemmCfg {
     static_assert(O0_BUF % 1024 == 0 && (O1_BUF % 1024 == 0) && (AUX_BUF % 1024 == 0), "staging must keep 1024-byte alignment");
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync(uint32_t group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(EPI_GROUP_WARPS * 32) : "memory"); }
 
 // load CW fp32 accumulator columns of this warp's 32 TMEM lanes
 template <int CW>
@@ -219,25 +222,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        // ===================================================== epilogue warps (8 warps = 256 threads)
+        // ===================================================== epilogue: 2 groups x 8 warps, groups take alternate stripes
         constexpr int STRIPE = Cfg::STRIPE, CW = Cfg::CW;
         const uint32_t quarter = warp & 3;              // TMEM lane quarter this warp may access
         const uint32_t ew = warp - 2;
-        const uint32_t half = ew >> 2;                  // which half of the stripe's columns
+        const uint32_t grp = ew >> 3;                   // epilogue group
+        const uint32_t half = (ew & 7) >> 2;            // which half of the stripe's columns
         const uint32_t row = quarter * 32 + lane;       // row of the 128-row tile owned by this thread
-        const bool elected = (ew == 0 && lane == 0);
-        uint32_t o0_buf[2], o1_buf[2], aux_buf[2];
-        {
-            uint32_t off = sEpi;
-            o0_buf[0] = off; o0_buf[1] = off + Cfg::O0_BUF; off += 2 * Cfg::O0_BUF;
-            aux_buf[0] = off; aux_buf[1] = off + Cfg::AUX_BUF; off += 2 * Cfg::AUX_BUF;
-            o1_buf[0] = off; o1_buf[1] = off + Cfg::O1_BUF;
-        }
+        const bool elected = ((ew & 7) == 0 && lane == 0);
+        const uint32_t gbase = sEpi + grp * (Cfg::O0_BUF + Cfg::O1_BUF + Cfg::AUX_BUF);
+        const uint32_t o0_buf = gbase, aux_buf = gbase + Cfg::O0_BUF, o1_buf = gbase + Cfg::O0_BUF + Cfg::AUX_BUF;
         const bool write_o1 = (EPI == EPI_GELU) || (EPI == EPI_F32 && p.has_out1);
 
         int iter = 0;
-        uint32_t aux_it = 0;     // aux stripes consumed so far (buffer = aux_it & 1, parity = (aux_it >> 1) & 1)
-        uint32_t st_it = 0;      // stripes stored so far (staging buffer = st_it & 1)
+        uint32_t aux_it = 0;     // aux stripes consumed by this group so far (parity = aux_it & 1)
         for (int t = cluster_id; t < total_tiles; t += num_clusters, ++iter) {
             const int mt = t / p.num_n_tiles, nt = t % p.num_n_tiles;
             const int acc = iter & 1;
@@ -248,25 +246,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int nstripes = ((n_rem >= BN ? BN : n_rem) + STRIPE - 1) / STRIPE;
             const bool tile_live = m_base < p.M;     // CTA-uniform (the second CTA of a pair can be past the M tail)
 
-            if (T::AUX && tile_live && elected) {
-                const uint32_t b = aux_it & 1;
-                mbar_arrive_expect_tx(aux_bar(b), Cfg::AUX_BUF);
-                tma_load_2d<1>(&tmAux, aux_bar(b), aux_buf[b], n_base, m_base);
+            if (T::AUX && tile_live && elected && (int)grp < nstripes) {
+                mbar_arrive_expect_tx(aux_bar(grp), Cfg::AUX_BUF);
+                tma_load_2d<1>(&tmAux, aux_bar(grp), aux_buf, n_base + grp * STRIPE, m_base);
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
+            if ((int)grp >= nstripes) {              // nothing to do for this group in a narrow tile: just release the accumulator
+                tcgen05_fence_before();
+                if (CG == 2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+            }
 
-            for (int sidx = 0; sidx < nstripes; ++sidx) {
+            for (int sidx = grp; sidx < nstripes; sidx += EPI_GROUPS) {
                 const int n0 = n_base + sidx * STRIPE + (int)half * CW;      // first column of this warp
                 float f[CW];
-                if (T::AUX && tile_live && elected && sidx + 1 < nstripes) {
-                    const uint32_t b = (aux_it + 1) & 1;
-                    mbar_arrive_expect_tx(aux_bar(b), Cfg::AUX_BUF);
-                    tma_load_2d<1>(&tmAux, aux_bar(b), aux_buf[b], n_base + (sidx + 1) * STRIPE, m_base);
-                }
                 tmem_ld_cols<CW>(tmem_base + ((quarter * 32u) << 16) + acc * BN + sidx * STRIPE + half * CW, f);
-                if (sidx == nstripes - 1) {
-                    // all TMEM reads of this accumulator are in registers: hand the buffer back to the MMA warp
+                if (sidx + EPI_GROUPS >= nstripes) {
+                    // this thread's last TMEM read of the accumulator: hand the buffer back to the MMA warp
                     tcgen05_fence_before();
                     if (CG == 2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
                 }
@@ -291,14 +287,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
                 if (T::AUX) {
-                    const uint32_t b = aux_it & 1;
-                    mbar_wait(aux_bar(b), (aux_it >> 1) & 1);
+                    mbar_wait(aux_bar(grp), aux_it & 1);
                     if (T::AUX == 4) {          // fp32 residual stripe [128 x 32]: this warp's 16 columns = chunks half*4 .. +3
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             float4 r;
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(aux_buf[b] + sw128_off(row, half * 4 + j)));
+                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(aux_buf + sw128_off(row, half * 4 + j)));
                             f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
                         }
                     } else {                    // fp16 pre-activation stripe H [128 x 64]: dH = dG * gelu'(H)
@@ -306,7 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int j = 0; j < 4; ++j) {
                             uint32_t h0, h1, h2, h3;
                             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(aux_buf[b] + sw128_off(row, half * 4 + j)));
+                                         : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(aux_buf + sw128_off(row, half * 4 + j)));
                             const uint32_t hh[4] = {h0, h1, h2, h3};
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -350,21 +345,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
 
-                // staging buffer reuse: the TMA store issued two stripes ago must have finished reading smem
-                const uint32_t sb = st_it & 1;
-                if (elected) tma_store_wait_read<1>();
-                epi_bar_sync();
+                // staging reuse: this group's previous TMA store must have finished reading smem; every thread of the group
+                // has consumed the aux stripe by the time it reaches the barrier
+                if (elected) tma_store_wait_read<0>();
+                epi_bar_sync(grp);
+                if (T::AUX && elected && sidx + EPI_GROUPS < nstripes) {     // prefetch this group's next aux stripe
+                    mbar_arrive_expect_tx(aux_bar(grp), Cfg::AUX_BUF);
+                    tma_load_2d<1>(&tmAux, aux_bar(grp), aux_buf, n_base + (sidx + EPI_GROUPS) * STRIPE, m_base);
+                }
 
                 if (T::O0 == 4) {   // fp32 [128 x 32] stripe: this warp's 16 columns = 16-byte chunks half*4 .. +3
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-                                     ::"r"(o0_buf[sb] + sw128_off(row, half * 4 + j)), "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
+                                     ::"r"(o0_buf + sw128_off(row, half * 4 + j)), "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
                 } else {            // fp16 [128 x 64] stripe: this warp's 32 columns = chunks half*4 .. +3
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                     ::"r"(o0_buf[sb] + sw128_off(row, half * 4 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
+                                     ::"r"(o0_buf + sw128_off(row, half * 4 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
                                        "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
                 }
                 if (T::O1 && write_o1) {
@@ -383,24 +382,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < CW / 8; ++j)
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                         ::"r"(o1_buf[sb] + sw128_off(row, half * 4 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
+                                         ::"r"(o1_buf + sw128_off(row, half * 4 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
                                            "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
                     } else {                    // fp16 copy of an fp32 stripe, [128 x 32] = 64-byte rows: this warp's 16 columns = chunks half*2 .. +1
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                         ::"r"(o1_buf[sb] + sw64_off(row, half * 2 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
+                                         ::"r"(o1_buf + sw64_off(row, half * 2 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
                                            "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
                     }
                 }
                 fence_proxy_async_smem();
-                epi_bar_sync();
+                epi_bar_sync(grp);
                 if (elected) {
-                    tma_store_2d(&tmO0, o0_buf[sb], n_base + sidx * STRIPE, m_base);
-                    if (T::O1 && write_o1) tma_store_2d(&tmO1, o1_buf[sb], n_base + sidx * STRIPE, m_base);
+                    tma_store_2d(&tmO0, o0_buf, n_base + sidx * STRIPE, m_base);
+                    if (T::O1 && write_o1) tma_store_2d(&tmO1, o1_buf, n_base + sidx * STRIPE, m_base);
                     tma_store_commit();
                 }
-                ++st_it;
             }
         }
         if (elected) tma_store_wait_all();
