@@ -117,7 +117,7 @@ void* gsl_engine_slot_ptr(void* handle, int slot, int what) {
         case GSL_SLOT_LOGITS: return s.logits;
         case GSL_SLOT_CE: return s.ce;
         case GSL_SLOT_CORRECT: return s.correct;
-        case GSL_SLOT_XFINAL: return s.x.back();
+        case GSL_SLOT_XFINAL: return s.cls.xout32;
         default: return nullptr;
     }
 }

@@ -74,6 +74,10 @@ size_t Engine::carve(bool assign) {
             a.gcat16 = (__half*)take((size_t)M * (H + 16) * 2);
             sl.blk.push_back(a);
         }
+        sl.cls.xin32 = (float*)take((size_t)Bm * D * 4); sl.cls.xmid32 = (float*)take((size_t)Bm * D * 4); sl.cls.xout32 = (float*)take((size_t)Bm * D * 4);
+        sl.cls.ln2_mean = (float*)take((size_t)Bm * 4); sl.cls.ln2_rstd = (float*)take((size_t)Bm * 4); sl.cls.lse = (float*)take((size_t)Bm * cfg.heads * 4);
+        sl.cls.o16 = (__half*)take((size_t)Bm * inner * 2); sl.cls.xn2cat16 = (__half*)take((size_t)Bm * (D + 16) * 2);
+        sl.cls.h16 = (__half*)take((size_t)Bm * H * 2); sl.cls.gcat16 = (__half*)take((size_t)Bm * (H + 16) * 2);
         sl.emb = (float*)take((size_t)Bm * D * 4);
         sl.logits = (float*)take((size_t)Bm * C * 4);
         sl.ce = (float*)take((size_t)Bm * 4);
@@ -90,6 +94,11 @@ size_t Engine::carve(bool assign) {
     auto* t_dqkv = (__half*)take((size_t)M * 3 * inner * 2);
     auto* t_dx32 = (float*)take((size_t)M * D * 4);
     auto* t_dxn32 = (float*)take((size_t)M * D * 4);
+    auto* t_cdx = (float*)take((size_t)Bm * D * 4);
+    auto* t_cdxn = (float*)take((size_t)Bm * D * 4);
+    auto* t_cdxcat = (__half*)take((size_t)Bm * (D + 16) * 2);
+    auto* t_cdhcat = (__half*)take((size_t)Bm * (H + 16) * 2);
+    auto* t_cdo = (__half*)take((size_t)Bm * inner * 2);
     const size_t sk = skinny_tn_workspace(M, (int)(H > D ? H : D), cfg.lora_rank);
     auto* t_sk = (float*)take(sk);
     auto* t_go = (int*)take((size_t)(L + 1) * 4);
@@ -100,6 +109,7 @@ size_t Engine::carve(bool assign) {
     if (assign) {
         patches16 = t_patches; xn16 = t_xn; dxcat16 = t_dxcat; dhcat16 = t_dhcat; do16 = t_do; dqkv16 = t_dqkv;
         dx32 = t_dx32; dxn32 = t_dxn32; skinny_ws = t_sk; skinny_ws_bytes = sk;
+        cls_dx32 = t_cdx; cls_dxn32 = t_cdxn; cls_dxcat16 = t_cdxcat; cls_dhcat16 = t_cdhcat; cls_do16 = t_cdo;
         group_offsets_dev = t_go; tensor_offsets_dev = t_to; group_norms_dev = t_gn; tensor_norms_dev = t_tn; pack_ptrs_dev = t_pp;
     }
     return align_up(off, 1024);
@@ -276,13 +286,39 @@ static inline uint32_t site_seed(uint64_t base, int block, int site) {
     return drop_hash((uint32_t)(block * 4 + site + 1), (uint32_t)base ^ (uint32_t)(base >> 32));
 }
 
+// x_out = FeedForward(LN2(x_mid)) + x_mid on M rows (dense tokens, or the compacted cls rows of the last block)
+int Engine::ffn_forward(int l, int64_t M, __half* xn2cat, float* ln_mean, float* ln_rstd, const float* x_mid, __half* h16, __half* gcat, float* x_out,
+                        int use_lora, float pdrop, uint64_t dseed, cudaStream_t s) {
+    const int D = cfg.dim, H = cfg.mlp_dim, r = cfg.lora_rank, kx = use_lora ? 16 : 0;
+    const BlockFrozen& f = frozen[l];
+    const BlockCache& c = cache[l];
+    int rc;
+    if ((rc = layernorm_fwd(x_mid, D, f.ln2_w, f.ln2_b, cfg.ln_eps, xn2cat, D + 16, ln_mean, ln_rstd, M, D, s))) return rc;
+    if (use_lora && (rc = lora_down(xn2cat, D + 16, c.A1h, D, xn2cat + D, D + 16, M, D, r, s))) return rc;      // T1 = LN2(x) A1^T
+    {
+        GemmArgs g;
+        g.A = xn2cat; g.lda = D + 16; g.B = c.fc1_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + kx;
+        g.epi = EPI_GELU; g.bias = f.fc1_b; g.out0 = h16; g.ld0 = H; g.out1 = gcat; g.ld1 = H + 16;
+        g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 2);
+        if ((rc = gemm_f16(g, s))) return rc;
+    }
+    if (use_lora && (rc = lora_down(gcat, H + 16, c.A2h, H, gcat + H, H + 16, M, H, r, s))) return rc;          // T2 = G A2^T
+    {
+        GemmArgs g;
+        g.A = gcat; g.lda = H + 16; g.B = c.fc2_cat; g.ldb = H + 16; g.M = M; g.N = D; g.K = H + kx;
+        g.epi = EPI_RES_F32; g.bias = f.fc2_b; g.out0 = x_out; g.ld0 = D; g.aux = x_mid; g.ldaux = D;
+        g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 3);
+        if ((rc = gemm_f16(g, s))) return rc;
+    }
+    return 0;
+}
+
 int Engine::forward(int slot, const float* img, const int64_t* labels, int B, int use_lora, uint64_t dropout_seed, cudaStream_t s) {
     GSL_REQUIRE(params_bound, "bind_params first");
     GSL_REQUIRE(slot >= 0 && slot < cfg.num_slots, "slot %d out of range", slot);
     GSL_REQUIRE(B >= 1 && B <= cfg.max_batch, "batch %d outside [1, %d]", B, cfg.max_batch);
-    const int D = cfg.dim, H = cfg.mlp_dim, L = cfg.depth, inner = cfg.heads * 64, r = cfg.lora_rank;
+    const int D = cfg.dim, L = cfg.depth, inner = cfg.heads * 64;
     const int64_t M = (int64_t)B * tokens;
-    const int kx = use_lora ? 16 : 0;
     Slot& S = slots[slot];
     S.batch = B; S.used_lora = use_lora; S.drop_seed = dropout_seed;
     const float pdrop = dropout_seed ? cfg.dropout : 0.f, pemb = dropout_seed ? cfg.emb_dropout : 0.f;
@@ -300,8 +336,6 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
         const BlockCache& c = cache[l];
         BlockActs& a = S.blk[l];
         float* x_in = S.x[2 * l];
-        float* x_mid = S.x[2 * l + 1];
-        float* x_out = S.x[2 * l + 2];
         // ---- x = Attention(LN(x)) + x
         if ((rc = layernorm_fwd(x_in, D, f.ln1_w, f.ln1_b, cfg.ln_eps, xn16, D, a.ln1_mean, a.ln1_rstd, M, D, s))) return rc;
         {
@@ -310,39 +344,75 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
             g.epi = EPI_F16; g.bias = f.qkv_b; g.out0 = a.qkv16; g.ld0 = 3 * inner;
             if ((rc = gemm_f16(g, s))) return rc;
         }
-        if ((rc = attention_fwd(a.qkv16, 3 * inner, a.o16, inner, a.lse, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
-        {
+        if (l < L - 1) {
+            float* x_mid = S.x[2 * l + 1];
+            float* x_out = S.x[2 * l + 2];
+            if ((rc = attention_fwd(a.qkv16, 3 * inner, a.o16, inner, a.lse, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
             GemmArgs g;
             g.A = a.o16; g.lda = inner; g.B = c.out_w16; g.ldb = inner; g.M = M; g.N = D; g.K = inner;
             g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = x_mid; g.ld0 = D; g.aux = x_in; g.ldaux = D;
             g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
-        }
-        // ---- x = FeedForward(LN(x)) + x, loralib.Linear on both projections
-        if ((rc = layernorm_fwd(x_mid, D, f.ln2_w, f.ln2_b, cfg.ln_eps, a.xn2cat16, D + 16, a.ln2_mean, a.ln2_rstd, M, D, s))) return rc;
-        if (use_lora && (rc = lora_down(a.xn2cat16, D + 16, c.A1h, D, a.xn2cat16 + D, D + 16, M, D, r, s))) return rc;      // T1
-        {
+            // ---- x = FeedForward(LN(x)) + x, loralib.Linear on both projections
+            if ((rc = ffn_forward(l, M, a.xn2cat16, a.ln2_mean, a.ln2_rstd, x_mid, a.h16, a.gcat16, x_out, use_lora, pdrop, dropout_seed, s))) return rc;
+        } else {
+            // ---- last block: only the cls token is pooled (vit_face.py:540), every other token of this block is dead.
+            //      Single-query attention per (image, head), then out-proj / FFN on the B compacted cls rows.
+            ClsActs& k = S.cls;
+            if ((rc = cls_attention_fwd(a.qkv16, 3 * inner, k.o16, inner, k.lse, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
+            if ((rc = copy_cls_rows(x_in, (int64_t)tokens * D * 4, k.xin32, (int64_t)D * 4, B, (int64_t)D * 4, s))) return rc;
             GemmArgs g;
-            g.A = a.xn2cat16; g.lda = D + 16; g.B = c.fc1_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + kx;
-            g.epi = EPI_GELU; g.bias = f.fc1_b; g.out0 = a.h16; g.ld0 = H; g.out1 = a.gcat16; g.ld1 = H + 16;
-            g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 2);
+            g.A = k.o16; g.lda = inner; g.B = c.out_w16; g.ldb = inner; g.M = B; g.N = D; g.K = inner;
+            g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = k.xmid32; g.ld0 = D; g.aux = k.xin32; g.ldaux = D;
+            g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
-        }
-        if (use_lora && (rc = lora_down(a.gcat16, H + 16, c.A2h, H, a.gcat16 + H, H + 16, M, H, r, s))) return rc;          // T2
-        {
-            GemmArgs g;
-            g.A = a.gcat16; g.lda = H + 16; g.B = c.fc2_cat; g.ldb = H + 16; g.M = M; g.N = D; g.K = H + kx;
-            g.epi = EPI_RES_F32; g.bias = f.fc2_b; g.out0 = x_out; g.ld0 = D; g.aux = x_mid; g.ldaux = D;
-            g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 3);
-            if ((rc = gemm_f16(g, s))) return rc;
+            if ((rc = ffn_forward(l, B, k.xn2cat16, k.ln2_mean, k.ln2_rstd, k.xmid32, k.h16, k.gcat16, k.xout32, use_lora, pdrop, dropout_seed, s))) return rc;
         }
     }
     HeadArgs h;
-    h.x = S.x[2 * L]; h.ldx = D; h.tokens = tokens; h.gamma = head_ln_w; h.beta = head_ln_b; h.eps = cfg.ln_eps;
+    h.x = S.cls.xout32; h.ldx = D; h.tokens = 1; h.gamma = head_ln_w; h.beta = head_ln_b; h.eps = cfg.ln_eps;
     h.W = labels ? loss_w : nullptr; h.labels = labels; h.cos_s = cfg.cos_s; h.cos_m = cfg.cos_m; h.B = B; h.D = D; h.C = cfg.num_class;
     h.emb = S.emb; h.logits = S.logits; h.ce = S.ce; h.correct = S.correct; h.xhat = S.xhat; h.rstd = S.head_rstd;
     if (labels) GSL_REQUIRE(loss_w != nullptr, "labelled forward needs loss.weight");
     return head_fwd(h, s);
+}
+
+// Backward of x_out = FeedForward(LN2(x_mid)) + x_mid on M rows.  In: dx / dxcat[:, :D] = gradient w.r.t. x_out (fp32 / fp16, the fp16 copy
+// already carries the fc2-output dropout mask).  Out: dA / dB of both LoRA layers; unless l == 0, dx / dxcat = gradient w.r.t. x_mid
+// (the fp16 copy masked for the attention to_out dropout).  Closed forms: SURVEY Appendix C.
+int Engine::ffn_backward(int l, int64_t M, __half* dxcat, float* dx, __half* dhcat, float* dxn, const __half* xn2cat, const __half* h16,
+                         const __half* gcat, const float* x_mid, const float* ln_mean, const float* ln_rstd, int accumulate, float pdrop,
+                         uint64_t dseed, cudaStream_t s) {
+    const int D = cfg.dim, H = cfg.mlp_dim, r = cfg.lora_rank;
+    const BlockFrozen& f = frozen[l];
+    const BlockCache& c = cache[l];
+    const float wscale = cfg.lora_scaling / cfg.grad_scale;     // dA, dB carry the LoRA scaling and undo the loss scale
+    float* gA1 = grad_flat + lora_offset(l, 0);
+    float* gB1 = grad_flat + lora_offset(l, 1);
+    float* gA2 = grad_flat + lora_offset(l, 2);
+    float* gB2 = grad_flat + lora_offset(l, 3);
+    int rc;
+    if ((rc = lora_down(dxcat, D + 16, c.B2T, D, dxcat + D, D + 16, M, D, r, s))) return rc;                                        // U2 = dY2 B2
+    if ((rc = skinny_tn(dxcat, D + 16, gcat + H, H + 16, gB2, r, 0, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // dB2 = s dY2^T T2
+    if ((rc = skinny_tn(gcat, H + 16, dxcat + D, D + 16, gA2, H, 1, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // dA2 = s U2^T G
+    {   // dH = (dY2 W2 + s U2 A2) * gelu'(H)
+        GemmArgs g;
+        g.A = dxcat; g.lda = D + 16; g.B = c.fc2T_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + 16;
+        g.epi = EPI_GELU_BWD; g.out0 = dhcat; g.ld0 = H + 16; g.aux = h16; g.ldaux = H;
+        g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 2);
+        if ((rc = gemm_f16(g, s))) return rc;
+    }
+    if ((rc = lora_down(dhcat, H + 16, c.B1T, H, dhcat + H, H + 16, M, H, r, s))) return rc;                                        // U1 = dH B1
+    if ((rc = skinny_tn(dhcat, H + 16, xn2cat + D, D + 16, gB1, r, 0, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc; // dB1 = s dH^T T1
+    if ((rc = skinny_tn(xn2cat, D + 16, dhcat + H, H + 16, gA1, D, 1, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc; // dA1 = s U1^T LN2(x)
+    if (l == 0) return 0;       // nothing trainable below block 0's FFN
+    {   // dLN2 = dH W1 + s U1 A1
+        GemmArgs g;
+        g.A = dhcat; g.lda = H + 16; g.B = c.fc1T_cat; g.ldb = H + 16; g.M = M; g.N = D; g.K = H + 16;
+        g.epi = EPI_F32; g.out0 = dxn; g.ld0 = D;
+        if ((rc = gemm_f16(g, s))) return rc;
+    }
+    return layernorm_bwd(dxn, D, x_mid, D, ln_mean, ln_rstd, f.ln2_w, dx, D, dx, D, dxcat, D + 16, M, D, pdrop, site_seed(dseed, l, 1), s);
 }
 
 int Engine::backward(int slot, const float* dlogits, const float* demb, int accumulate, cudaStream_t s) {
@@ -352,54 +422,54 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
     GSL_REQUIRE(S.batch > 0, "slot %d holds no forward", slot);
     GSL_REQUIRE(S.used_lora, "backward needs a forward run with use_lora = 1 (train mode, unmerged)");
     GSL_REQUIRE(dlogits || demb, "backward needs d logits and/or d emb");
-    const int B = S.batch, D = cfg.dim, H = cfg.mlp_dim, L = cfg.depth, inner = cfg.heads * 64, r = cfg.lora_rank;
+    const int B = S.batch, D = cfg.dim, L = cfg.depth, inner = cfg.heads * 64;
     const int64_t M = (int64_t)B * tokens;
-    const float gs = cfg.grad_scale;
-    const float wscale = cfg.lora_scaling / gs;     // dA, dB carry the LoRA scaling and undo the loss scale
     const uint64_t dseed = S.drop_seed;
     const float pdrop = dseed ? cfg.dropout : 0.f;
     int rc;
-    // gradient wrt the final residual stream: zero except the cls rows
-    if ((rc = fill_zero(dx32, (size_t)M * D * 4, s))) return rc;
-    if ((rc = fill_zero(dxcat16, (size_t)M * (D + 16) * 2, s))) return rc;
+    // ---------------- head: gradient of the B cls rows of the last block's output (scaled by the loss scale)
     HeadBwdArgs hb;
     hb.dlogits = dlogits; hb.demb = demb; hb.emb = S.emb; hb.W = loss_w; hb.labels = nullptr; hb.xhat = S.xhat; hb.rstd = S.head_rstd;
-    hb.gamma = head_ln_w; hb.cos_s = cfg.cos_s; hb.B = B; hb.D = D; hb.C = cfg.num_class; hb.tokens = tokens; hb.gscale = gs;
-    hb.dx = dx32; hb.lddx = D; hb.dx16 = dxcat16; hb.lddx16 = D + 16;
+    hb.gamma = head_ln_w; hb.cos_s = cfg.cos_s; hb.B = B; hb.D = D; hb.C = cfg.num_class; hb.tokens = 1; hb.gscale = cfg.grad_scale;
+    hb.dx = cls_dx32; hb.lddx = D; hb.dx16 = cls_dxcat16; hb.lddx16 = D + 16;
     hb.drop_p = pdrop; hb.drop_seed = site_seed(dseed, L - 1, 3);
     if ((rc = head_bwd(hb, s))) return rc;
-
-    for (int l = L - 1; l >= 0; --l) {
+    {   // ---------------- last block on the compacted cls rows
+        const int l = L - 1;
         const BlockFrozen& f = frozen[l];
         const BlockCache& c = cache[l];
         BlockActs& a = S.blk[l];
-        float* gA1 = grad_flat + lora_offset(l, 0);
-        float* gB1 = grad_flat + lora_offset(l, 1);
-        float* gA2 = grad_flat + lora_offset(l, 2);
-        float* gB2 = grad_flat + lora_offset(l, 3);
-        // ---------------- FFN: y = fc2(gelu(fc1(LN2(x)))) + x   (SURVEY Appendix C closed forms)
-        if ((rc = lora_down(dxcat16, D + 16, c.B2T, D, dxcat16 + D, D + 16, M, D, r, s))) return rc;                         // U2 = dY2 B2
-        if ((rc = skinny_tn(dxcat16, D + 16, a.gcat16 + H, H + 16, gB2, r, 0, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // dB2 = s dY2^T T2
-        if ((rc = skinny_tn(a.gcat16, H + 16, dxcat16 + D, D + 16, gA2, H, 1, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // dA2 = s U2^T G
-        {   // dH = (dY2 W2 + s U2 A2) * gelu'(H)
+        ClsActs& k = S.cls;
+        if ((rc = ffn_backward(l, B, cls_dxcat16, cls_dx32, cls_dhcat16, cls_dxn32, k.xn2cat16, k.h16, k.gcat16, k.xmid32, k.ln2_mean, k.ln2_rstd,
+                               accumulate, pdrop, dseed, s))) return rc;
+        if (l == 0) return 0;
+        {   // dO (cls rows) = dY Wo
             GemmArgs g;
-            g.A = dxcat16; g.lda = D + 16; g.B = c.fc2T_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + 16;
-            g.epi = EPI_GELU_BWD; g.out0 = dhcat16; g.ld0 = H + 16; g.aux = a.h16; g.ldaux = H;
-            g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 2);
+            g.A = cls_dxcat16; g.lda = D + 16; g.B = c.out_wT16; g.ldb = D; g.M = B; g.N = inner; g.K = D;
+            g.epi = EPI_F16; g.out0 = cls_do16; g.ld0 = inner;
             if ((rc = gemm_f16(g, s))) return rc;
         }
-        if ((rc = lora_down(dhcat16, H + 16, c.B1T, H, dhcat16 + H, H + 16, M, H, r, s))) return rc;                         // U1 = dH B1
-        if ((rc = skinny_tn(dhcat16, H + 16, a.xn2cat16 + D, D + 16, gB1, r, 0, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc; // dB1 = s dH^T T1
-        if ((rc = skinny_tn(a.xn2cat16, D + 16, dhcat16 + H, H + 16, gA1, D, 1, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc; // dA1 = s U1^T LN2(x)
-        if (l == 0) break;      // nothing trainable below block 0's FFN
-        {   // dLN2 = dH W1 + s U1 A1
+        if ((rc = cls_attention_bwd(a.qkv16, 3 * inner, k.o16, inner, cls_do16, inner, k.lse, dqkv16, 3 * inner, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
+        {   // dLN1 = dQKV Wqkv  (dense: dK / dV reach every token)
             GemmArgs g;
-            g.A = dhcat16; g.lda = H + 16; g.B = c.fc1T_cat; g.ldb = H + 16; g.M = M; g.N = D; g.K = H + 16;
+            g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
             g.epi = EPI_F32; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
-        if ((rc = layernorm_bwd(dxn32, D, S.x[2 * l + 1], D, a.ln2_mean, a.ln2_rstd, f.ln2_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, pdrop,
-                                site_seed(dseed, l, 1), s))) return rc;
+        // residual gradient of this block's input: zero except the cls rows
+        if ((rc = fill_zero(dx32, (size_t)M * D * 4, s))) return rc;
+        if ((rc = copy_cls_rows(cls_dx32, (int64_t)D * 4, dx32, (int64_t)tokens * D * 4, B, (int64_t)D * 4, s))) return rc;
+        if ((rc = layernorm_bwd(dxn32, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, pdrop,
+                                site_seed(dseed, l - 1, 3), s))) return rc;
+    }
+    for (int l = L - 2; l >= 0; --l) {
+        const BlockFrozen& f = frozen[l];
+        const BlockCache& c = cache[l];
+        BlockActs& a = S.blk[l];
+        // ---------------- FFN: y = fc2(gelu(fc1(LN2(x)))) + x
+        if ((rc = ffn_backward(l, M, dxcat16, dx32, dhcat16, dxn32, a.xn2cat16, a.h16, a.gcat16, S.x[2 * l + 1], a.ln2_mean, a.ln2_rstd, accumulate,
+                               pdrop, dseed, s))) return rc;
+        if (l == 0) break;      // nothing trainable below block 0's FFN
         // ---------------- attention: y = to_out(attn(to_qkv(LN1(x)))) + x
         {   // dO = dY Wo
             GemmArgs g;

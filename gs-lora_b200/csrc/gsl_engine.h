@@ -27,9 +27,15 @@ struct BlockActs {              // saved activations of one block for one slot
     __half *qkv16, *o16, *xn2cat16, *h16, *gcat16;
 };
 
+struct ClsActs {                // last block, compacted to the B cls rows (see gsl_clsattn.cu)
+    float *xin32, *xmid32, *xout32, *ln2_mean, *ln2_rstd, *lse;
+    __half *o16, *xn2cat16, *h16, *gcat16;
+};
+
 struct Slot {
     std::vector<float*> x;      // 2L+1 residual-stream snapshots, fp32 [M, D]
     std::vector<BlockActs> blk;
+    ClsActs cls;
     float *emb, *logits, *ce, *xhat, *head_rstd;
     int* correct;
     int batch = 0;
@@ -54,6 +60,7 @@ public:
     // transients (shared by all slots)
     __half *patches16, *xn16, *dxcat16, *dhcat16, *do16, *dqkv16;
     float *dx32, *dxn32, *skinny_ws;
+    float *cls_dx32, *cls_dxn32; __half *cls_dxcat16, *cls_dhcat16, *cls_do16;
     size_t skinny_ws_bytes = 0;
     void* pack_ptrs_dev = nullptr;
     int* group_offsets_dev = nullptr; int* tensor_offsets_dev = nullptr; float* group_norms_dev = nullptr; float* tensor_norms_dev = nullptr;
@@ -70,6 +77,10 @@ public:
     int64_t lora_offset(int block, int which) const;   // which: 0 A1, 1 B1, 2 A2, 3 B2
 private:
     size_t carve(bool assign);
+    int ffn_forward(int l, int64_t M, __half* xn2cat, float* ln_mean, float* ln_rstd, const float* x_mid, __half* h16, __half* gcat, float* x_out,
+                    int use_lora, float pdrop, uint64_t dseed, cudaStream_t s);
+    int ffn_backward(int l, int64_t M, __half* dxcat, float* dx, __half* dhcat, float* dxn, const __half* xn2cat, const __half* h16, const __half* gcat,
+                     const float* x_mid, const float* ln_mean, const float* ln_rstd, int accumulate, float pdrop, uint64_t dseed, cudaStream_t s);
 };
 
 }  // namespace gsl

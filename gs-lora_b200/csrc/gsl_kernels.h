@@ -64,6 +64,13 @@ int attention_fwd(const __half* qkv, int64_t ld, __half* out, int64_t ldo, float
 int attention_bwd(const __half* qkv, int64_t ld, const __half* out, int64_t ldo, const __half* dout, int64_t lddo, const float* lse,
                   __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s);
 
+// ---- last-block shortcut: single (cls) query attention + cls-row gather / scatter (gsl_clsattn.cu)
+int cls_attention_fwd(const __half* qkv, int64_t ld, __half* o_cls, int64_t ldo, float* lse_cls, int B, int N, int heads, float scale, cudaStream_t s);
+int cls_attention_bwd(const __half* qkv, int64_t ld, const __half* o_cls, int64_t ldo, const __half* do_cls, int64_t lddo, const float* lse_cls,
+                      __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s);
+// dst row b <- src row b (row pitches in bytes): with src_pitch = tokens * pitch this gathers the cls rows, with dst_pitch = tokens * pitch it scatters
+int copy_cls_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, int B, int64_t row_bytes, cudaStream_t s);
+
 // ---- head / losses (gsl_head.cu)
 struct HeadArgs {
     const float* x; int64_t ldx;      // final residual stream [B*N, D]; cls row = b * tokens

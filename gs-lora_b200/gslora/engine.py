@@ -143,7 +143,7 @@ class VitEngine:
         if what == F.SLOT_CORRECT:
             return self._view(p, (B,), torch.int32)
         if what == F.SLOT_XFINAL:
-            return self._view(p, (B * s.tokens, s.dim), torch.float32)
+            return self._view(p, (B, s.dim), torch.float32)
         raise ValueError(what)
 
     def forward(self, img: torch.Tensor, labels: Optional[torch.Tensor], slot: int = 0, use_lora: bool = True, dropout_seed: int = 0):

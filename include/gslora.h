@@ -126,6 +126,7 @@ int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* 
 /* selective backward of engine_cl.py:124: upstream d logits [B,C] and/or d emb [B,D] (fp32, may be NULL) ->
  * LoRA gradients written (accumulate = 0) or added (accumulate = 1) into grad_flat. */
 int gsl_engine_backward(void* handle, int slot, const float* dlogits, const float* demb, int accumulate, void* stream);
+/* XFINAL: fp32 [B, dim] -- the cls rows of the last block's output (the only rows of that block that are computed) */
 enum { GSL_SLOT_EMB = 0, GSL_SLOT_LOGITS = 1, GSL_SLOT_CE = 2, GSL_SLOT_CORRECT = 3, GSL_SLOT_XFINAL = 4 };
 void* gsl_engine_slot_ptr(void* handle, int slot, int what);
 int64_t gsl_engine_lora_offset(void* handle, int block, int which);   /* which: 0 A(net.0) 1 B(net.0) 2 A(net.3) 3 B(net.3) */

@@ -33,7 +33,15 @@ def engine_masks(cfg, B: int, base_seed: int, p: float, p_emb: float):
     N, D, H, L = cfg.tokens, cfg.dim, cfg.mlp_dim, cfg.depth
     m = {"emb": keep_mask(B * N, D, p_emb, site_seed(base_seed, L, 0)).view(B, N, D)}
     for i in range(L):
-        m[("attn", i)] = keep_mask(B * N, D, p, site_seed(base_seed, i, 1)).view(B, N, D)
-        m[("gelu", i)] = keep_mask(B * N, H, p, site_seed(base_seed, i, 2)).view(B, N, H)
-        m[("ffn", i)] = keep_mask(B * N, D, p, site_seed(base_seed, i, 3)).view(B, N, D)
+        if i < L - 1:
+            m[("attn", i)] = keep_mask(B * N, D, p, site_seed(base_seed, i, 1)).view(B, N, D)
+            m[("gelu", i)] = keep_mask(B * N, H, p, site_seed(base_seed, i, 2)).view(B, N, H)
+            m[("ffn", i)] = keep_mask(B * N, D, p, site_seed(base_seed, i, 3)).view(B, N, D)
+        else:
+            # last block: the engine only computes the B cls rows (compact row index b); the other tokens of this block never
+            # reach the loss, so their masks are irrelevant (ones)
+            for name, site, width in (("attn", 1, D), ("gelu", 2, H), ("ffn", 3, D)):
+                full = torch.ones(B, N, width)
+                full[:, 0, :] = keep_mask(B, width, p, site_seed(base_seed, i, site))
+                m[(name, i)] = full
     return m
