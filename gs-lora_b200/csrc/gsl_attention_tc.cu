@@ -355,24 +355,31 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         int it = 0;
         uint32_t n = 0;      // global block counter
         uint32_t m = 0;      // global key-tile counter
+        auto issue_sdp = [&](int qt, int kt) {      // S = Q_qt K_kt^T, dP = dO_qt V_kt^T
+            tcgen05_fence_after();
+            if (lane == 0) {
+                const uint64_t aq = atc_desc(sQ + qt * 16384), bk = atc_desc(sK + kt * 16384);
+                const uint64_t ad = atc_desc(sdO + qt * 16384), bv = atc_desc(sV + kt * 16384);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16<1>(tmem_base + T_S, aq + 2 * k, bk + 2 * k, idesc_s, k != 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16<1>(tmem_base + T_DP, ad + 2 * k, bv + 2 * k, idesc_s, k != 0);
+                umma_commit<1>(b_sdp_full);
+            }
+            __syncwarp();
+        };
         for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
             mbar_wait(b_slabs_full, it & 1);
-            if (it > 0) mbar_wait(b_dq_free, (it - 1) & 1);         // previous pair's dQ has been read out of TMEM
+            issue_sdp(0, 0);
             for (int kt = 0; kt < nt; ++kt, ++m) {
-                if (m > 0) mbar_wait(b_dkv_free, (m - 1) & 1);      // previous key tile's dK / dV have been read out
                 for (int qt = 0; qt < nt; ++qt, ++n) {
-                    tcgen05_fence_after();
-                    if (lane == 0) {
-                        const uint64_t aq = atc_desc(sQ + qt * 16384), bk = atc_desc(sK + kt * 16384);
-                        const uint64_t ad = atc_desc(sdO + qt * 16384), bv = atc_desc(sV + kt * 16384);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16<1>(tmem_base + T_S, aq + 2 * k, bk + 2 * k, idesc_s, k != 0);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16<1>(tmem_base + T_DP, ad + 2 * k, bv + 2 * k, idesc_s, k != 0);
-                        umma_commit<1>(b_sdp_full);
-                    }
-                    __syncwarp();
                     mbar_wait(b_pds_ready, n & 1);                  // P / dS tiles written, S / dP TMEM consumed
+                    // software pipeline: the next block's S / dP go to the tensor core first, so the workers can start on them
+                    // while this block's dQ / dV / dK MMAs run
+                    if (qt + 1 < nt) issue_sdp(qt + 1, kt);
+                    else if (kt + 1 < nt) issue_sdp(0, kt + 1);
+                    if (kt == 0 && qt == 0 && it > 0) mbar_wait(b_dq_free, (it - 1) & 1);   // previous pair's dQ has been read out of TMEM
+                    if (qt == 0 && m > 0) mbar_wait(b_dkv_free, (m - 1) & 1);               // previous key tile's dK / dV have been read out
                     tcgen05_fence_after();
                     if (lane == 0) {
 #pragma unroll
@@ -524,25 +531,22 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 mbar_arrive(b_dq_free);
-#pragma unroll
-                for (int tI = 0; tI < 2; ++tI) {
-                    const int q = tI * 128 + rl;
-                    if (tI < nt && q < N) {
-                        const uint32_t* qq = tI == 0 ? q0 : q1;
-                        uint4 u0, u1;
-                        u0.x = pack_half2(__uint_as_float(qq[0]) * scale, __uint_as_float(qq[1]) * scale);
-                        u0.y = pack_half2(__uint_as_float(qq[2]) * scale, __uint_as_float(qq[3]) * scale);
-                        u0.z = pack_half2(__uint_as_float(qq[4]) * scale, __uint_as_float(qq[5]) * scale);
-                        u0.w = pack_half2(__uint_as_float(qq[6]) * scale, __uint_as_float(qq[7]) * scale);
-                        u1.x = pack_half2(__uint_as_float(qq[8]) * scale, __uint_as_float(qq[9]) * scale);
-                        u1.y = pack_half2(__uint_as_float(qq[10]) * scale, __uint_as_float(qq[11]) * scale);
-                        u1.z = pack_half2(__uint_as_float(qq[12]) * scale, __uint_as_float(qq[13]) * scale);
-                        u1.w = pack_half2(__uint_as_float(qq[14]) * scale, __uint_as_float(qq[15]) * scale);
-                        uint4* dst = reinterpret_cast<uint4*>(dqkv + ((int64_t)b * N + q) * lddqkv + h * 64 + cg * 16);
-                        dst[0] = u0;
-                        dst[1] = u1;
-                    }
-                }
+                auto store_dq = [&](const uint32_t (&qq)[16], int q) {
+                    uint4 u0, u1;
+                    u0.x = pack_half2(__uint_as_float(qq[0]) * scale, __uint_as_float(qq[1]) * scale);
+                    u0.y = pack_half2(__uint_as_float(qq[2]) * scale, __uint_as_float(qq[3]) * scale);
+                    u0.z = pack_half2(__uint_as_float(qq[4]) * scale, __uint_as_float(qq[5]) * scale);
+                    u0.w = pack_half2(__uint_as_float(qq[6]) * scale, __uint_as_float(qq[7]) * scale);
+                    u1.x = pack_half2(__uint_as_float(qq[8]) * scale, __uint_as_float(qq[9]) * scale);
+                    u1.y = pack_half2(__uint_as_float(qq[10]) * scale, __uint_as_float(qq[11]) * scale);
+                    u1.z = pack_half2(__uint_as_float(qq[12]) * scale, __uint_as_float(qq[13]) * scale);
+                    u1.w = pack_half2(__uint_as_float(qq[14]) * scale, __uint_as_float(qq[15]) * scale);
+                    uint4* dst = reinterpret_cast<uint4*>(dqkv + ((int64_t)b * N + q) * lddqkv + h * 64 + cg * 16);
+                    dst[0] = u0;
+                    dst[1] = u1;
+                };
+                if (rl < N) store_dq(q0, rl);
+                if (nt > 1 && 128 + rl < N) store_dq(q1, 128 + rl);
             }
         }
     }

@@ -9,74 +9,86 @@
 
 namespace gsl {
 
-static constexpr int CLS_MAX_KEYS = 256;     // keys per lane: 8
+static constexpr int CLS_MAX_KEYS = 256;
+static constexpr int CLS_ITERS = CLS_MAX_KEYS / 4;      // 4 keys per warp iteration: 8 lanes x 16 bytes cover one 128-byte K / V row
 
-__device__ __forceinline__ float dot64_h(const __half* __restrict__ row, const float (&q)[64]) {
-    float acc = 0.f;
-    const uint4* r4 = reinterpret_cast<const uint4*>(row);
+// lane layout: group g = lane / 8 owns keys j = 4 i + g, chunk c = lane % 8 owns head dims [8c, 8c + 8)
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint4 u = __ldg(r4 + c);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f = unpack_half2(w[k]);
-            acc = fmaf(f.x, q[c * 8 + 2 * k], acc);
-            acc = fmaf(f.y, q[c * 8 + 2 * k + 1], acc);
-        }
-    }
-    return acc;
+    for (int k = 0; k < 4; ++k) { const float2 f = unpack_half2(w[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+}
+__device__ __forceinline__ float group_sum8(float v) {      // sum over the 8 lanes of a key group
+    v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+__device__ __forceinline__ float across_groups(float v) {   // sum over the 4 key groups (same chunk)
+    v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
 }
 
 // qkv fp16 [B*N, ld] (q | k | v column blocks of heads*64).  o_cls fp16 [B, ldo] (heads*64 columns), lse_cls [B, heads].
 __global__ void __launch_bounds__(128) cls_attention_fwd_kernel(const __half* __restrict__ qkv, int64_t ld, __half* __restrict__ o_cls, int64_t ldo,
                                                                 float* __restrict__ lse_cls, int B, int N, int heads, float scale) {
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
     if (w >= B * heads) return;
     const int b = w / heads, h = w % heads, D = heads * 64;
-    const __half* base = qkv + (int64_t)b * N * ld + h * 64;
-    float q[64];
-    {
-        const uint4* q4 = reinterpret_cast<const uint4*>(base);      // token 0 = cls
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 u = __ldg(q4 + c);
-            const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { const float2 f = unpack_half2(ww[k]); q[c * 8 + 2 * k] = f.x; q[c * 8 + 2 * k + 1] = f.y; }
-        }
-    }
-    float s[CLS_MAX_KEYS / 32];
+    const __half* base = qkv + (int64_t)b * N * ld + h * 64 + c * 8;
+    float q[8];
+    load8(base, q);                                           // token 0 = cls
+    const int iters = (N + 3) >> 2;
+    float s[CLS_ITERS];
     float mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < CLS_MAX_KEYS / 32; ++i) {
-        const int j = lane + 32 * i;
-        s[i] = j < N ? scale * dot64_h(base + (int64_t)j * ld + D, q) : -INFINITY;
-        mx = fmaxf(mx, s[i]);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
+    for (int i = 0; i < CLS_ITERS; ++i) {
+        s[i] = -INFINITY;
+        if (i < iters) {
+            const int j = 4 * i + g;
+            float acc = 0.f;
+            if (j < N) {
+                float k[8];
+                load8(base + (int64_t)j * ld + D, k);
 #pragma unroll
-    for (int i = 0; i < CLS_MAX_KEYS / 32; ++i) { s[i] = (lane + 32 * i) < N ? __expf(s[i] - mx) : 0.f; sum += s[i]; }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    // o[d] = sum_j p_j V[j, d]; lane owns d = 2*lane, 2*lane+1; p_j broadcast by shuffle, V rows read coalesced
-    float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < N; ++j) {
-        float p = 0.f;
-#pragma unroll
-        for (int i = 0; i < CLS_MAX_KEYS / 32; ++i) if ((j >> 5) == i) p = __shfl_sync(0xffffffffu, s[i], j & 31);
-        const float2 v = unpack_half2(__ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)j * ld + 2 * D) + lane));
-        o0 = fmaf(p, v.x, o0);
-        o1 = fmaf(p, v.y, o1);
+                for (int d = 0; d < 8; ++d) acc = fmaf(k[d], q[d], acc);
+            }
+            acc = group_sum8(acc);
+            s[i] = j < N ? acc * scale : -INFINITY;
+            mx = fmaxf(mx, s[i]);
+        }
     }
-    *reinterpret_cast<uint32_t*>(o_cls + (int64_t)b * ldo + h * 64 + 2 * lane) = pack_half2(o0 * inv, o1 * inv);
-    if (lane == 0) lse_cls[(int64_t)b * heads + h] = mx + __logf(sum);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    float sum = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < CLS_ITERS; ++i) {
+        if (i < iters) {
+            const int j = 4 * i + g;
+            if (j < N) {
+                const float p = __expf(s[i] - mx);
+                sum += p;
+                float v[8];
+                load8(base + (int64_t)j * ld + 2 * D, v);
+#pragma unroll
+                for (int d = 0; d < 8; ++d) o[d] = fmaf(p, v[d], o[d]);
+            }
+        }
+    }
+    sum = across_groups(sum);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d] = across_groups(o[d]);
+    if (g == 0) {
+        const float inv = 1.0f / sum;
+        uint4 u;
+        u.x = pack_half2(o[0] * inv, o[1] * inv); u.y = pack_half2(o[2] * inv, o[3] * inv);
+        u.z = pack_half2(o[4] * inv, o[5] * inv); u.w = pack_half2(o[6] * inv, o[7] * inv);
+        *reinterpret_cast<uint4*>(o_cls + (int64_t)b * ldo + h * 64 + c * 8) = u;
+        if (c == 0) lse_cls[(int64_t)b * heads + h] = mx + __logf(sum);
+    }
 }
 
 int cls_attention_fwd(const __half* qkv, int64_t ld, __half* o_cls, int64_t ldo, float* lse_cls, int B, int N, int heads, float scale, cudaStream_t s) {
-    GSL_REQUIRE(N <= CLS_MAX_KEYS && ld % 8 == 0 && ldo % 2 == 0, "cls_attention: tokens=%d > %d or unaligned pitch", N, CLS_MAX_KEYS);
+    GSL_REQUIRE(N <= CLS_MAX_KEYS && ld % 8 == 0 && ldo % 8 == 0, "cls_attention: tokens=%d > %d or unaligned pitch", N, CLS_MAX_KEYS);
     const int warps = 4;
     cls_attention_fwd_kernel<<<(B * heads + warps - 1) / warps, warps * 32, 0, s>>>(qkv, ld, o_cls, ldo, lse_cls, B, N, heads, scale);
     GSL_COUNT_LAUNCH(1);
@@ -85,78 +97,68 @@ int cls_attention_fwd(const __half* qkv, int64_t ld, __half* o_cls, int64_t ldo,
 }
 
 // Backward for the single cls query.  do_cls fp16 [B, lddo]; writes dqkv fp16 [B*N, lddqkv]: dQ row of token 0, dK / dV rows of every token.
-// (dQ rows of tokens > 0 are zero: the caller clears that column block.)
+// (dQ rows of tokens > 0 are zero: the launcher clears that column block.)
 __global__ void __launch_bounds__(128) cls_attention_bwd_kernel(const __half* __restrict__ qkv, int64_t ld, const __half* __restrict__ o_cls, int64_t ldo,
                                                                 const __half* __restrict__ do_cls, int64_t lddo, const float* __restrict__ lse_cls,
                                                                 __half* __restrict__ dqkv, int64_t lddqkv, int B, int N, int heads, float scale) {
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
     if (w >= B * heads) return;
     const int b = w / heads, h = w % heads, D = heads * 64;
-    const __half* base = qkv + (int64_t)b * N * ld + h * 64;
-    __half* dbase = dqkv + (int64_t)b * N * lddqkv + h * 64;
-    float q[64], g[64];
-    {
-        const uint4* q4 = reinterpret_cast<const uint4*>(base);
-        const uint4* g4 = reinterpret_cast<const uint4*>(do_cls + (int64_t)b * lddo + h * 64);
+    const __half* base = qkv + (int64_t)b * N * ld + h * 64 + c * 8;
+    __half* dbase = dqkv + (int64_t)b * N * lddqkv + h * 64 + c * 8;
+    float q[8], gr[8], ov[8];
+    load8(base, q);
+    load8(do_cls + (int64_t)b * lddo + h * 64 + c * 8, gr);
+    load8(o_cls + (int64_t)b * ldo + h * 64 + c * 8, ov);
+    float dl = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 u = __ldg(q4 + c), v = __ldg(g4 + c);
-            const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, vw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 a = unpack_half2(uw[k]), c2 = unpack_half2(vw[k]);
-                q[c * 8 + 2 * k] = a.x; q[c * 8 + 2 * k + 1] = a.y;
-                g[c * 8 + 2 * k] = c2.x; g[c * 8 + 2 * k + 1] = c2.y;
-            }
-        }
-    }
-    // delta = dO . O  (lane owns 2 elements)
-    const float2 ov = unpack_half2(*reinterpret_cast<const uint32_t*>(o_cls + (int64_t)b * ldo + h * 64 + 2 * lane));
-    const float2 gv = unpack_half2(*reinterpret_cast<const uint32_t*>(do_cls + (int64_t)b * lddo + h * 64 + 2 * lane));
-    const float delta = warp_sum(ov.x * gv.x + ov.y * gv.y);
+    for (int d = 0; d < 8; ++d) dl = fmaf(gr[d], ov[d], dl);
+    const float delta = group_sum8(dl);                       // dO . O
     const float lse = lse_cls[(int64_t)b * heads + h];
-    float ds[CLS_MAX_KEYS / 32];
-#pragma unroll
-    for (int i = 0; i < CLS_MAX_KEYS / 32; ++i) {
-        const int j = lane + 32 * i;
-        ds[i] = 0.f;
+    const int iters = (N + 3) >> 2;
+    float dq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        const int j = 4 * i + g;
+        float sa = 0.f, da = 0.f;
+        float k[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, v[8];
         if (j < N) {
-            const float p = __expf(scale * dot64_h(base + (int64_t)j * ld + D, q) - lse);
-            const float dp = dot64_h(base + (int64_t)j * ld + 2 * D, g);
-            ds[i] = p * (dp - delta);
-            // dV[j, :] = p * dO ; dK[j, :] = scale * dS_j * q   (this lane owns the whole 128-byte row of key j)
-            uint4* dv4 = reinterpret_cast<uint4*>(dbase + (int64_t)j * lddqkv + 2 * D);
-            uint4* dk4 = reinterpret_cast<uint4*>(dbase + (int64_t)j * lddqkv + D);
-            const float kd = scale * ds[i];
+            load8(base + (int64_t)j * ld + D, k);
+            load8(base + (int64_t)j * ld + 2 * D, v);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint4 a, k4;
-                a.x = pack_half2(p * g[8 * c], p * g[8 * c + 1]); a.y = pack_half2(p * g[8 * c + 2], p * g[8 * c + 3]);
-                a.z = pack_half2(p * g[8 * c + 4], p * g[8 * c + 5]); a.w = pack_half2(p * g[8 * c + 6], p * g[8 * c + 7]);
-                k4.x = pack_half2(kd * q[8 * c], kd * q[8 * c + 1]); k4.y = pack_half2(kd * q[8 * c + 2], kd * q[8 * c + 3]);
-                k4.z = pack_half2(kd * q[8 * c + 4], kd * q[8 * c + 5]); k4.w = pack_half2(kd * q[8 * c + 6], kd * q[8 * c + 7]);
-                dv4[c] = a;
-                dk4[c] = k4;
-            }
+            for (int d = 0; d < 8; ++d) { sa = fmaf(k[d], q[d], sa); da = fmaf(v[d], gr[d], da); }
+        }
+        sa = group_sum8(sa);
+        da = group_sum8(da);
+        if (j < N) {
+            const float p = __expf(sa * scale - lse);
+            const float ds = p * (da - delta);
+            const float kd = scale * ds;
+            uint4 a, k4;
+            a.x = pack_half2(p * gr[0], p * gr[1]); a.y = pack_half2(p * gr[2], p * gr[3]);
+            a.z = pack_half2(p * gr[4], p * gr[5]); a.w = pack_half2(p * gr[6], p * gr[7]);
+            k4.x = pack_half2(kd * q[0], kd * q[1]); k4.y = pack_half2(kd * q[2], kd * q[3]);
+            k4.z = pack_half2(kd * q[4], kd * q[5]); k4.w = pack_half2(kd * q[6], kd * q[7]);
+            *reinterpret_cast<uint4*>(dbase + (int64_t)j * lddqkv + 2 * D) = a;          // dV[j] = p dO
+            *reinterpret_cast<uint4*>(dbase + (int64_t)j * lddqkv + D) = k4;             // dK[j] = scale dS_j q
+#pragma unroll
+            for (int d = 0; d < 8; ++d) dq[d] = fmaf(ds, k[d], dq[d]);                    // dq += dS_j K[j]
         }
     }
-    // dq[d] = scale * sum_j dS_j K[j, d]
-    float d0 = 0.f, d1 = 0.f;
-    for (int j = 0; j < N; ++j) {
-        float dsj = 0.f;
 #pragma unroll
-        for (int i = 0; i < CLS_MAX_KEYS / 32; ++i) if ((j >> 5) == i) dsj = __shfl_sync(0xffffffffu, ds[i], j & 31);
-        const float2 kv = unpack_half2(__ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)j * ld + D) + lane));
-        d0 = fmaf(dsj, kv.x, d0);
-        d1 = fmaf(dsj, kv.y, d1);
+    for (int d = 0; d < 8; ++d) dq[d] = across_groups(dq[d]);
+    if (g == 0) {
+        uint4 u;
+        u.x = pack_half2(dq[0] * scale, dq[1] * scale); u.y = pack_half2(dq[2] * scale, dq[3] * scale);
+        u.z = pack_half2(dq[4] * scale, dq[5] * scale); u.w = pack_half2(dq[6] * scale, dq[7] * scale);
+        *reinterpret_cast<uint4*>(dbase) = u;                                              // dQ of the cls token
     }
-    *reinterpret_cast<uint32_t*>(dbase + 2 * lane) = pack_half2(d0 * scale, d1 * scale);
 }
 
 int cls_attention_bwd(const __half* qkv, int64_t ld, const __half* o_cls, int64_t ldo, const __half* do_cls, int64_t lddo, const float* lse_cls,
                       __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s) {
-    GSL_REQUIRE(N <= CLS_MAX_KEYS && ld % 8 == 0 && lddqkv % 8 == 0 && lddo % 8 == 0, "cls_attention_bwd: tokens=%d > %d or unaligned pitch", N, CLS_MAX_KEYS);
+    GSL_REQUIRE(N <= CLS_MAX_KEYS && ld % 8 == 0 && lddqkv % 8 == 0 && lddo % 8 == 0 && ldo % 8 == 0, "cls_attention_bwd: tokens=%d > %d or unaligned pitch", N, CLS_MAX_KEYS);
     // dQ of every non-cls token is zero
     GSL_CHECK_CUDA(cudaMemset2DAsync(dqkv, (size_t)lddqkv * 2, 0, (size_t)heads * 64 * 2, (size_t)B * N, s));
     const int warps = 4;
