@@ -172,7 +172,7 @@ int Engine::bind_params(const void* const* p, int n, float* lora, float* grads) 
     GSL_REQUIRE(n == GSL_NUM_GLOBAL_PARAMS + GSL_NUM_BLOCK_PARAMS * cfg.depth, "expected %d parameter pointers, got %d",
                 GSL_NUM_GLOBAL_PARAMS + GSL_NUM_BLOCK_PARAMS * cfg.depth, n);
     pos_embedding = (const float*)p[0]; cls_token = (const float*)p[1]; patch_w = (const float*)p[2]; patch_b = (const float*)p[3];
-    head_ln_w = (const float*)p[4]; head_ln_b = (const float*)p[5]; loss_w = (const float*)p[6];
+    head_ln_w = (const float*)p[4]; head_ln_b = (const float*)p[5]; loss_w = (const float*)p[6]; head_b = (const float*)p[7];
     frozen.assign(cfg.depth, BlockFrozen());
     for (int l = 0; l < cfg.depth; ++l) {
         const void* const* q = p + GSL_NUM_GLOBAL_PARAMS + GSL_NUM_BLOCK_PARAMS * l;
@@ -371,9 +371,10 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
     }
     HeadArgs h;
     h.x = S.cls.xout32; h.ldx = D; h.tokens = 1; h.gamma = head_ln_w; h.beta = head_ln_b; h.eps = cfg.ln_eps;
-    h.W = labels ? loss_w : nullptr; h.labels = labels; h.cos_s = cfg.cos_s; h.cos_m = cfg.cos_m; h.B = B; h.D = D; h.C = cfg.num_class;
+    h.head_type = cfg.head_type; h.head_b = head_b;
+    h.W = (labels || cfg.head_type == 1) ? loss_w : nullptr; h.labels = labels; h.cos_s = cfg.cos_s; h.cos_m = cfg.cos_m; h.B = B; h.D = D; h.C = cfg.num_class;
     h.emb = S.emb; h.logits = S.logits; h.ce = S.ce; h.correct = S.correct; h.xhat = S.xhat; h.rstd = S.head_rstd;
-    if (labels) GSL_REQUIRE(loss_w != nullptr, "labelled forward needs loss.weight");
+    if (labels && cfg.head_type == 0) GSL_REQUIRE(loss_w != nullptr, "labelled forward needs loss.weight");
     return head_fwd(h, s);
 }
 
@@ -430,6 +431,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
     // ---------------- head: gradient of the B cls rows of the last block's output (scaled by the loss scale)
     HeadBwdArgs hb;
     hb.dlogits = dlogits; hb.demb = demb; hb.emb = S.emb; hb.W = loss_w; hb.labels = nullptr; hb.xhat = S.xhat; hb.rstd = S.head_rstd;
+    hb.head_type = cfg.head_type;
     hb.gamma = head_ln_w; hb.cos_s = cfg.cos_s; hb.B = B; hb.D = D; hb.C = cfg.num_class; hb.tokens = 1; hb.gscale = cfg.grad_scale;
     hb.dx = cls_dx32; hb.lddx = D; hb.dx16 = cls_dxcat16; hb.lddx16 = D + 16;
     hb.drop_p = pdrop; hb.drop_seed = site_seed(dseed, L - 1, 3);

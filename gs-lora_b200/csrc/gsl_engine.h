@@ -48,7 +48,7 @@ public:
     GslConfig cfg;
     int tokens, patch_dim, M_max;
     // caller-owned parameter memory
-    const float *pos_embedding, *cls_token, *patch_w, *patch_b, *head_ln_w, *head_ln_b, *loss_w;
+    const float *pos_embedding, *cls_token, *patch_w, *patch_b, *head_ln_w, *head_ln_b, *loss_w, *head_b;
     std::vector<BlockFrozen> frozen;
     float* lora_flat = nullptr;     // [depth * (rD + Hr + rH + Dr)] fp32, block-major: A1, B1, A2, B2
     float* grad_flat = nullptr;

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(HeadArgs a) {
         dot = warp_sum(dot); wn = warp_sum(wn);
         if (lane == 0) {
             const float cosv = dot / (enorm * fmaxf(sqrtf(wn), 1e-12f));
-            const float lg = a.cos_s * (c == label ? cosv - a.cos_m : cosv);
+            const float lg = a.head_type == 1 ? dot + (a.head_b ? a.head_b[c] : 0.f)          // heads.head Linear (modified_VIT.py:35-37)
+                                              : a.cos_s * (c == label ? cosv - a.cos_m : cosv);
             s_logit[c] = lg;
             a.logits[(int64_t)b * C + c] = lg;
         }
@@ -128,7 +129,16 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_bwd_kernel(HeadBwdArgs a) {
     float en = 0.f;
     for (int d = tid; d < D; d += HEAD_THREADS) { en += e[d] * e[d]; s_de[d] = 0.f; }
     const float enorm = fmaxf(sqrtf(block_sum(en, red)), 1e-12f);
-    if (a.dlogits && a.W) {
+    if (a.dlogits && a.W && a.head_type == 1) {
+        // Linear head: d emb = d logits . W
+        for (int c = tid; c < C; c += HEAD_THREADS) s_dc[c] = a.dlogits[(int64_t)b * C + c];
+        __syncthreads();
+        for (int d = tid; d < D; d += HEAD_THREADS) {
+            float acc = 0.f;
+            for (int c = 0; c < C; ++c) acc += s_dc[c] * __ldg(a.W + (int64_t)c * D + d);
+            s_de[d] = acc;
+        }
+    } else if (a.dlogits && a.W) {
         for (int c = warp; c < C; c += HEAD_THREADS / 32) {
             const float* w = a.W + (int64_t)c * D;
             float wn = 0.f;

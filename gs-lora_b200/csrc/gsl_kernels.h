@@ -76,7 +76,9 @@ struct HeadArgs {
     const float* x; int64_t ldx;      // final residual stream [B*N, D]; cls row = b * tokens
     int tokens;
     const float* gamma; const float* beta; float eps;    // mlp_head LayerNorm
-    const float* W;                   // [C, D] CosFace weight (loss.weight)
+    const float* W;                   // [C, D] CosFace weight (loss.weight) or Linear head weight
+    const float* head_b = nullptr;    // [C] Linear head bias (head_type 1)
+    int head_type = 0;                // 0 = CosFace (vit_face.py:171-208), 1 = Linear (torchvision heads.head)
     const int64_t* labels;            // [B]
     float cos_s, cos_m;
     int B, D, C;
@@ -95,6 +97,7 @@ struct HeadBwdArgs {
     const float* demb;                // [B, D] or null
     const float* emb; const float* W; const int64_t* labels; const float* xhat; const float* rstd; const float* gamma;
     float cos_s; int B, D, C, tokens;
+    int head_type = 0;
     float gscale;
     float* dx; int64_t lddx; __half* dx16; int64_t lddx16;
     float drop_p = 0.f; uint32_t drop_seed = 0;      // mask of the last block's fc2-output dropout, applied to dx16 only

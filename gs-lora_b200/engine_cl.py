@@ -113,8 +113,8 @@ def get_structure_loss(model: torch.nn.Module, imagenet=False):
     """engine_cl.get_structure_loss (engine_cl.py:349-432): sum over Transformer blocks of the L2 norm of the block's four
     LoRA matrices.  Differentiable w.r.t. the LoRA parameters (gradient P / ||g||, 0 at ||g|| = 0 where the reference NaNs)."""
     m = _unwrap(model)
-    if imagenet:
-        raise NotImplementedError("gslora-b200: the torchvision ViT-B/16 family (config 4) is not built yet")
+    # `imagenet` only selects parameter NAMES in the reference (encoder.layers.encoder_layer_{i}.mlp.{0,3}.lora_{A,B}, 12 groups hard-coded,
+    # engine_cl.py:395-402); here the groups are the engine's per-block LoRA slices of whichever engine-backed model is passed.
     m.ensure_engine(1)
     m.sync_engine()
     return _StructureLossFn.apply(m, *m.lora_parameters())

@@ -31,11 +31,11 @@ def lib():
 class GslConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("image_size", "patch_size", "channels", "dim", "depth", "heads", "mlp_dim", "num_class",
                                               "lora_rank", "max_batch", "num_slots", "patch_order")] + \
-               [(n, ctypes.c_float) for n in ("attn_scale", "ln_eps", "cos_s", "cos_m", "lora_scaling", "grad_scale", "dropout", "emb_dropout")]
+               [(n, ctypes.c_float) for n in ("attn_scale", "ln_eps", "cos_s", "cos_m", "lora_scaling", "grad_scale", "dropout", "emb_dropout")] + [("head_type", ctypes.c_int32)]
 
 
 SLOT_EMB, SLOT_LOGITS, SLOT_CE, SLOT_CORRECT, SLOT_XFINAL = range(5)
-NUM_GLOBAL_PARAMS, NUM_BLOCK_PARAMS = 7, 12
+NUM_GLOBAL_PARAMS, NUM_BLOCK_PARAMS = 8, 12
 
 
 def _declare(L):

@@ -32,6 +32,7 @@ class EngineSpec:
     grad_scale: float = 1024.0
     dropout: float = 0.0
     emb_dropout: float = 0.0
+    head_type: int = 0          # 0 CosFace (ViT_face), 1 Linear + bias (torchvision heads.head)
 
     @property
     def tokens(self) -> int:
@@ -57,7 +58,7 @@ class VitEngine:
                                lora_rank=spec.lora_rank, max_batch=self.max_batch, num_slots=self.num_slots,
                                patch_order=spec.patch_order, attn_scale=spec.attn_scale, ln_eps=spec.ln_eps, cos_s=spec.cos_s,
                                cos_m=spec.cos_m, lora_scaling=1.0 / spec.lora_rank, grad_scale=spec.grad_scale,
-                               dropout=spec.dropout, emb_dropout=spec.emb_dropout)
+                               dropout=spec.dropout, emb_dropout=spec.emb_dropout, head_type=spec.head_type)
         L = F.lib()
         nbytes = L.gsl_engine_workspace_bytes(ctypes.byref(self.cfg))
         if nbytes == 0:

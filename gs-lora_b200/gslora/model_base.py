@@ -1,0 +1,168 @@
+"""Engine plumbing shared by the engine-backed drop-in models (ViT_face, ModifiedViT): lazily creates the native engine,
+keeps the LoRA nn.Parameters as views of the engine's flat fp32 buffer, refreshes the fp16 operand caches when a frozen weight
+changed (load_state_dict, loralib merge / un-merge), hands out activation slots and wires the selective backward into autograd."""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _ffi as F
+from .engine import EngineSpec, VitEngine
+
+
+class _EngineFn(torch.autograd.Function):
+    """One autograd node for the whole network: inputs are the LoRA matrices, outputs (logits, emb)."""
+
+    @staticmethod
+    def forward(ctx, model, img, label, always_logits, *lora_params):
+        eng = model._engine
+        slot = model._take_slot()
+        B = eng.forward(img, label, slot, use_lora=True, dropout_seed=model.dropout_seed())
+        ctx.model, ctx.slot, ctx.B, ctx.stamp = model, slot, B, model._slot_stamp[slot]
+        emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
+        if label is None and not always_logits:
+            return emb
+        return eng.slot_tensor(slot, F.SLOT_LOGITS, B).clone(), emb
+
+    @staticmethod
+    def backward(ctx, *grads):
+        model, eng, slot = ctx.model, ctx.model._engine, ctx.slot
+        if model._slot_stamp[slot] != ctx.stamp:
+            raise RuntimeError("gslora-b200: the activations of this forward were overwritten by later forwards; raise "
+                               "GSLORA_SLOTS (activation sets kept alive) or call backward sooner")
+        if len(grads) == 2:
+            dlogits, demb = grads
+        else:
+            dlogits, demb = None, grads[0]
+        dlogits = dlogits.contiguous().float() if dlogits is not None else None
+        demb = demb.contiguous().float() if demb is not None else None
+        eng.backward(slot, dlogits, demb, accumulate=False)
+        out = [eng.lora_view(eng.grad_flat, l, w).clone() for l in range(eng.spec.depth) for w in range(4)]
+        return (None, None, None, None, *out)
+
+
+
+class EngineBackedModel(nn.Module):
+    """Subclasses provide: lora_layers() -> iterable of (fc1, fc2) loralib.Linear pairs per block, _frozen_tensors() -> the
+    pointer table of include/gslora.h, engine_spec() -> EngineSpec, and the attributes dropout_p / emb_dropout_p."""
+
+    def _init_engine_state(self):
+        # engine state (not parameters / buffers: never part of state_dict)
+        self._engine: Optional[VitEngine] = None
+        self._frozen_sig = None
+        self._lora_sig = None
+        self._slot_next = 0
+        self._slot_stamp: List[int] = []
+
+    def __deepcopy__(self, memo):
+        import copy
+        eng, self._engine = self._engine, None
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            for k, v in self.__dict__.items():
+                setattr(new, k, copy.deepcopy(v, memo))
+        finally:
+            self._engine = eng
+        new._engine, new._frozen_sig, new._lora_sig = None, None, None
+        return new
+
+
+    def lora_parameters(self) -> List[nn.Parameter]:
+        out = []
+        for fc1, fc2 in self.lora_layers():
+            out += [fc1.lora_A, fc1.lora_B, fc2.lora_A, fc2.lora_B]
+        return out
+
+
+
+    def ensure_engine(self, batch: int, slots: Optional[int] = None) -> VitEngine:
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise F.GslError("gslora-b200: ViT_face executes on a CUDA device (sm_100a) only; there is no CPU fallback")
+        slots = slots or int(os.environ.get("GSLORA_SLOTS", "2"))
+        e = self._engine
+        if e is None or e.device != dev or e.max_batch < batch or e.num_slots < slots:
+            old = e
+            cap = max(batch, old.max_batch if old is not None and old.device == dev else 0)
+            self._engine = None
+            del old, e
+            self._engine = VitEngine(self.engine_spec(), dev, cap, slots)
+            self._frozen_sig = self._lora_sig = None
+            self._slot_stamp = [0] * slots
+            self._slot_next = 0
+        return self._engine
+
+    def sync_engine(self, force_lora: bool = False):
+        """Re-link parameters into the engine and refresh its fp16 operand caches if anything changed."""
+        eng = self._engine
+        relinked = False
+        for l, (fc1, fc2) in enumerate(self.lora_layers()):
+            for w, p in enumerate((fc1.lora_A, fc1.lora_B, fc2.lora_A, fc2.lora_B)):
+                view = eng.lora_view(eng.lora_flat, l, w)
+                if p.data_ptr() != view.data_ptr():
+                    view.copy_(p.data)
+                    p.data = view
+                    relinked = True
+        params = self._frozen_tensors()
+        frozen = [None if t is None else t.data for t in params]
+        for t in frozen:
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+                raise F.GslError("gslora-b200: frozen parameters must be contiguous fp32")
+        sig = tuple((0, 0) if q is None else (q.data_ptr(), q._version) for q in params)
+        sig += tuple(m._gsl_generation for pair in self.lora_layers() for m in pair)
+        if sig != self._frozen_sig:
+            eng.bind(frozen)
+            eng.refresh_frozen()
+            self._frozen_sig = sig
+            self._lora_sig = None
+        lsig = tuple(p._version for p in self.lora_parameters()) + (eng.opt_step,)
+        if relinked or force_lora or lsig != self._lora_sig:
+            eng.refresh_lora()
+            self._lora_sig = lsig
+
+    def mark_lora_updated_by_engine(self):
+        self._lora_sig = tuple(p._version for p in self.lora_parameters()) + (self._engine.opt_step,)
+
+    def _take_slot(self) -> int:
+        s = self._slot_next
+        self._slot_next = (s + 1) % self._engine.num_slots
+        self._slot_stamp[s] += 1
+        return s
+
+    def dropout_seed(self) -> int:
+        """Non-zero seed for the engine's counter-based dropout masks in train mode (drawn from torch's CPU generator, so
+        torch.manual_seed makes runs reproducible); 0 (= no dropout) in eval mode or when both probabilities are 0."""
+        if not self.training or (self.dropout_p <= 0.0 and self.emb_dropout_p <= 0.0) or os.environ.get("GSLORA_DROPOUT", "on") == "off":
+            return 0
+        return int(torch.randint(1, 2 ** 62, (1,)).item())
+
+    def _merged(self) -> bool:
+        states = {m.merged for pair in self.lora_layers() for m in pair}
+        if len(states) != 1:
+            raise RuntimeError("gslora-b200: LoRA layers are in mixed merged / un-merged states")
+        return states.pop()
+
+    # ------------------------------------------------------------------ forward
+    def _engine_forward(self, img, label=None, always_logits: bool = False):
+        """(logits, emb) if `label` is given (or always_logits) else emb."""
+        img = img.float().contiguous()
+        if label is not None:
+            label = label.to(device=img.device, dtype=torch.int64).contiguous()
+        eng = self.ensure_engine(img.shape[0])
+        self.sync_engine()
+        merged = self._merged()
+        lora_params = self.lora_parameters()
+        need_grad = torch.is_grad_enabled() and not merged and any(p.requires_grad for p in lora_params)
+        if need_grad:
+            return _EngineFn.apply(self, img, label, always_logits, *lora_params)
+        slot = self._take_slot()
+        B = eng.forward(img, label, slot, use_lora=not merged, dropout_seed=self.dropout_seed())
+        emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
+        if label is None and not always_logits:
+            return emb
+        return eng.slot_tensor(slot, F.SLOT_LOGITS, B).clone(), emb

@@ -22,13 +22,20 @@ _NAMES = ["transformer.layers.{}.1.fn.fn.net.0.lora_A", "transformer.layers.{}.1
           "transformer.layers.{}.1.fn.fn.net.3.lora_A", "transformer.layers.{}.1.fn.fn.net.3.lora_B"]
 
 
+_NAMES_TV = ["encoder.layers.encoder_layer_{}.mlp.0.lora_A", "encoder.layers.encoder_layer_{}.mlp.0.lora_B",
+             "encoder.layers.encoder_layer_{}.mlp.3.lora_A", "encoder.layers.encoder_layer_{}.mlp.3.lora_B"]
+
+
 def get_norm_of_lora(model, type="L2", group_num=6, group_type: str = "block", group_pos: str = "FFN", imagenet: bool = False):
     if type not in ("L1", "L2"):
         raise ValueError("type should be L1 or L2")
-    if group_pos != "FFN" or imagenet:
-        raise NotImplementedError("gslora-b200: get_norm_of_lora is built for the ViT_face FFN groupings (SURVEY.md 8f-2 lists the rest)")
+    if group_pos != "FFN":
+        raise NotImplementedError("gslora-b200: get_norm_of_lora is built for the FFN groupings (LoRA on attention is SURVEY.md 8f-2)")
+    if imagenet and group_type != "block":
+        raise ValueError("the reference defines only the block grouping for imagenet models (util/cal_norm.py:82-99)")
     groups = _ffn_groups(group_num, group_type)
-    print("\033[31mgroup_layers_names\033[0m\n", [[_NAMES[w].format(i) for i, w in g] for g in groups])
+    names = _NAMES_TV if imagenet else _NAMES
+    print("\033[31mgroup_layers_names\033[0m\n", [[names[w].format(i) for i, w in g] for g in groups])
     with torch.no_grad():
         eng = getattr(model, "_engine", None)
         if eng is None and hasattr(model, "ensure_engine"):

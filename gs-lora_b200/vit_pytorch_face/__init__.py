@@ -1,5 +1,5 @@
 """Drop-in for the reference package `vit_pytorch_face` (its __init__.py:1-3 exports ViT_face, ViT_face_low, ViT_face_up,
-ViTs_face, ModifiedViT).  `ViT_face` is the gslora-b200 engine-backed model; the other four are outside the GS-LoRA hot
+ViTs_face, ModifiedViT).  `ViT_face` and `ModifiedViT` are the gslora-b200 engine-backed models; the other three are outside the GS-LoRA hot
 path (SURVEY.md section 2 rows 6, 15 and the LIRF halves) and are re-exported from the reference's own files when the reference tree is
 importable (the unmodified driver builds all backbones eagerly, train_own_forget_cl.py:206-242)."""
 import importlib.util
@@ -7,6 +7,7 @@ import os
 import sys
 
 from .vit_face import ViT_face, CosFace  # noqa: F401
+from .modified_VIT import ModifiedViT  # noqa: F401
 
 
 def _reference_dir():
@@ -44,7 +45,6 @@ try:
     _rvf = _load(os.path.join(_ref, "vit_face.py"), "_gslora_ref_vit_face")
     ViT_face_low, ViT_face_up = _rvf.ViT_face_low, _rvf.ViT_face_up
     ViTs_face = _load(os.path.join(_ref, "vits_face.py"), "_gslora_ref_vits_face").ViTs_face
-    ModifiedViT = _load(os.path.join(_ref, "modified_VIT.py"), "_gslora_ref_modified_vit").ModifiedViT
 except Exception:  # reference not importable here (e.g. on the GPU box)
     ViT_face_low, ViT_face_up = _missing("ViT_face_low"), _missing("ViT_face_up")
-    ViTs_face, ModifiedViT = _missing("ViTs_face"), _missing("ModifiedViT")
+    ViTs_face = _missing("ViTs_face")

@@ -18,7 +18,8 @@ import torch.nn as nn
 
 import loralib as lora
 from gslora import _ffi as F
-from gslora.engine import EngineSpec, VitEngine
+from gslora.engine import EngineSpec
+from gslora.model_base import EngineBackedModel
 
 MIN_NUM_PATCHES = 16
 
@@ -90,38 +91,7 @@ class CosFace(nn.Module):
         return f"{self.__class__.__name__}(in_features={self.in_features}, out_features={self.out_features}, s={self.s}, m={self.m})"
 
 
-class _EngineFn(torch.autograd.Function):
-    """One autograd node for the whole network: inputs are the LoRA matrices, outputs (logits, emb)."""
-
-    @staticmethod
-    def forward(ctx, model, img, label, *lora_params):
-        eng = model._engine
-        slot = model._take_slot()
-        B = eng.forward(img, label, slot, use_lora=True, dropout_seed=model.dropout_seed())
-        ctx.model, ctx.slot, ctx.B, ctx.stamp = model, slot, B, model._slot_stamp[slot]
-        emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
-        if label is None:
-            return emb
-        return eng.slot_tensor(slot, F.SLOT_LOGITS, B).clone(), emb
-
-    @staticmethod
-    def backward(ctx, *grads):
-        model, eng, slot = ctx.model, ctx.model._engine, ctx.slot
-        if model._slot_stamp[slot] != ctx.stamp:
-            raise RuntimeError("gslora-b200: the activations of this forward were overwritten by later forwards; raise "
-                               "GSLORA_SLOTS (activation sets kept alive) or call backward sooner")
-        if len(grads) == 2:
-            dlogits, demb = grads
-        else:
-            dlogits, demb = None, grads[0]
-        dlogits = dlogits.contiguous().float() if dlogits is not None else None
-        demb = demb.contiguous().float() if demb is not None else None
-        eng.backward(slot, dlogits, demb, accumulate=False)
-        out = [eng.lora_view(eng.grad_flat, l, w).clone() for l in range(eng.spec.depth) for w in range(4)]
-        return (None, None, None, *out)
-
-
-class ViT_face(nn.Module):
+class ViT_face(EngineBackedModel):
     def __init__(self, *, loss_type, GPU_ID, num_class, image_size, patch_size, dim, depth, heads, mlp_dim, pool="cls", channels=3,
                  dim_head=64, dropout=0.0, emb_dropout=0.0, lora_rank=8, lora_pos: str = "FFN"):
         super().__init__()
@@ -152,41 +122,15 @@ class ViT_face(nn.Module):
             self.loss = CosFace(in_features=dim, out_features=num_class, device_id=GPU_ID)
         else:
             raise NotImplementedError(f"gslora-b200 builds the CosFace head only (every GS-LoRA script uses -head CosFace); got {loss_type}")
-        # engine state (not parameters / buffers: never part of state_dict)
-        self._engine: Optional[VitEngine] = None
-        self._frozen_sig = None
-        self._lora_sig = None
-        self._slot_next = 0
-        self._slot_stamp: List[int] = []
-
-    # ------------------------------------------------------------------ module plumbing
-    def __deepcopy__(self, memo):
-        import copy
-        eng, self._engine = self._engine, None
-        try:
-            cls = self.__class__
-            new = cls.__new__(cls)
-            memo[id(self)] = new
-            for k, v in self.__dict__.items():
-                setattr(new, k, copy.deepcopy(v, memo))
-        finally:
-            self._engine = eng
-        new._engine, new._frozen_sig, new._lora_sig = None, None, None
-        return new
+        self._init_engine_state()
 
     def lora_layers(self):
         for attn, ff in self.transformer.layers:
             yield ff.fn.fn.net[0], ff.fn.fn.net[3]
 
-    def lora_parameters(self) -> List[nn.Parameter]:
-        out = []
-        for fc1, fc2 in self.lora_layers():
-            out += [fc1.lora_A, fc1.lora_B, fc2.lora_A, fc2.lora_B]
-        return out
-
     def _frozen_tensors(self):
         t = [self.pos_embedding, self.cls_token, self.patch_to_embedding.weight, self.patch_to_embedding.bias,
-             self.mlp_head[0].weight, self.mlp_head[0].bias, self.loss.weight if hasattr(self, "loss") else None]
+             self.mlp_head[0].weight, self.mlp_head[0].bias, self.loss.weight if hasattr(self, "loss") else None, None]
         for attn, ff in self.transformer.layers:
             a, f = attn.fn, ff.fn
             t += [a.norm.weight, a.norm.bias, a.fn.to_qkv.weight, a.fn.to_qkv.bias, a.fn.to_out[0].weight, a.fn.to_out[0].bias,
@@ -200,93 +144,10 @@ class ViT_face(nn.Module):
                           cos_s=getattr(getattr(self, "loss", None), "s", 64.0), cos_m=getattr(getattr(self, "loss", None), "m", 0.35),
                           grad_scale=float(os.environ.get("GSLORA_GRAD_SCALE", "1024")), dropout=self.dropout_p, emb_dropout=self.emb_dropout_p)
 
-    def ensure_engine(self, batch: int, slots: Optional[int] = None) -> VitEngine:
-        dev = self.pos_embedding.device
-        if dev.type != "cuda":
-            raise F.GslError("gslora-b200: ViT_face executes on a CUDA device (sm_100a) only; there is no CPU fallback")
-        slots = slots or int(os.environ.get("GSLORA_SLOTS", "2"))
-        e = self._engine
-        if e is None or e.device != dev or e.max_batch < batch or e.num_slots < slots:
-            old = e
-            cap = max(batch, old.max_batch if old is not None and old.device == dev else 0)
-            self._engine = None
-            del old, e
-            self._engine = VitEngine(self.engine_spec(), dev, cap, slots)
-            self._frozen_sig = self._lora_sig = None
-            self._slot_stamp = [0] * slots
-            self._slot_next = 0
-        return self._engine
-
-    def sync_engine(self, force_lora: bool = False):
-        """Re-link parameters into the engine and refresh its fp16 operand caches if anything changed."""
-        eng = self._engine
-        relinked = False
-        for l, (fc1, fc2) in enumerate(self.lora_layers()):
-            for w, p in enumerate((fc1.lora_A, fc1.lora_B, fc2.lora_A, fc2.lora_B)):
-                view = eng.lora_view(eng.lora_flat, l, w)
-                if p.data_ptr() != view.data_ptr():
-                    view.copy_(p.data)
-                    p.data = view
-                    relinked = True
-        params = self._frozen_tensors()
-        frozen = [None if t is None else t.data for t in params]
-        for t in frozen:
-            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
-                raise F.GslError("gslora-b200: frozen parameters must be contiguous fp32")
-        sig = tuple((0, 0) if q is None else (q.data_ptr(), q._version) for q in params)
-        sig += tuple(m._gsl_generation for pair in self.lora_layers() for m in pair)
-        if sig != self._frozen_sig:
-            eng.bind(frozen)
-            eng.refresh_frozen()
-            self._frozen_sig = sig
-            self._lora_sig = None
-        lsig = tuple(p._version for p in self.lora_parameters()) + (eng.opt_step,)
-        if relinked or force_lora or lsig != self._lora_sig:
-            eng.refresh_lora()
-            self._lora_sig = lsig
-
-    def mark_lora_updated_by_engine(self):
-        self._lora_sig = tuple(p._version for p in self.lora_parameters()) + (self._engine.opt_step,)
-
-    def _take_slot(self) -> int:
-        s = self._slot_next
-        self._slot_next = (s + 1) % self._engine.num_slots
-        self._slot_stamp[s] += 1
-        return s
-
-    def dropout_seed(self) -> int:
-        """Non-zero seed for the engine's counter-based dropout masks in train mode (drawn from torch's CPU generator, so
-        torch.manual_seed makes runs reproducible); 0 (= no dropout) in eval mode or when both probabilities are 0."""
-        if not self.training or (self.dropout_p <= 0.0 and self.emb_dropout_p <= 0.0) or os.environ.get("GSLORA_DROPOUT", "on") == "off":
-            return 0
-        return int(torch.randint(1, 2 ** 62, (1,)).item())
-
-    def _merged(self) -> bool:
-        states = {m.merged for pair in self.lora_layers() for m in pair}
-        if len(states) != 1:
-            raise RuntimeError("gslora-b200: LoRA layers are in mixed merged / un-merged states")
-        return states.pop()
-
-    # ------------------------------------------------------------------ forward
     def forward(self, img, label=None, mask=None):
         """:return: (logits, emb) if `label` is given else emb -- as vit_face.py:523-548"""
         if mask is not None:
             raise NotImplementedError("gslora-b200: attention masks are not used by any GS-LoRA script and are not built")
-        img = img.float().contiguous()
-        if label is not None:
-            label = label.to(device=img.device, dtype=torch.int64).contiguous()
-            if not hasattr(self, "loss"):
-                raise RuntimeError("labelled forward needs loss_type='CosFace'")
-        eng = self.ensure_engine(img.shape[0])
-        self.sync_engine()
-        merged = self._merged()
-        lora_params = self.lora_parameters()
-        need_grad = torch.is_grad_enabled() and not merged and any(p.requires_grad for p in lora_params)
-        if need_grad:
-            return _EngineFn.apply(self, img, label, *lora_params)
-        slot = self._take_slot()
-        B = eng.forward(img, label, slot, use_lora=not merged, dropout_seed=self.dropout_seed())
-        emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
-        if label is None:
-            return emb
-        return eng.slot_tensor(slot, F.SLOT_LOGITS, B).clone(), emb
+        if label is not None and not hasattr(self, "loss"):
+            raise RuntimeError("labelled forward needs loss_type='CosFace'")
+        return self._engine_forward(img, label)

@@ -91,7 +91,7 @@ typedef struct GslConfig {
   int32_t image_size, patch_size, channels, dim, depth, heads, mlp_dim, num_class, lora_rank;
   int32_t max_batch;     /* images per forward call */
   int32_t num_slots;     /* activation sets kept alive at once (autograd: one per un-backwarded forward) */
-  int32_t patch_order;   /* 0 = (p1 p2 c) ViT_face */
+  int32_t patch_order;   /* 0 = (p1 p2 c) ViT_face, 1 = (c p1 p2) torchvision conv_proj */
   float attn_scale;      /* dim ** -0.5 for ViT_face (vit_face.py:346) */
   float ln_eps;          /* 1e-5 */
   float cos_s, cos_m;    /* CosFace s = 64, m = 0.35 (vit_face.py:158) */
@@ -99,15 +99,18 @@ typedef struct GslConfig {
   float grad_scale;      /* power-of-two loss scale of the fp16 gradient stream (unscaled again in dA/dB) */
   float dropout;         /* nn.Dropout p of to_out / after GELU / after fc2 (vit_face.py:332,334,356), applied when dropout_seed != 0 */
   float emb_dropout;     /* nn.Dropout p after the pos-embedding add (vit_face.py:489,537) */
+  int32_t head_type;     /* 0 = CosFace on LN(cls) (ViT_face), 1 = Linear + bias on LN(cls) (torchvision heads.head, modified_VIT.py:23-39) */
 } GslConfig;
 
 /* Frozen parameter pointer table order for gsl_engine_bind_params (fp32 device pointers, reference state_dict names):
  *   [0] pos_embedding  [1] cls_token  [2] patch_to_embedding.weight  [3] patch_to_embedding.bias
- *   [4] mlp_head.0.weight  [5] mlp_head.0.bias  [6] loss.weight
+ *   [4] mlp_head.0.weight  [5] mlp_head.0.bias  [6] loss.weight  [7] NULL
+ *   (torchvision family: encoder.pos_embedding, class_token, conv_proj.weight [D, C*p*p], conv_proj.bias, encoder.ln.{weight,bias},
+ *    heads.head.weight, heads.head.bias; per block ln_1, self_attention.in_proj_{weight,bias}, out_proj, ln_2, mlp.0, mlp.3)
  *   then per block i (12 entries): 0.fn.norm.{weight,bias}, 0.fn.fn.to_qkv.{weight, bias(NULL for ViT_face)},
  *   0.fn.fn.to_out.0.{weight,bias}, 1.fn.norm.{weight,bias}, 1.fn.fn.net.0.{weight,bias}, 1.fn.fn.net.3.{weight,bias}
  * lora_flat / grad_flat: fp32 [depth][ lora_A(net.0) r*D | lora_B(net.0) H*r | lora_A(net.3) r*H | lora_B(net.3) D*r ]  */
-#define GSL_NUM_GLOBAL_PARAMS 7
+#define GSL_NUM_GLOBAL_PARAMS 8
 #define GSL_NUM_BLOCK_PARAMS 12
 
 size_t gsl_engine_workspace_bytes(const GslConfig* cfg);

@@ -219,3 +219,65 @@ def test_dropout_step_matches_oracle_with_replayed_masks():
         l1, _ = m(x, y)
         l2, _ = m(x, y)
     assert torch.equal(l1, l2)
+
+
+def _tv_pair(image_size, patch, layers, heads, hidden, mlp, classes, rank, seed):
+    """(reference, ours): torchvision VisionTransformer + oracle loralib in FP32 eager vs the engine-backed ModifiedViT, same weights
+    (the reference path of modified_VIT.py:23-39 + util/utils.py:552-576 replace_ffn_with_lora)."""
+    from torchvision.models.vision_transformer import VisionTransformer
+    from oracle import loralib_restated as olora
+    import loralib as lora
+    from vit_pytorch_face import ModifiedViT
+    torch.manual_seed(seed)
+    ref = VisionTransformer(image_size=image_size, patch_size=patch, num_layers=layers, num_heads=heads, hidden_dim=hidden, mlp_dim=mlp,
+                            num_classes=classes)
+    for blk in ref.encoder.layers.children():
+        blk.mlp[0] = olora.Linear(hidden, mlp, r=rank)
+        blk.mlp[3] = olora.Linear(mlp, hidden, r=rank)
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if "lora_B" in n:
+                p.normal_(0, 0.02)
+            if n.endswith("heads.head.weight"):
+                p.normal_(0, 0.02)          # torchvision zero-inits the head: make the logits non-trivial
+        ref.encoder.pos_embedding.normal_(0, 0.02)
+        ref.class_token.normal_(0, 0.02)
+    olora.mark_only_lora_as_trainable(ref)
+    from torchvision.models.vision_transformer import VisionTransformer as VT
+    mine_tv = VT(image_size=image_size, patch_size=patch, num_layers=layers, num_heads=heads, hidden_dim=hidden, mlp_dim=mlp, num_classes=classes)
+    mine = ModifiedViT(mine_tv)
+    for blk in mine.encoder.layers.children():
+        blk.mlp[0] = lora.Linear(hidden, mlp, r=rank)
+        blk.mlp[3] = lora.Linear(mlp, hidden, r=rank)
+    missing = mine.load_state_dict(ref.state_dict(), strict=True)
+    lora.mark_only_lora_as_trainable(mine)
+    return ref.cuda().train(), mine.cuda().train()
+
+
+@pytest.mark.parametrize("shape", [dict(image_size=64, patch=16, layers=3, heads=2, hidden=128, mlp=256, classes=10, rank=8, B=5),
+                                   dict(image_size=224, patch=16, layers=12, heads=12, hidden=768, mlp=3072, classes=100, rank=8, B=4),
+                                   dict(image_size=224, patch=16, layers=2, heads=16, hidden=1024, mlp=4096, classes=100, rank=16, B=3)])
+def test_torchvision_family_matches_torchvision_fp32(shape):
+    """Configs 4 / 5 (ViT-B/16 r=8, ViT-L/16-width r=16): logits, cls embedding and LoRA gradients vs torchvision FP32 eager."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B = shape.pop("B")
+    ref, mine = _tv_pair(seed=5, **shape)
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn(B, 3, shape["image_size"], shape["image_size"], generator=gen).cuda()
+    y = torch.randint(0, shape["classes"], (B,), generator=gen).cuda()
+    ref_logits = ref(x)
+    torch.nn.functional.cross_entropy(ref_logits, y).backward()
+    logits, emb = mine(x, y)
+    torch.nn.functional.cross_entropy(logits, y).backward()
+    assert emb.shape == (B, shape["hidden"])
+    assert rel(logits, ref_logits) < 2e-3
+    names = [n for n, p in ref.named_parameters() if p.requires_grad]
+    assert len(names) == 4 * shape["layers"]
+    got = torch.cat([mine.get_parameter(n).grad.flatten() for n in names])
+    want = torch.cat([ref.get_parameter(n).grad.flatten() for n in names])
+    print(f"tv family {shape['hidden']}: logits {rel(logits, ref_logits):.2e} grads {rel(got, want):.2e}")
+    assert rel(got, want) < 2e-3
+    import engine_cl
+    s_loss = engine_cl.get_structure_loss(mine, imagenet=True)
+    want_s = sum(torch.sqrt(sum((ref.get_parameter(n) ** 2).sum() for n in names[4 * i:4 * i + 4])) for i in range(shape["layers"]))
+    assert abs(float(s_loss) - float(want_s)) < 1e-4 * float(want_s)
