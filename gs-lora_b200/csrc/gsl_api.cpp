@@ -51,7 +51,7 @@ int gsl_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const flo
 }
 int gsl_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
                       const float* dres, int64_t lddres, float* dx, int64_t lddx, void* dx16, int64_t lddx16, int64_t M, int D, void* stream) {
-    return layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__half*)dx16, lddx16, M, D, 0.f, 0u, ST(stream));
+    return layernorm_bwd(dy, 0, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__half*)dx16, lddx16, M, D, 0.f, 0u, ST(stream));
 }
 int gsl_lora_down(const void* X16, int64_t ldx, const void* A16, int64_t lda, void* out16, int64_t ldo, int64_t M, int K, int r, void* stream) {
     return lora_down((const __half*)X16, ldx, (const __half*)A16, lda, (__half*)out16, ldo, M, K, r, ST(stream));

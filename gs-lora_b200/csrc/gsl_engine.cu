@@ -410,10 +410,10 @@ int Engine::ffn_backward(int l, int64_t M, __half* dxcat, float* dx, __half* dhc
     {   // dLN2 = dH W1 + s U1 A1
         GemmArgs g;
         g.A = dhcat; g.lda = H + 16; g.B = c.fc1T_cat; g.ldb = H + 16; g.M = M; g.N = D; g.K = H + 16;
-        g.epi = EPI_F32; g.out0 = dxn; g.ld0 = D;
+        g.epi = EPI_F16; g.out0 = dxn; g.ld0 = D;            // fp16: halves the traffic of the LayerNorm-backward pass that consumes it
         if ((rc = gemm_f16(g, s))) return rc;
     }
-    return layernorm_bwd(dxn, D, x_mid, D, ln_mean, ln_rstd, f.ln2_w, dx, D, dx, D, dxcat, D + 16, M, D, pdrop, site_seed(dseed, l, 1), s);
+    return layernorm_bwd(dxn, 1, D, x_mid, D, ln_mean, ln_rstd, f.ln2_w, dx, D, dx, D, dxcat, D + 16, M, D, pdrop, site_seed(dseed, l, 1), s);
 }
 
 int Engine::backward(int slot, const float* dlogits, const float* demb, int accumulate, cudaStream_t s) {
@@ -455,13 +455,13 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         {   // dLN1 = dQKV Wqkv  (dense: dK / dV reach every token)
             GemmArgs g;
             g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
-            g.epi = EPI_F32; g.out0 = dxn32; g.ld0 = D;
+            g.epi = EPI_F16; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
         // residual gradient of this block's input: zero except the cls rows
         if ((rc = fill_zero(dx32, (size_t)M * D * 4, s))) return rc;
         if ((rc = copy_cls_rows(cls_dx32, (int64_t)D * 4, dx32, (int64_t)tokens * D * 4, B, (int64_t)D * 4, s))) return rc;
-        if ((rc = layernorm_bwd(dxn32, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, pdrop,
+        if ((rc = layernorm_bwd(dxn32, 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, pdrop,
                                 site_seed(dseed, l - 1, 3), s))) return rc;
     }
     for (int l = L - 2; l >= 0; --l) {
@@ -483,10 +483,10 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         {   // dLN1 = dQKV Wqkv
             GemmArgs g;
             g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
-            g.epi = EPI_F32; g.out0 = dxn32; g.ld0 = D;
+            g.epi = EPI_F16; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
-        if ((rc = layernorm_bwd(dxn32, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, pdrop,
+        if ((rc = layernorm_bwd(dxn32, 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, pdrop,
                                 site_seed(dseed, l - 1, 3), s))) return rc;
     }
     return 0;

@@ -43,7 +43,7 @@ int patchify_f16(const float* img, __half* out, int64_t ld, int B, int C, int S,
 int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, __half* y, int64_t ldy,
                   float* mean, float* rstd, int64_t M, int D, cudaStream_t s);
 // dx = dres + LNbwd(dy) ; writes fp32 dx and an fp16 copy (GEMM operand for the next dX GEMM)
-int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+int layernorm_bwd(const void* dy, int dy_is_fp16, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                   const float* gamma, const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16,
                   int64_t M, int D, float drop_p, uint32_t drop_seed, cudaStream_t s);   // dropout mask applies to the fp16 copy only
 // T[M, 0:16] = X[M, K] * A16[16, K]^T  (fp16 in, fp32 accumulate, fp16 out at out[:, 0:16], row pitch ldo)

@@ -11,36 +11,42 @@ namespace gsl {
 // Reference: einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (vit_pytorch_face/vit_face.py:530) and, for the
 // torchvision family, conv_proj's implicit (c p1 p2) patch vector.  Token 0 (cls slot) is a zero row so that the
 // patch-embedding GEMM's rows line up 1:1 with the [B, tokens, D] residual stream.
+// output-centric: one thread per pair of consecutive patch-vector elements (coalesced half2 stores; the gathers hit L1/L2)
 __global__ void patchify_kernel(const float* __restrict__ img, __half* __restrict__ out, int64_t ld, int B, int C, int S,
                                 int patch, int order) {
     const int w = S / patch;
     const int P = w * w;
-    const int64_t total = (int64_t)B * C * S * S;
     const int pd = C * patch * patch;
+    const int half_pd = pd >> 1;
+    const int64_t total = (int64_t)B * (P + 1) * half_pd;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % S);
-        const int y = (int)((i / S) % S);
-        const int c = (int)((i / ((int64_t)S * S)) % C);
-        const int b = (int)(i / ((int64_t)S * S * C));
-        const int ph = y / patch, p1 = y % patch, pw = x / patch, p2 = x % patch;
-        const int tok = 1 + ph * w + pw;
-        const int e = order == 0 ? (p1 * patch + p2) * C + c : (c * patch + p1) * patch + p2;
-        out[((int64_t)b * (P + 1) + tok) * ld + e] = __float2half_rn(img[i]);
-    }
-    // zero the cls-slot rows
-    const int64_t ztotal = (int64_t)B * pd;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ztotal; i += (int64_t)gridDim.x * blockDim.x) {
-        const int b = (int)(i / pd), e = (int)(i % pd);
-        out[(int64_t)b * (P + 1) * ld + e] = __float2half_rn(0.f);
+        const int e0 = (int)(i % half_pd) * 2;
+        const int64_t row = i / half_pd;
+        const int tok = (int)(row % (P + 1));
+        const int b = (int)(row / (P + 1));
+        float v[2] = {0.f, 0.f};
+        if (tok > 0) {
+            const int ph = (tok - 1) / w, pw = (tok - 1) % w;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int e = e0 + k;
+                int c, p1, p2;
+                if (order == 0) { c = e % C; p2 = (e / C) % patch; p1 = e / (C * patch); }
+                else { p2 = e % patch; p1 = (e / patch) % patch; c = e / (patch * patch); }
+                v[k] = __ldg(img + (((int64_t)b * C + c) * S + ph * patch + p1) * S + pw * patch + p2);
+            }
+        }
+        *reinterpret_cast<__half2*>(out + row * ld + e0) = __floats2half2_rn(v[0], v[1]);
     }
 }
 
 int patchify_f16(const float* img, __half* out, int64_t ld, int B, int C, int S, int patch, int order, cudaStream_t s) {
     GSL_REQUIRE(S % patch == 0, "image size %d not divisible by patch %d", S, patch);
-    const int64_t total = (int64_t)B * C * S * S;
+    GSL_REQUIRE((C * patch * patch) % 2 == 0 && ld % 2 == 0, "patchify: patch_dim and ld must be even");
+    const int64_t total = (int64_t)B * ((S / patch) * (S / patch) + 1) * (C * patch * patch / 2);
     const int threads = 256;
     int blocks = (int)((total + threads - 1) / threads);
-    const int cap = device_sm_count() * 16;
+    const int cap = device_sm_count() * 32;
     if (blocks > cap) blocks = cap;
     patchify_kernel<<<blocks, threads, 0, s>>>(img, out, ld, B, C, S, patch, order);
     GSL_COUNT_LAUNCH(1);
@@ -113,8 +119,8 @@ int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* 
 // (autograd's native_layer_norm_backward for the frozen-affine case: gamma/beta get no gradient because
 //  lora.mark_only_lora_as_trainable froze them, train_own_forget_cl.py:316.)
 // Emits the fp32 gradient stream and its fp16 copy (A operand of the next dX GEMM).
-template <int VEC>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
+template <int VEC, bool DY16>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy_v, int64_t lddy, const float* __restrict__ x, int64_t ldx,
                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                             const float* __restrict__ gamma, const float* __restrict__ dres, int64_t lddres,
                                                             float* __restrict__ dx, int64_t lddx, __half* __restrict__ dx16, int64_t lddx16,
@@ -125,13 +131,21 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     if (row >= M) return;
     const float mean = mean_in[row], rstd = rstd_in[row];
     const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
-    const float4* dyr = reinterpret_cast<const float4*>(dy + row * lddy);
+    const float4* dyr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_v) + (DY16 ? 0 : row * lddy));
+    const uint2* dyh = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(dy_v) + (DY16 ? row * lddy : 0));
     float4 xh[VEC], g[VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         const float4 xv = xr[lane + 32 * i];
-        const float4 dv = dyr[lane + 32 * i];
+        float4 dv;
+        if (DY16) {
+            const uint2 h = dyh[lane + 32 * i];
+            const float2 a = unpack_half2(h.x), b = unpack_half2(h.y);
+            dv = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            dv = dyr[lane + 32 * i];
+        }
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
         xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
         g[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
@@ -168,7 +182,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
 }
 
-int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+int layernorm_bwd(const void* dy, int dy_is_fp16, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16, int64_t M, int D,
                   float drop_p, uint32_t drop_seed, cudaStream_t s) {
     const uint32_t dth = drop_p > 0.f ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
@@ -176,7 +190,10 @@ int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, co
     GSL_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm_bwd: D=%d must be a multiple of 128 and <= 1024", D);
     const int warps = 8;
     const int blocks = (int)((M + warps - 1) / warps);
-#define GSL_LN_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc); break;
+#define GSL_LN_CASE(V) case V: \
+        if (dy_is_fp16) layernorm_bwd_kernel<V, true><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc); \
+        else layernorm_bwd_kernel<V, false><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc); \
+        break;
     switch (D / 128) {
         GSL_LN_CASE(1) GSL_LN_CASE(2) GSL_LN_CASE(3) GSL_LN_CASE(4) GSL_LN_CASE(5) GSL_LN_CASE(6) GSL_LN_CASE(7) GSL_LN_CASE(8)
     }
