@@ -224,9 +224,16 @@ def kernel_roofline(dev, cfg, peaks):
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * M * (D * H * 2 + 2 * r * (D + H))
     ach = flops / ms / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram bytes of the same two launches from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("ffn_pair_bytes"), tj.get("source")
     return dict(bound="tensor", kernel="gemm_tcgen05_kernel<2,256,EPI_GELU> + <2,256,EPI_RES_F32> (fused FFN+LoRA pair)", achieved=round(ach, 1),
-                peak=peaks["burst"], unit="TFLOP/s", frac=round(ach / peaks["burst"], 4), traffic=None, ms_per_launch_pair=round(ms, 4),
-                peak_source=peaks["source"] + " cuBLAS bf16 burst")
+                peak=peaks["burst"], unit="TFLOP/s", frac=round(ach / peaks["burst"], 4), traffic=traffic, traffic_source=traffic_src,
+                algorithmic_bytes=int(2 * M * (D + 16) + 2 * (2 * M * H + 16 * M) + 2 * M * (H + 16) + 8 * M * D),
+                ms_per_launch_pair=round(ms, 4), peak_source=peaks["source"] + " cuBLAS bf16 burst")
 
 
 def cpu_baseline(sample_batch=16, steps=2):
