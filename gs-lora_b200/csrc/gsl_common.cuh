@@ -286,21 +286,108 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {                // Phi
     return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
-// Counter-based dropout mask (nn.Dropout of the reference: vit_face.py:332,334,356,489).  One 32-bit hash per PAIR of
-// consecutive elements (murmur3 finalizer of pair index ^ seed), 16 bits each: keep iff bits >= p * 65536.  The forward and the
-// backward regenerate the same mask from (seed, row * width + col); nothing is stored.  torch's Philox stream cannot be
-// reproduced bit-for-bit, so parity tests replay this hash on the host (tests/dropout_ref.py) and feed the masks to the oracle.
+// ---- packed fp32 pairs: FFMA2 / FMUL2 / FADD2 (sm_100a) do two lanes of fp32 work per issue slot.  The GEMM epilogues are
+// issue-bound (fma-pipe instructions issue every other cycle per scheduler), so all their arithmetic runs on pairs.
+__device__ __forceinline__ unsigned long long f2_pack(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2_unpack(unsigned long long a) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ float2 splat2(float c) { return make_float2(c, c); }
+
+// g = s * gelu(x), gp = s * gelu'(x) for a pair (s = dropout keep scale, 1 without dropout).  Abramowitz-Stegun 7.1.26 again:
+//   u = s (1 - Phi(|x|)) = s/2 t poly(t) exp(-x^2 / 2),  t = 1 / (1 + p |x| / sqrt 2),   d = s/2 - u = s (Phi(|x|) - 1/2) >= 0
+//   gelu(x)  = relu(x) - |x| (1 - Phi(|x|)) = x/2 + |x| (Phi(|x|) - 1/2)          -> g  = s x / 2 + |x| d
+//   gelu'(x) = Phi(x) + x pdf(x),  Phi(x) = 1/2 + sign(x) (Phi(|x|) - 1/2)          -> gp = (s/2 + s x pdf) + copysign(d, x)
+// 15 fma-pipe pair instructions + 4 MUFU + 4 LOP3 per pair; max abs error 1.1e-6 (g), 4.3e-7 (gp) over [-12, 12].
+// The s-scaled constants come pre-splatted from kernel parameters (constant bank operands: no register moves in the loop).
+struct GeluConsts {
+    float2 den_c, one, q4, q3, q2, q1, q0, arg_c, neg_hs, half_s, pdf_c, hs;
+};
+inline GeluConsts make_gelu_consts(float s) {
+    auto sp = [](float c) { return make_float2(c, c); };
+    const float hs = 0.5f * s;
+    GeluConsts k;
+    k.den_c = sp(-0.3275911f * 0.70710678118654752f); k.one = sp(1.0f);
+    k.q4 = sp(hs * 1.061405429f); k.q3 = sp(hs * -1.453152027f); k.q2 = sp(hs * 1.421413741f); k.q1 = sp(hs * -0.284496736f); k.q0 = sp(hs * 0.254829592f);
+    k.arg_c = sp(-0.72134752044448170f); k.neg_hs = sp(-hs); k.half_s = sp(hs); k.pdf_c = sp(0.39894228040143268f * s); k.hs = sp(hs);
+    return k;
+}
+__device__ __forceinline__ void gelu_pair(float2 x, const GeluConsts& k, float2& g, float2& gp) {
+    const float2 nax = make_float2(__uint_as_float(__float_as_uint(x.x) | 0x80000000u), __uint_as_float(__float_as_uint(x.y) | 0x80000000u));   // -|x|
+    const float2 den = fma2(nax, k.den_c, k.one);
+    const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+    float2 q = fma2(t, k.q4, k.q3);
+    q = fma2(q, t, k.q2);
+    q = fma2(q, t, k.q1);
+    q = fma2(q, t, k.q0);
+    const float2 arg = mul2(mul2(x, k.arg_c), x);
+    const float2 e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));      // exp(-x^2 / 2)
+    const float2 nd = fma2(mul2(q, t), e, k.neg_hs);                         // u - s/2 = -d <= 0
+    g = fma2(nax, nd, mul2(x, k.half_s));
+    // copysign(d, x) from nd: flip nd's sign where x >= 0
+    const float2 cs = make_float2(__uint_as_float(__float_as_uint(nd.x) ^ (~__float_as_uint(x.x) & 0x80000000u)),
+                                  __uint_as_float(__float_as_uint(nd.y) ^ (~__float_as_uint(x.y) & 0x80000000u)));
+    gp = add2(fma2(mul2(x, k.pdf_c), e, k.hs), cs);
+}
+
+// Counter-based dropout masks (nn.Dropout of the reference: vit_face.py:332,334,356,489).  One 32-bit hash per PAIR of
+// consecutive elements, 15 bits each (bits 0-14 and 16-30): element kept iff its field >= thresh15 = round(p * 32768).  The forward and the backward regenerate the
+// same mask from (seed, row * width + col); nothing is stored.  torch's Philox stream cannot be reproduced bit-for-bit, so the
+// parity tests replay this hash on the host (tests/dropout_ref.py) and feed the masks to the oracle.
+//   drop_hash : murmur3 finalizer, used once per (block, site) to derive the per-site seeds (gsl_engine.cu site_seed)
+//   drop_bits : the per-pair mask hash -- two multiply / xor-shift rounds (it runs per pair inside issue-bound GEMM epilogues)
 __device__ __host__ __forceinline__ uint32_t drop_hash(uint32_t pair, uint32_t seed) {
     uint32_t h = pair * 0x9E3779B1u ^ seed;
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
     return h;
 }
-// scale factors (0 or 1/(1-p)) for elements e and e+1, e even
-__device__ __forceinline__ void drop_pair(uint32_t e, uint32_t seed, uint32_t thresh16, float keep_scale, float& s0, float& s1) {
-    const uint32_t h = drop_hash(e >> 1, seed);
-    s0 = (h & 0xFFFFu) >= thresh16 ? keep_scale : 0.f;
-    s1 = (h >> 16) >= thresh16 ? keep_scale : 0.f;
+__device__ __host__ __forceinline__ uint32_t drop_bits(uint32_t pair, uint32_t seed) {
+    uint32_t h = (pair ^ seed) * 0x9E3779B1u;
+    h ^= h >> 15;
+    return h * 0x85EBCA77u;
 }
+// scale factors (0 or 1/(1-p)) for elements e and e+1, e even
+__device__ __forceinline__ void drop_pair(uint32_t e, uint32_t seed, uint32_t thresh15, float keep_scale, float& s0, float& s1) {
+    const uint32_t h = drop_bits(e >> 1, seed);
+    s0 = (h & 0x7FFFu) >= thresh15 ? keep_scale : 0.f;
+    s1 = ((h >> 16) & 0x7FFFu) >= thresh15 ? keep_scale : 0.f;
+}
+__device__ __forceinline__ float2 drop_pair2(uint32_t e, uint32_t seed, uint32_t thresh15, float keep_scale) {
+    float2 s;
+    drop_pair(e, seed, thresh15, keep_scale, s.x, s.y);
+    return s;
+}
+// 0xFFFF in each 16-bit half of the result whose 15-bit field is >= the threshold (thr2 = thresh15 | thresh15 << 16): AND it onto a
+// packed half2 to zero the dropped elements.  SWAR compare: with bit 15 of each half forced to 1, (half - thresh15) keeps bit 15
+// iff field >= thresh15 and never borrows from the neighbouring half; PRMT replicates that bit over the half.
+__device__ __forceinline__ uint32_t drop_keep_mask2(uint32_t e, uint32_t seed, uint32_t thr2) {
+    const uint32_t h = drop_bits(e >> 1, seed);
+    uint32_t m;
+    asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(m) : "r"((h | 0x80008000u) - thr2));      // (__byte_perm would strip the sign-replicate bits)
+    return m;
+}
+__device__ __host__ __forceinline__ uint32_t drop_thresh15(float p) { return p > 0.f ? (uint32_t)(p * 32768.0f + 0.5f) : 0u; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -396,11 +396,10 @@ int Engine::ffn_backward(int l, int64_t M, __half* dxcat, float* dx, __half* dhc
     if ((rc = lora_down(dxcat, D + 16, c.B2T, D, dxcat + D, D + 16, M, D, r, s))) return rc;                                        // U2 = dY2 B2
     if ((rc = skinny_tn(dxcat, D + 16, gcat + H, H + 16, gB2, r, 0, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // dB2 = s dY2^T T2
     if ((rc = skinny_tn(gcat, H + 16, dxcat + D, D + 16, gA2, H, 1, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // dA2 = s U2^T G
-    {   // dH = (dY2 W2 + s U2 A2) * gelu'(H)
+    {   // dH = (dY2 W2 + s U2 A2) * d[Dropout(gelu(h))] / dh
         GemmArgs g;
         g.A = dxcat; g.lda = D + 16; g.B = c.fc2T_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + 16;
-        g.epi = EPI_GELU_BWD; g.out0 = dhcat; g.ld0 = H + 16; g.aux = h16; g.ldaux = H;
-        g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 2);
+        g.epi = EPI_GELU_BWD; g.out0 = dhcat; g.ld0 = H + 16; g.aux = h16; g.ldaux = H;      // h16 = Dropout-mask * gelu'(h), saved by the forward
         if ((rc = gemm_f16(g, s))) return rc;
     }
     if ((rc = lora_down(dhcat, H + 16, c.B1T, H, dhcat + H, H + 16, M, H, r, s))) return rc;                                        // U1 = dH B1

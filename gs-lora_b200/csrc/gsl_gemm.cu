@@ -39,9 +39,10 @@ struct GemmParams {
     const float* table;   // EPI_PERIODIC_F32: fp32 [period, ld_table]
     int period, ld_table;
     int has_out1;         // EPI_F32: also emit an fp16 copy through tmO1
-    uint32_t drop_thresh; // p * 65536 (0 = no dropout)
+    uint32_t drop_thresh; // round(p * 32768) (0 = no dropout)
     uint32_t drop_seed;
     float drop_scale;     // 1 / (1 - p)
+    GeluConsts gelu;      // EPI_GELU: constants of gelu_pair, scaled by the keep scale
 };
 
 template <int EPI> struct EpiTraits;
@@ -84,15 +85,15 @@ struct GemmCfg {
 
 __device__ __forceinline__ void epi_bar_sync(uint32_t group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(EPI_GROUP_WARPS * 32) : "memory"); }
 
-// load CW fp32 accumulator columns of this warp's 32 TMEM lanes
+// load CW fp32 accumulator columns of this warp's 32 TMEM lanes, as CW / 2 pairs
 template <int CW>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&f)[CW]) {
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float2 (&f)[CW / 2]) {
     if constexpr (CW == 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) f[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
     } else {
         uint32_t v[16];
         asm volatile(
@@ -102,7 +103,7 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&f)[CW]) {
             : "r"(taddr) : "memory");
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 8; ++j) f[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
     }
 }
 
@@ -259,67 +260,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
             for (int sidx = grp; sidx < nstripes; sidx += EPI_GROUPS) {
                 const int n0 = n_base + sidx * STRIPE + (int)half * CW;      // first column of this warp
-                float f[CW];
-                tmem_ld_cols<CW>(tmem_base + ((quarter * 32u) << 16) + acc * BN + sidx * STRIPE + half * CW, f);
+                float2 v[CW / 2];                                            // this thread's CW accumulator columns, as pairs
+                tmem_ld_cols<CW>(tmem_base + ((quarter * 32u) << 16) + acc * BN + sidx * STRIPE + half * CW, v);
                 if (sidx + EPI_GROUPS >= nstripes) {
                     // this thread's last TMEM read of the accumulator: hand the buffer back to the MMA warp
                     tcgen05_fence_before();
                     if (CG == 2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
                 }
                 if (!tile_live) continue;
+                const uint32_t e0 = (uint32_t)(m_base + (int)row) * (uint32_t)p.N + (uint32_t)n0;     // dropout counter of column n0
 
                 if (p.bias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < CW; j += 4) {
                         if (n0 + j < p.N) {
                             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                            v[j / 2] = add2(v[j / 2], make_float2(b4.x, b4.y));
+                            v[j / 2 + 1] = add2(v[j / 2 + 1], make_float2(b4.z, b4.w));
                         }
                     }
                 }
-                if ((EPI == EPI_RES_F32) && p.drop_thresh) {       // Dropout(to_out / fc2 output) before the residual add
-                    const uint32_t e0 = (uint32_t)(m_base + (int)row) * (uint32_t)p.N + (uint32_t)n0;
-#pragma unroll
-                    for (int j = 0; j < CW; j += 2) {
-                        float s0, s1;
-                        drop_pair(e0 + j, p.drop_seed, p.drop_thresh, p.drop_scale, s0, s1);
-                        f[j] *= s0; f[j + 1] *= s1;
-                    }
-                }
-                if (T::AUX) {
+                if (EPI == EPI_RES_F32) {      // out = Dropout(acc + bias) + residual   (to_out / fc2 output, then the Residual add)
                     mbar_wait(aux_bar(grp), aux_it & 1);
-                    if (T::AUX == 4) {          // fp32 residual stripe [128 x 32]: this warp's 16 columns = chunks half*4 .. +3
+                    ++aux_it;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float4 r;
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(aux_buf + sw128_off(row, half * 4 + j)));
-                            f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
-                        }
-                    } else {                    // fp16 pre-activation stripe H [128 x 64]: dH = dG * gelu'(H)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t h0, h1, h2, h3;
-                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(aux_buf + sw128_off(row, half * 4 + j)));
-                            const uint32_t hh[4] = {h0, h1, h2, h3};
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 h = unpack_half2(hh[q]);
-                                f[8 * j + 2 * q] *= gelu_grad_fast(h.x);
-                                f[8 * j + 2 * q + 1] *= gelu_grad_fast(h.y);
-                            }
+                    for (int j = 0; j < 4; ++j) {       // fp32 residual stripe [128 x 32]: this warp's 16 columns = chunks half*4 .. +3
+                        float4 r;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(aux_buf + sw128_off(row, half * 4 + j)));
+                        if (p.drop_thresh) {
+                            v[2 * j] = fma2(v[2 * j], drop_pair2(e0 + 4 * j, p.drop_seed, p.drop_thresh, p.drop_scale), make_float2(r.x, r.y));
+                            v[2 * j + 1] = fma2(v[2 * j + 1], drop_pair2(e0 + 4 * j + 2, p.drop_seed, p.drop_thresh, p.drop_scale), make_float2(r.z, r.w));
+                        } else {
+                            v[2 * j] = add2(v[2 * j], make_float2(r.x, r.y));
+                            v[2 * j + 1] = add2(v[2 * j + 1], make_float2(r.z, r.w));
                         }
                     }
-                    ++aux_it;
                 }
-                if ((EPI == EPI_GELU_BWD) && p.drop_thresh) {       // backward of Dropout(gelu(h)): same mask as the forward
-                    const uint32_t e0 = (uint32_t)(m_base + (int)row) * (uint32_t)p.N + (uint32_t)n0;
+                if (EPI == EPI_GELU_BWD) {     // out = acc * aux, aux = keep-scale * mask * gelu'(h) as written by EPI_GELU (fp16 stripe [128 x 64])
+                    mbar_wait(aux_bar(grp), aux_it & 1);
+                    ++aux_it;
 #pragma unroll
-                    for (int j = 0; j < CW; j += 2) {
-                        float s0, s1;
-                        drop_pair(e0 + j, p.drop_seed, p.drop_thresh, p.drop_scale, s0, s1);
-                        f[j] *= s0; f[j + 1] *= s1;
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t h0, h1, h2, h3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(aux_buf + sw128_off(row, half * 4 + j)));
+                        v[4 * j] = mul2(v[4 * j], unpack_half2(h0));
+                        v[4 * j + 1] = mul2(v[4 * j + 1], unpack_half2(h1));
+                        v[4 * j + 2] = mul2(v[4 * j + 2], unpack_half2(h2));
+                        v[4 * j + 3] = mul2(v[4 * j + 3], unpack_half2(h3));
                     }
                 }
                 if (EPI == EPI_PERIODIC_F32) {
@@ -330,19 +319,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int j = 0; j < CW; j += 4) {
                             if (n0 + j < p.N) {
                                 const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + j));
-                                f[j] += t4.x; f[j + 1] += t4.y; f[j + 2] += t4.z; f[j + 3] += t4.w;
+                                v[j / 2] = add2(v[j / 2], make_float2(t4.x, t4.y));
+                                v[j / 2 + 1] = add2(v[j / 2 + 1], make_float2(t4.z, t4.w));
                             }
                         }
                     }
                     if (p.drop_thresh) {                            // emb_dropout after the pos-embedding add
-                        const uint32_t e0 = (uint32_t)r * (uint32_t)p.N + (uint32_t)n0;
 #pragma unroll
-                        for (int j = 0; j < CW; j += 2) {
-                            float s0, s1;
-                            drop_pair(e0 + j, p.drop_seed, p.drop_thresh, p.drop_scale, s0, s1);
-                            f[j] *= s0; f[j + 1] *= s1;
+                        for (int j = 0; j < CW; j += 2) v[j / 2] = mul2(v[j / 2], drop_pair2(e0 + j, p.drop_seed, p.drop_thresh, p.drop_scale));
+                    }
+                }
+                uint32_t pk0[CW / 2], pk1[CW / 2];      // packed half2 outputs (fp16 epilogues)
+                if (EPI == EPI_GELU) {         // out1 = Dropout(gelu(h)), out0 = d out1 / d h   (h = acc + bias never leaves the SM)
+                    const uint32_t thr2 = p.drop_thresh | (p.drop_thresh << 16);
+#pragma unroll
+                    for (int j = 0; j < CW / 2; ++j) {
+                        float2 g, gp;
+                        gelu_pair(v[j], p.gelu, g, gp);
+                        pk0[j] = pack_half2(gp.x, gp.y);
+                        pk1[j] = pack_half2(g.x, g.y);
+                        if (p.drop_thresh) {
+                            const uint32_t keep = drop_keep_mask2(e0 + 2 * j, p.drop_seed, thr2);
+                            pk0[j] &= keep;
+                            pk1[j] &= keep;
                         }
                     }
+                } else if (T::O0 == 2) {
+#pragma unroll
+                    for (int j = 0; j < CW / 2; ++j) pk0[j] = pack_half2(v[j].x, v[j].y);
+                } else if (T::O1) {            // fp16 copy of an fp32 stripe
+#pragma unroll
+                    for (int j = 0; j < CW / 2; ++j) pk1[j] = pack_half2(v[j].x, v[j].y);
                 }
 
                 // staging reuse: this group's previous TMA store must have finished reading smem; every thread of the group
@@ -358,38 +365,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-                                     ::"r"(o0_buf + sw128_off(row, half * 4 + j)), "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
+                                     ::"r"(o0_buf + sw128_off(row, half * 4 + j)), "f"(v[2 * j].x), "f"(v[2 * j].y), "f"(v[2 * j + 1].x), "f"(v[2 * j + 1].y) : "memory");
                 } else {            // fp16 [128 x 64] stripe: this warp's 32 columns = chunks half*4 .. +3
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                     ::"r"(o0_buf + sw128_off(row, half * 4 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
-                                       "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
+                                     ::"r"(o0_buf + sw128_off(row, half * 4 + j)), "r"(pk0[4 * j]), "r"(pk0[4 * j + 1]), "r"(pk0[4 * j + 2]), "r"(pk0[4 * j + 3]) : "memory");
                 }
                 if (T::O1 && write_o1) {
-                    if (EPI == EPI_GELU) {      // second output G = gelu(h), fp16 [128 x 64]
-#pragma unroll
-                        for (int j = 0; j < CW; ++j) f[j] = gelu_fast(f[j]);
-                        if (p.drop_thresh) {                        // Dropout(gelu(h)): G is stored already masked and scaled
-                            const uint32_t e0 = (uint32_t)(m_base + (int)row) * (uint32_t)p.N + (uint32_t)n0;
-#pragma unroll
-                            for (int j = 0; j < CW; j += 2) {
-                                float s0, s1;
-                                drop_pair(e0 + j, p.drop_seed, p.drop_thresh, p.drop_scale, s0, s1);
-                                f[j] *= s0; f[j + 1] *= s1;
-                            }
-                        }
+                    if (EPI == EPI_GELU) {      // fp16 [128 x 64]
 #pragma unroll
                         for (int j = 0; j < CW / 8; ++j)
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                         ::"r"(o1_buf + sw128_off(row, half * 4 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
-                                           "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
+                                         ::"r"(o1_buf + sw128_off(row, half * 4 + j)), "r"(pk1[4 * j]), "r"(pk1[4 * j + 1]), "r"(pk1[4 * j + 2]), "r"(pk1[4 * j + 3]) : "memory");
                     } else {                    // fp16 copy of an fp32 stripe, [128 x 32] = 64-byte rows: this warp's 16 columns = chunks half*2 .. +1
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                         ::"r"(o1_buf + sw64_off(row, half * 2 + j)), "r"(pack_half2(f[8 * j], f[8 * j + 1])), "r"(pack_half2(f[8 * j + 2], f[8 * j + 3])),
-                                           "r"(pack_half2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_half2(f[8 * j + 6], f[8 * j + 7])) : "memory");
+                                         ::"r"(o1_buf + sw64_off(row, half * 2 + j)), "r"(pk1[4 * j]), "r"(pk1[4 * j + 1]), "r"(pk1[4 * j + 2]), "r"(pk1[4 * j + 3]) : "memory");
                     }
                 }
                 fence_proxy_async_smem();
@@ -499,9 +492,10 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.table = (EPI == EPI_PERIODIC_F32) ? reinterpret_cast<const float*>(a.aux) : nullptr;
     p.period = (int)a.aux_period; p.ld_table = (int)a.ldaux;
     p.has_out1 = has_o1 ? 1 : 0;
-    p.drop_thresh = a.drop_p > 0.f ? (uint32_t)(a.drop_p * 65536.0f + 0.5f) : 0u;
+    p.drop_thresh = drop_thresh15(a.drop_p);
     p.drop_seed = a.drop_seed;
     p.drop_scale = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+    p.gelu = make_gelu_consts(p.drop_thresh ? p.drop_scale : 1.0f);
 
     auto kern = gemm_tcgen05_kernel<CG, BN, EPI>;
     static bool attr_set = false;

@@ -181,9 +181,9 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_bwd_kernel(HeadBwdArgs a) {
             float m = 1.0f;
             if (a.drop_p > 0.f) {
                 const uint32_t e = (uint32_t)(b * a.tokens) * (uint32_t)D + (uint32_t)d;
-                const uint32_t h = drop_hash(e >> 1, a.drop_seed);
-                const uint32_t bits = (e & 1u) ? (h >> 16) : (h & 0xFFFFu);
-                m = bits >= (uint32_t)(a.drop_p * 65536.0f + 0.5f) ? 1.0f / (1.0f - a.drop_p) : 0.f;
+                const uint32_t h = drop_bits(e >> 1, a.drop_seed);
+                const uint32_t bits = ((e & 1u) ? (h >> 16) : h) & 0x7FFFu;
+                m = bits >= drop_thresh15(a.drop_p) ? 1.0f / (1.0f - a.drop_p) : 0.f;
             }
             a.dx16[(int64_t)b * a.tokens * a.lddx16 + d] = __float2half_rn(v * m);
         }

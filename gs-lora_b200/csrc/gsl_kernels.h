@@ -11,8 +11,8 @@ namespace gsl {
 enum GemmEpi {
     EPI_F16 = 0,           // out0(fp16) = acc + bias
     EPI_F32 = 1,           // out0(fp32) = acc + bias                    [+ out1(fp16) copy]
-    EPI_GELU = 2,          // out0(fp16) = h = acc + bias ; out1(fp16) = gelu(h)          (FFN fc1)
-    EPI_GELU_BWD = 3,      // out0(fp16) = acc * gelu'(aux(fp16))                          (dH = dG * gelu'(H))
+    EPI_GELU = 2,          // h = acc + bias ; out1(fp16) = Dropout(gelu(h)) ; out0(fp16) = d out1 / d h   (FFN fc1; h itself is not stored)
+    EPI_GELU_BWD = 3,      // out0(fp16) = acc * aux(fp16)                                  (dH = dG * [mask * gelu'(h)] saved by EPI_GELU)
     EPI_RES_F32 = 4,       // out0(fp32) = acc + bias + aux(fp32)                            (residual adds)
     EPI_PERIODIC_F32 = 5,  // out0(fp32) = acc + aux_table(fp32)[row % period]             (patch embed + pos/cls)
 };
@@ -28,7 +28,7 @@ struct GemmArgs {
     const void* aux = nullptr; int64_t ldaux = 0; int64_t aux_period = 0;
     int cta_group = 0;   // 0 = library default, 1 or 2
     int block_n = 0;     // 0 = auto, 128 or 256
-    float drop_p = 0.f;  // dropout on the produced value (before the residual add; on G for EPI_GELU; times gelu' for EPI_GELU_BWD)
+    float drop_p = 0.f;  // dropout on the produced value (before the residual add; on both outputs of EPI_GELU)
     uint32_t drop_seed = 0;
 };
 int gemm_f16(const GemmArgs& a, cudaStream_t stream);

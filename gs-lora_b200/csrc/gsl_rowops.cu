@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
 int layernorm_bwd(const void* dy, int dy_is_fp16, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16, int64_t M, int D,
                   float drop_p, uint32_t drop_seed, cudaStream_t s) {
-    const uint32_t dth = drop_p > 0.f ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
+    const uint32_t dth = drop_thresh15(drop_p);
     const float dsc = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     GSL_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm_bwd: D=%d must be a multiple of 128 and <= 1024", D);
     const int warps = 8;

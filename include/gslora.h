@@ -28,8 +28,8 @@ void gsl_set_gemm_cta_group(int cta_group);
 enum {
   GSL_EPI_F16 = 0,          /* out0 fp16 = acc + bias                                              */
   GSL_EPI_F32 = 1,          /* out0 fp32 = acc + bias                     [+ out1 fp16 copy]        */
-  GSL_EPI_GELU = 2,         /* out0 fp16 = h = acc + bias, out1 fp16 = gelu_erf(h)                  */
-  GSL_EPI_GELU_BWD = 3,     /* out0 fp16 = acc * gelu'(aux fp16)                                    */
+  GSL_EPI_GELU = 2,         /* h = acc + bias: out1 fp16 = Dropout(gelu_erf(h)), out0 fp16 = d out1/d h */
+  GSL_EPI_GELU_BWD = 3,     /* out0 fp16 = acc * aux fp16  (aux = out0 of GSL_EPI_GELU)             */
   GSL_EPI_RES_F32 = 4,      /* out0 fp32 = acc + bias + aux fp32                                    */
   GSL_EPI_PERIODIC_F32 = 5  /* out0 fp32 = acc + aux_table fp32[row % aux_period]                   */
 };

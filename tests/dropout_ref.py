@@ -12,19 +12,26 @@ def drop_hash(pair: torch.Tensor, seed: int) -> torch.Tensor:
     return h ^ (h >> 16)
 
 
+def drop_bits(pair: torch.Tensor, seed: int) -> torch.Tensor:
+    """csrc/gsl_common.cuh drop_bits: the per-pair mask hash (two multiply / xor-shift rounds)."""
+    h = ((pair ^ seed) * 0x9E3779B1) & M32
+    h = h ^ (h >> 15)
+    return (h * 0x85EBCA77) & M32
+
+
 def site_seed(base: int, block: int, site: int) -> int:
     s = (base & M32) ^ ((base >> 32) & M32)
     return int(drop_hash(torch.tensor([block * 4 + site + 1], dtype=torch.int64), s).item())
 
 
 def keep_mask(rows: int, cols: int, p: float, seed: int) -> torch.Tensor:
-    """[rows, cols] float mask with values 0 or 1/(1-p); element index e = row * cols + col, pair e >> 1, 16 bits per element."""
+    """[rows, cols] float mask with values 0 or 1/(1-p); element index e = row * cols + col, pair e >> 1, 15 bits per element."""
     if p <= 0:
         return torch.ones(rows, cols)
     e = torch.arange(rows * cols, dtype=torch.int64)
-    h = drop_hash(e >> 1, seed)
-    bits = torch.where((e & 1) == 1, h >> 16, h & 0xFFFF)
-    thresh = int(p * 65536.0 + 0.5)
+    h = drop_bits(e >> 1, seed)
+    bits = torch.where((e & 1) == 1, h >> 16, h) & 0x7FFF
+    thresh = int(p * 32768.0 + 0.5)
     return ((bits >= thresh).float() / (1.0 - p)).view(rows, cols)
 
 

@@ -45,11 +45,11 @@ def test_gemm_epilogues(F, M, N, K, epi, cg, bn):
         out0 = torch.empty(M, N, device=dev); out1 = torch.empty(M, N, device=dev, dtype=torch.half); want0 = want1 = acc + bias
     elif epi == F.EPI_GELU:
         out0 = torch.empty(M, N, device=dev, dtype=torch.half); out1 = torch.empty(M, N, device=dev, dtype=torch.half)
-        want0 = acc + bias; want1 = torch.nn.functional.gelu(want0)
+        h = (acc + bias).requires_grad_(True); want1 = torch.nn.functional.gelu(h); want1.sum().backward()
+        want0 = h.grad; want1 = want1.detach()       # out0 = gelu'(h) (what the backward multiplies by), out1 = gelu(h)
     elif epi == F.EPI_GELU_BWD:
         aux = torch.randn(M, N, device=dev).half(); out0 = torch.empty(M, N, device=dev, dtype=torch.half)
-        h = aux.float().requires_grad_(True); torch.nn.functional.gelu(h).sum().backward()
-        bias = None; want0 = acc * h.grad
+        bias = None; want0 = acc * aux.float()
     elif epi == F.EPI_RES_F32:
         aux = torch.randn(M, N, device=dev); out0 = torch.empty(M, N, device=dev)
         want0 = acc + bias + aux
