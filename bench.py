@@ -60,7 +60,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.1)
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
@@ -194,23 +194,25 @@ def run_gslora(args):
 
 
 def kernel_roofline(dev, cfg, peaks):
-    """Fused FFN+LoRA GEMM pair (fc1: [x | T1][W1 | sB1]^T + b1 -> H, gelu(H); fc2: [G | T2][W2 | sB2]^T + b2 + x), timed live with CUDA
-    events on the launching stream at the step's own shape (M = 1024 * 197 rows).  Algorithmic FLOPs per launch pair:
-    2 * M * (D*H*2 + 2r(D+H)); peak = measured cuBLAS bf16 burst."""
+    """Fused FFN+LoRA GEMM pair at the step's own shape (M = 1024 * 197 rows), timed live with CUDA events on the launching stream:
+      fc1: x W1'^T + b1 -> G = Dropout(gelu(h)) and mask * gelu'(h)        (W' = W + s B A: the LoRA branch of loralib.Linear folded in)
+      fc2: G W2'^T + b2, Dropout, + residual x
+    Algorithmic FLOPs per launch pair: 2 * M * (D*H*2 + 2r(D+H)) (SURVEY 8d -- what the reference's two lora.Linear layers compute);
+    peak = measured cuBLAS bf16 burst."""
     from gslora import _ffi as F
     M, D, H, r = 2 * BATCH * cfg.tokens, cfg.dim, cfg.mlp_dim, cfg.lora_rank
-    x = (torch.randn(M, D + 16, device=dev) * 0.5).half()
-    w1 = (torch.randn(H, D + 16, device=dev) * 0.05).half()
-    w2 = (torch.randn(D, H + 16, device=dev) * 0.02).half()
+    x = (torch.randn(M, D, device=dev) * 0.5).half()
+    w1 = (torch.randn(H, D, device=dev) * 0.05).half()
+    w2 = (torch.randn(D, H, device=dev) * 0.02).half()
     b1, b2 = torch.randn(H, device=dev), torch.randn(D, device=dev)
-    h = torch.empty(M, H, device=dev, dtype=torch.half)
-    gcat = torch.empty(M, H + 16, device=dev, dtype=torch.half)
+    gp = torch.empty(M, H, device=dev, dtype=torch.half)
+    g = torch.empty(M, H, device=dev, dtype=torch.half)
     res = torch.randn(M, D, device=dev)
     y = torch.empty(M, D, device=dev)
 
     def pair():
-        F.gemm_f16(x, w1, epi=F.EPI_GELU, bias=b1, out0=h, out1=gcat, N=H)
-        F.gemm_f16(gcat, w2, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=res)
+        F.gemm_f16(x, w1, epi=F.EPI_GELU, bias=b1, out0=gp, out1=g, drop_p=DROPOUT, drop_seed=17)
+        F.gemm_f16(g, w2, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=res, drop_p=DROPOUT, drop_seed=18)
     for _ in range(3):
         pair()
     torch.cuda.synchronize()
@@ -230,10 +232,12 @@ def kernel_roofline(dev, cfg, peaks):
         with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_src = tj.get("ffn_pair_bytes"), tj.get("source")
-    return dict(bound="tensor", kernel="gemm_tcgen05_kernel<2,256,EPI_GELU> + <2,256,EPI_RES_F32> (fused FFN+LoRA pair)", achieved=round(ach, 1),
-                peak=peaks["burst"], unit="TFLOP/s", frac=round(ach / peaks["burst"], 4), traffic=traffic, traffic_source=traffic_src,
-                algorithmic_bytes=int(2 * M * (D + 16) + 2 * (2 * M * H + 16 * M) + 2 * M * (H + 16) + 8 * M * D),
-                ms_per_launch_pair=round(ms, 4), peak_source=peaks["source"] + " cuBLAS bf16 burst")
+    # fc1 reads x, writes G and mask*gelu'(h) (fp16); fc2 reads G and the fp32 residual, writes the fp32 stream; weights 4 x D x H fp16
+    alg_bytes = 2 * M * D + 2 * 2 * M * H + 2 * M * H + 2 * 4 * M * D + 4 * D * H
+    return dict(bound="tensor", kernel="gemm_tcgen05_kernel<2,256,EPI_GELU> + <2,256,EPI_RES_F32> (fused FFN+LoRA pair, dropout 0.1)",
+                achieved=round(ach, 1), peak=peaks["burst"], unit="TFLOP/s", frac=round(ach / peaks["burst"], 4), traffic=traffic,
+                traffic_source=traffic_src, algorithmic_bytes=int(alg_bytes), ms_per_launch_pair=round(ms, 4),
+                peak_source=peaks["source"] + " cuBLAS bf16 burst")
 
 
 def cpu_baseline(sample_batch=16, steps=2):
@@ -277,7 +281,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gslora", choices=["gslora", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -62,6 +62,13 @@ int gsl_skinny_tn(const void* L16, int64_t ldl, const void* R16, int64_t ldr, fl
     return skinny_tn((const __half*)L16, ldl, (const __half*)R16, ldr, out, ldo, transpose_out, scale, accumulate, M, N, r, workspace,
                      workspace_bytes, ST(stream));
 }
+size_t gsl_lora_side_workspace(int64_t M, int N, int r) { return lora_side_workspace(M, N, r); }
+int gsl_lora_side(const void* L16, int64_t ldl, const void* P16, int64_t ldp, void* T16, int64_t ldt, const void* R16, int64_t ldr,
+                  float* out, int64_t ldo, int transpose_out, float scale, int accumulate, int64_t M, int N, int r,
+                  float* workspace, size_t workspace_bytes, void* stream) {
+    return lora_side((const __half*)L16, ldl, (const __half*)P16, ldp, (__half*)T16, ldt, (const __half*)R16, ldr, out, ldo, transpose_out, scale,
+                     accumulate, M, N, r, workspace, workspace_bytes, ST(stream));
+}
 int gsl_attention_fwd(const void* qkv16, int64_t ld, void* out16, int64_t ldo, float* lse, int B, int N, int heads, float scale, void* stream) {
     return attention_fwd((const __half*)qkv16, ld, (__half*)out16, ldo, lse, B, N, heads, scale, ST(stream));
 }

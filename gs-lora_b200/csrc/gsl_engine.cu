@@ -3,12 +3,14 @@
 // the frozen layers from the head down to block 0's FFN, nothing below that has a trainable ancestor).
 //
 // Memory: the caller hands over ONE workspace (a torch uint8 tensor); carve() lays out
-//   fp16 operand caches of the frozen weights  [W | s*B] and transposes [W^T | s*A^T]  (K-extension for LoRA)
+//   fp16 operand caches of the frozen weights and their transposes; the FFN caches hold W + s*B*A while LoRA is live
 //   `num_slots` activation sets (what the backward needs: residual snapshots, LN stats, q/k/v, O, LSE,
-//    [LN2(x) | T1], pre-GELU H, [G | T2])
+//    LN2(x), mask*gelu'(h), G = Dropout(gelu(h)))
 //   transient gradient buffers shared by all slots.
 #include "gsl_engine.h"
 #include "gsl_common.cuh"
+
+#include <cstring>
 
 namespace gsl {
 
@@ -48,10 +50,10 @@ size_t Engine::carve(bool assign) {
         c.qkv_wT16 = (__half*)take((size_t)D * 3 * inner * 2);
         c.out_w16 = (__half*)take((size_t)D * inner * 2);
         c.out_wT16 = (__half*)take((size_t)inner * D * 2);
-        c.fc1_cat = (__half*)take((size_t)H * (D + 16) * 2);
-        c.fc1T_cat = (__half*)take((size_t)D * (H + 16) * 2);
-        c.fc2_cat = (__half*)take((size_t)D * (H + 16) * 2);
-        c.fc2T_cat = (__half*)take((size_t)H * (D + 16) * 2);
+        c.fc1_w16 = (__half*)take((size_t)H * D * 2);
+        c.fc1T_w16 = (__half*)take((size_t)D * H * 2);
+        c.fc2_w16 = (__half*)take((size_t)D * H * 2);
+        c.fc2T_w16 = (__half*)take((size_t)H * D * 2);
         c.A1h = (__half*)take((size_t)16 * D * 2);
         c.A2h = (__half*)take((size_t)16 * H * 2);
         c.B1T = (__half*)take((size_t)16 * H * 2);
@@ -69,15 +71,15 @@ size_t Engine::carve(bool assign) {
             a.lse = (float*)take((size_t)Bm * cfg.heads * tokens * 4);
             a.qkv16 = (__half*)take((size_t)M * 3 * inner * 2);
             a.o16 = (__half*)take((size_t)M * inner * 2);
-            a.xn2cat16 = (__half*)take((size_t)M * (D + 16) * 2);
-            a.h16 = (__half*)take((size_t)M * H * 2);
-            a.gcat16 = (__half*)take((size_t)M * (H + 16) * 2);
+            a.xn2_16 = (__half*)take((size_t)M * D * 2);
+            a.gp16 = (__half*)take((size_t)M * H * 2);
+            a.g16 = (__half*)take((size_t)M * H * 2);
             sl.blk.push_back(a);
         }
         sl.cls.xin32 = (float*)take((size_t)Bm * D * 4); sl.cls.xmid32 = (float*)take((size_t)Bm * D * 4); sl.cls.xout32 = (float*)take((size_t)Bm * D * 4);
         sl.cls.ln2_mean = (float*)take((size_t)Bm * 4); sl.cls.ln2_rstd = (float*)take((size_t)Bm * 4); sl.cls.lse = (float*)take((size_t)Bm * cfg.heads * 4);
-        sl.cls.o16 = (__half*)take((size_t)Bm * inner * 2); sl.cls.xn2cat16 = (__half*)take((size_t)Bm * (D + 16) * 2);
-        sl.cls.h16 = (__half*)take((size_t)Bm * H * 2); sl.cls.gcat16 = (__half*)take((size_t)Bm * (H + 16) * 2);
+        sl.cls.o16 = (__half*)take((size_t)Bm * inner * 2); sl.cls.xn2_16 = (__half*)take((size_t)Bm * D * 2);
+        sl.cls.gp16 = (__half*)take((size_t)Bm * H * 2); sl.cls.g16 = (__half*)take((size_t)Bm * H * 2);
         sl.emb = (float*)take((size_t)Bm * D * 4);
         sl.logits = (float*)take((size_t)Bm * C * 4);
         sl.ce = (float*)take((size_t)Bm * 4);
@@ -88,29 +90,36 @@ size_t Engine::carve(bool assign) {
     }
     auto* t_patches = (__half*)take((size_t)M * patch_dim * 2);
     auto* t_xn = (__half*)take((size_t)M * D * 2);
-    auto* t_dxcat = (__half*)take((size_t)M * (D + 16) * 2);
-    auto* t_dhcat = (__half*)take((size_t)M * (H + 16) * 2);
+    auto* t_dy = (__half*)take((size_t)M * D * 2);
+    auto* t_dh = (__half*)take((size_t)M * H * 2);
+    __half* t_tu[4];
+    for (int i = 0; i < 4; ++i) t_tu[i] = (__half*)take((size_t)M * 16 * 2);
     auto* t_do = (__half*)take((size_t)M * inner * 2);
     auto* t_dqkv = (__half*)take((size_t)M * 3 * inner * 2);
     auto* t_dx32 = (float*)take((size_t)M * D * 4);
     auto* t_dxn32 = (float*)take((size_t)M * D * 4);
     auto* t_cdx = (float*)take((size_t)Bm * D * 4);
     auto* t_cdxn = (float*)take((size_t)Bm * D * 4);
-    auto* t_cdxcat = (__half*)take((size_t)Bm * (D + 16) * 2);
-    auto* t_cdhcat = (__half*)take((size_t)Bm * (H + 16) * 2);
+    auto* t_cdy = (__half*)take((size_t)Bm * D * 2);
+    auto* t_cdh = (__half*)take((size_t)Bm * H * 2);
     auto* t_cdo = (__half*)take((size_t)Bm * inner * 2);
-    const size_t sk = skinny_tn_workspace(M, (int)(H > D ? H : D), cfg.lora_rank);
+    size_t sk = skinny_tn_workspace(M, (int)(H > D ? H : D), cfg.lora_rank);
+    const size_t sk_side = lora_side_workspace(M, (int)H, cfg.lora_rank);
+    if (sk_side > sk) sk = sk_side;
     auto* t_sk = (float*)take(sk);
     auto* t_go = (int*)take((size_t)(L + 1) * 4);
     auto* t_to = (int*)take((size_t)(4 * L + 1) * 4);
     auto* t_gn = (float*)take((size_t)L * 4);
     auto* t_tn = (float*)take((size_t)4 * L * 4);
     auto* t_pp = (void*)take((size_t)L * 8 * sizeof(void*));
+    auto* t_mj = (void*)take((size_t)L * 2 * 64);
     if (assign) {
-        patches16 = t_patches; xn16 = t_xn; dxcat16 = t_dxcat; dhcat16 = t_dhcat; do16 = t_do; dqkv16 = t_dqkv;
+        patches16 = t_patches; xn16 = t_xn; dy16 = t_dy; dh16 = t_dh; do16 = t_do; dqkv16 = t_dqkv;
+        t1_16 = t_tu[0]; t2_16 = t_tu[1]; u1_16 = t_tu[2]; u2_16 = t_tu[3];
         dx32 = t_dx32; dxn32 = t_dxn32; skinny_ws = t_sk; skinny_ws_bytes = sk;
-        cls_dx32 = t_cdx; cls_dxn32 = t_cdxn; cls_dxcat16 = t_cdxcat; cls_dhcat16 = t_cdhcat; cls_do16 = t_cdo;
+        cls_dx32 = t_cdx; cls_dxn32 = t_cdxn; cls_dy16 = t_cdy; cls_dh16 = t_cdh; cls_do16 = t_cdo;
         group_offsets_dev = t_go; tensor_offsets_dev = t_to; group_norms_dev = t_gn; tensor_norms_dev = t_tn; pack_ptrs_dev = t_pp;
+        merge_jobs_dev = t_mj;
     }
     return align_up(off, 1024);
 }
@@ -161,10 +170,56 @@ int Engine::init(const GslConfig& c, void* workspace, size_t bytes) {
     std::vector<void*> pp;
     for (int l = 0; l < c.depth; ++l) {
         const BlockCache& bc = cache[l];
-        void* row[8] = {bc.A1h, bc.A2h, bc.B1T, bc.B2T, bc.fc1_cat, bc.fc1T_cat, bc.fc2_cat, bc.fc2T_cat};
+        void* row[8] = {bc.A1h, bc.A2h, bc.B1T, bc.B2T, nullptr, nullptr, nullptr, nullptr};
         pp.insert(pp.end(), row, row + 8);
     }
     GSL_CHECK_CUDA(cudaMemcpy(pack_ptrs_dev, pp.data(), pp.size() * sizeof(void*), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// out = fp16(W + sc * B A) and its transpose, W [R, C] fp32, A [r, C], B [R, r] (loralib.Linear's merged weight, layers.py train/eval);
+// sc = 0 gives the plain fp16 cast.  One 32 x 32 tile per CTA, the transpose goes through shared memory.
+struct MergeJob {
+    const float *W, *A, *B;
+    __half *out, *outT;
+    int R, C;
+};
+__global__ void __launch_bounds__(256) merge_weights_kernel(const uint8_t* __restrict__ jobs_raw, int r, float sc) {
+    __shared__ float tile[32][33];
+    const MergeJob j = *reinterpret_cast<const MergeJob*>(jobs_raw + (size_t)blockIdx.z * 64);
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    if (c0 >= j.C || r0 >= j.R) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = r0 + ty + 8 * i, col = c0 + tx;
+        float v = j.W[(int64_t)row * j.C + col];
+        if (sc != 0.f) {
+            float d = 0.f;
+            for (int k = 0; k < r; ++k) d = fmaf(j.B[(int64_t)row * r + k], j.A[(int64_t)k * j.C + col], d);
+            v = fmaf(sc, d, v);
+        }
+        j.out[(int64_t)row * j.C + col] = __float2half_rn(v);
+        tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int col = c0 + ty + 8 * i, row = r0 + tx;
+        j.outT[(int64_t)col * j.R + row] = __float2half_rn(tile[tx][ty + 8 * i]);
+    }
+}
+
+int Engine::ensure_ffn_weights(int use_lora, cudaStream_t s) {
+    const int mode = use_lora ? 1 : 0;
+    if (ffn_cache_mode == mode) return 0;
+    const int D = cfg.dim, H = cfg.mlp_dim;
+    const int big = H > D ? H : D;
+    dim3 grid(big / 32, big / 32, 2 * cfg.depth);
+    merge_weights_kernel<<<grid, 256, 0, s>>>((const uint8_t*)merge_jobs_dev, cfg.lora_rank, use_lora ? cfg.lora_scaling : 0.f);
+    GSL_COUNT_LAUNCH(1);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    ffn_cache_mode = mode;
     return 0;
 }
 
@@ -187,6 +242,21 @@ int Engine::bind_params(const void* const* p, int n, float* lora, float* grads) 
     GSL_REQUIRE(lora != nullptr, "lora_flat is null");
     lora_flat = lora; grad_flat = grads;
     params_bound = true;
+    ffn_cache_mode = -1;
+    // merge jobs: per block  fc1 (W1 [H, D], A1, B1)  and  fc2 (W2 [D, H], A2, B2)
+    std::vector<MergeJob> jobs;
+    for (int l = 0; l < cfg.depth; ++l) {
+        MergeJob j1, j2;
+        j1.W = frozen[l].fc1_w; j1.A = lora_flat + lora_offset(l, 0); j1.B = lora_flat + lora_offset(l, 1);
+        j1.out = cache[l].fc1_w16; j1.outT = cache[l].fc1T_w16; j1.R = cfg.mlp_dim; j1.C = cfg.dim;
+        j2.W = frozen[l].fc2_w; j2.A = lora_flat + lora_offset(l, 2); j2.B = lora_flat + lora_offset(l, 3);
+        j2.out = cache[l].fc2_w16; j2.outT = cache[l].fc2T_w16; j2.R = cfg.dim; j2.C = cfg.mlp_dim;
+        jobs.push_back(j1); jobs.push_back(j2);
+    }
+    static_assert(sizeof(MergeJob) <= 64, "MergeJob slot");
+    std::vector<uint8_t> raw(jobs.size() * 64, 0);
+    for (size_t i = 0; i < jobs.size(); ++i) memcpy(raw.data() + i * 64, &jobs[i], sizeof(MergeJob));
+    GSL_CHECK_CUDA(cudaMemcpy(merge_jobs_dev, raw.data(), raw.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -218,66 +288,41 @@ int Engine::refresh_frozen(cudaStream_t s) {
         if ((rc = fill_zero(c.A2h, (size_t)16 * H * 2, s))) return rc;
         if ((rc = fill_zero(c.B1T, (size_t)16 * H * 2, s))) return rc;
         if ((rc = fill_zero(c.B2T, (size_t)16 * D * 2, s))) return rc;
-        if ((rc = fill_zero(c.fc1_cat, (size_t)H * (D + 16) * 2, s))) return rc;
-        if ((rc = fill_zero(c.fc1T_cat, (size_t)D * (H + 16) * 2, s))) return rc;
-        if ((rc = fill_zero(c.fc2_cat, (size_t)D * (H + 16) * 2, s))) return rc;
-        if ((rc = fill_zero(c.fc2T_cat, (size_t)H * (D + 16) * 2, s))) return rc;
-        if ((rc = cast_f32_to_f16(f.fc1_w, D, c.fc1_cat, D + 16, H, D, 1.f, 0, s))) return rc;
-        if ((rc = cast_f32_to_f16(f.fc1_w, D, c.fc1T_cat, H + 16, H, D, 1.f, 1, s))) return rc;
-        if ((rc = cast_f32_to_f16(f.fc2_w, H, c.fc2_cat, H + 16, D, H, 1.f, 0, s))) return rc;
-        if ((rc = cast_f32_to_f16(f.fc2_w, H, c.fc2T_cat, D + 16, D, H, 1.f, 1, s))) return rc;
     }
+    ffn_cache_mode = -1;        // the FFN caches are rebuilt (with or without the LoRA delta) by the next forward
     return refresh_lora(s);
 }
 
-// One launch repacks every fp16 LoRA operand of every block from the flat fp32 parameter buffer:
-//   A1h/A2h = lora_A, B1T/B2T = lora_B^T (skinny products), and the K-extension columns  s*B -> [W | sB],  s*A^T -> [W^T | sA^T].
+// One launch repacks the fp16 LoRA operands of every block from the flat fp32 parameter buffer: A1h/A2h = lora_A, B1T/B2T = lora_B^T
+// (the rank-r by-products T = x A^T, U = dY B of the backward).  The FFN weight caches are re-merged lazily by the next forward.
 struct LoraPackPtrs {
-    __half *A1h, *A2h, *B1T, *B2T, *fc1_cat, *fc1T_cat, *fc2_cat, *fc2T_cat;
+    __half *A1h, *A2h, *B1T, *B2T;
+    void* unused[4];
 };
-__global__ void lora_pack_kernel(const float* __restrict__ flat, const LoraPackPtrs* __restrict__ ptrs, int D, int H, int r, float sc, int per_block) {
+__global__ void lora_pack_kernel(const float* __restrict__ flat, const LoraPackPtrs* __restrict__ ptrs, int D, int H, int r, int per_block) {
     const int l = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= per_block) return;
     const LoraPackPtrs p = ptrs[l];
-    const float v = flat[(int64_t)l * per_block + i];
-    const __half hv = __float2half_rn(v), hs = __float2half_rn(v * sc);
+    const __half hv = __float2half_rn(flat[(int64_t)l * per_block + i]);
     int k = i;
-    if (k < r * D) {                       // lora_A(net.0) [r, D]
-        const int j = k / D, d = k % D;
-        p.A1h[(int64_t)j * D + d] = hv;
-        p.fc1T_cat[(int64_t)d * (H + 16) + H + j] = hs;
-        return;
-    }
+    if (k < r * D) { p.A1h[k] = hv; return; }                                   // lora_A(net.0) [r, D]
     k -= r * D;
-    if (k < H * r) {                       // lora_B(net.0) [H, r]
-        const int h = k / r, j = k % r;
-        p.B1T[(int64_t)j * H + h] = hv;
-        p.fc1_cat[(int64_t)h * (D + 16) + D + j] = hs;
-        return;
-    }
+    if (k < H * r) { p.B1T[(int64_t)(k % r) * H + k / r] = hv; return; }       // lora_B(net.0) [H, r]
     k -= H * r;
-    if (k < r * H) {                       // lora_A(net.3) [r, H]
-        const int j = k / H, h = k % H;
-        p.A2h[(int64_t)j * H + h] = hv;
-        p.fc2T_cat[(int64_t)h * (D + 16) + D + j] = hs;
-        return;
-    }
+    if (k < r * H) { p.A2h[k] = hv; return; }                                   // lora_A(net.3) [r, H]
     k -= r * H;
-    {                                      // lora_B(net.3) [D, r]
-        const int d = k / r, j = k % r;
-        p.B2T[(int64_t)j * D + d] = hv;
-        p.fc2_cat[(int64_t)d * (H + 16) + H + j] = hs;
-    }
+    p.B2T[(int64_t)(k % r) * D + k / r] = hv;                                   // lora_B(net.3) [D, r]
 }
 
 int Engine::refresh_lora(cudaStream_t s) {
     GSL_REQUIRE(params_bound, "bind_params first");
     const int per_block = (int)lora_block_elems();
     dim3 grid((per_block + 255) / 256, cfg.depth);
-    lora_pack_kernel<<<grid, 256, 0, s>>>(lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, cfg.lora_scaling, per_block);
+    lora_pack_kernel<<<grid, 256, 0, s>>>(lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, per_block);
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
+    if (ffn_cache_mode == 1) ffn_cache_mode = -1;       // W + s B A is stale
     return 0;
 }
 
@@ -286,26 +331,25 @@ static inline uint32_t site_seed(uint64_t base, int block, int site) {
     return drop_hash((uint32_t)(block * 4 + site + 1), (uint32_t)base ^ (uint32_t)(base >> 32));
 }
 
-// x_out = FeedForward(LN2(x_mid)) + x_mid on M rows (dense tokens, or the compacted cls rows of the last block)
-int Engine::ffn_forward(int l, int64_t M, __half* xn2cat, float* ln_mean, float* ln_rstd, const float* x_mid, __half* h16, __half* gcat, float* x_out,
-                        int use_lora, float pdrop, uint64_t dseed, cudaStream_t s) {
-    const int D = cfg.dim, H = cfg.mlp_dim, r = cfg.lora_rank, kx = use_lora ? 16 : 0;
+// x_out = FeedForward(LN2(x_mid)) + x_mid on M rows (dense tokens, or the compacted cls rows of the last block).  The LoRA branches
+// of both lora.Linear layers are inside the cached weights (ensure_ffn_weights), so this is LN -> GEMM(+GELU) -> GEMM(+residual).
+int Engine::ffn_forward(int l, int64_t M, __half* xn2, float* ln_mean, float* ln_rstd, const float* x_mid, __half* gp16, __half* g16, float* x_out,
+                        float pdrop, uint64_t dseed, cudaStream_t s) {
+    const int D = cfg.dim, H = cfg.mlp_dim;
     const BlockFrozen& f = frozen[l];
     const BlockCache& c = cache[l];
     int rc;
-    if ((rc = layernorm_fwd(x_mid, D, f.ln2_w, f.ln2_b, cfg.ln_eps, xn2cat, D + 16, ln_mean, ln_rstd, M, D, s))) return rc;
-    if (use_lora && (rc = lora_down(xn2cat, D + 16, c.A1h, D, xn2cat + D, D + 16, M, D, r, s))) return rc;      // T1 = LN2(x) A1^T
+    if ((rc = layernorm_fwd(x_mid, D, f.ln2_w, f.ln2_b, cfg.ln_eps, xn2, D, ln_mean, ln_rstd, M, D, s))) return rc;
     {
         GemmArgs g;
-        g.A = xn2cat; g.lda = D + 16; g.B = c.fc1_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + kx;
-        g.epi = EPI_GELU; g.bias = f.fc1_b; g.out0 = h16; g.ld0 = H; g.out1 = gcat; g.ld1 = H + 16;
+        g.A = xn2; g.lda = D; g.B = c.fc1_w16; g.ldb = D; g.M = M; g.N = H; g.K = D;
+        g.epi = EPI_GELU; g.bias = f.fc1_b; g.out0 = gp16; g.ld0 = H; g.out1 = g16; g.ld1 = H;
         g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 2);
         if ((rc = gemm_f16(g, s))) return rc;
     }
-    if (use_lora && (rc = lora_down(gcat, H + 16, c.A2h, H, gcat + H, H + 16, M, H, r, s))) return rc;          // T2 = G A2^T
     {
         GemmArgs g;
-        g.A = gcat; g.lda = H + 16; g.B = c.fc2_cat; g.ldb = H + 16; g.M = M; g.N = D; g.K = H + kx;
+        g.A = g16; g.lda = H; g.B = c.fc2_w16; g.ldb = H; g.M = M; g.N = D; g.K = H;
         g.epi = EPI_RES_F32; g.bias = f.fc2_b; g.out0 = x_out; g.ld0 = D; g.aux = x_mid; g.ldaux = D;
         g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 3);
         if ((rc = gemm_f16(g, s))) return rc;
@@ -323,6 +367,7 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
     S.batch = B; S.used_lora = use_lora; S.drop_seed = dropout_seed;
     const float pdrop = dropout_seed ? cfg.dropout : 0.f, pemb = dropout_seed ? cfg.emb_dropout : 0.f;
     int rc;
+    if ((rc = ensure_ffn_weights(use_lora, s))) return rc;
     if ((rc = patchify_f16(img, patches16, patch_dim, B, cfg.channels, cfg.image_size, cfg.patch_size, cfg.patch_order, s))) return rc;
     {   // patch_to_embedding + cls token + pos_embedding (vit_face.py:531-536)
         GemmArgs g;
@@ -354,7 +399,7 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
             g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
             // ---- x = FeedForward(LN(x)) + x, loralib.Linear on both projections
-            if ((rc = ffn_forward(l, M, a.xn2cat16, a.ln2_mean, a.ln2_rstd, x_mid, a.h16, a.gcat16, x_out, use_lora, pdrop, dropout_seed, s))) return rc;
+            if ((rc = ffn_forward(l, M, a.xn2_16, a.ln2_mean, a.ln2_rstd, x_mid, a.gp16, a.g16, x_out, pdrop, dropout_seed, s))) return rc;
         } else {
             // ---- last block: only the cls token is pooled (vit_face.py:540), every other token of this block is dead.
             //      Single-query attention per (image, head), then out-proj / FFN on the B compacted cls rows.
@@ -366,7 +411,7 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
             g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = k.xmid32; g.ld0 = D; g.aux = k.xin32; g.ldaux = D;
             g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
-            if ((rc = ffn_forward(l, B, k.xn2cat16, k.ln2_mean, k.ln2_rstd, k.xmid32, k.h16, k.gcat16, k.xout32, use_lora, pdrop, dropout_seed, s))) return rc;
+            if ((rc = ffn_forward(l, B, k.xn2_16, k.ln2_mean, k.ln2_rstd, k.xmid32, k.gp16, k.g16, k.xout32, pdrop, dropout_seed, s))) return rc;
         }
     }
     HeadArgs h;
@@ -378,12 +423,12 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
     return head_fwd(h, s);
 }
 
-// Backward of x_out = FeedForward(LN2(x_mid)) + x_mid on M rows.  In: dx / dxcat[:, :D] = gradient w.r.t. x_out (fp32 / fp16, the fp16 copy
-// already carries the fc2-output dropout mask).  Out: dA / dB of both LoRA layers; unless l == 0, dx / dxcat = gradient w.r.t. x_mid
-// (the fp16 copy masked for the attention to_out dropout).  Closed forms: SURVEY Appendix C.
-int Engine::ffn_backward(int l, int64_t M, __half* dxcat, float* dx, __half* dhcat, float* dxn, const __half* xn2cat, const __half* h16,
-                         const __half* gcat, const float* x_mid, const float* ln_mean, const float* ln_rstd, int accumulate, float pdrop,
-                         uint64_t dseed, cudaStream_t s) {
+// Backward of x_out = FeedForward(LN2(x_mid)) + x_mid on M rows.  In: dx (fp32) and dy (fp16, already carrying the fc2-output dropout
+// mask) = gradient w.r.t. x_out.  Out: dA / dB of both LoRA layers; unless l == 0, dx / dy = gradient w.r.t. x_mid (the fp16 copy masked
+// for the attention to_out dropout).  Closed forms: SURVEY Appendix C; the dX GEMMs use the merged weights (dY W' = dY W + s (dY B) A),
+// the rank-r by-products T = x A^T, U = dY B exist only here and the two wide ones ride on the single pass that reads G / dH anyway.
+int Engine::ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, float* dxn, const __half* xn2, const __half* gp16, const __half* g16,
+                         const float* x_mid, const float* ln_mean, const float* ln_rstd, int accumulate, float pdrop, uint64_t dseed, cudaStream_t s) {
     const int D = cfg.dim, H = cfg.mlp_dim, r = cfg.lora_rank;
     const BlockFrozen& f = frozen[l];
     const BlockCache& c = cache[l];
@@ -393,26 +438,26 @@ int Engine::ffn_backward(int l, int64_t M, __half* dxcat, float* dx, __half* dhc
     float* gA2 = grad_flat + lora_offset(l, 2);
     float* gB2 = grad_flat + lora_offset(l, 3);
     int rc;
-    if ((rc = lora_down(dxcat, D + 16, c.B2T, D, dxcat + D, D + 16, M, D, r, s))) return rc;                                        // U2 = dY2 B2
-    if ((rc = skinny_tn(dxcat, D + 16, gcat + H, H + 16, gB2, r, 0, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // dB2 = s dY2^T T2
-    if ((rc = skinny_tn(gcat, H + 16, dxcat + D, D + 16, gA2, H, 1, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // dA2 = s U2^T G
-    {   // dH = (dY2 W2 + s U2 A2) * d[Dropout(gelu(h))] / dh
+    if ((rc = lora_down(dy, D, c.B2T, D, u2_16, 16, M, D, r, s))) return rc;                                                        // U2 = dY2 B2
+    if ((rc = lora_side(g16, H, c.A2h, H, t2_16, 16, u2_16, 16, gA2, H, 1, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // T2 = G A2^T, dA2 = s U2^T G
+    if ((rc = skinny_tn(dy, D, t2_16, 16, gB2, r, 0, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;       // dB2 = s dY2^T T2
+    {   // dH = (dY2 W2') * d[Dropout(gelu(h))] / dh
         GemmArgs g;
-        g.A = dxcat; g.lda = D + 16; g.B = c.fc2T_cat; g.ldb = D + 16; g.M = M; g.N = H; g.K = D + 16;
-        g.epi = EPI_GELU_BWD; g.out0 = dhcat; g.ld0 = H + 16; g.aux = h16; g.ldaux = H;      // h16 = Dropout-mask * gelu'(h), saved by the forward
+        g.A = dy; g.lda = D; g.B = c.fc2T_w16; g.ldb = D; g.M = M; g.N = H; g.K = D;
+        g.epi = EPI_GELU_BWD; g.out0 = dh; g.ld0 = H; g.aux = gp16; g.ldaux = H;
         if ((rc = gemm_f16(g, s))) return rc;
     }
-    if ((rc = lora_down(dhcat, H + 16, c.B1T, H, dhcat + H, H + 16, M, H, r, s))) return rc;                                        // U1 = dH B1
-    if ((rc = skinny_tn(dhcat, H + 16, xn2cat + D, D + 16, gB1, r, 0, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc; // dB1 = s dH^T T1
-    if ((rc = skinny_tn(xn2cat, D + 16, dhcat + H, H + 16, gA1, D, 1, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc; // dA1 = s U1^T LN2(x)
+    if ((rc = lora_down(xn2, D, c.A1h, D, t1_16, 16, M, D, r, s))) return rc;                                                       // T1 = LN2(x) A1^T
+    if ((rc = lora_side(dh, H, c.B1T, H, u1_16, 16, t1_16, 16, gB1, r, 0, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc;    // U1 = dH B1, dB1 = s dH^T T1
+    if ((rc = skinny_tn(xn2, D, u1_16, 16, gA1, D, 1, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;      // dA1 = s U1^T LN2(x)
     if (l == 0) return 0;       // nothing trainable below block 0's FFN
-    {   // dLN2 = dH W1 + s U1 A1
+    {   // dLN2 = dH W1'
         GemmArgs g;
-        g.A = dhcat; g.lda = H + 16; g.B = c.fc1T_cat; g.ldb = H + 16; g.M = M; g.N = D; g.K = H + 16;
+        g.A = dh; g.lda = H; g.B = c.fc1T_w16; g.ldb = H; g.M = M; g.N = D; g.K = H;
         g.epi = EPI_F16; g.out0 = dxn; g.ld0 = D;            // fp16: halves the traffic of the LayerNorm-backward pass that consumes it
         if ((rc = gemm_f16(g, s))) return rc;
     }
-    return layernorm_bwd(dxn, 1, D, x_mid, D, ln_mean, ln_rstd, f.ln2_w, dx, D, dx, D, dxcat, D + 16, M, D, pdrop, site_seed(dseed, l, 1), s);
+    return layernorm_bwd(dxn, 1, D, x_mid, D, ln_mean, ln_rstd, f.ln2_w, dx, D, dx, D, dy, D, M, D, pdrop, site_seed(dseed, l, 1), s);
 }
 
 int Engine::backward(int slot, const float* dlogits, const float* demb, int accumulate, cudaStream_t s) {
@@ -432,7 +477,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
     hb.dlogits = dlogits; hb.demb = demb; hb.emb = S.emb; hb.W = loss_w; hb.labels = nullptr; hb.xhat = S.xhat; hb.rstd = S.head_rstd;
     hb.head_type = cfg.head_type;
     hb.gamma = head_ln_w; hb.cos_s = cfg.cos_s; hb.B = B; hb.D = D; hb.C = cfg.num_class; hb.tokens = 1; hb.gscale = cfg.grad_scale;
-    hb.dx = cls_dx32; hb.lddx = D; hb.dx16 = cls_dxcat16; hb.lddx16 = D + 16;
+    hb.dx = cls_dx32; hb.lddx = D; hb.dx16 = cls_dy16; hb.lddx16 = D;
     hb.drop_p = pdrop; hb.drop_seed = site_seed(dseed, L - 1, 3);
     if ((rc = head_bwd(hb, s))) return rc;
     {   // ---------------- last block on the compacted cls rows
@@ -441,12 +486,12 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         const BlockCache& c = cache[l];
         BlockActs& a = S.blk[l];
         ClsActs& k = S.cls;
-        if ((rc = ffn_backward(l, B, cls_dxcat16, cls_dx32, cls_dhcat16, cls_dxn32, k.xn2cat16, k.h16, k.gcat16, k.xmid32, k.ln2_mean, k.ln2_rstd,
+        if ((rc = ffn_backward(l, B, cls_dy16, cls_dx32, cls_dh16, cls_dxn32, k.xn2_16, k.gp16, k.g16, k.xmid32, k.ln2_mean, k.ln2_rstd,
                                accumulate, pdrop, dseed, s))) return rc;
         if (l == 0) return 0;
         {   // dO (cls rows) = dY Wo
             GemmArgs g;
-            g.A = cls_dxcat16; g.lda = D + 16; g.B = c.out_wT16; g.ldb = D; g.M = B; g.N = inner; g.K = D;
+            g.A = cls_dy16; g.lda = D; g.B = c.out_wT16; g.ldb = D; g.M = B; g.N = inner; g.K = D;
             g.epi = EPI_F16; g.out0 = cls_do16; g.ld0 = inner;
             if ((rc = gemm_f16(g, s))) return rc;
         }
@@ -460,7 +505,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         // residual gradient of this block's input: zero except the cls rows
         if ((rc = fill_zero(dx32, (size_t)M * D * 4, s))) return rc;
         if ((rc = copy_cls_rows(cls_dx32, (int64_t)D * 4, dx32, (int64_t)tokens * D * 4, B, (int64_t)D * 4, s))) return rc;
-        if ((rc = layernorm_bwd(dxn32, 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, pdrop,
+        if ((rc = layernorm_bwd(dxn32, 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dy16, D, M, D, pdrop,
                                 site_seed(dseed, l - 1, 3), s))) return rc;
     }
     for (int l = L - 2; l >= 0; --l) {
@@ -468,13 +513,13 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         const BlockCache& c = cache[l];
         BlockActs& a = S.blk[l];
         // ---------------- FFN: y = fc2(gelu(fc1(LN2(x)))) + x
-        if ((rc = ffn_backward(l, M, dxcat16, dx32, dhcat16, dxn32, a.xn2cat16, a.h16, a.gcat16, S.x[2 * l + 1], a.ln2_mean, a.ln2_rstd, accumulate,
+        if ((rc = ffn_backward(l, M, dy16, dx32, dh16, dxn32, a.xn2_16, a.gp16, a.g16, S.x[2 * l + 1], a.ln2_mean, a.ln2_rstd, accumulate,
                                pdrop, dseed, s))) return rc;
         if (l == 0) break;      // nothing trainable below block 0's FFN
         // ---------------- attention: y = to_out(attn(to_qkv(LN1(x)))) + x
         {   // dO = dY Wo
             GemmArgs g;
-            g.A = dxcat16; g.lda = D + 16; g.B = c.out_wT16; g.ldb = D; g.M = M; g.N = inner; g.K = D;
+            g.A = dy16; g.lda = D; g.B = c.out_wT16; g.ldb = D; g.M = M; g.N = inner; g.K = D;
             g.epi = EPI_F16; g.out0 = do16; g.ld0 = inner;
             if ((rc = gemm_f16(g, s))) return rc;
         }
@@ -485,7 +530,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
             g.epi = EPI_F16; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
-        if ((rc = layernorm_bwd(dxn32, 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dxcat16, D + 16, M, D, pdrop,
+        if ((rc = layernorm_bwd(dxn32, 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dy16, D, M, D, pdrop,
                                 site_seed(dseed, l - 1, 3), s))) return rc;
     }
     return 0;

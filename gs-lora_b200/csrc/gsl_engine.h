@@ -14,22 +14,27 @@ struct BlockFrozen {            // fp32 parameters of one Transformer block (cal
 
 struct BlockCache {             // fp16 operand caches (engine workspace)
     __half *qkv_w16, *qkv_wT16, *out_w16, *out_wT16;
-    __half *fc1_cat;    // [H, D+16]  = [W1 | s*B1 | 0]
-    __half *fc1T_cat;   // [D, H+16]  = [W1^T | s*A1^T | 0]
-    __half *fc2_cat;    // [D, H+16]  = [W2 | s*B2 | 0]
-    __half *fc2T_cat;   // [H, D+16]  = [W2^T | s*A2^T | 0]
-    __half *A1h, *A2h;  // [16, D], [16, H]   lora_A (rows >= r zero)
-    __half *B1T, *B2T;  // [16, H], [16, D]   lora_B^T
+    // FFN weights with the LoRA branch folded in while LoRA is live (un-merged train mode):  W' = W + s * B A, rounded to fp16 once per
+    // optimizer step.  x W'^T = x W^T + s (x A^T) B^T and dY W' = dY W + s (dY B) A, so neither GEMM needs the rank-r intermediates.
+    __half *fc1_w16;    // [H, D]  W1'
+    __half *fc1T_w16;   // [D, H]  W1'^T   (B operand of dLN2 = dH W1')
+    __half *fc2_w16;    // [D, H]  W2'
+    __half *fc2T_w16;   // [H, D]  W2'^T   (B operand of dG = dY2 W2')
+    __half *A1h, *A2h;  // [16, D], [16, H]   lora_A (rows >= r zero)   -> T = x A^T for dB
+    __half *B1T, *B2T;  // [16, H], [16, D]   lora_B^T                  -> U = dY B for dA
 };
 
 struct BlockActs {              // saved activations of one block for one slot
     float *ln1_mean, *ln1_rstd, *ln2_mean, *ln2_rstd, *lse;
-    __half *qkv16, *o16, *xn2cat16, *h16, *gcat16;
+    __half *qkv16, *o16;
+    __half *xn2_16;     // [M, D]  LN2(x), input of fc1
+    __half *gp16;       // [M, H]  d Dropout(gelu(h)) / d h  (EPI_GELU out0)
+    __half *g16;        // [M, H]  Dropout(gelu(h)), input of fc2
 };
 
 struct ClsActs {                // last block, compacted to the B cls rows (see gsl_clsattn.cu)
     float *xin32, *xmid32, *xout32, *ln2_mean, *ln2_rstd, *lse;
-    __half *o16, *xn2cat16, *h16, *gcat16;
+    __half *o16, *xn2_16, *gp16, *g16;
 };
 
 struct Slot {
@@ -58,11 +63,14 @@ public:
     std::vector<BlockCache> cache;
     std::vector<Slot> slots;
     // transients (shared by all slots)
-    __half *patches16, *xn16, *dxcat16, *dhcat16, *do16, *dqkv16;
+    __half *patches16, *xn16, *dy16, *dh16, *do16, *dqkv16;
+    __half *t1_16, *t2_16, *u1_16, *u2_16;      // rank-r by-products [M, 16] of the block being back-propagated
     float *dx32, *dxn32, *skinny_ws;
-    float *cls_dx32, *cls_dxn32; __half *cls_dxcat16, *cls_dhcat16, *cls_do16;
+    float *cls_dx32, *cls_dxn32; __half *cls_dy16, *cls_dh16, *cls_do16;
     size_t skinny_ws_bytes = 0;
     void* pack_ptrs_dev = nullptr;
+    void* merge_jobs_dev = nullptr;
+    int ffn_cache_mode = -1;        // -1 stale, 0 plain W, 1 W + s B A
     int* group_offsets_dev = nullptr; int* tensor_offsets_dev = nullptr; float* group_norms_dev = nullptr; float* tensor_norms_dev = nullptr;
     bool params_bound = false;
 
@@ -77,9 +85,10 @@ public:
     int64_t lora_offset(int block, int which) const;   // which: 0 A1, 1 B1, 2 A2, 3 B2
 private:
     size_t carve(bool assign);
-    int ffn_forward(int l, int64_t M, __half* xn2cat, float* ln_mean, float* ln_rstd, const float* x_mid, __half* h16, __half* gcat, float* x_out,
-                    int use_lora, float pdrop, uint64_t dseed, cudaStream_t s);
-    int ffn_backward(int l, int64_t M, __half* dxcat, float* dx, __half* dhcat, float* dxn, const __half* xn2cat, const __half* h16, const __half* gcat,
+    int ensure_ffn_weights(int use_lora, cudaStream_t s);
+    int ffn_forward(int l, int64_t M, __half* xn2, float* ln_mean, float* ln_rstd, const float* x_mid, __half* gp16, __half* g16, float* x_out,
+                    float pdrop, uint64_t dseed, cudaStream_t s);
+    int ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, float* dxn, const __half* xn2, const __half* gp16, const __half* g16,
                      const float* x_mid, const float* ln_mean, const float* ln_rstd, int accumulate, float pdrop, uint64_t dseed, cudaStream_t s);
 };
 

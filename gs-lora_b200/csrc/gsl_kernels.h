@@ -54,6 +54,13 @@ int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __ha
 int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float* out, int64_t ldo, int transpose_out,
               float scale, int accumulate, int64_t M, int N, int r, float* workspace, size_t workspace_bytes, cudaStream_t s);
 size_t skinny_tn_workspace(int64_t M, int N, int r);
+// Fused side pass over a wide activation L [M, N] (one read): T[M, 0:16] = L * P16[16, N]^T (fp16) AND
+// out[n, j] = scale * sum_m L[m, n] * Rm[m, j] (same conventions as skinny_tn).  Rank 16 / N not a multiple of 256 run as the
+// two separate kernels.  Workspace: lora_side_workspace bytes.
+int lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __half* T, int64_t ldt, const __half* Rm, int64_t ldr,
+              float* out, int64_t ldo, int transpose_out, float scale, int accumulate, int64_t M, int N, int r,
+              float* workspace, size_t workspace_bytes, cudaStream_t s);
+size_t lora_side_workspace(int64_t M, int N, int r);
 // fp32 -> fp16 casts with optional scale / transpose / column placement (weight cache building, LoRA operand packing)
 int cast_f32_to_f16(const float* src, int64_t lds, __half* dst, int64_t ldd, int64_t rows, int64_t cols, float scale,
                     int transpose, cudaStream_t s);

@@ -463,6 +463,186 @@ int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ fused LoRA side pass
+// One read of a wide activation L [M, N] (G = Dropout(gelu(h)) or dH, N = mlp_dim) yields BOTH LoRA by-products that need it
+// (SURVEY Appendix C):
+//   T[m, j] = sum_n L[m, n] * P[j, n]             down projection   T2 = G A2^T,   U1 = dH B1          -> fp16 [M, 16]
+//   Q[n, j] = scale * sum_m L[m, n] * R[m, j]      token contraction dA2^T = s G^T U2,  dB1 = s dH^T T1 -> fp32
+// so the rank-r intermediates never cost an extra pass over L.  CTA = one m-range and ALL N columns: 16 warps x (N / 16)
+// columns; 16-row chunks of L stream through a cp.async ring; every warp reads each 16 x 16 block of its columns twice with
+// ldmatrix (plain = A operand of the down projection, .trans = A operand of the token contraction) and feeds mma.sync
+// m16n8k16; P stays in registers as B fragments; the per-warp partial rows of T are summed across the 16 warps through
+// shared memory; the Q partials of every CTA go to the workspace and skinny_tn_reduce_kernel adds them in a fixed order.
+// HBM-bound: algorithmic bytes = 2 M N.
+static constexpr int SP_WARPS = 16, SP_THREADS = SP_WARPS * 32, SP_ROWS = 16;
+static constexpr int SP_RED_BYTES = 2 * SP_WARPS * SP_ROWS * 8 * 4;
+
+template <int NB, int STAGES>   // NB = 16-column blocks per warp (N = 256 * NB)
+__global__ void __launch_bounds__(SP_THREADS, 1) lora_side_kernel(const __half* __restrict__ L, int64_t ldl, const __half* __restrict__ P, int64_t ldp,
+                                                                 __half* __restrict__ T, int64_t ldt, const __half* __restrict__ Rm, int64_t ldr,
+                                                                 float* __restrict__ partial, int64_t M, int rows_per_cta) {
+    constexpr int N = 256 * NB, ROW_BYTES = 2 * N, CHUNKS = N / 8;          // 16-byte chunks per row
+    constexpr int L_BYTES = SP_ROWS * ROW_BYTES, STAGE_BYTES = L_BYTES + SP_ROWS * 32;
+    extern __shared__ __align__(128) uint8_t sp_smem[];
+    const uint32_t sbase = smem_u32(sp_smem);
+    float* red = reinterpret_cast<float*>(sp_smem + STAGES * STAGE_BYTES);  // [2][16 warps][16 rows x 8]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int64_t m0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t m1 = (m0 + rows_per_cta < M) ? m0 + rows_per_cta : M;
+    const int nchunks = m1 > m0 ? (int)((m1 - m0 + SP_ROWS - 1) / SP_ROWS) : 0;
+
+    auto load_chunk = [&](int c, int stage) {
+        const int64_t mb = m0 + (int64_t)c * SP_ROWS;
+        const uint32_t sL = sbase + stage * STAGE_BYTES, sR = sL + L_BYTES;
+#pragma unroll
+        for (int i = 0; i < (SP_ROWS * CHUNKS) / SP_THREADS; ++i) {
+            const int idx = tid + i * SP_THREADS;
+            const int row = idx / CHUNKS, chunk = idx % CHUNKS;
+            const bool ok = mb + row < m1;
+            const __half* src = L + (ok ? (mb + row) * ldl + chunk * 8 : 0);
+            cp_async16(sL + row * ROW_BYTES + (((chunk & ~7) | ((chunk ^ row) & 7)) << 4), src, ok);
+        }
+        if (tid < SP_ROWS * 2) {
+            const int row = tid >> 1, chunk = tid & 1;
+            const bool ok = mb + row < m1;
+            const __half* src = Rm + (ok ? (mb + row) * ldr + chunk * 8 : 0);
+            cp_async16(sR + row * 32 + chunk * 16, src, ok);
+        }
+    };
+
+    // B fragments of the down projection (k = n, 8 output columns j): lane (g, t) holds P[g][c + 2t, 2t+1] and P[g][c + 8 + 2t, ...]
+    uint32_t pf[NB][2];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+        const __half* pr = P + (int64_t)g * ldp + (warp * NB + nb) * 16 + 2 * t;
+        pf[nb][0] = __ldg(reinterpret_cast<const uint32_t*>(pr));
+        pf[nb][1] = __ldg(reinterpret_cast<const uint32_t*>(pr + 8));
+    }
+    float accQ[NB][4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) accQ[nb][0] = accQ[nb][1] = accQ[nb][2] = accQ[nb][3] = 0.f;
+
+    for (int c = 0; c < STAGES - 1; ++c) {
+        if (c < nchunks) load_chunk(c, c);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+        __syncthreads();
+        if (c + STAGES - 1 < nchunks) load_chunk(c + STAGES - 1, (c + STAGES - 1) % STAGES);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const uint32_t sL = sbase + (c % STAGES) * STAGE_BYTES, sR = sL + L_BYTES;
+        uint32_t bf[2];     // token contraction B fragment: R tile rows m (k), columns j (n), transposed load
+        {
+            const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(bf[0]), "=r"(bf[1]) : "r"(sR + row * 32));
+        }
+        float accT[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            const int cb = (warp * NB + nb) * 2;        // first 16-byte chunk of this 16-column block
+            uint32_t af[4];
+            {   // rows = n, k = m: transposed 8x8 blocks of the [m][n] tile
+                const int row = (lane & 7) + ((lane >> 4) & 1) * 8;
+                const int chunk = cb + ((lane >> 3) & 1);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3])
+                             : "r"(sL + row * ROW_BYTES + (((chunk & ~7) | ((chunk ^ row) & 7)) << 4)));
+            }
+            mma_16816(accQ[nb], af[0], af[1], af[2], af[3], bf[0], bf[1]);
+            {   // rows = m, k = n: plain 8x8 blocks
+                const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int chunk = cb + (lane >> 4);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3])
+                             : "r"(sL + row * ROW_BYTES + (((chunk & ~7) | ((chunk ^ row) & 7)) << 4)));
+            }
+            mma_16816(accT, af[0], af[1], af[2], af[3], pf[nb][0], pf[nb][1]);
+        }
+        // per-warp partial T rows -> shared, summed by the first 128 threads: c0,c1 -> (row g, j = 2t, 2t+1); c2,c3 -> (row g + 8)
+        float* rbuf = red + (c & 1) * (SP_WARPS * SP_ROWS * 8);
+        *reinterpret_cast<float2*>(rbuf + warp * (SP_ROWS * 8) + g * 8 + 2 * t) = make_float2(accT[0], accT[1]);
+        *reinterpret_cast<float2*>(rbuf + warp * (SP_ROWS * 8) + (g + 8) * 8 + 2 * t) = make_float2(accT[2], accT[3]);
+        __syncthreads();
+        if (tid < 2 * SP_ROWS * 8) {
+            const int e = tid & (SP_ROWS * 8 - 1), row = e >> 3, j = e & 7;
+            const int64_t m = m0 + (int64_t)c * SP_ROWS + row;
+            if (m < m1) {
+                float sum = 0.f;
+                if (tid < SP_ROWS * 8) {
+#pragma unroll
+                    for (int w = 0; w < SP_WARPS; ++w) sum += rbuf[w * (SP_ROWS * 8) + e];
+                }
+                T[m * ldt + (tid < SP_ROWS * 8 ? j : 8 + j)] = __float2half_rn(sum);      // columns 8..15 are zero padding
+            }
+        }
+    }
+    // Q partials: c0,c1 -> (n = g, j = 2t, 2t+1) ; c2,c3 -> (n = g + 8)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+        const int n = (warp * NB + nb) * 16 + g;
+        *reinterpret_cast<float2*>(partial + ((int64_t)blockIdx.x * N + n) * 8 + 2 * t) = make_float2(accQ[nb][0], accQ[nb][1]);
+        *reinterpret_cast<float2*>(partial + ((int64_t)blockIdx.x * N + n + 8) * 8 + 2 * t) = make_float2(accQ[nb][2], accQ[nb][3]);
+    }
+}
+
+static bool lora_side_fused_ok(int N, int r) { return r == 8 && N % 256 == 0 && N / 256 >= 1 && N / 256 <= 12; }
+static int lora_side_ctas(int64_t M) {
+    const int64_t chunks = (M + SP_ROWS - 1) / SP_ROWS;
+    const int sms = device_sm_count();
+    return (int)(chunks < sms ? chunks : sms);
+}
+size_t lora_side_workspace(int64_t M, int N, int r) {
+    const size_t fallback = skinny_tn_workspace(M, N, r);
+    if (!lora_side_fused_ok(N, r)) return fallback;
+    const size_t fused = (size_t)lora_side_ctas(M) * N * 8 * sizeof(float);
+    return fused > fallback ? fused : fallback;
+}
+
+template <int NB, int STAGES>
+static int launch_lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __half* T, int64_t ldt, const __half* Rm, int64_t ldr,
+                            float* workspace, int64_t M, int ctas, int rows_per_cta, cudaStream_t s) {
+    constexpr int smem = STAGES * (SP_ROWS * 512 * NB + SP_ROWS * 32) + SP_RED_BYTES;
+    static_assert(smem <= 232448, "lora_side: stage ring does not fit in shared memory");
+    static bool attr = false;
+    if (!attr) {
+        GSL_CHECK_CUDA(cudaFuncSetAttribute(lora_side_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    lora_side_kernel<NB, STAGES><<<ctas, SP_THREADS, smem, s>>>(L, ldl, P16, ldp, T, ldt, Rm, ldr, workspace, M, rows_per_cta);
+    GSL_COUNT_LAUNCH(1);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __half* T, int64_t ldt, const __half* Rm, int64_t ldr,
+              float* out, int64_t ldo, int transpose_out, float scale, int accumulate, int64_t M, int N, int r,
+              float* workspace, size_t workspace_bytes, cudaStream_t s) {
+    GSL_REQUIRE(r == 8 || r == 16, "lora_side: rank must be 8 or 16 (got %d)", r);
+    GSL_REQUIRE(N % 16 == 0 && ldl % 8 == 0 && ldp % 8 == 0 && ldr % 8 == 0 && ldt % 8 == 0, "lora_side: N %% 16 and pitches %% 8 required");
+    GSL_REQUIRE(workspace_bytes >= lora_side_workspace(M, N, r), "lora_side: workspace too small");
+    if (!lora_side_fused_ok(N, r)) {        // rank 16 / odd widths: the two separate passes
+        int rc = lora_down(L, ldl, P16, ldp, T, ldt, M, N, r, s);
+        if (rc) return rc;
+        return skinny_tn(L, ldl, Rm, ldr, out, ldo, transpose_out, scale, accumulate, M, N, r, workspace, workspace_bytes, s);
+    }
+    const int ctas = lora_side_ctas(M);
+    int rows_per_cta = (int)((M + ctas - 1) / ctas);
+    rows_per_cta = (rows_per_cta + SP_ROWS - 1) / SP_ROWS * SP_ROWS;
+    int rc = -1;
+#define GSL_SP_CASE(NBV, ST) case NBV: rc = launch_lora_side<NBV, ST>(L, ldl, P16, ldp, T, ldt, Rm, ldr, workspace, M, ctas, rows_per_cta, s); break;
+    switch (N / 256) {
+        GSL_SP_CASE(1, 4) GSL_SP_CASE(2, 4) GSL_SP_CASE(3, 4) GSL_SP_CASE(4, 4) GSL_SP_CASE(5, 4) GSL_SP_CASE(6, 4)
+        GSL_SP_CASE(7, 3) GSL_SP_CASE(8, 3) GSL_SP_CASE(9, 2) GSL_SP_CASE(10, 2) GSL_SP_CASE(11, 2) GSL_SP_CASE(12, 2)
+    }
+#undef GSL_SP_CASE
+    if (rc) return rc;
+    skinny_tn_reduce_kernel<8><<<(N * 8 + 255) / 256, 256, 0, s>>>(workspace, ctas, N, scale, out, ldo, transpose_out, r, accumulate);
+    GSL_COUNT_LAUNCH(1);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ casts
 __global__ void cast_kernel(const float* __restrict__ src, int64_t lds, __half* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols,
                             float scale, int transpose) {

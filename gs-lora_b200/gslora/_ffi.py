@@ -53,6 +53,7 @@ def _declare(L):
         "gsl_layernorm_bwd": [P, c_int64, P, c_int64, P, P, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int, P],
         "gsl_lora_down": [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int, c_int, P],
         "gsl_skinny_tn": [P, c_int64, P, c_int64, P, c_int64, c_int, c_float, c_int, c_int64, c_int, c_int, P, c_size_t, P],
+        "gsl_lora_side": [P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int, c_float, c_int, c_int64, c_int, c_int, P, c_size_t, P],
         "gsl_attention_fwd": [P, c_int64, P, c_int64, P, c_int, c_int, c_int, c_float, P],
         "gsl_attention_bwd": [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, c_int, c_int, c_float, P],
         "gsl_cast_f32_to_f16": [P, c_int64, P, c_int64, c_int64, c_int64, c_float, c_int, P],
@@ -73,6 +74,8 @@ def _declare(L):
         fn.restype = c_int
     L.gsl_skinny_tn_workspace.argtypes = [c_int64, c_int, c_int]
     L.gsl_skinny_tn_workspace.restype = c_size_t
+    L.gsl_lora_side_workspace.argtypes = [c_int64, c_int, c_int]
+    L.gsl_lora_side_workspace.restype = c_size_t
     L.gsl_engine_workspace_bytes.argtypes = [ctypes.POINTER(GslConfig)]
     L.gsl_engine_workspace_bytes.restype = c_size_t
     L.gsl_engine_destroy.argtypes = [P]
@@ -86,7 +89,7 @@ def _declare(L):
 
 
 EXPORTS = ["gsl_last_error", "gsl_version", "gsl_launch_count", "gsl_set_gemm_cta_group", "gsl_gemm_f16", "gsl_patchify_f16", "gsl_layernorm_fwd",
-           "gsl_layernorm_bwd", "gsl_lora_down", "gsl_skinny_tn_workspace", "gsl_skinny_tn", "gsl_attention_fwd", "gsl_attention_bwd",
+           "gsl_layernorm_bwd", "gsl_lora_down", "gsl_skinny_tn_workspace", "gsl_skinny_tn", "gsl_lora_side_workspace", "gsl_lora_side", "gsl_attention_fwd", "gsl_attention_bwd",
            "gsl_cast_f32_to_f16", "gsl_grouplasso_adamw_step", "gsl_tensor_norms", "gsl_engine_workspace_bytes", "gsl_engine_create",
            "gsl_engine_destroy", "gsl_engine_bind_params", "gsl_engine_refresh_frozen", "gsl_engine_refresh_lora", "gsl_engine_forward",
            "gsl_engine_backward", "gsl_engine_slot_ptr", "gsl_engine_lora_offset", "gsl_engine_lora_numel", "gsl_loss_sums",

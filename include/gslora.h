@@ -67,6 +67,13 @@ int gsl_lora_down(const void* X16, int64_t ldx, const void* A16, int64_t lda, vo
 size_t gsl_skinny_tn_workspace(int64_t M, int N, int r);
 int gsl_skinny_tn(const void* L16, int64_t ldl, const void* R16, int64_t ldr, float* out, int64_t ldo, int transpose_out, float scale,
                   int accumulate, int64_t M, int N, int r, float* workspace, size_t workspace_bytes, void* stream);
+/* Fused side pass over a wide activation L16 [M, N] (one HBM read):  T16[M, 0:16] = L * P16[16, N]^T  (gsl_lora_down)  AND
+ * out[n, j] (+)= scale * sum_m L[m, n] * R16[m, j]  (gsl_skinny_tn).  Backward of loralib Linear:
+ * (T2 = G A2^T, dA2 = s U2^T G) and (U1 = dH B1, dB1 = s dH^T T1).  Workspace: gsl_lora_side_workspace bytes. */
+size_t gsl_lora_side_workspace(int64_t M, int N, int r);
+int gsl_lora_side(const void* L16, int64_t ldl, const void* P16, int64_t ldp, void* T16, int64_t ldt, const void* R16, int64_t ldr,
+                  float* out, int64_t ldo, int transpose_out, float scale, int accumulate, int64_t M, int N, int r,
+                  float* workspace, size_t workspace_bytes, void* stream);
 /* Attention.forward (vit_face.py:358-379) on qkv fp16 [B*N, ld] (q | k | v blocks of heads*64 columns). */
 int gsl_attention_fwd(const void* qkv16, int64_t ld, void* out16, int64_t ldo, float* lse, int B, int N, int heads, float scale, void* stream);
 int gsl_attention_bwd(const void* qkv16, int64_t ld, const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,

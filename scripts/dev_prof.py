@@ -20,18 +20,21 @@ def timeit(fn, name, flops=None, bytes_=None):
     extra = (f" {flops/ms/1e9:.0f} TFLOP/s" if flops else "") + (f" {bytes_/ms/1e6:.0f} GB/s" if bytes_ else "")
     print(f"{name}: {ms:.3f} ms{extra}", flush=True)
 if "gelu" in what:
-    A = (torch.randn(M, D + 16, device=dev) * 0.5).half(); W = (torch.randn(H, D + 16, device=dev) * 0.05).half(); bias = torch.randn(H, device=dev)
-    o0 = torch.empty(M, H, device=dev, dtype=torch.half); o1 = torch.empty(M, H + 16, device=dev, dtype=torch.half)
-    timeit(lambda: F.gemm_f16(A, W, epi=F.EPI_GELU, bias=bias, out0=o0, out1=o1, N=H), "fc1 GELU gemm", flops=2.0 * M * H * (D + 16))
-    dy = (torch.randn(M, D + 16, device=dev) * 0.5).half(); WT = (torch.randn(H, D + 16, device=dev) * 0.05).half()
-    timeit(lambda: F.gemm_f16(dy, WT, epi=F.EPI_GELU_BWD, out0=o1, aux=o0, N=H), "dH GELU' gemm", flops=2.0 * M * H * (D + 16))
+    A = (torch.randn(M, D, device=dev) * 0.5).half(); W = (torch.randn(H, D, device=dev) * 0.05).half(); bias = torch.randn(H, device=dev)
+    o0 = torch.empty(M, H, device=dev, dtype=torch.half); o1 = torch.empty(M, H, device=dev, dtype=torch.half)
+    timeit(lambda: F.gemm_f16(A, W, epi=F.EPI_GELU, bias=bias, out0=o0, out1=o1), "fc1 GELU gemm", flops=2.0 * M * H * D)
+    timeit(lambda: F.gemm_f16(A, W, epi=F.EPI_GELU, bias=bias, out0=o0, out1=o1, drop_p=0.1, drop_seed=1234), "fc1 GELU gemm, dropout 0.1", flops=2.0 * M * H * D)
+    dy = (torch.randn(M, D, device=dev) * 0.5).half(); WT = (torch.randn(H, D, device=dev) * 0.05).half()
+    timeit(lambda: F.gemm_f16(dy, WT, epi=F.EPI_GELU_BWD, out0=o1, aux=o0), "dH gemm (x saved gelu')", flops=2.0 * M * H * D)
     del A, W, o0, o1, dy, WT
 if "res" in what:
-    G = (torch.randn(M, H + 16, device=dev) * 0.5).half(); W2 = (torch.randn(D, H + 16, device=dev) * 0.05).half(); bias = torch.randn(D, device=dev)
+    G = (torch.randn(M, H, device=dev) * 0.5).half(); W2 = (torch.randn(D, H, device=dev) * 0.05).half(); bias = torch.randn(D, device=dev)
     x = torch.randn(M, D, device=dev); y = torch.empty(M, D, device=dev)
-    timeit(lambda: F.gemm_f16(G, W2, epi=F.EPI_RES_F32, bias=bias, out0=y, aux=x), "fc2 RES gemm", flops=2.0 * M * D * (H + 16))
-    timeit(lambda: F.gemm_f16(G, W2, epi=F.EPI_F32, out0=y), "dXn F32 gemm (K=2064)", flops=2.0 * M * D * (H + 16))
-    del G, W2, x, y
+    timeit(lambda: F.gemm_f16(G, W2, epi=F.EPI_RES_F32, bias=bias, out0=y, aux=x), "fc2 RES gemm", flops=2.0 * M * D * H)
+    timeit(lambda: F.gemm_f16(G, W2, epi=F.EPI_RES_F32, bias=bias, out0=y, aux=x, drop_p=0.1, drop_seed=99), "fc2 RES gemm, dropout 0.1", flops=2.0 * M * D * H)
+    y16 = torch.empty(M, D, device=dev, dtype=torch.half)
+    timeit(lambda: F.gemm_f16(G, W2, epi=F.EPI_F16, out0=y16), "dXn F16 gemm (K=2048)", flops=2.0 * M * D * H)
+    del G, W2, x, y, y16
 if "f16" in what:
     xn = (torch.randn(M, D, device=dev) * 0.5).half(); Wq = (torch.randn(3 * D, D, device=dev) * 0.05).half()
     qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.half)
@@ -45,8 +48,13 @@ if "attn" in what:
     timeit(lambda: F.check(F.lib().gsl_attention_bwd(F.ptr(qkv), 3 * D, F.ptr(out), D, F.ptr(dout), D, F.ptr(lse), F.ptr(dqkv), 3 * D, B, N, heads, sc, F.cur_stream())), "attention bwd", flops=14.0 * B * heads * N * N * 64)
     del qkv, out, dout, dqkv
 if "skinny" in what:
-    L = torch.randn(M, H + 16, device=dev).half(); R = torch.randn(M, 16, device=dev).half()
-    nb = F.lib().gsl_skinny_tn_workspace(M, H, 8); ws = torch.empty(nb // 4 + 16, device=dev); out = torch.zeros(H, 8, device=dev)
-    timeit(lambda: F.check(F.lib().gsl_skinny_tn(F.ptr(L), H + 16, F.ptr(R), 16, F.ptr(out), 8, 0, 1.0, 0, M, H, 8, F.ptr(ws), nb, F.cur_stream())), "skinny_tn N=2048", bytes_=M * H * 2.0)
-    A16 = torch.randn(16, H, device=dev).half()
-    timeit(lambda: F.check(F.lib().gsl_lora_down(F.ptr(L), H + 16, F.ptr(A16), H, F.ptr(L[:, H:]), H + 16, M, H, 8, F.cur_stream())), "lora_down K=2048", bytes_=M * H * 2.0)
+    L = torch.randn(M, H, device=dev).half(); R = torch.randn(M, 16, device=dev).half()
+    nb = F.lib().gsl_lora_side_workspace(M, H, 8); ws = torch.empty(nb // 4 + 16, device=dev); out = torch.zeros(H, 8, device=dev)
+    timeit(lambda: F.check(F.lib().gsl_skinny_tn(F.ptr(L), H, F.ptr(R), 16, F.ptr(out), 8, 0, 1.0, 0, M, H, 8, F.ptr(ws), nb, F.cur_stream())), "skinny_tn N=2048", bytes_=M * H * 2.0)
+    A16 = torch.randn(16, H, device=dev).half(); T = torch.empty(M, 16, device=dev, dtype=torch.half)
+    timeit(lambda: F.check(F.lib().gsl_lora_down(F.ptr(L), H, F.ptr(A16), H, F.ptr(T), 16, M, H, 8, F.cur_stream())), "lora_down K=2048", bytes_=M * H * 2.0)
+    timeit(lambda: F.check(F.lib().gsl_lora_side(F.ptr(L), H, F.ptr(A16), H, F.ptr(T), 16, F.ptr(R), 16, F.ptr(out), 8, 0, 1.0, 0, M, H, 8, F.ptr(ws), nb, F.cur_stream())), "lora_side N=2048 (both, one pass)", bytes_=M * H * 2.0)
+    X = torch.randn(M, D, device=dev).half(); A5 = torch.randn(16, D, device=dev).half()
+    timeit(lambda: F.check(F.lib().gsl_lora_down(F.ptr(X), D, F.ptr(A5), D, F.ptr(T), 16, M, D, 8, F.cur_stream())), "lora_down K=512", bytes_=M * D * 2.0)
+    outd = torch.zeros(D, 8, device=dev)
+    timeit(lambda: F.check(F.lib().gsl_skinny_tn(F.ptr(X), D, F.ptr(R), 16, F.ptr(outd), 8, 0, 1.0, 0, M, D, 8, F.ptr(ws), nb, F.cur_stream())), "skinny_tn N=512", bytes_=M * D * 2.0)

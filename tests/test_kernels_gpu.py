@@ -112,6 +112,29 @@ def test_skinny_tn(F, M, N, r, tr):
         assert rel(got, want * (1 + acc)) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,r,tr", [(197 * 9, 2048, 8, 1), (197 * 9, 2048, 8, 0), (5000, 3072, 8, 0), (37, 256, 8, 1), (1, 512, 8, 0),
+                                      (300, 1024, 16, 1), (200, 320, 8, 0)])
+def test_lora_side_fused_pass(F, M, N, r, tr):
+    """One pass over L gives T = L P^T (fp16) and out = scale * L^T R; rank 16 / N % 256 != 0 take the two-kernel fallback."""
+    torch.manual_seed(4)
+    L = torch.randn(M, N, device="cuda").half()
+    P = torch.zeros(16, N, device="cuda", dtype=torch.half); P[:r] = (torch.randn(r, N, device="cuda") * 0.05).half()
+    R = torch.zeros(M, 16, device="cuda", dtype=torch.half); R[:, :r] = torch.randn(M, r, device="cuda").half()
+    T = torch.full((M, 16), 7.0, device="cuda", dtype=torch.half)
+    nb = F.lib().gsl_lora_side_workspace(M, N, r)
+    ws = torch.empty(nb // 4 + 16, device="cuda")
+    out = torch.full((r, N) if tr else (N, r), 0.5, device="cuda")
+    want_t = L.float() @ P[:r].float().t()
+    want_q = 0.25 * (L.float().t() @ R[:, :r].float())
+    for acc in (0, 1):
+        F.check(F.lib().gsl_lora_side(F.ptr(L), N, F.ptr(P), N, F.ptr(T), 16, F.ptr(R), 16, F.ptr(out), N if tr else r, tr, 0.25, acc,
+                                      M, N, r, F.ptr(ws), nb, F.cur_stream()))
+        got = out.t() if tr else out
+        assert rel(got, want_q * (1 + acc)) < 1e-5
+        assert (T[:, :r].float() - want_t).abs().max() <= 2e-3 * want_t.abs().max() + 1e-4
+        assert (T[:, r:] == 0).all()
+
+
 @pytest.mark.parametrize("B,N,heads,scale", [(3, 197, 8, 512 ** -0.5), (2, 26, 2, 128 ** -0.5), (1, 197, 12, 0.125), (5, 50, 4, 0.2)])
 def test_attention_fwd_bwd(F, B, N, heads, scale):
     torch.manual_seed(3)
