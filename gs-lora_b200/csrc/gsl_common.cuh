@@ -89,7 +89,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > GSL_SPIN_LIMIT) {
+#ifdef GSL_DEBUG_BARRIERS      // (a printf call in this loop makes the compiler spill live registers around every wait)
             printf("gslora: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+#endif
             __trap();
         }
     }
@@ -105,7 +107,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) break;
         if (++spins > GSL_SPIN_LIMIT) {
+#ifdef GSL_DEBUG_BARRIERS
             printf("gslora: cluster mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+#endif
             __trap();
         }
     }

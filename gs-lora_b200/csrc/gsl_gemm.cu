@@ -152,7 +152,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(tfull_bar(i), 1);             // one tcgen05.commit
-                mbar_init(tempty_bar(i), CG * EPI_WARPS * 32);     // every epilogue thread of the pair
+                mbar_init(tempty_bar(i), CG * EPI_WARPS);          // one elected lane per epilogue warp of the pair
             }
             for (int i = 0; i < 2; ++i) mbar_init(aux_bar(i), 1);
             fence_mbar_init();
@@ -255,7 +255,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tcgen05_fence_after();
             if ((int)grp >= nstripes) {              // nothing to do for this group in a narrow tile: just release the accumulator
                 tcgen05_fence_before();
-                if (CG == 2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+                __syncwarp();
+                if (lane == 0) { if (CG == 2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
             }
 
             for (int sidx = grp; sidx < nstripes; sidx += EPI_GROUPS) {
@@ -263,9 +264,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float2 v[CW / 2];                                            // this thread's CW accumulator columns, as pairs
                 tmem_ld_cols<CW>(tmem_base + ((quarter * 32u) << 16) + acc * BN + sidx * STRIPE + half * CW, v);
                 if (sidx + EPI_GROUPS >= nstripes) {
-                    // this thread's last TMEM read of the accumulator: hand the buffer back to the MMA warp
+                    // this warp's last TMEM read of the accumulator (tcgen05.wait::ld is warp-wide): hand the buffer back to the MMA warp
                     tcgen05_fence_before();
-                    if (CG == 2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+                    __syncwarp();
+                    if (lane == 0) { if (CG == 2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
                 }
                 if (!tile_live) continue;
                 const uint32_t e0 = (uint32_t)(m_base + (int)row) * (uint32_t)p.N + (uint32_t)n0;     // dropout counter of column n0
