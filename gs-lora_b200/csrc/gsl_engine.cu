@@ -10,6 +10,7 @@
 #include "gsl_engine.h"
 #include "gsl_common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace gsl {
