@@ -49,6 +49,12 @@ except Exception:
         return (str(datetime.datetime.now())[:-10]).replace(" ", "-").replace(":", "-")
 
 
+def _wandb_log(d):
+    """The reference logs unconditionally (its driver has called wandb.init); stay silent when no run is active."""
+    if getattr(wandb, "run", None) is not None or not hasattr(wandb, "run"):
+        wandb.log(d)
+
+
 def _unwrap(model):
     return model.module if isinstance(model, (torch.nn.DataParallel, torch.nn.parallel.DistributedDataParallel)) else model
 
@@ -120,11 +126,67 @@ def get_structure_loss(model: torch.nn.Module, imagenet=False):
     return _StructureLossFn.apply(m, *m.lora_parameters())
 
 
-def unlearn_step(model, inputs_remain, labels_remain, inputs_forget, labels_forget, *, beta: float, alpha: float, BND: float,
-                 optimizer=None, hparams: Optional[dict] = None, use_prototype: bool = False, prototype_dict=None,
-                 prototype_weight_forget: float = 0.0, prototype_weight_remain: float = 0.0, BND_pro: float = 0.0,
-                 dropout_seed: Optional[int] = None) -> Dict[str, float]:
-    """One step of engine_cl.train_one_epoch (engine_cl.py:59-125), fused.  Returns the scalars the reference logs."""
+class StepResult:
+    """Scalars of one unlearning step (what the reference reads with >= 8 `.item()` calls, engine_cl.py:68-121).  The device-to-host
+    copy is queued on the step's stream into pinned memory; nothing blocks until a value is read (`result["total"]`, `.wait()`), so
+    the host can queue the next step while this one runs."""
+
+    _KEYS = ("loss_remain", "ce_forget", "loss_forget", "structure", "top1_remain", "top1_forget", "proto_forget", "proto_remain", "total")
+
+    def __init__(self, pinned, event, n_vals, consts):
+        self._pinned, self._event, self._n, self._c = pinned, event, n_vals, consts
+        self._vals = None
+
+    def wait(self) -> Dict[str, float]:
+        if self._vals is None:
+            self._event.synchronize()
+            host = self._pinned[:self._n].tolist()
+            c = self._c
+            s_ce_r, n_r, s_ce_f, n_f, hit_r, hit_f, structure = host[:7]
+            loss_remain = s_ce_r / max(n_r, 1.0)
+            ce_forget = s_ce_f / max(n_f, 1.0)
+            loss_forget = max(c["BND"] - ce_forget, 0.0)
+            pf_v, pr_v = (host[7], host[8]) if self._n > 7 else (0.0, 0.0)
+            proto_total = c["pwf"] * max(c["BND_pro"] - pf_v, 0.0) + c["pwr"] * pr_v if c["use_prototype"] else 0.0
+            self._vals = dict(loss_remain=loss_remain, ce_forget=ce_forget, loss_forget=loss_forget, structure=structure,
+                              top1_remain=100.0 * hit_r / max(n_r, 1.0), top1_forget=100.0 * hit_f / max(n_f, 1.0),
+                              proto_forget=pf_v, proto_remain=pr_v,
+                              total=c["beta"] * loss_forget + loss_remain + c["alpha"] * structure + proto_total)
+            self._pinned = None
+        return self._vals
+
+    def __getitem__(self, k):
+        return self.wait()[k]
+
+    def keys(self):
+        return self._KEYS
+
+
+class _PinnedRing:
+    """Small ring of pinned host buffers for the per-step scalar read-back (cudaHostAlloc per step would serialise the host)."""
+
+    def __init__(self, n=8, width=16):
+        self.bufs = [torch.empty(width, dtype=torch.float32).pin_memory() for _ in range(n)]
+        self.pending = [None] * n
+        self.i = 0
+
+    def take(self):
+        i = self.i
+        self.i = (i + 1) % len(self.bufs)
+        if self.pending[i] is not None:
+            self.pending[i].wait()          # an unread result still owns this buffer: materialise it first
+        return i, self.bufs[i]
+
+
+_RING = None
+
+
+def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, labels_forget, *, beta: float, alpha: float, BND: float,
+                       optimizer=None, hparams: Optional[dict] = None, use_prototype: bool = False, prototype_dict=None,
+                       prototype_weight_forget: float = 0.0, prototype_weight_remain: float = 0.0, BND_pro: float = 0.0,
+                       dropout_seed: Optional[int] = None) -> StepResult:
+    """One step of engine_cl.train_one_epoch (engine_cl.py:59-125), fused; returns a StepResult whose scalars arrive asynchronously."""
+    global _RING
     m = _unwrap(model)
     Br, Bf = int(inputs_remain.shape[0]), int(inputs_forget.shape[0])
     B = Br + Bf
@@ -162,21 +224,26 @@ def unlearn_step(model, inputs_remain, labels_remain, inputs_forget, labels_forg
     hp = hparams if hparams is not None else _adamw_hparams(optimizer, m.lora_parameters())
     eng.optimizer_step(lr=hp["lr"], wd=hp["wd"], alpha=alpha, betas=hp.get("betas", (0.9, 0.999)), eps=hp.get("eps", 1e-8))
     m.mark_lora_updated_by_engine()
-    # one D2H copy for everything the reference reads with .item()
+    # one D2H copy (queued, pinned) for everything the reference reads with .item()
     pieces = [sums[:6], eng.group_norms.sum().view(1)]
     if proto_vals is not None:
         pieces.append(proto_vals)
-    host = torch.cat(pieces).cpu().tolist()
-    s_ce_r, n_r, s_ce_f, n_f, hit_r, hit_f, structure = host[:7]
-    loss_remain = s_ce_r / max(n_r, 1.0)
-    ce_forget = s_ce_f / max(n_f, 1.0)
-    loss_forget = max(BND - ce_forget, 0.0)
-    pf_v, pr_v = (host[7], host[8]) if proto_vals is not None else (0.0, 0.0)
-    proto_total = prototype_weight_forget * max(BND_pro - pf_v, 0.0) + prototype_weight_remain * pr_v if use_prototype else 0.0
-    return dict(loss_remain=loss_remain, ce_forget=ce_forget, loss_forget=loss_forget, structure=structure,
-                top1_remain=100.0 * hit_r / max(n_r, 1.0), top1_forget=100.0 * hit_f / max(n_f, 1.0),
-                proto_forget=pf_v, proto_remain=pr_v,
-                total=beta * loss_forget + loss_remain + alpha * structure + proto_total)
+    packed = torch.cat(pieces)
+    if _RING is None:
+        _RING = _PinnedRing()
+    slot_i, pinned = _RING.take()
+    pinned[:packed.numel()].copy_(packed, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    res = StepResult(pinned, ev, packed.numel(), dict(beta=beta, alpha=alpha, BND=BND, BND_pro=BND_pro, pwf=prototype_weight_forget,
+                                                      pwr=prototype_weight_remain, use_prototype=use_prototype))
+    _RING.pending[slot_i] = res
+    return res
+
+
+def unlearn_step(model, inputs_remain, labels_remain, inputs_forget, labels_forget, **kw) -> Dict[str, float]:
+    """Synchronous form of unlearn_step_async: returns the dict of scalars the reference logs."""
+    return unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, labels_forget, **kw).wait()
 
 
 def sync_optimizer_state(model, optimizer):
@@ -235,14 +302,10 @@ def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criteri
     inputs_forget, labels_forget = prefetcher.next()
     DISP_FREQ, VER_FREQ = 5, 100
     rank0 = _dist() is None or _dist().get_rank() == 0
-    for inputs_remain, labels_remain in iter(dataloader_remain):
-        inputs_remain = inputs_remain.to(device)
-        labels_remain = labels_remain.to(device)
-        out = unlearn_step(model, inputs_remain, labels_remain, inputs_forget, labels_forget, beta=beta, alpha=alpha, BND=BND,
-                           optimizer=optimizer, use_prototype=use_prototype, prototype_dict=prototype_dict,
-                           prototype_weight_forget=prototype_weight_forget, prototype_weight_remain=prototype_weight_remain,
-                           BND_pro=cfg.get("BND_pro", 0.0) if use_prototype else 0.0)
-        nr, nf = inputs_remain.size(0), inputs_forget.size(0)
+    pending = None      # (StepResult, n_remain, n_forget) of the step whose scalars have not been folded into the meters yet
+
+    def absorb(p):
+        out, nr, nf = p[0].wait(), p[1], p[2]
         losses_remain.update(out["loss_remain"], nr)
         top1_remain.update(out["top1_remain"], nr)
         losses_forget.update(beta * out["loss_forget"], nf)
@@ -252,9 +315,25 @@ def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criteri
         losses_prototype_remain.update(out["proto_remain"] * prototype_weight_remain, nr)
         losses_total.update(out["total"], nr)
 
+    for inputs_remain, labels_remain in iter(dataloader_remain):
+        inputs_remain = inputs_remain.to(device)
+        labels_remain = labels_remain.to(device)
+        res = unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, labels_forget, beta=beta, alpha=alpha, BND=BND,
+                                 optimizer=optimizer, use_prototype=use_prototype, prototype_dict=prototype_dict,
+                                 prototype_weight_forget=prototype_weight_forget, prototype_weight_remain=prototype_weight_remain,
+                                 BND_pro=cfg.get("BND_pro", 0.0) if use_prototype else 0.0)
+        # the scalars of step i are folded into the meters after step i+1 has been queued (the host never waits for the GPU in the
+        # steady state); at the steps where the reference prints or evaluates, the meters are brought fully up to date first
+        if pending is not None:
+            absorb(pending)
+        pending = (res, inputs_remain.size(0), inputs_forget.size(0))
+        if (((batch + 1) % DISP_FREQ == 0) or ((batch + 1) % VER_FREQ == 0)) and batch != 0:
+            absorb(pending)
+            pending = None
+
         if ((batch + 1) % DISP_FREQ == 0) and batch != 0:
             if rank0:
-                wandb.log({
+                _wandb_log({
                     "epoch_loss_forget-{}".format(task_i): losses_forget.avg, "epoch_loss_remain-{}".format(task_i): losses_remain.avg,
                     "epoch_acc_forget-{}".format(task_i): top1_forget.avg, "epoch_acc_remain-{}".format(task_i): top1_remain.avg,
                     "epoch_loss_total-{}".format(task_i): losses_total.avg, "epoch_loss_structure-{}".format(task_i): losses_structure.avg,
@@ -282,6 +361,8 @@ def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criteri
         if inputs_forget is None:
             prefetcher = _Prefetcher(dataloader_forget, device)
             inputs_forget, labels_forget = prefetcher.next()
+    if pending is not None:
+        absorb(pending)
     sync_optimizer_state(model, optimizer)
     return (batch, highest_H_mean, losses_forget, losses_remain, top1_forget, top1_remain, losses_total, losses_structure,
             losses_prototype_forget, losses_prototype_remain)
@@ -341,5 +422,5 @@ def eval_data(model, dataloader, device, mode: str, batch: int = 0):
             total += labels.size(0)
     accuracy = 100 * int(hits.item()) / max(total, 1)
     print("Test {} Accuracy:{:2f}%".format(mode, accuracy))
-    wandb.log({"Test {} Accuracy".format(mode): accuracy})
+    _wandb_log({"Test {} Accuracy".format(mode): accuracy})
     return accuracy

@@ -32,3 +32,23 @@ for e in evs:
     agg.setdefault(e.name[:60], [0, 0.0]); agg[e.name[:60]][0] += 1; agg[e.name[:60]][1] += d
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:16]:
     print(f"  {v[1] / 1e3 / steps:7.3f} ms  n={v[0] / steps:5.1f}  {k}")
+
+# sync vs pipelined read-back, same process, alternating blocks of 20 steps
+def run(fn, n=20):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    prev = None
+    for _ in range(n):
+        r = fn()
+        if prev is not None and hasattr(prev, "wait"):
+            prev.wait()
+        prev = r
+    if hasattr(prev, "wait"):
+        prev.wait()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+for rep in range(3):
+    a = run(lambda: engine_cl.unlearn_step(model, *t, **kw))
+    b = run(lambda: engine_cl.unlearn_step_async(model, *t, **kw))
+    print(f"sync {a:.2f} ms/step   pipelined read-back {b:.2f} ms/step")

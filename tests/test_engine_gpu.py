@@ -122,6 +122,48 @@ def test_fused_step_matches_reference_golden(golden_dir, name):
         assert abs(float(a) - b) < 2e-3 * abs(b)
 
 
+def test_train_one_epoch_pipelined_readback_equals_sequential_steps(golden_dir):
+    """engine_cl.train_one_epoch (engine_cl.py:12-244 contract) folds step i's scalars into the meters after step i+1 is queued; the
+    meters, the batch counter and the LoRA parameters must equal those of synchronous engine_cl.unlearn_step calls on the same batches."""
+    import engine_cl
+    from engine_cl import AverageMeter
+    g, cfg, sd = load_case(golden_dir, "tiny6_b4")
+    hp = g["hp"]
+    gen = torch.Generator().manual_seed(11)
+    S = cfg.image_size
+    remain = [(torch.rand(4, 3, S, S, generator=gen), torch.randint(0, cfg.num_class, (4,), generator=gen)) for _ in range(7)]
+    forget = [(torch.rand(3, 3, S, S, generator=gen), torch.randint(0, cfg.num_class, (3,), generator=gen)) for _ in range(3)]
+
+    def fresh():
+        m = build_model(cfg, sd)
+        m.dropout_seed = lambda: 0
+        opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=hp["lr"], weight_decay=hp["wd"])
+        return m, opt
+
+    # sequential reference: synchronous steps, forget loader cycled like the prefetcher does
+    m1, opt1 = fresh()
+    tot1, n1 = 0.0, 0
+    for i, (xr, yr) in enumerate(remain):
+        xf, yf = forget[i % len(forget)]
+        out = engine_cl.unlearn_step(m1, xr.cuda(), yr.cuda(), xf.cuda(), yf.cuda(), beta=hp["beta"], alpha=hp["alpha"], BND=hp["BND"], optimizer=opt1)
+        tot1 += out["total"] * xr.shape[0]
+        n1 += xr.shape[0]
+    # the epoch function
+    m2, opt2 = fresh()
+    meters = [AverageMeter() for _ in range(8)]
+    lf, lr_, lt, ls, tf, tr, lpf, lpr = meters
+    ret = engine_cl.train_one_epoch(m2, forget, remain, torch.device("cuda"), torch.nn.CrossEntropyLoss(), opt2, 0, lf, lr_, lt, ls, tf, tr,
+                                    hp["beta"], hp["alpha"], hp["BND"], 0, None, None, 0.0, 0.0, {"WORK_PATH": "/tmp", "BACKBONE_NAME": "VIT"}, 0,
+                                    False, None, 0.0, 0.0, lpf, lpr)
+    assert ret[0] == len(remain)
+    # display resets the meters every 5 steps (batch 4): the returned total meter holds steps 5..6 only
+    names = O.lora_param_list(cfg)
+    for n in names:
+        assert torch.equal(m1.get_parameter(n).data, m2.get_parameter(n).data), n
+    lt_ret = ret[6]
+    assert lt_ret.count == sum(x.shape[0] for x, _ in remain[5:])
+
+
 def test_p8s8_batch_vs_oracle_fp32_on_gpu():
     """Config-2 shape at bs 32+32: engine vs the oracle executed in torch FP32 on the same GPU (TF32 off)."""
     import engine_cl
