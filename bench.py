@@ -187,7 +187,7 @@ def run_gslora(args):
                        "loss": out["total"]},
             "clocks": sampler.summary(),
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(ms_e2e, 3), "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 7 * 4},
+                    "d2h_bytes_per_step": 9 * 4},
             "gpu_launches": int(launches),
             "roofline": roof,
         }

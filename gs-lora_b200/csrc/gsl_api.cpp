@@ -130,8 +130,15 @@ void* gsl_engine_slot_ptr(void* handle, int slot, int what) {
 }
 int64_t gsl_engine_lora_offset(void* handle, int block, int which) { return ((Engine*)handle)->lora_offset(block, which); }
 int64_t gsl_engine_lora_numel(void* handle) { Engine* e = (Engine*)handle; return e->cfg.depth * e->lora_block_elems(); }
-int gsl_loss_sums(const float* ce, const int32_t* correct, int n_remain, int B, float* sums, void* stream) {
-    return loss_sums(ce, correct, n_remain, B, sums, ST(stream));
+int gsl_loss_sums(const float* ce, const int32_t* correct, const float* kl, int n_remain, int B, float* sums, void* stream) {
+    return loss_sums(ce, correct, kl, n_remain, B, sums, ST(stream));
+}
+int gsl_prototype_kl_fwd(const float* emb, const int64_t* labels, const float* proto, int B, int D, float* kl, void* stream) {
+    return prototype_kl_fwd(emb, labels, proto, B, D, kl, ST(stream));
+}
+int gsl_prototype_kl_grad(const float* emb, const int64_t* labels, const float* proto, const float* sums, int n_remain_local, int B, int D,
+                          float w_f, float w_r, float BND_pro, float* demb, void* stream) {
+    return prototype_kl_grad(emb, labels, proto, sums, n_remain_local, B, D, w_f, w_r, BND_pro, demb, ST(stream));
 }
 int gsl_unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C, float beta, float BND,
                         float* dlogits, void* stream) {

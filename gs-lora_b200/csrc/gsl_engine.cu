@@ -538,27 +538,29 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
 }
 
 // ------------------------------------------------------------------------------------------------ step-loss helpers
-__global__ void loss_sums_kernel(const float* __restrict__ ce, const int* __restrict__ correct, int n_remain, int B, float* __restrict__ sums) {
-    __shared__ float red[6][32];
-    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+__global__ void loss_sums_kernel(const float* __restrict__ ce, const int* __restrict__ correct, const float* __restrict__ kl, int n_remain, int B,
+                                 float* __restrict__ sums) {
+    __shared__ float red[8][32];
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        if (b < n_remain) { v[0] += ce[b]; v[1] += 1.f; v[4] += correct ? (float)correct[b] : 0.f; }
-        else { v[2] += ce[b]; v[3] += 1.f; v[5] += correct ? (float)correct[b] : 0.f; }
+        if (b < n_remain) { v[0] += ce[b]; v[1] += 1.f; v[4] += correct ? (float)correct[b] : 0.f; v[6] += kl ? kl[b] : 0.f; }
+        else { v[2] += ce[b]; v[3] += 1.f; v[5] += correct ? (float)correct[b] : 0.f; v[7] += kl ? kl[b] : 0.f; }
     }
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 8; ++k) {
         v[k] = warp_sum(v[k]);
         if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
     }
     __syncthreads();
-    if (threadIdx.x < 6) {
+    if (threadIdx.x < 8) {
         float t = 0.f;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[threadIdx.x][i];
         sums[threadIdx.x] = t;
     }
 }
 
-int loss_sums(const float* ce, const int* correct, int n_remain, int B, float* sums, cudaStream_t s) {
-    loss_sums_kernel<<<1, 1024, 0, s>>>(ce, correct, n_remain, B, sums);
+// sums[0..7] = sum CE remain, n remain, sum CE forget, n forget, hits remain, hits forget, sum KL remain, sum KL forget (kl may be null)
+int loss_sums(const float* ce, const int* correct, const float* kl, int n_remain, int B, float* sums, cudaStream_t s) {
+    loss_sums_kernel<<<1, 1024, 0, s>>>(ce, correct, kl, n_remain, B, sums);
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;

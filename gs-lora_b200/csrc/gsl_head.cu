@@ -198,4 +198,70 @@ int head_bwd(const HeadBwdArgs& a, cudaStream_t s) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ GS-LoRA++ prototype term
+// engine_cl.get_prototype_loss (engine_cl.py:571-603, distance "kl"):
+//   F.kl_div(log_softmax(emb), log_softmax(proto[label]), reduction="batchmean", log_target=True) = mean_b sum_d pt_bd (lt_bd - lo_bd)
+// used as  w_f * relu(BND_pro - KL_forget) + w_r * KL_remain  (engine_cl.py:97-101).  One warp per sample; the per-sample KL goes to
+// loss_sums (-> sums[6], sums[7]); the gradient kernel recomputes the two softmaxes and scales them with the gate read from the
+// (all-reduced) sums:  d/d emb_b = coef_b (softmax(emb_b) - softmax(proto_b)),  coef = w_r / n_r  or  -w_f [KL_f < BND_pro] / n_f.
+__device__ __forceinline__ void proto_row_stats(const float* __restrict__ e, const float* __restrict__ p, int D, int lane, float& me, float& se,
+                                                float& mp, float& sp) {
+    me = -INFINITY; mp = -INFINITY;
+    for (int d = lane; d < D; d += 32) { me = fmaxf(me, e[d]); mp = fmaxf(mp, p[d]); }
+    me = warp_max(me); mp = warp_max(mp);
+    se = 0.f; sp = 0.f;
+    for (int d = lane; d < D; d += 32) { se += __expf(e[d] - me); sp += __expf(p[d] - mp); }
+    se = warp_sum(se); sp = warp_sum(sp);
+}
+__global__ void prototype_kl_fwd_kernel(const float* __restrict__ emb, const int64_t* __restrict__ labels, const float* __restrict__ proto, int B, int D,
+                                        float* __restrict__ kl) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const float* e = emb + (int64_t)b * D;
+    const float* p = proto + labels[b] * D;
+    float me, se, mp, sp;
+    proto_row_stats(e, p, D, lane, me, se, mp, sp);
+    const float le = me + __logf(se), lp = mp + __logf(sp);     // log-sum-exp of both rows
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float lt = p[d] - lp, lo = e[d] - le;
+        acc += __expf(lt) * (lt - lo);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) kl[b] = acc;
+}
+__global__ void prototype_kl_grad_kernel(const float* __restrict__ emb, const int64_t* __restrict__ labels, const float* __restrict__ proto,
+                                         const float* __restrict__ sums, int n_remain_local, int B, int D, float w_f, float w_r, float BND_pro,
+                                         float* __restrict__ demb) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float coef;
+    if (b < n_remain_local) coef = sums[1] > 0.f ? w_r / sums[1] : 0.f;
+    else {
+        const float mean_f = sums[3] > 0.f ? sums[7] / sums[3] : 0.f;
+        coef = (sums[3] > 0.f && mean_f < BND_pro) ? -w_f / sums[3] : 0.f;      // relu'(BND_pro - KL_f) = [KL_f < BND_pro]
+    }
+    const float* e = emb + (int64_t)b * D;
+    const float* p = proto + labels[b] * D;
+    float me, se, mp, sp;
+    proto_row_stats(e, p, D, lane, me, se, mp, sp);
+    const float ie = 1.0f / se, ip = 1.0f / sp;
+    for (int d = lane; d < D; d += 32) demb[(int64_t)b * D + d] = coef * (__expf(e[d] - me) * ie - __expf(p[d] - mp) * ip);
+}
+int prototype_kl_fwd(const float* emb, const int64_t* labels, const float* proto, int B, int D, float* kl, cudaStream_t s) {
+    const int warps = 4;
+    prototype_kl_fwd_kernel<<<(B + warps - 1) / warps, warps * 32, 0, s>>>(emb, labels, proto, B, D, kl);
+    GSL_COUNT_LAUNCH(1);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int prototype_kl_grad(const float* emb, const int64_t* labels, const float* proto, const float* sums, int n_remain_local, int B, int D, float w_f,
+                      float w_r, float BND_pro, float* demb, cudaStream_t s) {
+    const int warps = 4;
+    prototype_kl_grad_kernel<<<(B + warps - 1) / warps, warps * 32, 0, s>>>(emb, labels, proto, sums, n_remain_local, B, D, w_f, w_r, BND_pro, demb);
+    GSL_COUNT_LAUNCH(1);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace gsl

@@ -112,7 +112,11 @@ struct HeadBwdArgs {
 int head_bwd(const HeadBwdArgs& a, cudaStream_t s);
 // dlogits[b, :] = coef * (softmax(logits[b]) - onehot) / B_total ; coef read from device (gate applied by caller)
 int ce_grad(const float* logits, const int64_t* labels, const float* coef_dev, float scale, float* dlogits, int B, int C, cudaStream_t s);
-int loss_sums(const float* ce, const int* correct, int n_remain, int B, float* sums, cudaStream_t s);
+int loss_sums(const float* ce, const int* correct, const float* kl, int n_remain, int B, float* sums, cudaStream_t s);
+// GS-LoRA++ prototype term (engine_cl.py:571-603, 97-101): per-sample KL(log_softmax(emb) || log_softmax(proto[label])) and its gated gradient
+int prototype_kl_fwd(const float* emb, const int64_t* labels, const float* proto, int B, int D, float* kl, cudaStream_t s);
+int prototype_kl_grad(const float* emb, const int64_t* labels, const float* proto, const float* sums, int n_remain_local, int B, int D, float w_f,
+                      float w_r, float BND_pro, float* demb, cudaStream_t s);
 int unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C, float beta, float BND,
                     float* dlogits, cudaStream_t s);
 

@@ -84,8 +84,9 @@ def _prototype_tensor(prototype_dict, num_class, dim, device):
 
 
 def get_prototype_loss(output, labels, prototype_dict, distance="kl"):
-    """engine_cl.get_prototype_loss (engine_cl.py:571-603) without the per-sample `.item()` loop: the prototypes are
-    gathered on device.  (The KL itself is a [B, dim] torch expression; a fused kernel is SURVEY 8f-1.)"""
+    """engine_cl.get_prototype_loss (engine_cl.py:571-603) without the per-sample `.item()` loop: the prototypes are gathered on
+    device.  Differentiable torch expression for callers that run their own autograd loop; the fused step (unlearn_step) uses the
+    gsl_prototype_kl_fwd / _grad kernels instead."""
     if torch.is_tensor(prototype_dict):
         pt = prototype_dict[labels.long()].to(output.device)
     else:
@@ -142,11 +143,11 @@ class StepResult:
             self._event.synchronize()
             host = self._pinned[:self._n].tolist()
             c = self._c
-            s_ce_r, n_r, s_ce_f, n_f, hit_r, hit_f, structure = host[:7]
+            s_ce_r, n_r, s_ce_f, n_f, hit_r, hit_f, s_kl_r, s_kl_f, structure = host[:9]
             loss_remain = s_ce_r / max(n_r, 1.0)
             ce_forget = s_ce_f / max(n_f, 1.0)
             loss_forget = max(c["BND"] - ce_forget, 0.0)
-            pf_v, pr_v = (host[7], host[8]) if self._n > 7 else (0.0, 0.0)
+            pf_v, pr_v = s_kl_f / max(n_f, 1.0), s_kl_r / max(n_r, 1.0)
             proto_total = c["pwf"] * max(c["BND_pro"] - pf_v, 0.0) + c["pwr"] * pr_v if c["use_prototype"] else 0.0
             self._vals = dict(loss_remain=loss_remain, ce_forget=ce_forget, loss_forget=loss_forget, structure=structure,
                               top1_remain=100.0 * hit_r / max(n_r, 1.0), top1_forget=100.0 * hit_f / max(n_f, 1.0),
@@ -199,25 +200,17 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
         raise RuntimeError("unlearn_step needs model.train() (un-merged LoRA)")
     slot = m._take_slot()
     eng.forward(img, lab, slot, use_lora=True, dropout_seed=m.dropout_seed() if dropout_seed is None else dropout_seed)
-    sums = eng.loss_sums(slot, Br, B)
+    table = kl = None
+    if use_prototype:                                           # GS-LoRA++ (engine_cl.py:97-101): per-sample KL to the class prototype, on device
+        table = _prototype_tensor(prototype_dict, eng.spec.num_class, eng.spec.dim, dev).float().contiguous()
+        kl = eng.prototype_kl(slot, lab, table, B)
+    sums = eng.loss_sums(slot, Br, B, kl)
     dist = _dist()
-    world = 1
     if dist is not None:
-        world = dist.get_world_size()
-        dist.all_reduce(sums)                                   # global CE sums / counts / hits (<= 8 floats)
+        dist.all_reduce(sums)                                   # global CE / KL sums, counts, hits (8 floats)
     dlogits = torch.empty(B, eng.spec.num_class, dtype=torch.float32, device=dev)
     eng.unlearn_ce_grad(slot, lab, Br, B, beta, BND, dlogits)
-    demb = None
-    proto_vals = None
-    if use_prototype:
-        table = _prototype_tensor(prototype_dict, eng.spec.num_class, eng.spec.dim, dev)
-        emb = eng.slot_tensor(slot, F.SLOT_EMB, B).detach().clone().requires_grad_(True)
-        pr = get_prototype_loss(emb[:Br], lab[:Br], table)
-        pf = get_prototype_loss(emb[Br:], lab[Br:], table)
-        proto = prototype_weight_forget * F_t.relu(BND_pro - pf) + prototype_weight_remain * pr      # engine_cl.py:97-101
-        proto.backward()
-        demb = (emb.grad / world).contiguous()
-        proto_vals = torch.stack([pf.detach(), pr.detach()])
+    demb = eng.prototype_kl_grad(slot, lab, table, Br, B, prototype_weight_forget, prototype_weight_remain, BND_pro) if use_prototype else None
     eng.backward(slot, dlogits, demb, accumulate=False)
     if dist is not None:
         dist.all_reduce(eng.grad_flat)                          # the one flat LoRA-gradient allreduce (0.98 MB for ViT-P8S8 r=8)
@@ -225,10 +218,7 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
     eng.optimizer_step(lr=hp["lr"], wd=hp["wd"], alpha=alpha, betas=hp.get("betas", (0.9, 0.999)), eps=hp.get("eps", 1e-8))
     m.mark_lora_updated_by_engine()
     # one D2H copy (queued, pinned) for everything the reference reads with .item()
-    pieces = [sums[:6], eng.group_norms.sum().view(1)]
-    if proto_vals is not None:
-        pieces.append(proto_vals)
-    packed = torch.cat(pieces)
+    packed = torch.cat([sums, eng.group_norms.sum().view(1)])
     if _RING is None:
         _RING = _PinnedRing()
     slot_i, pinned = _RING.take()

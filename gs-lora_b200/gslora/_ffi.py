@@ -65,7 +65,9 @@ def _declare(L):
         "gsl_engine_refresh_lora": [P, P],
         "gsl_engine_forward": [P, c_int, P, P, c_int, c_int, ctypes.c_uint64, P],
         "gsl_engine_backward": [P, c_int, P, P, c_int, P],
-        "gsl_loss_sums": [P, P, c_int, c_int, P, P],
+        "gsl_loss_sums": [P, P, P, c_int, c_int, P, P],
+        "gsl_prototype_kl_fwd": [P, P, P, c_int, c_int, P, P],
+        "gsl_prototype_kl_grad": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_float, P, P],
         "gsl_unlearn_ce_grad": [P, P, P, c_int, c_int, c_int, c_float, c_float, P, P],
     }
     for name, args in sigs.items():
@@ -93,7 +95,7 @@ EXPORTS = ["gsl_last_error", "gsl_version", "gsl_launch_count", "gsl_set_gemm_ct
            "gsl_cast_f32_to_f16", "gsl_grouplasso_adamw_step", "gsl_tensor_norms", "gsl_engine_workspace_bytes", "gsl_engine_create",
            "gsl_engine_destroy", "gsl_engine_bind_params", "gsl_engine_refresh_frozen", "gsl_engine_refresh_lora", "gsl_engine_forward",
            "gsl_engine_backward", "gsl_engine_slot_ptr", "gsl_engine_lora_offset", "gsl_engine_lora_numel", "gsl_loss_sums",
-           "gsl_unlearn_ce_grad"]
+           "gsl_unlearn_ce_grad", "gsl_prototype_kl_fwd", "gsl_prototype_kl_grad"]
 
 
 def check(rc, what=""):

@@ -164,11 +164,26 @@ class VitEngine:
                 "gsl_engine_backward")
 
     # ------------------------------------------------------------------ losses / optimizer (device side, no host sync)
-    def loss_sums(self, slot: int, n_remain: int, B: int) -> torch.Tensor:
+    def loss_sums(self, slot: int, n_remain: int, B: int, kl: Optional[torch.Tensor] = None) -> torch.Tensor:
         ce = self.slot_tensor(slot, F.SLOT_CE, B)
         correct = self.slot_tensor(slot, F.SLOT_CORRECT, B)
-        F.check(F.lib().gsl_loss_sums(F.ptr(ce), F.ptr(correct), n_remain, B, F.ptr(self.sums), F.cur_stream()), "gsl_loss_sums")
+        F.check(F.lib().gsl_loss_sums(F.ptr(ce), F.ptr(correct), F.ptr(kl), n_remain, B, F.ptr(self.sums), F.cur_stream()), "gsl_loss_sums")
         return self.sums
+
+    def prototype_kl(self, slot: int, labels: torch.Tensor, proto: torch.Tensor, B: int) -> torch.Tensor:
+        """Per-sample KL(log_softmax(emb) || log_softmax(proto[label])) of engine_cl.get_prototype_loss (engine_cl.py:571-603)."""
+        emb = self.slot_tensor(slot, F.SLOT_EMB, B)
+        kl = torch.empty(B, dtype=torch.float32, device=self.device)
+        F.check(F.lib().gsl_prototype_kl_fwd(F.ptr(emb), F.ptr(labels), F.ptr(proto), B, self.spec.dim, F.ptr(kl), F.cur_stream()), "gsl_prototype_kl_fwd")
+        return kl
+
+    def prototype_kl_grad(self, slot: int, labels: torch.Tensor, proto: torch.Tensor, n_remain: int, B: int, w_f: float, w_r: float,
+                          BND_pro: float) -> torch.Tensor:
+        emb = self.slot_tensor(slot, F.SLOT_EMB, B)
+        demb = torch.empty(B, self.spec.dim, dtype=torch.float32, device=self.device)
+        F.check(F.lib().gsl_prototype_kl_grad(F.ptr(emb), F.ptr(labels), F.ptr(proto), F.ptr(self.sums), n_remain, B, self.spec.dim, float(w_f),
+                                              float(w_r), float(BND_pro), F.ptr(demb), F.cur_stream()), "gsl_prototype_kl_grad")
+        return demb
 
     def unlearn_ce_grad(self, slot: int, labels: torch.Tensor, n_remain: int, B: int, beta: float, BND: float, out: torch.Tensor):
         logits = self.slot_tensor(slot, F.SLOT_LOGITS, B)

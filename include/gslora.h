@@ -143,9 +143,16 @@ int64_t gsl_engine_lora_offset(void* handle, int block, int which);   /* which: 
 int64_t gsl_engine_lora_numel(void* handle);
 
 /* Step losses of engine_cl.train_one_epoch (engine_cl.py:65-80) on device, no host sync:
- *   sums[0..5] = { sum CE_remain, n_remain, sum CE_forget, n_forget, hits_remain, hits_forget } over ce/correct[0:B],
+ *   sums[0..7] = { sum CE_remain, n_remain, sum CE_forget, n_forget, hits_remain, hits_forget, sum KL_remain, sum KL_forget } over ce/correct/kl[0:B]
+ *   (kl may be null -> zeros),
  *   samples [0, n_remain) are the remain batch, [n_remain, B) the forget batch.  (Allreduce `sums` for data parallel.) */
-int gsl_loss_sums(const float* ce, const int32_t* correct, int n_remain, int B, float* sums, void* stream);
+int gsl_loss_sums(const float* ce, const int32_t* correct, const float* kl, int n_remain, int B, float* sums, void* stream);
+/* GS-LoRA++ prototype term, engine_cl.get_prototype_loss (engine_cl.py:571-603, distance "kl") and its use at engine_cl.py:97-101:
+ *   kl[b] = sum_d softmax(proto[label_b])_d * (log_softmax(proto[label_b])_d - log_softmax(emb_b)_d)      (batchmean is taken by gsl_loss_sums:
+ *   sums[6] / sums[1] = KL_remain, sums[7] / sums[3] = KL_forget);  gsl_prototype_kl_grad writes d[w_f relu(BND_pro - KL_f) + w_r KL_r] / d emb. */
+int gsl_prototype_kl_fwd(const float* emb, const int64_t* labels, const float* proto, int B, int D, float* kl, void* stream);
+int gsl_prototype_kl_grad(const float* emb, const int64_t* labels, const float* proto, const float* sums, int n_remain_local, int B, int D,
+                          float w_f, float w_r, float BND_pro, float* demb, void* stream);
 /* dlogits[b] = w_b * (softmax(logits[b]) - onehot(label_b)) with w_b = 1/n_remain (remain) or
  *   -beta * [CE_forget_mean < BND] / n_forget (forget), counts and means taken from `sums` (device). */
 int gsl_unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C,

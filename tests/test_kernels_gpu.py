@@ -177,3 +177,29 @@ def test_grouplasso_adamw_matches_torch(F):
     tn = torch.empty(G, device="cuda")
     F.check(F.lib().gsl_tensor_norms(F.ptr(p), F.ptr(offs), G, 1, F.ptr(tn), F.cur_stream()))
     assert rel(tn, p.view(G, -1).abs().sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("Br,Bf,D,C,bnd", [(5, 3, 512, 100, 50.0), (4, 4, 128, 10, 1e-4), (7, 0, 768, 100, 18.0)])
+def test_prototype_kl_matches_reference_expression(F, Br, Bf, D, C, bnd):
+    """gsl_prototype_kl_fwd / _grad vs engine_cl.get_prototype_loss' expression (engine_cl.py:571-603) and its use at :97-101."""
+    import torch.nn.functional as Fn
+    torch.manual_seed(5)
+    B = Br + Bf
+    emb = torch.randn(B, D, device="cuda"); proto = torch.randn(C, D, device="cuda") * 2; lab = torch.randint(0, C, (B,), device="cuda")
+    w_f, w_r = 0.7, 0.3
+    e = emb.clone().requires_grad_(True)
+    def kl(x, y):
+        return Fn.kl_div(Fn.log_softmax(x, 1), Fn.log_softmax(proto[y], 1), reduction="batchmean", log_target=True)
+    kr = kl(e[:Br], lab[:Br])
+    kf = kl(e[Br:], lab[Br:]) if Bf else torch.zeros((), device="cuda")
+    (w_f * torch.relu(bnd - kf) + w_r * kr).backward() if Bf else (w_r * kr).backward()
+    klv = torch.empty(B, device="cuda")
+    F.check(F.lib().gsl_prototype_kl_fwd(F.ptr(emb), F.ptr(lab), F.ptr(proto), B, D, F.ptr(klv), F.cur_stream()))
+    ce = torch.zeros(B, device="cuda"); sums = torch.zeros(8, device="cuda")
+    F.check(F.lib().gsl_loss_sums(F.ptr(ce), None, F.ptr(klv), Br, B, F.ptr(sums), F.cur_stream()))
+    assert abs(float(sums[6] / max(Br, 1)) - float(kr)) < 1e-4 * max(1.0, abs(float(kr)))
+    if Bf:
+        assert abs(float(sums[7] / Bf) - float(kf)) < 1e-4 * max(1.0, abs(float(kf)))
+    demb = torch.empty(B, D, device="cuda")
+    F.check(F.lib().gsl_prototype_kl_grad(F.ptr(emb), F.ptr(lab), F.ptr(proto), F.ptr(sums), Br, B, D, w_f, w_r, bnd, F.ptr(demb), F.cur_stream()))
+    assert (demb - e.grad).abs().max() < 1e-5 * max(1.0, float(e.grad.abs().max()))
