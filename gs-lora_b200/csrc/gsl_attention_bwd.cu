@@ -19,9 +19,10 @@
 //     K0 / V0 stream in during the kt = 1 blocks; Q0 / dO0 are double-buffered across pairs; the small tile-1 buffers are
 //     refilled at the pair boundary, one block ahead of their first use;
 //   * delta = rowsum(dO * O) and LSE of the NEXT pair are prepared by a dedicated warp straight from global memory.
-// Warp roles: warps 0-7 workers (two warpgroups, raised to 224 registers with setmaxnreg: few fat threads with 16-wide independent
-// chains hide the MUFU / TMEM latencies far better than many thin ones), warp 8 TMA producer, warp 9 MMA issuer (+ TMEM allocation),
-// warps 10-11 delta (that warpgroup drops to 56 registers).
+// Warp roles: warps 0-7 workers (two warpgroups, raised to 176 registers with setmaxnreg: few fat threads with 16-wide independent
+// chains hide the MUFU / TMEM latencies far better than many thin ones), warps 8-11 gradient writers (read dK / dV / dQ out of TMEM,
+// stage them and issue the TMA stores - off the workers' critical path, where they cost 5.8 of 15.5 us per pair), warp 12 TMA producer,
+// warp 13 MMA issuer (+ TMEM allocation), warps 14-15 delta.
 #include "gsl_common.cuh"
 #include <cuda.h>
 #include <cstdlib>
@@ -35,8 +36,10 @@ int make_tmap_qkv(CUtensorMap* map, const void* ptr, int64_t ld, int B, int N, i
 static constexpr int AB_WORKER_WARPS = 8;
 static constexpr int AB_WORKERS = AB_WORKER_WARPS * 32;
 static constexpr int AB_DELTA_THREADS = 64;
-static constexpr int AB_THREADS = AB_WORKERS + 128;       // + one warpgroup: producer, MMA issuer, two delta warps
-static constexpr uint32_t AB_W_PROD = AB_WORKER_WARPS, AB_W_MMA = AB_WORKER_WARPS + 1, AB_W_DELTA = AB_WORKER_WARPS + 2;
+static constexpr int AB_STORE_WARPS = 4;                  // one per TMEM lane quarter
+static constexpr int AB_STORERS = AB_STORE_WARPS * 32;
+static constexpr int AB_THREADS = AB_WORKERS + AB_STORERS + 128;       // + one warpgroup: producer, MMA issuer, two delta warps
+static constexpr uint32_t AB_W_STORE = AB_WORKER_WARPS, AB_W_PROD = AB_W_STORE + AB_STORE_WARPS, AB_W_MMA = AB_W_PROD + 1, AB_W_DELTA = AB_W_PROD + 2;
 static constexpr int AB_MAX_TOKENS = 208;
 
 // shared memory map (bytes from the 1024-aligned base)
@@ -118,7 +121,7 @@ __device__ __forceinline__ void ab_math16(const uint32_t (&sv)[16], const uint32
     pp0 = make_uint4(po[0], po[1], po[2], po[3]); pp1 = make_uint4(po[4], po[5], po[6], po[7]);
     ds0 = make_uint4(so[0], so[1], so[2], so[3]); ds1 = make_uint4(so[4], so[5], so[6], so[7]);
 }
-__device__ __forceinline__ void ab_bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(AB_WORKERS) : "memory"); }
+__device__ __forceinline__ void ab_bar_storers() { asm volatile("bar.sync 2, %0;" ::"n"(AB_STORERS) : "memory"); }
 // 32 fp32 accumulator values -> 32 fp16 (four 16-byte chunks), scaled
 struct AbRow32 { uint4 c0, c1, c2, c3; };
 __device__ __forceinline__ AbRow32 ab_pack32(const uint32_t (&v)[32], float scale) {
@@ -130,21 +133,21 @@ __device__ __forceinline__ AbRow32 ab_pack32(const uint32_t (&v)[32], float scal
     r.c3 = make_uint4(pk(24), pk(26), pk(28), pk(30));
     return r;
 }
-// Write-out of one [128 rows x 64] gradient tile (dQ / dK / dV): every worker thread drops its 32 values of row `rl` (columns
-// cg * 32 ..) as fp16 into the swizzled staging tile, one elected thread issues a single TMA store (rows >= N are clipped by the
-// tensor map).  (Per-thread 32-byte global stores at a 6 KB row pitch cost ~0.7 ms per launch; this costs two named barriers.)
-__device__ __forceinline__ void ab_stage_store(const void* tmap, uint32_t stage, const AbRow32& v, bool write, int rl, int cg,
-                                               bool elected, int col, int row0, int b) {
+// Write-out of one [128 rows x 64] gradient tile (dQ / dK / dV) by the four writer warps: every thread drops the 64 values of row `rl`
+// as fp16 into the swizzled staging tile, one elected thread issues a single TMA store (rows >= N are clipped by the tensor map).
+// (Per-thread 32-byte global stores at a 6 KB row pitch cost ~0.7 ms per launch.)
+__device__ __forceinline__ void ab_stage_store(const void* tmap, uint32_t stage, const AbRow32& lo, const AbRow32& hi, bool write, int rl, bool elected,
+                                               int col, int row0, int b) {
     if (elected) tma_store_wait_read<0>();      // the previous store has finished reading the staging tile
-    ab_bar_workers();
+    ab_bar_storers();
     if (write) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + sw128_off(rl, cg * 4 + 0)), "r"(v.c0.x), "r"(v.c0.y), "r"(v.c0.z), "r"(v.c0.w) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + sw128_off(rl, cg * 4 + 1)), "r"(v.c1.x), "r"(v.c1.y), "r"(v.c1.z), "r"(v.c1.w) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + sw128_off(rl, cg * 4 + 2)), "r"(v.c2.x), "r"(v.c2.y), "r"(v.c2.z), "r"(v.c2.w) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + sw128_off(rl, cg * 4 + 3)), "r"(v.c3.x), "r"(v.c3.y), "r"(v.c3.z), "r"(v.c3.w) : "memory");
+        auto st = [&](int chunk, const uint4& v) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + sw128_off(rl, chunk)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        };
+        st(0, lo.c0); st(1, lo.c1); st(2, lo.c2); st(3, lo.c3); st(4, hi.c0); st(5, hi.c1); st(6, hi.c2); st(7, hi.c3);
     }
     fence_proxy_async_smem();
-    ab_bar_workers();
+    ab_bar_storers();
     if (elected) {
         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                      ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(stage), "r"(col), "r"(row0), "r"(b) : "memory");
@@ -179,8 +182,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV0, const __grid
             for (uint32_t i = 0; i < B_COUNT; ++i) mbar_init(bar(i), 1);
             // worker-side barriers count WARPS: one elected lane arrives after __syncwarp() (512 per-thread arrivals on one mbarrier
             // serialise in the shared-memory atomics unit and cost microseconds per block)
-            mbar_init(bar(B_SDP_FREE), AB_WORKER_WARPS); mbar_init(bar(B_PDS_READY), AB_WORKER_WARPS); mbar_init(bar(B_DKV_FREE), AB_WORKER_WARPS);
-            mbar_init(bar(B_DQ_FREE), AB_WORKER_WARPS);
+            mbar_init(bar(B_SDP_FREE), AB_WORKER_WARPS); mbar_init(bar(B_PDS_READY), AB_WORKER_WARPS); mbar_init(bar(B_DKV_FREE), AB_STORE_WARPS);
+            mbar_init(bar(B_DQ_FREE), AB_STORE_WARPS);
             for (uint32_t p = 0; p < 2; ++p) { mbar_init(bar(B_STATS_READY + p), AB_DELTA_THREADS / 32); mbar_init(bar(B_STATS_FREE + p), AB_WORKER_WARPS); }
             fence_mbar_init();
         }
@@ -193,8 +196,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV0, const __grid
     const uint32_t tmem_base = *tmem_ptr_smem;
     constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_DK = 384, T_DV = 448;
 
-    if (warp >= AB_WORKER_WARPS) {
+    // 512 threads x 128 registers at launch; producer / MMA / delta drop to 56, the writers to 96, the workers take the 13312 freed
+    if (warp >= AB_W_PROD) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else if (warp >= AB_W_STORE) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     }
     if (warp == AB_W_PROD) {
         // ===================================================== TMA producer
@@ -295,17 +301,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV0, const __grid
         if (pv_valid) issue_back();
     } else if (warp < AB_WORKER_WARPS) {
         // ===================================================== workers: thread = (query row, 64-key half of the block)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
         const uint32_t quarter = warp & 3;                          // TMEM lane quarter this warp may access
         const uint32_t cg = warp >> 2;                              // 0..1: which 64-key block of the [128 x 128] tile
         const int rl = quarter * 32 + lane;                         // row inside a 128-row tile
         const float sl2 = scale * 1.4426950408889634f;
         const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
-        const bool elected = threadIdx.x == 0;                      // issues the TMA stores of the gradient tiles
         int it = 0;
         uint32_t n = 0;
         for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
-            const int b = w / heads, h = w % heads;
             const uint32_t p = it & 1;
             const float* st_lse = s_stat + p * 512;
             const float* st_del = st_lse + 256;
@@ -361,56 +365,57 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV0, const __grid
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(B_PDS_READY));
 
-                // dK / dV of a finished key tile are read out one block late (kt = 0: after the first kt = 1 block's elementwise stage),
-                // or right away for the last key tile of the pair
-                const bool read_kt0 = nt == 2 && blk == 2, read_last = blk == nblk - 1;
-                for (int pass = 0; pass < 2; ++pass) {
-                    if (!(pass == 0 ? read_kt0 : read_last)) continue;
-                    const int rkt = pass == 0 ? 0 : nt - 1;
-                    const uint32_t m = (uint32_t)(it * nt + rkt);
-                    const bool rows_live = (rkt * 128 + (int)quarter * 32) < N;
-                    AbRow32 kr = {}, vr = {};
-                    mbar_wait(bar(B_DKV_FULL), m & 1);
-                    tcgen05_fence_after();
-                    if (rows_live) {
-                        uint32_t t32[32];
-                        tmem_ld_32x32(tlane + T_DK + cg * 32, t32);
-                        tmem_ld_wait();
-                        kr = ab_pack32(t32, scale);
-                        tmem_ld_32x32(tlane + T_DV + cg * 32, t32);
-                        tmem_ld_wait();
-                        vr = ab_pack32(t32, 1.0f);
-                    }
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(B_DKV_FREE));
-                    if (!(dbg & 16)) {
-                        ab_stage_store(&tmDQKV, sb + AB_STAGE, kr, rows_live, rl, cg, elected, D + h * 64, rkt * 128, b);
-                        ab_stage_store(&tmDQKV, sb + AB_STAGE, vr, rows_live, rl, cg, elected, 2 * D + h * 64, rkt * 128, b);
-                    }
-                }
             }
-            // dQ of both query tiles
-            mbar_wait(bar(B_DQ_FULL), it & 1);
-            tcgen05_fence_after();
-            {
-                AbRow32 q0 = {}, q1 = {};
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_STATS_FREE + p));      // this pair's LSE / delta are no longer needed
+        }
+    } else if (warp < AB_W_PROD) {
+        // ===================================================== gradient writers: thread = one row of a [128 x 64] tile
+        const uint32_t quarter = warp & 3;
+        const int rl = quarter * 32 + lane;
+        const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
+        const bool elected = warp == AB_W_STORE && lane == 0;
+        const uint32_t stage = sb + AB_STAGE;
+        auto read64 = [&](uint32_t tcol, float sc, AbRow32& lo, AbRow32& hi) {
+            uint32_t t32[32];
+            tmem_ld_32x32(tlane + tcol, t32);
+            tmem_ld_wait();
+            lo = ab_pack32(t32, sc);
+            tmem_ld_32x32(tlane + tcol + 32, t32);
+            tmem_ld_wait();
+            hi = ab_pack32(t32, sc);
+        };
+        int it = 0;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+            const int b = w / heads, h = w % heads;
+            for (int kt = 0; kt < nt; ++kt) {
+                const uint32_t m = (uint32_t)(it * nt + kt);
+                const bool rows_live = (kt * 128 + (int)quarter * 32) < N;
+                AbRow32 lo = {}, hi = {};
+                mbar_wait(bar(B_DKV_FULL), m & 1);
+                tcgen05_fence_after();
+                if (rows_live) read64(T_DK, scale, lo, hi);
+                if (!(dbg & 16)) ab_stage_store(&tmDQKV, stage, lo, hi, rows_live, rl, elected, D + h * 64, kt * 128, b);
+                if (rows_live) read64(T_DV, 1.0f, lo, hi);
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(B_DKV_FREE));       // dK / dV accumulators may be overwritten by the next key tile
+                if (!(dbg & 16)) ab_stage_store(&tmDQKV, stage, lo, hi, rows_live, rl, elected, 2 * D + h * 64, kt * 128, b);
+            }
+            {   // dQ of both query tiles
                 const bool live0 = (int)quarter * 32 < N, live1 = nt == 2 && (128 + (int)quarter * 32) < N;
-                {
-                    uint32_t t32[32];
-                    if (live0) { tmem_ld_32x32(tlane + T_DQ + cg * 32, t32); tmem_ld_wait(); q0 = ab_pack32(t32, scale); }
-                    if (live1) { tmem_ld_32x32(tlane + T_DQ + 64 + cg * 32, t32); tmem_ld_wait(); q1 = ab_pack32(t32, scale); }
+                AbRow32 lo = {}, hi = {};
+                mbar_wait(bar(B_DQ_FULL), it & 1);
+                tcgen05_fence_after();
+                if (live0) read64(T_DQ, scale, lo, hi);
+                if (nt == 2) {
+                    if (!(dbg & 16)) ab_stage_store(&tmDQKV, stage, lo, hi, live0, rl, elected, h * 64, 0, b);
+                    if (live1) read64(T_DQ + 64, scale, lo, hi);
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(bar(B_DQ_FREE));
-                    mbar_arrive(bar(B_STATS_FREE + p));     // this pair's LSE / delta are no longer needed
-                }
-                if (!(dbg & 16)) {
-                    ab_stage_store(&tmDQKV, sb + AB_STAGE, q0, live0, rl, cg, elected, h * 64, 0, b);
-                    if (nt == 2) ab_stage_store(&tmDQKV, sb + AB_STAGE, q1, live1, rl, cg, elected, h * 64, 128, b);
-                }
+                if (lane == 0) mbar_arrive(bar(B_DQ_FREE));
+                if (!(dbg & 16)) ab_stage_store(&tmDQKV, stage, lo, hi, nt == 2 ? live1 : live0, rl, elected, h * 64, nt == 2 ? 128 : 0, b);
             }
         }
         if (elected) tma_store_wait_all();

@@ -11,7 +11,7 @@ from oracle import vit_oracle as O
 
 pytestmark = pytest.mark.gpu
 # north_star tolerance: 1e-3 relative.  Metric: ||x - ref||_2 / ||ref||_2 (SURVEY section 7 "Hard parts").
-# Measured on B200 at the config-2 shape against the FP32 reference (scripts/dev_parity.py, weight seeds 1337 / 1 / 2 / 3 / 4):
+# Measured on B200 at the config-2 shape against the FP32 reference (tests/dev_parity.py, weight seeds 1337 / 1 / 2 / 3 / 4):
 #   logits                         5.2e-4  5.1e-4  5.5e-4  4.9e-4  4.5e-4     (well inside 1e-3 for every seed)
 #   all LoRA gradients concatenated 1.02e-3 1.38e-3 1.29e-3 7.1e-4  1.01e-3   (batch-size independent: 9.4e-4 .. 1.02e-3 for bs 8 .. 256)
 #   worst single tensor            1.6e-3  2.1e-3  2.4e-3  1.3e-3  2.0e-3
