@@ -9,10 +9,11 @@
 //   O_j = P_j V           tcgen05.mma  M=128, N=64, K=npad; V is consumed straight from its TMA slab as an MN-major B operand
 //                         -> TMEM O (its own 64 columns, so S buffers are recycled as soon as the workers have read them)
 //   epilogue              scale by 1 / (sum_half0 + sum_half1), fp16 O tile staged in shared memory, one TMA store (rows >= N clipped)
-// Software pipeline: the workers run  softmax(j), epilogue(j-1), softmax(j+1), ...  while the MMA issuer runs
+// Software pipeline: the workers run  softmax(j), softmax(j+1), ...; the writers trail them with the epilogues; the MMA issuer runs
 // S(j+1) (as soon as S[(j+1) & 1] has been read) and P V of item j (as soon as P_j is written): the tensor core works on the
 // neighbouring items while the MUFU-bound softmax of item j runs, and TMEM loads are double-buffered inside the sweeps.
-// Warp roles: warps 0-7 workers (setmaxnreg 224), warp 8 TMA producer, warp 9 MMA issuer (+ TMEM allocation), warps 10-11 idle.
+// Warp roles: warps 0-7 softmax workers (setmaxnreg 176), warps 8-11 output writers (O out of TMEM, 1/sum, staging, TMA store, LSE - off
+// the workers' critical path), warp 12 TMA producer, warp 13 MMA issuer (+ TMEM allocation), warps 14-15 idle.
 #include "gsl_common.cuh"
 #include <cuda.h>
 #include <cstdlib>
@@ -24,29 +25,33 @@ int make_tmap_qkv(CUtensorMap* map, const void* ptr, int64_t ld, int B, int N, i
 
 static constexpr int AF_WORKER_WARPS = 8;
 static constexpr int AF_WORKERS = AF_WORKER_WARPS * 32;
-static constexpr int AF_THREADS = AF_WORKERS + 128;
-static constexpr uint32_t AF_W_PROD = AF_WORKER_WARPS, AF_W_MMA = AF_WORKER_WARPS + 1;
+static constexpr int AF_WRITER_WARPS = 4;
+static constexpr int AF_WRITERS = AF_WRITER_WARPS * 32;
+static constexpr int AF_THREADS = AF_WORKERS + AF_WRITERS + 128;
+static constexpr uint32_t AF_W_WRITE = AF_WORKER_WARPS, AF_W_PROD = AF_W_WRITE + AF_WRITER_WARPS, AF_W_MMA = AF_W_PROD + 1;
 static constexpr int AF_MAX_TOKENS = 208;
 
 static constexpr uint32_t AF_QT = 128 * 128;                    // one query tile [128 x 64] fp16
 static constexpr uint32_t AF_SLAB = AF_MAX_TOKENS * 128;        // K / V slab [208 x 64] fp16
 static constexpr uint32_t AF_PT = 4 * 16384;                    // full P tile [128 q x 256 keys] fp16 as four 64-key K-major blocks
 static constexpr uint32_t AF_Q = 0;                             // two parities (per item)
-static constexpr uint32_t AF_K = AF_Q + 2 * AF_QT;              // two parities (per pair): the next pair's K streams in a full pair ahead
-static constexpr uint32_t AF_V = AF_K + 2 * AF_SLAB;
+static constexpr uint32_t AF_K = AF_Q + 2 * AF_QT;
+static constexpr uint32_t AF_V = AF_K + AF_SLAB;
 static constexpr uint32_t AF_PA = AF_V + AF_SLAB;               // P tile of even items: four 64-key blocks of [128 rows x 128 B]
 static constexpr uint32_t AF_PB = AF_PA + AF_PT;                // P tile of odd items: with two query tiles these are the tile-1 items, whose
 static constexpr uint32_t AF_PB_BYTES = 3 * 80 * 128 + 16384;   //   blocks hold only 80 rows (the M = 128 MMA still reads 128 rows of the last block:
                                                                 //   keep that in bounds); with one tile npad <= 128 needs two full blocks
-static constexpr uint32_t AF_SUMS = AF_PB + AF_PB_BYTES;        // [2 parities][2 halves][128] partial row sums, then [2 halves][128] half-row maxima
-static constexpr uint32_t AF_BARS = AF_SUMS + 2 * 2 * 128 * 4 + 2 * 128 * 4;
+static constexpr uint32_t AF_STAGE = AF_PB + AF_PB_BYTES;       // [128 rows x 64] fp16 staging tile of the O TMA store
+static constexpr uint32_t AF_SUMS = AF_STAGE + AF_QT;           // [2 parities][2 halves][128] partial row sums, [2 parities][128] row maxima,
+static constexpr uint32_t AF_BARS = AF_SUMS + (2 * 2 * 128 + 2 * 128 + 2 * 128) * 4;     //   [2 halves][128] half-row maxima (exchange)
 static constexpr uint32_t AF_SMEM = AF_BARS + 256;
-static_assert(AF_K % 1024 == 0 && AF_V % 1024 == 0 && AF_PA % 1024 == 0 && AF_PB % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+static_assert(AF_K % 1024 == 0 && AF_V % 1024 == 0 && AF_PA % 1024 == 0 && AF_PB % 1024 == 0 && AF_STAGE % 1024 == 0, "tiles must stay 1024-byte aligned");
 static_assert(AF_SMEM + 1024 <= 232448, "attention forward: shared memory budget");
 
 enum : uint32_t {
-    F_FULL_Q = 0 /* +parity */, F_FREE_Q = 2 /* +parity */, F_FULL_K = 4 /* +parity */, F_FREE_K = 6 /* +parity */, F_FULL_V = 8, F_FREE_V = 9,
-    F_S_FULL = 10 /* +buf */, F_S_FREE = 12 /* +buf */, F_P_READY = 14 /* +buf */, F_O_FULL = 16, F_O_FREE = 17, F_COUNT = 18
+    F_FULL_Q = 0 /* +parity */, F_FREE_Q = 2 /* +parity */, F_FULL_K = 4, F_FREE_K = 5, F_FULL_V = 8, F_FREE_V = 9,
+    F_S_FULL = 10 /* +buf */, F_S_FREE = 12 /* +buf */, F_P_READY = 14 /* +buf */, F_O_FULL = 16, F_O_FREE = 17, F_STATS_FREE = 18 /* +buf */,
+    F_COUNT = 20
 };
 
 __device__ __forceinline__ uint64_t af_desc(uint32_t smem_addr) {      // 128-byte rows, 128B swizzle, 8-row atoms of 1024 bytes
@@ -120,7 +125,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
     auto bar = [&](uint32_t i) { return sb + AF_BARS + 8u * i; };
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AF_BARS + 8 * F_COUNT);
     float* s_sums = reinterpret_cast<float*>(smem + AF_SUMS);
-    float* s_max = s_sums + 2 * 2 * 128;
+    float* s_rowmax = s_sums + 2 * 2 * 128;        // [2 parities][128]: final row max of the item (for its LSE)
+    float* s_max = s_rowmax + 2 * 128;             // [2 halves][128]: exchange of the half-row maxima
     const uint32_t pb_stride = nt == 2 ? 80u * 128u : 16384u;      // block stride of the odd-item P tile
     auto p_base = [&](uint32_t pb) { return pb == 0 ? sb + AF_PA : sb + AF_PB; };
     auto p_stride = [&](uint32_t pb) { return pb == 0 ? 16384u : pb_stride; };
@@ -136,7 +142,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
             tma_prefetch_desc(&tmQ0); tma_prefetch_desc(&tmQ1); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmO);
             for (uint32_t i = 0; i < F_COUNT; ++i) mbar_init(bar(i), 1);
             for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar(F_S_FREE + i), AF_WORKER_WARPS); mbar_init(bar(F_P_READY + i), AF_WORKER_WARPS); }
-            mbar_init(bar(F_O_FREE), AF_WORKER_WARPS);
+            mbar_init(bar(F_O_FREE), AF_WRITER_WARPS);
+            for (uint32_t i = 0; i < 2; ++i) mbar_init(bar(F_STATS_FREE + i), AF_WRITER_WARPS);
             fence_mbar_init();
         }
         __syncwarp();
@@ -148,8 +155,11 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
     const uint32_t tmem_base = *tmem_ptr_smem;
     constexpr uint32_t T_S = 0, T_S_STRIDE = 288, T_O = 224;      // S[0] = [0, 208), O = [224, 288), S[1] = [288, 496): all 32-column aligned
 
-    if (warp >= AF_WORKER_WARPS) {
+    // 512 threads x 128 registers at launch; producer / MMA drop to 56, the writers to 96, the workers take the 13312 freed
+    if (warp >= AF_W_PROD) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else if (warp >= AF_W_WRITE) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     }
     if (warp == AF_W_PROD) {
         // ===================================================== TMA producer
@@ -159,10 +169,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
                 const int w = blockIdx.x + it * gridDim.x;
                 const int wb = w / heads, wh = w % heads;
                 if (t == 0) {
-                    const uint32_t kb = it & 1;
-                    if (it >= 2) mbar_wait(bar(F_FREE_K + kb), ((it >> 1) - 1) & 1);
-                    mbar_arrive_expect_tx(bar(F_FULL_K + kb), (uint32_t)npad * 128u);
-                    af_tma(&tmKV, bar(F_FULL_K + kb), sb + AF_K + kb * AF_SLAB, D + wh * 64, 0, wb);
+                    if (it >= 1) mbar_wait(bar(F_FREE_K), (it - 1) & 1);
+                    mbar_arrive_expect_tx(bar(F_FULL_K), (uint32_t)npad * 128u);
+                    af_tma(&tmKV, bar(F_FULL_K), sb + AF_K, D + wh * 64, 0, wb);
                 }
                 const uint32_t qb = j & 1, u = j >> 1;
                 if (u >= 1) mbar_wait(bar(F_FREE_Q + qb), (u - 1) & 1);
@@ -205,18 +214,17 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
         for (int j = 0; j < nitems; ++j) {
             const int it = j / nt, t = j % nt;
             const uint32_t qb = j & 1;
-            const uint32_t kb = it & 1;
-            if (t == 0) mbar_wait(bar(F_FULL_K + kb), (it >> 1) & 1);
+            if (t == 0) mbar_wait(bar(F_FULL_K), it & 1);
             mbar_wait(bar(F_FULL_Q + qb), (j >> 1) & 1);
             if (j >= 2) mbar_wait(bar(F_S_FREE + qb), ((j >> 1) - 1) & 1);  // the workers have read S of item j - 2
             tcgen05_fence_after();
             if (lane == 0) {
-                const uint64_t da = af_desc(sb + AF_Q + qb * AF_QT), db = af_desc(sb + AF_K + kb * AF_SLAB);
+                const uint64_t da = af_desc(sb + AF_Q + qb * AF_QT), db = af_desc(sb + AF_K);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16<1>(tmem_base + T_S + qb * T_S_STRIDE, da + 2 * k, db + 2 * k, idesc_s, k != 0);
                 umma_commit<1>(bar(F_S_FULL + qb));
                 umma_commit<1>(bar(F_FREE_Q + qb));
-                if (t == nt - 1) umma_commit<1>(bar(F_FREE_K + kb));
+                if (t == nt - 1) umma_commit<1>(bar(F_FREE_K));
             }
             __syncwarp();
             if (j >= 1) issue_pv(j - 1);
@@ -224,54 +232,14 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
         if (nitems >= 1) issue_pv(nitems - 1);
     } else if (warp < AF_WORKER_WARPS) {
         // ===================================================== workers: thread = (query row, half of the key columns)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
         const uint32_t quarter = warp & 3, hf = warp >> 2;
         const int rl = quarter * 32 + lane;
         const float sl2 = scale * 1.4426950408889634f;
         const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
-        const bool elected = threadIdx.x == 0;
         const int npieces = npad / 16;                      // 16-column pieces of a score row
         const int h0p = (npieces + 1) / 2;                  // half 0 takes pieces [0, h0p), half 1 the rest
         const int p_lo = hf == 0 ? 0 : h0p, p_hi = hf == 0 ? h0p : npieces;
-        float mx_prev = 0.f;                                // row max of the previous item (for its LSE)
-
-        auto epilogue = [&](int jj, float mx) {
-            const int it = jj / nt, t = jj % nt;
-            const int w = blockIdx.x + it * gridDim.x;
-            const int b = w / heads, h = w % heads;
-            const uint32_t pb = jj & 1;
-            const int row = t * 128 + rl;
-            const bool rows_on = (t * 128 + (int)quarter * 32) < N;
-            uint32_t o[32];
-            mbar_wait(bar(F_O_FULL), jj & 1);
-            tcgen05_fence_after();
-            if (rows_on) { tmem_ld_32x32(tlane + T_O + hf * 32, o); tmem_ld_wait(); }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(F_O_FREE));
-            const float sum = s_sums[pb * 256 + rl] + s_sums[pb * 256 + 128 + rl];
-            const float inv = 1.0f / sum;
-            // O tile staging = block 0 of this item's P tile (the P V MMAs that read it have completed: o_full)
-            const uint32_t stage = p_base(pb);
-            if (rows_on) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + sw128_off(rl, hf * 4 + c)),
-                                 "r"(pack_half2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv)),
-                                 "r"(pack_half2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv)),
-                                 "r"(pack_half2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv)),
-                                 "r"(pack_half2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv)) : "memory");
-                if (hf == 0 && row < N && lse != nullptr) lse[((int64_t)b * heads + h) * N + row] = mx * scale + __logf(sum);
-            }
-            fence_proxy_async_smem();
-            af_bar_workers();
-            if (elected && !(dbg & 16)) {
-                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(stage), "r"(h * 64), "r"(t * 128), "r"(b) : "memory");
-                tma_store_commit();
-            }
-        };
-
         for (int j = 0; j < nitems; ++j) {
             const int t = j % nt;
             const uint32_t sbuf = j & 1;
@@ -300,9 +268,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
                 for (int k = 0; k < MAXP; ++k) if (k < cnt) mx = af_max16(sv[k], mx, (p_lo + k) * 16, N);
             }
             s_max[hf * 128 + rl] = mx;
-            // the staging use of this P tile by the epilogue two items ago must be over before it is overwritten
-            if (elected) tma_store_wait_read<0>();
-            af_bar_workers();
+            af_bar_workers();                   // exchange of the half-row maxima
             mx = fmaxf(mx, s_max[(hf ^ 1) * 128 + rl]);
             if (dbg & 1) mx = 0.f;
             if (rows_on && !(dbg & 2)) {
@@ -325,14 +291,62 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
                     }
                 }
             }
+            // row statistics for the writers (the writers of item j - 2 must be done with this parity's slots)
+            if (j >= 2) mbar_wait(bar(F_STATS_FREE + sbuf), ((j >> 1) - 1) & 1);
             s_sums[sbuf * 256 + hf * 128 + rl] = sum;
+            if (hf == 0) s_rowmax[sbuf * 128 + rl] = mx;
             fence_proxy_async_smem();          // P tile -> visible to the tensor core's async proxy
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(F_P_READY + sbuf));
-            if (j >= 1) epilogue(j - 1, mx_prev);
-            mx_prev = mx;
+            if (lane == 0) mbar_arrive(bar(F_P_READY + sbuf));      // (release: the statistics above are ordered before the P V MMAs and O_FULL)
         }
-        if (nitems >= 1) epilogue(nitems - 1, mx_prev);
+    } else if (warp < AF_W_PROD) {
+        // ===================================================== output writers: thread = one row of the [128 x 64] O tile
+        const uint32_t quarter = warp & 3;
+        const int rl = quarter * 32 + lane;
+        const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
+        const bool elected = warp == AF_W_WRITE && lane == 0;
+        const uint32_t stage = sb + AF_STAGE;
+        for (int jj = 0; jj < nitems; ++jj) {
+            const int it = jj / nt, t = jj % nt;
+            const int w = blockIdx.x + it * gridDim.x;
+            const int b = w / heads, h = w % heads;
+            const uint32_t pb = jj & 1;
+            const int row = t * 128 + rl;
+            const bool rows_on = (t * 128 + (int)quarter * 32) < N;
+            uint32_t o[32];
+            mbar_wait(bar(F_O_FULL), jj & 1);
+            tcgen05_fence_after();
+            const float sum = s_sums[pb * 256 + rl] + s_sums[pb * 256 + 128 + rl];
+            const float mx = s_rowmax[pb * 128 + rl];
+            const float inv = 1.0f / sum;
+            if (elected) tma_store_wait_read<0>();      // the previous store has finished reading the staging tile
+            asm volatile("bar.sync 2, %0;" ::"n"(AF_WRITERS) : "memory");
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                if (rows_on) {
+                    tmem_ld_32x32(tlane + T_O + hh * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + sw128_off(rl, hh * 4 + q)),
+                                     "r"(pack_half2(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv)),
+                                     "r"(pack_half2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv)),
+                                     "r"(pack_half2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv)),
+                                     "r"(pack_half2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv)) : "memory");
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar(F_O_FREE)); mbar_arrive(bar(F_STATS_FREE + pb)); }     // O and this parity's statistics have been read
+            if (rows_on && row < N && lse != nullptr) lse[((int64_t)b * heads + h) * N + row] = mx * scale + __logf(sum);
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 2, %0;" ::"n"(AF_WRITERS) : "memory");
+            if (elected && !(dbg & 16)) {
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(stage), "r"(h * 64), "r"(t * 128), "r"(b) : "memory");
+                tma_store_commit();
+            }
+        }
         if (elected) tma_store_wait_all();
     }
     tcgen05_fence_before();
