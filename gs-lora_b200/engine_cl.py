@@ -99,32 +99,36 @@ def get_prototype_loss(output, labels, prototype_dict, distance="kl"):
 
 class _StructureLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, *lora_params):
+    def forward(ctx, model, group_type, *lora_params):
         eng = model._engine
-        norms = torch.empty(eng.spec.depth, dtype=torch.float32, device=eng.device)
-        F.check(F.lib().gsl_tensor_norms(F.ptr(eng.lora_flat), F.ptr(eng.group_offsets), eng.spec.depth, 0, F.ptr(norms), F.cur_stream()),
-                "gsl_tensor_norms")
-        ctx.model, ctx.norms = model, norms
+        offs = eng.group_offsets_by_type[group_type]
+        G = offs.numel() - 1
+        norms = torch.empty(G, dtype=torch.float32, device=eng.device)
+        F.check(F.lib().gsl_tensor_norms(F.ptr(eng.lora_flat), F.ptr(offs), G, 0, F.ptr(norms), F.cur_stream()), "gsl_tensor_norms")
+        ctx.model, ctx.norms, ctx.offs = model, norms, offs
         return norms.sum()
 
     @staticmethod
     def backward(ctx, g):
         eng = ctx.model._engine
         inv = torch.where(ctx.norms > 0, 1.0 / ctx.norms, torch.zeros_like(ctx.norms))
-        flat = (eng.lora_flat.view(eng.spec.depth, -1) * inv[:, None] * g).view(-1)
+        sizes = (ctx.offs[1:] - ctx.offs[:-1]).long()
+        flat = eng.lora_flat * torch.repeat_interleave(inv, sizes) * g
         out = [eng.lora_view(flat, l, w) for l in range(eng.spec.depth) for w in range(4)]
-        return (None, *out)
+        return (None, None, *out)
 
 
-def get_structure_loss(model: torch.nn.Module, imagenet=False):
+def get_structure_loss(model: torch.nn.Module, imagenet=False, group_type: str = "block"):
     """engine_cl.get_structure_loss (engine_cl.py:349-432): sum over Transformer blocks of the L2 norm of the block's four
-    LoRA matrices.  Differentiable w.r.t. the LoRA parameters (gradient P / ||g||, 0 at ||g|| = 0 where the reference NaNs)."""
+    LoRA matrices.  Differentiable w.r.t. the LoRA parameters (gradient P / ||g||, 0 at ||g|| = 0 where the reference NaNs).
+    `group_type` adds the groupings of engine.get_structure_loss (engine.py:532-687, group_pos "FFN"): "lora" (one (A, B) pair per
+    group) and "matrix" (every LoRA matrix on its own)."""
     m = _unwrap(model)
     # `imagenet` only selects parameter NAMES in the reference (encoder.layers.encoder_layer_{i}.mlp.{0,3}.lora_{A,B}, 12 groups hard-coded,
     # engine_cl.py:395-402); here the groups are the engine's per-block LoRA slices of whichever engine-backed model is passed.
     m.ensure_engine(1)
     m.sync_engine()
-    return _StructureLossFn.apply(m, *m.lora_parameters())
+    return _StructureLossFn.apply(m, group_type, *m.lora_parameters())
 
 
 class StepResult:
@@ -185,7 +189,7 @@ _RING = None
 def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, labels_forget, *, beta: float, alpha: float, BND: float,
                        optimizer=None, hparams: Optional[dict] = None, use_prototype: bool = False, prototype_dict=None,
                        prototype_weight_forget: float = 0.0, prototype_weight_remain: float = 0.0, BND_pro: float = 0.0,
-                       dropout_seed: Optional[int] = None) -> StepResult:
+                       dropout_seed: Optional[int] = None, group_type: str = "block") -> StepResult:
     """One step of engine_cl.train_one_epoch (engine_cl.py:59-125), fused; returns a StepResult whose scalars arrive asynchronously."""
     global _RING
     m = _unwrap(model)
@@ -215,10 +219,11 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
     if dist is not None:
         dist.all_reduce(eng.grad_flat)                          # the one flat LoRA-gradient allreduce (0.98 MB for ViT-P8S8 r=8)
     hp = hparams if hparams is not None else _adamw_hparams(optimizer, m.lora_parameters())
-    eng.optimizer_step(lr=hp["lr"], wd=hp["wd"], alpha=alpha, betas=hp.get("betas", (0.9, 0.999)), eps=hp.get("eps", 1e-8))
+    eng.optimizer_step(lr=hp["lr"], wd=hp["wd"], alpha=alpha, betas=hp.get("betas", (0.9, 0.999)), eps=hp.get("eps", 1e-8),
+                       group_type=group_type)                   # cfg["GROUP_TYPE"] of engine.py:82-90
     m.mark_lora_updated_by_engine()
     # one D2H copy (queued, pinned) for everything the reference reads with .item()
-    packed = torch.cat([sums, eng.group_norms.sum().view(1)])
+    packed = torch.cat([sums, eng.group_norms[:eng.num_groups].sum().view(1)])
     if _RING is None:
         _RING = _PinnedRing()
     slot_i, pinned = _RING.take()

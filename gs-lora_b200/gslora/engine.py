@@ -87,7 +87,16 @@ class VitEngine:
         offs.append(n)
         self.tensor_offsets_host = offs
         self.tensor_offsets = torch.tensor(offs, dtype=torch.int32, device=device)
-        self.group_norms = torch.zeros(spec.depth, dtype=torch.float32, device=device)
+        # group-lasso groupings of engine.get_structure_loss (engine.py:532-687): "block" = the 4 LoRA matrices of a block (what
+        # engine_cl.get_structure_loss hard-codes, engine_cl.py:387-402), "lora" = one (A, B) pair, "matrix" = every matrix on its own.
+        # All three are contiguous slices of the flat [A1 | B1 | A2 | B2] layout, so a grouping is just another offsets array.
+        self.group_offsets_by_type = {
+            "block": self.group_offsets,
+            "lora": torch.tensor(offs[0::2], dtype=torch.int32, device=device),
+            "matrix": self.tensor_offsets,
+        }
+        self.group_norms = torch.zeros(4 * spec.depth, dtype=torch.float32, device=device)
+        self.num_groups = spec.depth
         self.sums = torch.zeros(8, dtype=torch.float32, device=device)
         self._frozen_keep: List[torch.Tensor] = []
 
@@ -190,12 +199,15 @@ class VitEngine:
         F.check(F.lib().gsl_unlearn_ce_grad(F.ptr(logits), F.ptr(labels), F.ptr(self.sums), n_remain, B, self.spec.num_class,
                                             float(beta), float(BND), F.ptr(out), F.cur_stream()), "gsl_unlearn_ce_grad")
 
-    def optimizer_step(self, lr: float, wd: float, alpha: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
+    def optimizer_step(self, lr: float, wd: float, alpha: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0,
+                       group_type: str = "block"):
         """Fused group-Lasso + AdamW on the flat LoRA buffer; repacks the fp16 LoRA operands afterwards."""
         self.opt_step += 1
         n = self.lora_flat.numel()
+        offs = self.group_offsets_by_type[group_type]
+        self.num_groups = offs.numel() - 1
         F.check(F.lib().gsl_grouplasso_adamw_step(F.ptr(self.lora_flat), F.ptr(self.grad_flat), F.ptr(self.exp_avg), F.ptr(self.exp_avg_sq),
-                                                  F.ptr(self.group_offsets), self.spec.depth, n, float(lr), float(wd), float(betas[0]),
+                                                  F.ptr(offs), self.num_groups, n, float(lr), float(wd), float(betas[0]),
                                                   float(betas[1]), float(eps), float(alpha), float(grad_scale), self.opt_step,
                                                   F.ptr(self.group_norms), F.cur_stream()), "gsl_grouplasso_adamw_step")
         self.refresh_lora()

@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 for w in $WHAT; do
   case $w in
     tests)
-      timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest_gpu.log
+      GSLORA_SPEEDUP_OUT=$OUT/${TAG}_speedup.json timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest_gpu.log
       tail -5 $OUT/${TAG}_pytest_gpu.log ;;
     smoke)
       timeout 300 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; tail -3 $OUT/${TAG}_smoke.log ;;

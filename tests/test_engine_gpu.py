@@ -164,6 +164,41 @@ def test_train_one_epoch_pipelined_readback_equals_sequential_steps(golden_dir):
     assert lt_ret.count == sum(x.shape[0] for x, _ in remain[5:])
 
 
+@pytest.mark.parametrize("group_type", ["block", "lora", "matrix"])
+def test_structure_loss_group_types_match_engine_py_formula(golden_dir, group_type):
+    """engine.get_structure_loss groupings (engine.py:532-687, group_pos FFN): value, autograd gradient and the fused group-lasso AdamW
+    step against the plain torch formula  sum_g sqrt(sum_{P in g} ||P||^2)  + torch.optim.AdamW."""
+    import engine_cl
+    g, cfg, sd = load_case(golden_dir, "tiny6_b4")
+    hp = g["hp"]
+    model = build_model(cfg, sd)
+    names = O.lora_names(cfg)            # per block: [fc1.A, fc1.B, fc2.A, fc2.B]
+    groups = {"block": [blk for blk in names], "lora": [pair for blk in names for pair in (blk[:2], blk[2:])],
+              "matrix": [[n] for blk in names for n in blk]}[group_type]
+    params = {n: model.get_parameter(n) for blk in names for n in blk}
+    ref_p = {n: p.detach().clone().requires_grad_(True) for n, p in params.items()}
+    ref_loss = sum(torch.sqrt(sum((ref_p[n] ** 2).sum() for n in grp)) for grp in groups)
+    ref_loss.backward()
+    loss = engine_cl.get_structure_loss(model, group_type=group_type)
+    assert abs(float(loss) - float(ref_loss)) < 1e-5 * float(ref_loss)
+    loss.backward()
+    for n, p in params.items():
+        assert (p.grad - ref_p[n].grad).abs().max() < 1e-6, n
+    # fused step: zero data gradient -> the update is driven by alpha * d structure / d P alone
+    alpha = 0.05
+    opt = torch.optim.AdamW([ref_p[n] for blk in names for n in blk], lr=hp["lr"], weight_decay=hp["wd"])
+    for n in ref_p:
+        ref_p[n].grad.mul_(alpha)
+    opt.step()
+    eng = model._engine
+    eng.grad_flat.zero_()
+    eng.reset_optimizer()
+    eng.optimizer_step(lr=hp["lr"], wd=hp["wd"], alpha=alpha, group_type=group_type)
+    assert abs(float(eng.group_norms[:eng.num_groups].sum()) - float(ref_loss)) < 1e-5 * float(ref_loss)
+    for n, p in params.items():
+        assert (p.data - ref_p[n].data).abs().max() < 2e-6, n
+
+
 def test_p8s8_batch_vs_oracle_fp32_on_gpu():
     """Config-2 shape at bs 32+32: engine vs the oracle executed in torch FP32 on the same GPU (TF32 off)."""
     import engine_cl
