@@ -72,7 +72,9 @@ struct GemmCfg {
     static constexpr int O0_BUF = BLOCK_M * STRIPE * T::O0;
     static constexpr int O1_BUF = BLOCK_M * STRIPE * T::O1;
     static constexpr int AUX_BUF = BLOCK_M * STRIPE * T::AUX;
-    static constexpr int EPI_TOTAL = EPI_GROUPS * (O0_BUF + O1_BUF + AUX_BUF);   // one staging set per group (the groups alternate)
+    // aux stripes in flight per group: a TMA round trip is ~3x a stripe's epilogue time, so two when the operand ring keeps >= 4 stages
+    static constexpr int AUX_DEPTH = (SMEM_LIMIT - 1024 - EPI_GROUPS * (O0_BUF + O1_BUF + 2 * AUX_BUF) - 1024) / STAGE >= 4 ? 2 : 1;
+    static constexpr int EPI_TOTAL = EPI_GROUPS * (O0_BUF + O1_BUF + AUX_DEPTH * AUX_BUF);   // one staging set per group (the groups alternate)
     static constexpr int BAR_BYTES = 1024;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - EPI_TOTAL - BAR_BYTES) / STAGE;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -127,8 +129,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto empty_bar = [&](int i) { return sBar + 8u * (S + i); };
     auto tfull_bar = [&](int i) { return sBar + 8u * (2 * S + i); };
     auto tempty_bar = [&](int i) { return sBar + 8u * (2 * S + 2 + i); };
-    auto aux_bar = [&](int i) { return sBar + 8u * (2 * S + 4 + i); };
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (sBar - smem_base) + 8 * (2 * S + 4 + 2));
+    auto aux_bar = [&](int i) { return sBar + 8u * (2 * S + 4 + i); };      // [group][slot]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (sBar - smem_base) + 8 * (2 * S + 4 + 4));
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
@@ -154,7 +156,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_init(tfull_bar(i), 1);             // one tcgen05.commit
                 mbar_init(tempty_bar(i), CG * EPI_WARPS);          // one elected lane per epilogue warp of the pair
             }
-            for (int i = 0; i < 2; ++i) mbar_init(aux_bar(i), 1);
+            for (int i = 0; i < 4; ++i) mbar_init(aux_bar(i), 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -231,12 +233,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t half = (ew & 7) >> 2;            // which half of the stripe's columns
         const uint32_t row = quarter * 32 + lane;       // row of the 128-row tile owned by this thread
         const bool elected = ((ew & 7) == 0 && lane == 0);
-        const uint32_t gbase = sEpi + grp * (Cfg::O0_BUF + Cfg::O1_BUF + Cfg::AUX_BUF);
-        const uint32_t o0_buf = gbase, aux_buf = gbase + Cfg::O0_BUF, o1_buf = gbase + Cfg::O0_BUF + Cfg::AUX_BUF;
+        const uint32_t gbase = sEpi + grp * (Cfg::O0_BUF + Cfg::O1_BUF + Cfg::AUX_DEPTH * Cfg::AUX_BUF);
+        const uint32_t o0_buf = gbase, aux_base = gbase + Cfg::O0_BUF, o1_buf = gbase + Cfg::O0_BUF + Cfg::AUX_DEPTH * Cfg::AUX_BUF;
         const bool write_o1 = (EPI == EPI_GELU) || (EPI == EPI_F32 && p.has_out1);
 
         int iter = 0;
-        uint32_t aux_it = 0;     // aux stripes consumed by this group so far (parity = aux_it & 1)
+        uint32_t aux_it = 0;     // aux stripes consumed by this group so far: slot = aux_it % AUX_DEPTH, parity = (aux_it / AUX_DEPTH) & 1
         for (int t = cluster_id; t < total_tiles; t += num_clusters, ++iter) {
             const int mt = t / p.num_n_tiles, nt = t % p.num_n_tiles;
             const int acc = iter & 1;
@@ -247,9 +249,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int nstripes = ((n_rem >= BN ? BN : n_rem) + STRIPE - 1) / STRIPE;
             const bool tile_live = m_base < p.M;     // CTA-uniform (the second CTA of a pair can be past the M tail)
 
-            if (T::AUX && tile_live && elected && (int)grp < nstripes) {
-                mbar_arrive_expect_tx(aux_bar(grp), Cfg::AUX_BUF);
-                tma_load_2d<1>(&tmAux, aux_bar(grp), aux_buf, n_base + grp * STRIPE, m_base);
+            if (T::AUX && tile_live && elected) {       // this group's first two aux stripes of the tile
+#pragma unroll
+                for (int q = 0; q < Cfg::AUX_DEPTH; ++q) {
+                    const int sq = (int)grp + q * EPI_GROUPS;
+                    if (sq < nstripes) {
+                        const uint32_t slot = (aux_it + q) % Cfg::AUX_DEPTH;
+                        mbar_arrive_expect_tx(aux_bar(grp * 2 + slot), Cfg::AUX_BUF);
+                        tma_load_2d<1>(&tmAux, aux_bar(grp * 2 + slot), aux_base + slot * Cfg::AUX_BUF, n_base + sq * STRIPE, m_base);
+                    }
+                }
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
@@ -283,7 +292,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
                 if (EPI == EPI_RES_F32) {      // out = Dropout(acc + bias) + residual   (to_out / fc2 output, then the Residual add)
-                    mbar_wait(aux_bar(grp), aux_it & 1);
+                    const uint32_t aux_buf = aux_base + (aux_it % Cfg::AUX_DEPTH) * Cfg::AUX_BUF;
+                    mbar_wait(aux_bar(grp * 2 + (aux_it % Cfg::AUX_DEPTH)), (aux_it / Cfg::AUX_DEPTH) & 1);
                     ++aux_it;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {       // fp32 residual stripe [128 x 32]: this warp's 16 columns = chunks half*4 .. +3
@@ -300,7 +310,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
                 if (EPI == EPI_GELU_BWD) {     // out = acc * aux, aux = keep-scale * mask * gelu'(h) as written by EPI_GELU (fp16 stripe [128 x 64])
-                    mbar_wait(aux_bar(grp), aux_it & 1);
+                    const uint32_t aux_buf = aux_base + (aux_it % Cfg::AUX_DEPTH) * Cfg::AUX_BUF;
+                    mbar_wait(aux_bar(grp * 2 + (aux_it % Cfg::AUX_DEPTH)), (aux_it / Cfg::AUX_DEPTH) & 1);
                     ++aux_it;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -358,9 +369,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // has consumed the aux stripe by the time it reaches the barrier
                 if (elected) tma_store_wait_read<0>();
                 epi_bar_sync(grp);
-                if (T::AUX && elected && sidx + EPI_GROUPS < nstripes) {     // prefetch this group's next aux stripe
-                    mbar_arrive_expect_tx(aux_bar(grp), Cfg::AUX_BUF);
-                    tma_load_2d<1>(&tmAux, aux_bar(grp), aux_buf, n_base + (sidx + EPI_GROUPS) * STRIPE, m_base);
+                if (T::AUX && elected && sidx + Cfg::AUX_DEPTH * EPI_GROUPS < nstripes) {     // refill the slot just consumed: two stripes ahead
+                    const uint32_t slot = (aux_it - 1) % Cfg::AUX_DEPTH;      // (aux_it was advanced when this stripe's aux was consumed)
+                    mbar_arrive_expect_tx(aux_bar(grp * 2 + slot), Cfg::AUX_BUF);
+                    tma_load_2d<1>(&tmAux, aux_bar(grp * 2 + slot), aux_base + slot * Cfg::AUX_BUF, n_base + (sidx + Cfg::AUX_DEPTH * EPI_GROUPS) * STRIPE, m_base);
                 }
 
                 if (T::O0 == 4) {   // fp32 [128 x 32] stripe: this warp's 16 columns = 16-byte chunks half*4 .. +3
