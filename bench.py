@@ -146,6 +146,28 @@ def run_gslora(args):
         issue_copy()                                   # next step's inputs (154 MB) travel while this step runs
         return engine_cl.unlearn_step_async(model, *tens, **step_kw)     # ends with the queued D2H copy of the loss scalars
 
+    # the same e2e step fed with RAW uint8 pixels: 1 byte / pixel over PCIe, ToTensor's /255 applied inside the patchify kernel
+    host_u8 = [torch.randint(0, 256, (BATCH, 3, S, S), dtype=torch.uint8, generator=g).pin_memory(), host[1],
+               torch.randint(0, 256, (BATCH, 3, S, S), dtype=torch.uint8, generator=g).pin_memory(), host[3]]
+    staged_u8 = {"next": None}
+
+    def issue_copy_u8():
+        with torch.cuda.stream(copy_stream):
+            tens = [t.to(dev, non_blocking=True) for t in host_u8]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged_u8["next"] = (tens, ev)
+
+    def step_e2e_u8():
+        if staged_u8["next"] is None:
+            issue_copy_u8()
+        tens, ev = staged_u8["next"]
+        torch.cuda.current_stream().wait_event(ev)
+        for t in tens:
+            t.record_stream(torch.cuda.current_stream())
+        issue_copy_u8()
+        return engine_cl.unlearn_step_async(model, *tens, **step_kw)
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
@@ -179,6 +201,7 @@ def run_gslora(args):
         sampler.start()
     ms, launches, out = timed(step_resident, args.steps, args.warmup)
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e_u8, _, _ = timed(step_e2e_u8, args.steps, max(1, args.warmup // 2))
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=3)
@@ -205,7 +228,11 @@ def run_gslora(args):
                        "loss": out["total"]},
             "clocks": sampler.summary(),
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(ms_e2e, 3), "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 9 * 4},
+                    "d2h_bytes_per_step": 9 * 4,
+                    "input_format": "fp32 NCHW in pinned host memory (the reference loader's transforms.ToTensor() output)",
+                    "uint8_pipeline": {"value": round(images / ms_e2e_u8 * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms_e2e_u8, 3),
+                                       "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_u8),
+                                       "note": "same step from raw uint8 pixels (transforms.PILToTensor()); /255 runs in the patchify kernel"}},
             "gpu_launches": int(launches),
             "roofline": roof,
         }

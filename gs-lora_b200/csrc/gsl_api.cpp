@@ -45,6 +45,10 @@ int gsl_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
 int gsl_patchify_f16(const float* img, void* out, int64_t ld, int B, int C, int S, int patch, int order, void* stream) {
     return patchify_f16(img, (__half*)out, ld, B, C, S, patch, order, ST(stream));
 }
+int gsl_patchify_u8_f16(const uint8_t* img, int layout, const float* mean, const float* std, void* out, int64_t ld, int B, int C, int S, int patch,
+                        int order, void* stream) {
+    return patchify_u8_f16(img, layout, mean, std, (__half*)out, ld, B, C, S, patch, order, ST(stream));
+}
 int gsl_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y16, int64_t ldy, float* mean,
                       float* rstd, int64_t M, int D, void* stream) {
     return layernorm_fwd(x, ldx, gamma, beta, eps, (__half*)y16, ldy, mean, rstd, M, D, ST(stream));
@@ -110,7 +114,11 @@ int gsl_engine_refresh_frozen(void* handle, void* stream) { return ((Engine*)han
 int gsl_engine_refresh_lora(void* handle, void* stream) { return ((Engine*)handle)->refresh_lora(ST(stream)); }
 int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* labels, int B, int use_lora, uint64_t dropout_seed,
                        void* stream) {
-    return ((Engine*)handle)->forward(slot, img, labels, B, use_lora, dropout_seed, ST(stream));
+    return ((Engine*)handle)->forward(slot, img, 0, nullptr, nullptr, labels, B, use_lora, dropout_seed, ST(stream));
+}
+int gsl_engine_forward_u8(void* handle, int slot, const uint8_t* img, int layout, const float* mean, const float* std, const int64_t* labels,
+                          int B, int use_lora, uint64_t dropout_seed, void* stream) {
+    return ((Engine*)handle)->forward(slot, img, 1 + (layout != 0), mean, std, labels, B, use_lora, dropout_seed, ST(stream));
 }
 int gsl_engine_backward(void* handle, int slot, const float* dlogits, const float* demb, int accumulate, void* stream) {
     return ((Engine*)handle)->backward(slot, dlogits, demb, accumulate, ST(stream));
@@ -139,6 +147,12 @@ int gsl_prototype_kl_fwd(const float* emb, const int64_t* labels, const float* p
 int gsl_prototype_kl_grad(const float* emb, const int64_t* labels, const float* proto, const float* sums, int n_remain_local, int B, int D,
                           float w_f, float w_r, float BND_pro, float* demb, void* stream) {
     return prototype_kl_grad(emb, labels, proto, sums, n_remain_local, B, D, w_f, w_r, BND_pro, demb, ST(stream));
+}
+int gsl_class_sums(const float* emb, const int64_t* labels, int B, int D, int C, float* sums, float* counts, void* stream) {
+    return class_sums(emb, labels, B, D, C, sums, counts, ST(stream));
+}
+int gsl_class_means(const float* sums, const float* counts, int C, int D, float* out, void* stream) {
+    return class_means(sums, counts, C, D, out, ST(stream));
 }
 int gsl_unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C, float beta, float BND,
                         float* dlogits, void* stream) {

@@ -358,7 +358,9 @@ int Engine::ffn_forward(int l, int64_t M, __half* xn2, float* ln_mean, float* ln
     return 0;
 }
 
-int Engine::forward(int slot, const float* img, const int64_t* labels, int B, int use_lora, uint64_t dropout_seed, cudaStream_t s) {
+int Engine::forward(int slot, const void* img, int img_kind, const float* mean, const float* std, const int64_t* labels, int B, int use_lora,
+                    uint64_t dropout_seed, cudaStream_t s) {
+    GSL_REQUIRE(img_kind >= 0 && img_kind <= 2, "image kind %d (0 fp32 NCHW, 1 uint8 NCHW, 2 uint8 NHWC)", img_kind);
     GSL_REQUIRE(params_bound, "bind_params first");
     GSL_REQUIRE(slot >= 0 && slot < cfg.num_slots, "slot %d out of range", slot);
     GSL_REQUIRE(B >= 1 && B <= cfg.max_batch, "batch %d outside [1, %d]", B, cfg.max_batch);
@@ -369,7 +371,10 @@ int Engine::forward(int slot, const float* img, const int64_t* labels, int B, in
     const float pdrop = dropout_seed ? cfg.dropout : 0.f, pemb = dropout_seed ? cfg.emb_dropout : 0.f;
     int rc;
     if ((rc = ensure_ffn_weights(use_lora, s))) return rc;
-    if ((rc = patchify_f16(img, patches16, patch_dim, B, cfg.channels, cfg.image_size, cfg.patch_size, cfg.patch_order, s))) return rc;
+    if (img_kind == 0) rc = patchify_f16((const float*)img, patches16, patch_dim, B, cfg.channels, cfg.image_size, cfg.patch_size, cfg.patch_order, s);
+    else rc = patchify_u8_f16((const uint8_t*)img, img_kind - 1, mean, std, patches16, patch_dim, B, cfg.channels, cfg.image_size, cfg.patch_size,
+                              cfg.patch_order, s);
+    if (rc) return rc;
     {   // patch_to_embedding + cls token + pos_embedding (vit_face.py:531-536)
         GemmArgs g;
         g.A = patches16; g.lda = patch_dim; g.B = patch_w16; g.ldb = patch_dim; g.M = M; g.N = D; g.K = patch_dim;

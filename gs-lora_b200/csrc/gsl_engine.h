@@ -79,7 +79,9 @@ public:
     int bind_params(const void* const* ptrs, int n, float* lora, float* grads);
     int refresh_frozen(cudaStream_t s);
     int refresh_lora(cudaStream_t s);
-    int forward(int slot, const float* img, const int64_t* labels, int B, int use_lora, uint64_t dropout_seed, cudaStream_t s);
+    // img_kind 0: fp32 NCHW (ToTensor output); 1 / 2: uint8 NCHW / NHWC with /255 and optional Normalize(mean, std) (host pointers) in flight
+    int forward(int slot, const void* img, int img_kind, const float* mean, const float* std, const int64_t* labels, int B, int use_lora,
+                uint64_t dropout_seed, cudaStream_t s);
     int backward(int slot, const float* dlogits, const float* demb, int accumulate, cudaStream_t s);
     int64_t lora_block_elems() const;
     int64_t lora_offset(int block, int which) const;   // which: 0 A1, 1 B1, 2 A2, 3 B2

@@ -264,4 +264,70 @@ int prototype_kl_grad(const float* emb, const int64_t* labels, const float* prot
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ class prototypes
+// util.utils.calculate_prototypes (util/utils.py:502-549): the reference walks every sample on the host (`embeds_sum[label.item()] += embed`,
+// one device sync per image) and divides by the count at the end.  Here one CTA per class scans the batch's labels and adds the matching
+// embedding rows IN BATCH ORDER into the class row (each thread owns its columns, so the fp32 summation order is the reference's:
+// dataset order), counts go to a float per class; class_means divides with IEEE division.  Deterministic, no atomics, no host sync.
+__global__ void class_sums_kernel(const float* __restrict__ emb, const int64_t* __restrict__ labels, int B, int D, float* __restrict__ sums,
+                                  float* __restrict__ counts) {
+    const int c = blockIdx.x;
+    __shared__ int s_hit[256];
+    constexpr int MAXV = 8;                       // D <= 8 * blockDim.x
+    float acc[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int d = threadIdx.x + i * blockDim.x;
+        acc[i] = d < D ? sums[(int64_t)c * D + d] : 0.f;
+    }
+    int n = 0;
+    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+        const int b = b0 + threadIdx.x;
+        s_hit[threadIdx.x] = (b < B && labels[b] == (int64_t)c) ? 1 : 0;
+        __syncthreads();
+        const int lim = min((int)blockDim.x, B - b0);
+        for (int j = 0; j < lim; ++j) {
+            if (!s_hit[j]) continue;
+            const float* e = emb + (int64_t)(b0 + j) * D;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const int d = threadIdx.x + i * blockDim.x;
+                if (d < D) acc[i] += e[d];
+            }
+            ++n;
+        }
+        __syncthreads();
+    }
+    if (n) {
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int d = threadIdx.x + i * blockDim.x;
+            if (d < D) sums[(int64_t)c * D + d] = acc[i];
+        }
+        if (threadIdx.x == 0) counts[c] += (float)n;
+    }
+}
+__global__ void class_means_kernel(const float* __restrict__ sums, const float* __restrict__ counts, int C, int D, float* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)C * D) return;
+    const float n = counts[i / D];
+    out[i] = n > 0.f ? __fdiv_rn(sums[i], n) : 0.f;
+}
+int class_sums(const float* emb, const int64_t* labels, int B, int D, int C, float* sums, float* counts, cudaStream_t s) {
+    GSL_REQUIRE(D >= 1 && D <= 8 * 256, "class_sums: embedding width %d outside [1, 2048]", D);
+    GSL_REQUIRE(C >= 1 && B >= 0, "class_sums: bad sizes");
+    if (B == 0) return 0;
+    class_sums_kernel<<<C, 256, 0, s>>>(emb, labels, B, D, sums, counts);
+    GSL_COUNT_LAUNCH(1);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int class_means(const float* sums, const float* counts, int C, int D, float* out, cudaStream_t s) {
+    const int64_t n = (int64_t)C * D;
+    class_means_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(sums, counts, C, D, out);
+    GSL_COUNT_LAUNCH(1);
+    GSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace gsl

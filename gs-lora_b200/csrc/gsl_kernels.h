@@ -39,6 +39,10 @@ int device_sm_count();
 // img [B,C,S,S] fp32 NCHW -> patches fp16 [B*(P+1), ld] with a zero row at token 0 of every image;
 // order 0: (p1 p2 c) channel fastest (vit_face.py:530); order 1: (c p1 p2) (torchvision conv_proj)
 int patchify_f16(const float* img, __half* out, int64_t ld, int B, int C, int S, int patch, int order, cudaStream_t s);
+// the same from raw uint8 pixels (layout 0 NCHW, 1 NHWC): ToTensor's /255 and an optional Normalize(mean, std) (HOST pointers, C floats each, or
+// both null) are applied in flight -- the input pipeline moves 1 byte per pixel over PCIe instead of 4
+int patchify_u8_f16(const uint8_t* img, int layout, const float* mean, const float* std, __half* out, int64_t ld, int B, int C, int S, int patch,
+                    int order, cudaStream_t s);
 // y = LN(x) * gamma + beta -> fp16 [M, ldy] ; saves mean/rstd
 int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, __half* y, int64_t ldy,
                   float* mean, float* rstd, int64_t M, int D, cudaStream_t s);
@@ -117,6 +121,10 @@ int loss_sums(const float* ce, const int* correct, const float* kl, int n_remain
 int prototype_kl_fwd(const float* emb, const int64_t* labels, const float* proto, int B, int D, float* kl, cudaStream_t s);
 int prototype_kl_grad(const float* emb, const int64_t* labels, const float* proto, const float* sums, int n_remain_local, int B, int D, float w_f,
                       float w_r, float BND_pro, float* demb, cudaStream_t s);
+// calculate_prototypes (util/utils.py:502-549): sums[label_b, :] += emb[b, :] in batch order, counts[label_b] += 1; means = sums / counts (0 rows
+// for classes never seen).  sums [C, D] / counts [C] are caller-zeroed accumulators carried across batches.
+int class_sums(const float* emb, const int64_t* labels, int B, int D, int C, float* sums, float* counts, cudaStream_t s);
+int class_means(const float* sums, const float* counts, int C, int D, float* out, cudaStream_t s);
 int unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C, float beta, float BND,
                     float* dlogits, cudaStream_t s);
 

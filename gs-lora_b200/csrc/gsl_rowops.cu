@@ -12,8 +12,15 @@ namespace gsl {
 // torchvision family, conv_proj's implicit (c p1 p2) patch vector.  Token 0 (cls slot) is a zero row so that the
 // patch-embedding GEMM's rows line up 1:1 with the [B, tokens, D] residual stream.
 // output-centric: one thread per pair of consecutive patch-vector elements (coalesced half2 stores; the gathers hit L1/L2)
-__global__ void patchify_kernel(const float* __restrict__ img, __half* __restrict__ out, int64_t ld, int B, int C, int S,
-                                int patch, int order) {
+// T = float: the reference's loader output (transforms.ToTensor(): fp32 NCHW in [0, 1]).
+// T = uint8_t: raw pixels, NCHW (layout 0, transforms.PILToTensor()) or NHWC (layout 1, decoded image rows); ToTensor's `/ 255` and the optional
+// transforms.Normalize(mean, std) of the ImageNet configs (train_own_forget_cl.py:138-139) are applied on the fly with IEEE division, so
+// the fp32 value that gets rounded to fp16 is bit-identical to what the reference's transform pipeline would have produced on the host.
+struct PixelNorm { float mean[4]; float std[4]; int enabled; };
+
+template <typename T>
+__global__ void patchify_kernel(const T* __restrict__ img, __half* __restrict__ out, int64_t ld, int B, int C, int S,
+                                int patch, int order, int layout, PixelNorm nrm) {
     const int w = S / patch;
     const int P = w * w;
     const int pd = C * patch * patch;
@@ -33,14 +40,24 @@ __global__ void patchify_kernel(const float* __restrict__ img, __half* __restric
                 int c, p1, p2;
                 if (order == 0) { c = e % C; p2 = (e / C) % patch; p1 = e / (C * patch); }
                 else { p2 = e % patch; p1 = (e / patch) % patch; c = e / (patch * patch); }
-                v[k] = __ldg(img + (((int64_t)b * C + c) * S + ph * patch + p1) * S + pw * patch + p2);
+                const int y = ph * patch + p1, x = pw * patch + p2;
+                const int64_t idx = layout == 0 ? (((int64_t)b * C + c) * S + y) * S + x : (((int64_t)b * S + y) * S + x) * C + c;
+                if constexpr (sizeof(T) == 1) {
+                    float f = __fdiv_rn((float)__ldg(img + idx), 255.f);
+                    if (nrm.enabled) f = __fdiv_rn(f - nrm.mean[c & 3], nrm.std[c & 3]);
+                    v[k] = f;
+                } else {
+                    v[k] = __ldg(img + idx);
+                }
             }
         }
         *reinterpret_cast<__half2*>(out + row * ld + e0) = __floats2half2_rn(v[0], v[1]);
     }
 }
 
-int patchify_f16(const float* img, __half* out, int64_t ld, int B, int C, int S, int patch, int order, cudaStream_t s) {
+template <typename T>
+static int patchify_launch(const T* img, __half* out, int64_t ld, int B, int C, int S, int patch, int order, int layout, const PixelNorm& nrm,
+                           cudaStream_t s) {
     GSL_REQUIRE(S % patch == 0, "image size %d not divisible by patch %d", S, patch);
     GSL_REQUIRE((C * patch * patch) % 2 == 0 && ld % 2 == 0, "patchify: patch_dim and ld must be even");
     const int64_t total = (int64_t)B * ((S / patch) * (S / patch) + 1) * (C * patch * patch / 2);
@@ -48,10 +65,31 @@ int patchify_f16(const float* img, __half* out, int64_t ld, int B, int C, int S,
     int blocks = (int)((total + threads - 1) / threads);
     const int cap = device_sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    patchify_kernel<<<blocks, threads, 0, s>>>(img, out, ld, B, C, S, patch, order);
+    patchify_kernel<T><<<blocks, threads, 0, s>>>(img, out, ld, B, C, S, patch, order, layout, nrm);
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+int patchify_f16(const float* img, __half* out, int64_t ld, int B, int C, int S, int patch, int order, cudaStream_t s) {
+    PixelNorm nrm{};
+    return patchify_launch<float>(img, out, ld, B, C, S, patch, order, 0, nrm, s);
+}
+
+int patchify_u8_f16(const uint8_t* img, int layout, const float* mean, const float* std, __half* out, int64_t ld, int B, int C, int S, int patch,
+                    int order, cudaStream_t s) {
+    GSL_REQUIRE(layout == 0 || layout == 1, "patchify_u8: layout must be 0 (NCHW) or 1 (NHWC)");
+    GSL_REQUIRE(C >= 1 && C <= 4, "patchify_u8: 1..4 channels");
+    GSL_REQUIRE((mean == nullptr) == (std == nullptr), "patchify_u8: pass both mean and std (host pointers, C floats each) or neither");
+    PixelNorm nrm{};
+    if (mean) {
+        nrm.enabled = 1;
+        for (int c = 0; c < C; ++c) {
+            GSL_REQUIRE(std[c] != 0.f, "patchify_u8: std[%d] is zero", c);
+            nrm.mean[c] = mean[c]; nrm.std[c] = std[c];
+        }
+    }
+    return patchify_launch<uint8_t>(img, out, ld, B, C, S, patch, order, layout, nrm, s);
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm forward

@@ -196,14 +196,19 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
     Br, Bf = int(inputs_remain.shape[0]), int(inputs_forget.shape[0])
     B = Br + Bf
     dev = inputs_remain.device
-    img = torch.cat([inputs_remain.float(), inputs_forget.float()], dim=0).contiguous()
+    if inputs_remain.dtype == torch.uint8 or inputs_forget.dtype == torch.uint8:     # raw pixels: ToTensor [+ Normalize] runs in the patchify kernel
+        if inputs_remain.dtype != inputs_forget.dtype:
+            raise TypeError("unlearn_step: remain and forget images must both be uint8 (raw pixels) or both floating point (ToTensor output)")
+        img = torch.cat([inputs_remain, inputs_forget], dim=0).contiguous()
+    else:
+        img = torch.cat([inputs_remain.float(), inputs_forget.float()], dim=0).contiguous()
     lab = torch.cat([labels_remain.to(torch.int64), labels_forget.to(torch.int64)], dim=0).contiguous()
     eng = m.ensure_engine(B)
     m.sync_engine()
     if m._merged():
         raise RuntimeError("unlearn_step needs model.train() (un-merged LoRA)")
     slot = m._take_slot()
-    eng.forward(img, lab, slot, use_lora=True, dropout_seed=m.dropout_seed() if dropout_seed is None else dropout_seed)
+    eng.forward(img, lab, slot, use_lora=True, dropout_seed=m.dropout_seed() if dropout_seed is None else dropout_seed, **m.image_kwargs(img))
     table = kl = None
     if use_prototype:                                           # GS-LoRA++ (engine_cl.py:97-101): per-sample KL to the class prototype, on device
         table = _prototype_tensor(prototype_dict, eng.spec.num_class, eng.spec.dim, dev).float().contiguous()
@@ -407,12 +412,12 @@ def eval_data(model, dataloader, device, mode: str, batch: int = 0):
     model.eval()
     with torch.no_grad():
         for images, labels in dataloader:
-            images = images.to(device).float().contiguous()
+            images = m.prepare_images(images.to(device))
             labels = labels.to(device).long().contiguous()
             eng = m.ensure_engine(images.shape[0])
             m.sync_engine()
             slot = m._take_slot()
-            B = eng.forward(images, labels, slot, use_lora=not m._merged())
+            B = eng.forward(images, labels, slot, use_lora=not m._merged(), **m.image_kwargs(images))
             hits += eng.slot_tensor(slot, F.SLOT_CORRECT, B).sum()
             total += labels.size(0)
     accuracy = 100 * int(hits.item()) / max(total, 1)

@@ -49,6 +49,10 @@ def _declare(L):
     P = c_void_p
     sigs = {
         "gsl_patchify_f16": [P, P, c_int64, c_int, c_int, c_int, c_int, c_int, P],
+        "gsl_patchify_u8_f16": [P, c_int, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, P],
+        "gsl_engine_forward_u8": [P, c_int, P, c_int, P, P, P, c_int, c_int, ctypes.c_uint64, P],
+        "gsl_class_sums": [P, P, c_int, c_int, c_int, P, P, P],
+        "gsl_class_means": [P, P, c_int, c_int, P, P],
         "gsl_layernorm_fwd": [P, c_int64, P, P, c_float, P, c_int64, P, P, c_int64, c_int, P],
         "gsl_layernorm_bwd": [P, c_int64, P, c_int64, P, P, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int, P],
         "gsl_lora_down": [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int, c_int, P],
@@ -95,7 +99,16 @@ EXPORTS = ["gsl_last_error", "gsl_version", "gsl_launch_count", "gsl_set_gemm_ct
            "gsl_cast_f32_to_f16", "gsl_grouplasso_adamw_step", "gsl_tensor_norms", "gsl_engine_workspace_bytes", "gsl_engine_create",
            "gsl_engine_destroy", "gsl_engine_bind_params", "gsl_engine_refresh_frozen", "gsl_engine_refresh_lora", "gsl_engine_forward",
            "gsl_engine_backward", "gsl_engine_slot_ptr", "gsl_engine_lora_offset", "gsl_engine_lora_numel", "gsl_loss_sums",
-           "gsl_unlearn_ce_grad", "gsl_prototype_kl_fwd", "gsl_prototype_kl_grad"]
+           "gsl_unlearn_ce_grad", "gsl_prototype_kl_fwd", "gsl_prototype_kl_grad", "gsl_patchify_u8_f16", "gsl_engine_forward_u8",
+           "gsl_class_sums", "gsl_class_means"]
+
+
+def host_floats(values):
+    """ctypes float array for the HOST-pointer arguments (mean / std of gsl_patchify_u8_f16), or None."""
+    if values is None:
+        return None
+    vals = [float(v) for v in values]
+    return (ctypes.c_float * len(vals))(*vals)
 
 
 def check(rc, what=""):

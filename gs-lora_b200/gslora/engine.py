@@ -156,14 +156,32 @@ class VitEngine:
             return self._view(p, (B, s.dim), torch.float32)
         raise ValueError(what)
 
-    def forward(self, img: torch.Tensor, labels: Optional[torch.Tensor], slot: int = 0, use_lora: bool = True, dropout_seed: int = 0):
-        assert img.is_cuda and img.dtype == torch.float32 and img.is_contiguous()
+    def forward(self, img: torch.Tensor, labels: Optional[torch.Tensor], slot: int = 0, use_lora: bool = True, dropout_seed: int = 0,
+                pixel_norm=None, channels_last: bool = False):
+        """fp32 NCHW images (the reference loader's ToTensor output), or raw uint8 pixels ([B,C,S,S], or [B,S,S,C] with channels_last):
+        ToTensor's /255 and the optional Normalize `pixel_norm = (mean, std)` are then applied inside the patchify kernel."""
+        assert img.is_cuda and img.is_contiguous() and img.dtype in (torch.float32, torch.uint8)
         B = img.shape[0]
         if labels is not None:
             assert labels.is_cuda and labels.dtype == torch.int64 and labels.is_contiguous()
+        if img.dtype == torch.uint8:
+            s = self.spec
+            want = (B, s.image_size, s.image_size, s.channels) if channels_last else (B, s.channels, s.image_size, s.image_size)
+            assert tuple(img.shape) == want, f"uint8 images {tuple(img.shape)} != {want}"
+            mean, std = (F.host_floats(pixel_norm[0]), F.host_floats(pixel_norm[1])) if pixel_norm is not None else (None, None)
+            F.check(F.lib().gsl_engine_forward_u8(self.handle, slot, F.ptr(img), 1 if channels_last else 0, mean, std, F.ptr(labels), B,
+                                                  1 if use_lora else 0, int(dropout_seed), F.cur_stream()), "gsl_engine_forward_u8")
+            return B
+        assert pixel_norm is None and not channels_last, "pixel_norm / channels_last apply to uint8 images only"
         F.check(F.lib().gsl_engine_forward(self.handle, slot, F.ptr(img), F.ptr(labels), B, 1 if use_lora else 0, int(dropout_seed), F.cur_stream()),
                 "gsl_engine_forward")
         return B
+
+    def class_sums(self, slot: int, labels: torch.Tensor, B: int, sums: torch.Tensor, counts: torch.Tensor):
+        """calculate_prototypes' accumulation (util/utils.py:535-541) for the slot's embeddings: sums[label] += emb, counts[label] += 1."""
+        emb = self.slot_tensor(slot, F.SLOT_EMB, B)
+        F.check(F.lib().gsl_class_sums(F.ptr(emb), F.ptr(labels), B, self.spec.dim, sums.shape[0], F.ptr(sums), F.ptr(counts), F.cur_stream()),
+                "gsl_class_sums")
 
     def backward(self, slot: int, dlogits: Optional[torch.Tensor], demb: Optional[torch.Tensor], accumulate: bool = False):
         for t in (dlogits, demb):

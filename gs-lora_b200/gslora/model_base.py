@@ -20,7 +20,7 @@ class _EngineFn(torch.autograd.Function):
     def forward(ctx, model, img, label, always_logits, *lora_params):
         eng = model._engine
         slot = model._take_slot()
-        B = eng.forward(img, label, slot, use_lora=True, dropout_seed=model.dropout_seed())
+        B = eng.forward(img, label, slot, use_lora=True, dropout_seed=model.dropout_seed(), **model.image_kwargs(img))
         ctx.model, ctx.slot, ctx.B, ctx.stamp = model, slot, B, model._slot_stamp[slot]
         emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
         if label is None and not always_logits:
@@ -71,6 +71,22 @@ class EngineBackedModel(nn.Module):
         new._engine, new._frozen_sig, new._lora_sig = None, None, None
         return new
 
+
+    # uint8 input pipeline: raw pixels cross PCIe (1 byte / pixel instead of 4) and transforms.ToTensor() [+ Normalize] runs
+    # inside the patchify kernel.  `input_pixel_norm = (mean, std)` mirrors transforms.Normalize of the ImageNet runs
+    # (train_own_forget_cl.py:138-139); None = ToTensor only (the CASIA runs).
+    input_pixel_norm = None
+
+    def prepare_images(self, img: torch.Tensor) -> torch.Tensor:
+        """fp32 NCHW (anything non-uint8 is cast, as the reference's modules would) or uint8 NCHW / NHWC, contiguous."""
+        return img.contiguous() if img.dtype == torch.uint8 else img.float().contiguous()
+
+    def image_kwargs(self, img: torch.Tensor) -> dict:
+        if img.dtype != torch.uint8:
+            return {}
+        C = self.engine_spec().channels
+        nhwc = img.dim() == 4 and img.shape[-1] == C and img.shape[1] != C
+        return dict(pixel_norm=self.input_pixel_norm, channels_last=nhwc)
 
     def lora_parameters(self) -> List[nn.Parameter]:
         out = []
@@ -150,7 +166,7 @@ class EngineBackedModel(nn.Module):
     # ------------------------------------------------------------------ forward
     def _engine_forward(self, img, label=None, always_logits: bool = False):
         """(logits, emb) if `label` is given (or always_logits) else emb."""
-        img = img.float().contiguous()
+        img = self.prepare_images(img)
         if label is not None:
             label = label.to(device=img.device, dtype=torch.int64).contiguous()
         eng = self.ensure_engine(img.shape[0])
@@ -161,7 +177,7 @@ class EngineBackedModel(nn.Module):
         if need_grad:
             return _EngineFn.apply(self, img, label, always_logits, *lora_params)
         slot = self._take_slot()
-        B = eng.forward(img, label, slot, use_lora=not merged, dropout_seed=self.dropout_seed())
+        B = eng.forward(img, label, slot, use_lora=not merged, dropout_seed=self.dropout_seed(), **self.image_kwargs(img))
         emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
         if label is None and not always_logits:
             return emb

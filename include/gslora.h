@@ -54,6 +54,12 @@ int gsl_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
 /* einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (vit_face.py:530) -> fp16 [B*(P+1), ld], zero row at token 0.
  * order 0 = (p1 p2 c) ViT_face, 1 = (c p1 p2) torchvision conv_proj. */
 int gsl_patchify_f16(const float* img, void* out, int64_t ld, int B, int C, int S, int patch, int order, void* stream);
+/* The same from raw uint8 pixels (layout 0 = NCHW as transforms.PILToTensor() stacks them, 1 = NHWC decoded rows): transforms.ToTensor()'s
+ * `/ 255` and the optional transforms.Normalize(mean, std) of the ImageNet runs (train/train_own_forget_cl.py:138-139) happen in flight with
+ * IEEE division, so the value rounded to fp16 is the one the reference's host transform produces.  mean / std: HOST pointers to C floats, or
+ * both NULL.  Replaces the fp32 H2D copy of util/data_prefetcher.py:4-7 by one byte per pixel. */
+int gsl_patchify_u8_f16(const uint8_t* img, int layout, const float* mean, const float* std, void* out, int64_t ld, int B, int C, int S,
+                        int patch, int order, void* stream);
 /* nn.LayerNorm forward (vit_face.py:316-323): fp32 in, fp16 out, row mean / rstd saved. */
 int gsl_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y16, int64_t ldy,
                       float* mean, float* rstd, int64_t M, int D, void* stream);
@@ -133,6 +139,9 @@ int gsl_engine_refresh_lora(void* handle, void* stream);
  * it (the backward of the same slot regenerates them).  Results stay in the slot: see gsl_engine_slot_ptr. */
 int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* labels, int B, int use_lora, uint64_t dropout_seed,
                        void* stream);
+/* gsl_engine_forward on raw uint8 pixels (see gsl_patchify_u8_f16 for layout / mean / std). */
+int gsl_engine_forward_u8(void* handle, int slot, const uint8_t* img, int layout, const float* mean, const float* std, const int64_t* labels,
+                          int B, int use_lora, uint64_t dropout_seed, void* stream);
 /* selective backward of engine_cl.py:124: upstream d logits [B,C] and/or d emb [B,D] (fp32, may be NULL) ->
  * LoRA gradients written (accumulate = 0) or added (accumulate = 1) into grad_flat. */
 int gsl_engine_backward(void* handle, int slot, const float* dlogits, const float* demb, int accumulate, void* stream);
@@ -153,6 +162,11 @@ int gsl_loss_sums(const float* ce, const int32_t* correct, const float* kl, int 
 int gsl_prototype_kl_fwd(const float* emb, const int64_t* labels, const float* proto, int B, int D, float* kl, void* stream);
 int gsl_prototype_kl_grad(const float* emb, const int64_t* labels, const float* proto, const float* sums, int n_remain_local, int B, int D,
                           float w_f, float w_r, float BND_pro, float* demb, void* stream);
+/* Class prototypes, util.utils.calculate_prototypes (util/utils.py:502-549): per batch sums[label_b, :] += emb[b, :] (in batch order: the
+ * reference's fp32 summation order) and counts[label_b] += 1 on caller-zeroed accumulators sums [C, D] / counts [C]; gsl_class_means writes
+ * sums / counts (zero rows for classes never seen).  No host sync per sample (the reference does one `.item()` per image). */
+int gsl_class_sums(const float* emb, const int64_t* labels, int B, int D, int C, float* sums, float* counts, void* stream);
+int gsl_class_means(const float* sums, const float* counts, int C, int D, float* out, void* stream);
 /* dlogits[b] = w_b * (softmax(logits[b]) - onehot(label_b)) with w_b = 1/n_remain (remain) or
  *   -beta * [CE_forget_mean < BND] / n_forget (forget), counts and means taken from `sums` (device). */
 int gsl_unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C,

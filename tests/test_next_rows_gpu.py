@@ -1,0 +1,187 @@
+"""SURVEY 8f rows on the GPU: the uint8 input pipeline (8f-4) and device-side class prototypes (8f-1), each against a plain PyTorch
+restatement of the reference's host code (transforms.ToTensor / Normalize, util/utils.py:502-549).  Integer / selection work and the
+fp32 sums taken in the reference's order are held to bit equality; the rest to the tolerances of test_engine_gpu.py."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    from gslora import _ffi
+    _ffi.lib()
+    return _ffi
+
+
+def rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).norm() / (b.double().cpu().norm() + 1e-30))
+
+
+def _model(cfg, seed=5, device="cuda"):
+    from test_engine_gpu import build_model
+    sd = O.init_state_dict(cfg, seed=seed)
+    return build_model(cfg, sd, device), sd
+
+
+IMAGENET_NORM = ([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])       # train/train_own_forget_cl.py:138-139
+
+
+@pytest.mark.parametrize("B,C,S,patch,order", [(3, 3, 112, 8, 0), (2, 3, 64, 16, 1), (1, 3, 40, 8, 0), (5, 1, 32, 8, 1)])
+@pytest.mark.parametrize("norm", [None, IMAGENET_NORM])
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_patchify_u8_equals_host_totensor_normalize_bitwise(F, B, C, S, patch, order, norm, nhwc):
+    """uint8 pixels -> ToTensor (/255) -> Normalize -> patchify: the kernel's fp16 rows must equal, bit for bit, the fp32 patchify of the
+    host-transformed image (what the reference's loader hands to the model)."""
+    g = torch.Generator().manual_seed(B * 131 + S)
+    u8 = torch.randint(0, 256, (B, C, S, S), dtype=torch.uint8, generator=g)
+    ref = u8.float().div(255)                                           # transforms.ToTensor
+    mean = std = None
+    if norm is not None:
+        mean, std = norm[0][:C], norm[1][:C]
+        ref = ref.sub(torch.tensor(mean).view(1, C, 1, 1)).div(torch.tensor(std).view(1, C, 1, 1))      # transforms.Normalize
+    P = (S // patch) ** 2
+    pd = C * patch * patch
+    out_ref = torch.full((B * (P + 1), pd), 7.0, dtype=torch.half, device="cuda")
+    out_u8 = torch.full_like(out_ref, 9.0)
+    L = F.lib()
+    F.check(L.gsl_patchify_f16(F.ptr(ref.cuda().contiguous()), F.ptr(out_ref), pd, B, C, S, patch, order, F.cur_stream()))
+    src = (u8.permute(0, 2, 3, 1) if nhwc else u8).contiguous().cuda()
+    F.check(L.gsl_patchify_u8_f16(F.ptr(src), 1 if nhwc else 0, F.host_floats(mean), F.host_floats(std), F.ptr(out_u8), pd, B, C, S, patch, order,
+                                  F.cur_stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out_u8.view(torch.int16), out_ref.view(torch.int16))
+    assert float(out_u8.view(B, P + 1, pd)[:, 0].abs().max()) == 0.0      # cls slot rows stay zero
+
+
+def test_patchify_u8_rejects_bad_arguments(F):
+    L = F.lib()
+    img = torch.zeros(1, 3, 16, 16, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(5, 192, dtype=torch.half, device="cuda")
+    assert L.gsl_patchify_u8_f16(F.ptr(img), 2, None, None, F.ptr(out), 192, 1, 3, 16, 8, 0, F.cur_stream()) != 0          # layout
+    assert L.gsl_patchify_u8_f16(F.ptr(img), 0, F.host_floats([0.5] * 3), None, F.ptr(out), 192, 1, 3, 16, 8, 0, F.cur_stream()) != 0   # mean w/o std
+    assert L.gsl_patchify_u8_f16(F.ptr(img), 0, F.host_floats([0.5] * 3), F.host_floats([1, 0, 1]), F.ptr(out), 192, 1, 3, 16, 8, 0,
+                                 F.cur_stream()) != 0                                                                        # std == 0
+    assert b"std" in L.gsl_last_error()
+
+
+def test_uint8_forward_and_unlearn_step_equal_the_fp32_path():
+    """Same pixels as uint8 (NCHW and NHWC) or as ToTensor output: identical logits / embeddings, and an identical fused unlearning step."""
+    import engine_cl
+    cfg = O.TINY
+    g = torch.Generator().manual_seed(11)
+    S = cfg.image_size
+    u_r = torch.randint(0, 256, (5, 3, S, S), dtype=torch.uint8, generator=g).cuda()
+    u_f = torch.randint(0, 256, (3, 3, S, S), dtype=torch.uint8, generator=g).cuda()
+    y_r = torch.randint(0, cfg.num_class, (5,), generator=g).cuda()
+    y_f = torch.randint(0, cfg.num_class, (3,), generator=g).cuda()
+    m32, _ = _model(cfg)
+    m8, _ = _model(cfg)
+    with torch.no_grad():
+        l32, e32 = m32(u_r.float().div(255), y_r)
+        l8, e8 = m8(u_r, y_r)
+        l8c, e8c = m8(u_r.permute(0, 2, 3, 1).contiguous(), y_r)
+    assert torch.equal(l32, l8) and torch.equal(e32, e8) and torch.equal(l32, l8c) and torch.equal(e32, e8c)
+    kw = dict(beta=0.15, alpha=1e-3, BND=105.0, hparams=dict(lr=1e-2, wd=0.05))
+    o32 = engine_cl.unlearn_step(m32, u_r.float().div(255), y_r, u_f.float().div(255), y_f, **kw)
+    o8 = engine_cl.unlearn_step(m8, u_r, y_r, u_f, y_f, **kw)
+    assert o32 == o8
+    for p, q in zip(m32.lora_parameters(), m8.lora_parameters()):
+        assert torch.equal(p, q)
+    with pytest.raises(TypeError):
+        engine_cl.unlearn_step(m8, u_r, y_r, u_f.float(), y_f, **kw)
+    # Normalize in flight (ImageNet runs): equals the host-normalised fp32 input
+    m8.input_pixel_norm = IMAGENET_NORM
+    mean, std = (torch.tensor(v, device="cuda").view(1, 3, 1, 1) for v in IMAGENET_NORM)
+    with torch.no_grad():
+        ln, _ = m8(u_r, y_r)
+        lr_, _ = m32(u_r.float().div(255).sub(mean).div(std), y_r)
+    assert torch.equal(ln, lr_)
+
+
+@pytest.mark.parametrize("B,D,C", [(37, 512, 100), (300, 128, 10), (1, 768, 100), (64, 1024, 7)])
+def test_class_sums_follow_the_reference_loop_bitwise(F, B, D, C):
+    """util/utils.py:535-547 restated: sums in dataset order, fp32, then / count.  Two batches to cover the carried accumulators."""
+    g = torch.Generator().manual_seed(B + D)
+    emb = torch.randn(B, D, generator=g).cuda()
+    lab = torch.randint(0, C, (B,), generator=g).cuda()
+    sums = torch.zeros(C, D, device="cuda")
+    counts = torch.zeros(C, device="cuda")
+    L = F.lib()
+    cut = B // 3
+    for lo, hi in ((0, cut), (cut, B)):
+        F.check(L.gsl_class_sums(F.ptr(emb[lo:hi].contiguous()), F.ptr(lab[lo:hi].contiguous()), hi - lo, D, C, F.ptr(sums), F.ptr(counts),
+                                 F.cur_stream()))
+    means = torch.empty_like(sums)
+    F.check(L.gsl_class_means(F.ptr(sums), F.ptr(counts), C, D, F.ptr(means), F.cur_stream()))
+    ref_sum, ref_n = {}, {}
+    emb_h, lab_h = emb.cpu(), lab.cpu()
+    for e, l in zip(emb_h, lab_h):                     # the reference's per-sample loop
+        k = int(l)
+        ref_sum[k] = ref_sum.get(k, 0) + e
+        ref_n[k] = ref_n.get(k, 0) + 1
+    means_h, counts_h = means.cpu(), counts.cpu()
+    for k in range(C):
+        if k in ref_sum:
+            assert counts_h[k] == ref_n[k]
+            assert torch.equal(means_h[k], ref_sum[k] / ref_n[k])
+        else:
+            assert counts_h[k] == 0 and float(means_h[k].abs().max()) == 0.0
+
+
+def test_calculate_prototypes_matches_reference_function_semantics():
+    """util.utils.calculate_prototypes on an engine-backed model == the reference's loop over the same model's eval-mode embeddings; feeds
+    engine_cl.get_prototype_loss / the fused GS-LoRA++ step unchanged."""
+    from util.utils import calculate_prototypes
+    import engine_cl
+    cfg = O.TINY
+    model, _ = _model(cfg, seed=9)
+    g = torch.Generator().manual_seed(21)
+    N = 23
+    imgs = torch.rand(N, 3, cfg.image_size, cfg.image_size, generator=g)
+    labs = torch.randint(0, 4, (N,), generator=g)                       # 4 of the classes only: absent classes must not appear
+    ds = torch.utils.data.TensorDataset(imgs, labs)
+    protos = calculate_prototypes(model, ds, batch_size=8, device="cuda")
+    assert not model.training                                            # the reference leaves the backbone in eval mode
+    ref_sum, ref_n = {}, {}
+    with torch.no_grad():
+        for lo in range(0, N, 8):
+            _, emb = model(imgs[lo:lo + 8].cuda(), labs[lo:lo + 8].cuda())
+            for e, l in zip(emb, labs[lo:lo + 8]):
+                ref_sum[int(l)] = ref_sum.get(int(l), 0) + e
+                ref_n[int(l)] = ref_n.get(int(l), 0) + 1
+    assert sorted(protos) == sorted(ref_sum)
+    for k in ref_sum:
+        assert protos[k].device.type == "cpu" and protos[k].shape == (cfg.dim,)
+        assert torch.equal(protos[k], (ref_sum[k] / ref_n[k]).cpu())
+    model.train()
+    out = engine_cl.unlearn_step(model, imgs[:6].cuda(), labs[:6].cuda(), imgs[6:10].cuda(), labs[6:10].cuda(), beta=0.15, alpha=1e-3, BND=105.0,
+                                 hparams=dict(lr=1e-2, wd=0.05), use_prototype=True, prototype_dict=protos, prototype_weight_forget=0.5,
+                                 prototype_weight_remain=0.5, BND_pro=1.0)
+    assert out["proto_remain"] >= 0.0 and out["total"] == out["total"]
+
+
+def test_reinitialize_lora_parameters_is_seen_by_the_engine():
+    """util/utils.py:428-441 mutates lora_A / lora_B in place between tasks (train_own_forget_cl.py:536): the engine must pick the new values up
+    (lora_B = 0 => the LoRA branch vanishes: logits equal the frozen model's)."""
+    from util.utils import reinitialize_lora_parameters
+    cfg = O.TINY
+    model, sd = _model(cfg, seed=4)
+    x = torch.rand(4, 3, cfg.image_size, cfg.image_size).cuda()
+    y = torch.randint(0, cfg.num_class, (4,)).cuda()
+    with torch.no_grad():
+        before, _ = model(x, y)
+        reinitialize_lora_parameters(model)
+        after, _ = model(x, y)
+    assert all(float(p.abs().max()) == 0.0 for n, p in model.named_parameters() if "lora_B" in n)
+    sd0 = {k: (torch.zeros_like(v) if "lora_B" in k else v) for k, v in sd.items()}
+    from test_engine_gpu import build_model
+    frozen_only = build_model(cfg, sd0)
+    with torch.no_grad():
+        base, _ = frozen_only(x, y)
+    assert torch.equal(after, base) and not torch.equal(before, after)
