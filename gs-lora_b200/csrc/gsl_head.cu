@@ -268,7 +268,8 @@ int prototype_kl_grad(const float* emb, const int64_t* labels, const float* prot
 // util.utils.calculate_prototypes (util/utils.py:502-549): the reference walks every sample on the host (`embeds_sum[label.item()] += embed`,
 // one device sync per image) and divides by the count at the end.  Here one CTA per class scans the batch's labels and adds the matching
 // embedding rows IN BATCH ORDER into the class row (each thread owns its columns, so the fp32 summation order is the reference's:
-// dataset order), counts go to a float per class; class_means divides with IEEE division.  Deterministic, no atomics, no host sync.
+// dataset order), counts go to a float per class; class_means scales by the correctly rounded reciprocal of the count, which is how ATen
+// evaluates `cuda_tensor / python_int`.  Deterministic, no atomics, no host sync.
 __global__ void class_sums_kernel(const float* __restrict__ emb, const int64_t* __restrict__ labels, int B, int D, float* __restrict__ sums,
                                   float* __restrict__ counts) {
     const int c = blockIdx.x;
@@ -311,7 +312,9 @@ __global__ void class_means_kernel(const float* __restrict__ sums, const float* 
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= (int64_t)C * D) return;
     const float n = counts[i / D];
-    out[i] = n > 0.f ? __fdiv_rn(sums[i], n) : 0.f;
+    // `feature_sum / count` runs on the device in the reference (util/utils.py:547), where ATen divides a CUDA tensor by a host scalar as
+    // a * (1.0f / b): reproduce exactly that rounding
+    out[i] = n > 0.f ? __fmul_rn(sums[i], __frcp_rn(n)) : 0.f;
 }
 int class_sums(const float* emb, const int64_t* labels, int B, int D, int C, float* sums, float* counts, cudaStream_t s) {
     GSL_REQUIRE(D >= 1 && D <= 8 * 256, "class_sums: embedding width %d outside [1, 2048]", D);

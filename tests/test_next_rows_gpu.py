@@ -120,7 +120,7 @@ def test_class_sums_follow_the_reference_loop_bitwise(F, B, D, C):
     means = torch.empty_like(sums)
     F.check(L.gsl_class_means(F.ptr(sums), F.ptr(counts), C, D, F.ptr(means), F.cur_stream()))
     ref_sum, ref_n = {}, {}
-    emb_h, lab_h = emb.cpu(), lab.cpu()
+    emb_h, lab_h = emb, lab.cpu()                      # sums and the final division run on the DEVICE in the reference (a * (1.0f / n) in ATen)
     for e, l in zip(emb_h, lab_h):                     # the reference's per-sample loop
         k = int(l)
         ref_sum[k] = ref_sum.get(k, 0) + e
@@ -129,7 +129,7 @@ def test_class_sums_follow_the_reference_loop_bitwise(F, B, D, C):
     for k in range(C):
         if k in ref_sum:
             assert counts_h[k] == ref_n[k]
-            assert torch.equal(means_h[k], ref_sum[k] / ref_n[k])
+            assert torch.equal(means_h[k], (ref_sum[k] / ref_n[k]).cpu())
         else:
             assert counts_h[k] == 0 and float(means_h[k].abs().max()) == 0.0
 
@@ -178,10 +178,102 @@ def test_reinitialize_lora_parameters_is_seen_by_the_engine():
         before, _ = model(x, y)
         reinitialize_lora_parameters(model)
         after, _ = model(x, y)
-    assert all(float(p.abs().max()) == 0.0 for n, p in model.named_parameters() if "lora_B" in n)
+    assert all(float(p.detach().abs().max()) == 0.0 for n, p in model.named_parameters() if "lora_B" in n)
     sd0 = {k: (torch.zeros_like(v) if "lora_B" in k else v) for k, v in sd.items()}
     from test_engine_gpu import build_model
     frozen_only = build_model(cfg, sd0)
     with torch.no_grad():
         base, _ = frozen_only(x, y)
     assert torch.equal(after, base) and not torch.equal(before, after)
+
+
+# ------------------------------------------------------------------------------------------------ engine.py twin
+def _loaders(cfg, n_forget, n_remain, seed=17):
+    gen = torch.Generator().manual_seed(seed)
+    S = cfg.image_size
+    forget = [(torch.rand(3, 3, S, S, generator=gen), torch.randint(0, cfg.num_class, (3,), generator=gen)) for _ in range(n_forget)]
+    remain = [(torch.rand(4, 3, S, S, generator=gen), torch.randint(0, cfg.num_class, (4,), generator=gen)) for _ in range(n_remain)]
+    return forget, remain
+
+
+@pytest.mark.parametrize("few_shot,alpha_epoch,group_type", [(True, 0, "block"), (False, 0, "matrix"), (True, 5, "lora")])
+def test_engine_py_train_one_epoch_loader_swap_and_alpha_gate(few_shot, alpha_epoch, group_type):
+    """engine.train_one_epoch (engine.py:13-434): with the longer forget loader and cfg["few_shot"] the FORGET loader drives the epoch and the
+    remain loader is recycled (engine.py:53-57); epoch < ALPHA_EPOCH switches the structure term off (engine.py:82-90); GROUP_TYPE picks the
+    group-lasso grouping.  Result must equal the same sequence of synchronous fused steps."""
+    import engine
+    import engine_cl
+    from engine_cl import AverageMeter
+    cfg = O.TINY
+    forget, remain = _loaders(cfg, 6, 4)
+    hp = dict(lr=1e-2, wd=0.05, beta=0.15, alpha=1e-2, BND=105.0)
+    run_cfg = {"few_shot": few_shot, "ALPHA_EPOCH": alpha_epoch, "GROUP_TYPE": group_type, "GROUP_POS": "FFN", "NUM_LAYERS": cfg.depth,
+               "WORK_PATH": "/tmp", "BACKBONE_NAME": "VIT", "MULTI_GPU": False}
+
+    def fresh():
+        m, _ = _model(cfg, seed=6)
+        opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=hp["lr"], weight_decay=hp["wd"])
+        return m, opt
+
+    m1, opt1 = fresh()
+    alpha_eff = 0.0 if 0 < alpha_epoch else hp["alpha"]
+    if few_shot:    # forget (6 batches) drives, remain (4) recycled
+        pairs = [(remain[i % len(remain)], forget[i]) for i in range(len(forget))]
+    else:           # remain drives, forget recycled
+        pairs = [(remain[i], forget[i % len(forget)]) for i in range(len(remain))]
+    for (xr, yr), (xf, yf) in pairs:
+        out = engine_cl.unlearn_step(m1, xr.cuda(), yr.cuda(), xf.cuda(), yf.cuda(), beta=hp["beta"], alpha=alpha_eff, BND=hp["BND"], optimizer=opt1,
+                                     group_type=group_type)
+    m2, opt2 = fresh()
+    mt = [AverageMeter() for _ in range(8)]
+    ret = engine.train_one_epoch(m2, forget, remain, torch.device("cuda"), torch.nn.CrossEntropyLoss(), opt2, 0, mt[0], mt[1], mt[2], mt[3], mt[4],
+                                 mt[5], hp["beta"], hp["alpha"], hp["BND"], 0, None, None, 0.0, 0.0, run_cfg,
+                                 losses_prototype_forget=mt[6], losses_prototype_remain=mt[7])
+    assert ret[0] == len(pairs) and len(ret) == 10
+    for p, q in zip(m1.lora_parameters(), m2.lora_parameters()):
+        assert torch.equal(p.data, q.data)
+    if alpha_eff == 0.0:
+        assert ret[7].sum == 0.0          # structure meter: alpha * loss with the term gated off
+    # the structure loss of the twin's signature equals engine_cl's for the same grouping
+    a = engine.get_structure_loss(m2, num_layers=cfg.depth, group_type=group_type, group_pos="FFN")
+    b = engine_cl.get_structure_loss(m2, group_type=group_type)
+    assert float(a) == float(b)
+    with pytest.raises(NotImplementedError):
+        engine.get_structure_loss(m2, num_layers=cfg.depth, group_type="block", group_pos="Attention")
+    with pytest.raises(ValueError):
+        engine.get_structure_loss(m2, num_layers=cfg.depth + 1)
+
+
+def test_engine_py_eval_and_checkpoint_match_a_merged_deepcopy(tmp_path):
+    """engine.eval_data / evaluate (engine.py:436-529) evaluate `copy.deepcopy(model).eval()` in the reference; the twin evaluates the live weights
+    and saves a merged state_dict without touching the training model."""
+    import copy
+    import engine
+    cfg = O.TINY
+    model, _ = _model(cfg, seed=8)
+    gen = torch.Generator().manual_seed(2)
+    S = cfg.image_size
+    test = [(torch.rand(6, 3, S, S, generator=gen), torch.randint(0, cfg.num_class, (6,), generator=gen)) for _ in range(3)]
+    w_name = "transformer.layers.0.1.fn.fn.net.0.weight"
+    w0 = model.get_parameter(w_name).detach().clone()
+    acc = engine.eval_data(model, test, torch.device("cuda"), "forget")
+    assert model.training and torch.equal(model.get_parameter(w_name), w0)          # model untouched, still in train mode
+    ref = copy.deepcopy(model).eval()
+    hits = total = 0
+    with torch.no_grad():
+        for x, y in test:
+            logits, _ = ref(x.cuda(), y.cuda())
+            hits += int((logits.argmax(1).cpu() == y).sum())
+            total += len(y)
+    assert abs(acc - 100 * hits / total) < 1e-9
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-2)
+    run_cfg = {"WORK_PATH": str(tmp_path), "BACKBONE_NAME": "VIT", "MULTI_GPU": False}
+    h = engine.evaluate(model, test, test, torch.device("cuda"), 0, 0, forget_acc_before=100.0, highest_H_mean=-1.0, cfg=run_cfg, optimizer=opt)
+    files = [f for f in os.listdir(tmp_path) if f.endswith(".pth")]
+    assert len(files) == 1 and h > -1.0
+    saved = torch.load(os.path.join(tmp_path, files[0]))
+    ref_sd = ref.state_dict()
+    assert set(saved) == set(ref_sd)
+    for k in saved:
+        assert torch.allclose(saved[k].cpu(), ref_sd[k].cpu(), rtol=0, atol=1e-6), k
+    assert not torch.equal(saved[w_name].cpu(), w0.cpu())                            # the LoRA delta is in the saved weight
