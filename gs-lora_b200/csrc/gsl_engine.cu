@@ -508,11 +508,9 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
             g.epi = EPI_F16; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
-        // residual gradient of this block's input: zero except the cls rows
-        if ((rc = fill_zero(dx32, (size_t)M * D * 4, s))) return rc;
-        if ((rc = copy_cls_rows(cls_dx32, (int64_t)D * 4, dx32, (int64_t)tokens * D * 4, B, (int64_t)D * 4, s))) return rc;
-        if ((rc = layernorm_bwd(dxn32, 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dy16, D, M, D, pdrop,
-                                site_seed(dseed, l - 1, 3), s))) return rc;
+        // residual gradient of this block's input: zero except the cls rows, which LayerNorm backward picks from the compacted cls_dx32
+        if ((rc = layernorm_bwd(dxn32, 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, cls_dx32, D, dx32, D, dy16, D, M, D, pdrop,
+                                site_seed(dseed, l - 1, 3), s, tokens))) return rc;
     }
     for (int l = L - 2; l >= 0; --l) {
         const BlockFrozen& f = frozen[l];

@@ -49,7 +49,8 @@ int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* 
 // dx = dres + LNbwd(dy) ; writes fp32 dx and an fp16 copy (GEMM operand for the next dX GEMM)
 int layernorm_bwd(const void* dy, int dy_is_fp16, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                   const float* gamma, const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16,
-                  int64_t M, int D, float drop_p, uint32_t drop_seed, cudaStream_t s);   // dropout mask applies to the fp16 copy only
+                  int64_t M, int D, float drop_p, uint32_t drop_seed, cudaStream_t s,    // dropout mask applies to the fp16 copy only
+                  int dres_period = 0);   // > 0: dres holds one compacted row per `dres_period` rows (added at rows r % period == 0, zero elsewhere)
 // T[M, 0:16] = X[M, K] * A16[16, K]^T  (fp16 in, fp32 accumulate, fp16 out at out[:, 0:16], row pitch ldo)
 int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __half* out, int64_t ldo, int64_t M, int K, int r, cudaStream_t s);
 // dW[R, 16-ish] style skinny reductions over M (split-M partials + deterministic second pass):

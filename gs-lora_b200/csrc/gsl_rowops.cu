@@ -162,12 +162,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                             const float* __restrict__ gamma, const float* __restrict__ dres, int64_t lddres,
                                                             float* __restrict__ dx, int64_t lddx, __half* __restrict__ dx16, int64_t lddx16,
-                                                            int64_t M, uint32_t drop_thresh, uint32_t drop_seed, float drop_scale) {
+                                                            int64_t M, uint32_t drop_thresh, uint32_t drop_seed, float drop_scale, int dres_period) {
     constexpr int D = VEC * 128;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const float mean = mean_in[row], rstd = rstd_in[row];
+    // dres_period > 0: the residual gradient is non-zero only at rows that are multiples of the period (the cls tokens under the last
+    // block, whose other tokens are dead) and `dres` holds those rows compacted, one per image
+    const float* dres_row = nullptr;
+    if (dres) {
+        if (dres_period == 0) dres_row = dres + row * lddres;
+        else if (row % dres_period == 0) dres_row = dres + (row / dres_period) * lddres;
+    }
     const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
     const float4* dyr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_v) + (DY16 ? 0 : row * lddy));
     const uint2* dyh = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(dy_v) + (DY16 ? row * lddy : 0));
@@ -199,8 +206,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
         o.y = rstd * (g[i].y - mg - xh[i].y * mgx);
         o.z = rstd * (g[i].z - mg - xh[i].z * mgx);
         o.w = rstd * (g[i].w - mg - xh[i].w * mgx);
-        if (dres) {
-            const float4 r = reinterpret_cast<const float4*>(dres + row * lddres)[lane + 32 * i];
+        if (dres_row) {
+            const float4 r = reinterpret_cast<const float4*>(dres_row)[lane + 32 * i];
             o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         if (dx) reinterpret_cast<float4*>(dx + row * lddx)[lane + 32 * i] = o;
@@ -222,15 +229,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
 
 int layernorm_bwd(const void* dy, int dy_is_fp16, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16, int64_t M, int D,
-                  float drop_p, uint32_t drop_seed, cudaStream_t s) {
+                  float drop_p, uint32_t drop_seed, cudaStream_t s, int dres_period) {
     const uint32_t dth = drop_thresh15(drop_p);
     const float dsc = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     GSL_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm_bwd: D=%d must be a multiple of 128 and <= 1024", D);
     const int warps = 8;
     const int blocks = (int)((M + warps - 1) / warps);
 #define GSL_LN_CASE(V) case V: \
-        if (dy_is_fp16) layernorm_bwd_kernel<V, true><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc); \
-        else layernorm_bwd_kernel<V, false><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc); \
+        if (dy_is_fp16) layernorm_bwd_kernel<V, true><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc, dres_period); \
+        else layernorm_bwd_kernel<V, false><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc, dres_period); \
         break;
     switch (D / 128) {
         GSL_LN_CASE(1) GSL_LN_CASE(2) GSL_LN_CASE(3) GSL_LN_CASE(4) GSL_LN_CASE(5) GSL_LN_CASE(6) GSL_LN_CASE(7) GSL_LN_CASE(8)
