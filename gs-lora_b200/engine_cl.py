@@ -424,3 +424,31 @@ def eval_data(model, dataloader, device, mode: str, batch: int = 0):
     print("Test {} Accuracy:{:2f}%".format(mode, accuracy))
     _wandb_log({"Test {} Accuracy".format(mode): accuracy})
     return accuracy
+
+
+# ------------------------------------------------------------------------------------------------ baselines' loop (OUT of the hot path)
+def _reference_engine_cl():
+    """The reference's own engine_cl.py, loaded under a private name (EWC / MAS / L2 regularisation baselines, engine_cl.py:435-568: full
+    autograd loops that are not the GS-LoRA path -- SURVEY section 2 row 3).  They run on the engine-backed model through its autograd seam."""
+    import importlib.util
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for r in [os.environ.get("GSLORA_REFERENCE_ROOT", "")] + list(sys.path):
+        f = os.path.join(r, "engine_cl.py") if r else ""
+        if f and os.path.isfile(f) and os.path.abspath(r) != here:
+            spec = importlib.util.spec_from_file_location("_gslora_ref_engine_cl", f)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod
+    raise NotImplementedError("gslora-b200: train_one_epoch_regularzation / get_reg_loss belong to the reference's EWC / MAS / L2 baselines "
+                              "(outside the GS-LoRA hot path); put the reference tree on sys.path or set GSLORA_REFERENCE_ROOT to use them")
+
+
+def train_one_epoch_regularzation(*args, **kwargs):
+    """engine_cl.train_one_epoch_regularzation (engine_cl.py:435-568), imported by the driver (train_own_forget_cl.py:41): delegated to the
+    reference's implementation."""
+    return _reference_engine_cl().train_one_epoch_regularzation(*args, **kwargs)
+
+
+def get_reg_loss(*args, **kwargs):
+    return _reference_engine_cl().get_reg_loss(*args, **kwargs)

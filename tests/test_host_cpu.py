@@ -144,3 +144,38 @@ def test_data_parallel_formulation_two_gloo_ranks():
     ret = mgr.dict()
     mp.spawn(_dp_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert ret["rel"] < 1e-5, ret["rel"]
+
+
+def test_driver_import_lines_resolve_on_the_overlay():
+    """Every name the reference's drivers import from the shadowed modules exists with the reference's signature
+    (train/train_own_forget_cl.py:15-55, train/train_own_forget.py:40)."""
+    import inspect
+    import engine
+    import engine_cl
+    import loralib as lora
+    import vit_pytorch_face as vpf
+    from util.cal_norm import get_norm_of_lora  # noqa: F401
+    from util.utils import AverageMeter, calculate_prototypes, get_time, reinitialize_lora_parameters  # noqa: F401
+    for name in ("train_one_epoch", "eval_data", "train_one_epoch_regularzation", "evaluate", "get_structure_loss", "get_prototype_loss"):
+        assert callable(getattr(engine_cl, name)), name
+    for name in ("train_one_epoch", "eval_data", "evaluate", "get_structure_loss", "get_prototype_loss"):
+        assert callable(getattr(engine, name)), name
+    for name in ("ViT_face", "ViT_face_low", "ViT_face_up", "ViTs_face", "ModifiedViT"):
+        assert hasattr(vpf, name), name
+    for name in ("Linear", "MergedLinear", "mark_only_lora_as_trainable"):
+        assert hasattr(lora, name), name
+    # positional order of the reference's train_one_epoch signatures (engine_cl.py:12-43, engine.py:13-43)
+    cl = list(inspect.signature(engine_cl.train_one_epoch).parameters)
+    assert cl[:8] == ["model", "dataloader_forget", "dataloader_remain", "device", "criterion", "optimizer", "epoch", "losses_forget"]
+    assert cl[-8:] == ["task_i", "use_prototype", "prototype_dict", "prototype_weight_forget", "prototype_weight_remain",
+                       "losses_prototype_forget", "losses_prototype_remain", "dataloader_open"]
+    sg = list(inspect.signature(engine.train_one_epoch).parameters)
+    assert sg[:6] == cl[:6] and sg[21:] == ["cfg", "dataloader_open", "prototype_weight_forget", "prototype_weight_remain", "use_prototype",
+                                            "prototype_dict", "losses_prototype_forget", "losses_prototype_remain"]
+    assert list(inspect.signature(engine.get_structure_loss).parameters) == ["model", "num_layers", "group_type", "group_pos"]
+    assert list(inspect.signature(calculate_prototypes).parameters) == ["backbone", "dataset", "batch_size", "device", "aug_num"]
+    # the baselines' loop is the reference's own code: without the reference tree it must say so instead of silently doing something else
+    import sys
+    if not any(os.path.isfile(os.path.join(p, "baselines", "LIRFtrain.py")) for p in sys.path if p):
+        with pytest.raises(NotImplementedError):
+            engine_cl.get_reg_loss()
