@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include <atomic>
 
@@ -15,6 +16,11 @@ void set_last_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool pdl_enabled() {
+    // opt-in: measured on B200 (profiles/r01r_pdl_ab.md) the early-trigger form is 0.8 ms / step SLOWER than plain stream order
+    static const bool on = [] { const char* e = getenv("GSLORA_PDL"); return e && e[0] == '1'; }();
+    return on;
 }
 }  // namespace gsl
 

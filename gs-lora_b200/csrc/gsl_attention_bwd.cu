@@ -194,6 +194,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV0, const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_prologue();     // set-up above overlaps the previous kernel's tail; global memory (TMA, LSE, stats) only from here on
     constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_DK = 384, T_DV = 448;
 
     // 512 threads x 128 registers at launch; producer / MMA / delta drop to 56, the writers to 96, the workers take the 13312 freed
@@ -489,8 +490,8 @@ int attention_bwd_tc(const __half* qkv, int64_t ld, const __half* out, int64_t l
     const int nwork = B * heads;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("GSL_ATTN_DBG"); dbg = e ? atoi(e) : 0; }       // dev switch: knock out stages to time the rest
-    attention_bwd_tc_kernel<<<nwork < sms ? nwork : sms, AB_THREADS, smem, s>>>(tq0, tq1, td0, td1, tout, out, ldo, dout, lddo, lse, dqkv, lddqkv, B, N,
-                                                                                heads, scale, dbg);
+    GSL_CHECK_CUDA(launch_pdl(attention_bwd_tc_kernel, dim3(nwork < sms ? nwork : sms), dim3(AB_THREADS), smem, s, tq0, tq1, td0, td1, tout, out, ldo, dout, lddo, lse, dqkv, lddqkv, B, N,
+                                                                                heads, scale, dbg));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -153,6 +153,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_prologue();     // set-up above overlaps the previous kernel's tail; global memory (TMA, LSE, stats) only from here on
     constexpr uint32_t T_S = 0, T_S_STRIDE = 288, T_O = 224;      // S[0] = [0, 208), O = [224, 288), S[1] = [288, 496): all 32-column aligned
 
     // 512 threads x 128 registers at launch; producer / MMA drop to 56, the writers to 96, the workers take the 13312 freed
@@ -379,7 +380,7 @@ int attention_fwd_tc(const __half* qkv, int64_t ld, __half* out, int64_t ldo, fl
     const int nwork = B * heads;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("GSL_ATTN_DBG"); dbg = e ? atoi(e) : 0; }       // dev switch: knock out stages to time the rest
-    attention_fwd_tc_kernel<<<nwork < sms ? nwork : sms, AF_THREADS, smem, s>>>(tq0, tq1, tkv, to, lse, B, N, heads, scale, dbg);
+    GSL_CHECK_CUDA(launch_pdl(attention_fwd_tc_kernel, dim3(nwork < sms ? nwork : sms), dim3(AF_THREADS), smem, s, tq0, tq1, tkv, to, lse, B, N, heads, scale, dbg));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;

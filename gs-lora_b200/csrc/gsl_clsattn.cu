@@ -31,6 +31,7 @@ __device__ __forceinline__ float across_groups(float v) {   // sum over the 4 ke
 // qkv fp16 [B*N, ld] (q | k | v column blocks of heads*64).  o_cls fp16 [B, ldo] (heads*64 columns), lse_cls [B, heads].
 __global__ void __launch_bounds__(128) cls_attention_fwd_kernel(const __half* __restrict__ qkv, int64_t ld, __half* __restrict__ o_cls, int64_t ldo,
                                                                 float* __restrict__ lse_cls, int B, int N, int heads, float scale) {
+    pdl_prologue();
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
     if (w >= B * heads) return;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(128) cls_attention_fwd_kernel(const __half* __
 int cls_attention_fwd(const __half* qkv, int64_t ld, __half* o_cls, int64_t ldo, float* lse_cls, int B, int N, int heads, float scale, cudaStream_t s) {
     GSL_REQUIRE(N <= CLS_MAX_KEYS && ld % 8 == 0 && ldo % 8 == 0, "cls_attention: tokens=%d > %d or unaligned pitch", N, CLS_MAX_KEYS);
     const int warps = 4;
-    cls_attention_fwd_kernel<<<(B * heads + warps - 1) / warps, warps * 32, 0, s>>>(qkv, ld, o_cls, ldo, lse_cls, B, N, heads, scale);
+    GSL_CHECK_CUDA(launch_pdl(cls_attention_fwd_kernel, dim3((B * heads + warps - 1) / warps), dim3(warps * 32), 0, s, qkv, ld, o_cls, ldo, lse_cls, B, N, heads, scale));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -101,6 +102,7 @@ int cls_attention_fwd(const __half* qkv, int64_t ld, __half* o_cls, int64_t ldo,
 __global__ void __launch_bounds__(128) cls_attention_bwd_kernel(const __half* __restrict__ qkv, int64_t ld, const __half* __restrict__ o_cls, int64_t ldo,
                                                                 const __half* __restrict__ do_cls, int64_t lddo, const float* __restrict__ lse_cls,
                                                                 __half* __restrict__ dqkv, int64_t lddqkv, int B, int N, int heads, float scale) {
+    pdl_prologue();
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
     if (w >= B * heads) return;
@@ -162,7 +164,7 @@ int cls_attention_bwd(const __half* qkv, int64_t ld, const __half* o_cls, int64_
     // dQ of every non-cls token is zero
     GSL_CHECK_CUDA(cudaMemset2DAsync(dqkv, (size_t)lddqkv * 2, 0, (size_t)heads * 64 * 2, (size_t)B * N, s));
     const int warps = 4;
-    cls_attention_bwd_kernel<<<(B * heads + warps - 1) / warps, warps * 32, 0, s>>>(qkv, ld, o_cls, ldo, do_cls, lddo, lse_cls, dqkv, lddqkv, B, N, heads, scale);
+    GSL_CHECK_CUDA(launch_pdl(cls_attention_bwd_kernel, dim3((B * heads + warps - 1) / warps), dim3(warps * 32), 0, s, qkv, ld, o_cls, ldo, do_cls, lddo, lse_cls, dqkv, lddqkv, B, N, heads, scale));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -170,6 +172,7 @@ int cls_attention_bwd(const __half* qkv, int64_t ld, const __half* o_cls, int64_
 
 // rows[b] = src[b * stride_rows] for b < B : gathers the cls rows of a [B*tokens, cols] matrix into [B, cols] (16-byte granules)
 __global__ void gather_rows_kernel(const uint4* __restrict__ src, int64_t src_pitch16, uint4* __restrict__ dst, int64_t dst_pitch16, int B, int granules) {
+    pdl_prologue();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * granules) return;
     const int b = (int)(i / granules), g = (int)(i % granules);
@@ -181,7 +184,7 @@ int copy_cls_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t d
     GSL_REQUIRE(row_bytes % 16 == 0 && src_pitch_bytes % 16 == 0 && dst_pitch_bytes % 16 == 0, "copy_cls_rows: 16-byte granularity required");
     const int granules = (int)(row_bytes / 16);
     const int64_t total = (int64_t)B * granules;
-    gather_rows_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>((const uint4*)src, src_pitch_bytes / 16, (uint4*)dst, dst_pitch_bytes / 16, B, granules);
+    GSL_CHECK_CUDA(launch_pdl(gather_rows_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, s, (const uint4*)src, src_pitch_bytes / 16, (uint4*)dst, dst_pitch_bytes / 16, B, granules));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;

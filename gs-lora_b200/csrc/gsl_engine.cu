@@ -186,6 +186,7 @@ struct MergeJob {
     int R, C;
 };
 __global__ void __launch_bounds__(256) merge_weights_kernel(const uint8_t* __restrict__ jobs_raw, int r, float sc) {
+    pdl_prologue();
     __shared__ float tile[32][33];
     const MergeJob j = *reinterpret_cast<const MergeJob*>(jobs_raw + (size_t)blockIdx.z * 64);
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -217,7 +218,7 @@ int Engine::ensure_ffn_weights(int use_lora, cudaStream_t s) {
     const int D = cfg.dim, H = cfg.mlp_dim;
     const int big = H > D ? H : D;
     dim3 grid(big / 32, big / 32, 2 * cfg.depth);
-    merge_weights_kernel<<<grid, 256, 0, s>>>((const uint8_t*)merge_jobs_dev, cfg.lora_rank, use_lora ? cfg.lora_scaling : 0.f);
+    GSL_CHECK_CUDA(launch_pdl(merge_weights_kernel, dim3(grid), dim3(256), 0, s, (const uint8_t*)merge_jobs_dev, cfg.lora_rank, use_lora ? cfg.lora_scaling : 0.f));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     ffn_cache_mode = mode;
@@ -301,6 +302,7 @@ struct LoraPackPtrs {
     void* unused[4];
 };
 __global__ void lora_pack_kernel(const float* __restrict__ flat, const LoraPackPtrs* __restrict__ ptrs, int D, int H, int r, int per_block) {
+    pdl_prologue();
     const int l = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= per_block) return;
@@ -320,7 +322,7 @@ int Engine::refresh_lora(cudaStream_t s) {
     GSL_REQUIRE(params_bound, "bind_params first");
     const int per_block = (int)lora_block_elems();
     dim3 grid((per_block + 255) / 256, cfg.depth);
-    lora_pack_kernel<<<grid, 256, 0, s>>>(lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, per_block);
+    GSL_CHECK_CUDA(launch_pdl(lora_pack_kernel, dim3(grid), dim3(256), 0, s, lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, per_block));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     if (ffn_cache_mode == 1) ffn_cache_mode = -1;       // W + s B A is stale
@@ -543,6 +545,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
 // ------------------------------------------------------------------------------------------------ step-loss helpers
 __global__ void loss_sums_kernel(const float* __restrict__ ce, const int* __restrict__ correct, const float* __restrict__ kl, int n_remain, int B,
                                  float* __restrict__ sums) {
+    pdl_prologue();
     __shared__ float red[8][32];
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -563,7 +566,7 @@ __global__ void loss_sums_kernel(const float* __restrict__ ce, const int* __rest
 
 // sums[0..7] = sum CE remain, n remain, sum CE forget, n forget, hits remain, hits forget, sum KL remain, sum KL forget (kl may be null)
 int loss_sums(const float* ce, const int* correct, const float* kl, int n_remain, int B, float* sums, cudaStream_t s) {
-    loss_sums_kernel<<<1, 1024, 0, s>>>(ce, correct, kl, n_remain, B, sums);
+    GSL_CHECK_CUDA(launch_pdl(loss_sums_kernel, dim3(1), dim3(1024), 0, s, ce, correct, kl, n_remain, B, sums));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -572,6 +575,7 @@ int loss_sums(const float* ce, const int* correct, const float* kl, int n_remain
 // loss = CE_r + beta * relu(BND - CE_f)  (engine_cl.py:65-80,118-120): d/dlogits per sample
 __global__ void unlearn_ce_grad_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const float* __restrict__ sums,
                                        int n_remain_local, int B, int C, float beta, float BND, float* __restrict__ dlogits) {
+    pdl_prologue();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -596,7 +600,7 @@ __global__ void unlearn_ce_grad_kernel(const float* __restrict__ logits, const i
 int unlearn_ce_grad(const float* logits, const int64_t* labels, const float* sums, int n_remain_local, int B, int C, float beta, float BND,
                     float* dlogits, cudaStream_t s) {
     const int warps = 4;
-    unlearn_ce_grad_kernel<<<(B + warps - 1) / warps, warps * 32, 0, s>>>(logits, labels, sums, n_remain_local, B, C, beta, BND, dlogits);
+    GSL_CHECK_CUDA(launch_pdl(unlearn_ce_grad_kernel, dim3((B + warps - 1) / warps), dim3(warps * 32), 0, s, logits, labels, sums, n_remain_local, B, C, beta, BND, dlogits));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;

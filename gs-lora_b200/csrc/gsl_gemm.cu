@@ -166,6 +166,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_prologue();     // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail; global memory from here on
 
     const int num_clusters = gridDim.x / CG;
     const int cluster_id = blockIdx.x / CG;
@@ -526,10 +527,12 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     GSL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO0, tmO1, tmAux, p));
     GSL_COUNT_LAUNCH(1);
     return 0;

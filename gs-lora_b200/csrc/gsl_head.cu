@@ -26,6 +26,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(HeadArgs a) {
+    pdl_prologue();
     __shared__ float s_e[HEAD_MAX_D];
     __shared__ float s_logit[HEAD_MAX_C];
     __shared__ float red[HEAD_THREADS / 32];
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(HeadArgs a) {
 
 int head_fwd(const HeadArgs& a, cudaStream_t s) {
     GSL_REQUIRE(a.D <= HEAD_MAX_D && a.C <= HEAD_MAX_C, "head: D=%d C=%d exceed limits", a.D, a.C);
-    head_fwd_kernel<<<a.B, HEAD_THREADS, 0, s>>>(a);
+    GSL_CHECK_CUDA(launch_pdl(head_fwd_kernel, dim3(a.B), dim3(HEAD_THREADS), 0, s, a));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -95,6 +96,7 @@ int head_fwd(const HeadArgs& a, cudaStream_t s) {
 // bounded-forget gate relu(BND - CE_f) (engine_cl.py:78) never needs a host round trip.
 __global__ void ce_grad_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const float* __restrict__ coef_dev,
                                float scale, float* __restrict__ dlogits, int B, int C) {
+    pdl_prologue();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -113,13 +115,14 @@ __global__ void ce_grad_kernel(const float* __restrict__ logits, const int64_t* 
 
 int ce_grad(const float* logits, const int64_t* labels, const float* coef_dev, float scale, float* dlogits, int B, int C, cudaStream_t s) {
     const int warps = 4;
-    ce_grad_kernel<<<(B + warps - 1) / warps, warps * 32, 0, s>>>(logits, labels, coef_dev, scale, dlogits, B, C);
+    GSL_CHECK_CUDA(launch_pdl(ce_grad_kernel, dim3((B + warps - 1) / warps), dim3(warps * 32), 0, s, logits, labels, coef_dev, scale, dlogits, B, C));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 __global__ void __launch_bounds__(HEAD_THREADS) head_bwd_kernel(HeadBwdArgs a) {
+    pdl_prologue();
     __shared__ float s_de[HEAD_MAX_D];     // d ehat, then d e
     __shared__ float s_dc[HEAD_MAX_C];     // d cos[c] / ||W_c||
     __shared__ float red[HEAD_THREADS / 32];
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_bwd_kernel(HeadBwdArgs a) {
 
 int head_bwd(const HeadBwdArgs& a, cudaStream_t s) {
     GSL_REQUIRE(a.D <= HEAD_MAX_D && a.C <= HEAD_MAX_C, "head_bwd: D=%d C=%d exceed limits", a.D, a.C);
-    head_bwd_kernel<<<a.B, HEAD_THREADS, 0, s>>>(a);
+    GSL_CHECK_CUDA(launch_pdl(head_bwd_kernel, dim3(a.B), dim3(HEAD_THREADS), 0, s, a));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -215,6 +218,7 @@ __device__ __forceinline__ void proto_row_stats(const float* __restrict__ e, con
 }
 __global__ void prototype_kl_fwd_kernel(const float* __restrict__ emb, const int64_t* __restrict__ labels, const float* __restrict__ proto, int B, int D,
                                         float* __restrict__ kl) {
+    pdl_prologue();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= B) return;
     const float* e = emb + (int64_t)b * D;
@@ -233,6 +237,7 @@ __global__ void prototype_kl_fwd_kernel(const float* __restrict__ emb, const int
 __global__ void prototype_kl_grad_kernel(const float* __restrict__ emb, const int64_t* __restrict__ labels, const float* __restrict__ proto,
                                          const float* __restrict__ sums, int n_remain_local, int B, int D, float w_f, float w_r, float BND_pro,
                                          float* __restrict__ demb) {
+    pdl_prologue();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= B) return;
     float coef;
@@ -250,7 +255,7 @@ __global__ void prototype_kl_grad_kernel(const float* __restrict__ emb, const in
 }
 int prototype_kl_fwd(const float* emb, const int64_t* labels, const float* proto, int B, int D, float* kl, cudaStream_t s) {
     const int warps = 4;
-    prototype_kl_fwd_kernel<<<(B + warps - 1) / warps, warps * 32, 0, s>>>(emb, labels, proto, B, D, kl);
+    GSL_CHECK_CUDA(launch_pdl(prototype_kl_fwd_kernel, dim3((B + warps - 1) / warps), dim3(warps * 32), 0, s, emb, labels, proto, B, D, kl));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -258,7 +263,7 @@ int prototype_kl_fwd(const float* emb, const int64_t* labels, const float* proto
 int prototype_kl_grad(const float* emb, const int64_t* labels, const float* proto, const float* sums, int n_remain_local, int B, int D, float w_f,
                       float w_r, float BND_pro, float* demb, cudaStream_t s) {
     const int warps = 4;
-    prototype_kl_grad_kernel<<<(B + warps - 1) / warps, warps * 32, 0, s>>>(emb, labels, proto, sums, n_remain_local, B, D, w_f, w_r, BND_pro, demb);
+    GSL_CHECK_CUDA(launch_pdl(prototype_kl_grad_kernel, dim3((B + warps - 1) / warps), dim3(warps * 32), 0, s, emb, labels, proto, sums, n_remain_local, B, D, w_f, w_r, BND_pro, demb));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -21,6 +21,7 @@ struct PixelNorm { float mean[4]; float std[4]; int enabled; };
 template <typename T>
 __global__ void patchify_kernel(const T* __restrict__ img, __half* __restrict__ out, int64_t ld, int B, int C, int S,
                                 int patch, int order, int layout, PixelNorm nrm) {
+    pdl_prologue();
     const int w = S / patch;
     const int P = w * w;
     const int pd = C * patch * patch;
@@ -65,7 +66,7 @@ static int patchify_launch(const T* img, __half* out, int64_t ld, int B, int C, 
     int blocks = (int)((total + threads - 1) / threads);
     const int cap = device_sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    patchify_kernel<T><<<blocks, threads, 0, s>>>(img, out, ld, B, C, S, patch, order, layout, nrm);
+    GSL_CHECK_CUDA(launch_pdl(patchify_kernel<T>, dim3(blocks), dim3(threads), 0, s, img, out, ld, B, C, S, patch, order, layout, nrm));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ beta, float eps, __half* __restrict__ y,
                                                             int64_t ldy, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                             int64_t M) {
+    pdl_prologue();
     constexpr int D = VEC * 128;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -142,7 +144,7 @@ int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* 
     GSL_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "layernorm: leading dimensions must be multiples of 4");
     const int warps = 8;
     const int blocks = (int)((M + warps - 1) / warps);
-#define GSL_LN_CASE(V) case V: layernorm_fwd_kernel<V><<<blocks, warps * 32, 0, s>>>(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M); break;
+#define GSL_LN_CASE(V) case V: GSL_CHECK_CUDA(launch_pdl(layernorm_fwd_kernel<V>, dim3(blocks), dim3(warps * 32), 0, s, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M)); break;
     switch (D / 128) {
         GSL_LN_CASE(1) GSL_LN_CASE(2) GSL_LN_CASE(3) GSL_LN_CASE(4) GSL_LN_CASE(5) GSL_LN_CASE(6) GSL_LN_CASE(7) GSL_LN_CASE(8)
     }
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
                                                             const float* __restrict__ gamma, const float* __restrict__ dres, int64_t lddres,
                                                             float* __restrict__ dx, int64_t lddx, __half* __restrict__ dx16, int64_t lddx16,
                                                             int64_t M, uint32_t drop_thresh, uint32_t drop_seed, float drop_scale, int dres_period) {
+    pdl_prologue();
     constexpr int D = VEC * 128;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -236,8 +239,8 @@ int layernorm_bwd(const void* dy, int dy_is_fp16, int64_t lddy, const float* x, 
     const int warps = 8;
     const int blocks = (int)((M + warps - 1) / warps);
 #define GSL_LN_CASE(V) case V: \
-        if (dy_is_fp16) layernorm_bwd_kernel<V, true><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc, dres_period); \
-        else layernorm_bwd_kernel<V, false><<<blocks, warps * 32, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc, dres_period); \
+        if (dy_is_fp16) GSL_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<V, true>, dim3(blocks), dim3(warps * 32), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc, dres_period)); \
+        else GSL_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<V, false>, dim3(blocks), dim3(warps * 32), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx16, lddx16, M, dth, drop_seed, dsc, dres_period)); \
         break;
     switch (D / 128) {
         GSL_LN_CASE(1) GSL_LN_CASE(2) GSL_LN_CASE(3) GSL_LN_CASE(4) GSL_LN_CASE(5) GSL_LN_CASE(6) GSL_LN_CASE(7) GSL_LN_CASE(8)
@@ -263,6 +266,7 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
 template <int NT>   // NT n-tiles of 8 (r = 8 -> 1, r = 16 -> 2)
 __global__ void __launch_bounds__(128) lora_down_kernel(const __half* __restrict__ X, int64_t ldx, const __half* __restrict__ A, int64_t lda,
                                                         __half* __restrict__ out, int64_t ldo, int64_t M, int K) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int64_t row_base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 16;
@@ -336,8 +340,8 @@ int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __ha
     const int warps = 4;
     const int64_t groups = (M + 15) / 16;
     const int blocks = (int)((groups + warps - 1) / warps);
-    if (r == 8) lora_down_kernel<1><<<blocks, warps * 32, 0, s>>>(X, ldx, A16, lda, out, ldo, M, K);
-    else lora_down_kernel<2><<<blocks, warps * 32, 0, s>>>(X, ldx, A16, lda, out, ldo, M, K);
+    if (r == 8) GSL_CHECK_CUDA(launch_pdl(lora_down_kernel<1>, dim3(blocks), dim3(warps * 32), 0, s, X, ldx, A16, lda, out, ldo, M, K));
+    else GSL_CHECK_CUDA(launch_pdl(lora_down_kernel<2>, dim3(blocks), dim3(warps * 32), 0, s, X, ldx, A16, lda, out, ldo, M, K));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -362,6 +366,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 template <int R>
 __global__ void __launch_bounds__(SK_THREADS, 2) skinny_tn_partial_kernel(const __half* __restrict__ L, int64_t ldl, const __half* __restrict__ Rm, int64_t ldr,
                                                                          float* __restrict__ partial, int64_t M, int N, int rows_per_split) {
+    pdl_prologue();
     extern __shared__ __align__(128) uint8_t sk_smem[];
     const uint32_t sbase = smem_u32(sk_smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -452,6 +457,7 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_tn_partial_kernel(const 
 template <int R>
 __global__ void skinny_tn_reduce_kernel(const float* __restrict__ partial, int splits, int N, float scale, float* __restrict__ out, int64_t ldo,
                                         int transpose_out, int r_out, int accumulate) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * R) return;
     const int n = i / R, j = i % R;
@@ -494,14 +500,14 @@ int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float
         attr = true;
     }
     if (r == 8) {
-        skinny_tn_partial_kernel<8><<<grid, SK_THREADS, smem, s>>>(L, ldl, Rm, ldr, workspace, M, N, rows_per_split);
+        GSL_CHECK_CUDA(launch_pdl(skinny_tn_partial_kernel<8>, dim3(grid), dim3(SK_THREADS), smem, s, L, ldl, Rm, ldr, workspace, M, N, rows_per_split));
         GSL_COUNT_LAUNCH(1);
-        skinny_tn_reduce_kernel<8><<<(N * 8 + 255) / 256, 256, 0, s>>>(workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate);
+        GSL_CHECK_CUDA(launch_pdl(skinny_tn_reduce_kernel<8>, dim3((N * 8 + 255) / 256), dim3(256), 0, s, workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate));
         GSL_COUNT_LAUNCH(1);
     } else {
-        skinny_tn_partial_kernel<16><<<grid, SK_THREADS, smem, s>>>(L, ldl, Rm, ldr, workspace, M, N, rows_per_split);
+        GSL_CHECK_CUDA(launch_pdl(skinny_tn_partial_kernel<16>, dim3(grid), dim3(SK_THREADS), smem, s, L, ldl, Rm, ldr, workspace, M, N, rows_per_split));
         GSL_COUNT_LAUNCH(1);
-        skinny_tn_reduce_kernel<16><<<(N * 16 + 255) / 256, 256, 0, s>>>(workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate);
+        GSL_CHECK_CUDA(launch_pdl(skinny_tn_reduce_kernel<16>, dim3((N * 16 + 255) / 256), dim3(256), 0, s, workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate));
         GSL_COUNT_LAUNCH(1);
     }
     GSL_CHECK_CUDA(cudaGetLastError());
@@ -526,6 +532,7 @@ template <int NB, int STAGES>   // NB = 16-column blocks per warp (N = 256 * NB)
 __global__ void __launch_bounds__(SP_THREADS, 1) lora_side_kernel(const __half* __restrict__ L, int64_t ldl, const __half* __restrict__ P, int64_t ldp,
                                                                  __half* __restrict__ T, int64_t ldt, const __half* __restrict__ Rm, int64_t ldr,
                                                                  float* __restrict__ partial, int64_t M, int rows_per_cta) {
+    pdl_prologue();
     constexpr int N = 256 * NB, ROW_BYTES = 2 * N, CHUNKS = N / 8;          // 16-byte chunks per row
     constexpr int L_BYTES = SP_ROWS * ROW_BYTES, STAGE_BYTES = L_BYTES + SP_ROWS * 32;
     extern __shared__ __align__(128) uint8_t sp_smem[];
@@ -654,7 +661,7 @@ static int launch_lora_side(const __half* L, int64_t ldl, const __half* P16, int
         GSL_CHECK_CUDA(cudaFuncSetAttribute(lora_side_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    lora_side_kernel<NB, STAGES><<<ctas, SP_THREADS, smem, s>>>(L, ldl, P16, ldp, T, ldt, Rm, ldr, workspace, M, rows_per_cta);
+    GSL_CHECK_CUDA(launch_pdl(lora_side_kernel<NB, STAGES>, dim3(ctas), dim3(SP_THREADS), smem, s, L, ldl, P16, ldp, T, ldt, Rm, ldr, workspace, M, rows_per_cta));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -682,7 +689,7 @@ int lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __ha
     }
 #undef GSL_SP_CASE
     if (rc) return rc;
-    skinny_tn_reduce_kernel<8><<<(N * 8 + 255) / 256, 256, 0, s>>>(workspace, ctas, N, scale, out, ldo, transpose_out, r, accumulate);
+    GSL_CHECK_CUDA(launch_pdl(skinny_tn_reduce_kernel<8>, dim3((N * 8 + 255) / 256), dim3(256), 0, s, workspace, ctas, N, scale, out, ldo, transpose_out, r, accumulate));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
