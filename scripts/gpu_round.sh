@@ -21,7 +21,7 @@ for w in $WHAT; do
       REPS=10 timeout 300 python scripts/dev_prof.py > $OUT/${TAG}_kernels.log 2>&1; cat $OUT/${TAG}_kernels.log ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_launches.csv \
-        python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1; tail -2 $OUT/${TAG}_launches.log ;;
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-u8-leg > $OUT/${TAG}_launches.log 2>&1; tail -2 $OUT/${TAG}_launches.log ;;
     full)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tcgen05|attention_|lora_side' -c 16 -f \
         -o $OUT/${TAG}_full python scripts/dev_prof.py gelu res f16 attn skinny > $OUT/${TAG}_full.log 2>&1; tail -3 $OUT/${TAG}_full.log ;;
