@@ -345,14 +345,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 uint32_t pk0[CW / 2], pk1[CW / 2];      // packed half2 outputs (fp16 epilogues)
                 if (EPI == EPI_GELU) {         // out1 = Dropout(gelu(h)), out0 = d out1 / d h   (h = acc + bias never leaves the SM)
-                    const uint32_t thr2 = p.drop_thresh | (p.drop_thresh << 16);
+                    // Two branch-free loops: a per-pair `if (drop_thresh)` puts every pair in its own basic block and the rcp -> polynomial
+                    // -> ex2 -> combine chains (11 dependent steps) of the 16 pairs run strictly one after the other (SASS of round 1's
+                    // visit n: stall_wait dominated the epilogue).  In one block ptxas interleaves independent pairs.
 #pragma unroll
                     for (int j = 0; j < CW / 2; ++j) {
                         float2 g, gp;
                         gelu_pair(v[j], p.gelu, g, gp);
                         pk0[j] = pack_half2(gp.x, gp.y);
                         pk1[j] = pack_half2(g.x, g.y);
-                        if (p.drop_thresh) {
+                    }
+                    if (p.drop_thresh) {
+                        const uint32_t thr2 = p.drop_thresh | (p.drop_thresh << 16);
+#pragma unroll
+                        for (int j = 0; j < CW / 2; ++j) {
                             const uint32_t keep = drop_keep_mask2(e0 + 2 * j, p.drop_seed, thr2);
                             pk0[j] &= keep;
                             pk1[j] &= keep;
