@@ -366,7 +366,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = 96
+    B = args.ref_batch
     steps = max(1, min(args.steps, 3))
     cb = cpu_baseline(sample_batch=B, steps=steps)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
@@ -386,6 +386,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="p8s8_bs512", choices=sorted(WORKLOADS))
     ap.add_argument("--no-u8-leg", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=96, help="--impl reference: images per stream of the bounded CPU sample")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "gslora":
         args.warmup = 3

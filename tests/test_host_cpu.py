@@ -179,3 +179,27 @@ def test_driver_import_lines_resolve_on_the_overlay():
     if not any(os.path.isfile(os.path.join(p, "baselines", "LIRFtrain.py")) for p in sys.path if p):
         with pytest.raises(NotImplementedError):
             engine_cl.get_reg_loss()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path via the oracle port) prints ONE JSON line with the contract's keys; a tiny
+    sample keeps this test to seconds (the driver's run uses the default 96 + 96 images per step)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-batch", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"] == "unlearn-step images/sec ViT-P8S8 112px bs512" and d["config"]["workload"] == "p8s8_bs512"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # non-zero ranks of a torchrun launch exit silently
+    env = dict(os.environ, RANK="1")
+    out1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--ref-batch", "2"],
+                          capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""
