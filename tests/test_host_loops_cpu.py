@@ -1,0 +1,138 @@
+"""Host-side logic of the drop-in loops on CPU (no GPU, no kernels): the engine step is replaced by a recording fake so that what is
+checked is exactly what this repo adds around it -- loader pairing / recycling (engine_cl.py:51-58,226-231; engine.py:53-57), the meters'
+arithmetic (engine_cl.py:68-121), the ALPHA_EPOCH gate (engine.py:82-90), display resets, the return tuple, and the scalar algebra of
+StepResult (what the reference reads with `.item()`)."""
+import types
+
+import pytest
+import torch
+
+import engine
+import engine_cl
+from engine_cl import AverageMeter, StepResult
+
+
+class _FakeEvent:
+    def synchronize(self):
+        pass
+
+
+def _result(ce_r, n_r, ce_f, n_f, hit_r, hit_f, kl_r, kl_f, structure, **consts):
+    c = dict(beta=0.15, alpha=1e-2, BND=105.0, BND_pro=0.0, pwf=0.0, pwr=0.0, use_prototype=False)
+    c.update(consts)
+    host = torch.tensor([ce_r * n_r, n_r, ce_f * n_f, n_f, hit_r, hit_f, kl_r * n_r, kl_f * n_f, structure], dtype=torch.float32)
+    return StepResult(host, _FakeEvent(), 9, c)
+
+
+def test_step_result_reproduces_the_reference_scalars():
+    r = _result(2.0, 4, 100.0, 3, 3, 1, 0.0, 0.0, 7.5)
+    assert r["loss_remain"] == pytest.approx(2.0) and r["ce_forget"] == pytest.approx(100.0)
+    assert r["loss_forget"] == pytest.approx(5.0)                         # relu(BND - CE_f), engine_cl.py:78
+    assert r["top1_remain"] == pytest.approx(75.0) and r["top1_forget"] == pytest.approx(100.0 / 3)
+    assert r["total"] == pytest.approx(0.15 * 5.0 + 2.0 + 1e-2 * 7.5)    # engine_cl.py:118-121
+    closed = _result(2.0, 4, 110.0, 3, 0, 0, 0.0, 0.0, 1.0)               # CE_f above the bound: the forget term is switched off
+    assert closed["loss_forget"] == 0.0 and closed["total"] == pytest.approx(2.0 + 1e-2)
+    proto = _result(1.0, 2, 50.0, 2, 0, 0, 0.25, 3.0, 0.0, use_prototype=True, BND_pro=18.0, pwf=0.5, pwr=2.0)
+    assert proto["proto_forget"] == pytest.approx(3.0) and proto["proto_remain"] == pytest.approx(0.25)
+    assert proto["total"] == pytest.approx(0.15 * 55.0 + 1.0 + 0.5 * (18.0 - 3.0) + 2.0 * 0.25)      # engine_cl.py:97-101
+    empty = _result(0.0, 0, 0.0, 0, 0, 0, 0.0, 0.0, 0.0)                  # a rank with an empty shard divides by max(n, 1)
+    assert empty["loss_remain"] == 0.0 and empty["top1_forget"] == 0.0
+
+
+class _Recorder:
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, model, xr, yr, xf, yf, **kw):
+        self.calls.append((int(xr[0, 0]), int(xf[0, 0]), xr.shape[0], xf.shape[0], kw))
+        return _result(1.0, xr.shape[0], 100.0, xf.shape[0], 1, 0, 0.0, 0.0, 4.0, beta=kw["beta"], alpha=kw["alpha"], BND=kw["BND"])
+
+
+class _CpuPrefetcher:
+    def __init__(self, loader, device):
+        self.it = iter(loader)
+
+    def next(self):
+        return next(self.it, (None, None))
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    rec = _Recorder()
+    for mod in (engine_cl, engine):
+        monkeypatch.setattr(mod, "unlearn_step_async", rec)
+    monkeypatch.setattr(engine_cl, "_Prefetcher", _CpuPrefetcher)
+    monkeypatch.setattr(engine_cl, "engine_fresh_optimizer", lambda m, o: False)
+    monkeypatch.setattr(engine_cl, "sync_optimizer_state", lambda m, o: None)
+    return rec
+
+
+def _loader(tag, n, bs):
+    """batches whose first element identifies them: value = tag + index"""
+    return [(torch.full((bs, 1), float(tag + i)), torch.zeros(bs, dtype=torch.long)) for i in range(n)]
+
+
+def _meters(n=8):
+    return [AverageMeter() for _ in range(n)]
+
+
+def test_engine_cl_epoch_pairs_remain_batches_with_a_recycled_forget_loader(fake, capsys):
+    remain, forget = _loader(100, 7, 4), _loader(200, 3, 2)
+    lf, lr, lt, ls, tf, tr, lpf, lpr = _meters()
+    ret = engine_cl.train_one_epoch(torch.nn.Linear(1, 1), forget, remain, "cpu", torch.nn.CrossEntropyLoss(), None, 0, lf, lr, lt, ls, tf, tr,
+                                    0.15, 1e-2, 105.0, 0, None, None, 0.0, 0.0, {}, 3, False, None, 0.0, 0.0, lpf, lpr)
+    assert [(c[0], c[1]) for c in fake.calls] == [(100, 200), (101, 201), (102, 202), (103, 200), (104, 201), (105, 202), (106, 200)]
+    assert ret[0] == 7 and len(ret) == 10 and ret[1] == 0.0
+    # the display at batch 5 (batch index 4) printed the running averages and reset the meters: the returned ones hold steps 5 and 6
+    out = capsys.readouterr().out
+    assert "Task 3 Epoch 1 Batch 5" in out
+    losses_forget, losses_remain, losses_total, losses_structure = ret[2], ret[3], ret[6], ret[7]
+    assert losses_remain.count == 8 and losses_forget.count == 4         # 2 steps x 4 remain / 2 forget images
+    assert losses_forget.avg == pytest.approx(0.15 * 5.0) and losses_structure.avg == pytest.approx(1e-2 * 4.0)
+    assert losses_total.avg == pytest.approx(0.15 * 5.0 + 1.0 + 1e-2 * 4.0)
+
+
+@pytest.mark.parametrize("few_shot", [True, False])
+def test_engine_py_epoch_swaps_the_driving_loader_only_for_few_shot(fake, few_shot):
+    remain, forget = _loader(100, 2, 4), _loader(200, 5, 3)               # forget loader is the longer one
+    m = _meters()
+    cfg = {"few_shot": few_shot, "ALPHA_EPOCH": 0, "GROUP_TYPE": "lora", "GROUP_POS": "FFN"}
+    ret = engine.train_one_epoch(torch.nn.Linear(1, 1), forget, remain, "cpu", torch.nn.CrossEntropyLoss(), None, 0, m[0], m[1], m[2], m[3], m[4],
+                                 m[5], 0.15, 1e-2, 105.0, 0, None, None, 0.0, 0.0, cfg, losses_prototype_forget=m[6], losses_prototype_remain=m[7])
+    pairs = [(c[0], c[1]) for c in fake.calls]
+    if few_shot:        # engine.py:53-57: the forget loader drives, remain is prefetched and recycled
+        assert pairs == [(100, 200), (101, 201), (100, 202), (101, 203), (100, 204)]
+    else:               # engine.py:236-: remain drives, forget recycled
+        assert pairs == [(100, 200), (101, 201)]
+    assert ret[0] == len(pairs)
+    assert all(c[4]["group_type"] == "lora" for c in fake.calls)
+    assert all(c[2] == 4 and c[3] == 3 for c in fake.calls)               # remain / forget tensors never swap roles
+
+
+def test_engine_py_alpha_epoch_gate_and_unsupported_group_pos(fake):
+    remain, forget = _loader(100, 2, 4), _loader(200, 2, 3)
+    m = _meters()
+    cfg = {"few_shot": False, "ALPHA_EPOCH": 3, "GROUP_TYPE": "block", "GROUP_POS": "FFN"}
+    args = (torch.nn.Linear(1, 1), forget, remain, "cpu", torch.nn.CrossEntropyLoss(), None)
+    engine.train_one_epoch(*args, 2, m[0], m[1], m[2], m[3], m[4], m[5], 0.15, 1e-2, 105.0, 0, None, None, 0.0, 0.0, cfg)
+    assert all(c[4]["alpha"] == 0.0 for c in fake.calls)                  # epoch 2 < ALPHA_EPOCH 3: structure term off (engine.py:82-90)
+    fake.calls.clear()
+    ret = engine.train_one_epoch(*args, 3, *_meters(6), 0.15, 1e-2, 105.0, 0, None, None, 0.0, 0.0, cfg)
+    assert all(c[4]["alpha"] == 1e-2 for c in fake.calls)
+    assert ret[7].avg == pytest.approx(1e-2 * 4.0)
+    with pytest.raises(NotImplementedError):
+        engine.train_one_epoch(*args, 0, *_meters(6), 0.15, 1e-2, 105.0, 0, None, None, 0.0, 0.0, dict(cfg, GROUP_POS="Attention"))
+
+
+def test_prototype_loss_torch_form_matches_the_reference_expression():
+    """engine_cl.get_prototype_loss (engine_cl.py:571-603): dict of per-class CPU tensors or a [C, D] table, 'kl' and 'l2'."""
+    g = torch.Generator().manual_seed(0)
+    emb = torch.randn(6, 16, generator=g)
+    labels = torch.tensor([0, 2, 2, 1, 0, 1])
+    protos = {k: torch.randn(16, generator=g) for k in range(3)}
+    stacked = torch.stack([protos[int(l)] for l in labels])
+    want = torch.nn.functional.kl_div(torch.log_softmax(emb, 1), torch.log_softmax(stacked, 1), reduction="batchmean", log_target=True)
+    assert torch.allclose(engine_cl.get_prototype_loss(emb, labels, protos), want)
+    table = torch.stack([protos[k] for k in range(3)])
+    assert torch.allclose(engine_cl.get_prototype_loss(emb, labels, table), want)
+    assert torch.allclose(engine_cl.get_prototype_loss(emb, labels, protos, distance="l2"), torch.mean((emb - stacked) ** 2))
