@@ -40,11 +40,8 @@ def test_patchify_u8_equals_host_totensor_normalize_bitwise(F, B, C, S, patch, o
     host-transformed image (what the reference's loader hands to the model)."""
     g = torch.Generator().manual_seed(B * 131 + S)
     u8 = torch.randint(0, 256, (B, C, S, S), dtype=torch.uint8, generator=g)
-    ref = u8.float().div(255)                                           # transforms.ToTensor
-    mean = std = None
-    if norm is not None:
-        mean, std = norm[0][:C], norm[1][:C]
-        ref = ref.sub(torch.tensor(mean).view(1, C, 1, 1)).div(torch.tensor(std).view(1, C, 1, 1))      # transforms.Normalize
+    mean, std = (norm[0][:C], norm[1][:C]) if norm is not None else (None, None)
+    ref = O.pixels_to_tensor(u8, mean, std)        # transforms.ToTensor [+ Normalize]; pinned bit-equal to torchvision in test_oracle_golden.py
     P = (S // patch) ** 2
     pd = C * patch * patch
     out_ref = torch.full((B * (P + 1), pd), 7.0, dtype=torch.half, device="cuda")

@@ -78,3 +78,37 @@ def test_flop_table_matches_baseline_md():
     f = O.flops_per_image(O.P8S8)
     assert abs(f["fwd"] / 1e9 - 8.049) < 0.01
     assert abs(f["bwd"] / 1e9 - 7.599) < 0.01
+
+
+def test_class_prototypes_match_the_unmodified_reference_function(golden_dir):
+    """util.utils.calculate_prototypes of the UNMODIFIED reference (tests/golden/make_golden_prototypes.py) vs the oracle's restatement."""
+    g = torch.load(os.path.join(golden_dir, "tiny6_prototypes.pt"), weights_only=False)
+    cfg = O.VitConfig(**g["cfg"])
+    sd = O.init_state_dict(cfg, seed=g["seed"])
+    for k, v in g["state_dict_checksum"].items():
+        assert abs(float(sd[k].double().abs().sum()) - v) <= 1e-9 * max(1.0, abs(v)), f"weight regen drift: {k}"
+    got = O.class_prototypes(sd, cfg, g["images"], g["labels"], batch_size=g["batch_size"])
+    assert sorted(got) == sorted(g["prototypes"]) == sorted(set(g["labels"].tolist()))      # only the classes that occur
+    for k, want in g["prototypes"].items():
+        assert got[k].shape == want.shape == (cfg.dim,)
+        assert rel(got[k], want) < 2e-6, k
+    # the per-class mean does not depend on how the dataset was batched (up to fp32 matmul blocking)
+    other = O.class_prototypes(sd, cfg, g["images"], g["labels"], batch_size=5)
+    for k in got:
+        assert rel(other[k], got[k]) < 2e-6
+
+
+def test_pixels_to_tensor_is_torchvisions_totensor_normalize():
+    """oracle.pixels_to_tensor vs torchvision's own ToTensor / Normalize on PIL images (the reference's loader transforms,
+    train/train_own_forget_cl.py:130-146): bit-equal."""
+    import numpy as np
+    from PIL import Image
+    import torchvision.transforms as T
+    rng = np.random.default_rng(0)
+    arrs = [rng.integers(0, 256, (24, 24, 3), dtype=np.uint8) for _ in range(3)]
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    u8 = torch.stack([torch.from_numpy(a).permute(2, 0, 1) for a in arrs])
+    plain = torch.stack([T.ToTensor()(Image.fromarray(a)) for a in arrs])
+    normed = torch.stack([T.Compose([T.ToTensor(), T.Normalize(mean, std)])(Image.fromarray(a)) for a in arrs])
+    assert torch.equal(O.pixels_to_tensor(u8), plain)
+    assert torch.equal(O.pixels_to_tensor(u8, mean, std), normed)
