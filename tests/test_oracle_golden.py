@@ -112,3 +112,27 @@ def test_pixels_to_tensor_is_torchvisions_totensor_normalize():
     normed = torch.stack([T.Compose([T.ToTensor(), T.Normalize(mean, std)])(Image.fromarray(a)) for a in arrs])
     assert torch.equal(O.pixels_to_tensor(u8), plain)
     assert torch.equal(O.pixels_to_tensor(u8, mean, std), normed)
+
+
+@pytest.mark.parametrize("depth", [6, 3])
+def test_groupings_match_the_unmodified_reference_engine_py_and_cal_norm(golden_dir, depth):
+    """engine.get_structure_loss(group_type) and util.cal_norm.get_norm_of_lora(group_type) of the UNMODIFIED reference
+    (tests/golden/make_golden_groups.py) vs the oracle's group-lasso value and vs the group ORDER the drop-in util.cal_norm reports in."""
+    import sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gs-lora_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    from util import cal_norm
+    rec = torch.load(os.path.join(golden_dir, "tiny_groupings.pt"), weights_only=False)[f"depth{depth}"]
+    cfg = O.VitConfig(**rec["cfg"])
+    sd = O.init_state_dict(cfg, seed=rec["seed"])
+    blocks = O.lora_names(cfg)                       # per block [fc1.A, fc1.B, fc2.A, fc2.B] = the engine's flat tensor order
+    for gt in ("block", "lora", "matrix"):
+        assert abs(float(O.structure_loss(sd, cfg, gt)) - rec["structure"][gt]) < 1e-5 * rec["structure"][gt], gt
+        groups = cal_norm._ffn_groups(depth, gt)     # [(block, which)] per reported group
+        for typ, fn in (("L2", lambda t: t.norm(p=2)), ("L1", lambda t: t.abs().sum())):
+            got = [float(sum(fn(sd[blocks[i][w]]) for i, w in grp)) for grp in groups]
+            want = rec["norms"][f"{gt}_{typ}"]
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert abs(a - b) < 1e-5 * abs(b), (gt, typ)
