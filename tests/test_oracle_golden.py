@@ -136,3 +136,34 @@ def test_groupings_match_the_unmodified_reference_engine_py_and_cal_norm(golden_
             assert len(got) == len(want)
             for a, b in zip(got, want):
                 assert abs(a - b) < 1e-5 * abs(b), (gt, typ)
+
+
+def test_torchvision_family_reference_is_plain_torchvision_plus_loralib(golden_dir):
+    """The GPU parity tests of configs 4 / 5 (tests/test_engine_gpu.py::_tv_pair) use torchvision's VisionTransformer + the loralib restatement,
+    FP32 eager, as their reference.  This pins that construction against the UNMODIFIED reference wrapper (ModifiedViT + replace_ffn_with_lora,
+    tests/golden/make_golden_tv.py): same state_dict keys, logits, cls embedding (= encoder output row 0, after encoder.ln) and LoRA gradients."""
+    from torchvision.models.vision_transformer import VisionTransformer
+    from oracle import loralib_restated as olora
+    g = torch.load(os.path.join(golden_dir, "tv_small_b3.pt"), weights_only=False)
+    sh = g["shape"]
+    ref = VisionTransformer(**sh)
+    for blk in ref.encoder.layers.children():
+        blk.mlp[0] = olora.Linear(sh["hidden_dim"], sh["mlp_dim"], r=g["rank"])
+        blk.mlp[3] = olora.Linear(sh["mlp_dim"], sh["hidden_dim"], r=g["rank"])
+    assert set(ref.state_dict().keys()) == set(g["state_dict"].keys())
+    ref.load_state_dict(g["state_dict"], strict=True)
+    olora.mark_only_lora_as_trainable(ref)
+    ref.train()
+    names = [n for n, p in ref.named_parameters() if p.requires_grad]
+    assert names == g["trainable"] and len(names) == 4 * sh["num_layers"]
+    # torchvision's forward up to the head, keeping the cls row the reference returns as the embedding (modified_VIT.py:26-37)
+    x = ref._process_input(g["x"])
+    x = torch.cat([ref.class_token.expand(x.shape[0], -1, -1), x], dim=1)
+    emb = ref.encoder(x)[:, 0]
+    logits = ref.heads(emb)
+    assert torch.equal(logits, ref(g["x"]))                       # == torchvision's own forward()
+    loss = torch.nn.functional.cross_entropy(logits, g["y"])
+    loss.backward()
+    assert rel(logits, g["logits"]) < 1e-6 and rel(emb, g["emb"]) < 1e-6 and abs(float(loss) - g["loss"]) < 1e-6
+    for n in names:
+        assert rel(ref.get_parameter(n).grad, g["grads"][n]) < 1e-5, n
