@@ -311,7 +311,8 @@ def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criteri
         losses_forget.update(beta * out["loss_forget"], nf)
         top1_forget.update(out["top1_forget"], nf)
         losses_structure.update(alpha * out["structure"], nr)
-        losses_prototype_forget.update(prototype_weight_forget * max(cfg.get("BND_pro", 0.0) - out["proto_forget"], 0.0) if use_prototype else 0.0, nr)
+        # the reference updates this meter unconditionally (engine_cl.py:103-108): without prototypes KL_f is 0 and the logged value is w_f * BND_pro
+        losses_prototype_forget.update(prototype_weight_forget * max(cfg.get("BND_pro", 0.0) - out["proto_forget"], 0.0), nr)
         losses_prototype_remain.update(out["proto_remain"] * prototype_weight_remain, nr)
         losses_total.update(out["total"], nr)
 

@@ -136,3 +136,63 @@ def test_prototype_loss_torch_form_matches_the_reference_expression():
     table = torch.stack([protos[k] for k in range(3)])
     assert torch.allclose(engine_cl.get_prototype_loss(emb, labels, table), want)
     assert torch.allclose(engine_cl.get_prototype_loss(emb, labels, protos, distance="l2"), torch.mean((emb - stacked) ** 2))
+
+
+# ------------------------------------------------------------------------------------------------ against the UNMODIFIED reference epoch
+class _OracleStep:
+    """unlearn_step_async stand-in that executes the step with the CPU oracle (so the arithmetic is the reference's) -- what is under test is
+    engine_cl.train_one_epoch's own host logic around it, against a golden recorded from the unmodified reference loop."""
+
+    def __init__(self, sd, cfg, hp, prototypes):
+        from oracle import vit_oracle as O
+        self.O, self.sd, self.cfg, self.hp, self.protos, self.state = O, sd, cfg, hp, prototypes, {}
+
+    def __call__(self, model, xr, yr, xf, yf, *, beta, alpha, BND, optimizer=None, use_prototype=False, prototype_dict=None,
+                 prototype_weight_forget=0.0, prototype_weight_remain=0.0, BND_pro=0.0, **kw):
+        pk = dict(prototypes=self.protos, w_pf=prototype_weight_forget, w_pr=prototype_weight_remain, BND_pro=BND_pro) if use_prototype else {}
+        out, _ = self.O.unlearn_step(self.sd, self.cfg, self.state, xr, yr, xf, yf, lr=self.hp["lr"], wd=self.hp["wd"], beta=beta, alpha=alpha,
+                                     BND=BND, **pk)
+        vals = dict(loss_remain=float(out["loss_remain"]), ce_forget=float(out["ce_forget"]), loss_forget=float(out["loss_forget"]),
+                    structure=float(out["structure"]), top1_remain=float(out["top1_r"]), top1_forget=float(out["top1_f"]),
+                    proto_forget=float(out["proto_forget"]), proto_remain=float(out["proto_remain"]), total=float(out["total"]))
+        return types.SimpleNamespace(wait=lambda: vals)
+
+
+@pytest.mark.parametrize("case", ["plain", "proto"])
+def test_epoch_loop_reproduces_the_unmodified_reference_epoch(golden_dir, monkeypatch, case):
+    """tests/golden/make_golden_epoch.py ran the UNMODIFIED engine_cl.train_one_epoch (7 remain batches, 3 recycled forget batches, display reset
+    at batch 5, with and without the prototype term).  The drop-in's loop, stepping through the oracle, must return the same batch counter,
+    the same eight meters (val / avg / sum / count) and the same LoRA parameters."""
+    import os
+    from oracle import vit_oracle as O
+    g = torch.load(os.path.join(golden_dir, "tiny6_epoch.pt"), weights_only=False)[case]
+    cfg = O.VitConfig(**g["cfg"])
+    sd = O.init_state_dict(cfg, seed=g["seed"])
+    for k, v in g["state_dict_checksum"].items():
+        assert abs(float(sd[k].double().abs().sum()) - v) <= 1e-9 * max(1.0, abs(v)), f"weight regen drift: {k}"
+    gen = torch.Generator().manual_seed(g["loader_seed"])
+    S = cfg.image_size
+    remain = [(torch.rand(4, 3, S, S, generator=gen), torch.randint(0, cfg.num_class, (4,), generator=gen)) for _ in range(g["n_remain"])]
+    forget = [(torch.rand(3, 3, S, S, generator=gen), torch.randint(0, cfg.num_class, (3,), generator=gen)) for _ in range(g["n_forget"])]
+    hp = g["hp"]
+    step = _OracleStep(sd, cfg, hp, g["prototypes"])
+    monkeypatch.setattr(engine_cl, "unlearn_step_async", step)
+    monkeypatch.setattr(engine_cl, "_Prefetcher", _CpuPrefetcher)
+    monkeypatch.setattr(engine_cl, "engine_fresh_optimizer", lambda m, o: False)
+    monkeypatch.setattr(engine_cl, "sync_optimizer_state", lambda m, o: None)
+    lf, lr, lt, ls, tf, tr, lpf, lpr = _meters()
+    proto_dict = {i: g["prototypes"][i] for i in range(cfg.num_class)}
+    ret = engine_cl.train_one_epoch(torch.nn.Linear(1, 1), forget, remain, "cpu", torch.nn.CrossEntropyLoss(), None, 0, lf, lr, lt, ls, tf, tr,
+                                    hp["beta"], hp["alpha"], hp["BND"], 0, None, None, 0.0, 0.0, {"BND_pro": hp["BND_pro"]}, 2, g["use_proto"], proto_dict,
+                                    hp["w_pf"], hp["w_pr"], lpf, lpr)
+    assert ret[0] == g["batch"] and ret[1] == g["highest_H_mean"]
+    names = ["losses_forget", "losses_remain", "top1_forget", "top1_remain", "losses_total", "losses_structure", "losses_prototype_forget",
+             "losses_prototype_remain"]
+    for n, meter in zip(names, ret[2:]):
+        want = g["meters"][n]
+        assert meter.count == want["count"], n
+        for field in ("val", "avg", "sum"):
+            assert getattr(meter, field) == pytest.approx(want[field], rel=2e-4, abs=1e-6), (n, field)
+    for n in O.lora_param_list(cfg):
+        a, b = sd[n], g["params_after"][n]
+        assert float((a.double() - b.double()).norm() / b.double().norm()) < 1e-3, n
