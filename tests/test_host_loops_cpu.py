@@ -150,6 +150,8 @@ class _OracleStep:
     def __call__(self, model, xr, yr, xf, yf, *, beta, alpha, BND, optimizer=None, use_prototype=False, prototype_dict=None,
                  prototype_weight_forget=0.0, prototype_weight_remain=0.0, BND_pro=0.0, **kw):
         pk = dict(prototypes=self.protos, w_pf=prototype_weight_forget, w_pr=prototype_weight_remain, BND_pro=BND_pro) if use_prototype else {}
+        if "group_type" in kw:
+            pk["group_type"] = kw["group_type"]
         out, _ = self.O.unlearn_step(self.sd, self.cfg, self.state, xr, yr, xf, yf, lr=self.hp["lr"], wd=self.hp["wd"], beta=beta, alpha=alpha,
                                      BND=BND, **pk)
         vals = dict(loss_remain=float(out["loss_remain"]), ce_forget=float(out["ce_forget"]), loss_forget=float(out["loss_forget"]),
@@ -185,6 +187,46 @@ def test_epoch_loop_reproduces_the_unmodified_reference_epoch(golden_dir, monkey
     ret = engine_cl.train_one_epoch(torch.nn.Linear(1, 1), forget, remain, "cpu", torch.nn.CrossEntropyLoss(), None, 0, lf, lr, lt, ls, tf, tr,
                                     hp["beta"], hp["alpha"], hp["BND"], 0, None, None, 0.0, 0.0, {"BND_pro": hp["BND_pro"]}, 2, g["use_proto"], proto_dict,
                                     hp["w_pf"], hp["w_pr"], lpf, lpr)
+    assert ret[0] == g["batch"] and ret[1] == g["highest_H_mean"]
+    names = ["losses_forget", "losses_remain", "top1_forget", "top1_remain", "losses_total", "losses_structure", "losses_prototype_forget",
+             "losses_prototype_remain"]
+    for n, meter in zip(names, ret[2:]):
+        want = g["meters"][n]
+        assert meter.count == want["count"], n
+        for field in ("val", "avg", "sum"):
+            assert getattr(meter, field) == pytest.approx(want[field], rel=2e-4, abs=1e-6), (n, field)
+    for n in O.lora_param_list(cfg):
+        a, b = sd[n], g["params_after"][n]
+        assert float((a.double() - b.double()).norm() / b.double().norm()) < 1e-3, n
+
+
+@pytest.mark.parametrize("case", ["few_shot_lora", "gated_matrix", "open_block"])
+def test_single_step_twin_reproduces_the_unmodified_reference_engine_py_epoch(golden_dir, monkeypatch, case):
+    """tests/golden/make_golden_epoch_single.py ran the UNMODIFIED engine.train_one_epoch: the few-shot branch (forget loader drives, remain
+    recycled, GROUP_TYPE lora), the ordinary branch with the structure term gated off by ALPHA_EPOCH (GROUP_TYPE matrix), and the ordinary
+    branch with a longer forget loader but few_shot off at epoch == ALPHA_EPOCH (GROUP_TYPE block).  gs-lora_b200/engine.py, stepping through
+    the oracle, must return the same batch counter, meters and LoRA parameters."""
+    import os
+    from oracle import vit_oracle as O
+    g = torch.load(os.path.join(golden_dir, "tiny3_epoch_single.pt"), weights_only=False)[case]
+    cfg = O.VitConfig(**g["cfg"])
+    sd = O.init_state_dict(cfg, seed=g["seed"])
+    for k, v in g["state_dict_checksum"].items():
+        assert abs(float(sd[k].double().abs().sum()) - v) <= 1e-9 * max(1.0, abs(v)), f"weight regen drift: {k}"
+    gen = torch.Generator().manual_seed(g["loader_seed"])
+    S = cfg.image_size
+    remain = [(torch.rand(4, 3, S, S, generator=gen), torch.randint(0, cfg.num_class, (4,), generator=gen)) for _ in range(g["n_remain"])]
+    forget = [(torch.rand(3, 3, S, S, generator=gen), torch.randint(0, cfg.num_class, (3,), generator=gen)) for _ in range(g["n_forget"])]
+    hp = g["hp"]
+    step = _OracleStep(sd, cfg, hp, None)
+    monkeypatch.setattr(engine, "unlearn_step_async", step)
+    monkeypatch.setattr(engine_cl, "_Prefetcher", _CpuPrefetcher)
+    monkeypatch.setattr(engine_cl, "engine_fresh_optimizer", lambda m, o: False)
+    monkeypatch.setattr(engine_cl, "sync_optimizer_state", lambda m, o: None)
+    m = _meters()
+    ret = engine.train_one_epoch(torch.nn.Linear(1, 1), forget, remain, "cpu", torch.nn.CrossEntropyLoss(), None, g["epoch"], m[0], m[1], m[2], m[3],
+                                 m[4], m[5], hp["beta"], hp["alpha"], hp["BND"], 0, None, None, 0.0, 0.0, g["run_cfg"],
+                                 losses_prototype_forget=m[6], losses_prototype_remain=m[7])
     assert ret[0] == g["batch"] and ret[1] == g["highest_H_mean"]
     names = ["losses_forget", "losses_remain", "top1_forget", "top1_remain", "losses_total", "losses_structure", "losses_prototype_forget",
              "losses_prototype_remain"]
