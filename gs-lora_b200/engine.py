@@ -153,16 +153,12 @@ def evaluate(model, testloader_forget, testloader_remain, device, batch, epoch, 
 
 
 def _merged_state_dict(m):
-    """state_dict of `copy.deepcopy(model).eval()` without the copy: loralib's merge (W + B A * scaling) applied to the FFN weights of a
-    cloned dict; the training model itself stays un-merged."""
+    """state_dict of `copy.deepcopy(model).eval()` without the copy: loralib's merge (W + B A * scaling, loralib Linear.train(False)) applied to
+    the weights of every un-merged LoRA layer in a cloned dict; the training model itself stays un-merged."""
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    if m._merged():
-        return sd
-    names = {id(p): n for n, p in m.named_parameters()}
-    for pair in m.lora_layers():
-        for lin in pair:
-            if lin.r > 0:
-                sd[names[id(lin.weight)]] += (lin.lora_B.detach() @ lin.lora_A.detach()) * lin.scaling
+    for name, mod in m.named_modules():
+        if getattr(mod, "r", 0) > 0 and hasattr(mod, "lora_A") and hasattr(mod, "lora_B") and not getattr(mod, "merged", False):
+            sd[(name + "." if name else "") + "weight"] += (mod.lora_B.detach() @ mod.lora_A.detach()) * mod.scaling
     return sd
 
 

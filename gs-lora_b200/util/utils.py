@@ -46,6 +46,13 @@ if not _ref_loaded:
             self.count += n
             self.avg = self.sum / self.count
 
+    def train_accuracy(output, target, topk=(1,)):
+        """precision@k in percent for the FIRST k of `topk` (util/utils.py:354-368 returns res[0])"""
+        maxk = max(topk)
+        _, pred = output.topk(maxk, 1, True, True)
+        correct = pred.t().eq(target.view(1, -1).expand_as(pred.t()))
+        return correct[:topk[0]].reshape(-1).float().sum(0).mul_(100.0 / target.size(0))
+
     def count_trainable_parameters(model):
         return sum(p.numel() for p in model.parameters() if p.requires_grad)
 

@@ -238,3 +238,114 @@ def test_single_step_twin_reproduces_the_unmodified_reference_engine_py_epoch(go
     for n in O.lora_param_list(cfg):
         a, b = sd[n], g["params_after"][n]
         assert float((a.double() - b.double()).norm() / b.double().norm()) < 1e-3, n
+
+
+# ------------------------------------------------------------------------------------------------ evaluate(): H-mean and checkpoint rotation
+def _run_evaluate(mod, workdir, accs, task_kw, monkeypatch):
+    """Drive `mod.evaluate` through a sequence of (forget_acc, remain_acc) results; returns (H-mean trajectory, surviving checkpoint names)."""
+    import itertools
+    import os
+    seq = iter(accs)
+    cur = {}
+
+    def fake_eval_data(model, loader, device, mode, batch=0):
+        if mode.startswith("forget"):
+            cur["pair"] = next(seq)
+            return cur["pair"][0]
+        return cur["pair"][1]
+
+    tick = itertools.count()
+    monkeypatch.setattr(mod, "eval_data", fake_eval_data)
+    monkeypatch.setattr(mod, "get_time", lambda: f"t{next(tick):03d}")
+    model = torch.nn.Linear(2, 2)
+    opt = torch.optim.AdamW(model.parameters(), lr=0.01)
+    cfg = {"WORK_PATH": str(workdir), "BACKBONE_NAME": "VIT", "MULTI_GPU": False}
+    open(os.path.join(workdir, "config.txt"), "w").write("x")
+    h, traj = -1.0, []
+    for i in range(len(accs)):
+        h = mod.evaluate(model, None, None, "cpu", batch=i, epoch=0, forget_acc_before=90.0, highest_H_mean=h, cfg=cfg, optimizer=opt, **task_kw)
+        traj.append(h)
+        for f in os.listdir(workdir):                      # make the mtime order unambiguous
+            os.utime(os.path.join(workdir, f), None) if f.endswith(f"t{i:03d}_checkpoint.pth") else None
+    return traj, sorted(f for f in os.listdir(workdir) if f.endswith(".pth"))
+
+
+ACCS = [(80.0, 70.0), (60.0, 72.0), (65.0, 71.0), (30.0, 69.0), (10.0, 75.0), (90.0, 75.0)]      # improving, a dip, improving, then forget_drop = 0
+
+
+def test_evaluate_hmean_and_checkpoint_rotation(tmp_path, monkeypatch):
+    """engine_cl.evaluate (engine_cl.py:247-315): H = 2 d r / (d + r + 1e-8) with d = forget_acc_before - forget_acc; a checkpoint is written
+    only when H improves and the oldest .pth is dropped once the directory holds 4 entries (config.txt + 3 checkpoints -> 2 survive)."""
+    (tmp_path / "a").mkdir()
+    traj, files = _run_evaluate(engine_cl, tmp_path / "a", ACCS, dict(task_i=1), monkeypatch)
+    want, h = [], -1.0
+    for fa, ra in ACCS:
+        d = 90.0 - fa
+        h = max(h, 2 * d * ra / (d + ra + 1e-8))
+        want.append(h)
+    assert traj == pytest.approx(want)
+    assert len(files) == 2 and files[-1].startswith("Backbone_VIT_Epoch_1_Batch_5_")         # the 5th call (batch index 4) was the last improvement
+    # the single-step twin keeps one checkpoint fewer (engine.py:486: `>= 3`) and divides unguarded
+    (tmp_path / "b").mkdir()
+    traj2, files2 = _run_evaluate(engine, tmp_path / "b", ACCS[:5], {}, monkeypatch)
+    assert traj2 == pytest.approx([2 * (90 - fa) * ra / ((90 - fa) + ra) for fa, ra in [ACCS[0], ACCS[1], ACCS[1], ACCS[3], ACCS[4]]])
+    assert len(files2) == 1
+
+
+def test_evaluate_matches_the_reference_functions_live(tmp_path, monkeypatch):
+    """Same driver against the UNMODIFIED reference engine_cl.evaluate / engine.evaluate when the reference tree is present."""
+    import importlib.util
+    import os
+    import sys
+    ref_root = "/root/reference"
+    if not os.path.isfile(os.path.join(ref_root, "engine_cl.py")):
+        pytest.skip("reference tree not present")
+    shims = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "shims")
+    # the reference modules must see the reference's own `util` package, not the drop-in overlay this process has already imported
+    before = set(sys.modules)
+    for k in [k for k in sys.modules if k == "util" or k.startswith("util.")]:
+        monkeypatch.delitem(sys.modules, k)
+    monkeypatch.setattr(sys, "path", [shims, ref_root] + sys.path)
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    monkeypatch.setitem(sys.modules, "image_iter", types.SimpleNamespace(CustomSubset=type("CustomSubset", (), {})))
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location("_ref_" + name, os.path.join(ref_root, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert mod.util.__file__.startswith(ref_root)
+        return mod
+
+    for name, ours, kw, accs in (("engine_cl", engine_cl, dict(task_i=1), ACCS), ("engine", engine, {}, ACCS[:5])):
+        ref = load(name)
+        (tmp_path / (name + "_ref")).mkdir()
+        (tmp_path / (name + "_ours")).mkdir()
+        t_ref, f_ref = _run_evaluate(ref, tmp_path / (name + "_ref"), accs, kw, monkeypatch)
+        t_ours, f_ours = _run_evaluate(ours, tmp_path / (name + "_ours"), accs, kw, monkeypatch)
+        assert t_ours == pytest.approx(t_ref) and f_ours == f_ref, name
+    for k in set(sys.modules) - before:                 # reference modules imported on the way: leave no trace for later tests
+        if k == "util" or k.startswith("util.") or k.startswith("_ref_"):
+            sys.modules.pop(k, None)
+
+
+def test_merged_state_dict_equals_an_eval_mode_deepcopy():
+    """engine.evaluate saves `copy.deepcopy(model).eval().state_dict()` in the reference (engine.py:449-476): loralib merges W += B A / r in
+    eval().  The twin builds the same dict without copying the model and without touching its mode."""
+    import copy
+    from oracle import vit_oracle as O
+    from vit_pytorch_face import ViT_face
+    cfg = O.TINY
+    m = ViT_face(loss_type="CosFace", GPU_ID=[0], num_class=cfg.num_class, image_size=cfg.image_size, patch_size=cfg.patch_size, dim=cfg.dim,
+                 depth=cfg.depth, heads=cfg.heads, mlp_dim=cfg.mlp_dim, lora_rank=cfg.lora_rank)
+    m.load_state_dict(O.init_state_dict(cfg, seed=3), strict=True)
+    m.train()
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    got = engine._merged_state_dict(m)
+    want = copy.deepcopy(m).eval().state_dict()
+    assert set(got) == set(want)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    assert m.training and all(torch.equal(v, before[k]) for k, v in m.state_dict().items())
+    w = "transformer.layers.0.1.fn.fn.net.0.weight"
+    assert not torch.equal(got[w], before[w])                        # the LoRA delta is in the saved weight
+    assert torch.equal(engine._merged_state_dict(m.eval())[w], got[w])      # already merged: nothing is added twice
