@@ -203,3 +203,38 @@ def test_bench_reference_arm_prints_the_contract_line():
     out1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--ref-batch", "2"],
                           capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert out1.returncode == 0 and out1.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("with_reference", [True, False])
+def test_image_iter_overlay_defuses_the_customsubset_landmine(with_reference):
+    """SURVEY 8b landmine 2: the reference's CustomSubset cannot be constructed on torch >= 2.1.  The overlay executes the reference's own
+    image_iter.py (when present) and adds `__getitems__`; without the reference tree it still provides CustomSubset."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = "/root/reference"
+    if with_reference and not os.path.isfile(os.path.join(ref, "image_iter.py")):
+        pytest.skip("reference tree not present")
+    code = r'''
+import sys, torch
+sys.path[:0] = [%r] + ([%r, %r] if %r else [])      # drop-in first; shims for the reference's IPython / mxnet imports; the reference tree
+import image_iter
+assert image_iter.__file__.startswith(%r), image_iter.__file__
+assert image_iter._ref_loaded == %r, getattr(image_iter, "_ref_error", None)
+class DS(torch.utils.data.Dataset):
+    targets = [0, 1, 2, 0]; classes = ["a", "b", "c"]
+    def __getitem__(self, i): return torch.full((2,), float(i)), self.targets[i]
+    def __len__(self): return 4
+s = image_iter.CustomSubset(DS(), [3, 0, 2])
+assert len(s) == 3 and s.classes == ["a", "b", "c"] and s.targets == [0, 1, 2, 0]
+x, y = s[0]
+assert float(x[0]) == 3.0 and y == 0
+xb, yb = next(iter(torch.utils.data.DataLoader(s, batch_size=3)))
+assert xb[:, 0].tolist() == [3.0, 0.0, 2.0] and yb.tolist() == [0, 0, 2]
+if %r:
+    assert hasattr(image_iter, "CLDatasetWrapper") and hasattr(image_iter, "ImageNet900Dataset")
+print("ok")
+''' % (os.path.join(root, "gs-lora_b200"), os.path.join(root, "oracle", "shims"), ref, with_reference, os.path.join(root, "gs-lora_b200"),
+       with_reference, with_reference)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-3000:]
