@@ -238,3 +238,37 @@ print("ok")
        with_reference, with_reference)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("driver", ["train/train_own_forget_cl.py", "train/train_own_forget.py"])
+def test_unmodified_driver_import_block_resolves_on_the_overlay(driver):
+    """Every top-level import of the UNMODIFIED reference drivers executes with `gs-lora_b200` first on sys.path (then the stand-ins for the
+    third-party packages this image lacks, then the reference tree), and the hot-path names bind to this repo's modules."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = "/root/reference"
+    if not os.path.isfile(os.path.join(ref, driver)):
+        pytest.skip("reference tree not present")
+    code = r'''
+import ast, os, sys
+pkg, shims, ref, driver = %r, %r, %r, %r
+sys.path[:0] = [pkg, shims, ref]
+os.environ["WANDB_MODE"] = "disabled"
+tree = ast.parse(open(os.path.join(ref, driver)).read())
+imports = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+ns = {}
+exec(compile(ast.Module(body=imports, type_ignores=[]), driver, "exec"), ns)
+mine = {"ViT_face": "vit_pytorch_face", "ModifiedViT": "vit_pytorch_face", "train_one_epoch": None, "eval_data": None,
+        "get_norm_of_lora": "util/cal_norm.py", "CustomSubset": "image_iter.py", "calculate_prototypes": "util/utils.py"}
+for name, where in mine.items():
+    if name not in ns:
+        continue
+    f = sys.modules[ns[name].__module__].__file__
+    assert f.startswith(pkg), (name, f)
+assert ns["lora"].__file__.startswith(pkg)
+assert ns["train_one_epoch"].__module__ in ("engine_cl", "engine")
+print("ok", len(imports))
+''' % (os.path.join(root, "gs-lora_b200"), os.path.join(root, "oracle", "shims"), ref, driver)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip().splitlines()[-1].startswith("ok"), out.stderr[-3000:]
