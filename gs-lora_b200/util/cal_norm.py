@@ -31,9 +31,9 @@ def get_norm_of_lora(model, type="L2", group_num=6, group_type: str = "block", g
         raise ValueError("type should be L1 or L2")
     if group_pos != "FFN":
         raise NotImplementedError("gslora-b200: get_norm_of_lora is built for the FFN groupings (LoRA on attention is SURVEY.md 8f-2)")
-    if imagenet and group_type != "block":
-        raise ValueError("the reference defines only the block grouping for imagenet models (util/cal_norm.py:82-99)")
-    groups = _ffn_groups(group_num, group_type)
+    # imagenet=True: the reference ignores group_num and group_type and always reports the first 12 encoder blocks (util/cal_norm.py:82-99;
+    # the driver passes group_num=args.vit_depth=6 for ViT-B/16, train_own_forget_cl.py:1100-1105)
+    groups = _ffn_groups(12, "block") if imagenet else _ffn_groups(group_num, group_type)
     names = _NAMES_TV if imagenet else _NAMES
     print("\033[31mgroup_layers_names\033[0m\n", [[names[w].format(i) for i, w in g] for g in groups])
     with torch.no_grad():
@@ -42,4 +42,6 @@ def get_norm_of_lora(model, type="L2", group_num=6, group_type: str = "block", g
             eng = model.ensure_engine(1)
         model.sync_engine()
         per_tensor = eng.tensor_norms(type)          # [4 * depth] on device
+        if max(i for g in groups for i, _ in g) >= eng.spec.depth:
+            raise KeyError(f"get_norm_of_lora: the grouping names block {max(i for g in groups for i, _ in g)} but the model has {eng.spec.depth}")
         return [sum(per_tensor[4 * i + w] for i, w in g) for g in groups]

@@ -7,6 +7,8 @@ import os
 import re
 import socket
 
+import types
+
 import pytest
 import torch
 import torch.multiprocessing as mp
@@ -95,6 +97,28 @@ def test_cal_norm_groupings():
     from util import cal_norm
     assert len(cal_norm._ffn_groups(6, "block")) == 6 and len(cal_norm._ffn_groups(6, "lora")) == 12 and len(cal_norm._ffn_groups(6, "matrix")) == 24
     assert cal_norm._ffn_groups(2, "block")[1] == [(1, 0), (1, 1), (1, 2), (1, 3)]
+
+
+def test_cal_norm_imagenet_always_reports_twelve_block_groups():
+    """util/cal_norm.py:82-99: with imagenet=True the reference ignores group_num / group_type (the driver passes group_num=vit_depth=6 for
+    ViT-B/16) and reports the first 12 encoder blocks."""
+    from util import cal_norm
+
+    class FakeEngine:
+        class spec:
+            depth = 12
+
+        def tensor_norms(self, type):
+            return torch.arange(48, dtype=torch.float32)
+
+    model = types.SimpleNamespace(_engine=FakeEngine(), sync_engine=lambda: None)
+    out = cal_norm.get_norm_of_lora(model, type="L2", group_num=6, group_type="matrix", imagenet=True)
+    assert len(out) == 12 and float(out[0]) == 0 + 1 + 2 + 3 and float(out[11]) == 44 + 45 + 46 + 47
+    out6 = cal_norm.get_norm_of_lora(model, type="L1", group_num=6, group_type="lora")
+    assert len(out6) == 12 and float(out6[0]) == 0 + 1 and float(out6[6]) == 2 + 3      # (A, B) of net.0 for all blocks, then of net.3
+    FakeEngine.spec.depth = 6
+    with pytest.raises(KeyError):
+        cal_norm.get_norm_of_lora(model, type="L2", group_num=6, imagenet=True)
 
 
 # ---------------------------------------------------------------------------------------------- data parallel (gloo, 2 ranks)
