@@ -79,13 +79,15 @@ def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criteri
     for main_x, main_y in iter(driving):
         main_x, main_y = main_x.to(device), main_y.to(device)
         (xr, yr), (xf, yf) = ((side_x, side_y), (main_x, main_y)) if forget_drives else ((main_x, main_y), (side_x, side_y))
+        n_r, n_f = xr.size(0), xf.size(0)                       # the meters weigh by the GLOBAL batch sizes
+        (xr, yr), (xf, yf) = _cl.shard_batch(xr, yr), _cl.shard_batch(xf, yf)
         res = unlearn_step_async(model, xr, yr, xf, yf, beta=beta, alpha=alpha_eff, BND=BND, optimizer=optimizer,
                                  use_prototype=use_prototype, prototype_dict=prototype_dict, prototype_weight_forget=prototype_weight_forget,
                                  prototype_weight_remain=prototype_weight_remain, BND_pro=_PROTO_BOUND if use_prototype else 0.0,
                                  group_type=group_type)
         if pending is not None:
             absorb(pending)
-        pending = (res, xr.size(0), xf.size(0))
+        pending = (res, n_r, n_f)
         show = ((batch + 1) % DISP_FREQ == 0) and batch != 0
         verify = ((batch + 1) % VER_FREQ == 0) and batch != 0
         if show or verify:

@@ -64,6 +64,17 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
 
 
+def shard_batch(x, y):
+    """Data parallel under torchrun: every rank builds the same seeded loaders (the driver is unchanged), so each step's
+    GLOBAL batch is identical on all ranks; rank r keeps the samples r, r + world, ... and the step's all-reduces (loss sums / counts, flat LoRA
+    gradient) put the global batch back together.  No process group (or world size 1): the batch is returned as is."""
+    d = _dist()
+    if d is None or x is None:
+        return x, y
+    r, w = d.get_rank(), d.get_world_size()
+    return x[r::w], y[r::w]
+
+
 def _adamw_hparams(optimizer, params):
     ids = {id(p) for p in params}
     for g in optimizer.param_groups:
@@ -195,6 +206,8 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
     m = _unwrap(model)
     Br, Bf = int(inputs_remain.shape[0]), int(inputs_forget.shape[0])
     B = Br + Bf
+    if B == 0:
+        raise ValueError("unlearn_step: this rank's share of the batch is empty (global batch smaller than the world size?)")
     dev = inputs_remain.device
     if inputs_remain.dtype == torch.uint8 or inputs_forget.dtype == torch.uint8:     # raw pixels: ToTensor [+ Normalize] runs in the patchify kernel
         if inputs_remain.dtype != inputs_forget.dtype:
@@ -319,7 +332,8 @@ def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criteri
     for inputs_remain, labels_remain in iter(dataloader_remain):
         inputs_remain = inputs_remain.to(device)
         labels_remain = labels_remain.to(device)
-        res = unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, labels_forget, beta=beta, alpha=alpha, BND=BND,
+        (xr, yr), (xf, yf) = shard_batch(inputs_remain, labels_remain), shard_batch(inputs_forget, labels_forget)
+        res = unlearn_step_async(model, xr, yr, xf, yf, beta=beta, alpha=alpha, BND=BND,
                                  optimizer=optimizer, use_prototype=use_prototype, prototype_dict=prototype_dict,
                                  prototype_weight_forget=prototype_weight_forget, prototype_weight_remain=prototype_weight_remain,
                                  BND_pro=cfg.get("BND_pro", 0.0) if use_prototype else 0.0)

@@ -349,3 +349,45 @@ def test_merged_state_dict_equals_an_eval_mode_deepcopy():
     w = "transformer.layers.0.1.fn.fn.net.0.weight"
     assert not torch.equal(got[w], before[w])                        # the LoRA delta is in the saved weight
     assert torch.equal(engine._merged_state_dict(m.eval())[w], got[w])      # already merged: nothing is added twice
+
+
+# ------------------------------------------------------------------------------------------------ data parallel sharding of the epoch loops
+class _FakeDist:
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def get_rank(self):
+        return self.rank
+
+    def get_world_size(self):
+        return self.world
+
+
+@pytest.mark.parametrize("mod_name", ["engine_cl", "engine"])
+def test_epoch_loops_shard_the_global_batch_by_rank(fake, monkeypatch, mod_name, capsys):
+    """under torchrun every rank iterates the SAME seeded loaders; rank r of w must step on samples r, r + w, ... of each global
+    batch (remain and forget alike) while the meters keep weighing by the global batch sizes.  The union over ranks is the global batch."""
+    x = torch.arange(10, dtype=torch.float32).view(10, 1)
+    y = torch.arange(10)
+    assert engine_cl.shard_batch(x, y)[0] is x                                       # no process group: untouched
+    seen = {}
+    for rank in range(3):
+        monkeypatch.setattr(engine_cl, "_dist", lambda r=rank: _FakeDist(r, 3))
+        xs, ys = engine_cl.shard_batch(x, y)
+        assert xs[:, 0].tolist() == list(range(rank, 10, 3)) and ys.tolist() == list(range(rank, 10, 3))
+        seen[rank] = set(ys.tolist())
+    assert set().union(*seen.values()) == set(range(10)) and sum(len(v) for v in seen.values()) == 10
+    # through the loops: 4-image remain batches, 2-image forget batches, rank 1 of 2
+    monkeypatch.setattr(engine_cl, "_dist", lambda: _FakeDist(1, 2))
+    remain, forget = _loader(100, 3, 4), _loader(200, 2, 2)
+    m = _meters()
+    if mod_name == "engine_cl":
+        ret = engine_cl.train_one_epoch(torch.nn.Linear(1, 1), forget, remain, "cpu", torch.nn.CrossEntropyLoss(), None, 0, m[0], m[1], m[2], m[3], m[4],
+                                        m[5], 0.15, 1e-2, 105.0, 0, None, None, 0.0, 0.0, {}, 0, False, None, 0.0, 0.0, m[6], m[7])
+    else:
+        ret = engine.train_one_epoch(torch.nn.Linear(1, 1), forget, remain, "cpu", torch.nn.CrossEntropyLoss(), None, 0, m[0], m[1], m[2], m[3], m[4],
+                                     m[5], 0.15, 1e-2, 105.0, 0, None, None, 0.0, 0.0, {"few_shot": False}, losses_prototype_forget=m[6],
+                                     losses_prototype_remain=m[7])
+    assert [(c[2], c[3]) for c in fake.calls] == [(2, 1)] * 3                          # each step saw half of each global batch
+    assert ret[0] == 3 and ret[3].count == 12 and ret[2].count == 6                    # meters: global sizes (3 steps x 4 remain / 2 forget)
+    assert capsys.readouterr().out == ""                                               # rank 1 does not print
