@@ -60,8 +60,17 @@ def _unwrap(model):
 
 
 def _dist():
+    """torch.distributed when this process is one of several data-parallel ranks, else None.  The reference drivers know nothing about
+    torch.distributed (they use nn.DataParallel, train_own_forget_cl.py:494-497); launched unchanged under `torchrun` (RANK / WORLD_SIZE /
+    MASTER_* in the environment) the process group is created here on first use -- NCCL on GPUs, gloo otherwise.  GSLORA_AUTO_DIST=0 opts out."""
     import torch.distributed as dist
-    return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
+    if not dist.is_available():
+        return None
+    if not dist.is_initialized():
+        if int(os.environ.get("WORLD_SIZE", "1")) <= 1 or "RANK" not in os.environ or os.environ.get("GSLORA_AUTO_DIST", "1") == "0":
+            return None
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    return dist if dist.get_world_size() > 1 else None
 
 
 def shard_batch(x, y):

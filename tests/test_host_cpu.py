@@ -296,3 +296,39 @@ print("ok", len(imports))
 ''' % (os.path.join(root, "gs-lora_b200"), os.path.join(root, "oracle", "shims"), ref, driver)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd="/tmp")
     assert out.returncode == 0 and out.stdout.strip().splitlines()[-1].startswith("ok"), out.stderr[-3000:]
+
+
+def _auto_dist_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import engine_cl
+    import torch.distributed as dist
+    assert not dist.is_initialized()
+    d = engine_cl._dist()                                  # what torchrun + the unchanged driver relies on: created on first use
+    assert d is not None and dist.is_initialized() and d.get_world_size() == world and d.get_rank() == rank
+    x = torch.arange(7, dtype=torch.float32).view(7, 1)
+    xs, ys = engine_cl.shard_batch(x, torch.arange(7))
+    t = torch.zeros(7)
+    t[ys] = 1.0
+    d.all_reduce(t)                                        # every sample is owned by exactly one rank
+    if rank == 0:
+        ret["cover"] = t.tolist()
+        ret["mine"] = ys.tolist()
+    d.barrier()
+    d.destroy_process_group()
+
+
+def test_process_group_is_created_on_first_use_under_torchrun_env():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_auto_dist_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret["cover"] == [1.0] * 7 and ret["mine"] == [0, 2, 4, 6]
+    # a single process (no torchrun environment) never creates a group
+    import engine_cl
+    assert engine_cl._dist() is None
