@@ -44,7 +44,18 @@ int gsl_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
     a.cta_group = cta_group; a.block_n = block_n; a.drop_p = drop_p; a.drop_seed = drop_seed;
     return gemm_f16(a, (cudaStream_t)stream);
 }
-
+int gsl_gemm_f16_split(const void* A, int64_t lda, const void* B, const void* B_lo, int64_t ldb, int64_t M, int64_t N, int64_t K, int epi,
+                       const float* bias, void* out0, int64_t ld0, void* out1, int64_t ld1, const void* aux, int64_t ldaux,
+                       int64_t aux_period, int cta_group, int block_n, float drop_p, uint32_t drop_seed, void* stream) {
+    if (B_lo == nullptr) { set_last_error("gsl_gemm_f16_split: B_lo is null"); return -1; }
+    GemmArgs a;
+    a.A = (const __half*)A; a.lda = lda; a.B = (const __half*)B; a.B_lo = (const __half*)B_lo; a.ldb = ldb;
+    a.M = M; a.N = N; a.K = K; a.epi = epi; a.bias = bias;
+    a.out0 = out0; a.ld0 = ld0; a.out1 = out1; a.ld1 = ld1;
+    a.aux = aux; a.ldaux = ldaux; a.aux_period = aux_period;
+    a.cta_group = cta_group; a.block_n = block_n; a.drop_p = drop_p; a.drop_seed = drop_seed;
+    return gemm_f16(a, (cudaStream_t)stream);
+}
 
 #define ST(x) ((cudaStream_t)(x))
 
@@ -66,6 +77,9 @@ int gsl_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx
 int gsl_lora_down(const void* X16, int64_t ldx, const void* A16, int64_t lda, void* out16, int64_t ldo, int64_t M, int K, int r, void* stream) {
     return lora_down((const __half*)X16, ldx, (const __half*)A16, lda, (__half*)out16, ldo, M, K, r, ST(stream));
 }
+int gsl_lora_down_split(const void* X16, int64_t ldx, const void* A32, int64_t lda, void* out16, int64_t ldo, int64_t M, int K, int r, void* stream) {
+    return lora_down((const __half*)X16, ldx, (const __half*)A32, lda, (__half*)out16, ldo, M, K, r, ST(stream), 1);
+}
 size_t gsl_skinny_tn_workspace(int64_t M, int N, int r) { return skinny_tn_workspace(M, N, r); }
 int gsl_skinny_tn(const void* L16, int64_t ldl, const void* R16, int64_t ldr, float* out, int64_t ldo, int transpose_out, float scale,
                   int accumulate, int64_t M, int N, int r, float* workspace, size_t workspace_bytes, void* stream) {
@@ -79,6 +93,12 @@ int gsl_lora_side(const void* L16, int64_t ldl, const void* P16, int64_t ldp, vo
     return lora_side((const __half*)L16, ldl, (const __half*)P16, ldp, (__half*)T16, ldt, (const __half*)R16, ldr, out, ldo, transpose_out, scale,
                      accumulate, M, N, r, workspace, workspace_bytes, ST(stream));
 }
+int gsl_lora_side_split(const void* L16, int64_t ldl, const void* P32, int64_t ldp, void* T16, int64_t ldt, const void* R16, int64_t ldr,
+                        float* out, int64_t ldo, int transpose_out, float scale, int accumulate, int64_t M, int N, int r,
+                        float* workspace, size_t workspace_bytes, void* stream) {
+    return lora_side((const __half*)L16, ldl, (const __half*)P32, ldp, (__half*)T16, ldt, (const __half*)R16, ldr, out, ldo, transpose_out, scale,
+                     accumulate, M, N, r, workspace, workspace_bytes, ST(stream), 1);
+}
 int gsl_attention_fwd(const void* qkv16, int64_t ld, void* out16, int64_t ldo, float* lse, int B, int N, int heads, float scale, void* stream) {
     return attention_fwd((const __half*)qkv16, ld, (__half*)out16, ldo, lse, B, N, heads, scale, ST(stream));
 }
@@ -90,6 +110,10 @@ int gsl_attention_bwd(const void* qkv16, int64_t ld, const void* out16, int64_t 
 int gsl_cast_f32_to_f16(const float* src, int64_t lds, void* dst16, int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose,
                         void* stream) {
     return cast_f32_to_f16(src, lds, (__half*)dst16, ldd, rows, cols, scale, transpose, ST(stream));
+}
+int gsl_cast_f32_to_f16_split(const float* src, int64_t lds, void* dst16, void* dst_lo16, int64_t ldd, int64_t rows, int64_t cols, float scale,
+                              int transpose, void* stream) {
+    return cast_f32_to_f16(src, lds, (__half*)dst16, ldd, rows, cols, scale, transpose, ST(stream), (__half*)dst_lo16);
 }
 int gsl_grouplasso_adamw_step(float* params, const float* grads, float* m, float* v, const int32_t* group_offsets, int num_groups, int64_t n,
                               float lr, float wd, float beta1, float beta2, float eps, float alpha, float grad_scale, int step,

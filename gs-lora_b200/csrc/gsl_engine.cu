@@ -42,23 +42,30 @@ size_t Engine::carve(bool assign) {
     const int64_t D = cfg.dim, H = cfg.mlp_dim, L = cfg.depth, C = cfg.num_class, Bm = cfg.max_batch;
     const int64_t inner = (int64_t)cfg.heads * 64;
     const int64_t M = Bm * tokens;
-    auto* pw = (__half*)take((size_t)D * patch_dim * 2);
+    const bool split = cfg.precision == 1;
+    auto take_w = [&](size_t elems) -> WOp {        // one cached B operand: hi [, lo]
+        WOp w;
+        w.hi = (__half*)take(elems * 2);
+        w.lo = split ? (__half*)take(elems * 2) : nullptr;
+        return w;
+    };
+    const WOp pw = take_w((size_t)D * patch_dim);
     auto* pb = (float*)take((size_t)tokens * D * 4);
     if (assign) { patch_w16 = pw; posb = pb; cache.assign(L, BlockCache()); }
     for (int l = 0; l < L; ++l) {
         BlockCache c;
-        c.qkv_w16 = (__half*)take((size_t)3 * inner * D * 2);
-        c.qkv_wT16 = (__half*)take((size_t)D * 3 * inner * 2);
-        c.out_w16 = (__half*)take((size_t)D * inner * 2);
-        c.out_wT16 = (__half*)take((size_t)inner * D * 2);
-        c.fc1_w16 = (__half*)take((size_t)H * D * 2);
-        c.fc1T_w16 = (__half*)take((size_t)D * H * 2);
-        c.fc2_w16 = (__half*)take((size_t)D * H * 2);
-        c.fc2T_w16 = (__half*)take((size_t)H * D * 2);
-        c.A1h = (__half*)take((size_t)16 * D * 2);
-        c.A2h = (__half*)take((size_t)16 * H * 2);
-        c.B1T = (__half*)take((size_t)16 * H * 2);
-        c.B2T = (__half*)take((size_t)16 * D * 2);
+        c.qkv_w16 = take_w((size_t)3 * inner * D);
+        c.qkv_wT16 = take_w((size_t)D * 3 * inner);
+        c.out_w16 = take_w((size_t)D * inner);
+        c.out_wT16 = take_w((size_t)inner * D);
+        c.fc1_w16 = take_w((size_t)H * D);
+        c.fc1T_w16 = take_w((size_t)D * H);
+        c.fc2_w16 = take_w((size_t)D * H);
+        c.fc2T_w16 = take_w((size_t)H * D);
+        c.A1h = (__half*)take((size_t)32 * D * 2);
+        c.A2h = (__half*)take((size_t)32 * H * 2);
+        c.B1T = (__half*)take((size_t)32 * H * 2);
+        c.B2T = (__half*)take((size_t)32 * D * 2);
         if (assign) cache[l] = c;
     }
     if (assign) slots.assign(cfg.num_slots, Slot());
@@ -130,7 +137,8 @@ static int validate(const GslConfig& c) {
     GSL_REQUIRE(c.dim % 128 == 0 && c.dim <= 1024, "dim=%d must be a multiple of 128 and <= 1024", c.dim);
     GSL_REQUIRE(c.mlp_dim % 64 == 0, "mlp_dim=%d must be a multiple of 64", c.mlp_dim);
     GSL_REQUIRE(c.heads * 64 == c.dim || c.heads > 0, "bad heads");
-    GSL_REQUIRE(c.lora_rank == 8 || c.lora_rank == 16, "lora_rank=%d: this build supports r in {8, 16}", c.lora_rank);
+    GSL_REQUIRE(c.lora_rank >= 1 && c.lora_rank <= 16, "lora_rank=%d: the rank-r side kernels hold r <= 16 (args.py --lora_rank)", c.lora_rank);
+    GSL_REQUIRE(c.precision == 0 || c.precision == 1, "precision=%d: 0 (fast: fp16 weights) or 1 (split: fp16 hi + lo weights)", c.precision);
     GSL_REQUIRE((c.channels * c.patch_size * c.patch_size) % 16 == 0, "patch_dim must be a multiple of 16");
     GSL_REQUIRE(c.max_batch >= 1 && c.num_slots >= 1 && c.depth >= 1, "bad max_batch / num_slots / depth");
     const int tokens = (c.image_size / c.patch_size) * (c.image_size / c.patch_size) + 1;
@@ -179,10 +187,11 @@ int Engine::init(const GslConfig& c, void* workspace, size_t bytes) {
 }
 
 // out = fp16(W + sc * B A) and its transpose, W [R, C] fp32, A [r, C], B [R, r] (loralib.Linear's merged weight, layers.py train/eval);
-// sc = 0 gives the plain fp16 cast.  One 32 x 32 tile per CTA, the transpose goes through shared memory.
+// sc = 0 gives the plain fp16 cast.  One 32 x 32 tile per CTA, the transpose goes through shared memory.  Split mode: out_lo / outT_lo
+// receive fp16(v - fp16(v)), the second term of the split operand (gsl_gemm.cu SPLIT).
 struct MergeJob {
     const float *W, *A, *B;
-    __half *out, *outT;
+    __half *out, *outT, *out_lo, *outT_lo;
     int R, C;
 };
 __global__ void __launch_bounds__(256) merge_weights_kernel(const uint8_t* __restrict__ jobs_raw, int r, float sc) {
@@ -201,14 +210,19 @@ __global__ void __launch_bounds__(256) merge_weights_kernel(const uint8_t* __res
             for (int k = 0; k < r; ++k) d = fmaf(j.B[(int64_t)row * r + k], j.A[(int64_t)k * j.C + col], d);
             v = fmaf(sc, d, v);
         }
-        j.out[(int64_t)row * j.C + col] = __float2half_rn(v);
+        const __half hv = __float2half_rn(v);
+        j.out[(int64_t)row * j.C + col] = hv;
+        if (j.out_lo) j.out_lo[(int64_t)row * j.C + col] = __float2half_rn(v - __half2float(hv));
         tile[ty + 8 * i][tx] = v;
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int col = c0 + ty + 8 * i, row = r0 + tx;
-        j.outT[(int64_t)col * j.R + row] = __float2half_rn(tile[tx][ty + 8 * i]);
+        const float v = tile[tx][ty + 8 * i];
+        const __half hv = __float2half_rn(v);
+        j.outT[(int64_t)col * j.R + row] = hv;
+        if (j.outT_lo) j.outT_lo[(int64_t)col * j.R + row] = __float2half_rn(v - __half2float(hv));
     }
 }
 
@@ -250,9 +264,11 @@ int Engine::bind_params(const void* const* p, int n, float* lora, float* grads) 
     for (int l = 0; l < cfg.depth; ++l) {
         MergeJob j1, j2;
         j1.W = frozen[l].fc1_w; j1.A = lora_flat + lora_offset(l, 0); j1.B = lora_flat + lora_offset(l, 1);
-        j1.out = cache[l].fc1_w16; j1.outT = cache[l].fc1T_w16; j1.R = cfg.mlp_dim; j1.C = cfg.dim;
+        j1.out = cache[l].fc1_w16.hi; j1.outT = cache[l].fc1T_w16.hi; j1.out_lo = cache[l].fc1_w16.lo; j1.outT_lo = cache[l].fc1T_w16.lo;
+        j1.R = cfg.mlp_dim; j1.C = cfg.dim;
         j2.W = frozen[l].fc2_w; j2.A = lora_flat + lora_offset(l, 2); j2.B = lora_flat + lora_offset(l, 3);
-        j2.out = cache[l].fc2_w16; j2.outT = cache[l].fc2T_w16; j2.R = cfg.dim; j2.C = cfg.mlp_dim;
+        j2.out = cache[l].fc2_w16.hi; j2.outT = cache[l].fc2T_w16.hi; j2.out_lo = cache[l].fc2_w16.lo; j2.outT_lo = cache[l].fc2T_w16.lo;
+        j2.R = cfg.dim; j2.C = cfg.mlp_dim;
         jobs.push_back(j1); jobs.push_back(j2);
     }
     static_assert(sizeof(MergeJob) <= 64, "MergeJob slot");
@@ -275,21 +291,21 @@ int Engine::refresh_frozen(cudaStream_t s) {
     GSL_REQUIRE(params_bound, "bind_params first");
     const int D = cfg.dim, H = cfg.mlp_dim, inner = cfg.heads * 64;
     int rc;
-    if ((rc = cast_f32_to_f16(patch_w, patch_dim, patch_w16, patch_dim, D, patch_dim, 1.f, 0, s))) return rc;
+    if ((rc = cast_f32_to_f16(patch_w, patch_dim, patch_w16.hi, patch_dim, D, patch_dim, 1.f, 0, s, patch_w16.lo))) return rc;
     posb_kernel<<<(tokens * D + 255) / 256, 256, 0, s>>>(pos_embedding, cls_token, patch_b, posb, tokens, D);
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     for (int l = 0; l < cfg.depth; ++l) {
         const BlockFrozen& f = frozen[l];
         BlockCache& c = cache[l];
-        if ((rc = cast_f32_to_f16(f.qkv_w, D, c.qkv_w16, D, 3 * inner, D, 1.f, 0, s))) return rc;
-        if ((rc = cast_f32_to_f16(f.qkv_w, D, c.qkv_wT16, 3 * inner, 3 * inner, D, 1.f, 1, s))) return rc;
-        if ((rc = cast_f32_to_f16(f.out_w, inner, c.out_w16, inner, D, inner, 1.f, 0, s))) return rc;
-        if ((rc = cast_f32_to_f16(f.out_w, inner, c.out_wT16, D, D, inner, 1.f, 1, s))) return rc;
-        if ((rc = fill_zero(c.A1h, (size_t)16 * D * 2, s))) return rc;
-        if ((rc = fill_zero(c.A2h, (size_t)16 * H * 2, s))) return rc;
-        if ((rc = fill_zero(c.B1T, (size_t)16 * H * 2, s))) return rc;
-        if ((rc = fill_zero(c.B2T, (size_t)16 * D * 2, s))) return rc;
+        if ((rc = cast_f32_to_f16(f.qkv_w, D, c.qkv_w16.hi, D, 3 * inner, D, 1.f, 0, s, c.qkv_w16.lo))) return rc;
+        if ((rc = cast_f32_to_f16(f.qkv_w, D, c.qkv_wT16.hi, 3 * inner, 3 * inner, D, 1.f, 1, s, c.qkv_wT16.lo))) return rc;
+        if ((rc = cast_f32_to_f16(f.out_w, inner, c.out_w16.hi, inner, D, inner, 1.f, 0, s, c.out_w16.lo))) return rc;
+        if ((rc = cast_f32_to_f16(f.out_w, inner, c.out_wT16.hi, D, D, inner, 1.f, 1, s, c.out_wT16.lo))) return rc;
+        if ((rc = fill_zero(c.A1h, (size_t)32 * D * 2, s))) return rc;
+        if ((rc = fill_zero(c.A2h, (size_t)32 * H * 2, s))) return rc;
+        if ((rc = fill_zero(c.B1T, (size_t)32 * H * 2, s))) return rc;
+        if ((rc = fill_zero(c.B2T, (size_t)32 * D * 2, s))) return rc;
     }
     ffn_cache_mode = -1;        // the FFN caches are rebuilt (with or without the LoRA delta) by the next forward
     return refresh_lora(s);
@@ -301,28 +317,30 @@ struct LoraPackPtrs {
     __half *A1h, *A2h, *B1T, *B2T;
     void* unused[4];
 };
-__global__ void lora_pack_kernel(const float* __restrict__ flat, const LoraPackPtrs* __restrict__ ptrs, int D, int H, int r, int per_block) {
+__global__ void lora_pack_kernel(const float* __restrict__ flat, const LoraPackPtrs* __restrict__ ptrs, int D, int H, int r, int per_block, int split) {
     pdl_prologue();
     const int l = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= per_block) return;
     const LoraPackPtrs p = ptrs[l];
-    const __half hv = __float2half_rn(flat[(int64_t)l * per_block + i]);
+    const float v = flat[(int64_t)l * per_block + i];
+    const __half hv = __float2half_rn(v);
+    const __half lv = __float2half_rn(v - __half2float(hv));      // split mode: residual rows [16, 32) of each operand
     int k = i;
-    if (k < r * D) { p.A1h[k] = hv; return; }                                   // lora_A(net.0) [r, D]
-    k -= r * D;
-    if (k < H * r) { p.B1T[(int64_t)(k % r) * H + k / r] = hv; return; }       // lora_B(net.0) [H, r]
-    k -= H * r;
-    if (k < r * H) { p.A2h[k] = hv; return; }                                   // lora_A(net.3) [r, H]
-    k -= r * H;
-    p.B2T[(int64_t)(k % r) * D + k / r] = hv;                                   // lora_B(net.3) [D, r]
+    __half* dst; int64_t off, lo_off;
+    if (k < r * D) { dst = p.A1h; off = k; lo_off = (int64_t)16 * D; }                                              // lora_A(net.0) [r, D]
+    else if ((k -= r * D) < H * r) { dst = p.B1T; off = (int64_t)(k % r) * H + k / r; lo_off = (int64_t)16 * H; }    // lora_B(net.0) [H, r]
+    else if ((k -= H * r) < r * H) { dst = p.A2h; off = k; lo_off = (int64_t)16 * H; }                              // lora_A(net.3) [r, H]
+    else { k -= r * H; dst = p.B2T; off = (int64_t)(k % r) * D + k / r; lo_off = (int64_t)16 * D; }                  // lora_B(net.3) [D, r]
+    dst[off] = hv;
+    if (split) dst[off + lo_off] = lv;
 }
 
 int Engine::refresh_lora(cudaStream_t s) {
     GSL_REQUIRE(params_bound, "bind_params first");
     const int per_block = (int)lora_block_elems();
     dim3 grid((per_block + 255) / 256, cfg.depth);
-    GSL_CHECK_CUDA(launch_pdl(lora_pack_kernel, dim3(grid), dim3(256), 0, s, lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, per_block));
+    GSL_CHECK_CUDA(launch_pdl(lora_pack_kernel, dim3(grid), dim3(256), 0, s, lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, per_block, cfg.precision == 1 ? 1 : 0));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     if (ffn_cache_mode == 1) ffn_cache_mode = -1;       // W + s B A is stale
@@ -345,14 +363,14 @@ int Engine::ffn_forward(int l, int64_t M, __half* xn2, float* ln_mean, float* ln
     if ((rc = layernorm_fwd(x_mid, D, f.ln2_w, f.ln2_b, cfg.ln_eps, xn2, D, ln_mean, ln_rstd, M, D, s))) return rc;
     {
         GemmArgs g;
-        g.A = xn2; g.lda = D; g.B = c.fc1_w16; g.ldb = D; g.M = M; g.N = H; g.K = D;
+        g.A = xn2; g.lda = D; g.B = c.fc1_w16.hi; g.B_lo = c.fc1_w16.lo; g.ldb = D; g.M = M; g.N = H; g.K = D;
         g.epi = EPI_GELU; g.bias = f.fc1_b; g.out0 = gp16; g.ld0 = H; g.out1 = g16; g.ld1 = H;
         g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 2);
         if ((rc = gemm_f16(g, s))) return rc;
     }
     {
         GemmArgs g;
-        g.A = g16; g.lda = H; g.B = c.fc2_w16; g.ldb = H; g.M = M; g.N = D; g.K = H;
+        g.A = g16; g.lda = H; g.B = c.fc2_w16.hi; g.B_lo = c.fc2_w16.lo; g.ldb = H; g.M = M; g.N = D; g.K = H;
         g.epi = EPI_RES_F32; g.bias = f.fc2_b; g.out0 = x_out; g.ld0 = D; g.aux = x_mid; g.ldaux = D;
         g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 3);
         if ((rc = gemm_f16(g, s))) return rc;
@@ -379,7 +397,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
     if (rc) return rc;
     {   // patch_to_embedding + cls token + pos_embedding (vit_face.py:531-536)
         GemmArgs g;
-        g.A = patches16; g.lda = patch_dim; g.B = patch_w16; g.ldb = patch_dim; g.M = M; g.N = D; g.K = patch_dim;
+        g.A = patches16; g.lda = patch_dim; g.B = patch_w16.hi; g.B_lo = patch_w16.lo; g.ldb = patch_dim; g.M = M; g.N = D; g.K = patch_dim;
         g.epi = EPI_PERIODIC_F32; g.out0 = S.x[0]; g.ld0 = D; g.aux = posb; g.ldaux = D; g.aux_period = tokens;
         g.drop_p = pemb; g.drop_seed = site_seed(dropout_seed, L, 0);
         if ((rc = gemm_f16(g, s))) return rc;
@@ -393,7 +411,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
         if ((rc = layernorm_fwd(x_in, D, f.ln1_w, f.ln1_b, cfg.ln_eps, xn16, D, a.ln1_mean, a.ln1_rstd, M, D, s))) return rc;
         {
             GemmArgs g;
-            g.A = xn16; g.lda = D; g.B = c.qkv_w16; g.ldb = D; g.M = M; g.N = 3 * inner; g.K = D;
+            g.A = xn16; g.lda = D; g.B = c.qkv_w16.hi; g.B_lo = c.qkv_w16.lo; g.ldb = D; g.M = M; g.N = 3 * inner; g.K = D;
             g.epi = EPI_F16; g.bias = f.qkv_b; g.out0 = a.qkv16; g.ld0 = 3 * inner;
             if ((rc = gemm_f16(g, s))) return rc;
         }
@@ -402,7 +420,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
             float* x_out = S.x[2 * l + 2];
             if ((rc = attention_fwd(a.qkv16, 3 * inner, a.o16, inner, a.lse, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
             GemmArgs g;
-            g.A = a.o16; g.lda = inner; g.B = c.out_w16; g.ldb = inner; g.M = M; g.N = D; g.K = inner;
+            g.A = a.o16; g.lda = inner; g.B = c.out_w16.hi; g.B_lo = c.out_w16.lo; g.ldb = inner; g.M = M; g.N = D; g.K = inner;
             g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = x_mid; g.ld0 = D; g.aux = x_in; g.ldaux = D;
             g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
@@ -415,7 +433,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
             if ((rc = cls_attention_fwd(a.qkv16, 3 * inner, k.o16, inner, k.lse, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
             if ((rc = copy_cls_rows(x_in, (int64_t)tokens * D * 4, k.xin32, (int64_t)D * 4, B, (int64_t)D * 4, s))) return rc;
             GemmArgs g;
-            g.A = k.o16; g.lda = inner; g.B = c.out_w16; g.ldb = inner; g.M = B; g.N = D; g.K = inner;
+            g.A = k.o16; g.lda = inner; g.B = c.out_w16.hi; g.B_lo = c.out_w16.lo; g.ldb = inner; g.M = B; g.N = D; g.K = inner;
             g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = k.xmid32; g.ld0 = D; g.aux = k.xin32; g.ldaux = D;
             g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
@@ -446,22 +464,23 @@ int Engine::ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, fl
     float* gA2 = grad_flat + lora_offset(l, 2);
     float* gB2 = grad_flat + lora_offset(l, 3);
     int rc;
-    if ((rc = lora_down(dy, D, c.B2T, D, u2_16, 16, M, D, r, s))) return rc;                                                        // U2 = dY2 B2
-    if ((rc = lora_side(g16, H, c.A2h, H, t2_16, 16, u2_16, 16, gA2, H, 1, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc;   // T2 = G A2^T, dA2 = s U2^T G
+    const int fold = cfg.precision == 1 ? 1 : 0;                // split mode: the rank-r operands carry their rounding residual too
+    if ((rc = lora_down(dy, D, c.B2T, D, u2_16, 16, M, D, r, s, fold))) return rc;                                                        // U2 = dY2 B2
+    if ((rc = lora_side(g16, H, c.A2h, H, t2_16, 16, u2_16, 16, gA2, H, 1, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s, fold))) return rc;   // T2 = G A2^T, dA2 = s U2^T G
     if ((rc = skinny_tn(dy, D, t2_16, 16, gB2, r, 0, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;       // dB2 = s dY2^T T2
     {   // dH = (dY2 W2') * d[Dropout(gelu(h))] / dh
         GemmArgs g;
-        g.A = dy; g.lda = D; g.B = c.fc2T_w16; g.ldb = D; g.M = M; g.N = H; g.K = D;
+        g.A = dy; g.lda = D; g.B = c.fc2T_w16.hi; g.B_lo = c.fc2T_w16.lo; g.ldb = D; g.M = M; g.N = H; g.K = D;
         g.epi = EPI_GELU_BWD; g.out0 = dh; g.ld0 = H; g.aux = gp16; g.ldaux = H;
         if ((rc = gemm_f16(g, s))) return rc;
     }
-    if ((rc = lora_down(xn2, D, c.A1h, D, t1_16, 16, M, D, r, s))) return rc;                                                       // T1 = LN2(x) A1^T
-    if ((rc = lora_side(dh, H, c.B1T, H, u1_16, 16, t1_16, 16, gB1, r, 0, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s))) return rc;    // U1 = dH B1, dB1 = s dH^T T1
+    if ((rc = lora_down(xn2, D, c.A1h, D, t1_16, 16, M, D, r, s, fold))) return rc;                                                       // T1 = LN2(x) A1^T
+    if ((rc = lora_side(dh, H, c.B1T, H, u1_16, 16, t1_16, 16, gB1, r, 0, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s, fold))) return rc;    // U1 = dH B1, dB1 = s dH^T T1
     if ((rc = skinny_tn(xn2, D, u1_16, 16, gA1, D, 1, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;      // dA1 = s U1^T LN2(x)
     if (l == 0) return 0;       // nothing trainable below block 0's FFN
     {   // dLN2 = dH W1'
         GemmArgs g;
-        g.A = dh; g.lda = H; g.B = c.fc1T_w16; g.ldb = H; g.M = M; g.N = D; g.K = H;
+        g.A = dh; g.lda = H; g.B = c.fc1T_w16.hi; g.B_lo = c.fc1T_w16.lo; g.ldb = H; g.M = M; g.N = D; g.K = H;
         g.epi = EPI_F16; g.out0 = dxn; g.ld0 = D;            // fp16: halves the traffic of the LayerNorm-backward pass that consumes it
         if ((rc = gemm_f16(g, s))) return rc;
     }
@@ -499,14 +518,14 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         if (l == 0) return 0;
         {   // dO (cls rows) = dY Wo
             GemmArgs g;
-            g.A = cls_dy16; g.lda = D; g.B = c.out_wT16; g.ldb = D; g.M = B; g.N = inner; g.K = D;
+            g.A = cls_dy16; g.lda = D; g.B = c.out_wT16.hi; g.B_lo = c.out_wT16.lo; g.ldb = D; g.M = B; g.N = inner; g.K = D;
             g.epi = EPI_F16; g.out0 = cls_do16; g.ld0 = inner;
             if ((rc = gemm_f16(g, s))) return rc;
         }
         if ((rc = cls_attention_bwd(a.qkv16, 3 * inner, k.o16, inner, cls_do16, inner, k.lse, dqkv16, 3 * inner, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
         {   // dLN1 = dQKV Wqkv  (dense: dK / dV reach every token)
             GemmArgs g;
-            g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
+            g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16.hi; g.B_lo = c.qkv_wT16.lo; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
             g.epi = EPI_F16; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
@@ -525,14 +544,14 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         // ---------------- attention: y = to_out(attn(to_qkv(LN1(x)))) + x
         {   // dO = dY Wo
             GemmArgs g;
-            g.A = dy16; g.lda = D; g.B = c.out_wT16; g.ldb = D; g.M = M; g.N = inner; g.K = D;
+            g.A = dy16; g.lda = D; g.B = c.out_wT16.hi; g.B_lo = c.out_wT16.lo; g.ldb = D; g.M = M; g.N = inner; g.K = D;
             g.epi = EPI_F16; g.out0 = do16; g.ld0 = inner;
             if ((rc = gemm_f16(g, s))) return rc;
         }
         if ((rc = attention_bwd(a.qkv16, 3 * inner, a.o16, inner, do16, inner, a.lse, dqkv16, 3 * inner, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
         {   // dLN1 = dQKV Wqkv
             GemmArgs g;
-            g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
+            g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16.hi; g.B_lo = c.qkv_wT16.lo; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
             g.epi = EPI_F16; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }

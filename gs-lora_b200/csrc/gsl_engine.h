@@ -12,16 +12,23 @@ struct BlockFrozen {            // fp32 parameters of one Transformer block (cal
     const float *ln1_w, *ln1_b, *qkv_w, *qkv_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
 };
 
+// A cached GEMM B operand: `hi` = fp16(W); `lo` = fp16(W - hi) in precision mode "split" (cfg.precision = 1), else null.
+struct WOp {
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+};
+
 struct BlockCache {             // fp16 operand caches (engine workspace)
-    __half *qkv_w16, *qkv_wT16, *out_w16, *out_wT16;
+    WOp qkv_w16, qkv_wT16, out_w16, out_wT16;
     // FFN weights with the LoRA branch folded in while LoRA is live (un-merged train mode):  W' = W + s * B A, rounded to fp16 once per
     // optimizer step.  x W'^T = x W^T + s (x A^T) B^T and dY W' = dY W + s (dY B) A, so neither GEMM needs the rank-r intermediates.
-    __half *fc1_w16;    // [H, D]  W1'
-    __half *fc1T_w16;   // [D, H]  W1'^T   (B operand of dLN2 = dH W1')
-    __half *fc2_w16;    // [D, H]  W2'
-    __half *fc2T_w16;   // [H, D]  W2'^T   (B operand of dG = dY2 W2')
-    __half *A1h, *A2h;  // [16, D], [16, H]   lora_A (rows >= r zero)   -> T = x A^T for dB
-    __half *B1T, *B2T;  // [16, H], [16, D]   lora_B^T                  -> U = dY B for dA
+    WOp fc1_w16;        // [H, D]  W1'
+    WOp fc1T_w16;       // [D, H]  W1'^T   (B operand of dLN2 = dH W1')
+    WOp fc2_w16;        // [D, H]  W2'
+    WOp fc2T_w16;       // [H, D]  W2'^T   (B operand of dG = dY2 W2')
+    // rank-r operands, 32 rows each: rows [0, 16) = fp16 value (rows >= r zero), rows [16, 32) = fp16 of the rounding residual (split mode, else zero)
+    __half *A1h, *A2h;  // [32, D], [32, H]   lora_A    -> T = x A^T for dB
+    __half *B1T, *B2T;  // [32, H], [32, D]   lora_B^T  -> U = dY B for dA
 };
 
 struct BlockActs {              // saved activations of one block for one slot
@@ -59,7 +66,7 @@ public:
     float* grad_flat = nullptr;
     // workspace
     uint8_t* ws = nullptr; size_t ws_bytes = 0;
-    __half* patch_w16 = nullptr; float* posb = nullptr;
+    WOp patch_w16; float* posb = nullptr;
     std::vector<BlockCache> cache;
     std::vector<Slot> slots;
     // transients (shared by all slots)

@@ -20,6 +20,7 @@ enum GemmEpi {
 struct GemmArgs {
     const __half* A = nullptr; int64_t lda = 0;     // [M, K] row-major
     const __half* B = nullptr; int64_t ldb = 0;     // [N, K] row-major (a torch Linear weight)
+    const __half* B_lo = nullptr;                   // optional second term of a split weight: C = epi(A (B + B_lo)^T), same shape / ldb as B
     int64_t M = 0, N = 0, K = 0;
     int epi = EPI_F16;
     const float* bias = nullptr;
@@ -52,7 +53,9 @@ int layernorm_bwd(const void* dy, int dy_is_fp16, int64_t lddy, const float* x, 
                   int64_t M, int D, float drop_p, uint32_t drop_seed, cudaStream_t s,    // dropout mask applies to the fp16 copy only
                   int dres_period = 0);   // > 0: dres holds one compacted row per `dres_period` rows (added at rows r % period == 0, zero elsewhere)
 // T[M, 0:16] = X[M, K] * A16[16, K]^T  (fp16 in, fp32 accumulate, fp16 out at out[:, 0:16], row pitch ldo)
-int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __half* out, int64_t ldo, int64_t M, int K, int r, cudaStream_t s);
+// fold != 0: A16 has 32 rows, [0, 16) = fp16(A) and [16, 32) = fp16(A - fp16(A)); both halves feed the same accumulator (split-precision LoRA factor)
+int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __half* out, int64_t ldo, int64_t M, int K, int r, cudaStream_t s,
+              int fold = 0);
 // dW[R, 16-ish] style skinny reductions over M (split-M partials + deterministic second pass):
 //   out[n, j] = scale * sum_m  L[m, n] * Rm[m, j]   n < N, j < r    (L fp16 [M, ldl], Rm fp16 [M, ldr])
 //   accumulate != 0 adds into `out` (second data stream / gradient accumulation)
@@ -64,11 +67,11 @@ size_t skinny_tn_workspace(int64_t M, int N, int r);
 // two separate kernels.  Workspace: lora_side_workspace bytes.
 int lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __half* T, int64_t ldt, const __half* Rm, int64_t ldr,
               float* out, int64_t ldo, int transpose_out, float scale, int accumulate, int64_t M, int N, int r,
-              float* workspace, size_t workspace_bytes, cudaStream_t s);
+              float* workspace, size_t workspace_bytes, cudaStream_t s, int fold = 0);      // fold: P16 has 32 rows (hi | lo), as in lora_down
 size_t lora_side_workspace(int64_t M, int N, int r);
 // fp32 -> fp16 casts with optional scale / transpose / column placement (weight cache building, LoRA operand packing)
 int cast_f32_to_f16(const float* src, int64_t lds, __half* dst, int64_t ldd, int64_t rows, int64_t cols, float scale,
-                    int transpose, cudaStream_t s);
+                    int transpose, cudaStream_t s, __half* dst_lo = nullptr);     // dst_lo: fp16(v - fp16(v)), same layout as dst
 int fill_zero(void* ptr, size_t bytes, cudaStream_t s);
 
 // ---- attention (gsl_attention.cu); qkv fp16 [B*N, ld] with q|k|v column blocks of heads*64

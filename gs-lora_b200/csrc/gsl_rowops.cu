@@ -263,7 +263,9 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int NT>   // NT n-tiles of 8 (r = 8 -> 1, r = 16 -> 2)
+// FOLD: A16 holds 32 rows -- rows [0, 16) = fp16(A) ("hi"), rows [16, 32) = fp16(A - hi) ("lo") -- and both feed the same accumulator,
+// so the LoRA factor enters with ~22 significand bits (precision mode "split": its rounding is systematic, like the frozen weights').
+template <int NT, bool FOLD>   // NT n-tiles of 8 (r <= 8 -> 1, r <= 16 -> 2)
 __global__ void __launch_bounds__(128) lora_down_kernel(const __half* __restrict__ X, int64_t ldx, const __half* __restrict__ A, int64_t lda,
                                                         __half* __restrict__ out, int64_t ldo, int64_t M, int K) {
     pdl_prologue();
@@ -295,6 +297,13 @@ __global__ void __launch_bounds__(128) lora_down_kernel(const __half* __restrict
             const uint32_t wb[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
             for (int s = 0; s < 4; ++s) mma_16816(acc[n], xa[2 * s], xb[2 * s], xa[2 * s + 1], xb[2 * s + 1], wb[2 * s], wb[2 * s + 1]);
+            if (FOLD) {
+                const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(ar + 16 * lda));
+                const uint4 l1 = __ldg(reinterpret_cast<const uint4*>(ar + 16 * lda + 8));
+                const uint32_t lb[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+                for (int s = 0; s < 4; ++s) mma_16816(acc[n], xa[2 * s], xb[2 * s], xa[2 * s + 1], xb[2 * s + 1], lb[2 * s], lb[2 * s + 1]);
+            }
         }
     }
     // K tail (K % 64 in {16, 32, 48}): same scheme on 16-wide pieces, lanes t >= pieces contribute zeros
@@ -312,15 +321,18 @@ __global__ void __launch_bounds__(128) lora_down_kernel(const __half* __restrict
         }
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
-            uint32_t wb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (t < pieces) {
-                const __half* ar = A + (int64_t)(8 * n + g) * lda + nchunks * 64 + 16 * t;
-                const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(ar));
-                const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(ar + 8));
-                wb[0] = w0.x; wb[1] = w0.y; wb[2] = w0.z; wb[3] = w0.w; wb[4] = w1.x; wb[5] = w1.y; wb[6] = w1.z; wb[7] = w1.w;
-            }
 #pragma unroll
-            for (int s = 0; s < 4; ++s) mma_16816(acc[n], xa[2 * s], xb[2 * s], xa[2 * s + 1], xb[2 * s + 1], wb[2 * s], wb[2 * s + 1]);
+            for (int part = 0; part < (FOLD ? 2 : 1); ++part) {
+                uint32_t wb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (t < pieces) {
+                    const __half* ar = A + (int64_t)(16 * part + 8 * n + g) * lda + nchunks * 64 + 16 * t;
+                    const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(ar));
+                    const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(ar + 8));
+                    wb[0] = w0.x; wb[1] = w0.y; wb[2] = w0.z; wb[3] = w0.w; wb[4] = w1.x; wb[5] = w1.y; wb[6] = w1.z; wb[7] = w1.w;
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) mma_16816(acc[n], xa[2 * s], xb[2 * s], xa[2 * s + 1], xb[2 * s + 1], wb[2 * s], wb[2 * s + 1]);
+            }
         }
     }
     // c0,c1 -> (row g, cols 2t, 2t+1) ; c2,c3 -> (row g+8, ...) ; columns [8*NT, 16) are zero padding
@@ -334,14 +346,19 @@ __global__ void __launch_bounds__(128) lora_down_kernel(const __half* __restrict
 }
 
 int lora_down(const __half* X, int64_t ldx, const __half* A16, int64_t lda, __half* out, int64_t ldo, int64_t M, int K, int r,
-              cudaStream_t s) {
+              cudaStream_t s, int fold) {
     GSL_REQUIRE(K % 16 == 0 && ldx % 8 == 0 && lda % 8 == 0 && ldo % 2 == 0, "lora_down: K %% 16, ldx %% 8, lda %% 8 required (K=%d)", K);
-    GSL_REQUIRE(r == 8 || r == 16, "lora_down: rank must be 8 or 16 (got %d)", r);
+    GSL_REQUIRE(r >= 1 && r <= 16, "lora_down: rank must be in [1, 16] (got %d)", r);
     const int warps = 4;
     const int64_t groups = (M + 15) / 16;
     const int blocks = (int)((groups + warps - 1) / warps);
-    if (r == 8) GSL_CHECK_CUDA(launch_pdl(lora_down_kernel<1>, dim3(blocks), dim3(warps * 32), 0, s, X, ldx, A16, lda, out, ldo, M, K));
-    else GSL_CHECK_CUDA(launch_pdl(lora_down_kernel<2>, dim3(blocks), dim3(warps * 32), 0, s, X, ldx, A16, lda, out, ldo, M, K));
+    if (r <= 8) {
+        if (fold) GSL_CHECK_CUDA(launch_pdl(lora_down_kernel<1, true>, dim3(blocks), dim3(warps * 32), 0, s, X, ldx, A16, lda, out, ldo, M, K));
+        else GSL_CHECK_CUDA(launch_pdl(lora_down_kernel<1, false>, dim3(blocks), dim3(warps * 32), 0, s, X, ldx, A16, lda, out, ldo, M, K));
+    } else {
+        if (fold) GSL_CHECK_CUDA(launch_pdl(lora_down_kernel<2, true>, dim3(blocks), dim3(warps * 32), 0, s, X, ldx, A16, lda, out, ldo, M, K));
+        else GSL_CHECK_CUDA(launch_pdl(lora_down_kernel<2, false>, dim3(blocks), dim3(warps * 32), 0, s, X, ldx, A16, lda, out, ldo, M, K));
+    }
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -485,7 +502,7 @@ size_t skinny_tn_workspace(int64_t M, int N, int r) {
 
 int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float* out, int64_t ldo, int transpose_out, float scale,
               int accumulate, int64_t M, int N, int r, float* workspace, size_t workspace_bytes, cudaStream_t s) {
-    GSL_REQUIRE(r == 8 || r == 16, "skinny_tn: rank must be 8 or 16 (got %d)", r);
+    GSL_REQUIRE(r >= 1 && r <= 16, "skinny_tn: rank must be in [1, 16] (got %d)", r);
     GSL_REQUIRE(N % 8 == 0 && ldl % 8 == 0 && ldr % 8 == 0, "skinny_tn: N, ldl, ldr must be multiples of 8");
     GSL_REQUIRE(workspace_bytes >= skinny_tn_workspace(M, N, r), "skinny_tn: workspace too small");
     const int splits = skinny_splits(M, N);
@@ -499,7 +516,7 @@ int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float
         GSL_CHECK_CUDA(cudaFuncSetAttribute(skinny_tn_partial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    if (r == 8) {
+    if (r <= 8) {
         GSL_CHECK_CUDA(launch_pdl(skinny_tn_partial_kernel<8>, dim3(grid), dim3(SK_THREADS), smem, s, L, ldl, Rm, ldr, workspace, M, N, rows_per_split));
         GSL_COUNT_LAUNCH(1);
         GSL_CHECK_CUDA(launch_pdl(skinny_tn_reduce_kernel<8>, dim3((N * 8 + 255) / 256), dim3(256), 0, s, workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate));
@@ -528,7 +545,7 @@ int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float
 static constexpr int SP_WARPS = 16, SP_THREADS = SP_WARPS * 32, SP_ROWS = 16;
 static constexpr int SP_RED_BYTES = 2 * SP_WARPS * SP_ROWS * 8 * 4;
 
-template <int NB, int STAGES>   // NB = 16-column blocks per warp (N = 256 * NB)
+template <int NB, int STAGES, bool FOLD>   // NB = 16-column blocks per warp (N = 256 * NB); FOLD: P has 32 rows, hi [0, 16) + lo [16, 32) (see lora_down_kernel)
 __global__ void __launch_bounds__(SP_THREADS, 1) lora_side_kernel(const __half* __restrict__ L, int64_t ldl, const __half* __restrict__ P, int64_t ldp,
                                                                  __half* __restrict__ T, int64_t ldt, const __half* __restrict__ Rm, int64_t ldr,
                                                                  float* __restrict__ partial, int64_t M, int rows_per_cta) {
@@ -563,12 +580,16 @@ __global__ void __launch_bounds__(SP_THREADS, 1) lora_side_kernel(const __half* 
     };
 
     // B fragments of the down projection (k = n, 8 output columns j): lane (g, t) holds P[g][c + 2t, 2t+1] and P[g][c + 8 + 2t, ...]
-    uint32_t pf[NB][2];
+    uint32_t pf[NB][2], pl[FOLD ? NB : 1][2];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
         const __half* pr = P + (int64_t)g * ldp + (warp * NB + nb) * 16 + 2 * t;
         pf[nb][0] = __ldg(reinterpret_cast<const uint32_t*>(pr));
         pf[nb][1] = __ldg(reinterpret_cast<const uint32_t*>(pr + 8));
+        if (FOLD) {
+            pl[nb][0] = __ldg(reinterpret_cast<const uint32_t*>(pr + 16 * ldp));
+            pl[nb][1] = __ldg(reinterpret_cast<const uint32_t*>(pr + 16 * ldp + 8));
+        }
     }
     float accQ[NB][4];
 #pragma unroll
@@ -610,6 +631,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) lora_side_kernel(const __half* 
                              : "r"(sL + row * ROW_BYTES + (((chunk & ~7) | ((chunk ^ row) & 7)) << 4)));
             }
             mma_16816(accT, af[0], af[1], af[2], af[3], pf[nb][0], pf[nb][1]);
+            if (FOLD) mma_16816(accT, af[0], af[1], af[2], af[3], pl[nb][0], pl[nb][1]);
         }
         // per-warp partial T rows -> shared, summed by the first 128 threads: c0,c1 -> (row g, j = 2t, 2t+1); c2,c3 -> (row g + 8)
         float* rbuf = red + (c & 1) * (SP_WARPS * SP_ROWS * 8);
@@ -638,7 +660,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) lora_side_kernel(const __half* 
     }
 }
 
-static bool lora_side_fused_ok(int N, int r) { return r == 8 && N % 256 == 0 && N / 256 >= 1 && N / 256 <= 12; }
+static bool lora_side_fused_ok(int N, int r) { return r <= 8 && N % 256 == 0 && N / 256 >= 1 && N / 256 <= 12; }
 static int lora_side_ctas(int64_t M) {
     const int64_t chunks = (M + SP_ROWS - 1) / SP_ROWS;
     const int sms = device_sm_count();
@@ -651,17 +673,17 @@ size_t lora_side_workspace(int64_t M, int N, int r) {
     return fused > fallback ? fused : fallback;
 }
 
-template <int NB, int STAGES>
+template <int NB, int STAGES, bool FOLD>
 static int launch_lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __half* T, int64_t ldt, const __half* Rm, int64_t ldr,
                             float* workspace, int64_t M, int ctas, int rows_per_cta, cudaStream_t s) {
     constexpr int smem = STAGES * (SP_ROWS * 512 * NB + SP_ROWS * 32) + SP_RED_BYTES;
     static_assert(smem <= 232448, "lora_side: stage ring does not fit in shared memory");
     static bool attr = false;
     if (!attr) {
-        GSL_CHECK_CUDA(cudaFuncSetAttribute(lora_side_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GSL_CHECK_CUDA(cudaFuncSetAttribute(lora_side_kernel<NB, STAGES, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    GSL_CHECK_CUDA(launch_pdl(lora_side_kernel<NB, STAGES>, dim3(ctas), dim3(SP_THREADS), smem, s, L, ldl, P16, ldp, T, ldt, Rm, ldr, workspace, M, rows_per_cta));
+    GSL_CHECK_CUDA(launch_pdl(lora_side_kernel<NB, STAGES, FOLD>, dim3(ctas), dim3(SP_THREADS), smem, s, L, ldl, P16, ldp, T, ldt, Rm, ldr, workspace, M, rows_per_cta));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -669,12 +691,12 @@ static int launch_lora_side(const __half* L, int64_t ldl, const __half* P16, int
 
 int lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __half* T, int64_t ldt, const __half* Rm, int64_t ldr,
               float* out, int64_t ldo, int transpose_out, float scale, int accumulate, int64_t M, int N, int r,
-              float* workspace, size_t workspace_bytes, cudaStream_t s) {
-    GSL_REQUIRE(r == 8 || r == 16, "lora_side: rank must be 8 or 16 (got %d)", r);
+              float* workspace, size_t workspace_bytes, cudaStream_t s, int fold) {
+    GSL_REQUIRE(r >= 1 && r <= 16, "lora_side: rank must be in [1, 16] (got %d)", r);
     GSL_REQUIRE(N % 16 == 0 && ldl % 8 == 0 && ldp % 8 == 0 && ldr % 8 == 0 && ldt % 8 == 0, "lora_side: N %% 16 and pitches %% 8 required");
     GSL_REQUIRE(workspace_bytes >= lora_side_workspace(M, N, r), "lora_side: workspace too small");
     if (!lora_side_fused_ok(N, r)) {        // rank 16 / odd widths: the two separate passes
-        int rc = lora_down(L, ldl, P16, ldp, T, ldt, M, N, r, s);
+        int rc = lora_down(L, ldl, P16, ldp, T, ldt, M, N, r, s, fold);
         if (rc) return rc;
         return skinny_tn(L, ldl, Rm, ldr, out, ldo, transpose_out, scale, accumulate, M, N, r, workspace, workspace_bytes, s);
     }
@@ -682,7 +704,9 @@ int lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __ha
     int rows_per_cta = (int)((M + ctas - 1) / ctas);
     rows_per_cta = (rows_per_cta + SP_ROWS - 1) / SP_ROWS * SP_ROWS;
     int rc = -1;
-#define GSL_SP_CASE(NBV, ST) case NBV: rc = launch_lora_side<NBV, ST>(L, ldl, P16, ldp, T, ldt, Rm, ldr, workspace, M, ctas, rows_per_cta, s); break;
+#define GSL_SP_CASE(NBV, ST) case NBV: \
+        rc = fold ? launch_lora_side<NBV, ST, true>(L, ldl, P16, ldp, T, ldt, Rm, ldr, workspace, M, ctas, rows_per_cta, s) \
+                  : launch_lora_side<NBV, ST, false>(L, ldl, P16, ldp, T, ldt, Rm, ldr, workspace, M, ctas, rows_per_cta, s); break;
     switch (N / 256) {
         GSL_SP_CASE(1, 4) GSL_SP_CASE(2, 4) GSL_SP_CASE(3, 4) GSL_SP_CASE(4, 4) GSL_SP_CASE(5, 4) GSL_SP_CASE(6, 4)
         GSL_SP_CASE(7, 3) GSL_SP_CASE(8, 3) GSL_SP_CASE(9, 2) GSL_SP_CASE(10, 2) GSL_SP_CASE(11, 2) GSL_SP_CASE(12, 2)
@@ -696,24 +720,28 @@ int lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __ha
 }
 
 // ------------------------------------------------------------------------------------------------ casts
-__global__ void cast_kernel(const float* __restrict__ src, int64_t lds, __half* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols,
-                            float scale, int transpose) {
+// dst = fp16(v), v = src * scale; dst_lo (optional, same layout) = fp16(v - dst): the second term of a split operand (hi + lo = v to ~2^-22)
+__global__ void cast_kernel(const float* __restrict__ src, int64_t lds, __half* __restrict__ dst, __half* __restrict__ dst_lo, int64_t ldd,
+                            int64_t rows, int64_t cols, float scale, int transpose) {
     const int64_t total = rows * cols;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / cols, c = i % cols;
-        const __half h = __float2half_rn(src[r * lds + c] * scale);
-        if (transpose) dst[c * ldd + r] = h; else dst[r * ldd + c] = h;
+        const float v = src[r * lds + c] * scale;
+        const __half h = __float2half_rn(v);
+        const int64_t o = transpose ? c * ldd + r : r * ldd + c;
+        dst[o] = h;
+        if (dst_lo) dst_lo[o] = __float2half_rn(v - __half2float(h));
     }
 }
 
 int cast_f32_to_f16(const float* src, int64_t lds, __half* dst, int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose,
-                    cudaStream_t s) {
+                    cudaStream_t s, __half* dst_lo) {
     const int64_t total = rows * cols;
     if (total == 0) return 0;
     int blocks = (int)((total + 255) / 256);
     const int cap = device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    cast_kernel<<<blocks, 256, 0, s>>>(src, lds, dst, ldd, rows, cols, scale, transpose);
+    cast_kernel<<<blocks, 256, 0, s>>>(src, lds, dst, dst_lo, ldd, rows, cols, scale, transpose);
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;

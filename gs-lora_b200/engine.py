@@ -77,10 +77,12 @@ def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criteri
         losses_total.update(out["total"], nr)
 
     for main_x, main_y in iter(driving):
+        n_main = int(main_x.size(0))                            # the meters weigh by the GLOBAL batch sizes
+        main_x, main_y = _cl.shard_batch(main_x, main_y)        # sharded on the host: each rank copies only its share over PCIe
         main_x, main_y = main_x.to(device), main_y.to(device)
+        (side_x, side_y), n_side = _cl._own_share(prefetcher, side_x, side_y)
         (xr, yr), (xf, yf) = ((side_x, side_y), (main_x, main_y)) if forget_drives else ((main_x, main_y), (side_x, side_y))
-        n_r, n_f = xr.size(0), xf.size(0)                       # the meters weigh by the GLOBAL batch sizes
-        (xr, yr), (xf, yf) = _cl.shard_batch(xr, yr), _cl.shard_batch(xf, yf)
+        n_r, n_f = (n_side, n_main) if forget_drives else (n_main, n_side)
         res = unlearn_step_async(model, xr, yr, xf, yf, beta=beta, alpha=alpha_eff, BND=BND, optimizer=optimizer,
                                  use_prototype=use_prototype, prototype_dict=prototype_dict, prototype_weight_forget=prototype_weight_forget,
                                  prototype_weight_remain=prototype_weight_remain, BND_pro=_PROTO_BOUND if use_prototype else 0.0,
@@ -174,11 +176,8 @@ def eval_data(model, dataloader, device, mode: str, batch: int = 0):
         for images, labels in dataloader:
             images = m.prepare_images(images.to(device))
             labels = labels.to(device).long().contiguous()
-            eng = m.ensure_engine(images.shape[0])
-            m.sync_engine()
-            slot = m._take_slot()
-            B = eng.forward(images, labels, slot, use_lora=not m._merged(), dropout_seed=0, **m.image_kwargs(images))
-            hits += eng.slot_tensor(slot, F.SLOT_CORRECT, B).sum()
+            for slot, _, B in m.inference_slots(images, labels):          # chunks of the engine's capacity: eval never grows the workspace
+                hits += m._engine.slot_tensor(slot, F.SLOT_CORRECT, B).sum()
             total += labels.size(0)
     accuracy = 100 * int(hits.item()) / max(total, 1)
     print("Test {} Accuracy:{:2f}%".format(mode, accuracy))

@@ -69,7 +69,14 @@ def _dist():
     if not dist.is_initialized():
         if int(os.environ.get("WORLD_SIZE", "1")) <= 1 or "RANK" not in os.environ or os.environ.get("GSLORA_AUTO_DIST", "1") == "0":
             return None
-        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        if torch.cuda.is_available():
+            # one rank per GPU: without CUDA_VISIBLE_DEVICES=$LOCAL_RANK every rank would otherwise land on cuda:0
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            if torch.cuda.device_count() > 1:
+                torch.cuda.set_device(local % torch.cuda.device_count())
+            dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+        else:
+            dist.init_process_group("gloo")
     return dist if dist.get_world_size() > 1 else None
 
 
@@ -95,12 +102,32 @@ def _adamw_hparams(optimizer, params):
 
 
 def _prototype_tensor(prototype_dict, num_class, dim, device):
+    """Dense [num_class, dim] table (+ a per-class `present` mask, None for a caller-supplied tensor) of the driver's {label: CPU tensor} dict
+    (util/utils.py:546-549), built with ONE stacked host-to-device copy."""
     if torch.is_tensor(prototype_dict):
-        return prototype_dict.to(device)
-    t = torch.zeros(num_class, dim, device=device)
-    for k, v in prototype_dict.items():
-        t[int(k)] = v.to(device)
-    return t
+        return prototype_dict.to(device), None
+    keys = sorted(int(k) for k in prototype_dict)
+    if keys and (keys[0] < 0 or keys[-1] >= num_class):
+        raise KeyError(f"prototype label {keys[0] if keys[0] < 0 else keys[-1]} outside [0, {num_class})")
+    t = torch.zeros(num_class, dim)
+    present = torch.zeros(num_class, dtype=torch.bool)
+    if keys:
+        idx = torch.tensor(keys, dtype=torch.long)
+        t[idx] = torch.stack([torch.as_tensor(prototype_dict[k]).detach().float().cpu().reshape(dim) for k in keys])
+        present[idx] = True
+    return t.to(device), present.to(device)
+
+
+def _cached_prototype_table(m, prototype_dict, num_class, dim, device):
+    """The table is rebuilt only when the driver hands over a different dict object (it computes the prototypes once per task,
+    train_own_forget_cl.py:1026-1040): the step itself issues no host-to-device copy for it."""
+    key = (id(prototype_dict), len(prototype_dict) if hasattr(prototype_dict, "__len__") else -1, str(device))
+    cache = getattr(m, "_gsl_proto_cache", None)
+    if cache is None or cache[0] != key:
+        table, present = _prototype_tensor(prototype_dict, num_class, dim, device)
+        cache = (key, table.float().contiguous(), present, prototype_dict)      # the dict is kept alive so its id cannot be recycled
+        m._gsl_proto_cache = cache
+    return cache[1], cache[2]
 
 
 def get_prototype_loss(output, labels, prototype_dict, distance="kl"):
@@ -110,8 +137,11 @@ def get_prototype_loss(output, labels, prototype_dict, distance="kl"):
     if torch.is_tensor(prototype_dict):
         pt = prototype_dict[labels.long()].to(output.device)
     else:
-        table = _prototype_tensor(prototype_dict, max(int(k) for k in prototype_dict) + 1, output.shape[1], output.device)
-        pt = table[labels.long()]
+        table, present = _prototype_tensor(prototype_dict, max(int(k) for k in prototype_dict) + 1, output.shape[1], output.device)
+        lab = labels.long()
+        if bool((lab >= table.shape[0]).any()) or not bool(present[lab.clamp(max=table.shape[0] - 1)].all()):
+            raise KeyError("get_prototype_loss: a label of the batch has no prototype")      # the reference's dict lookup raises too
+        pt = table[lab]
     if distance == "l2":
         return torch.mean((output - pt) ** 2)
     return F_t.kl_div(F_t.log_softmax(output, dim=1), F_t.log_softmax(pt, dim=1), reduction="batchmean", log_target=True)
@@ -168,6 +198,9 @@ class StepResult:
             host = self._pinned[:self._n].tolist()
             c = self._c
             s_ce_r, n_r, s_ce_f, n_f, hit_r, hit_f, s_kl_r, s_kl_f, structure = host[:9]
+            if self._n > 9 and host[9] != 0.0:
+                raise KeyError("unlearn_step: a label of this step's batch has no entry in prototype_dict (engine_cl.py:571-603 looks every "
+                               "label up in the dict)")
             loss_remain = s_ce_r / max(n_r, 1.0)
             ce_forget = s_ce_f / max(n_f, 1.0)
             loss_forget = max(c["BND"] - ce_forget, 0.0)
@@ -215,34 +248,45 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
     m = _unwrap(model)
     Br, Bf = int(inputs_remain.shape[0]), int(inputs_forget.shape[0])
     B = Br + Bf
-    if B == 0:
-        raise ValueError("unlearn_step: this rank's share of the batch is empty (global batch smaller than the world size?)")
+    dist = _dist()
+    if B == 0 and dist is None:
+        raise ValueError("unlearn_step: empty batch")
     dev = inputs_remain.device
-    if inputs_remain.dtype == torch.uint8 or inputs_forget.dtype == torch.uint8:     # raw pixels: ToTensor [+ Normalize] runs in the patchify kernel
-        if inputs_remain.dtype != inputs_forget.dtype:
-            raise TypeError("unlearn_step: remain and forget images must both be uint8 (raw pixels) or both floating point (ToTensor output)")
-        img = torch.cat([inputs_remain, inputs_forget], dim=0).contiguous()
-    else:
-        img = torch.cat([inputs_remain.float(), inputs_forget.float()], dim=0).contiguous()
-    lab = torch.cat([labels_remain.to(torch.int64), labels_forget.to(torch.int64)], dim=0).contiguous()
-    eng = m.ensure_engine(B)
+    eng = m.ensure_engine(max(B, 1))
     m.sync_engine()
     if m._merged():
         raise RuntimeError("unlearn_step needs model.train() (un-merged LoRA)")
-    slot = m._take_slot()
-    eng.forward(img, lab, slot, use_lora=True, dropout_seed=m.dropout_seed() if dropout_seed is None else dropout_seed, **m.image_kwargs(img))
-    table = kl = None
-    if use_prototype:                                           # GS-LoRA++ (engine_cl.py:97-101): per-sample KL to the class prototype, on device
-        table = _prototype_tensor(prototype_dict, eng.spec.num_class, eng.spec.dim, dev).float().contiguous()
-        kl = eng.prototype_kl(slot, lab, table, B)
-    sums = eng.loss_sums(slot, Br, B, kl)
-    dist = _dist()
+    missing = None
+    if B > 0:
+        if inputs_remain.dtype == torch.uint8 or inputs_forget.dtype == torch.uint8:     # raw pixels: ToTensor [+ Normalize] runs in the patchify kernel
+            if inputs_remain.dtype != inputs_forget.dtype:
+                raise TypeError("unlearn_step: remain and forget images must both be uint8 (raw pixels) or both floating point (ToTensor output)")
+            img = torch.cat([inputs_remain, inputs_forget], dim=0).contiguous()
+        else:
+            img = torch.cat([inputs_remain.float(), inputs_forget.float()], dim=0).contiguous()
+        lab = torch.cat([labels_remain.to(torch.int64), labels_forget.to(torch.int64)], dim=0).contiguous()
+        slot = m._take_slot()
+        eng.forward(img, lab, slot, use_lora=True, dropout_seed=m.dropout_seed() if dropout_seed is None else dropout_seed, **m.image_kwargs(img))
+        table = kl = None
+        if use_prototype:                                       # GS-LoRA++ (engine_cl.py:97-101): per-sample KL to the class prototype, on device
+            table, present = _cached_prototype_table(m, prototype_dict, eng.spec.num_class, eng.spec.dim, dev)
+            if present is not None:                             # a label without a prototype is a KeyError in the reference: flagged on device,
+                missing = (~present[lab.clamp(0, eng.spec.num_class - 1)]).any().float().view(1)     # raised when the step's scalars are read
+            kl = eng.prototype_kl(slot, lab, table, B)
+        sums = eng.loss_sums(slot, Br, B, kl)
+    else:
+        # this rank's share of the global batch is empty (drop_last=False tails, few-shot forget sets smaller than the world size): it still
+        # joins both collectives -- with zero sums and a zero gradient -- and applies the same optimizer step as every other rank
+        sums = eng.sums.zero_()
     if dist is not None:
         dist.all_reduce(sums)                                   # global CE / KL sums, counts, hits (8 floats)
-    dlogits = torch.empty(B, eng.spec.num_class, dtype=torch.float32, device=dev)
-    eng.unlearn_ce_grad(slot, lab, Br, B, beta, BND, dlogits)
-    demb = eng.prototype_kl_grad(slot, lab, table, Br, B, prototype_weight_forget, prototype_weight_remain, BND_pro) if use_prototype else None
-    eng.backward(slot, dlogits, demb, accumulate=False)
+    if B > 0:
+        dlogits = torch.empty(B, eng.spec.num_class, dtype=torch.float32, device=dev)
+        eng.unlearn_ce_grad(slot, lab, Br, B, beta, BND, dlogits)
+        demb = eng.prototype_kl_grad(slot, lab, table, Br, B, prototype_weight_forget, prototype_weight_remain, BND_pro) if use_prototype else None
+        eng.backward(slot, dlogits, demb, accumulate=False)
+    else:
+        eng.grad_flat.zero_()
     if dist is not None:
         dist.all_reduce(eng.grad_flat)                          # the one flat LoRA-gradient allreduce (0.98 MB for ViT-P8S8 r=8)
     hp = hparams if hparams is not None else _adamw_hparams(optimizer, m.lora_parameters())
@@ -250,7 +294,7 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
                        group_type=group_type)                   # cfg["GROUP_TYPE"] of engine.py:82-90
     m.mark_lora_updated_by_engine()
     # one D2H copy (queued, pinned) for everything the reference reads with .item()
-    packed = torch.cat([sums, eng.group_norms[:eng.num_groups].sum().view(1)])
+    packed = torch.cat([sums, eng.group_norms[:eng.num_groups].sum().view(1)] + ([missing] if missing is not None else []))
     if _RING is None:
         _RING = _PinnedRing()
     slot_i, pinned = _RING.take()
@@ -283,11 +327,15 @@ def sync_optimizer_state(model, optimizer):
 
 
 class _Prefetcher:
-    """Side-stream H2D prefetch of the forget loader (the reference's util/data_prefetcher.py:10-58 behaviour)."""
+    """Side-stream H2D prefetch of the forget loader (the reference's util/data_prefetcher.py:10-58 behaviour).  Under torch.distributed the
+    batch is sharded on the HOST first (`shards = True`: what next() returns is already this rank's share), so each rank copies 1/world of the
+    global batch over PCIe; `global_n` is the size of the global batch the last next() came from (the meters weigh by it)."""
+    shards = True
 
     def __init__(self, loader, device):
         self.loader, self.device = iter(loader), device
         self.stream = torch.cuda.Stream(device=device)
+        self.global_n = self._n = 0
         self._preload()
 
     def _preload(self):
@@ -296,17 +344,27 @@ class _Prefetcher:
         except StopIteration:
             self.s = self.t = None
             return
+        self._n = int(s.shape[0])
+        s, t = shard_batch(s, t)
         with torch.cuda.stream(self.stream):
             self.s, self.t = s.to(self.device, non_blocking=True), t.to(self.device, non_blocking=True)
 
     def next(self):
         torch.cuda.current_stream().wait_stream(self.stream)
         s, t = self.s, self.t
+        self.global_n = self._n
         if s is not None:
             s.record_stream(torch.cuda.current_stream())
             t.record_stream(torch.cuda.current_stream())
         self._preload()
         return s, t
+
+
+def _own_share(prefetcher, x, y):
+    """(this rank's share of a prefetched batch, size of the global batch)"""
+    if getattr(prefetcher, "shards", False):
+        return (x, y), prefetcher.global_n
+    return shard_batch(x, y), int(x.shape[0])
 
 
 def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criterion, optimizer, epoch, losses_forget, losses_remain,
@@ -339,9 +397,10 @@ def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criteri
         losses_total.update(out["total"], nr)
 
     for inputs_remain, labels_remain in iter(dataloader_remain):
-        inputs_remain = inputs_remain.to(device)
-        labels_remain = labels_remain.to(device)
-        (xr, yr), (xf, yf) = shard_batch(inputs_remain, labels_remain), shard_batch(inputs_forget, labels_forget)
+        n_r = int(inputs_remain.size(0))                               # the meters weigh by the GLOBAL batch sizes
+        xr, yr = shard_batch(inputs_remain, labels_remain)             # sharded on the host: each rank copies only its share over PCIe
+        xr, yr = xr.to(device), yr.to(device)
+        (xf, yf), n_f = _own_share(prefetcher, inputs_forget, labels_forget)
         res = unlearn_step_async(model, xr, yr, xf, yf, beta=beta, alpha=alpha, BND=BND,
                                  optimizer=optimizer, use_prototype=use_prototype, prototype_dict=prototype_dict,
                                  prototype_weight_forget=prototype_weight_forget, prototype_weight_remain=prototype_weight_remain,
@@ -350,7 +409,7 @@ def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criteri
         # steady state); at the steps where the reference prints or evaluates, the meters are brought fully up to date first
         if pending is not None:
             absorb(pending)
-        pending = (res, inputs_remain.size(0), inputs_forget.size(0))
+        pending = (res, n_r, n_f)
         if (((batch + 1) % DISP_FREQ == 0) or ((batch + 1) % VER_FREQ == 0)) and batch != 0:
             absorb(pending)
             pending = None
@@ -438,11 +497,8 @@ def eval_data(model, dataloader, device, mode: str, batch: int = 0):
         for images, labels in dataloader:
             images = m.prepare_images(images.to(device))
             labels = labels.to(device).long().contiguous()
-            eng = m.ensure_engine(images.shape[0])
-            m.sync_engine()
-            slot = m._take_slot()
-            B = eng.forward(images, labels, slot, use_lora=not m._merged(), **m.image_kwargs(images))
-            hits += eng.slot_tensor(slot, F.SLOT_CORRECT, B).sum()
+            for slot, _, B in m.inference_slots(images, labels):          # chunks of the engine's capacity: eval never grows the workspace
+                hits += m._engine.slot_tensor(slot, F.SLOT_CORRECT, B).sum()
             total += labels.size(0)
     accuracy = 100 * int(hits.item()) / max(total, 1)
     print("Test {} Accuracy:{:2f}%".format(mode, accuracy))

@@ -33,6 +33,7 @@ class EngineSpec:
     dropout: float = 0.0
     emb_dropout: float = 0.0
     head_type: int = 0          # 0 CosFace (ViT_face), 1 Linear + bias (torchvision heads.head)
+    precision: int = -1         # -1: GSLORA_PRECISION (default "split"); 0 fast (fp16 weights); 1 split (fp16 hi + lo weights, grads <= 1e-3)
 
     @property
     def tokens(self) -> int:
@@ -53,12 +54,13 @@ class VitEngine:
         if device.type != "cuda":
             raise F.GslError("gslora-b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         self.spec, self.device, self.max_batch, self.num_slots = spec, device, int(max_batch), int(num_slots)
+        self.precision = F.default_precision() if spec.precision < 0 else int(spec.precision)
         self.cfg = F.GslConfig(image_size=spec.image_size, patch_size=spec.patch_size, channels=spec.channels, dim=spec.dim,
                                depth=spec.depth, heads=spec.heads, mlp_dim=spec.mlp_dim, num_class=spec.num_class,
                                lora_rank=spec.lora_rank, max_batch=self.max_batch, num_slots=self.num_slots,
                                patch_order=spec.patch_order, attn_scale=spec.attn_scale, ln_eps=spec.ln_eps, cos_s=spec.cos_s,
                                cos_m=spec.cos_m, lora_scaling=1.0 / spec.lora_rank, grad_scale=spec.grad_scale,
-                               dropout=spec.dropout, emb_dropout=spec.emb_dropout, head_type=spec.head_type)
+                               dropout=spec.dropout, emb_dropout=spec.emb_dropout, head_type=spec.head_type, precision=self.precision)
         L = F.lib()
         nbytes = L.gsl_engine_workspace_bytes(ctypes.byref(self.cfg))
         if nbytes == 0:

@@ -96,22 +96,54 @@ class EngineBackedModel(nn.Module):
 
 
 
+    # Arithmetic of the frozen-weight GEMMs: None = GSLORA_PRECISION (default "split"), or "split" / "fast" per model
+    # (include/gslora.h GslConfig.precision).  Changing it re-creates the engine at the next forward.
+    gsl_precision: Optional[str] = None
+
+    def _spec(self) -> EngineSpec:
+        spec = self.engine_spec()
+        if self.gsl_precision is not None:
+            spec.precision = {"fast": F.PRECISION_FAST, "split": F.PRECISION_SPLIT}[self.gsl_precision]
+        return spec
+
     def ensure_engine(self, batch: int, slots: Optional[int] = None) -> VitEngine:
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise F.GslError("gslora-b200: ViT_face executes on a CUDA device (sm_100a) only; there is no CPU fallback")
         slots = slots or int(os.environ.get("GSLORA_SLOTS", "2"))
         e = self._engine
-        if e is None or e.device != dev or e.max_batch < batch or e.num_slots < slots:
+        spec = self._spec()
+        want_prec = F.default_precision() if spec.precision < 0 else spec.precision
+        if e is None or e.device != dev or e.max_batch < batch or e.num_slots < slots or e.precision != want_prec:
             old = e
-            cap = max(batch, old.max_batch if old is not None and old.device == dev else 0)
+            same_dev = old is not None and old.device == dev
+            cap = max(batch, old.max_batch if same_dev else 0)
+            # the workspace grows, the training state must not change: LoRA values are re-linked by sync_engine, the fused AdamW moments and the
+            # bias-correction step are carried over here (a fresh engine would silently restart Adam in the middle of a task)
+            carry = None
+            if old is not None and old.lora_flat.numel() == spec.depth * spec.lora_block_elems:
+                carry = (old.exp_avg.detach().clone(), old.exp_avg_sq.detach().clone(), old.opt_step)
+                old.workspace = None            # release the old activation workspace before the bigger one is allocated
             self._engine = None
             del old, e
-            self._engine = VitEngine(self.engine_spec(), dev, cap, slots)
+            self._engine = VitEngine(spec, dev, cap, slots)
+            if carry is not None:
+                self._engine.exp_avg.copy_(carry[0].to(dev))
+                self._engine.exp_avg_sq.copy_(carry[1].to(dev))
+                self._engine.opt_step = carry[2]
             self._frozen_sig = self._lora_sig = None
             self._slot_stamp = [0] * slots
             self._slot_next = 0
         return self._engine
+
+    def inference_chunk(self, batch: int) -> int:
+        """Images per engine call of a no-grad forward.  The workspace is sized for TRAINING (every activation the selective backward needs, for
+        max_batch x slots); an eval pass with a bigger loader batch (the drivers evaluate with 5x / 1000-image batches, train_own_forget_cl.py:
+        899-937) must not grow it -- that would pin tens of GB for a forward that saves nothing -- so it runs in chunks of the current capacity
+        (at least GSLORA_EVAL_CHUNK images, default 128, when no engine exists yet)."""
+        floor = int(os.environ.get("GSLORA_EVAL_CHUNK", "128"))
+        have = self._engine.max_batch if self._engine is not None else 0
+        return max(1, min(batch, max(have, floor)))
 
     def sync_engine(self, force_lora: bool = False):
         """Re-link parameters into the engine and refresh its fp16 operand caches if anything changed."""
@@ -157,6 +189,19 @@ class EngineBackedModel(nn.Module):
             return 0
         return int(torch.randint(1, 2 ** 62, (1,)).item())
 
+    def inference_slots(self, images: torch.Tensor, labels: Optional[torch.Tensor], dropout_seed: int = 0):
+        """No-grad forward of a (possibly large) batch in chunks of the engine's capacity: yields (slot, lo, B) per chunk, results in the slot
+        (eval_data counts hits, calculate_prototypes accumulates class sums).  `images` / `labels` already prepared (prepare_images, int64)."""
+        chunk = self.inference_chunk(int(images.shape[0]))
+        eng = self.ensure_engine(chunk)
+        self.sync_engine()
+        use_lora = not self._merged()
+        for lo in range(0, int(images.shape[0]), chunk):
+            slot = self._take_slot()
+            lab = labels[lo:lo + chunk] if labels is not None else None
+            B = eng.forward(images[lo:lo + chunk], lab, slot, use_lora=use_lora, dropout_seed=dropout_seed, **self.image_kwargs(images))
+            yield slot, lo, B
+
     def _merged(self) -> bool:
         states = {m.merged for pair in self.lora_layers() for m in pair}
         if len(states) != 1:
@@ -169,16 +214,22 @@ class EngineBackedModel(nn.Module):
         img = self.prepare_images(img)
         if label is not None:
             label = label.to(device=img.device, dtype=torch.int64).contiguous()
-        eng = self.ensure_engine(img.shape[0])
-        self.sync_engine()
         merged = self._merged()
         lora_params = self.lora_parameters()
         need_grad = torch.is_grad_enabled() and not merged and any(p.requires_grad for p in lora_params)
         if need_grad:
+            self.ensure_engine(img.shape[0])
+            self.sync_engine()
             return _EngineFn.apply(self, img, label, always_logits, *lora_params)
-        slot = self._take_slot()
-        B = eng.forward(img, label, slot, use_lora=not merged, dropout_seed=self.dropout_seed(), **self.image_kwargs(img))
-        emb = eng.slot_tensor(slot, F.SLOT_EMB, B).clone()
-        if label is None and not always_logits:
+        # no-grad forward: chunked to the engine's current capacity (see inference_chunk)
+        embs, logits = [], []
+        want_logits = label is not None or always_logits
+        for slot, lo, B in self.inference_slots(img, label, dropout_seed=self.dropout_seed()):
+            eng = self._engine
+            embs.append(eng.slot_tensor(slot, F.SLOT_EMB, B).clone())
+            if want_logits:
+                logits.append(eng.slot_tensor(slot, F.SLOT_LOGITS, B).clone())
+        emb = embs[0] if len(embs) == 1 else torch.cat(embs, dim=0)
+        if not want_logits:
             return emb
-        return eng.slot_tensor(slot, F.SLOT_LOGITS, B).clone(), emb
+        return (logits[0] if len(logits) == 1 else torch.cat(logits, dim=0)), emb

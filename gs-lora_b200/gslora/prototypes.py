@@ -27,15 +27,12 @@ def class_prototype_table(backbone, batches, device="cuda"):
         for images, labels in batches:
             images = m.prepare_images(images.to(device))
             labels = labels.to(device).long().contiguous()
-            B = int(images.shape[0])
-            eng = m.ensure_engine(B)
-            m.sync_engine()
-            if sums is None:
-                sums = torch.zeros(eng.spec.num_class, eng.spec.dim, dtype=torch.float32, device=eng.device)
-                counts = torch.zeros(eng.spec.num_class, dtype=torch.float32, device=eng.device)
-            slot = m._take_slot()
-            eng.forward(images, labels, slot, use_lora=not m._merged(), **m.image_kwargs(images))
-            eng.class_sums(slot, labels, B, sums, counts)
+            for slot, lo, B in m.inference_slots(images, labels):         # chunks in dataset order: the per-class fp32 summation order is unchanged
+                eng = m._engine
+                if sums is None:
+                    sums = torch.zeros(eng.spec.num_class, eng.spec.dim, dtype=torch.float32, device=eng.device)
+                    counts = torch.zeros(eng.spec.num_class, dtype=torch.float32, device=eng.device)
+                eng.class_sums(slot, labels[lo:lo + B].contiguous(), B, sums, counts)
     if sums is None:
         return None, None
     means = torch.empty_like(sums)

@@ -36,8 +36,8 @@ enum {
 
 /* C[M,N] = epi(A[M,K] * B[N,K]^T), fp16 operands, fp32 accumulation on tcgen05 tensor cores.
  * Replaces torch.nn.functional.linear / loralib.Linear.forward on the hot path
- * (vit_pytorch_face/vit_face.py:330-334,360,377,531; loralib Linear.forward: the LoRA term is an extra
- * K = 16 step when A carries T = x*A^T and B carries s*lora_B in 16 trailing columns) and the dX GEMMs
+ * (vit_pytorch_face/vit_face.py:330-334,360,377,531; for loralib Linear.forward the caller passes the merged
+ * operand B = fp16(W + s*lora_B*lora_A), which is what the engine caches) and the dX GEMMs
  * autograd builds for engine_cl.py:124.  drop_p > 0 applies a counter-based nn.Dropout mask (seed drop_seed, element index
  * row * N + col) to the produced value: before the residual add (RES), after the table add (PERIODIC), on out1 (GELU), and as a
  * factor in GELU_BWD. */
@@ -45,7 +45,13 @@ int gsl_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
                  int epi, const float* bias, void* out0, int64_t ld0, void* out1, int64_t ld1,
                  const void* aux, int64_t ldaux, int64_t aux_period, int cta_group, int block_n, float drop_p, uint32_t drop_seed,
                  void* stream);
-
+/* The same with a split B operand: C = epi(A * (B + B_lo)^T), B_lo = fp16(W - B) the rounding residual of the fp32 weight W
+ * (same shape / ldb as B).  Both terms are contracted against the SAME shared-memory A tile into one TMEM accumulator, so the
+ * frozen weights enter with ~22 significand bits (GslConfig.precision = 1). */
+int gsl_gemm_f16_split(const void* A, int64_t lda, const void* B, const void* B_lo, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                       int epi, const float* bias, void* out0, int64_t ld0, void* out1, int64_t ld1,
+                       const void* aux, int64_t ldaux, int64_t aux_period, int cta_group, int block_n, float drop_p, uint32_t drop_seed,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Op-level entry points (each one kernel family; used by the engine and by the parity tests)
@@ -67,8 +73,10 @@ int gsl_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const flo
 int gsl_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                       const float* gamma, const float* dres, int64_t lddres, float* dx, int64_t lddx, void* dx16, int64_t lddx16,
                       int64_t M, int D, void* stream);
-/* T[M, 0:16] = X[M,K] * A16[r,K]^T   (loralib Linear.forward's  x @ A^T ; backward U = dY @ B with A16 = B^T). r in {8,16}. */
+/* T[M, 0:16] = X[M,K] * A16[16,K]^T   (loralib Linear.forward's  x @ A^T ; backward U = dY @ B with A16 = B^T).  1 <= r <= 16; rows >= r of
+ * A16 are zero padding.  gsl_lora_down_split: A16 has 32 rows, [0,16) = fp16(A), [16,32) = fp16(A - fp16(A)); both feed one accumulator. */
 int gsl_lora_down(const void* X16, int64_t ldx, const void* A16, int64_t lda, void* out16, int64_t ldo, int64_t M, int K, int r, void* stream);
+int gsl_lora_down_split(const void* X16, int64_t ldx, const void* A32, int64_t lda, void* out16, int64_t ldo, int64_t M, int K, int r, void* stream);
 /* out[n, j] (or out[j, n] if transpose_out) (+)= scale * sum_m L[m, n] * R[m, j]  -- dB = s dY^T T, dA = s U^T X. */
 size_t gsl_skinny_tn_workspace(int64_t M, int N, int r);
 int gsl_skinny_tn(const void* L16, int64_t ldl, const void* R16, int64_t ldr, float* out, int64_t ldo, int transpose_out, float scale,
@@ -80,12 +88,19 @@ size_t gsl_lora_side_workspace(int64_t M, int N, int r);
 int gsl_lora_side(const void* L16, int64_t ldl, const void* P16, int64_t ldp, void* T16, int64_t ldt, const void* R16, int64_t ldr,
                   float* out, int64_t ldo, int transpose_out, float scale, int accumulate, int64_t M, int N, int r,
                   float* workspace, size_t workspace_bytes, void* stream);
+/* gsl_lora_side with a split P operand (32 rows: hi | lo, as gsl_lora_down_split) */
+int gsl_lora_side_split(const void* L16, int64_t ldl, const void* P32, int64_t ldp, void* T16, int64_t ldt, const void* R16, int64_t ldr,
+                        float* out, int64_t ldo, int transpose_out, float scale, int accumulate, int64_t M, int N, int r,
+                        float* workspace, size_t workspace_bytes, void* stream);
 /* Attention.forward (vit_face.py:358-379) on qkv fp16 [B*N, ld] (q | k | v blocks of heads*64 columns). */
 int gsl_attention_fwd(const void* qkv16, int64_t ld, void* out16, int64_t ldo, float* lse, int B, int N, int heads, float scale, void* stream);
 int gsl_attention_bwd(const void* qkv16, int64_t ld, const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
                       void* dqkv16, int64_t lddqkv, int B, int N, int heads, float scale, void* stream);
 /* fp32 -> fp16 cast (optional scale / transpose) used to build the frozen-weight operand caches. */
 int gsl_cast_f32_to_f16(const float* src, int64_t lds, void* dst16, int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose, void* stream);
+/* split form: dst16 = fp16(v), dst_lo16 = fp16(v - dst16), v = src * scale (the operand pair of gsl_gemm_f16_split) */
+int gsl_cast_f32_to_f16_split(const float* src, int64_t lds, void* dst16, void* dst_lo16, int64_t ldd, int64_t rows, int64_t cols, float scale,
+                              int transpose, void* stream);
 
 /* Fused group-Lasso + AdamW (engine_cl.get_structure_loss engine_cl.py:349-432 + torch.optim.AdamW as built by
  * timm create_optimizer, train_own_forget_cl.py:811-813).  group_offsets: device int32 [G+1] element offsets.
@@ -113,6 +128,9 @@ typedef struct GslConfig {
   float dropout;         /* nn.Dropout p of to_out / after GELU / after fc2 (vit_face.py:332,334,356), applied when dropout_seed != 0 */
   float emb_dropout;     /* nn.Dropout p after the pos-embedding add (vit_face.py:489,537) */
   int32_t head_type;     /* 0 = CosFace on LN(cls) (ViT_face), 1 = Linear + bias on LN(cls) (torchvision heads.head, modified_VIT.py:23-39) */
+  int32_t precision;     /* 0 = "fast": every frozen weight rounded to fp16 once (LoRA gradients ~1-2e-3 of the FP32 reference);
+                            1 = "split": weights and LoRA factors enter the GEMMs as fp16 hi + lo pairs (22 significand bits; gradients <= 1e-3,
+                            the north-star parity bar) at 2x the tensor-pipe work.  Activations are fp16 with fp32 accumulation in both. */
 } GslConfig;
 
 /* Frozen parameter pointer table order for gsl_engine_bind_params (fp32 device pointers, reference state_dict names):
