@@ -152,7 +152,12 @@ def run_gslora(args):
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     BATCH = wl["batch"]
+    # north-star denominator first (its 80 GB of fp32 autograd activations are freed before the engine's workspace is allocated)
+    gpu_ref = None
+    if world == 1 and args.workload == "p8s8_bs512" and not args.no_gpu_reference:
+        gpu_ref = gpu_reference(dev, BATCH)
     model, cfg = build_model(dev) if args.workload == "p8s8_bs512" else build_torchvision_model(dev, wl["cfg"])
+    model.gsl_precision = args.precision
     g = torch.Generator().manual_seed(100 + rank)
     S = cfg.image_size
     host = [torch.rand(BATCH, 3, S, S, generator=g).pin_memory(), torch.randint(0, 100, (BATCH,), generator=g).pin_memory(),
@@ -253,13 +258,32 @@ def run_gslora(args):
     images = 2 * BATCH * world
     value = images / ms * 1e3
     e2e_value = images / ms_e2e * 1e3
+    # the other precision mode beside it (resident leg only): the cost of meeting the 1e-3 gradient bar ("split") vs round 1's arithmetic ("fast")
+    other = None
+    if not args.single_mode:
+        other_mode = "fast" if args.precision == "split" else "split"
+        model.gsl_precision = other_mode                    # the next step re-creates the engine (optimizer state carried over)
+        ms_o, _, _ = timed(step_resident, args.steps, args.warmup)
+        other = {"precision": other_mode, "value": round(images / ms_o * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms_o, 3)}
+        model.gsl_precision = args.precision
     result = None
     if rank == 0:
         peaks = load_peaks()
         step_tflops = value * wl["flops"] / 1e12 / world
-        roof = kernel_roofline(dev, cfg, peaks, BATCH, wl["dropout"])
+        roof = kernel_roofline(dev, cfg, peaks, BATCH, wl["dropout"], split=args.precision == "split")
+        if not args.single_mode:
+            o = kernel_roofline(dev, cfg, peaks, BATCH, wl["dropout"], split=args.precision != "split")
+            roof["other_mode"] = {k: o[k] for k in ("kernel", "achieved", "frac", "ms_per_launch_pair", "executed_frac")}
+        # executed FLOPs: the last block's out-proj / FFN / attention run on the B cls rows only (exact dead-code elimination, gsl_engine.cu
+        # forward / backward), so the tensor cores execute less than the algorithmic count the reference's autograd would
+        exe = executed_flops_per_image(cfg)
+        exe_tflops = value * exe / 1e12 / world
         roof["step"] = dict(achieved=round(step_tflops, 1), peak=peaks["sustained"], unit="TFLOP/s", frac=round(step_tflops / peaks["sustained"], 4),
-                            note=f"whole step, algorithmic FLOPs per image {wl['flops'] / 1e9:.3f} G (BASELINE.md section 3) vs sustained bf16 peak (" + peaks["source"] + ")")
+                            executed=round(exe_tflops, 1), executed_frac=round(exe_tflops / peaks["sustained"], 4),
+                            executed_gflop_per_image=round(exe / 1e9, 3),
+                            note=f"whole step: `achieved` = algorithmic FLOPs per image {wl['flops'] / 1e9:.3f} G (BASELINE.md section 3), `executed` = the dense "
+                                 "FLOPs the engine really issues (last block on cls rows only; split mode's second MMA per k-step NOT counted), both vs "
+                                 "sustained bf16 peak (" + peaks["source"] + ")")
         h2d = sum(t.numel() * t.element_size() for t in host)
         result = {
             "metric": wl["metric"], "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -267,7 +291,11 @@ def run_gslora(args):
             "data": "synthetic",
             "config": {"workload": args.workload, "model": wl["model"],
                        "per_gpu_batch": f"{BATCH} remain + {BATCH} forget", "global_batch": images, "parallelism": f"dp{world}",
-                       "arithmetic": "fp16 operands, fp32 accumulate / residual stream / loss", "dropout": wl["dropout"],
+                       "precision": args.precision,
+                       "arithmetic": ("fp16 activations x (fp16 hi + fp16 lo) frozen weights and LoRA factors, fp32 accumulate / residual stream / loss: "
+                                      "logits and every LoRA gradient within 1e-3 of FP32 (tests/test_engine_gpu.py)") if args.precision == "split" else
+                                     "fp16 operands (one rounding per weight), fp32 accumulate / residual stream / loss: LoRA gradients 1-2.4e-3 of FP32",
+                       "dropout": wl["dropout"],
                        "cache": f"inputs_larger_than_l2 ({h2d / 1e6:.0f} MB images + multi-GB activations per step vs 126 MB L2)",
                        "loss": out["total"]},
             "clocks": sampler.summary(),
@@ -280,7 +308,12 @@ def run_gslora(args):
                         "note": "same step from raw uint8 pixels (transforms.PILToTensor()); /255 runs in the patchify kernel"}},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "other_precision_mode": other,
+            "gpu_reference": gpu_ref,
         }
+        if gpu_ref is not None:
+            gpu_ref["ratio"] = round(gpu_ref["ms_per_step"] / ms, 2)
+            gpu_ref["ratio_e2e"] = round(gpu_ref["ms_per_step"] / ms_e2e, 2)
         if world == 1 and not args.no_cpu_baseline and args.workload == "p8s8_bs512":
             result["cpu_baseline"] = cpu_baseline(sample_batch=96, steps=3)
     if world > 1:
@@ -290,7 +323,58 @@ def run_gslora(args):
         print(json.dumps(result), flush=True)
 
 
-def kernel_roofline(dev, cfg, peaks, BATCH=BATCH, DROPOUT=DROPOUT):
+def executed_flops_per_image(cfg):
+    """Dense FLOPs (2mnk) per image the engine issues: as BASELINE.md section 3 / oracle.flops_per_image, minus what the last block skips --
+    its attention is one query per (image, head), its out-proj / FFN and their backward run on the single cls row (gsl_engine.cu)."""
+    N, D, H, r, L = cfg.tokens, cfg.dim, cfg.mlp_dim, cfg.lora_rank, cfg.depth
+    inner = cfg.heads * 64
+    qkv, qk, out, fc, lora = 2 * N * D * 3 * inner, 2 * N * N * inner, 2 * N * inner * D, 2 * N * D * H, 2 * N * r * (D + H)
+    patch = 2 * (N - 1) * (3 * cfg.patch_size ** 2) * D
+    tok = 1.0 / N                                                   # share of the cls row
+    fwd = patch + (L - 1) * (qkv + 2 * qk + out + 2 * fc + 2 * lora) + (qkv + tok * (2 * qk + out + 2 * fc + 2 * lora))
+    ffn_bwd, attn_bwd = 2 * fc + 4 * lora, qkv + out + 4 * qk
+    dense_blocks = max(L - 2, 0)                                    # blocks 1 .. L-2: full FFN + attention backward; block 0: FFN only, no fc1 dX
+    bwd = dense_blocks * (ffn_bwd + attn_bwd) + (ffn_bwd - fc if L > 1 else 0) + tok * ffn_bwd + (qkv + tok * (out + 4 * qk) if L > 1 else 0)
+    return float(fwd + bwd)
+
+
+def gpu_reference(dev, B):
+    """BASELINE.md section 4 / north_star denominator: the reference step (oracle restatement of engine_cl.py:59-125: two forwards, CE + bounded
+    forget loss + structure loss, autograd backward, AdamW) as stock PyTorch FP32 eager, TF32 off, on THIS GPU at the headline batch, timed with
+    CUDA events outside the repo arm's timed region."""
+    from oracle import vit_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.P8S8
+    sd = {k: v.to(dev) for k, v in O.init_state_dict(cfg, seed=1337).items()}
+    g = torch.Generator().manual_seed(3)
+    xr, xf = torch.rand(B, 3, 112, 112, generator=g).to(dev), torch.rand(B, 3, 112, 112, generator=g).to(dev)
+    yr, yf = torch.randint(0, 100, (B,), generator=g).to(dev), torch.randint(0, 100, (B,), generator=g).to(dev)
+    state = {}
+
+    def step():
+        O.unlearn_step(sd, cfg, state, xr, yr, xf, yf, lr=HP["lr"], wd=HP["wd"], beta=HP["beta"], alpha=HP["alpha"], BND=HP["BND"])
+    try:
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out = dict(ms_per_step=round(ms, 2), images_per_s=round(2 * B / ms * 1e3, 1), batch=f"{B}+{B}",
+                   what="reference step, PyTorch FP32 eager (TF32 off, dropout 0) on the same B200: oracle/vit_oracle.py unlearn_step, 2 warm-up + 5 timed")
+    except torch.cuda.OutOfMemoryError as e:       # never take the box down for a side measurement
+        out = dict(error=f"out of memory: {str(e)[:120]}")
+    del sd, state, xr, xf
+    torch.cuda.empty_cache()
+    return out
+
+
+def kernel_roofline(dev, cfg, peaks, BATCH=BATCH, DROPOUT=DROPOUT, split=True):
     """Fused FFN+LoRA GEMM pair at the step's own shape (M = 1024 * 197 rows), timed live with CUDA events on the launching stream:
       fc1: x W1'^T + b1 -> G = Dropout(gelu(h)) and mask * gelu'(h)        (W' = W + s B A: the LoRA branch of loralib.Linear folded in)
       fc2: G W2'^T + b2, Dropout, + residual x
@@ -299,8 +383,10 @@ def kernel_roofline(dev, cfg, peaks, BATCH=BATCH, DROPOUT=DROPOUT):
     from gslora import _ffi as F
     M, D, H, r = 2 * BATCH * cfg.tokens, cfg.dim, cfg.mlp_dim, cfg.lora_rank
     x = (torch.randn(M, D, device=dev) * 0.5).half()
-    w1 = (torch.randn(H, D, device=dev) * 0.05).half()
-    w2 = (torch.randn(D, H, device=dev) * 0.02).half()
+    w1f, w2f = torch.randn(H, D, device=dev) * 0.05, torch.randn(D, H, device=dev) * 0.02
+    w1, w2 = w1f.half(), w2f.half()
+    w1lo = (w1f - w1.float()).half() if split else None      # precision mode "split": second term of each weight (gsl_gemm_f16_split)
+    w2lo = (w2f - w2.float()).half() if split else None
     b1, b2 = torch.randn(H, device=dev), torch.randn(D, device=dev)
     gp = torch.empty(M, H, device=dev, dtype=torch.half)
     g = torch.empty(M, H, device=dev, dtype=torch.half)
@@ -308,8 +394,8 @@ def kernel_roofline(dev, cfg, peaks, BATCH=BATCH, DROPOUT=DROPOUT):
     y = torch.empty(M, D, device=dev)
 
     def pair():
-        F.gemm_f16(x, w1, epi=F.EPI_GELU, bias=b1, out0=gp, out1=g, drop_p=DROPOUT, drop_seed=17)
-        F.gemm_f16(g, w2, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=res, drop_p=DROPOUT, drop_seed=18)
+        F.gemm_f16(x, w1, B_lo=w1lo, epi=F.EPI_GELU, bias=b1, out0=gp, out1=g, drop_p=DROPOUT, drop_seed=17)
+        F.gemm_f16(g, w2, B_lo=w2lo, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=res, drop_p=DROPOUT, drop_seed=18)
     for _ in range(3):
         pair()
     torch.cuda.synchronize()
@@ -333,13 +419,16 @@ def kernel_roofline(dev, cfg, peaks, BATCH=BATCH, DROPOUT=DROPOUT):
     alg_bytes = 2 * M * D + 2 * 2 * M * H + 2 * M * H + 2 * 4 * M * D + 4 * D * H
     if (M, D, H) != (2 * 512 * 197, 512, 2048):
         traffic = traffic_src = None                                   # the committed ncu capture is of the P8S8 shape
-    return dict(bound="tensor", kernel=f"gemm_tcgen05_kernel<2,256,EPI_GELU> + <2,256,EPI_RES_F32> (fused FFN+LoRA pair, dropout {DROPOUT})",
-                achieved=round(ach, 1), peak=peaks["burst"], unit="TFLOP/s", frac=round(ach / peaks["burst"], 4), traffic=traffic,
+    mma = 2.0 * M * D * H * 2 * (2 if split else 1)          # tensor-pipe FLOPs really issued (split mode: two MMAs per k-step)
+    return dict(bound="tensor", kernel=f"gemm_tcgen05_kernel<2,256,EPI_GELU,{'SPLIT' if split else 'plain'}> + <2,256,EPI_RES_F32,...> (FFN+LoRA pair, "
+                       f"precision {'split' if split else 'fast'}, dropout {DROPOUT})",
+                achieved=round(ach, 1), peak=peaks["burst"], unit="TFLOP/s", frac=round(ach / peaks["burst"], 4),
+                executed_frac=round(mma / ms / 1e9 / peaks["burst"], 4), traffic=traffic,
                 traffic_source=traffic_src, algorithmic_bytes=int(alg_bytes), ms_per_launch_pair=round(ms, 4),
                 peak_source=peaks["source"] + " cuBLAS bf16 burst")
 
 
-def cpu_baseline(sample_batch=16, steps=2):
+def cpu_baseline(sample_batch=16, steps=2, warm_batch=None):
     """The reference's CPU path (oracle port: oracle/vit_oracle.py restates vit_face.py / engine_cl.py:59-125; the reference tree itself
     does not travel to the GPU box) on all host cores, bounded sample: bs `sample_batch`+`sample_batch`, FP32."""
     from oracle import vit_oracle as O
@@ -352,27 +441,41 @@ def cpu_baseline(sample_batch=16, steps=2):
     xr, xf = torch.rand(B, 3, 112, 112, generator=g), torch.rand(B, 3, 112, 112, generator=g)
     yr, yf = torch.randint(0, 100, (B,), generator=g), torch.randint(0, 100, (B,), generator=g)
     state = {}
-    O.unlearn_step(sd, cfg, state, xr, yr, xf, yf, lr=HP["lr"], wd=HP["wd"], beta=HP["beta"], alpha=HP["alpha"], BND=HP["BND"])
+    w = warm_batch or B         # warm-up (thread pool, allocator): a small batch is enough when one full step costs tens of seconds
+    O.unlearn_step(sd, cfg, state, xr[:w], yr[:w], xf[:w], yf[:w], lr=HP["lr"], wd=HP["wd"], beta=HP["beta"], alpha=HP["alpha"], BND=HP["BND"])
     t0 = time.perf_counter()
     for _ in range(steps):
         O.unlearn_step(sd, cfg, state, xr, yr, xf, yf, lr=HP["lr"], wd=HP["wd"], beta=HP["beta"], alpha=HP["alpha"], BND=HP["BND"])
     dt = (time.perf_counter() - t0) / steps
     return dict(value=round(2 * B / dt, 2), unit="images/s", cores=cores, kind="port",
-                sample=f"oracle port of the reference step (PyTorch FP32 eager, dropout 0), bs {B}+{B}, 1 warm-up + {steps} timed steps, {dt:.2f} s/step")
+                sample=f"oracle port of the reference step (PyTorch FP32 eager, dropout 0), bs {B}+{B}, 1 warm-up (bs {w}+{w}) + {steps} timed steps, {dt:.2f} s/step")
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path, via the oracle port, on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle port of engine_cl.py:59-125 over vit_face.py; the reference
+    tree itself does not travel to the GPU box), all host cores, FP32, at the HEADLINE batch 512+512 -- the same config as the repo arm --
+    when host memory allows (autograd keeps ~80 MB of fp32 activations per image), else the largest halving that fits.  One step is tens of
+    seconds on CPU, so the run is 1 small warm-up step + at most 2 timed steps whatever --steps says."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     B = args.ref_batch
-    steps = max(1, min(args.steps, 3))
-    cb = cpu_baseline(sample_batch=B, steps=steps)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        while B > 16 and 2 * B * 80e6 * 1.3 > avail:
+            B //= 2
+    except Exception:
+        pass
+    steps = max(1, min(args.steps, 2))
+    cb = cpu_baseline(sample_batch=B, steps=steps, warm_batch=8)
+    same = B == BATCH
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
            "warmup": 1, "ms_per_step": round(2 * B / cb["value"] * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "p8s8_bs512", "sample": f"bs {B}+{B} per step (bounded sample of the 512+512 workload)", "device": "host CPU"},
+           "config": {"workload": "p8s8_bs512", "per_gpu_batch": f"{B} remain + {B} forget", "global_batch": 2 * B,
+                      "sample": ("the full 512+512 step" if same else f"bs {B}+{B} per step (host memory bounds the sample of the 512+512 workload)"),
+                      "device": "host CPU", "dropout": 0.0},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -386,7 +489,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="p8s8_bs512", choices=sorted(WORKLOADS))
     ap.add_argument("--no-u8-leg", action="store_true")
-    ap.add_argument("--ref-batch", type=int, default=96, help="--impl reference: images per stream of the bounded CPU sample")
+    ap.add_argument("--precision", default="split", choices=["split", "fast"],
+                    help="split (default): fp16 hi+lo weights, gradients within the 1e-3 parity bar; fast: one fp16 rounding per weight")
+    ap.add_argument("--single-mode", action="store_true", help="skip the resident leg of the other precision mode")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the FP32-eager reference step on the GPU (north-star denominator)")
+    ap.add_argument("--ref-batch", type=int, default=BATCH, help="--impl reference: images per stream of the CPU step (default: the headline 512)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "gslora":
         args.warmup = 3

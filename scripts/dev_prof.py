@@ -40,6 +40,31 @@ if "f16" in what:
     qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.half)
     timeit(lambda: F.gemm_f16(xn, Wq, epi=F.EPI_F16, out0=qkv), "QKV F16 gemm", flops=2.0 * M * 3 * D * D)
     del xn, Wq, qkv
+if "split" in what:
+    # precision mode "split": the same GEMMs with a (hi, lo) weight pair -- two MMAs per k-step on one A tile
+    def pair(n, k, std=0.05):
+        w = torch.randn(n, k, device=dev) * std
+        hi = w.half()
+        return hi, (w - hi.float()).half()
+    A = (torch.randn(M, D, device=dev) * 0.5).half(); bias = torch.randn(H, device=dev)
+    W, Wl = pair(H, D)
+    o0 = torch.empty(M, H, device=dev, dtype=torch.half); o1 = torch.empty(M, H, device=dev, dtype=torch.half)
+    timeit(lambda: F.gemm_f16(A, W, B_lo=Wl, epi=F.EPI_GELU, bias=bias, out0=o0, out1=o1, drop_p=0.1, drop_seed=1234), "SPLIT fc1 GELU gemm, dropout 0.1", flops=2.0 * M * H * D)
+    timeit(lambda: F.gemm_f16(A, W, B_lo=Wl, epi=F.EPI_GELU_BWD, out0=o1, aux=o0), "SPLIT dH gemm (x saved gelu')", flops=2.0 * M * H * D)
+    Wq, Wql = pair(3 * D, D)
+    qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.half)
+    timeit(lambda: F.gemm_f16(A, Wq, B_lo=Wql, epi=F.EPI_F16, out0=qkv), "SPLIT QKV F16 gemm", flops=2.0 * M * 3 * D * D)
+    timeit(lambda: F.gemm_f16(qkv, Wq.t().contiguous(), B_lo=Wql.t().contiguous(), epi=F.EPI_F16, out0=A), "SPLIT dLN1 F16 gemm (K=1536)", flops=2.0 * M * 3 * D * D)
+    del qkv, Wq, Wql
+    W2, W2l = pair(D, H)
+    x = torch.randn(M, D, device=dev); y = torch.empty(M, D, device=dev); b2 = torch.randn(D, device=dev)
+    timeit(lambda: F.gemm_f16(o1, W2, B_lo=W2l, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=x, drop_p=0.1, drop_seed=99), "SPLIT fc2 RES gemm, dropout 0.1", flops=2.0 * M * D * H)
+    y16 = torch.empty(M, D, device=dev, dtype=torch.half)
+    timeit(lambda: F.gemm_f16(o1, W2, B_lo=W2l, epi=F.EPI_F16, out0=y16), "SPLIT dXn F16 gemm (K=2048)", flops=2.0 * M * D * H)
+    Wo, Wol = pair(D, D)
+    timeit(lambda: F.gemm_f16(A, Wo, B_lo=Wol, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=x), "SPLIT out-proj RES gemm (K=512)", flops=2.0 * M * D * D)
+    timeit(lambda: F.gemm_f16(A, Wo, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=x), "plain out-proj RES gemm (K=512)", flops=2.0 * M * D * D)
+    del A, W, Wl, o0, o1, W2, W2l, x, y, y16
 if "attn" in what:
     qkv = torch.randn(M, 3 * D, device=dev).half(); out = torch.empty(M, D, device=dev, dtype=torch.half); lse = torch.empty(B * heads * N, device=dev)
     sc = 512 ** -0.5

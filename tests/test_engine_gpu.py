@@ -10,20 +10,15 @@ import torch
 from oracle import vit_oracle as O
 
 pytestmark = pytest.mark.gpu
-# north_star tolerance: 1e-3 relative.  Metric: ||x - ref||_2 / ||ref||_2 (SURVEY section 7 "Hard parts").
-# Measured on B200 at the config-2 shape against the FP32 reference (tests/dev_parity.py, weight seeds 1337 / 1 / 2 / 3 / 4):
-#   logits                         5.2e-4  5.1e-4  5.5e-4  4.9e-4  4.5e-4     (well inside 1e-3 for every seed)
-#   all LoRA gradients concatenated 1.02e-3 1.38e-3 1.29e-3 7.1e-4  1.01e-3   (batch-size independent: 9.4e-4 .. 1.02e-3 for bs 8 .. 256)
-#   worst single tensor            1.6e-3  2.1e-3  2.4e-3  1.3e-3  2.0e-3
-# The gradient error is the fp16-operand / fp32-accumulate floor: it is systematic (set by how the frozen weights round to fp16, not
-# by per-sample noise), it moves +-40 % with the weight seed and it is reached identically by the K-extension and the merged-weight
-# formulations of the LoRA branch.  The CosFace head (s = 64) turns the 5e-4 logit error into a ~1e-3 error of d loss / d logits,
-# which every LoRA gradient inherits as a common factor.  bf16 operands give 7e-3.  Hence: the north-star bound is asserted on the
-# logits; the gradients are held to 2e-3 (worst tensor 3.5e-3) and the seed table above is the honest statement of where they sit.
+# north_star tolerance: 1e-3 relative, ||x - ref||_2 / ||ref||_2, logits and EVERY LoRA gradient tensor.
+# Precision mode "split" (the engine default, GslConfig.precision = 1) is held to exactly that.  Mode "fast" (one fp16 rounding per frozen
+# weight, round 1's arithmetic) keeps its measured floor -- logits 5e-4, gradients 0.7-1.4e-3 concatenated / 1.3-2.4e-3 worst tensor over the
+# five weight seeds -- and is tested against the looser, documented bounds below (DESIGN.md section 2 has both tables).
 TOL_LOGITS = 1e-3
-TOL_GRAD_ALL = 2e-3          # all LoRA gradients concatenated, P8S8 shapes
-TOL_GRAD_ALL_TOY = 2e-3      # dim-128 toy fixtures
-TOL_GRAD_TENSOR = 3.5e-3     # worst single tensor
+TOL_GRAD_ALL = 1e-3          # all LoRA gradients concatenated
+TOL_GRAD_ALL_TOY = 1e-3      # dim-128 toy fixtures
+TOL_GRAD_TENSOR = 1e-3       # worst single tensor
+TOL_FAST_GRAD_ALL, TOL_FAST_GRAD_TENSOR = 2e-3, 3.5e-3
 
 
 def rel(a, b):
@@ -199,12 +194,13 @@ def test_structure_loss_group_types_match_engine_py_formula(golden_dir, group_ty
         assert (p.data - ref_p[n].data).abs().max() < 2e-6, n
 
 
-def test_p8s8_batch_vs_oracle_fp32_on_gpu():
-    """Config-2 shape at bs 32+32: engine vs the oracle executed in torch FP32 on the same GPU (TF32 off)."""
+@pytest.mark.parametrize("seed,mode", [(1337, "split"), (1, "split"), (2, "split"), (3, "split"), (4, "split"), (1337, "fast"), (2, "fast")])
+def test_p8s8_batch_vs_oracle_fp32_on_gpu(seed, mode):
+    """Config-2 shape at bs 32+32: engine vs the oracle executed in torch FP32 on the same GPU (TF32 off), five weight seeds."""
     import engine_cl
     torch.backends.cuda.matmul.allow_tf32 = False
     cfg = O.P8S8
-    sd = O.init_state_dict(cfg, seed=1337)
+    sd = O.init_state_dict(cfg, seed=seed)
     gen = torch.Generator().manual_seed(7)
     B = 32
     xr, xf = torch.rand(B, 3, 112, 112, generator=gen).cuda(), torch.rand(B, 3, 112, 112, generator=gen).cuda()
@@ -212,6 +208,7 @@ def test_p8s8_batch_vs_oracle_fp32_on_gpu():
     sd_gpu = {k: v.cuda() for k, v in sd.items()}
     ref, ref_grads = O.unlearn_grads(sd_gpu, cfg, xr, yr, xf, yf, beta=0.15, alpha=1e-4, BND=105.0, include_structure=False)
     model = build_model(cfg, sd)
+    model.gsl_precision = mode
     crit = torch.nn.CrossEntropyLoss()
     out_r, _ = model(xr, yr)
     out_f, _ = model(xf, yf)
@@ -221,9 +218,12 @@ def test_p8s8_batch_vs_oracle_fp32_on_gpu():
     lr_, lf_ = rel(out_r, ref["logits_r"]), rel(out_f, ref["logits_f"])
     per = {n: rel(model.get_parameter(n).grad, ref_grads[n]) for n in names}
     allrel = rel(torch.cat([model.get_parameter(n).grad.flatten() for n in names]), torch.cat([ref_grads[n].flatten() for n in names]))
-    print(f"P8S8 bs32+32: logits {lr_:.2e}/{lf_:.2e} grads all {allrel:.2e} worst {max(per.values()):.2e}")
+    print(f"P8S8 bs32+32 seed {seed} {mode}: logits {lr_:.2e}/{lf_:.2e} grads all {allrel:.2e} worst {max(per.values()):.2e}")
     assert lr_ < TOL_LOGITS and lf_ < TOL_LOGITS
-    assert allrel < TOL_GRAD_ALL and max(per.values()) < TOL_GRAD_TENSOR
+    if mode == "split":
+        assert allrel < TOL_GRAD_ALL and max(per.values()) < TOL_GRAD_TENSOR, (allrel, max(per.values()))
+    else:
+        assert allrel < TOL_FAST_GRAD_ALL and max(per.values()) < TOL_FAST_GRAD_TENSOR, (allrel, max(per.values()))
 
 
 def test_eval_merge_unmerge_roundtrip(golden_dir):
@@ -293,7 +293,8 @@ def test_dropout_step_matches_oracle_with_replayed_masks():
     assert rel(logits, ref_logits) < TOL_LOGITS
     got = torch.cat([m.get_parameter(n).grad.flatten() for n in names])
     want = torch.cat([g.flatten() for g in ref_grads])
-    assert rel(got, want) < 1.5e-3
+    print(f"dropout step: logits {rel(logits, ref_logits):.2e} grads {rel(got, want):.2e}")
+    assert rel(got, want) < 1e-3
     # the masks really drop ~p of the activations and eval mode is deterministic / mask-free
     assert abs(float((masks[("gelu", 0)] == 0).float().mean()) - p) < 5e-3
     m.eval()
@@ -338,7 +339,8 @@ def _tv_pair(image_size, patch, layers, heads, hidden, mlp, classes, rank, seed)
 
 @pytest.mark.parametrize("shape", [dict(image_size=64, patch=16, layers=3, heads=2, hidden=128, mlp=256, classes=10, rank=8, B=5),
                                    dict(image_size=224, patch=16, layers=12, heads=12, hidden=768, mlp=3072, classes=100, rank=8, B=4),
-                                   dict(image_size=224, patch=16, layers=2, heads=16, hidden=1024, mlp=4096, classes=100, rank=16, B=3)])
+                                   dict(image_size=224, patch=16, layers=2, heads=16, hidden=1024, mlp=4096, classes=100, rank=16, B=3),
+                                   dict(image_size=224, patch=16, layers=24, heads=16, hidden=1024, mlp=4096, classes=100, rank=16, B=4)])
 def test_torchvision_family_matches_torchvision_fp32(shape):
     """Configs 4 / 5 (ViT-B/16 r=8, ViT-L/16-width r=16): logits, cls embedding and LoRA gradients vs torchvision FP32 eager."""
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -352,13 +354,13 @@ def test_torchvision_family_matches_torchvision_fp32(shape):
     logits, emb = mine(x, y)
     torch.nn.functional.cross_entropy(logits, y).backward()
     assert emb.shape == (B, shape["hidden"])
-    assert rel(logits, ref_logits) < 2e-3
+    assert rel(logits, ref_logits) < TOL_LOGITS, rel(logits, ref_logits)
     names = [n for n, p in ref.named_parameters() if p.requires_grad]
     assert len(names) == 4 * shape["layers"]
     got = torch.cat([mine.get_parameter(n).grad.flatten() for n in names])
     want = torch.cat([ref.get_parameter(n).grad.flatten() for n in names])
     print(f"tv family {shape['hidden']}: logits {rel(logits, ref_logits):.2e} grads {rel(got, want):.2e}")
-    assert rel(got, want) < 2e-3
+    assert rel(got, want) < TOL_GRAD_ALL, rel(got, want)
     import engine_cl
     s_loss = engine_cl.get_structure_loss(mine, imagenet=True)
     want_s = sum(torch.sqrt(sum((ref.get_parameter(n) ** 2).sum() for n in names[4 * i:4 * i + 4])) for i in range(shape["layers"]))

@@ -203,3 +203,86 @@ def test_prototype_kl_matches_reference_expression(F, Br, Bf, D, C, bnd):
     demb = torch.empty(B, D, device="cuda")
     F.check(F.lib().gsl_prototype_kl_grad(F.ptr(emb), F.ptr(lab), F.ptr(proto), F.ptr(sums), Br, B, D, w_f, w_r, bnd, F.ptr(demb), F.cur_stream()))
     assert (demb - e.grad).abs().max() < 1e-5 * max(1.0, float(e.grad.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------ split-precision operands (GslConfig.precision = 1)
+def _split(F, W, transpose=False):
+    """(hi, lo) fp16 pair of an fp32 matrix through the library's own cast (gsl_cast_f32_to_f16_split)."""
+    R, C = W.shape
+    shape = (C, R) if transpose else (R, C)
+    hi = torch.empty(shape, device="cuda", dtype=torch.half); lo = torch.empty(shape, device="cuda", dtype=torch.half)
+    F.check(F.lib().gsl_cast_f32_to_f16_split(F.ptr(W), C, F.ptr(hi), F.ptr(lo), shape[1], R, C, 1.0, 1 if transpose else 0, F.cur_stream()))
+    return hi, lo
+
+
+@pytest.mark.parametrize("M,N,K,epi,cg,bn", [(512, 512, 512, 1, 2, 256), (1000, 1536, 528, 1, 2, 256), (777, 512, 2064, 4, 2, 256), (520, 2048, 528, 1, 1, 256),
+                                             (300, 384, 192, 1, 1, 128), (9456, 512, 2048, 4, 0, 0), (9456, 2048, 512, 2, 0, 0)])
+def test_gemm_split_weight_is_exact_in_the_weight(F, M, N, K, epi, cg, bn):
+    """A (B_hi + B_lo)^T against the fp32 product with the UNROUNDED weight: the only rounding left is the fp16 A operand, which the test
+    applies to the reference too -- so fp32-output epilogues must agree to accumulation-order level, 100x below one fp16 weight rounding."""
+    torch.manual_seed(M + N + K)
+    A = (torch.randn(M, K, device="cuda") * 0.5).half()
+    W = torch.randn(N, K, device="cuda") * 0.05
+    hi, lo = _split(F, W)
+    assert torch.equal(hi, W.half()) and rel(hi.float() + lo.float(), W) < 2e-6
+    hiT, loT = _split(F, W, transpose=True)
+    assert torch.equal(hiT, hi.t().contiguous()) and torch.equal(loT, lo.t().contiguous())
+    bias = torch.randn(N, device="cuda")
+    exact = (A.double() @ W.double().t()).float() + bias
+    if epi == F.EPI_F32:
+        out0 = torch.empty(M, N, device="cuda")
+        F.gemm_f16(A, hi, B_lo=lo, epi=epi, bias=bias, out0=out0, cta_group=cg, block_n=bn)
+        one = torch.empty(M, N, device="cuda")
+        F.gemm_f16(A, hi, epi=epi, bias=bias, out0=one, cta_group=cg, block_n=bn)
+        assert rel(out0, exact) < 3e-6
+        assert rel(one, exact) > 20 * rel(out0, exact)                 # the single-rounding product sits at the fp16 weight floor (~2e-4)
+    elif epi == F.EPI_RES_F32:
+        res = torch.randn(M, N, device="cuda"); out0 = torch.empty(M, N, device="cuda")
+        F.gemm_f16(A, hi, B_lo=lo, epi=epi, bias=bias, out0=out0, aux=res, cta_group=cg, block_n=bn)
+        assert rel(out0, exact + res) < 3e-6
+    else:       # GELU: fp16 outputs, checked to fp16 rounding
+        gp = torch.empty(M, N, device="cuda", dtype=torch.half); g = torch.empty(M, N, device="cuda", dtype=torch.half)
+        F.gemm_f16(A, hi, B_lo=lo, epi=epi, bias=bias, out0=gp, out1=g, cta_group=cg, block_n=bn)
+        want = torch.nn.functional.gelu(exact)
+        assert (g.float() - want).abs().max() <= 1e-3 * want.abs().max() + 1e-4
+
+
+@pytest.mark.parametrize("M,K,r", [(1000, 512, 8), (197 * 5, 2048, 8), (333, 1024, 16), (300, 512, 4), (300, 768, 12), (100, 272 - 16, 5)])
+def test_lora_down_split_and_odd_ranks(F, M, K, r):
+    """T = X P^T with P = hi + lo (32-row operand): exact in P; ranks 1..16 ride on the zero-padded 16-row tiles."""
+    torch.manual_seed(3)
+    X = torch.randn(M, K, device="cuda").half()
+    P = torch.randn(r, K, device="cuda") * 0.05
+    P32 = torch.zeros(32, K, device="cuda", dtype=torch.half)
+    P32[:r] = P.half(); P32[16:16 + r] = (P - P.half().float()).half()
+    T = torch.full((M, 16), 7.0, device="cuda", dtype=torch.half)
+    F.check(F.lib().gsl_lora_down_split(F.ptr(X), K, F.ptr(P32), K, F.ptr(T), 16, M, K, r, F.cur_stream()))
+    want = (X.double() @ P.double().t()).float()
+    assert (T[:, :r].float() - want).abs().max() <= 1e-3 * want.abs().max() + 1e-5      # fp16 store rounding only
+    assert (T[:, r:] == 0).all()
+    T1 = torch.full((M, 16), 7.0, device="cuda", dtype=torch.half)
+    F.check(F.lib().gsl_lora_down(F.ptr(X), K, F.ptr(P32), K, F.ptr(T1), 16, M, K, r, F.cur_stream()))
+    want1 = X.float() @ P32[:r].float().t()
+    assert (T1[:, :r].float() - want1).abs().max() <= 1e-3 * want1.abs().max() + 1e-5
+    assert (T1[:, r:] == 0).all()
+
+
+@pytest.mark.parametrize("M,N,r,tr", [(197 * 9, 2048, 8, 1), (5000, 3072, 8, 0), (300, 1024, 16, 1), (333, 2048, 6, 0), (200, 320, 8, 0)])
+def test_lora_side_split(F, M, N, r, tr):
+    torch.manual_seed(5)
+    L = torch.randn(M, N, device="cuda").half()
+    P = torch.randn(r, N, device="cuda") * 0.05
+    P32 = torch.zeros(32, N, device="cuda", dtype=torch.half)
+    P32[:r] = P.half(); P32[16:16 + r] = (P - P.half().float()).half()
+    R = torch.zeros(M, 16, device="cuda", dtype=torch.half); R[:, :r] = torch.randn(M, r, device="cuda").half()
+    T = torch.full((M, 16), 3.0, device="cuda", dtype=torch.half)
+    nb = F.lib().gsl_lora_side_workspace(M, N, r)
+    ws = torch.empty(nb // 4 + 16, device="cuda")
+    out = torch.zeros((r, N) if tr else (N, r), device="cuda")
+    F.check(F.lib().gsl_lora_side_split(F.ptr(L), N, F.ptr(P32), N, F.ptr(T), 16, F.ptr(R), 16, F.ptr(out), N if tr else r, tr, 0.5, 0, M, N, r,
+                                        F.ptr(ws), nb, F.cur_stream()))
+    wantT = (L.double() @ P.double().t()).float()
+    assert (T[:, :r].float() - wantT).abs().max() <= 1e-3 * wantT.abs().max() + 1e-5
+    assert (T[:, r:] == 0).all()
+    wantQ = 0.5 * (L.float().t() @ R[:, :r].float())
+    assert rel(out.t() if tr else out, wantQ) < 1e-5
