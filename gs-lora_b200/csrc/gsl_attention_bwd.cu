@@ -463,7 +463,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV0, const __grid
     }
 }
 
-int attention_bwd_tc(const __half* qkv, int64_t ld, const __half* out, int64_t ldo, const __half* dout, int64_t lddo, const float* lse,
+int attention_bwd(const __half* qkv, int64_t ld, const __half* out, int64_t ldo, const __half* dout, int64_t lddo, const float* lse,
                      __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s) {
     GSL_REQUIRE(N >= 1 && N <= AB_MAX_TOKENS, "attention_bwd: tokens=%d outside [1, %d]", N, AB_MAX_TOKENS);
     GSL_REQUIRE(ld % 8 == 0 && lddo % 8 == 0 && ldo % 8 == 0 && lddqkv % 8 == 0, "attention_bwd: pitches must be multiples of 8 halves");

@@ -358,7 +358,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
     }
 }
 
-int attention_fwd_tc(const __half* qkv, int64_t ld, __half* out, int64_t ldo, float* lse, int B, int N, int heads, float scale, cudaStream_t s) {
+int attention_fwd(const __half* qkv, int64_t ld, __half* out, int64_t ldo, float* lse, int B, int N, int heads, float scale, cudaStream_t s) {
     GSL_REQUIRE(N >= 1 && N <= AF_MAX_TOKENS, "attention: tokens=%d outside [1, %d]", N, AF_MAX_TOKENS);
     GSL_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "attention: pitches must be multiples of 8 halves");
     GSL_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention: output must be 16-byte aligned");

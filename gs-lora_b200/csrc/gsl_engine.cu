@@ -347,6 +347,12 @@ int Engine::refresh_lora(cudaStream_t s) {
     return 0;
 }
 
+// experiment switch (dev): GSLORA_DXN32=1 keeps the dLN GEMM outputs in fp32 instead of fp16
+static bool dxn_fp32() {
+    static const bool on = [] { const char* e = getenv("GSLORA_DXN32"); return e && e[0] == '1'; }();
+    return on;
+}
+
 // per-site dropout seeds: site 0 emb (block index = depth), 1 attention to_out, 2 after GELU, 3 after fc2
 static inline uint32_t site_seed(uint64_t base, int block, int site) {
     return drop_hash((uint32_t)(block * 4 + site + 1), (uint32_t)base ^ (uint32_t)(base >> 32));
@@ -481,10 +487,10 @@ int Engine::ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, fl
     {   // dLN2 = dH W1'
         GemmArgs g;
         g.A = dh; g.lda = H; g.B = c.fc1T_w16.hi; g.B_lo = c.fc1T_w16.lo; g.ldb = H; g.M = M; g.N = D; g.K = H;
-        g.epi = EPI_F16; g.out0 = dxn; g.ld0 = D;            // fp16: halves the traffic of the LayerNorm-backward pass that consumes it
+        g.epi = dxn_fp32() ? EPI_F32 : EPI_F16; g.out0 = dxn; g.ld0 = D;            // fp16: halves the traffic of the LayerNorm-backward pass that consumes it
         if ((rc = gemm_f16(g, s))) return rc;
     }
-    return layernorm_bwd(dxn, 1, D, x_mid, D, ln_mean, ln_rstd, f.ln2_w, dx, D, dx, D, dy, D, M, D, pdrop, site_seed(dseed, l, 1), s);
+    return layernorm_bwd(dxn, dxn_fp32() ? 0 : 1, D, x_mid, D, ln_mean, ln_rstd, f.ln2_w, dx, D, dx, D, dy, D, M, D, pdrop, site_seed(dseed, l, 1), s);
 }
 
 int Engine::backward(int slot, const float* dlogits, const float* demb, int accumulate, cudaStream_t s) {
@@ -526,11 +532,11 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         {   // dLN1 = dQKV Wqkv  (dense: dK / dV reach every token)
             GemmArgs g;
             g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16.hi; g.B_lo = c.qkv_wT16.lo; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
-            g.epi = EPI_F16; g.out0 = dxn32; g.ld0 = D;
+            g.epi = dxn_fp32() ? EPI_F32 : EPI_F16; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
         // residual gradient of this block's input: zero except the cls rows, which LayerNorm backward picks from the compacted cls_dx32
-        if ((rc = layernorm_bwd(dxn32, 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, cls_dx32, D, dx32, D, dy16, D, M, D, pdrop,
+        if ((rc = layernorm_bwd(dxn32, dxn_fp32() ? 0 : 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, cls_dx32, D, dx32, D, dy16, D, M, D, pdrop,
                                 site_seed(dseed, l - 1, 3), s, tokens))) return rc;
     }
     for (int l = L - 2; l >= 0; --l) {
@@ -552,10 +558,10 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         {   // dLN1 = dQKV Wqkv
             GemmArgs g;
             g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16.hi; g.B_lo = c.qkv_wT16.lo; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
-            g.epi = EPI_F16; g.out0 = dxn32; g.ld0 = D;
+            g.epi = dxn_fp32() ? EPI_F32 : EPI_F16; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
-        if ((rc = layernorm_bwd(dxn32, 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dy16, D, M, D, pdrop,
+        if ((rc = layernorm_bwd(dxn32, dxn_fp32() ? 0 : 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dy16, D, M, D, pdrop,
                                 site_seed(dseed, l - 1, 3), s))) return rc;
     }
     return 0;

@@ -74,7 +74,7 @@ int cast_f32_to_f16(const float* src, int64_t lds, __half* dst, int64_t ldd, int
                     int transpose, cudaStream_t s, __half* dst_lo = nullptr);     // dst_lo: fp16(v - fp16(v)), same layout as dst
 int fill_zero(void* ptr, size_t bytes, cudaStream_t s);
 
-// ---- attention (gsl_attention.cu); qkv fp16 [B*N, ld] with q|k|v column blocks of heads*64
+// ---- attention (gsl_attention_fwd.cu / gsl_attention_bwd.cu, tcgen05); qkv fp16 [B*N, ld] with q|k|v column blocks of heads*64
 int attention_fwd(const __half* qkv, int64_t ld, __half* out, int64_t ldo, float* lse, int B, int N, int heads, float scale, cudaStream_t s);
 int attention_bwd(const __half* qkv, int64_t ld, const __half* out, int64_t ldo, const __half* dout, int64_t lddo, const float* lse,
                   __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s);

@@ -37,7 +37,9 @@ class QLinear(torch.autograd.Function):
     """y = xq Wf^T (+ b), dx = dyq Wb; dW = dyq^T xq flows to the (differentiable) merged weight -> dA / dB."""
     @staticmethod
     def forward(ctx, x, W, b, w_fwd, w_bwd, act):
-        xq = r11(x) if act else x
+        act_f, act_b = (act if isinstance(act, tuple) else (act, act))
+        act = act_b
+        xq = r11(x) if act_f else x
         Wf = r11(W) if w_fwd else W
         ctx.save_for_backward(xq, W)
         ctx.w_bwd, ctx.act, ctx.has_b = w_bwd, act, b is not None
@@ -66,10 +68,11 @@ def forward(sd, cfg, img, label, knobs):
     for i in range(cfg.depth):
         xn = F.layer_norm(x, (D,), sd[O.blk(i, "0.fn.norm.weight")], sd[O.blk(i, "0.fn.norm.bias")], cfg.ln_eps)
         qkv = QLinear.apply(xn, sd[O.blk(i, "0.fn.fn.to_qkv.weight")], None, *knobs["qkv"], act)
-        qkv = RoundST.apply(qkv, act, act)
+        af, ab = (act if isinstance(act, tuple) else (act, act))
+        qkv = RoundST.apply(qkv, af, ab)
         q, k, v = [t.reshape(b, n + 1, cfg.heads, -1).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1)]
         dots = torch.einsum("bhid,bhjd->bhij", q, k) * cfg.attn_scale
-        attn = RoundST.apply(dots.softmax(dim=-1), act, act)
+        attn = RoundST.apply(dots.softmax(dim=-1), af, ab)
         out = torch.einsum("bhij,bhjd->bhid", attn, v).permute(0, 2, 1, 3).reshape(b, n + 1, -1)
         x = QLinear.apply(out, sd[O.blk(i, "0.fn.fn.to_out.0.weight")], sd[O.blk(i, "0.fn.fn.to_out.0.bias")], *knobs["out"], act) + x
         xn = F.layer_norm(x, (D,), sd[O.blk(i, "1.fn.norm.weight")], sd[O.blk(i, "1.fn.norm.bias")], cfg.ln_eps)
@@ -129,6 +132,12 @@ def main():
     report("weights exact in fwd only", k)
     k = {f: (True, False) for f in fams}; k["act"] = True
     report("weights exact in bwd only", k)
+    if os.environ.get("ACTSPLIT"):
+        k = {f: (False, False) for f in fams}; k["act"] = (True, False)
+        report("weights exact, FORWARD activations rounded only", k)
+        k = {f: (False, False) for f in fams}; k["act"] = (False, True)
+        report("weights exact, BACKWARD gradients rounded only", k)
+        return
     if os.environ.get("QUICK"):
         return
     for fam in ["qkv", "out", "fc1", "fc2"]:

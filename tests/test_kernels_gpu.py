@@ -239,7 +239,7 @@ def test_gemm_split_weight_is_exact_in_the_weight(F, M, N, K, epi, cg, bn):
     elif epi == F.EPI_RES_F32:
         res = torch.randn(M, N, device="cuda"); out0 = torch.empty(M, N, device="cuda")
         F.gemm_f16(A, hi, B_lo=lo, epi=epi, bias=bias, out0=out0, aux=res, cta_group=cg, block_n=bn)
-        assert rel(out0, exact + res) < 3e-6
+        assert rel(out0, exact + res) < 1e-5
     else:       # GELU: fp16 outputs, checked to fp16 rounding
         gp = torch.empty(M, N, device="cuda", dtype=torch.half); g = torch.empty(M, N, device="cuda", dtype=torch.half)
         F.gemm_f16(A, hi, B_lo=lo, epi=epi, bias=bias, out0=gp, out1=g, cta_group=cg, block_n=bn)
