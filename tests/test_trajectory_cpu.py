@@ -7,7 +7,7 @@ import os
 import torch
 
 from oracle import vit_oracle as O
-from trajectory_common import oracle_trajectory, windows
+from trajectory_common import COLLAPSED, oracle_trajectory, windows
 
 
 def test_oracle_free_running_trajectory_matches_unmodified_reference_loop(golden_dir):
@@ -27,7 +27,7 @@ def test_oracle_free_running_trajectory_matches_unmodified_reference_loop(golden
         for a, b in zip(norms[e], g["group_norms"][e]):
             assert abs(a - b) <= 2e-3 * b, (e, a, b)
     # the scenario is the interesting one: the structure term collapses most groups, the data term keeps at least one alive
-    collapsed = [n1 < 0.25 * n0 for n0, n1 in zip(*g["group_norms"])]
+    collapsed = [n1 < COLLAPSED * n0 for n0, n1 in zip(*g["group_norms"])]
     assert any(collapsed) and not all(collapsed)
     # the forget bound engages inside the run: CE_f starts below BND and is at or above it at some later step
     assert steps[0]["ce_forget"] < hp["BND"] and any(s["ce_forget"] >= hp["BND"] for s in steps)
