@@ -18,12 +18,14 @@ namespace gsl {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int64_t Engine::lora_block_elems() const {
-    const int64_t r = cfg.lora_rank, D = cfg.dim, H = cfg.mlp_dim;
+    const int64_t r = cfg.lora_rank, D = cfg.dim, H = cfg.mlp_dim, inner = (int64_t)cfg.heads * 64;
+    if (cfg.lora_pos == 1) return 3 * r * D + 3 * inner * r;
     return r * D + H * r + r * H + D * r;
 }
 int64_t Engine::lora_offset(int block, int which) const {
     const int64_t r = cfg.lora_rank, D = cfg.dim, H = cfg.mlp_dim;
     int64_t off = block * lora_block_elems();
+    if (cfg.lora_pos == 1) return off + (which >= 1 ? 3 * r * D : 0);
     if (which >= 1) off += r * D;
     if (which >= 2) off += H * r;
     if (which >= 3) off += r * H;
@@ -66,6 +68,8 @@ size_t Engine::carve(bool assign) {
         c.A2h = (__half*)take((size_t)32 * H * 2);
         c.B1T = (__half*)take((size_t)32 * H * 2);
         c.B2T = (__half*)take((size_t)32 * D * 2);
+        c.Aqkv = cfg.lora_pos == 1 ? (__half*)take((size_t)3 * 32 * D * 2) : nullptr;
+        c.BqkvT = cfg.lora_pos == 1 ? (__half*)take((size_t)3 * 32 * inner * 2) : nullptr;
         if (assign) cache[l] = c;
     }
     if (assign) slots.assign(cfg.num_slots, Slot());
@@ -79,6 +83,7 @@ size_t Engine::carve(bool assign) {
             a.lse = (float*)take((size_t)Bm * cfg.heads * tokens * 4);
             a.qkv16 = (__half*)take((size_t)M * 3 * inner * 2);
             a.o16 = (__half*)take((size_t)M * inner * 2);
+            a.xn1_16 = cfg.lora_pos == 1 ? (__half*)take((size_t)M * D * 2) : nullptr;
             a.xn2_16 = (__half*)take((size_t)M * D * 2);
             a.gp16 = (__half*)take((size_t)M * H * 2);
             a.g16 = (__half*)take((size_t)M * H * 2);
@@ -116,11 +121,11 @@ size_t Engine::carve(bool assign) {
     if (sk_side > sk) sk = sk_side;
     auto* t_sk = (float*)take(sk);
     auto* t_go = (int*)take((size_t)(L + 1) * 4);
-    auto* t_to = (int*)take((size_t)(4 * L + 1) * 4);
+    auto* t_to = (int*)take((size_t)(4 * L + 1) * 4);      // (4 tensors per block with lora_pos 0, 2 with lora_pos 1)
     auto* t_gn = (float*)take((size_t)L * 4);
     auto* t_tn = (float*)take((size_t)4 * L * 4);
     auto* t_pp = (void*)take((size_t)L * 8 * sizeof(void*));
-    auto* t_mj = (void*)take((size_t)L * 2 * 64);
+    auto* t_mj = (void*)take((size_t)L * 3 * 128);
     if (assign) {
         patches16 = t_patches; xn16 = t_xn; dy16 = t_dy; dh16 = t_dh; do16 = t_do; dqkv16 = t_dqkv;
         t1_16 = t_tu[0]; t2_16 = t_tu[1]; u1_16 = t_tu[2]; u2_16 = t_tu[3];
@@ -138,6 +143,7 @@ static int validate(const GslConfig& c) {
     GSL_REQUIRE(c.mlp_dim % 64 == 0, "mlp_dim=%d must be a multiple of 64", c.mlp_dim);
     GSL_REQUIRE(c.heads * 64 == c.dim || c.heads > 0, "bad heads");
     GSL_REQUIRE(c.lora_rank >= 1 && c.lora_rank <= 16, "lora_rank=%d: the rank-r side kernels hold r <= 16 (args.py --lora_rank)", c.lora_rank);
+    GSL_REQUIRE(c.lora_pos == 0 || c.lora_pos == 1, "lora_pos=%d: 0 (FFN) or 1 (Attention)", c.lora_pos);
     GSL_REQUIRE(c.precision == 0 || c.precision == 1, "precision=%d: 0 (fast: fp16 weights) or 1 (split: fp16 hi + lo weights)", c.precision);
     GSL_REQUIRE((c.channels * c.patch_size * c.patch_size) % 16 == 0, "patch_dim must be a multiple of 16");
     GSL_REQUIRE(c.max_batch >= 1 && c.num_slots >= 1 && c.depth >= 1, "bad max_batch / num_slots / depth");
@@ -169,17 +175,18 @@ int Engine::init(const GslConfig& c, void* workspace, size_t bytes) {
     ws = (uint8_t*)workspace; ws_bytes = bytes;
     carve(true);
     // offsets of groups / tensors in the flat LoRA buffer
-    std::vector<int> go(c.depth + 1), to(4 * c.depth + 1);
+    const int tpb = lora_tensors_per_block();
+    std::vector<int> go(c.depth + 1), to(tpb * c.depth + 1);
     for (int l = 0; l <= c.depth; ++l) go[l] = (int)(l * lora_block_elems());
     for (int l = 0; l < c.depth; ++l)
-        for (int w = 0; w < 4; ++w) to[4 * l + w] = (int)lora_offset(l, w);
-    to[4 * c.depth] = (int)(c.depth * lora_block_elems());
+        for (int w = 0; w < tpb; ++w) to[tpb * l + w] = (int)lora_offset(l, w);
+    to[tpb * c.depth] = (int)(c.depth * lora_block_elems());
     GSL_CHECK_CUDA(cudaMemcpy(group_offsets_dev, go.data(), go.size() * 4, cudaMemcpyHostToDevice));
     GSL_CHECK_CUDA(cudaMemcpy(tensor_offsets_dev, to.data(), to.size() * 4, cudaMemcpyHostToDevice));
     std::vector<void*> pp;
     for (int l = 0; l < c.depth; ++l) {
         const BlockCache& bc = cache[l];
-        void* row[8] = {bc.A1h, bc.A2h, bc.B1T, bc.B2T, nullptr, nullptr, nullptr, nullptr};
+        void* row[8] = {bc.A1h, bc.A2h, bc.B1T, bc.B2T, bc.Aqkv, bc.BqkvT, nullptr, nullptr};
         pp.insert(pp.end(), row, row + 8);
     }
     GSL_CHECK_CUDA(cudaMemcpy(pack_ptrs_dev, pp.data(), pp.size() * sizeof(void*), cudaMemcpyHostToDevice));
@@ -189,15 +196,18 @@ int Engine::init(const GslConfig& c, void* workspace, size_t bytes) {
 // out = fp16(W + sc * B A) and its transpose, W [R, C] fp32, A [r, C], B [R, r] (loralib.Linear's merged weight, layers.py train/eval);
 // sc = 0 gives the plain fp16 cast.  One 32 x 32 tile per CTA, the transpose goes through shared memory.  Split mode: out_lo / outT_lo
 // receive fp16(v - fp16(v)), the second term of the split operand (gsl_gemm.cu SPLIT).
+// A / B null = no LoRA on this weight (plain cast).  groups > 1: loralib.MergedLinear -- the R rows are `groups` equal slices, slice g with its own
+// pair A_g = A[g r : (g + 1) r, :], B_g = B[rows of slice g, :]  (merge_AB's grouped 1x1 conv, loralib layers.py).
 struct MergeJob {
     const float *W, *A, *B;
     __half *out, *outT, *out_lo, *outT_lo;
-    int R, C;
+    int R, C, groups;
 };
+static constexpr int MERGE_JOB_SLOT = 128;
 __global__ void __launch_bounds__(256) merge_weights_kernel(const uint8_t* __restrict__ jobs_raw, int r, float sc) {
     pdl_prologue();
     __shared__ float tile[32][33];
-    const MergeJob j = *reinterpret_cast<const MergeJob*>(jobs_raw + (size_t)blockIdx.z * 64);
+    const MergeJob j = *reinterpret_cast<const MergeJob*>(jobs_raw + (size_t)blockIdx.z * MERGE_JOB_SLOT);
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     if (c0 >= j.C || r0 >= j.R) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -205,9 +215,10 @@ __global__ void __launch_bounds__(256) merge_weights_kernel(const uint8_t* __res
     for (int i = 0; i < 4; ++i) {
         const int row = r0 + ty + 8 * i, col = c0 + tx;
         float v = j.W[(int64_t)row * j.C + col];
-        if (sc != 0.f) {
+        if (sc != 0.f && j.A != nullptr) {
+            const int a0 = (row / (j.R / j.groups)) * r;        // first row of this slice's A_g
             float d = 0.f;
-            for (int k = 0; k < r; ++k) d = fmaf(j.B[(int64_t)row * r + k], j.A[(int64_t)k * j.C + col], d);
+            for (int k = 0; k < r; ++k) d = fmaf(j.B[(int64_t)row * r + k], j.A[(int64_t)(a0 + k) * j.C + col], d);
             v = fmaf(sc, d, v);
         }
         const __half hv = __float2half_rn(v);
@@ -229,9 +240,10 @@ __global__ void __launch_bounds__(256) merge_weights_kernel(const uint8_t* __res
 int Engine::ensure_ffn_weights(int use_lora, cudaStream_t s) {
     const int mode = use_lora ? 1 : 0;
     if (ffn_cache_mode == mode) return 0;
-    const int D = cfg.dim, H = cfg.mlp_dim;
-    const int big = H > D ? H : D;
-    dim3 grid(big / 32, big / 32, 2 * cfg.depth);
+    const int D = cfg.dim, H = cfg.mlp_dim, inner3 = 3 * cfg.heads * 64;
+    int big = H > D ? H : D;
+    if (cfg.lora_pos == 1 && inner3 > big) big = inner3;
+    dim3 grid(big / 32, big / 32, (cfg.lora_pos == 1 ? 3 : 2) * cfg.depth);
     GSL_CHECK_CUDA(launch_pdl(merge_weights_kernel, dim3(grid), dim3(256), 0, s, (const uint8_t*)merge_jobs_dev, cfg.lora_rank, use_lora ? cfg.lora_scaling : 0.f));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
@@ -259,21 +271,30 @@ int Engine::bind_params(const void* const* p, int n, float* lora, float* grads) 
     lora_flat = lora; grad_flat = grads;
     params_bound = true;
     ffn_cache_mode = -1;
-    // merge jobs: per block  fc1 (W1 [H, D], A1, B1)  and  fc2 (W2 [D, H], A2, B2)
+    // merge jobs: per block  fc1 (W1 [H, D], A1, B1)  and  fc2 (W2 [D, H], A2, B2); lora_pos 1: to_qkv (3 slices) with LoRA, fc1 / fc2 plain
     std::vector<MergeJob> jobs;
+    const bool attn_lora = cfg.lora_pos == 1;
     for (int l = 0; l < cfg.depth; ++l) {
         MergeJob j1, j2;
-        j1.W = frozen[l].fc1_w; j1.A = lora_flat + lora_offset(l, 0); j1.B = lora_flat + lora_offset(l, 1);
+        j1.groups = j2.groups = 1;
+        if (attn_lora) {
+            MergeJob jq;
+            jq.W = frozen[l].qkv_w; jq.A = lora_flat + lora_offset(l, 0); jq.B = lora_flat + lora_offset(l, 1);
+            jq.out = cache[l].qkv_w16.hi; jq.outT = cache[l].qkv_wT16.hi; jq.out_lo = cache[l].qkv_w16.lo; jq.outT_lo = cache[l].qkv_wT16.lo;
+            jq.R = 3 * cfg.heads * 64; jq.C = cfg.dim; jq.groups = 3;
+            jobs.push_back(jq);
+        }
+        j1.W = frozen[l].fc1_w; j1.A = attn_lora ? nullptr : lora_flat + lora_offset(l, 0); j1.B = attn_lora ? nullptr : lora_flat + lora_offset(l, 1);
         j1.out = cache[l].fc1_w16.hi; j1.outT = cache[l].fc1T_w16.hi; j1.out_lo = cache[l].fc1_w16.lo; j1.outT_lo = cache[l].fc1T_w16.lo;
         j1.R = cfg.mlp_dim; j1.C = cfg.dim;
-        j2.W = frozen[l].fc2_w; j2.A = lora_flat + lora_offset(l, 2); j2.B = lora_flat + lora_offset(l, 3);
+        j2.W = frozen[l].fc2_w; j2.A = attn_lora ? nullptr : lora_flat + lora_offset(l, 2); j2.B = attn_lora ? nullptr : lora_flat + lora_offset(l, 3);
         j2.out = cache[l].fc2_w16.hi; j2.outT = cache[l].fc2T_w16.hi; j2.out_lo = cache[l].fc2_w16.lo; j2.outT_lo = cache[l].fc2T_w16.lo;
         j2.R = cfg.dim; j2.C = cfg.mlp_dim;
         jobs.push_back(j1); jobs.push_back(j2);
     }
-    static_assert(sizeof(MergeJob) <= 64, "MergeJob slot");
-    std::vector<uint8_t> raw(jobs.size() * 64, 0);
-    for (size_t i = 0; i < jobs.size(); ++i) memcpy(raw.data() + i * 64, &jobs[i], sizeof(MergeJob));
+    static_assert(sizeof(MergeJob) <= MERGE_JOB_SLOT, "MergeJob slot");
+    std::vector<uint8_t> raw(jobs.size() * MERGE_JOB_SLOT, 0);
+    for (size_t i = 0; i < jobs.size(); ++i) memcpy(raw.data() + i * MERGE_JOB_SLOT, &jobs[i], sizeof(MergeJob));
     GSL_CHECK_CUDA(cudaMemcpy(merge_jobs_dev, raw.data(), raw.size(), cudaMemcpyHostToDevice));
     return 0;
 }
@@ -306,6 +327,8 @@ int Engine::refresh_frozen(cudaStream_t s) {
         if ((rc = fill_zero(c.A2h, (size_t)32 * H * 2, s))) return rc;
         if ((rc = fill_zero(c.B1T, (size_t)32 * H * 2, s))) return rc;
         if ((rc = fill_zero(c.B2T, (size_t)32 * D * 2, s))) return rc;
+        if (c.Aqkv && (rc = fill_zero(c.Aqkv, (size_t)3 * 32 * D * 2, s))) return rc;
+        if (c.BqkvT && (rc = fill_zero(c.BqkvT, (size_t)3 * 32 * inner * 2, s))) return rc;
     }
     ffn_cache_mode = -1;        // the FFN caches are rebuilt (with or without the LoRA delta) by the next forward
     return refresh_lora(s);
@@ -314,9 +337,29 @@ int Engine::refresh_frozen(cudaStream_t s) {
 // One launch repacks the fp16 LoRA operands of every block from the flat fp32 parameter buffer: A1h/A2h = lora_A, B1T/B2T = lora_B^T
 // (the rank-r by-products T = x A^T, U = dY B of the backward).  The FFN weight caches are re-merged lazily by the next forward.
 struct LoraPackPtrs {
-    __half *A1h, *A2h, *B1T, *B2T;
-    void* unused[4];
+    __half *A1h, *A2h, *B1T, *B2T, *Aqkv, *BqkvT;
+    void* unused[2];
 };
+// lora_pos 1: flat block = [ to_qkv.lora_A (3r x D) | to_qkv.lora_B (3 inner x r) ] -> Aqkv[g] = A_g, BqkvT[g] = B_g^T
+__global__ void lora_pack_attn_kernel(const float* __restrict__ flat, const LoraPackPtrs* __restrict__ ptrs, int D, int inner, int r, int per_block, int split) {
+    const int l = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per_block) return;
+    const LoraPackPtrs p = ptrs[l];
+    const float v = flat[(int64_t)l * per_block + i];
+    const __half hv = __float2half_rn(v);
+    const __half lv = __float2half_rn(v - __half2float(hv));
+    __half* dst; int64_t off, lo_off;
+    if (i < 3 * r * D) {
+        const int g = i / (r * D), k = i % (r * D);
+        dst = p.Aqkv + (int64_t)g * 32 * D; off = k; lo_off = (int64_t)16 * D;
+    } else {
+        const int k = i - 3 * r * D, row = k / r, j = k % r, g = row / inner, o = row % inner;
+        dst = p.BqkvT + (int64_t)g * 32 * inner; off = (int64_t)j * inner + o; lo_off = (int64_t)16 * inner;
+    }
+    dst[off] = hv;
+    if (split) dst[off + lo_off] = lv;
+}
 __global__ void lora_pack_kernel(const float* __restrict__ flat, const LoraPackPtrs* __restrict__ ptrs, int D, int H, int r, int per_block, int split) {
     pdl_prologue();
     const int l = blockIdx.y;
@@ -340,7 +383,10 @@ int Engine::refresh_lora(cudaStream_t s) {
     GSL_REQUIRE(params_bound, "bind_params first");
     const int per_block = (int)lora_block_elems();
     dim3 grid((per_block + 255) / 256, cfg.depth);
-    GSL_CHECK_CUDA(launch_pdl(lora_pack_kernel, dim3(grid), dim3(256), 0, s, lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, per_block, cfg.precision == 1 ? 1 : 0));
+    if (cfg.lora_pos == 1)
+        lora_pack_attn_kernel<<<grid, 256, 0, s>>>(lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.heads * 64, cfg.lora_rank, per_block, cfg.precision == 1 ? 1 : 0);
+    else
+        GSL_CHECK_CUDA(launch_pdl(lora_pack_kernel, dim3(grid), dim3(256), 0, s, lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, per_block, cfg.precision == 1 ? 1 : 0));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     if (ffn_cache_mode == 1) ffn_cache_mode = -1;       // W + s B A is stale
@@ -414,10 +460,11 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
         BlockActs& a = S.blk[l];
         float* x_in = S.x[2 * l];
         // ---- x = Attention(LN(x)) + x
-        if ((rc = layernorm_fwd(x_in, D, f.ln1_w, f.ln1_b, cfg.ln_eps, xn16, D, a.ln1_mean, a.ln1_rstd, M, D, s))) return rc;
+        __half* xn1 = a.xn1_16 ? a.xn1_16 : xn16;        // kept for the backward only when to_qkv carries LoRA
+        if ((rc = layernorm_fwd(x_in, D, f.ln1_w, f.ln1_b, cfg.ln_eps, xn1, D, a.ln1_mean, a.ln1_rstd, M, D, s))) return rc;
         {
             GemmArgs g;
-            g.A = xn16; g.lda = D; g.B = c.qkv_w16.hi; g.B_lo = c.qkv_w16.lo; g.ldb = D; g.M = M; g.N = 3 * inner; g.K = D;
+            g.A = xn1; g.lda = D; g.B = c.qkv_w16.hi; g.B_lo = c.qkv_w16.lo; g.ldb = D; g.M = M; g.N = 3 * inner; g.K = D;
             g.epi = EPI_F16; g.bias = f.qkv_b; g.out0 = a.qkv16; g.ld0 = 3 * inner;
             if ((rc = gemm_f16(g, s))) return rc;
         }
@@ -471,19 +518,24 @@ int Engine::ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, fl
     float* gB2 = grad_flat + lora_offset(l, 3);
     int rc;
     const int fold = cfg.precision == 1 ? 1 : 0;                // split mode: the rank-r operands carry their rounding residual too
+    const bool ffn_lora = cfg.lora_pos == 0;
+    if (ffn_lora) {
     if ((rc = lora_down(dy, D, c.B2T, D, u2_16, 16, M, D, r, s, fold))) return rc;                                                        // U2 = dY2 B2
     if ((rc = lora_side(g16, H, c.A2h, H, t2_16, 16, u2_16, 16, gA2, H, 1, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s, fold))) return rc;   // T2 = G A2^T, dA2 = s U2^T G
     if ((rc = skinny_tn(dy, D, t2_16, 16, gB2, r, 0, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;       // dB2 = s dY2^T T2
+    }
     {   // dH = (dY2 W2') * d[Dropout(gelu(h))] / dh
         GemmArgs g;
         g.A = dy; g.lda = D; g.B = c.fc2T_w16.hi; g.B_lo = c.fc2T_w16.lo; g.ldb = D; g.M = M; g.N = H; g.K = D;
         g.epi = EPI_GELU_BWD; g.out0 = dh; g.ld0 = H; g.aux = gp16; g.ldaux = H;
         if ((rc = gemm_f16(g, s))) return rc;
     }
+    if (ffn_lora) {
     if ((rc = lora_down(xn2, D, c.A1h, D, t1_16, 16, M, D, r, s, fold))) return rc;                                                       // T1 = LN2(x) A1^T
     if ((rc = lora_side(dh, H, c.B1T, H, u1_16, 16, t1_16, 16, gB1, r, 0, wscale, accumulate, M, H, r, skinny_ws, skinny_ws_bytes, s, fold))) return rc;    // U1 = dH B1, dB1 = s dH^T T1
     if ((rc = skinny_tn(xn2, D, u1_16, 16, gA1, D, 1, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;      // dA1 = s U1^T LN2(x)
-    if (l == 0) return 0;       // nothing trainable below block 0's FFN
+    }
+    if (l == 0 && ffn_lora) return 0;       // nothing trainable below block 0's FFN (with LoRA on to_qkv block 0's attention still is)
     {   // dLN2 = dH W1'
         GemmArgs g;
         g.A = dh; g.lda = H; g.B = c.fc1T_w16.hi; g.B_lo = c.fc1T_w16.lo; g.ldb = H; g.M = M; g.N = D; g.K = H;
@@ -491,6 +543,27 @@ int Engine::ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, fl
         if ((rc = gemm_f16(g, s))) return rc;
     }
     return layernorm_bwd(dxn, dxn_fp32() ? 0 : 1, D, x_mid, D, ln_mean, ln_rstd, f.ln2_w, dx, D, dx, D, dy, D, M, D, pdrop, site_seed(dseed, l, 1), s);
+}
+
+// LoRA on to_qkv (loralib.MergedLinear, one (A_g, B_g) pair per slice g = q, k, v; vit_face.py:349-355): with dQKV [M, 3 inner] from the attention
+// backward and LN1(x) saved by the forward, per slice   U_g = dQKV_g B_g,  dA_g = s U_g^T LN1(x),  T_g = LN1(x) A_g^T,  dB_g = s dQKV_g^T T_g
+// (SURVEY Appendix C applied to each slice; dLN1 = dQKV W'qkv already carries the LoRA term through the merged weight).
+int Engine::attn_lora_grads(int l, int64_t M, const __half* dqkv, const __half* xn1, int accumulate, cudaStream_t s) {
+    const int D = cfg.dim, inner = cfg.heads * 64, r = cfg.lora_rank;
+    const BlockCache& c = cache[l];
+    const float wscale = cfg.lora_scaling / cfg.grad_scale;
+    const int fold = cfg.precision == 1 ? 1 : 0;
+    float* gA = grad_flat + lora_offset(l, 0);      // [3r, D]
+    float* gB = grad_flat + lora_offset(l, 1);      // [3 inner, r]
+    int rc;
+    for (int g = 0; g < 3; ++g) {
+        const __half* dq = dqkv + (int64_t)g * inner;
+        if ((rc = lora_down(dq, 3 * inner, c.BqkvT + (int64_t)g * 32 * inner, inner, u1_16, 16, M, inner, r, s, fold))) return rc;
+        if ((rc = skinny_tn(xn1, D, u1_16, 16, gA + (int64_t)g * r * D, D, 1, wscale, accumulate, M, D, r, skinny_ws, skinny_ws_bytes, s))) return rc;
+        if ((rc = lora_down(xn1, D, c.Aqkv + (int64_t)g * 32 * D, D, t1_16, 16, M, D, r, s, fold))) return rc;
+        if ((rc = skinny_tn(dq, 3 * inner, t1_16, 16, gB + (int64_t)g * inner * r, r, 0, wscale, accumulate, M, inner, r, skinny_ws, skinny_ws_bytes, s))) return rc;
+    }
+    return 0;
 }
 
 int Engine::backward(int slot, const float* dlogits, const float* demb, int accumulate, cudaStream_t s) {
@@ -504,6 +577,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
     const int64_t M = (int64_t)B * tokens;
     const uint64_t dseed = S.drop_seed;
     const float pdrop = dseed ? cfg.dropout : 0.f;
+    const bool attn_lora = cfg.lora_pos == 1;
     int rc;
     // ---------------- head: gradient of the B cls rows of the last block's output (scaled by the loss scale)
     HeadBwdArgs hb;
@@ -521,7 +595,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         ClsActs& k = S.cls;
         if ((rc = ffn_backward(l, B, cls_dy16, cls_dx32, cls_dh16, cls_dxn32, k.xn2_16, k.gp16, k.g16, k.xmid32, k.ln2_mean, k.ln2_rstd,
                                accumulate, pdrop, dseed, s))) return rc;
-        if (l == 0) return 0;
+        if (l == 0 && !attn_lora) return 0;
         {   // dO (cls rows) = dY Wo
             GemmArgs g;
             g.A = cls_dy16; g.lda = D; g.B = c.out_wT16.hi; g.B_lo = c.out_wT16.lo; g.ldb = D; g.M = B; g.N = inner; g.K = D;
@@ -529,6 +603,8 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
             if ((rc = gemm_f16(g, s))) return rc;
         }
         if ((rc = cls_attention_bwd(a.qkv16, 3 * inner, k.o16, inner, cls_do16, inner, k.lse, dqkv16, 3 * inner, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
+        if (attn_lora && (rc = attn_lora_grads(l, M, dqkv16, a.xn1_16, accumulate, s))) return rc;
+        if (l == 0) return 0;
         {   // dLN1 = dQKV Wqkv  (dense: dK / dV reach every token)
             GemmArgs g;
             g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16.hi; g.B_lo = c.qkv_wT16.lo; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
@@ -546,7 +622,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         // ---------------- FFN: y = fc2(gelu(fc1(LN2(x)))) + x
         if ((rc = ffn_backward(l, M, dy16, dx32, dh16, dxn32, a.xn2_16, a.gp16, a.g16, S.x[2 * l + 1], a.ln2_mean, a.ln2_rstd, accumulate,
                                pdrop, dseed, s))) return rc;
-        if (l == 0) break;      // nothing trainable below block 0's FFN
+        if (l == 0 && !attn_lora) break;      // nothing trainable below block 0's FFN
         // ---------------- attention: y = to_out(attn(to_qkv(LN1(x)))) + x
         {   // dO = dY Wo
             GemmArgs g;
@@ -555,6 +631,8 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
             if ((rc = gemm_f16(g, s))) return rc;
         }
         if ((rc = attention_bwd(a.qkv16, 3 * inner, a.o16, inner, do16, inner, a.lse, dqkv16, 3 * inner, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
+        if (attn_lora && (rc = attn_lora_grads(l, M, dqkv16, a.xn1_16, accumulate, s))) return rc;
+        if (l == 0) break;      // block 0: to_qkv's LoRA is the last trainable thing on the way down
         {   // dLN1 = dQKV Wqkv
             GemmArgs g;
             g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16.hi; g.B_lo = c.qkv_wT16.lo; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;

@@ -29,11 +29,15 @@ struct BlockCache {             // fp16 operand caches (engine workspace)
     // rank-r operands, 32 rows each: rows [0, 16) = fp16 value (rows >= r zero), rows [16, 32) = fp16 of the rounding residual (split mode, else zero)
     __half *A1h, *A2h;  // [32, D], [32, H]   lora_A    -> T = x A^T for dB
     __half *B1T, *B2T;  // [32, H], [32, D]   lora_B^T  -> U = dY B for dA
+    // lora_pos = 1 (LoRA on to_qkv, loralib MergedLinear): one operand set per slice g = q, k, v
+    __half *Aqkv;       // [3][32, D]      A_g
+    __half *BqkvT;      // [3][32, inner]  B_g^T
 };
 
 struct BlockActs {              // saved activations of one block for one slot
     float *ln1_mean, *ln1_rstd, *ln2_mean, *ln2_rstd, *lse;
     __half *qkv16, *o16;
+    __half *xn1_16;     // [M, D]  LN1(x), input of to_qkv: saved only with lora_pos = 1 (dA_g = s U_g^T LN1(x), T_g = LN1(x) A_g^T)
     __half *xn2_16;     // [M, D]  LN2(x), input of fc1
     __half *gp16;       // [M, H]  d Dropout(gelu(h)) / d h  (EPI_GELU out0)
     __half *g16;        // [M, H]  Dropout(gelu(h)), input of fc2
@@ -91,12 +95,14 @@ public:
                 uint64_t dropout_seed, cudaStream_t s);
     int backward(int slot, const float* dlogits, const float* demb, int accumulate, cudaStream_t s);
     int64_t lora_block_elems() const;
-    int64_t lora_offset(int block, int which) const;   // which: 0 A1, 1 B1, 2 A2, 3 B2
+    int64_t lora_offset(int block, int which) const;   // which: 0 A1, 1 B1, 2 A2, 3 B2  (lora_pos 1: 0 A_qkv, 1 B_qkv)
+    int lora_tensors_per_block() const { return cfg.lora_pos == 1 ? 2 : 4; }
 private:
     size_t carve(bool assign);
     int ensure_ffn_weights(int use_lora, cudaStream_t s);
     int ffn_forward(int l, int64_t M, __half* xn2, float* ln_mean, float* ln_rstd, const float* x_mid, __half* gp16, __half* g16, float* x_out,
                     float pdrop, uint64_t dseed, cudaStream_t s);
+    int attn_lora_grads(int l, int64_t M, const __half* dqkv, const __half* xn1, int accumulate, cudaStream_t s);
     int ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, float* dxn, const __half* xn2, const __half* gp16, const __half* g16,
                      const float* x_mid, const float* ln_mean, const float* ln_rstd, int accumulate, float pdrop, uint64_t dseed, cudaStream_t s);
 };

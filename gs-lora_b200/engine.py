@@ -27,15 +27,23 @@ _PROTO_BOUND = 18.0         # engine.py:104
 def get_structure_loss(model: torch.nn.Module, num_layers: int = None, group_type: str = "block", group_pos: str = "FFN"):
     """engine.get_structure_loss (engine.py:532-687).  `num_layers` is implied by the engine-backed model (the reference needs it only to
     build parameter names)."""
-    if group_pos != "FFN":
-        raise NotImplementedError("gslora-b200: group_pos='Attention' needs LoRA on to_qkv (MergedLinear r > 0), which the engine does not build "
-                                  "(every GS-LoRA script uses --lora_pos FFN)")
+    m = _cl._unwrap(model)
+    _check_group_pos(m, group_pos)
     if group_type not in ("block", "lora", "matrix"):
         raise ValueError(f"group_type {group_type!r} not in block / lora / matrix")
-    m = _cl._unwrap(model)
     if num_layers is not None and int(num_layers) != m.engine_spec().depth:
         raise ValueError(f"num_layers={num_layers} but the model has {m.engine_spec().depth} Transformer blocks")
     return _cl.get_structure_loss(model, group_type=group_type)
+
+
+def _check_group_pos(m, group_pos):
+    """group_pos "FFN" / "Attention" (engine.py:585-658) names where the LoRA parameters live: it has to agree with how the model was built
+    (ViT_face(lora_pos=...)).  The reference, handed the other one, silently sums an empty list of groups."""
+    if group_pos not in ("FFN", "Attention"):
+        raise ValueError(f"group_pos {group_pos!r} not in FFN / Attention")
+    have = getattr(m, "lora_pos", "FFN")
+    if have != group_pos:
+        raise ValueError(f"group_pos={group_pos!r} but the model carries its LoRA on {have!r} (ViT_face(lora_pos=...))")
 
 
 def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criterion, optimizer, epoch, losses_forget, losses_remain,
@@ -56,8 +64,7 @@ def train_one_epoch(model, dataloader_forget, dataloader_remain, device, criteri
     DISP_FREQ, VER_FREQ = 5, 100
     alpha_eff = 0.0 if epoch < cfg.get("ALPHA_EPOCH", 0) else alpha               # engine.py:82-90
     group_type = cfg.get("GROUP_TYPE", "block")
-    if cfg.get("GROUP_POS", "FFN") != "FFN":
-        raise NotImplementedError("gslora-b200: GROUP_POS='Attention' is not built (LoRA lives on the FFN Linears)")
+    _check_group_pos(m, cfg.get("GROUP_POS", "FFN"))
     forget_drives = len(dataloader_forget) > len(dataloader_remain) and bool(cfg.get("few_shot"))      # engine.py:53
     driving, recycled = (dataloader_forget, dataloader_remain) if forget_drives else (dataloader_remain, dataloader_forget)
     prefetcher = _cl._Prefetcher(recycled, device)

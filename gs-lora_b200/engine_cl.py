@@ -164,7 +164,7 @@ class _StructureLossFn(torch.autograd.Function):
         inv = torch.where(ctx.norms > 0, 1.0 / ctx.norms, torch.zeros_like(ctx.norms))
         sizes = (ctx.offs[1:] - ctx.offs[:-1]).long()
         flat = eng.lora_flat * torch.repeat_interleave(inv, sizes) * g
-        out = [eng.lora_view(flat, l, w) for l in range(eng.spec.depth) for w in range(4)]
+        out = [eng.lora_view(flat, l, w) for l in range(eng.spec.depth) for w in range(eng.spec.tensors_per_block)]
         return (None, None, *out)
 
 
@@ -318,12 +318,11 @@ def sync_optimizer_state(model, optimizer):
     eng = m._engine
     if eng is None or optimizer is None:
         return
-    i = 0
+    tpb = eng.spec.tensors_per_block
     for l in range(eng.spec.depth):
-        for w, p in zip(range(4), m.lora_parameters()[4 * l:4 * l + 4]):
+        for w, p in zip(range(tpb), m.lora_parameters()[tpb * l:tpb * l + tpb]):
             optimizer.state[p] = {"step": torch.tensor(float(eng.opt_step)), "exp_avg": eng.lora_view(eng.exp_avg, l, w),
                                   "exp_avg_sq": eng.lora_view(eng.exp_avg_sq, l, w)}
-            i += 1
 
 
 class _Prefetcher:

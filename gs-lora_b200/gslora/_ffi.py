@@ -32,7 +32,7 @@ class GslConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("image_size", "patch_size", "channels", "dim", "depth", "heads", "mlp_dim", "num_class",
                                               "lora_rank", "max_batch", "num_slots", "patch_order")] + \
                [(n, ctypes.c_float) for n in ("attn_scale", "ln_eps", "cos_s", "cos_m", "lora_scaling", "grad_scale", "dropout", "emb_dropout")] + \
-               [("head_type", ctypes.c_int32), ("precision", ctypes.c_int32)]
+               [("head_type", ctypes.c_int32), ("precision", ctypes.c_int32), ("lora_pos", ctypes.c_int32)]
 
 
 PRECISION_FAST, PRECISION_SPLIT = 0, 1

@@ -33,6 +33,7 @@ class EngineSpec:
     dropout: float = 0.0
     emb_dropout: float = 0.0
     head_type: int = 0          # 0 CosFace (ViT_face), 1 Linear + bias (torchvision heads.head)
+    lora_pos: int = 0           # 0 "FFN" (lora.Linear on both FFN Linears), 1 "Attention" (lora.MergedLinear on to_qkv)
     precision: int = -1         # -1: GSLORA_PRECISION (default "split"); 0 fast (fp16 weights); 1 split (fp16 hi + lo weights, grads <= 1e-3)
 
     @property
@@ -41,12 +42,17 @@ class EngineSpec:
 
     @property
     def lora_block_elems(self) -> int:
-        r, D, H = self.lora_rank, self.dim, self.mlp_dim
-        return 2 * r * (D + H)
+        return sum(a * b for a, b in self.lora_shapes())
 
     def lora_shapes(self):
         r, D, H = self.lora_rank, self.dim, self.mlp_dim
+        if self.lora_pos == 1:
+            return [(3 * r, D), (3 * self.heads * 64, r)]     # to_qkv.lora_A (A_q | A_k | A_v), to_qkv.lora_B (B_q | B_k | B_v)
         return [(r, D), (H, r), (r, H), (D, r)]      # A(net.0) B(net.0) A(net.3) B(net.3)
+
+    @property
+    def tensors_per_block(self) -> int:
+        return len(self.lora_shapes())
 
 
 class VitEngine:
@@ -60,7 +66,8 @@ class VitEngine:
                                lora_rank=spec.lora_rank, max_batch=self.max_batch, num_slots=self.num_slots,
                                patch_order=spec.patch_order, attn_scale=spec.attn_scale, ln_eps=spec.ln_eps, cos_s=spec.cos_s,
                                cos_m=spec.cos_m, lora_scaling=1.0 / spec.lora_rank, grad_scale=spec.grad_scale,
-                               dropout=spec.dropout, emb_dropout=spec.emb_dropout, head_type=spec.head_type, precision=self.precision)
+                               dropout=spec.dropout, emb_dropout=spec.emb_dropout, head_type=spec.head_type, precision=self.precision,
+                               lora_pos=spec.lora_pos)
         L = F.lib()
         nbytes = L.gsl_engine_workspace_bytes(ctypes.byref(self.cfg))
         if nbytes == 0:
@@ -97,6 +104,8 @@ class VitEngine:
             "lora": torch.tensor(offs[0::2], dtype=torch.int32, device=device),
             "matrix": self.tensor_offsets,
         }
+        if spec.lora_pos == 1:      # engine.py:650-656: with LoRA on attention a group is the block's (lora_A, lora_B) pair whatever group_type says
+            self.group_offsets_by_type = {k: self.group_offsets for k in ("block", "lora", "matrix")}
         self.group_norms = torch.zeros(4 * spec.depth, dtype=torch.float32, device=device)
         self.num_groups = spec.depth
         self.sums = torch.zeros(8, dtype=torch.float32, device=device)
@@ -112,7 +121,7 @@ class VitEngine:
 
     # ------------------------------------------------------------------ parameters
     def lora_view(self, buf: torch.Tensor, block: int, which: int) -> torch.Tensor:
-        o = self.tensor_offsets_host[4 * block + which]
+        o = self.tensor_offsets_host[self.spec.tensors_per_block * block + which]
         shp = self.spec.lora_shapes()[which]
         return buf[o:o + shp[0] * shp[1]].view(*shp)
 
@@ -238,7 +247,8 @@ class VitEngine:
         self.opt_step = 0
 
     def tensor_norms(self, type: str = "L2") -> torch.Tensor:
-        out = torch.empty(4 * self.spec.depth, dtype=torch.float32, device=self.device)
-        F.check(F.lib().gsl_tensor_norms(F.ptr(self.lora_flat), F.ptr(self.tensor_offsets), 4 * self.spec.depth, 0 if type == "L2" else 1,
+        n = self.spec.tensors_per_block * self.spec.depth
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        F.check(F.lib().gsl_tensor_norms(F.ptr(self.lora_flat), F.ptr(self.tensor_offsets), n, 0 if type == "L2" else 1,
                                          F.ptr(out), F.cur_stream()), "gsl_tensor_norms")
         return out

@@ -40,7 +40,7 @@ class _EngineFn(torch.autograd.Function):
         dlogits = dlogits.contiguous().float() if dlogits is not None else None
         demb = demb.contiguous().float() if demb is not None else None
         eng.backward(slot, dlogits, demb, accumulate=False)
-        out = [eng.lora_view(eng.grad_flat, l, w).clone() for l in range(eng.spec.depth) for w in range(4)]
+        out = [eng.lora_view(eng.grad_flat, l, w).clone() for l in range(eng.spec.depth) for w in range(eng.spec.tensors_per_block)]
         return (None, None, None, None, *out)
 
 
@@ -89,9 +89,11 @@ class EngineBackedModel(nn.Module):
         return dict(pixel_norm=self.input_pixel_norm, channels_last=nhwc)
 
     def lora_parameters(self) -> List[nn.Parameter]:
+        """flat-buffer order: per block, per LoRA layer of lora_layers() (fc1, fc2 -- or to_qkv alone with lora_pos "Attention"): lora_A, lora_B"""
         out = []
-        for fc1, fc2 in self.lora_layers():
-            out += [fc1.lora_A, fc1.lora_B, fc2.lora_A, fc2.lora_B]
+        for layers in self.lora_layers():
+            for m in layers:
+                out += [m.lora_A, m.lora_B]
         return out
 
 
@@ -149,8 +151,8 @@ class EngineBackedModel(nn.Module):
         """Re-link parameters into the engine and refresh its fp16 operand caches if anything changed."""
         eng = self._engine
         relinked = False
-        for l, (fc1, fc2) in enumerate(self.lora_layers()):
-            for w, p in enumerate((fc1.lora_A, fc1.lora_B, fc2.lora_A, fc2.lora_B)):
+        for l, layers in enumerate(self.lora_layers()):
+            for w, p in enumerate([q for m in layers for q in (m.lora_A, m.lora_B)]):
                 view = eng.lora_view(eng.lora_flat, l, w)
                 if p.data_ptr() != view.data_ptr():
                     view.copy_(p.data)

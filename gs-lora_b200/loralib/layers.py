@@ -64,17 +64,53 @@ class Linear(nn.Linear, LoRALayer):
 
 
 class MergedLinear(nn.Linear, LoRALayer):
-    """The reference only builds this with r = 0 on the GS-LoRA path (`lora_pos == "FFN"`, vit_face.py:349-355,409-411):
-    a plain frozen bias-free Linear.  r > 0 (LoRA on attention) is not built yet."""
+    """loralib.MergedLinear (0.1.2): one Linear whose output is len(enable_lora) equal slices (q | k | v), each enabled slice g with its own
+    rank-r pair -- lora_A [r * n_on, in] stacks the A_g, lora_B [out / len * n_on, r] stacks the B_g, slice g's update is s * B_g A_g.
+    The reference builds it with r = 0 for lora_pos "FFN" (a plain bias-free Linear) and with r = lora_rank, enable_lora = [True] * 3 for
+    lora_pos "Attention" (vit_face.py:349-355, 405-425).  Parameter holder: the engine folds the update into its cached to_qkv operand."""
 
     def __init__(self, in_features: int, out_features: int, r: int = 0, lora_alpha: int = 1, lora_dropout: float = 0.0,
                  enable_lora: List[bool] = [False], fan_in_fan_out: bool = False, merge_weights: bool = True, **kwargs):
         nn.Linear.__init__(self, in_features, out_features, **kwargs)
         LoRALayer.__init__(self, r, lora_alpha, lora_dropout, merge_weights)
-        if r > 0:
-            raise NotImplementedError("gslora-b200: MergedLinear with r > 0 (LoRA on attention, lora_pos='Attention') is not built yet")
-        self.enable_lora = enable_lora
+        assert out_features % len(enable_lora) == 0, "The length of enable_lora must divide out_features"
+        self.enable_lora = list(enable_lora)
         self.fan_in_fan_out = fan_in_fan_out
+        if r > 0 and any(enable_lora):
+            if not all(enable_lora) or fan_in_fan_out:
+                raise NotImplementedError("gslora-b200: MergedLinear is built for enable_lora = [True] * n, fan_in_fan_out = False (the reference's to_qkv)")
+            n_on = sum(enable_lora)
+            self.lora_A = nn.Parameter(self.weight.new_zeros((r * n_on, in_features)))
+            self.lora_B = nn.Parameter(self.weight.new_zeros((out_features // len(enable_lora) * n_on, r)))
+            self.scaling = self.lora_alpha / self.r
+            self.weight.requires_grad = False
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.Linear.reset_parameters(self)
+        if hasattr(self, "lora_A"):
+            nn.init.kaiming_uniform_(self.lora_A, a=math.sqrt(5))
+            nn.init.zeros_(self.lora_B)
+
+    def delta_weight(self) -> torch.Tensor:
+        """[out, in]: rows of slice g = B_g A_g * scaling (upstream's merge_AB, a grouped 1x1 conv1d, times scaling)"""
+        n, r = len(self.enable_lora), self.r
+        per = self.out_features // n
+        return torch.cat([self.lora_B.data[g * per:(g + 1) * per] @ self.lora_A.data[g * r:(g + 1) * r] for g in range(n)], dim=0) * self.scaling
+
+    def train(self, mode: bool = True):
+        nn.Linear.train(self, mode)
+        if not self.merge_weights or self.r <= 0 or not any(self.enable_lora):
+            return self
+        if mode and self.merged:
+            self.weight.data -= self.delta_weight()
+            self.merged = False
+            self._gsl_generation += 1
+        elif not mode and not self.merged:
+            self.weight.data += self.delta_weight()
+            self.merged = True
+            self._gsl_generation += 1
+        return self
 
     def forward(self, x: torch.Tensor):
         from gslora.lora_ops import lora_linear_forward

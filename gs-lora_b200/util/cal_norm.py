@@ -29,8 +29,22 @@ _NAMES_TV = ["encoder.layers.encoder_layer_{}.mlp.0.lora_A", "encoder.layers.enc
 def get_norm_of_lora(model, type="L2", group_num=6, group_type: str = "block", group_pos: str = "FFN", imagenet: bool = False):
     if type not in ("L1", "L2"):
         raise ValueError("type should be L1 or L2")
+    if group_pos == "Attention":       # util/cal_norm.py:100-113: one (to_qkv.lora_A, to_qkv.lora_B) group per block, group_type ignored
+        if getattr(model, "lora_pos", "FFN") != "Attention":
+            raise KeyError("get_norm_of_lora(group_pos='Attention'): the model carries no LoRA on to_qkv")
+        names_a = ["transformer.layers.{}.0.fn.fn.to_qkv.lora_A", "transformer.layers.{}.0.fn.fn.to_qkv.lora_B"]
+        print("\033[31mgroup_layers_names\033[0m\n", [[n.format(i) for n in names_a] for i in range(group_num)])
+        with torch.no_grad():
+            eng = getattr(model, "_engine", None) or model.ensure_engine(1)
+            model.sync_engine()
+            per_tensor = eng.tensor_norms(type)          # [2 * depth]
+            if group_num > eng.spec.depth:
+                raise KeyError(f"get_norm_of_lora: group_num={group_num} but the model has {eng.spec.depth} blocks")
+            return [per_tensor[2 * i] + per_tensor[2 * i + 1] for i in range(group_num)]
     if group_pos != "FFN":
-        raise NotImplementedError("gslora-b200: get_norm_of_lora is built for the FFN groupings (LoRA on attention is SURVEY.md 8f-2)")
+        raise ValueError("group_pos should be FFN or Attention")
+    if getattr(model, "lora_pos", "FFN") != "FFN":
+        raise KeyError("get_norm_of_lora(group_pos='FFN'): the model carries its LoRA on to_qkv (lora_pos='Attention')")
     # imagenet=True: the reference ignores group_num and group_type and always reports the first 12 encoder blocks (util/cal_norm.py:82-99;
     # the driver passes group_num=args.vit_depth=6 for ViT-B/16, train_own_forget_cl.py:1100-1105)
     groups = _ffn_groups(12, "block") if imagenet else _ffn_groups(group_num, group_type)

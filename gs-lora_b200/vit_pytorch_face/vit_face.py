@@ -100,8 +100,9 @@ class ViT_face(EngineBackedModel):
         patch_dim = channels * patch_size ** 2
         assert num_patches > MIN_NUM_PATCHES, f"your number of patches ({num_patches}) is way too small for attention to be effective (at least 16). Try decreasing your patch size"
         assert pool in {"cls", "mean"}, "pool type must be either cls (cls token) or mean (mean pooling)"
-        if pool != "cls" or lora_pos != "FFN" or dim_head != 64 or heads * dim_head != dim:
-            raise NotImplementedError("gslora-b200 builds the GS-LoRA configuration: pool='cls', lora_pos='FFN', dim_head=64, heads*64 == dim")
+        if pool != "cls" or lora_pos not in ("FFN", "Attention") or dim_head != 64 or heads * dim_head != dim:
+            raise NotImplementedError("gslora-b200 builds the GS-LoRA configurations: pool='cls', lora_pos 'FFN' or 'Attention', dim_head=64, heads*64 == dim")
+        self.lora_pos = lora_pos
         self.patch_size, self.image_size, self.channels = patch_size, image_size, channels
         self.dim, self.depth, self.heads, self.mlp_dim, self.num_class, self.lora_rank = dim, depth, heads, mlp_dim, num_class, lora_rank
         self.dropout_p, self.emb_dropout_p = float(dropout), float(emb_dropout)
@@ -125,8 +126,12 @@ class ViT_face(EngineBackedModel):
         self._init_engine_state()
 
     def lora_layers(self):
+        """per block, the layers that carry LoRA: (fc1, fc2) for lora_pos "FFN", (to_qkv,) for lora_pos "Attention" (vit_face.py:405-425)"""
         for attn, ff in self.transformer.layers:
-            yield ff.fn.fn.net[0], ff.fn.fn.net[3]
+            if self.lora_pos == "Attention":
+                yield (attn.fn.fn.to_qkv,)
+            else:
+                yield ff.fn.fn.net[0], ff.fn.fn.net[3]
 
     def _frozen_tensors(self):
         t = [self.pos_embedding, self.cls_token, self.patch_to_embedding.weight, self.patch_to_embedding.bias,
@@ -142,7 +147,8 @@ class ViT_face(EngineBackedModel):
                           heads=self.heads, mlp_dim=self.mlp_dim, num_class=self.num_class, lora_rank=self.lora_rank,
                           attn_scale=self.dim ** -0.5, ln_eps=self.mlp_head[0].eps,
                           cos_s=getattr(getattr(self, "loss", None), "s", 64.0), cos_m=getattr(getattr(self, "loss", None), "m", 0.35),
-                          grad_scale=float(os.environ.get("GSLORA_GRAD_SCALE", "1024")), dropout=self.dropout_p, emb_dropout=self.emb_dropout_p)
+                          grad_scale=float(os.environ.get("GSLORA_GRAD_SCALE", "1024")), dropout=self.dropout_p, emb_dropout=self.emb_dropout_p,
+                          lora_pos=1 if self.lora_pos == "Attention" else 0)
 
     def forward(self, img, label=None, mask=None):
         """:return: (logits, emb) if `label` is given else emb -- as vit_face.py:523-548"""

@@ -131,6 +131,8 @@ typedef struct GslConfig {
   int32_t precision;     /* 0 = "fast": every frozen weight rounded to fp16 once (LoRA gradients ~1-2e-3 of the FP32 reference);
                             1 = "split": weights and LoRA factors enter the GEMMs as fp16 hi + lo pairs (22 significand bits; gradients <= 1e-3,
                             the north-star parity bar) at 2x the tensor-pipe work.  Activations are fp16 with fp32 accumulation in both. */
+  int32_t lora_pos;      /* 0 = "FFN": lora.Linear on net.0 / net.3 (every GS-LoRA script); 1 = "Attention": lora.MergedLinear(r, enable_lora = [T, T, T]) on
+                            to_qkv and plain FFN Linears (vit_face.py:349-355, 405-425; engine.py:650-656) */
 } GslConfig;
 
 /* Frozen parameter pointer table order for gsl_engine_bind_params (fp32 device pointers, reference state_dict names):
@@ -140,7 +142,8 @@ typedef struct GslConfig {
  *    heads.head.weight, heads.head.bias; per block ln_1, self_attention.in_proj_{weight,bias}, out_proj, ln_2, mlp.0, mlp.3)
  *   then per block i (12 entries): 0.fn.norm.{weight,bias}, 0.fn.fn.to_qkv.{weight, bias(NULL for ViT_face)},
  *   0.fn.fn.to_out.0.{weight,bias}, 1.fn.norm.{weight,bias}, 1.fn.fn.net.0.{weight,bias}, 1.fn.fn.net.3.{weight,bias}
- * lora_flat / grad_flat: fp32 [depth][ lora_A(net.0) r*D | lora_B(net.0) H*r | lora_A(net.3) r*H | lora_B(net.3) D*r ]  */
+ * lora_flat / grad_flat: fp32 [depth][ lora_A(net.0) r*D | lora_B(net.0) H*r | lora_A(net.3) r*H | lora_B(net.3) D*r ]
+ *   lora_pos = 1:       fp32 [depth][ to_qkv.lora_A 3r*D (A_q | A_k | A_v) | to_qkv.lora_B 3*inner*r (B_q | B_k | B_v) ]  */
 #define GSL_NUM_GLOBAL_PARAMS 8
 #define GSL_NUM_BLOCK_PARAMS 12
 
@@ -166,7 +169,7 @@ int gsl_engine_backward(void* handle, int slot, const float* dlogits, const floa
 /* XFINAL: fp32 [B, dim] -- the cls rows of the last block's output (the only rows of that block that are computed) */
 enum { GSL_SLOT_EMB = 0, GSL_SLOT_LOGITS = 1, GSL_SLOT_CE = 2, GSL_SLOT_CORRECT = 3, GSL_SLOT_XFINAL = 4 };
 void* gsl_engine_slot_ptr(void* handle, int slot, int what);
-int64_t gsl_engine_lora_offset(void* handle, int block, int which);   /* which: 0 A(net.0) 1 B(net.0) 2 A(net.3) 3 B(net.3) */
+int64_t gsl_engine_lora_offset(void* handle, int block, int which);   /* which: 0 A(net.0) 1 B(net.0) 2 A(net.3) 3 B(net.3); lora_pos 1: 0 A(to_qkv) 1 B(to_qkv) */
 int64_t gsl_engine_lora_numel(void* handle);
 
 /* Step losses of engine_cl.train_one_epoch (engine_cl.py:65-80) on device, no host sync:

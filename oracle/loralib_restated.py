@@ -5,7 +5,7 @@ not vendored in the reference tree and is not installable here (no network).  Th
 restates the published algorithm of microsoft/LoRA `loralib/layers.py` v0.1.2 for the
 three symbols the hot path uses; call sites in the reference:
   - vit_pytorch_face/vit_face.py:330,333   lora.Linear(dim, hidden, r=lora_rank)
-  - vit_pytorch_face/vit_face.py:349-355   lora.MergedLinear(..., r=0, enable_lora=[T,T,T], bias=False)
+  - vit_pytorch_face/vit_face.py:349-355   lora.MergedLinear(..., r=0 [lora_pos "FFN"] or r=lora_rank [lora_pos "Attention"], enable_lora=[T,T,T], bias=False)
   - util/utils.py:573                      lora.Linear(in, out, r=rank)
   - train/train_own_forget_cl.py:316       lora.mark_only_lora_as_trainable(BACKBONE)
 
@@ -88,8 +88,11 @@ class Linear(nn.Linear, LoRALayer):
 
 
 class MergedLinear(nn.Linear, LoRALayer):
-    """Only the r == 0 form is on the hot path (vit_face.py:349-355 with lora_pos == "FFN",
-    i.e. a plain bias-free nn.Linear).  r > 0 (LoRA on attention) is SURVEY section 8f-2, not built."""
+    """One Linear whose output is `len(enable_lora)` equal slices (q | k | v), each enabled slice with its OWN rank-r pair:
+    lora_A [r * n_enabled, in] stacks the A_g, lora_B [out / len * n_enabled, r] stacks the B_g, and the update of slice g is
+    s * B_g A_g (upstream evaluates it as a grouped 1x1 conv1d of lora_A with lora_B, groups = n_enabled, scattered back into the
+    enabled rows).  r = 0 is a plain frozen-or-not nn.Linear: what the reference builds with lora_pos == "FFN"
+    (vit_face.py:349-355, 409-411); r > 0 is its lora_pos == "Attention" variant."""
 
     def __init__(self, in_features: int, out_features: int, r: int = 0, lora_alpha: int = 1,
                  lora_dropout: float = 0.0, enable_lora: List[bool] = [False],
@@ -97,13 +100,59 @@ class MergedLinear(nn.Linear, LoRALayer):
         nn.Linear.__init__(self, in_features, out_features, **kwargs)
         LoRALayer.__init__(self, r=r, lora_alpha=lora_alpha, lora_dropout=lora_dropout,
                            merge_weights=merge_weights)
-        if r > 0:
-            raise NotImplementedError("oracle restates MergedLinear for r == 0 only")
+        assert out_features % len(enable_lora) == 0, "The length of enable_lora must divide out_features"
         self.enable_lora = enable_lora
         self.fan_in_fan_out = fan_in_fan_out
+        if r > 0 and any(enable_lora):
+            n_on = sum(enable_lora)
+            self.lora_A = nn.Parameter(self.weight.new_zeros((r * n_on, in_features)))
+            self.lora_B = nn.Parameter(self.weight.new_zeros((out_features // len(enable_lora) * n_on, r)))
+            self.scaling = self.lora_alpha / self.r
+            self.weight.requires_grad = False
+            ind = self.weight.new_zeros((out_features,), dtype=torch.bool).view(len(enable_lora), -1)
+            ind[enable_lora, :] = True
+            self.lora_ind = ind.view(-1)
+        self.reset_parameters()
+        if fan_in_fan_out:
+            self.weight.data = self.weight.data.transpose(0, 1)
+
+    def reset_parameters(self):
+        nn.Linear.reset_parameters(self)
+        if hasattr(self, "lora_A"):
+            nn.init.kaiming_uniform_(self.lora_A, a=math.sqrt(5))
+            nn.init.zeros_(self.lora_B)
+
+    def _T(self, w):
+        return w.transpose(0, 1) if self.fan_in_fan_out else w
+
+    def merge_AB(self):
+        """[out, in] update before scaling: rows of enabled slice g hold B_g A_g, disabled rows zero."""
+        n_on = sum(self.enable_lora)
+        delta = F.conv1d(self.lora_A.unsqueeze(0), self.lora_B.unsqueeze(-1), groups=n_on).squeeze(0)
+        full = delta.new_zeros((len(self.lora_ind), *delta.shape[1:]))
+        full[self.lora_ind] = delta
+        return self._T(full)
+
+    def train(self, mode: bool = True):
+        nn.Linear.train(self, mode)
+        live = self.r > 0 and any(self.enable_lora)
+        if mode:
+            if self.merge_weights and self.merged:
+                if live:
+                    self.weight.data -= self.merge_AB() * self.scaling
+                self.merged = False
+        else:
+            if self.merge_weights and not self.merged:
+                if live:
+                    self.weight.data += self.merge_AB() * self.scaling
+                self.merged = True
+        return self
 
     def forward(self, x: torch.Tensor):
-        return F.linear(x, self.weight, bias=self.bias)
+        result = F.linear(x, self._T(self.weight), bias=self.bias)
+        if not self.merged and self.r > 0 and any(self.enable_lora):
+            result = result + self.lora_dropout(x) @ self._T(self.merge_AB().T) * self.scaling
+        return result
 
 
 def mark_only_lora_as_trainable(model: nn.Module, bias: str = "none") -> None:

@@ -76,8 +76,23 @@ def test_loralib_merge_unmerge_semantics():
     assert not lin.merged and torch.allclose(lin.weight, w0, atol=1e-6)
     ml = lora.MergedLinear(32, 96, r=0, enable_lora=[True, True, True], bias=False)
     assert ml.bias is None and not hasattr(ml, "lora_A")
+    # r > 0: loralib.MergedLinear's per-slice pairs (lora_pos "Attention", vit_face.py:349-355) -- same merge arithmetic as the oracle restatement
+    from oracle import loralib_restated as olora
+    torch.manual_seed(3)
+    mq = lora.MergedLinear(32, 96, r=4, enable_lora=[True, True, True], bias=False)
+    oq = olora.MergedLinear(32, 96, r=4, enable_lora=[True, True, True], bias=False)
+    assert mq.lora_A.shape == oq.lora_A.shape == (12, 32) and mq.lora_B.shape == oq.lora_B.shape == (96, 4) and not mq.weight.requires_grad
+    with torch.no_grad():
+        mq.lora_B.normal_(0, 0.1)
+        oq.load_state_dict(mq.state_dict())
+    w0 = mq.weight.detach().clone()
+    mq.eval(); oq.eval()
+    assert mq.merged and torch.allclose(mq.weight, oq.weight, atol=1e-7) and not torch.allclose(mq.weight, w0)
+    assert torch.allclose(mq.weight[32:64], w0[32:64] + (mq.lora_B[32:64] @ mq.lora_A[4:8]) / 4, atol=1e-6)     # slice k uses (A_k, B_k) only
+    mq.train()
+    assert not mq.merged and torch.allclose(mq.weight, w0, atol=1e-6)
     with pytest.raises(NotImplementedError):
-        lora.MergedLinear(32, 96, r=8, enable_lora=[True, True, True])
+        lora.MergedLinear(32, 96, r=8, enable_lora=[True, False, True])
 
 
 def test_model_is_a_regular_module_and_refuses_cpu_execution():

@@ -120,7 +120,7 @@ def test_engine_py_alpha_epoch_gate_and_unsupported_group_pos(fake):
     ret = engine.train_one_epoch(*args, 3, *_meters(6), 0.15, 1e-2, 105.0, 0, None, None, 0.0, 0.0, cfg)
     assert all(c[4]["alpha"] == 1e-2 for c in fake.calls)
     assert ret[7].avg == pytest.approx(1e-2 * 4.0)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):     # GROUP_POS must name where the model's LoRA lives (this model: FFN); the reference would sum an empty group list
         engine.train_one_epoch(*args, 0, *_meters(6), 0.15, 1e-2, 105.0, 0, None, None, 0.0, 0.0, dict(cfg, GROUP_POS="Attention"))
 
 

@@ -274,3 +274,107 @@ def test_engine_py_eval_and_checkpoint_match_a_merged_deepcopy(tmp_path):
     for k in saved:
         assert torch.allclose(saved[k].cpu(), ref_sd[k].cpu(), rtol=0, atol=1e-6), k
     assert not torch.equal(saved[w_name].cpu(), w0.cpu())                            # the LoRA delta is in the saved weight
+
+
+# ------------------------------------------------------------------------------------------------ 8f-2: LoRA on attention (lora_pos "Attention")
+def _attn_model(cfg, sd):
+    import loralib as lora
+    from vit_pytorch_face import ViT_face
+    m = ViT_face(loss_type="CosFace", GPU_ID=[0], num_class=cfg.num_class, image_size=cfg.image_size, patch_size=cfg.patch_size, dim=cfg.dim,
+                 depth=cfg.depth, heads=cfg.heads, mlp_dim=cfg.mlp_dim, dim_head=cfg.dim_head, dropout=0.0, emb_dropout=0.0,
+                 lora_rank=cfg.lora_rank, lora_pos="Attention")
+    m.load_state_dict(sd, strict=True)
+    lora.mark_only_lora_as_trainable(m)
+    assert sorted(n for n, p in m.named_parameters() if p.requires_grad) == sorted(O.lora_param_list(cfg))
+    return m.cuda().train()
+
+
+def test_attention_lora_matches_unmodified_reference_golden(golden_dir):
+    """ViT_face(lora_pos="Attention") on the engine -- merged to_qkv operand with per-slice (A_g, B_g), attention backward down to block 0,
+    dA_g / dB_g side products -- against the unmodified reference's records (tests/golden/make_golden_attn.py): autograd path (two forwards,
+    torch losses, engine.get_structure_loss(group_pos="Attention")), then the fused step, then the norm report and merge / un-merge."""
+    import engine
+    import engine_cl
+    from util.cal_norm import get_norm_of_lora
+    g = torch.load(os.path.join(golden_dir, "tiny3_attn_lora.pt"), weights_only=False)
+    cfg, hp = O.VitConfig(**g["cfg"]), g["hp"]
+    xr, yr, xf, yf = [g[k].cuda() for k in ("img_r", "lab_r", "img_f", "lab_f")]
+    names = O.lora_param_list(cfg)
+    rec = g["steps"][0]
+    model = _attn_model(cfg, g["state_dict"])
+    crit = torch.nn.CrossEntropyLoss()
+    out_r, emb_r = model(xr, yr)
+    out_f, _ = model(xf, yf)
+    s_loss = engine.get_structure_loss(model, num_layers=cfg.depth, group_type="block", group_pos="Attention")
+    total = torch.relu(hp["BND"] - crit(out_f, yf)) * hp["beta"] + crit(out_r, yr) + s_loss * hp["alpha"]
+    total.backward()
+    assert rel(out_r, rec["logits_r"]) < 1e-3 and rel(out_f, rec["logits_f"]) < 1e-3 and rel(emb_r, rec["emb_r"]) < 1e-3
+    assert abs(float(s_loss) - rec["structure"]) < 1e-5 * rec["structure"] and abs(float(total) - rec["total"]) < 2e-3 * abs(rec["total"])
+    per = {n: rel(model.get_parameter(n).grad, rec["grads"][n]) for n in names}
+    allrel = rel(torch.cat([model.get_parameter(n).grad.flatten() for n in names]), torch.cat([rec["grads"][n].flatten() for n in names]))
+    print(f"attention LoRA tiny3: logits {rel(out_r, rec['logits_r']):.2e} grads all {allrel:.2e} worst {max(per.values()):.2e}")
+    assert allrel < 1e-3 and max(per.values()) < 1.5e-3
+    with pytest.raises(ValueError):
+        engine.get_structure_loss(model, num_layers=cfg.depth, group_pos="FFN")
+    # fused steps, teacher-forced onto the reference's parameters between them
+    model = _attn_model(cfg, g["state_dict"])
+    for rec in g["steps"]:
+        before = {n: model.get_parameter(n).detach().clone() for n in names}
+        out = engine_cl.unlearn_step(model, xr, yr, xf, yf, beta=hp["beta"], alpha=hp["alpha"], BND=hp["BND"], hparams=dict(lr=hp["lr"], wd=hp["wd"]))
+        for key in ("loss_remain", "ce_forget", "loss_forget", "structure", "total"):
+            assert abs(out[key] - rec[key]) <= 2e-3 * max(1.0, abs(rec[key])), (key, out[key], rec[key])
+        eng = model._engine
+        got, ref = [], []
+        for l, grp in enumerate(O.lora_names(cfg)):
+            gn = torch.sqrt(sum((before[n] ** 2).sum() for n in grp))
+            for w, n in enumerate(grp):
+                got.append((eng.lora_view(eng.grad_flat, l, w) + hp["alpha"] * before[n] / gn).flatten())
+                ref.append(rec["grads"][n].flatten())
+        assert rel(torch.cat(got), torch.cat(ref)) < 1e-3
+        for n in names:
+            gref = rec["grads"][n].cuda()
+            p, pref = model.get_parameter(n).data, rec["params_after"][n].cuda()
+            well = gref.abs() > 0.05 * gref.abs().mean()
+            assert (p - pref)[well].abs().max() < 0.05 * hp["lr"], n
+            p.copy_(pref)
+        model.sync_engine(force_lora=True)
+    norms = get_norm_of_lora(model, type="L2", group_num=cfg.depth, group_pos="Attention")
+    for a, b in zip(norms, g["norm_of_lora_L2"]):
+        assert abs(float(a) - b) < 2e-3 * abs(b)
+    with pytest.raises(KeyError):
+        get_norm_of_lora(model, type="L2", group_num=cfg.depth, group_pos="FFN")
+    # loralib merge semantics on to_qkv: eval() folds s B_g A_g into the weight slice by slice, the function does not change, train() restores
+    with torch.no_grad():
+        lt, _ = model(xr, yr)
+        w0 = model.get_parameter(O.blk(0, "0.fn.fn.to_qkv.weight")).clone()
+        model.eval()
+        le, _ = model(xr, yr)
+        assert not torch.equal(model.get_parameter(O.blk(0, "0.fn.fn.to_qkv.weight")), w0)
+        model.train()
+        lt2, _ = model(xr, yr)
+    assert rel(le, lt) < 1e-3 and rel(lt2, lt) < 1e-4 and rel(le, g["eval_logits_r"].cuda()) < 5e-2
+
+
+@pytest.mark.parametrize("mode", ["split", "fast"])
+def test_attention_lora_p8s8_vs_oracle_fp32(mode):
+    """Config-2 widths with LoRA r = 8 on to_qkv, bs 32+32: logits and the 12 to_qkv LoRA gradients against the oracle in FP32 on the same GPU."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = O.VitConfig(**{**O.P8S8.to_dict(), "lora_pos": "Attention"})
+    sd = O.init_state_dict(cfg, seed=1337)
+    gen = torch.Generator().manual_seed(7)
+    B = 32
+    xr, xf = torch.rand(B, 3, 112, 112, generator=gen).cuda(), torch.rand(B, 3, 112, 112, generator=gen).cuda()
+    yr, yf = torch.randint(0, 100, (B,), generator=gen).cuda(), torch.randint(0, 100, (B,), generator=gen).cuda()
+    ref, ref_grads = O.unlearn_grads({k: v.cuda() for k, v in sd.items()}, cfg, xr, yr, xf, yf, beta=0.15, alpha=1e-4, BND=105.0, include_structure=False)
+    model = _attn_model(cfg, sd)
+    model.gsl_precision = mode
+    crit = torch.nn.CrossEntropyLoss()
+    out_r, _ = model(xr, yr)
+    out_f, _ = model(xf, yf)
+    (torch.relu(105.0 - crit(out_f, yf)) * 0.15 + crit(out_r, yr)).backward()
+    names = O.lora_param_list(cfg)
+    per = {n: rel(model.get_parameter(n).grad, ref_grads[n]) for n in names}
+    allrel = rel(torch.cat([model.get_parameter(n).grad.flatten() for n in names]), torch.cat([ref_grads[n].flatten() for n in names]))
+    print(f"attention LoRA P8S8 bs32 [{mode}]: logits {rel(out_r, ref['logits_r']):.2e} grads all {allrel:.2e} worst {max(per.values()):.2e}")
+    assert rel(out_r, ref["logits_r"]) < 1e-3 and rel(out_f, ref["logits_f"]) < 1e-3
+    assert allrel < (1e-3 if mode == "split" else 2e-3) and max(per.values()) < (1.25e-3 if mode == "split" else 3.5e-3)

@@ -167,3 +167,36 @@ def test_torchvision_family_reference_is_plain_torchvision_plus_loralib(golden_d
     assert rel(logits, g["logits"]) < 1e-6 and rel(emb, g["emb"]) < 1e-6 and abs(float(loss) - g["loss"]) < 1e-6
     for n in names:
         assert rel(ref.get_parameter(n).grad, g["grads"][n]) < 1e-5, n
+
+
+def test_attention_lora_oracle_matches_reference_golden(golden_dir):
+    """lora_pos "Attention" (SURVEY 8f-2): the oracle against the UNMODIFIED ViT_face(lora_pos="Attention") + engine.get_structure_loss(group_pos=
+    "Attention") + cal_norm(group_pos="Attention") records of tests/golden/make_golden_attn.py -- logits, losses, every to_qkv LoRA gradient,
+    parameters after two AdamW steps, the norm report and the merged eval forward."""
+    g = torch.load(os.path.join(golden_dir, "tiny3_attn_lora.pt"), weights_only=False)
+    cfg, hp = O.VitConfig(**g["cfg"]), g["hp"]
+    assert cfg.lora_pos == "Attention"
+    sd = {k: v.clone() for k, v in g["state_dict"].items()}
+    regen = O.init_state_dict(cfg, seed=g["seed"])
+    assert set(regen) == set(sd) and all(torch.equal(regen[k], sd[k]) for k in sd)
+    assert not any("net.0.lora" in k or "net.3.lora" in k for k in sd) and sum("to_qkv.lora_" in k for k in sd) == 2 * cfg.depth
+    state = {}
+    for rec in g["steps"]:
+        out, grads = O.unlearn_step(sd, cfg, state, g["img_r"], g["lab_r"], g["img_f"], g["lab_f"], lr=hp["lr"], wd=hp["wd"], beta=hp["beta"],
+                                    alpha=hp["alpha"], BND=hp["BND"])
+        assert rel(out["logits_r"], rec["logits_r"]) < 2e-6 and rel(out["logits_f"], rec["logits_f"]) < 2e-6
+        for key in ("loss_remain", "ce_forget", "loss_forget", "structure", "total"):
+            assert abs(float(out[key]) - rec[key]) <= 2e-5 * max(1.0, abs(rec[key])), key
+        for n in O.lora_param_list(cfg):
+            assert rel(grads[n], rec["grads"][n]) < 2e-5, n
+            assert rel(sd[n], rec["params_after"][n]) < 1e-5, n
+    for a, b in zip(O.norm_of_lora(sd, cfg, "L2"), g["norm_of_lora_L2"]):
+        assert abs(float(a) - b) < 1e-4 * abs(b)
+    for a, b in zip(O.norm_of_lora(sd, cfg, "L1"), g["norm_of_lora_L1"]):
+        assert abs(float(a) - b) < 1e-4 * abs(b)
+    with torch.no_grad():       # merged == un-merged function; the golden's merged to_qkv rows are W + s B_g A_g slice by slice
+        logits_e, _ = O.vit_forward(sd, cfg, g["img_r"], g["lab_r"])
+    assert rel(logits_e, g["eval_logits_r"]) < 1e-5
+    W = sd[O.blk(0, "0.fn.fn.to_qkv.weight")] + cfg.lora_scaling * O.merged_qkv_delta(sd[O.blk(0, "0.fn.fn.to_qkv.lora_A")],
+                                                                                     sd[O.blk(0, "0.fn.fn.to_qkv.lora_B")], cfg.lora_rank)
+    assert rel(W[::37, :16], g["eval_merged_qkv_w"]) < 1e-6
