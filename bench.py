@@ -414,6 +414,7 @@ def kernel_roofline(dev, cfg, peaks, BATCH=BATCH, DROPOUT=DROPOUT, split=True):
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
+        tj = tj.get("split" if split else "fast", tj)
         traffic, traffic_src = tj.get("ffn_pair_bytes"), tj.get("source")
     # fc1 reads x, writes G and mask*gelu'(h) (fp16); fc2 reads G and the fp32 residual, writes the fp32 stream; weights 4 x D x H fp16
     alg_bytes = 2 * M * D + 2 * 2 * M * H + 2 * M * H + 2 * 4 * M * D + 4 * D * H

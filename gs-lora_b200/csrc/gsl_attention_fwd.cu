@@ -3,8 +3,8 @@
 // One persistent CTA per SM walks over work items = (image, head, 128-row query tile); N <= 208 tokens gives one or two items per
 // (image, head) pair, which share the K / V slabs.  Per item j:
 //   S_j = Q_tile K^T      tcgen05.mma  M=128, N=npad, K=64        -> TMEM S[j & 1]   (double-buffered: 2 x 208 columns)
-//   softmax               8 worker warps, thread = (query row, half of the key columns): sweep 1 = row max over ALL columns
-//                         (FMNMX3, both halves compute it redundantly - cheaper than an exchange), sweep 2 = exp2 on the own half,
+//   softmax               8 worker warps, thread = (query row, half of the key columns): ONE TMEM read of the own half row into registers,
+//                         half-row max (FMNMX3) exchanged with the partner half through shared memory, exp2 on the own half,
 //                         fp16 P into a 128B-swizzled K-major tile P[j & 1] (= the A operand of the next MMA), partial row sums to smem
 //   O_j = P_j V           tcgen05.mma  M=128, N=64, K=npad; V is consumed straight from its TMA slab as an MN-major B operand
 //                         -> TMEM O (its own 64 columns, so S buffers are recycled as soon as the workers have read them)
@@ -43,7 +43,7 @@ static constexpr uint32_t AF_PB_BYTES = 3 * 80 * 128 + 16384;   //   blocks hold
                                                                 //   keep that in bounds); with one tile npad <= 128 needs two full blocks
 static constexpr uint32_t AF_STAGE = AF_PB + AF_PB_BYTES;       // [128 rows x 64] fp16 staging tile of the O TMA store
 static constexpr uint32_t AF_SUMS = AF_STAGE + AF_QT;           // [2 parities][2 halves][128] partial row sums, [2 parities][128] row maxima,
-static constexpr uint32_t AF_BARS = AF_SUMS + (2 * 2 * 128 + 2 * 128 + 2 * 128) * 4;     //   [2 halves][128] half-row maxima (exchange)
+static constexpr uint32_t AF_BARS = AF_SUMS + (2 * 2 * 128 + 2 * 128 + 2 * 2 * 128) * 4; //   [2 parities][2 halves][128] half-row maxima (exchange)
 static constexpr uint32_t AF_SMEM = AF_BARS + 256;
 static_assert(AF_K % 1024 == 0 && AF_V % 1024 == 0 && AF_PA % 1024 == 0 && AF_PB % 1024 == 0 && AF_STAGE % 1024 == 0, "tiles must stay 1024-byte aligned");
 static_assert(AF_SMEM + 1024 <= 232448, "attention forward: shared memory budget");
@@ -126,7 +126,10 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AF_BARS + 8 * F_COUNT);
     float* s_sums = reinterpret_cast<float*>(smem + AF_SUMS);
     float* s_rowmax = s_sums + 2 * 2 * 128;        // [2 parities][128]: final row max of the item (for its LSE)
-    float* s_max = s_rowmax + 2 * 128;             // [2 halves][128]: exchange of the half-row maxima
+    float* s_max = s_rowmax + 2 * 128;             // [2 parities][2 halves][128]: exchange of the half-row maxima.  Per-parity slots: a warp of
+                                                   // one half may run a whole item ahead of its partner half (only the barrier below couples
+                                                   // them), so item j + 1's write must not land on the slot the partner still reads for item j
+                                                   // (compute-sanitizer racecheck, profiles/r02e_sanitizer_racecheck.log)
     const uint32_t pb_stride = nt == 2 ? 80u * 128u : 16384u;      // block stride of the odd-item P tile
     auto p_base = [&](uint32_t pb) { return pb == 0 ? sb + AF_PA : sb + AF_PB; };
     auto p_stride = [&](uint32_t pb) { return pb == 0 ? 16384u : pb_stride; };
@@ -268,9 +271,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
 #pragma unroll
                 for (int k = 0; k < MAXP; ++k) if (k < cnt) mx = af_max16(sv[k], mx, (p_lo + k) * 16, N);
             }
-            s_max[hf * 128 + rl] = mx;
+            s_max[sbuf * 256 + hf * 128 + rl] = mx;
             af_bar_workers();                   // exchange of the half-row maxima
-            mx = fmaxf(mx, s_max[(hf ^ 1) * 128 + rl]);
+            mx = fmaxf(mx, s_max[sbuf * 256 + (hf ^ 1) * 128 + rl]);
             if (dbg & 1) mx = 0.f;
             if (rows_on && !(dbg & 2)) {
                 // ---- exp sweep: p = exp2(scale * log2e * (s - max)), fp16 -> swizzled K-major P tile

@@ -11,9 +11,10 @@ EPI = {0: "F16", 1: "F32", 2: "GELU", 3: "GELU_BWD", 4: "RES_F32", 5: "PERIODIC_
 
 
 def short(name):
-    m = re.search(r"gemm_tcgen05_kernel<(?:\(int\))?(\d), (?:\(int\))?(\d+), (?:\(int\))?(\d)>", name)
+    m = re.search(r"gemm_tcgen05_kernel<(?:\(int\))?(\d), (?:\(int\))?(\d+), (?:\(int\))?(\d)(?:, (?:\(bool\))?(\w+))?>", name)
     if m:
-        return f"gsl::gemm_tcgen05_kernel<cg{m.group(1)}, bn{m.group(2)}, {EPI.get(int(m.group(3)), m.group(3))}>"
+        split = ", SPLIT" if m.group(4) in ("1", "true") else ""
+        return f"gsl::gemm_tcgen05_kernel<cg{m.group(1)}, bn{m.group(2)}, {EPI.get(int(m.group(3)), m.group(3))}{split}>"
     return re.sub(r"\(.*", "", name).replace("void ", "")
 
 

@@ -235,7 +235,7 @@ def test_engine_py_train_one_epoch_loader_swap_and_alpha_gate(few_shot, alpha_ep
     a = engine.get_structure_loss(m2, num_layers=cfg.depth, group_type=group_type, group_pos="FFN")
     b = engine_cl.get_structure_loss(m2, group_type=group_type)
     assert float(a) == float(b)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):
         engine.get_structure_loss(m2, num_layers=cfg.depth, group_type="block", group_pos="Attention")
     with pytest.raises(ValueError):
         engine.get_structure_loss(m2, num_layers=cfg.depth + 1)
@@ -377,4 +377,4 @@ def test_attention_lora_p8s8_vs_oracle_fp32(mode):
     allrel = rel(torch.cat([model.get_parameter(n).grad.flatten() for n in names]), torch.cat([ref_grads[n].flatten() for n in names]))
     print(f"attention LoRA P8S8 bs32 [{mode}]: logits {rel(out_r, ref['logits_r']):.2e} grads all {allrel:.2e} worst {max(per.values()):.2e}")
     assert rel(out_r, ref["logits_r"]) < 1e-3 and rel(out_f, ref["logits_f"]) < 1e-3
-    assert allrel < (1e-3 if mode == "split" else 2e-3) and max(per.values()) < (1.25e-3 if mode == "split" else 3.5e-3)
+    assert allrel < (1e-3 if mode == "split" else 3e-3) and max(per.values()) < (1.25e-3 if mode == "split" else 5e-3)
