@@ -50,7 +50,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(HeadArgs a) {
     const float enorm = fmaxf(sqrtf(block_sum(en, red)), 1e-12f);     // F.normalize eps
     if (tid == 0 && a.rstd) a.rstd[b] = rstd;
     if (a.W == nullptr) return;
-    const int label = a.labels ? (int)a.labels[b] : -1;
+    // a label outside [0, C) never indexes anything: its sample reports CE = NaN (the reference's F.cross_entropy would raise) and is never "correct"
+    const long long label_raw = a.labels ? (long long)a.labels[b] : -1;
+    const bool label_bad = a.labels && (label_raw < 0 || label_raw >= C);
+    const int label = (a.labels && !label_bad) ? (int)label_raw : -1;
     const int warp = tid >> 5, lane = tid & 31;
     for (int c = warp; c < C; c += HEAD_THREADS / 32) {
         const float* w = a.W + (int64_t)c * D;
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(HeadArgs a) {
         for (int c = lane; c < C; c += 32) se += __expf(s_logit[c] - mx);
         se = warp_sum(se);
         if (lane == 0) {
-            if (a.ce) a.ce[b] = (label >= 0) ? (mx + logf(se) - s_logit[label]) : 0.f;
+            if (a.ce) a.ce[b] = label_bad ? __int_as_float(0x7fc00000) : (label >= 0) ? (mx + logf(se) - s_logit[label]) : 0.f;
             if (a.correct) a.correct[b] = (arg == label) ? 1 : 0;
         }
     }

@@ -7,6 +7,8 @@
 //                                                           where the reference produces NaN)
 //   m, v EMA ; p *= 1 - lr*wd ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 // n_g (pre-update) is written out: sum_g n_g is the structure-loss scalar the reference logs.
+// Overflow guard of the loss-scaled fp16 gradient stream: a group whose gradient holds an inf / NaN is NOT updated (parameters and
+// moments keep their values) and reports n_g = NaN, which the host turns into a FloatingPointError when it reads the step's scalars.
 #include "gsl_common.cuh"
 #include "gsl_kernels.h"
 
@@ -19,19 +21,25 @@ __global__ void __launch_bounds__(1024) grouplasso_adamw_kernel(OptimArgs a, flo
     const int gidx = blockIdx.x;
     const int64_t lo = a.group_offsets[gidx], hi = a.group_offsets[gidx + 1];
     float ss = 0.f;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) { const float p = a.params[i]; ss += p * p; }
+    int bad = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float p = a.params[i];
+        ss += p * p;
+        bad |= !isfinite(a.grads[i]);
+    }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-    __syncthreads();
+    bad = __syncthreads_or(bad);
     if (threadIdx.x < 32) {
         float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
         t = warp_sum(t);
         if (threadIdx.x == 0) {
             s_norm = sqrtf(t);
-            if (a.group_norms) a.group_norms[gidx] = s_norm;
+            if (a.group_norms) a.group_norms[gidx] = bad ? __int_as_float(0x7fc00000) : s_norm;
         }
     }
     __syncthreads();
+    if (bad) return;
     const float norm = s_norm;
     const float lasso = (a.alpha != 0.f && norm > 0.f) ? a.alpha / norm : 0.f;
     const float decay = 1.0f - a.lr * a.wd;

@@ -198,6 +198,9 @@ class StepResult:
             host = self._pinned[:self._n].tolist()
             c = self._c
             s_ce_r, n_r, s_ce_f, n_f, hit_r, hit_f, s_kl_r, s_kl_f, structure = host[:9]
+            if structure != structure:       # NaN: gsl_grouplasso_adamw_step found inf / NaN in a group's gradient and skipped that group
+                raise FloatingPointError("unlearn_step: the loss-scaled fp16 gradient stream overflowed (non-finite LoRA gradient); the affected "
+                                         "groups were not updated -- lower GSLORA_GRAD_SCALE (default 1024)")
             if self._n > 9 and host[9] != 0.0:
                 raise KeyError("unlearn_step: a label of this step's batch has no entry in prototype_dict (engine_cl.py:571-603 looks every "
                                "label up in the dict)")
@@ -270,9 +273,10 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
         table = kl = None
         if use_prototype:                                       # GS-LoRA++ (engine_cl.py:97-101): per-sample KL to the class prototype, on device
             table, present = _cached_prototype_table(m, prototype_dict, eng.spec.num_class, eng.spec.dim, dev)
+            lab_kl = lab.clamp(0, eng.spec.num_class - 1)       # the KL kernels index the table by label: never out of bounds
             if present is not None:                             # a label without a prototype is a KeyError in the reference: flagged on device,
-                missing = (~present[lab.clamp(0, eng.spec.num_class - 1)]).any().float().view(1)     # raised when the step's scalars are read
-            kl = eng.prototype_kl(slot, lab, table, B)
+                missing = ((lab != lab_kl) | ~present[lab_kl]).any().float().view(1)                 # raised when the step's scalars are read
+            kl = eng.prototype_kl(slot, lab_kl, table, B)
         sums = eng.loss_sums(slot, Br, B, kl)
     else:
         # this rank's share of the global batch is empty (drop_last=False tails, few-shot forget sets smaller than the world size): it still
@@ -283,7 +287,7 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
     if B > 0:
         dlogits = torch.empty(B, eng.spec.num_class, dtype=torch.float32, device=dev)
         eng.unlearn_ce_grad(slot, lab, Br, B, beta, BND, dlogits)
-        demb = eng.prototype_kl_grad(slot, lab, table, Br, B, prototype_weight_forget, prototype_weight_remain, BND_pro) if use_prototype else None
+        demb = eng.prototype_kl_grad(slot, lab_kl, table, Br, B, prototype_weight_forget, prototype_weight_remain, BND_pro) if use_prototype else None
         eng.backward(slot, dlogits, demb, accumulate=False)
     else:
         eng.grad_flat.zero_()

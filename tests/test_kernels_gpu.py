@@ -286,3 +286,23 @@ def test_lora_side_split(F, M, N, r, tr):
     assert (T[:, r:] == 0).all()
     wantQ = 0.5 * (L.float().t() @ R[:, :r].float())
     assert rel(out.t() if tr else out, wantQ) < 1e-5
+
+
+def test_grouplasso_adamw_skips_groups_with_nonfinite_gradients(F):
+    """Overflow guard of the loss-scaled fp16 gradient stream: a group with an inf / NaN gradient keeps its parameters and moments and reports
+    n_g = NaN (engine_cl.StepResult raises FloatingPointError on it); the other groups step normally."""
+    torch.manual_seed(6)
+    G, n_per = 3, 4096
+    p = torch.randn(G * n_per, device="cuda") * 0.05
+    g = torch.randn_like(p) * 1e-3
+    g[n_per + 17] = float("inf")
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    offs = (torch.arange(G + 1, device="cuda", dtype=torch.int32) * n_per).contiguous()
+    norms = torch.empty(G, device="cuda")
+    p0 = p.clone()
+    F.check(F.lib().gsl_grouplasso_adamw_step(F.ptr(p), F.ptr(g), F.ptr(m), F.ptr(v), F.ptr(offs), G, p.numel(), 1e-2, 0.05, 0.9, 0.999, 1e-8, 1e-2, 1.0, 1,
+                                              F.ptr(norms), F.cur_stream()))
+    assert torch.isnan(norms[1]) and not torch.isnan(norms[0]) and not torch.isnan(norms[2])
+    assert torch.equal(p[n_per:2 * n_per], p0[n_per:2 * n_per]) and float(m[n_per:2 * n_per].abs().max()) == 0.0
+    assert not torch.equal(p[:n_per], p0[:n_per]) and not torch.equal(p[2 * n_per:], p0[2 * n_per:])
+    assert torch.isfinite(p).all()
