@@ -163,7 +163,8 @@ def run_gslora(args):
     host = [torch.rand(BATCH, 3, S, S, generator=g).pin_memory(), torch.randint(0, 100, (BATCH,), generator=g).pin_memory(),
             torch.rand(BATCH, 3, S, S, generator=g).pin_memory(), torch.randint(0, 100, (BATCH,), generator=g).pin_memory()]
     devt = [t.to(dev) for t in host]
-    step_kw = dict(beta=HP["beta"], alpha=HP["alpha"], BND=HP["BND"], hparams=dict(lr=HP["lr"], wd=HP["wd"]))
+    alpha = HP["alpha"] if args.alpha is None else args.alpha
+    step_kw = dict(beta=HP["beta"], alpha=alpha, BND=HP["BND"], hparams=dict(lr=HP["lr"], wd=HP["wd"]))
 
     # engine_cl.unlearn_step_async is what engine_cl.train_one_epoch calls: the step's scalars come back through a queued D2H copy into
     # pinned memory (every step, inside the timed region) and are read by the host one step later, so the launch queue never drains.
@@ -291,7 +292,7 @@ def run_gslora(args):
             "data": "synthetic",
             "config": {"workload": args.workload, "model": wl["model"],
                        "per_gpu_batch": f"{BATCH} remain + {BATCH} forget", "global_batch": images, "parallelism": f"dp{world}",
-                       "precision": args.precision,
+                       "precision": args.precision, "alpha": alpha,
                        "arithmetic": ("fp16 activations x (fp16 hi + fp16 lo) frozen weights and LoRA factors, fp32 accumulate / residual stream / loss: "
                                       "logits and every LoRA gradient within 1e-3 of FP32 (tests/test_engine_gpu.py)") if args.precision == "split" else
                                      "fp16 operands (one rounding per weight), fp32 accumulate / residual stream / loss: LoRA gradients 1-2.4e-3 of FP32",
@@ -492,6 +493,7 @@ def main():
     ap.add_argument("--no-u8-leg", action="store_true")
     ap.add_argument("--precision", default="split", choices=["split", "fast"],
                     help="split (default): fp16 hi+lo weights, gradients within the 1e-3 parity bar; fast: one fp16 rounding per weight")
+    ap.add_argument("--alpha", type=float, default=None, help="group-Lasso weight of the step (default 1e-4; BASELINE config 5 sweeps 0 / 1e-4 / 1e-3 / 1e-2)")
     ap.add_argument("--single-mode", action="store_true", help="skip the resident leg of the other precision mode")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the FP32-eager reference step on the GPU (north-star denominator)")
     ap.add_argument("--ref-batch", type=int, default=BATCH, help="--impl reference: images per stream of the CPU step (default: the headline 512)")
