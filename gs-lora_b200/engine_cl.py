@@ -69,14 +69,16 @@ def _dist():
     if not dist.is_initialized():
         if int(os.environ.get("WORLD_SIZE", "1")) <= 1 or "RANK" not in os.environ or os.environ.get("GSLORA_AUTO_DIST", "1") == "0":
             return None
+        backend = os.environ.get("GSLORA_DIST_BACKEND", "nccl" if torch.cuda.is_available() else "gloo")
         if torch.cuda.is_available():
             # one rank per GPU: without CUDA_VISIBLE_DEVICES=$LOCAL_RANK every rank would otherwise land on cuda:0
             local = int(os.environ.get("LOCAL_RANK", "0"))
             if torch.cuda.device_count() > 1:
                 torch.cuda.set_device(local % torch.cuda.device_count())
+        if backend == "nccl":
             dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
-        else:
-            dist.init_process_group("gloo")
+        else:       # gloo also moves CUDA tensors (through the host): lets several ranks share one GPU in tests
+            dist.init_process_group(backend)
     return dist if dist.get_world_size() > 1 else None
 
 
