@@ -375,3 +375,32 @@ def test_torchvision_family_matches_torchvision_fp32(shape):
     s_loss = engine_cl.get_structure_loss(mine, imagenet=True)
     want_s = sum(torch.sqrt(sum((ref.get_parameter(n) ** 2).sum() for n in names[4 * i:4 * i + 4])) for i in range(shape["layers"]))
     assert abs(float(s_loss) - float(want_s)) < 1e-4 * float(want_s)
+
+
+def test_engine_regrowth_keeps_the_fused_optimizer_state(golden_dir):
+    """A batch larger than the engine's capacity re-creates the engine mid-training (bigger workspace).  The fused AdamW moments and the
+    bias-correction step must move with it: two steps (batch 3, then batch 6 -> regrowth) must equal the same two steps on an engine that was
+    sized for 6 from the start.  Eval batches never trigger this (they run in chunks of the current capacity)."""
+    import engine_cl
+    g, cfg, sd = load_case(golden_dir, "tiny6_b4")
+    gen = torch.Generator().manual_seed(3)
+    S = cfg.image_size
+    mk = lambda n: (torch.rand(n, 3, S, S, generator=gen).cuda(), torch.randint(0, cfg.num_class, (n,), generator=gen).cuda())
+    b1, b2 = (mk(2), mk(1)), (mk(3), mk(3))
+    kw = dict(beta=0.15, alpha=1e-2, BND=105.0, hparams=dict(lr=1e-2, wd=0.05))
+    res = []
+    for presize in (False, True):
+        m = build_model(cfg, sd)
+        m.dropout_seed = lambda: 0
+        if presize:
+            m.ensure_engine(6)
+        for (xr, yr), (xf, yf) in (b1, b2):
+            engine_cl.unlearn_step(m, xr, yr, xf, yf, **kw)
+        if not presize:
+            assert m._engine.max_batch == 6 and m._engine.opt_step == 2          # grew from 3 to 6 between the steps, step count carried over
+        res.append(torch.cat([p.detach().flatten() for p in m.lora_parameters()]).clone())
+        with torch.no_grad():            # a 5x eval batch afterwards leaves the capacity alone
+            big = torch.rand(30, 3, S, S, generator=gen).cuda()
+            m.eval(); m(big, torch.zeros(30, dtype=torch.long).cuda()); m.train()
+        assert m._engine.max_batch <= 128
+    assert torch.equal(res[0], res[1])
