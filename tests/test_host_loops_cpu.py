@@ -391,3 +391,32 @@ def test_epoch_loops_shard_the_global_batch_by_rank(fake, monkeypatch, mod_name,
     assert [(c[2], c[3]) for c in fake.calls] == [(2, 1)] * 3                          # each step saw half of each global batch
     assert ret[0] == 3 and ret[3].count == 12 and ret[2].count == 6                    # meters: global sizes (3 steps x 4 remain / 2 forget)
     assert capsys.readouterr().out == ""                                               # rank 1 does not print
+
+
+def test_prototype_table_is_built_once_and_flags_missing_labels():
+    """engine_cl._cached_prototype_table: the driver's {label: CPU tensor} dict (util/utils.py:546-549) becomes ONE dense table per dict object
+    (no per-class copies per step); classes without a prototype are recorded so that a batch label without one can be reported (the reference's
+    dict lookup raises KeyError, engine_cl.py:585-590)."""
+    g = torch.Generator().manual_seed(1)
+    protos = {k: torch.randn(8, generator=g) for k in (0, 2, 5)}
+    holder = types.SimpleNamespace()
+    t1, present = engine_cl._cached_prototype_table(holder, protos, 6, 8, "cpu")
+    assert t1.shape == (6, 8) and present.tolist() == [True, False, True, False, False, True]
+    assert torch.equal(t1[2], protos[2]) and float(t1[1].abs().sum()) == 0.0
+    t2, _ = engine_cl._cached_prototype_table(holder, protos, 6, 8, "cpu")
+    assert t2 is t1                                                       # same dict object: cached
+    other = dict(protos)
+    t3, _ = engine_cl._cached_prototype_table(holder, other, 6, 8, "cpu")
+    assert t3 is not t1                                                   # a new dict (next task): rebuilt
+    with pytest.raises(KeyError):
+        engine_cl._prototype_tensor({7: torch.zeros(8)}, 6, 8, "cpu")     # prototype label outside [0, num_class)
+    with pytest.raises(KeyError):
+        engine_cl.get_prototype_loss(torch.randn(2, 8), torch.tensor([0, 1]), protos)     # label 1 has no prototype
+    r = StepResult(torch.tensor([2.0, 1, 3.0, 1, 0, 0, 0, 0, 1.0, 1.0]), _FakeEvent(), 10, dict(beta=0.1, alpha=0.0, BND=5.0, BND_pro=0.0, pwf=0.0, pwr=0.0,
+                                                                                            use_prototype=True))
+    with pytest.raises(KeyError):
+        r.wait()                                                          # the device-side "missing prototype" flag of the fused step
+    nan = StepResult(torch.tensor([2.0, 1, 3.0, 1, 0, 0, 0, 0, float("nan")]), _FakeEvent(), 9, dict(beta=0.1, alpha=0.0, BND=5.0, BND_pro=0.0, pwf=0.0,
+                                                                                                       pwr=0.0, use_prototype=False))
+    with pytest.raises(FloatingPointError):
+        nan.wait()                                                        # gsl_grouplasso_adamw_step skipped a group with a non-finite gradient
