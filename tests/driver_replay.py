@@ -17,13 +17,10 @@ from torch.utils.data import DataLoader, TensorDataset
 
 
 def reinitialize_lora_parameters(model):
-    """util/utils.py:428-441"""
-    with torch.no_grad():
-        for name, p in model.named_parameters():
-            if "lora_A" in name:
-                nn.init.kaiming_uniform_(p, a=math.sqrt(50))
-            elif "lora_B" in name:
-                nn.init.zeros_(p)
+    """util/utils.py:428-441, through the drop-in `util.utils` (the reference's own function when its tree is importable, the overlay's
+    restatement on the GPU box)"""
+    from util.utils import reinitialize_lora_parameters as f
+    return f(model)
 
 
 def timm_adamw(model, lr, weight_decay):
@@ -129,6 +126,8 @@ def replay(backbone, *, image_size, num_class, device, work_path, num_tasks=2, e
         with torch.no_grad():
             probe = BACKBONE(xte[:4].to(device), yte[:4].to(device))
         BACKBONE.train()
+        if task_i > 0:                                                                      # :1738-1741: old classes once more after the task
+            acc["old_after"] = engine_cl.eval_data(BACKBONE, mk(old_te, batch_size * 5, False), device, f"old-{task_i}", batch)
         out["tasks"].append(dict(acc=acc, steps=batch, total=float(lt.avg) if lt.count else None, norms=[float(n) for n in norm_list], ckpt=path,
                                  probe_logits=(probe[0] if isinstance(probe, tuple) else probe).detach().cpu(), opt_state_keys=len(OPTIMIZER.state)))
         log.append(("task_done", task_i, batch))
