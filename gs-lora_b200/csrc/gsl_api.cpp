@@ -124,6 +124,18 @@ int gsl_grouplasso_adamw_step(float* params, const float* grads, float* m, float
     a.group_norms = group_norms;
     return grouplasso_adamw_step(a, ST(stream));
 }
+int gsl_grouplasso_adamw_step_dev(float* params, const float* grads, float* m, float* v, const int32_t* group_offsets, int num_groups, int64_t n,
+                                  float wd, float beta1, float beta2, float eps, float alpha, float grad_scale, const void* state_dev,
+                                  float* group_norms, void* stream) {
+    if (state_dev == nullptr) { set_last_error("gsl_grouplasso_adamw_step_dev: state_dev is null"); return -1; }
+    OptimArgs a;
+    a.params = params; a.grads = grads; a.m = m; a.v = v; a.group_offsets = group_offsets; a.num_groups = num_groups; a.n = n;
+    a.lr = 0.f; a.wd = wd; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.alpha = alpha; a.grad_scale = grad_scale; a.step = 0;
+    a.state = (const StepState*)state_dev;
+    a.group_norms = group_norms;
+    return grouplasso_adamw_step(a, ST(stream));
+}
+void gsl_count_launches(long long n) { g_launches.fetch_add(n); }
 int gsl_tensor_norms(const float* params, const int32_t* tensor_offsets, int num_tensors, int type, float* out, void* stream) {
     return tensor_norms(params, tensor_offsets, num_tensors, type, out, ST(stream));
 }
@@ -149,6 +161,12 @@ int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* 
 int gsl_engine_forward_u8(void* handle, int slot, const uint8_t* img, int layout, const float* mean, const float* std, const int64_t* labels,
                           int B, int use_lora, uint64_t dropout_seed, void* stream) {
     return ((Engine*)handle)->forward(slot, img, 1 + (layout != 0), mean, std, labels, B, use_lora, dropout_seed, ST(stream));
+}
+int gsl_engine_forward_dev(void* handle, int slot, const void* img, int img_is_u8_layout, const int64_t* labels, int B, int use_lora, int dropout_on,
+                           const void* seed_dev, void* stream) {
+    // img_is_u8_layout: 0 = fp32 NCHW, 1 = uint8 NCHW, 2 = uint8 NHWC (no Normalize on this entry point)
+    return ((Engine*)handle)->forward(slot, img, img_is_u8_layout, nullptr, nullptr, labels, B, use_lora, dropout_on ? 1ull : 0ull, ST(stream),
+                                      (const unsigned long long*)seed_dev);
 }
 int gsl_engine_backward(void* handle, int slot, const float* dlogits, const float* demb, int accumulate, void* stream) {
     return ((Engine*)handle)->backward(slot, dlogits, demb, accumulate, ST(stream));

@@ -394,6 +394,28 @@ __device__ __host__ __forceinline__ uint32_t drop_bits(uint32_t pair, uint32_t s
     h ^= h >> 15;
     return h * 0x85EBCA77u;
 }
+// A per-site dropout seed as the kernels receive it: an immediate value (eager launches), or -- so that a captured CUDA graph can be replayed with a
+// fresh mask every step -- derived on the device from the step's 64-bit base seed in the step-state block (site key = block * 4 + site + 1, the
+// same derivation as gsl_engine.cu site_seed).
+struct DropSeed {
+    uint32_t value = 0;
+    const unsigned long long* dev = nullptr;
+    uint32_t key = 0;
+    DropSeed() = default;
+    DropSeed(uint32_t v) : value(v) {}
+};
+__device__ __forceinline__ uint32_t drop_seed_resolve(const DropSeed& s) {
+    if (s.dev == nullptr) return s.value;
+    const unsigned long long b = *s.dev;
+    return drop_hash(s.key, (uint32_t)b ^ (uint32_t)(b >> 32));
+}
+// Per-step scalars that change between replays of one captured step (written by the host into a 16-byte device block before each launch).
+struct StepState {
+    unsigned long long seed;    // base dropout seed of the step
+    int adam_step;              // 1-based AdamW step count (bias corrections)
+    float lr;
+};
+
 // scale factors (0 or 1/(1-p)) for elements e and e+1, e even
 __device__ __forceinline__ void drop_pair(uint32_t e, uint32_t seed, uint32_t thresh15, float keep_scale, float& s0, float& s1) {
     const uint32_t h = drop_bits(e >> 1, seed);

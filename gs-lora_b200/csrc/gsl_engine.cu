@@ -404,6 +404,12 @@ static inline uint32_t site_seed(uint64_t base, int block, int site) {
     return drop_hash((uint32_t)(block * 4 + site + 1), (uint32_t)base ^ (uint32_t)(base >> 32));
 }
 
+DropSeed Engine::site(uint64_t base, int block, int site_id) const {
+    DropSeed d(site_seed(base, block, site_id));
+    if (seed_dev_cur) { d.dev = seed_dev_cur; d.key = (uint32_t)(block * 4 + site_id + 1); }      // same derivation, evaluated on the device at run time
+    return d;
+}
+
 // x_out = FeedForward(LN2(x_mid)) + x_mid on M rows (dense tokens, or the compacted cls rows of the last block).  The LoRA branches
 // of both lora.Linear layers are inside the cached weights (ensure_ffn_weights), so this is LN -> GEMM(+GELU) -> GEMM(+residual).
 int Engine::ffn_forward(int l, int64_t M, __half* xn2, float* ln_mean, float* ln_rstd, const float* x_mid, __half* gp16, __half* g16, float* x_out,
@@ -417,21 +423,21 @@ int Engine::ffn_forward(int l, int64_t M, __half* xn2, float* ln_mean, float* ln
         GemmArgs g;
         g.A = xn2; g.lda = D; g.B = c.fc1_w16.hi; g.B_lo = c.fc1_w16.lo; g.ldb = D; g.M = M; g.N = H; g.K = D;
         g.epi = EPI_GELU; g.bias = f.fc1_b; g.out0 = gp16; g.ld0 = H; g.out1 = g16; g.ld1 = H;
-        g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 2);
+        g.drop_p = pdrop; g.drop_seed = site(dseed, l, 2);
         if ((rc = gemm_f16(g, s))) return rc;
     }
     {
         GemmArgs g;
         g.A = g16; g.lda = H; g.B = c.fc2_w16.hi; g.B_lo = c.fc2_w16.lo; g.ldb = H; g.M = M; g.N = D; g.K = H;
         g.epi = EPI_RES_F32; g.bias = f.fc2_b; g.out0 = x_out; g.ld0 = D; g.aux = x_mid; g.ldaux = D;
-        g.drop_p = pdrop; g.drop_seed = site_seed(dseed, l, 3);
+        g.drop_p = pdrop; g.drop_seed = site(dseed, l, 3);
         if ((rc = gemm_f16(g, s))) return rc;
     }
     return 0;
 }
 
 int Engine::forward(int slot, const void* img, int img_kind, const float* mean, const float* std, const int64_t* labels, int B, int use_lora,
-                    uint64_t dropout_seed, cudaStream_t s) {
+                    uint64_t dropout_seed, cudaStream_t s, const unsigned long long* seed_dev) {
     GSL_REQUIRE(img_kind >= 0 && img_kind <= 2, "image kind %d (0 fp32 NCHW, 1 uint8 NCHW, 2 uint8 NHWC)", img_kind);
     GSL_REQUIRE(params_bound, "bind_params first");
     GSL_REQUIRE(slot >= 0 && slot < cfg.num_slots, "slot %d out of range", slot);
@@ -439,7 +445,8 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
     const int D = cfg.dim, L = cfg.depth, inner = cfg.heads * 64;
     const int64_t M = (int64_t)B * tokens;
     Slot& S = slots[slot];
-    S.batch = B; S.used_lora = use_lora; S.drop_seed = dropout_seed;
+    S.batch = B; S.used_lora = use_lora; S.drop_seed = dropout_seed; S.seed_dev = dropout_seed ? seed_dev : nullptr;
+    seed_dev_cur = S.seed_dev;
     const float pdrop = dropout_seed ? cfg.dropout : 0.f, pemb = dropout_seed ? cfg.emb_dropout : 0.f;
     int rc;
     if ((rc = ensure_ffn_weights(use_lora, s))) return rc;
@@ -451,7 +458,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
         GemmArgs g;
         g.A = patches16; g.lda = patch_dim; g.B = patch_w16.hi; g.B_lo = patch_w16.lo; g.ldb = patch_dim; g.M = M; g.N = D; g.K = patch_dim;
         g.epi = EPI_PERIODIC_F32; g.out0 = S.x[0]; g.ld0 = D; g.aux = posb; g.ldaux = D; g.aux_period = tokens;
-        g.drop_p = pemb; g.drop_seed = site_seed(dropout_seed, L, 0);
+        g.drop_p = pemb; g.drop_seed = site(dropout_seed, L, 0);
         if ((rc = gemm_f16(g, s))) return rc;
     }
     for (int l = 0; l < L; ++l) {
@@ -475,7 +482,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
             GemmArgs g;
             g.A = a.o16; g.lda = inner; g.B = c.out_w16.hi; g.B_lo = c.out_w16.lo; g.ldb = inner; g.M = M; g.N = D; g.K = inner;
             g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = x_mid; g.ld0 = D; g.aux = x_in; g.ldaux = D;
-            g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 1);
+            g.drop_p = pdrop; g.drop_seed = site(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
             // ---- x = FeedForward(LN(x)) + x, loralib.Linear on both projections
             if ((rc = ffn_forward(l, M, a.xn2_16, a.ln2_mean, a.ln2_rstd, x_mid, a.gp16, a.g16, x_out, pdrop, dropout_seed, s))) return rc;
@@ -488,7 +495,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
             GemmArgs g;
             g.A = k.o16; g.lda = inner; g.B = c.out_w16.hi; g.B_lo = c.out_w16.lo; g.ldb = inner; g.M = B; g.N = D; g.K = inner;
             g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = k.xmid32; g.ld0 = D; g.aux = k.xin32; g.ldaux = D;
-            g.drop_p = pdrop; g.drop_seed = site_seed(dropout_seed, l, 1);
+            g.drop_p = pdrop; g.drop_seed = site(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
             if ((rc = ffn_forward(l, B, k.xn2_16, k.ln2_mean, k.ln2_rstd, k.xmid32, k.gp16, k.g16, k.xout32, pdrop, dropout_seed, s))) return rc;
         }
@@ -542,7 +549,7 @@ int Engine::ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, fl
         g.epi = dxn_fp32() ? EPI_F32 : EPI_F16; g.out0 = dxn; g.ld0 = D;            // fp16: halves the traffic of the LayerNorm-backward pass that consumes it
         if ((rc = gemm_f16(g, s))) return rc;
     }
-    return layernorm_bwd(dxn, dxn_fp32() ? 0 : 1, D, x_mid, D, ln_mean, ln_rstd, f.ln2_w, dx, D, dx, D, dy, D, M, D, pdrop, site_seed(dseed, l, 1), s);
+    return layernorm_bwd(dxn, dxn_fp32() ? 0 : 1, D, x_mid, D, ln_mean, ln_rstd, f.ln2_w, dx, D, dx, D, dy, D, M, D, pdrop, site(dseed, l, 1), s);
 }
 
 // LoRA on to_qkv (loralib.MergedLinear, one (A_g, B_g) pair per slice g = q, k, v; vit_face.py:349-355): with dQKV [M, 3 inner] from the attention
@@ -576,6 +583,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
     const int B = S.batch, D = cfg.dim, L = cfg.depth, inner = cfg.heads * 64;
     const int64_t M = (int64_t)B * tokens;
     const uint64_t dseed = S.drop_seed;
+    seed_dev_cur = S.seed_dev;
     const float pdrop = dseed ? cfg.dropout : 0.f;
     const bool attn_lora = cfg.lora_pos == 1;
     int rc;
@@ -585,7 +593,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
     hb.head_type = cfg.head_type;
     hb.gamma = head_ln_w; hb.cos_s = cfg.cos_s; hb.B = B; hb.D = D; hb.C = cfg.num_class; hb.tokens = 1; hb.gscale = cfg.grad_scale;
     hb.dx = cls_dx32; hb.lddx = D; hb.dx16 = cls_dy16; hb.lddx16 = D;
-    hb.drop_p = pdrop; hb.drop_seed = site_seed(dseed, L - 1, 3);
+    hb.drop_p = pdrop; hb.drop_seed = site(dseed, L - 1, 3);
     if ((rc = head_bwd(hb, s))) return rc;
     {   // ---------------- last block on the compacted cls rows
         const int l = L - 1;
@@ -613,7 +621,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         }
         // residual gradient of this block's input: zero except the cls rows, which LayerNorm backward picks from the compacted cls_dx32
         if ((rc = layernorm_bwd(dxn32, dxn_fp32() ? 0 : 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, cls_dx32, D, dx32, D, dy16, D, M, D, pdrop,
-                                site_seed(dseed, l - 1, 3), s, tokens))) return rc;
+                                site(dseed, l - 1, 3), s, tokens))) return rc;
     }
     for (int l = L - 2; l >= 0; --l) {
         const BlockFrozen& f = frozen[l];
@@ -640,7 +648,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
             if ((rc = gemm_f16(g, s))) return rc;
         }
         if ((rc = layernorm_bwd(dxn32, dxn_fp32() ? 0 : 1, D, S.x[2 * l], D, a.ln1_mean, a.ln1_rstd, f.ln1_w, dx32, D, dx32, D, dy16, D, M, D, pdrop,
-                                site_seed(dseed, l - 1, 3), s))) return rc;
+                                site(dseed, l - 1, 3), s))) return rc;
     }
     return 0;
 }

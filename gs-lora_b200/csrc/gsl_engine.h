@@ -56,7 +56,8 @@ struct Slot {
     int* correct;
     int batch = 0;
     int used_lora = 0;
-    uint64_t drop_seed = 0;
+    uint64_t drop_seed = 0;         // base seed of the forward's dropout masks (0 = no dropout); with seed_dev set only its non-zero-ness matters
+    const unsigned long long* seed_dev = nullptr;   // graph replay: the base seed lives in the device step state and is read by the kernels
 };
 
 class Engine {
@@ -92,7 +93,7 @@ public:
     int refresh_lora(cudaStream_t s);
     // img_kind 0: fp32 NCHW (ToTensor output); 1 / 2: uint8 NCHW / NHWC with /255 and optional Normalize(mean, std) (host pointers) in flight
     int forward(int slot, const void* img, int img_kind, const float* mean, const float* std, const int64_t* labels, int B, int use_lora,
-                uint64_t dropout_seed, cudaStream_t s);
+                uint64_t dropout_seed, cudaStream_t s, const unsigned long long* seed_dev = nullptr);
     int backward(int slot, const float* dlogits, const float* demb, int accumulate, cudaStream_t s);
     int64_t lora_block_elems() const;
     int64_t lora_offset(int block, int which) const;   // which: 0 A1, 1 B1, 2 A2, 3 B2  (lora_pos 1: 0 A_qkv, 1 B_qkv)
@@ -102,6 +103,8 @@ private:
     int ensure_ffn_weights(int use_lora, cudaStream_t s);
     int ffn_forward(int l, int64_t M, __half* xn2, float* ln_mean, float* ln_rstd, const float* x_mid, __half* gp16, __half* g16, float* x_out,
                     float pdrop, uint64_t dseed, cudaStream_t s);
+    DropSeed site(uint64_t base, int block, int site_id) const;     // immediate per-site seed, or its device-derived form while seed_dev_cur is set
+    const unsigned long long* seed_dev_cur = nullptr;
     int attn_lora_grads(int l, int64_t M, const __half* dqkv, const __half* xn1, int accumulate, cudaStream_t s);
     int ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, float* dxn, const __half* xn2, const __half* gp16, const __half* g16,
                      const float* x_mid, const float* ln_mean, const float* ln_rstd, int accumulate, float pdrop, uint64_t dseed, cudaStream_t s);

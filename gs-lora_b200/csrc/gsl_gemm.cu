@@ -44,7 +44,7 @@ struct GemmParams {
     int period, ld_table;
     int has_out1;         // EPI_F32: also emit an fp16 copy through tmO1
     uint32_t drop_thresh; // round(p * 32768) (0 = no dropout)
-    uint32_t drop_seed;
+    DropSeed drop_seed;
     float drop_scale;     // 1 / (1 - p)
     GeluConsts gelu;      // EPI_GELU: constants of gelu_pair, scaled by the keep scale
 };
@@ -248,6 +248,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t gbase = sEpi + grp * (Cfg::O0_BUF + Cfg::O1_BUF + Cfg::AUX_DEPTH * Cfg::AUX_BUF);
         const uint32_t o0_buf = gbase, aux_base = gbase + Cfg::O0_BUF, o1_buf = gbase + Cfg::O0_BUF + Cfg::AUX_DEPTH * Cfg::AUX_BUF;
         const bool write_o1 = (EPI == EPI_GELU) || (EPI == EPI_F32 && p.has_out1);
+        const uint32_t dseed = p.drop_thresh ? drop_seed_resolve(p.drop_seed) : 0u;
 
         int iter = 0;
         uint32_t aux_it = 0;     // aux stripes consumed by this group so far: slot = aux_it % AUX_DEPTH, parity = (aux_it / AUX_DEPTH) & 1
@@ -313,8 +314,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(aux_buf + sw128_off(row, half * 4 + j)));
                         if (p.drop_thresh) {
-                            v[2 * j] = fma2(v[2 * j], drop_pair2(e0 + 4 * j, p.drop_seed, p.drop_thresh, p.drop_scale), make_float2(r.x, r.y));
-                            v[2 * j + 1] = fma2(v[2 * j + 1], drop_pair2(e0 + 4 * j + 2, p.drop_seed, p.drop_thresh, p.drop_scale), make_float2(r.z, r.w));
+                            v[2 * j] = fma2(v[2 * j], drop_pair2(e0 + 4 * j, dseed, p.drop_thresh, p.drop_scale), make_float2(r.x, r.y));
+                            v[2 * j + 1] = fma2(v[2 * j + 1], drop_pair2(e0 + 4 * j + 2, dseed, p.drop_thresh, p.drop_scale), make_float2(r.z, r.w));
                         } else {
                             v[2 * j] = add2(v[2 * j], make_float2(r.x, r.y));
                             v[2 * j + 1] = add2(v[2 * j + 1], make_float2(r.z, r.w));
@@ -351,7 +352,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     if (p.drop_thresh) {                            // emb_dropout after the pos-embedding add
 #pragma unroll
-                        for (int j = 0; j < CW; j += 2) v[j / 2] = mul2(v[j / 2], drop_pair2(e0 + j, p.drop_seed, p.drop_thresh, p.drop_scale));
+                        for (int j = 0; j < CW; j += 2) v[j / 2] = mul2(v[j / 2], drop_pair2(e0 + j, dseed, p.drop_thresh, p.drop_scale));
                     }
                 }
                 uint32_t pk0[CW / 2], pk1[CW / 2];      // packed half2 outputs (fp16 epilogues)
@@ -370,7 +371,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint32_t thr2 = p.drop_thresh | (p.drop_thresh << 16);
 #pragma unroll
                         for (int j = 0; j < CW / 2; ++j) {
-                            const uint32_t keep = drop_keep_mask2(e0 + 2 * j, p.drop_seed, thr2);
+                            const uint32_t keep = drop_keep_mask2(e0 + 2 * j, dseed, thr2);
                             pk0[j] &= keep;
                             pk1[j] &= keep;
                         }

@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_bwd_kernel(HeadBwdArgs a) {
     const float mg = block_sum(s1, red) / D;
     const float mgx = block_sum(s2, red) / D;
     const float rstd = a.rstd[b];
+    const uint32_t dseed = a.drop_p > 0.f ? drop_seed_resolve(a.drop_seed) : 0u;
     for (int d = tid; d < D; d += HEAD_THREADS) {
         const float v = a.gscale * rstd * (s_de[d] - mg - a.xhat[(int64_t)b * D + d] * mgx);
         if (a.dx) a.dx[(int64_t)b * a.tokens * a.lddx + d] = v;
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_bwd_kernel(HeadBwdArgs a) {
             float m = 1.0f;
             if (a.drop_p > 0.f) {
                 const uint32_t e = (uint32_t)(b * a.tokens) * (uint32_t)D + (uint32_t)d;
-                const uint32_t h = drop_bits(e >> 1, a.drop_seed);
+                const uint32_t h = drop_bits(e >> 1, dseed);
                 const uint32_t bits = ((e & 1u) ? (h >> 16) : h) & 0x7FFFu;
                 m = bits >= drop_thresh15(a.drop_p) ? 1.0f / (1.0f - a.drop_p) : 0.f;
             }

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gsl_common.cuh"
+
 namespace gsl {
 
 enum GemmEpi {
@@ -30,7 +32,7 @@ struct GemmArgs {
     int cta_group = 0;   // 0 = library default, 1 or 2
     int block_n = 0;     // 0 = auto, 128 or 256
     float drop_p = 0.f;  // dropout on the produced value (before the residual add; on both outputs of EPI_GELU)
-    uint32_t drop_seed = 0;
+    DropSeed drop_seed;  // immediate seed, or (dev, key): derived on the device from the step state (graph replay)
 };
 int gemm_f16(const GemmArgs& a, cudaStream_t stream);
 void gemm_set_default_cta_group(int cg);
@@ -50,7 +52,7 @@ int layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* 
 // dx = dres + LNbwd(dy) ; writes fp32 dx and an fp16 copy (GEMM operand for the next dX GEMM)
 int layernorm_bwd(const void* dy, int dy_is_fp16, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                   const float* gamma, const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16,
-                  int64_t M, int D, float drop_p, uint32_t drop_seed, cudaStream_t s,    // dropout mask applies to the fp16 copy only
+                  int64_t M, int D, float drop_p, DropSeed drop_seed, cudaStream_t s,    // dropout mask applies to the fp16 copy only
                   int dres_period = 0);   // > 0: dres holds one compacted row per `dres_period` rows (added at rows r % period == 0, zero elsewhere)
 // T[M, 0:16] = X[M, K] * A16[16, K]^T  (fp16 in, fp32 accumulate, fp16 out at out[:, 0:16], row pitch ldo)
 // fold != 0: A16 has 32 rows, [0, 16) = fp16(A) and [16, 32) = fp16(A - fp16(A)); both halves feed the same accumulator (split-precision LoRA factor)
@@ -115,7 +117,7 @@ struct HeadBwdArgs {
     int head_type = 0;
     float gscale;
     float* dx; int64_t lddx; __half* dx16; int64_t lddx16;
-    float drop_p = 0.f; uint32_t drop_seed = 0;      // mask of the last block's fc2-output dropout, applied to dx16 only
+    float drop_p = 0.f; DropSeed drop_seed;          // mask of the last block's fc2-output dropout, applied to dx16 only
 };
 int head_bwd(const HeadBwdArgs& a, cudaStream_t s);
 // dlogits[b, :] = coef * (softmax(logits[b]) - onehot) / B_total ; coef read from device (gate applied by caller)
@@ -139,6 +141,7 @@ struct OptimArgs {
     int num_groups; int64_t n;
     float lr, wd, beta1, beta2, eps, alpha, grad_scale;      // grad_scale multiplies grads (1 / loss scale / world)
     int step;                                                // 1-based
+    const StepState* state = nullptr;                        // when set, `step` and `lr` are read from this device block at run time (graph replay)
     float* group_norms;         // device [G] : sqrt(sum p^2) per group, pre-update (structure loss terms)
 };
 int grouplasso_adamw_step(const OptimArgs& a, cudaStream_t s);

@@ -16,6 +16,12 @@ namespace gsl {
 
 __global__ void __launch_bounds__(1024) grouplasso_adamw_kernel(OptimArgs a, float bc1, float bc2_sqrt) {
     pdl_prologue();
+    if (a.state != nullptr) {       // graph replay: the step count and the learning rate of THIS replay come from the device step state
+        const int t = a.state->adam_step;
+        a.lr = a.state->lr;
+        bc1 = (float)(1.0 - pow((double)a.beta1, (double)t));
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, (double)t));
+    }
     __shared__ float red[32];
     __shared__ float s_norm;
     const int gidx = blockIdx.x;
@@ -58,9 +64,10 @@ __global__ void __launch_bounds__(1024) grouplasso_adamw_kernel(OptimArgs a, flo
 }
 
 int grouplasso_adamw_step(const OptimArgs& a, cudaStream_t s) {
-    GSL_REQUIRE(a.num_groups > 0 && a.step >= 1, "optimizer: bad arguments (groups=%d step=%d)", a.num_groups, a.step);
-    const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step);
-    const double bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
+    GSL_REQUIRE(a.num_groups > 0 && (a.step >= 1 || a.state != nullptr), "optimizer: bad arguments (groups=%d step=%d)", a.num_groups, a.step);
+    const int hstep = a.step >= 1 ? a.step : 1;
+    const double bc1 = 1.0 - pow((double)a.beta1, (double)hstep);
+    const double bc2 = 1.0 - pow((double)a.beta2, (double)hstep);
     GSL_CHECK_CUDA(launch_pdl(grouplasso_adamw_kernel, dim3(a.num_groups), dim3(1024), 0, s, a, (float)bc1, (float)sqrt(bc2)));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());

@@ -164,8 +164,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                             const float* __restrict__ gamma, const float* __restrict__ dres, int64_t lddres,
                                                             float* __restrict__ dx, int64_t lddx, __half* __restrict__ dx16, int64_t lddx16,
-                                                            int64_t M, uint32_t drop_thresh, uint32_t drop_seed, float drop_scale, int dres_period) {
+                                                            int64_t M, uint32_t drop_thresh, DropSeed drop_seed_in, float drop_scale, int dres_period) {
     pdl_prologue();
+    const uint32_t drop_seed = drop_thresh ? drop_seed_resolve(drop_seed_in) : 0u;
     constexpr int D = VEC * 128;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
 
 int layernorm_bwd(const void* dy, int dy_is_fp16, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* dres, int64_t lddres, float* dx, int64_t lddx, __half* dx16, int64_t lddx16, int64_t M, int D,
-                  float drop_p, uint32_t drop_seed, cudaStream_t s, int dres_period) {
+                  float drop_p, DropSeed drop_seed, cudaStream_t s, int dres_period) {
     const uint32_t dth = drop_thresh15(drop_p);
     const float dsc = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     GSL_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm_bwd: D=%d must be a multiple of 128 and <= 1024", D);

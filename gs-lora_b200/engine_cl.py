@@ -243,6 +243,94 @@ class _PinnedRing:
 
 _RING = None
 
+class _GraphedStep:
+    """One unlearning step (forward, loss sums, CE gradient, selective backward, fused group-lasso AdamW, LoRA repack) captured as a CUDA graph for
+    a fixed (engine, batch split, input dtype, beta / alpha / BND, AdamW constants, grouping, dropout on / off) key and replayed with ONE launch:
+    the ~150 kernel launches of a step otherwise leave ~1 ms of gaps between kernels (profiles/r02h_gaps.log).  What changes from replay to replay
+    -- the dropout base seed, the AdamW step count and the learning rate -- lives in a 16-byte device "step state" the kernels read
+    (include/gslora.h gsl_engine_forward_dev / gsl_grouplasso_adamw_step_dev); inputs are copied into the graph's static buffers (the copy that
+    torch.cat made before).  Single-process steps without the prototype term only; everything else takes the eager path."""
+
+    def __init__(self, m, eng, xr, xf, Br, Bf, beta, alpha, BND, hp, group_type, dropout_on):
+        import struct
+        self._struct = struct
+        dev = xr.device
+        B = Br + Bf
+        self.eng, self.Br, self.B, self.dropout_on = eng, Br, B, dropout_on
+        self.img = torch.empty((B,) + tuple(xr.shape[1:]), dtype=xr.dtype if xr.dtype == torch.uint8 else torch.float32, device=dev)
+        self.lab = torch.empty(B, dtype=torch.int64, device=dev)
+        self.dlogits = torch.empty(B, eng.spec.num_class, dtype=torch.float32, device=dev)
+        self.state_dev = torch.zeros(16, dtype=torch.uint8, device=dev)
+        self.state_host = [torch.zeros(16, dtype=torch.uint8).pin_memory() for _ in range(8)]
+        self.state_i = 0
+        self.packed = torch.zeros(9, dtype=torch.float32, device=dev)
+        self.slot = 0
+        kw = m.image_kwargs(self.img)
+        if kw.get("pixel_norm") is not None:
+            raise RuntimeError("graph capture: Normalize-in-kernel inputs take the eager path")
+        L = F.lib()
+        step0 = eng.opt_step
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.gsl_launch_count()
+        with torch.cuda.graph(self.graph):
+            eng.forward(self.img, self.lab, self.slot, use_lora=True, dropout_seed=1 if dropout_on else 0, seed_dev=self.state_dev,
+                        channels_last=kw.get("channels_last", False))
+            sums = eng.loss_sums(self.slot, Br, B, None)
+            eng.unlearn_ce_grad(self.slot, self.lab, Br, B, beta, BND, self.dlogits)
+            eng.backward(self.slot, self.dlogits, None, accumulate=False)
+            eng.optimizer_step(lr=0.0, wd=hp["wd"], alpha=alpha, betas=hp.get("betas", (0.9, 0.999)), eps=hp.get("eps", 1e-8), group_type=group_type,
+                               state_dev=self.state_dev)
+            self.packed.copy_(torch.cat([sums, eng.group_norms[:eng.num_groups].sum().view(1)]))
+        self.launches = int(L.gsl_launch_count() - n0)
+        eng.opt_step = step0                      # capturing executed nothing on the device
+
+    def run(self, m, xr, yr, xf, yf, seed, lr):
+        Br = self.Br
+        self.img[:Br].copy_(xr, non_blocking=True)
+        self.img[Br:].copy_(xf, non_blocking=True)
+        self.lab[:Br].copy_(yr, non_blocking=True)
+        self.lab[Br:].copy_(yf, non_blocking=True)
+        eng = self.eng
+        eng.opt_step += 1
+        host = self.state_host[self.state_i]
+        self.state_i = (self.state_i + 1) % len(self.state_host)
+        host.copy_(torch.frombuffer(bytearray(self._struct.pack("<QIf", seed & 0xFFFFFFFFFFFFFFFF, eng.opt_step, float(lr))), dtype=torch.uint8))
+        self.state_dev.copy_(host, non_blocking=True)
+        m._slot_stamp[self.slot] += 1             # the graph's slot now holds THIS step's activations
+        self.graph.replay()
+        F.lib().gsl_count_launches(self.launches)
+        return self.packed
+
+
+_GRAPH_AFTER = 2        # eager steps with an unchanged key before the step is captured
+
+
+def _graph_step(m, eng, xr, yr, xf, yf, beta, alpha, BND, hp, group_type, seed):
+    """The captured step for this call's key (or None: not yet / not eligible)."""
+    if os.environ.get("GSLORA_CUDA_GRAPH", "1") == "0":
+        return None
+    key = (id(eng), tuple(xr.shape), tuple(xf.shape), xr.dtype, xf.dtype, float(beta), float(alpha), float(BND), float(hp["wd"]),
+           tuple(hp.get("betas", (0.9, 0.999))), float(hp.get("eps", 1e-8)), group_type, seed != 0, m.input_pixel_norm is None)
+    st = m.__dict__.setdefault("_gsl_graph", dict(key=None, seen=0, step=None, failed=False))
+    if st["key"] != key:
+        st.update(key=key, seen=0, step=None)
+    if st["failed"] or m.input_pixel_norm is not None and xr.dtype == torch.uint8:
+        return None
+    if st["step"] is None:
+        st["seen"] += 1
+        if st["seen"] <= _GRAPH_AFTER:
+            return None
+        try:
+            st["step"] = _GraphedStep(m, eng, xr, xf, int(xr.shape[0]), int(xf.shape[0]), beta, alpha, BND, hp, group_type, seed != 0)
+        except Exception as e:     # capture is an optimisation: fall back to eager launches, loudly, once
+            st["failed"] = True
+            import warnings
+            warnings.warn(f"gslora-b200: CUDA-graph capture of the unlearning step failed ({e!r}); continuing with eager launches")
+            return None
+    return st["step"]
+
+
 
 def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, labels_forget, *, beta: float, alpha: float, BND: float,
                        optimizer=None, hparams: Optional[dict] = None, use_prototype: bool = False, prototype_dict=None,
@@ -262,6 +350,16 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
     if m._merged():
         raise RuntimeError("unlearn_step needs model.train() (un-merged LoRA)")
     missing = None
+    hp = hparams if hparams is not None else _adamw_hparams(optimizer, m.lora_parameters())
+    seed = m.dropout_seed() if dropout_seed is None else int(dropout_seed)
+    graphed = None
+    if B > 0 and Br > 0 and Bf > 0 and dist is None and not use_prototype and inputs_remain.dtype == inputs_forget.dtype:
+        graphed = _graph_step(m, eng, inputs_remain, labels_remain, inputs_forget, labels_forget, beta, alpha, BND, hp, group_type, seed)
+    if graphed is not None:
+        packed = graphed.run(m, inputs_remain, labels_remain, inputs_forget, labels_forget, seed, hp["lr"])
+        m.mark_lora_updated_by_engine()
+        return _queue_readback(packed, dict(beta=beta, alpha=alpha, BND=BND, BND_pro=BND_pro, pwf=prototype_weight_forget,
+                                            pwr=prototype_weight_remain, use_prototype=use_prototype))
     if B > 0:
         if inputs_remain.dtype == torch.uint8 or inputs_forget.dtype == torch.uint8:     # raw pixels: ToTensor [+ Normalize] runs in the patchify kernel
             if inputs_remain.dtype != inputs_forget.dtype:
@@ -271,7 +369,7 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
             img = torch.cat([inputs_remain.float(), inputs_forget.float()], dim=0).contiguous()
         lab = torch.cat([labels_remain.to(torch.int64), labels_forget.to(torch.int64)], dim=0).contiguous()
         slot = m._take_slot()
-        eng.forward(img, lab, slot, use_lora=True, dropout_seed=m.dropout_seed() if dropout_seed is None else dropout_seed, **m.image_kwargs(img))
+        eng.forward(img, lab, slot, use_lora=True, dropout_seed=seed, **m.image_kwargs(img))
         table = kl = None
         if use_prototype:                                       # GS-LoRA++ (engine_cl.py:97-101): per-sample KL to the class prototype, on device
             table, present = _cached_prototype_table(m, prototype_dict, eng.spec.num_class, eng.spec.dim, dev)
@@ -295,20 +393,25 @@ def unlearn_step_async(model, inputs_remain, labels_remain, inputs_forget, label
         eng.grad_flat.zero_()
     if dist is not None:
         dist.all_reduce(eng.grad_flat)                          # the one flat LoRA-gradient allreduce (0.98 MB for ViT-P8S8 r=8)
-    hp = hparams if hparams is not None else _adamw_hparams(optimizer, m.lora_parameters())
     eng.optimizer_step(lr=hp["lr"], wd=hp["wd"], alpha=alpha, betas=hp.get("betas", (0.9, 0.999)), eps=hp.get("eps", 1e-8),
                        group_type=group_type)                   # cfg["GROUP_TYPE"] of engine.py:82-90
     m.mark_lora_updated_by_engine()
     # one D2H copy (queued, pinned) for everything the reference reads with .item()
     packed = torch.cat([sums, eng.group_norms[:eng.num_groups].sum().view(1)] + ([missing] if missing is not None else []))
+    return _queue_readback(packed, dict(beta=beta, alpha=alpha, BND=BND, BND_pro=BND_pro, pwf=prototype_weight_forget,
+                                        pwr=prototype_weight_remain, use_prototype=use_prototype))
+
+
+def _queue_readback(packed, consts) -> StepResult:
+    """one D2H copy (queued, pinned) for everything the reference reads with .item()"""
+    global _RING
     if _RING is None:
         _RING = _PinnedRing()
     slot_i, pinned = _RING.take()
     pinned[:packed.numel()].copy_(packed, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
-    res = StepResult(pinned, ev, packed.numel(), dict(beta=beta, alpha=alpha, BND=BND, BND_pro=BND_pro, pwf=prototype_weight_forget,
-                                                      pwr=prototype_weight_remain, use_prototype=use_prototype))
+    res = StepResult(pinned, ev, packed.numel(), consts)
     _RING.pending[slot_i] = res
     return res
 

@@ -87,6 +87,8 @@ def _declare(L):
         "gsl_engine_refresh_lora": [P, P],
         "gsl_engine_forward": [P, c_int, P, P, c_int, c_int, ctypes.c_uint64, P],
         "gsl_engine_backward": [P, c_int, P, P, c_int, P],
+        "gsl_engine_forward_dev": [P, c_int, P, c_int, P, c_int, c_int, c_int, P, P],
+        "gsl_grouplasso_adamw_step_dev": [P, P, P, P, P, c_int, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P],
         "gsl_loss_sums": [P, P, P, c_int, c_int, P, P],
         "gsl_prototype_kl_fwd": [P, P, P, c_int, c_int, P, P],
         "gsl_prototype_kl_grad": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_float, P, P],
@@ -110,6 +112,8 @@ def _declare(L):
     L.gsl_engine_lora_offset.restype = c_int64
     L.gsl_engine_lora_numel.argtypes = [P]
     L.gsl_engine_lora_numel.restype = c_int64
+    L.gsl_count_launches.argtypes = [ctypes.c_longlong]
+    L.gsl_count_launches.restype = None
 
 
 EXPORTS = ["gsl_last_error", "gsl_version", "gsl_launch_count", "gsl_set_gemm_cta_group", "gsl_gemm_f16", "gsl_patchify_f16", "gsl_layernorm_fwd",
@@ -118,7 +122,8 @@ EXPORTS = ["gsl_last_error", "gsl_version", "gsl_launch_count", "gsl_set_gemm_ct
            "gsl_engine_destroy", "gsl_engine_bind_params", "gsl_engine_refresh_frozen", "gsl_engine_refresh_lora", "gsl_engine_forward",
            "gsl_engine_backward", "gsl_engine_slot_ptr", "gsl_engine_lora_offset", "gsl_engine_lora_numel", "gsl_loss_sums",
            "gsl_unlearn_ce_grad", "gsl_prototype_kl_fwd", "gsl_prototype_kl_grad", "gsl_patchify_u8_f16", "gsl_engine_forward_u8",
-           "gsl_class_sums", "gsl_class_means", "gsl_gemm_f16_split", "gsl_lora_down_split", "gsl_lora_side_split", "gsl_cast_f32_to_f16_split"]
+           "gsl_class_sums", "gsl_class_means", "gsl_gemm_f16_split", "gsl_lora_down_split", "gsl_lora_side_split", "gsl_cast_f32_to_f16_split",
+           "gsl_engine_forward_dev", "gsl_grouplasso_adamw_step_dev", "gsl_count_launches"]
 
 
 def host_floats(values):

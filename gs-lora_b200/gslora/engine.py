@@ -168,13 +168,20 @@ class VitEngine:
         raise ValueError(what)
 
     def forward(self, img: torch.Tensor, labels: Optional[torch.Tensor], slot: int = 0, use_lora: bool = True, dropout_seed: int = 0,
-                pixel_norm=None, channels_last: bool = False):
+                pixel_norm=None, channels_last: bool = False, seed_dev: Optional[torch.Tensor] = None):
         """fp32 NCHW images (the reference loader's ToTensor output), or raw uint8 pixels ([B,C,S,S], or [B,S,S,C] with channels_last):
         ToTensor's /255 and the optional Normalize `pixel_norm = (mean, std)` are then applied inside the patchify kernel."""
         assert img.is_cuda and img.is_contiguous() and img.dtype in (torch.float32, torch.uint8)
         B = img.shape[0]
         if labels is not None:
             assert labels.is_cuda and labels.dtype == torch.int64 and labels.is_contiguous()
+        if seed_dev is not None:
+            # CUDA-graph form: the dropout base seed is read on the device from the step-state block (gsl_engine_forward_dev)
+            assert pixel_norm is None, "the graph-capturable forward takes ToTensor output or raw pixels without Normalize"
+            kind = 0 if img.dtype != torch.uint8 else (2 if channels_last else 1)
+            F.check(F.lib().gsl_engine_forward_dev(self.handle, slot, F.ptr(img), kind, F.ptr(labels), B, 1 if use_lora else 0,
+                                                   1 if dropout_seed else 0, F.ptr(seed_dev), F.cur_stream()), "gsl_engine_forward_dev")
+            return B
         if img.dtype == torch.uint8:
             s = self.spec
             want = (B, s.image_size, s.image_size, s.channels) if channels_last else (B, s.channels, s.image_size, s.image_size)
@@ -229,12 +236,20 @@ class VitEngine:
                                             float(beta), float(BND), F.ptr(out), F.cur_stream()), "gsl_unlearn_ce_grad")
 
     def optimizer_step(self, lr: float, wd: float, alpha: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0,
-                       group_type: str = "block"):
-        """Fused group-Lasso + AdamW on the flat LoRA buffer; repacks the fp16 LoRA operands afterwards."""
+                       group_type: str = "block", state_dev: Optional[torch.Tensor] = None):
+        """Fused group-Lasso + AdamW on the flat LoRA buffer; repacks the fp16 LoRA operands afterwards.  state_dev: the step count and lr are
+        read from the device step state at run time (CUDA-graph capture; the caller advances `opt_step` per replay)."""
         self.opt_step += 1
         n = self.lora_flat.numel()
         offs = self.group_offsets_by_type[group_type]
         self.num_groups = offs.numel() - 1
+        if state_dev is not None:
+            F.check(F.lib().gsl_grouplasso_adamw_step_dev(F.ptr(self.lora_flat), F.ptr(self.grad_flat), F.ptr(self.exp_avg), F.ptr(self.exp_avg_sq),
+                                                          F.ptr(offs), self.num_groups, n, float(wd), float(betas[0]), float(betas[1]), float(eps),
+                                                          float(alpha), float(grad_scale), F.ptr(state_dev), F.ptr(self.group_norms),
+                                                          F.cur_stream()), "gsl_grouplasso_adamw_step_dev")
+            self.refresh_lora()
+            return
         F.check(F.lib().gsl_grouplasso_adamw_step(F.ptr(self.lora_flat), F.ptr(self.grad_flat), F.ptr(self.exp_avg), F.ptr(self.exp_avg_sq),
                                                   F.ptr(offs), self.num_groups, n, float(lr), float(wd), float(betas[0]),
                                                   float(betas[1]), float(eps), float(alpha), float(grad_scale), self.opt_step,

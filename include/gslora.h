@@ -108,6 +108,13 @@ int gsl_cast_f32_to_f16_split(const float* src, int64_t lds, void* dst16, void* 
 int gsl_grouplasso_adamw_step(float* params, const float* grads, float* m, float* v, const int32_t* group_offsets, int num_groups,
                               int64_t n, float lr, float wd, float beta1, float beta2, float eps, float alpha, float grad_scale,
                               int step, float* group_norms, void* stream);
+/* gsl_grouplasso_adamw_step for CUDA-graph capture: the 1-based step count (bias corrections) and the learning rate are read at run time from
+ * the device step state { uint64 seed; int32 adam_step; float lr } at `state_dev`. */
+int gsl_grouplasso_adamw_step_dev(float* params, const float* grads, float* m, float* v, const int32_t* group_offsets, int num_groups,
+                                  int64_t n, float wd, float beta1, float beta2, float eps, float alpha, float grad_scale,
+                                  const void* state_dev, float* group_norms, void* stream);
+/* adds n to the launch counter (a replayed CUDA graph launches the kernels it captured without passing through this library) */
+void gsl_count_launches(long long n);
 /* util.cal_norm.get_norm_of_lora (util/cal_norm.py:121-143): out[t] = ||P_t||_F (type 0) or ||P_t||_1 (type 1). */
 int gsl_tensor_norms(const float* params, const int32_t* tensor_offsets, int num_tensors, int type, float* out, void* stream);
 
@@ -163,6 +170,11 @@ int gsl_engine_forward(void* handle, int slot, const float* img, const int64_t* 
 /* gsl_engine_forward on raw uint8 pixels (see gsl_patchify_u8_f16 for layout / mean / std). */
 int gsl_engine_forward_u8(void* handle, int slot, const uint8_t* img, int layout, const float* mean, const float* std, const int64_t* labels,
                           int B, int use_lora, uint64_t dropout_seed, void* stream);
+/* gsl_engine_forward for CUDA-graph capture: train-mode dropout masks are derived ON THE DEVICE from the 64-bit base seed stored at `seed_dev`
+ * (first field of the 16-byte step state { uint64 seed; int32 adam_step; float lr }), so a captured step can be replayed with a fresh mask per
+ * replay by rewriting that block; dropout_on = 0 disables dropout.  The slot's backward reads the same block. */
+int gsl_engine_forward_dev(void* handle, int slot, const void* img, int img_is_u8_layout, const int64_t* labels, int B, int use_lora,
+                           int dropout_on, const void* seed_dev, void* stream);
 /* selective backward of engine_cl.py:124: upstream d logits [B,C] and/or d emb [B,D] (fp32, may be NULL) ->
  * LoRA gradients written (accumulate = 0) or added (accumulate = 1) into grad_flat. */
 int gsl_engine_backward(void* handle, int slot, const float* dlogits, const float* demb, int accumulate, void* stream);

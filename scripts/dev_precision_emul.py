@@ -132,6 +132,15 @@ def main():
     report("weights exact in fwd only", k)
     k = {f: (True, False) for f in fams}; k["act"] = True
     report("weights exact in bwd only", k)
+    if os.environ.get("PERFAMILY"):
+        k = {f: (False, False) for f in fams}; k["act"] = True
+        report("weights exact everywhere (split mode)", k)
+        for fam in ["qkv", "out", "fc1", "fc2", "patch"]:
+            for which, tag in (((True, False), "FWD"), ((False, True), "BWD")):
+                k = {f: (False, False) for f in fams}; k["act"] = True
+                k[fam] = which
+                report(f"single rounding only in {tag} of {fam}", k)
+        return
     if os.environ.get("ACTSPLIT"):
         k = {f: (False, False) for f in fams}; k["act"] = (True, False)
         report("weights exact, FORWARD activations rounded only", k)

@@ -30,7 +30,7 @@ EXPECTED = (["calculate_prototypes"] + ["eval_data"] * 4 + ["train_one_epoch", "
 
 
 def _env(tmp_path, trace):
-    return dict(os.environ, GSLORA_CPU_ORACLE_ENGINE="1", GSLORA_TRACE=str(trace), TORCH_HOME=str(tmp_path / "torch_home"), WANDB_MODE="offline",
+    return dict(os.environ, GSLORA_CPU_ORACLE_ENGINE="1", GSLORA_CUDA_GRAPH="0", GSLORA_TRACE=str(trace), TORCH_HOME=str(tmp_path / "torch_home"), WANDB_MODE="offline",
                 WANDB_DIR=str(tmp_path),
                 PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests", "cpu_engine"), os.path.join(ROOT, "gs-lora_b200"), os.path.join(ROOT, "oracle", "shims"), REF]))
 

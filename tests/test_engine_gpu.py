@@ -404,3 +404,43 @@ def test_engine_regrowth_keeps_the_fused_optimizer_state(golden_dir):
             m.eval(); m(big, torch.zeros(30, dtype=torch.long).cuda()); m.train()
         assert m._engine.max_batch <= 128
     assert torch.equal(res[0], res[1])
+
+
+def test_cuda_graph_replay_equals_eager_steps(golden_dir, monkeypatch):
+    """After two eager steps with an unchanged key engine_cl captures the step as a CUDA graph and replays it (one launch per step; dropout seed,
+    AdamW step count and lr come from the 16-byte device step state).  Same kernels, same seeds, same order => the replayed run must be
+    BIT-identical to eager launches: per-step scalars and the LoRA parameters after 7 steps with dropout on, changing lr and changing inputs."""
+    import engine_cl
+    import loralib as lora
+    from vit_pytorch_face import ViT_face
+    g, cfg, sd = load_case(golden_dir, "tiny6_b4")
+    gen = torch.Generator().manual_seed(17)
+    S = cfg.image_size
+    batches = [(torch.rand(4, 3, S, S, generator=gen).cuda(), torch.randint(0, cfg.num_class, (4,), generator=gen).cuda(),
+                torch.rand(3, 3, S, S, generator=gen).cuda(), torch.randint(0, cfg.num_class, (3,), generator=gen).cuda()) for _ in range(7)]
+
+    def run(graph_env):
+        monkeypatch.setenv("GSLORA_CUDA_GRAPH", graph_env)
+        m = ViT_face(loss_type="CosFace", GPU_ID=[0], num_class=cfg.num_class, image_size=cfg.image_size, patch_size=cfg.patch_size, dim=cfg.dim,
+                     depth=cfg.depth, heads=cfg.heads, mlp_dim=cfg.mlp_dim, dim_head=cfg.dim_head, dropout=0.1, emb_dropout=0.1, lora_rank=cfg.lora_rank)
+        m.load_state_dict(sd, strict=True)
+        lora.mark_only_lora_as_trainable(m)
+        m = m.cuda().train()
+        outs = []
+        for i, (xr, yr, xf, yf) in enumerate(batches):
+            outs.append(engine_cl.unlearn_step(m, xr, yr, xf, yf, beta=0.15, alpha=1e-2, BND=105.0, hparams=dict(lr=1e-2 * (0.9 ** i), wd=0.05),
+                                               dropout_seed=1000 + 7 * i))
+        st = m.__dict__.get("_gsl_graph")
+        return outs, torch.cat([p.detach().flatten() for p in m.lora_parameters()]).clone(), st, m
+    eager, p_eager, st0, _ = run("0")
+    graphed, p_graph, st1, m1 = run("1")
+    assert st0 is None and st1 is not None and st1["step"] is not None and not st1["failed"]          # steps 3..7 were graph replays
+    assert st1["step"].launches > 50 and m1._engine.opt_step == 7
+    for a, b in zip(eager, graphed):
+        for k in ("loss_remain", "ce_forget", "loss_forget", "structure", "total", "top1_remain", "top1_forget"):
+            assert a[k] == b[k], (k, a[k], b[k])
+    assert torch.equal(p_eager, p_graph)
+    # a different batch split is a different key: back to eager launches (and a fresh capture later), still correct
+    xr, yr, xf, yf = batches[0]
+    out = engine_cl.unlearn_step(m1, xr[:3], yr[:3], xf, yf, beta=0.15, alpha=1e-2, BND=105.0, hparams=dict(lr=1e-3, wd=0.05), dropout_seed=5)
+    assert m1.__dict__["_gsl_graph"]["step"] is None and m1._engine.opt_step == 8 and out["total"] == out["total"]
