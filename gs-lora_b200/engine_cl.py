@@ -310,7 +310,7 @@ def _graph_step(m, eng, xr, yr, xf, yf, beta, alpha, BND, hp, group_type, seed):
     """The captured step for this call's key (or None: not yet / not eligible)."""
     if os.environ.get("GSLORA_CUDA_GRAPH", "1") == "0":
         return None
-    key = (id(eng), tuple(xr.shape), tuple(xf.shape), xr.dtype, xf.dtype, float(beta), float(alpha), float(BND), float(hp["wd"]),
+    key = (getattr(eng, "serial", id(eng)), tuple(xr.shape), tuple(xf.shape), xr.dtype, xf.dtype, float(beta), float(alpha), float(BND), float(hp["wd"]),
            tuple(hp.get("betas", (0.9, 0.999))), float(hp.get("eps", 1e-8)), group_type, seed != 0, m.input_pixel_norm is None)
     st = m.__dict__.setdefault("_gsl_graph", dict(key=None, seen=0, step=None, failed=False))
     if st["key"] != key:

@@ -56,7 +56,11 @@ class EngineSpec:
 
 
 class VitEngine:
+    _next_serial = 0
+
     def __init__(self, spec: EngineSpec, device: torch.device, max_batch: int, num_slots: int = 1):
+        VitEngine._next_serial += 1
+        self.serial = VitEngine._next_serial        # identity of this engine instance (id() can be recycled after a re-creation)
         if device.type != "cuda":
             raise F.GslError("gslora-b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         self.spec, self.device, self.max_batch, self.num_slots = spec, device, int(max_batch), int(num_slots)
