@@ -59,15 +59,15 @@ class EngineBackedModel(nn.Module):
 
     def __deepcopy__(self, memo):
         import copy
-        eng, self._engine = self._engine, None
-        try:
-            cls = self.__class__
-            new = cls.__new__(cls)
-            memo[id(self)] = new
-            for k, v in self.__dict__.items():
+        # device-side companions are never copied: the engine (workspace), a captured CUDA graph of the step (static buffers, graph handle) and
+        # the cached prototype table belong to THIS instance; the copy (EMA model, modify_head / resume_head clones) builds its own lazily
+        skip = ("_engine", "_gsl_graph", "_gsl_proto_cache")
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k not in skip:
                 setattr(new, k, copy.deepcopy(v, memo))
-        finally:
-            self._engine = eng
         new._engine, new._frozen_sig, new._lora_sig = None, None, None
         return new
 

@@ -444,3 +444,22 @@ def test_cuda_graph_replay_equals_eager_steps(golden_dir, monkeypatch):
     xr, yr, xf, yf = batches[0]
     out = engine_cl.unlearn_step(m1, xr[:3], yr[:3], xf, yf, beta=0.15, alpha=1e-2, BND=105.0, hparams=dict(lr=1e-3, wd=0.05), dropout_seed=5)
     assert m1.__dict__["_gsl_graph"]["step"] is None and m1._engine.opt_step == 8 and out["total"] == out["total"]
+
+
+def test_deepcopy_after_graphed_steps_builds_its_own_engine(golden_dir):
+    """copy.deepcopy(BACKBONE) (the driver's EMA model, train_own_forget_cl.py:1058-1078) after the step has been captured as a CUDA graph: the copy
+    shares neither the engine, nor the graph's static buffers, nor the prototype cache, and evaluates to the same function."""
+    import engine_cl
+    g, cfg, sd = load_case(golden_dir, "tiny6_b4")
+    m = build_model(cfg, sd)
+    xr, yr, xf, yf = [g[k].cuda() for k in ("img_r", "lab_r", "img_f", "lab_f")]
+    for _ in range(4):
+        engine_cl.unlearn_step(m, xr, yr, xf, yf, beta=0.15, alpha=1e-2, BND=105.0, hparams=dict(lr=1e-2, wd=0.05))
+    assert m.__dict__["_gsl_graph"]["step"] is not None
+    c = copy.deepcopy(m)
+    assert c._engine is None and "_gsl_graph" not in c.__dict__
+    m.eval(); c.eval()
+    with torch.no_grad():
+        a, _ = m(xr, yr)
+        b, _ = c(xr, yr)
+    assert torch.equal(a, b) and c._engine is not m._engine
