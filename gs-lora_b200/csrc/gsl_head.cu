@@ -13,6 +13,7 @@ namespace gsl {
 static constexpr int HEAD_THREADS = 128;
 static constexpr int HEAD_MAX_D = 1024;
 static constexpr int HEAD_MAX_C = 1024;
+static constexpr int HEAD_IMGS = 4;          // images per CTA (head_fwd / head_bwd): W rows are shared by the CTA's images
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
     v = warp_sum(v);
@@ -25,71 +26,94 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return t;
 }
 
+// HEAD_IMGS images per CTA: every row of W is fetched once per CTA and dotted against all of its images (the per-image version re-read the
+// whole [C, D] matrix from L2 for each image and was pure load latency); per (image, class) the summation order is unchanged.
 __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(HeadArgs a) {
     pdl_prologue();
-    __shared__ float s_e[HEAD_MAX_D];
-    __shared__ float s_logit[HEAD_MAX_C];
+    __shared__ float s_e[HEAD_IMGS][HEAD_MAX_D];
+    __shared__ float s_logit[HEAD_IMGS][HEAD_MAX_C];
     __shared__ float red[HEAD_THREADS / 32];
-    const int b = blockIdx.x, tid = threadIdx.x, D = a.D, C = a.C;
-    const float* xr = a.x + (int64_t)b * a.tokens * a.ldx;
-    float sum = 0.f;
-    for (int d = tid; d < D; d += HEAD_THREADS) { s_e[d] = xr[d]; sum += s_e[d]; }
-    const float mean = block_sum(sum, red) / D;
-    float sq = 0.f;
-    for (int d = tid; d < D; d += HEAD_THREADS) { const float t = s_e[d] - mean; sq += t * t; }
-    const float rstd = rsqrtf(block_sum(sq, red) / D + a.eps);
-    float en = 0.f;
-    for (int d = tid; d < D; d += HEAD_THREADS) {
-        const float xh = (s_e[d] - mean) * rstd;
-        const float e = xh * a.gamma[d] + a.beta[d];
-        if (a.xhat) a.xhat[(int64_t)b * D + d] = xh;
-        a.emb[(int64_t)b * D + d] = e;
-        s_e[d] = e;
-        en += e * e;
+    __shared__ float s_enorm[HEAD_IMGS];
+    const int b0 = blockIdx.x * HEAD_IMGS, tid = threadIdx.x, D = a.D, C = a.C;
+    const int nimg = min(HEAD_IMGS, a.B - b0);
+    for (int i = 0; i < nimg; ++i) {
+        const int b = b0 + i;
+        const float* xr = a.x + (int64_t)b * a.tokens * a.ldx;
+        float sum = 0.f;
+        for (int d = tid; d < D; d += HEAD_THREADS) { s_e[i][d] = xr[d]; sum += s_e[i][d]; }
+        const float mean = block_sum(sum, red) / D;
+        float sq = 0.f;
+        for (int d = tid; d < D; d += HEAD_THREADS) { const float t = s_e[i][d] - mean; sq += t * t; }
+        const float rstd = rsqrtf(block_sum(sq, red) / D + a.eps);
+        float en = 0.f;
+        for (int d = tid; d < D; d += HEAD_THREADS) {
+            const float xh = (s_e[i][d] - mean) * rstd;
+            const float e = xh * a.gamma[d] + a.beta[d];
+            if (a.xhat) a.xhat[(int64_t)b * D + d] = xh;
+            a.emb[(int64_t)b * D + d] = e;
+            s_e[i][d] = e;
+            en += e * e;
+        }
+        const float enorm = fmaxf(sqrtf(block_sum(en, red)), 1e-12f);     // F.normalize eps
+        if (tid == 0) { s_enorm[i] = enorm; if (a.rstd) a.rstd[b] = rstd; }
     }
-    const float enorm = fmaxf(sqrtf(block_sum(en, red)), 1e-12f);     // F.normalize eps
-    if (tid == 0 && a.rstd) a.rstd[b] = rstd;
     if (a.W == nullptr) return;
+    __syncthreads();
     // a label outside [0, C) never indexes anything: its sample reports CE = NaN (the reference's F.cross_entropy would raise) and is never "correct"
-    const long long label_raw = a.labels ? (long long)a.labels[b] : -1;
-    const bool label_bad = a.labels && (label_raw < 0 || label_raw >= C);
-    const int label = (a.labels && !label_bad) ? (int)label_raw : -1;
     const int warp = tid >> 5, lane = tid & 31;
+    long long label_raw = -1;
+    if (lane < nimg && a.labels) label_raw = (long long)a.labels[b0 + lane];       // lane i keeps image i's label
+    const bool label_bad = a.labels && lane < nimg && (label_raw < 0 || label_raw >= C);
+    const int label = (a.labels && lane < nimg && !label_bad) ? (int)label_raw : -1;
     for (int c = warp; c < C; c += HEAD_THREADS / 32) {
         const float* w = a.W + (int64_t)c * D;
-        float dot = 0.f, wn = 0.f;
-        for (int d = lane; d < D; d += 32) { const float wv = __ldg(w + d); dot += wv * s_e[d]; wn += wv * wv; }
-        dot = warp_sum(dot); wn = warp_sum(wn);
-        if (lane == 0) {
-            const float cosv = dot / (enorm * fmaxf(sqrtf(wn), 1e-12f));
-            const float lg = a.head_type == 1 ? dot + (a.head_b ? a.head_b[c] : 0.f)          // heads.head Linear (modified_VIT.py:35-37)
+        float dot[HEAD_IMGS], wn = 0.f;
+#pragma unroll
+        for (int i = 0; i < HEAD_IMGS; ++i) dot[i] = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float wv = __ldg(w + d);
+            wn += wv * wv;
+#pragma unroll
+            for (int i = 0; i < HEAD_IMGS; ++i) dot[i] += wv * s_e[i][d];
+        }
+        wn = warp_sum(wn);
+        float mine = 0.f;
+#pragma unroll
+        for (int i = 0; i < HEAD_IMGS; ++i) { const float t = warp_sum(dot[i]); if (lane == i) mine = t; }
+        if (lane < nimg) {
+            const float cosv = mine / (s_enorm[lane] * fmaxf(sqrtf(wn), 1e-12f));
+            const float lg = a.head_type == 1 ? mine + (a.head_b ? a.head_b[c] : 0.f)          // heads.head Linear (modified_VIT.py:35-37)
                                               : a.cos_s * (c == label ? cosv - a.cos_m : cosv);
-            s_logit[c] = lg;
-            a.logits[(int64_t)b * C + c] = lg;
+            s_logit[lane][c] = lg;
+            a.logits[(int64_t)(b0 + lane) * C + c] = lg;
         }
     }
     __syncthreads();
-    if (warp == 0) {
+    for (int i = warp; i < nimg; i += HEAD_THREADS / 32) {      // one warp per image: arg max, log-sum-exp, CE
+        const int lab_bad = __shfl_sync(0xffffffffu, (int)label_bad, i);
+        const int lab = __shfl_sync(0xffffffffu, label, i);
         float mx = -INFINITY; int arg = 0;
-        for (int c = lane; c < C; c += 32) if (s_logit[c] > mx) { mx = s_logit[c]; arg = c; }
+        for (int c = lane; c < C; c += 32) if (s_logit[i][c] > mx) { mx = s_logit[i][c]; arg = c; }
         for (int o = 16; o > 0; o >>= 1) {
             const float om = __shfl_xor_sync(0xffffffffu, mx, o);
             const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
             if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
         }
         float se = 0.f;
-        for (int c = lane; c < C; c += 32) se += __expf(s_logit[c] - mx);
+        for (int c = lane; c < C; c += 32) se += __expf(s_logit[i][c] - mx);
         se = warp_sum(se);
         if (lane == 0) {
-            if (a.ce) a.ce[b] = label_bad ? __int_as_float(0x7fc00000) : (label >= 0) ? (mx + logf(se) - s_logit[label]) : 0.f;
-            if (a.correct) a.correct[b] = (arg == label) ? 1 : 0;
+            const int b = b0 + i;
+            if (a.ce) a.ce[b] = lab_bad ? __int_as_float(0x7fc00000) : (lab >= 0) ? (mx + logf(se) - s_logit[i][lab]) : 0.f;
+            if (a.correct) a.correct[b] = (arg == lab) ? 1 : 0;
         }
     }
 }
 
 int head_fwd(const HeadArgs& a, cudaStream_t s) {
     GSL_REQUIRE(a.D <= HEAD_MAX_D && a.C <= HEAD_MAX_C, "head: D=%d C=%d exceed limits", a.D, a.C);
-    GSL_CHECK_CUDA(launch_pdl(head_fwd_kernel, dim3(a.B), dim3(HEAD_THREADS), 0, s, a));
+    if (a.B == 0) return 0;
+    GSL_CHECK_CUDA(launch_pdl(head_fwd_kernel, dim3((a.B + HEAD_IMGS - 1) / HEAD_IMGS), dim3(HEAD_THREADS), 0, s, a));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -126,80 +150,99 @@ int ce_grad(const float* logits, const int64_t* labels, const float* coef_dev, f
 
 __global__ void __launch_bounds__(HEAD_THREADS) head_bwd_kernel(HeadBwdArgs a) {
     pdl_prologue();
-    __shared__ float s_de[HEAD_MAX_D];     // d ehat, then d e
-    __shared__ float s_dc[HEAD_MAX_C];     // d cos[c] / ||W_c||
+    __shared__ float s_de[HEAD_IMGS][HEAD_MAX_D];     // d ehat, then d e
+    __shared__ float s_dc[HEAD_IMGS][HEAD_MAX_C];     // d cos[c] / ||W_c||
     __shared__ float red[HEAD_THREADS / 32];
-    const int b = blockIdx.x, tid = threadIdx.x, D = a.D, C = a.C;
+    __shared__ float s_enorm[HEAD_IMGS];
+    const int b0 = blockIdx.x * HEAD_IMGS, tid = threadIdx.x, D = a.D, C = a.C;
+    const int nimg = min(HEAD_IMGS, a.B - b0);
     const int warp = tid >> 5, lane = tid & 31;
-    const float* e = a.emb + (int64_t)b * D;
-    float en = 0.f;
-    for (int d = tid; d < D; d += HEAD_THREADS) { en += e[d] * e[d]; s_de[d] = 0.f; }
-    const float enorm = fmaxf(sqrtf(block_sum(en, red)), 1e-12f);
-    if (a.dlogits && a.W && a.head_type == 1) {
-        // Linear head: d emb = d logits . W
-        for (int c = tid; c < C; c += HEAD_THREADS) s_dc[c] = a.dlogits[(int64_t)b * C + c];
+    for (int i = 0; i < HEAD_IMGS; ++i) {
+        const float* e = a.emb + (int64_t)(b0 + (i < nimg ? i : 0)) * D;
+        float en = 0.f;
+        for (int d = tid; d < D; d += HEAD_THREADS) { en += e[d] * e[d]; s_de[i][d] = 0.f; }
+        const float enorm = fmaxf(sqrtf(block_sum(en, red)), 1e-12f);
+        if (tid == 0) s_enorm[i] = enorm;
+    }
+    if (a.dlogits && a.W) {
+        if (a.head_type == 1) {
+            // Linear head: d emb = d logits . W
+            for (int i = 0; i < HEAD_IMGS; ++i)
+                for (int c = tid; c < C; c += HEAD_THREADS) s_dc[i][c] = i < nimg ? a.dlogits[(int64_t)(b0 + i) * C + c] : 0.f;
+        } else {
+            for (int c = warp; c < C; c += HEAD_THREADS / 32) {
+                const float* w = a.W + (int64_t)c * D;
+                float wn = 0.f;
+                for (int d = lane; d < D; d += 32) { const float wv = __ldg(w + d); wn += wv * wv; }
+                wn = warp_sum(wn);
+                if (lane < HEAD_IMGS) s_dc[lane][c] = lane < nimg ? a.cos_s * a.dlogits[(int64_t)(b0 + lane) * C + c] / fmaxf(sqrtf(wn), 1e-12f) : 0.f;
+            }
+        }
         __syncthreads();
+        // d ehat[d] = sum_c dcos[c] * what[c, d]  (Linear head: d emb directly); every W element is loaded once for the CTA's images
         for (int d = tid; d < D; d += HEAD_THREADS) {
-            float acc = 0.f;
-            for (int c = 0; c < C; ++c) acc += s_dc[c] * __ldg(a.W + (int64_t)c * D + d);
-            s_de[d] = acc;
+            float acc[HEAD_IMGS];
+#pragma unroll
+            for (int i = 0; i < HEAD_IMGS; ++i) acc[i] = 0.f;
+            for (int c = 0; c < C; ++c) {
+                const float wv = __ldg(a.W + (int64_t)c * D + d);
+#pragma unroll
+                for (int i = 0; i < HEAD_IMGS; ++i) acc[i] += s_dc[i][c] * wv;
+            }
+#pragma unroll
+            for (int i = 0; i < HEAD_IMGS; ++i) s_de[i][d] = acc[i];
         }
-    } else if (a.dlogits && a.W) {
-        for (int c = warp; c < C; c += HEAD_THREADS / 32) {
-            const float* w = a.W + (int64_t)c * D;
-            float wn = 0.f;
-            for (int d = lane; d < D; d += 32) { const float wv = __ldg(w + d); wn += wv * wv; }
-            wn = warp_sum(wn);
-            if (lane == 0) s_dc[c] = a.cos_s * a.dlogits[(int64_t)b * C + c] / fmaxf(sqrtf(wn), 1e-12f);
+        if (a.head_type != 1) {
+            __syncthreads();
+            // d e = (d ehat - ehat * (ehat . d ehat)) / ||e||
+            for (int i = 0; i < nimg; ++i) {
+                const float* e = a.emb + (int64_t)(b0 + i) * D;
+                const float enorm = s_enorm[i];
+                float dot = 0.f;
+                for (int d = tid; d < D; d += HEAD_THREADS) dot += s_de[i][d] * e[d];
+                dot = block_sum(dot, red) / enorm;
+                for (int d = tid; d < D; d += HEAD_THREADS) s_de[i][d] = (s_de[i][d] - (e[d] / enorm) * dot) / enorm;
+            }
         }
-        __syncthreads();
-        // d ehat[d] = sum_c dcos[c] * what[c, d]
-        for (int d = tid; d < D; d += HEAD_THREADS) {
-            float acc = 0.f;
-            for (int c = 0; c < C; ++c) acc += s_dc[c] * __ldg(a.W + (int64_t)c * D + d);
-            s_de[d] = acc;
-        }
-        __syncthreads();
-        // d e = (d ehat - ehat * (ehat . d ehat)) / ||e||
-        float dot = 0.f;
-        for (int d = tid; d < D; d += HEAD_THREADS) dot += s_de[d] * e[d];
-        dot = block_sum(dot, red) / enorm;
-        for (int d = tid; d < D; d += HEAD_THREADS) s_de[d] = (s_de[d] - (e[d] / enorm) * dot) / enorm;
     }
     __syncthreads();
     // LayerNorm backward of mlp_head (frozen affine)
-    float s1 = 0.f, s2 = 0.f;
-    for (int d = tid; d < D; d += HEAD_THREADS) {
-        float de = s_de[d];
-        if (a.demb) de += a.demb[(int64_t)b * D + d];
-        const float g = de * a.gamma[d];
-        s_de[d] = g;
-        s1 += g;
-        s2 += g * a.xhat[(int64_t)b * D + d];
-    }
-    const float mg = block_sum(s1, red) / D;
-    const float mgx = block_sum(s2, red) / D;
-    const float rstd = a.rstd[b];
     const uint32_t dseed = a.drop_p > 0.f ? drop_seed_resolve(a.drop_seed) : 0u;
-    for (int d = tid; d < D; d += HEAD_THREADS) {
-        const float v = a.gscale * rstd * (s_de[d] - mg - a.xhat[(int64_t)b * D + d] * mgx);
-        if (a.dx) a.dx[(int64_t)b * a.tokens * a.lddx + d] = v;
-        if (a.dx16) {
-            float m = 1.0f;
-            if (a.drop_p > 0.f) {
-                const uint32_t e = (uint32_t)(b * a.tokens) * (uint32_t)D + (uint32_t)d;
-                const uint32_t h = drop_bits(e >> 1, dseed);
-                const uint32_t bits = ((e & 1u) ? (h >> 16) : h) & 0x7FFFu;
-                m = bits >= drop_thresh15(a.drop_p) ? 1.0f / (1.0f - a.drop_p) : 0.f;
+    for (int i = 0; i < nimg; ++i) {
+        const int b = b0 + i;
+        float s1 = 0.f, s2 = 0.f;
+        for (int d = tid; d < D; d += HEAD_THREADS) {
+            float de = s_de[i][d];
+            if (a.demb) de += a.demb[(int64_t)b * D + d];
+            const float g = de * a.gamma[d];
+            s_de[i][d] = g;
+            s1 += g;
+            s2 += g * a.xhat[(int64_t)b * D + d];
+        }
+        const float mg = block_sum(s1, red) / D;
+        const float mgx = block_sum(s2, red) / D;
+        const float rstd = a.rstd[b];
+        for (int d = tid; d < D; d += HEAD_THREADS) {
+            const float v = a.gscale * rstd * (s_de[i][d] - mg - a.xhat[(int64_t)b * D + d] * mgx);
+            if (a.dx) a.dx[(int64_t)b * a.tokens * a.lddx + d] = v;
+            if (a.dx16) {
+                float m = 1.0f;
+                if (a.drop_p > 0.f) {
+                    const uint32_t e = (uint32_t)(b * a.tokens) * (uint32_t)D + (uint32_t)d;
+                    const uint32_t h = drop_bits(e >> 1, dseed);
+                    const uint32_t bits = ((e & 1u) ? (h >> 16) : h) & 0x7FFFu;
+                    m = bits >= drop_thresh15(a.drop_p) ? 1.0f / (1.0f - a.drop_p) : 0.f;
+                }
+                a.dx16[(int64_t)b * a.tokens * a.lddx16 + d] = __float2half_rn(v * m);
             }
-            a.dx16[(int64_t)b * a.tokens * a.lddx16 + d] = __float2half_rn(v * m);
         }
     }
 }
 
 int head_bwd(const HeadBwdArgs& a, cudaStream_t s) {
     GSL_REQUIRE(a.D <= HEAD_MAX_D && a.C <= HEAD_MAX_C, "head_bwd: D=%d C=%d exceed limits", a.D, a.C);
-    GSL_CHECK_CUDA(launch_pdl(head_bwd_kernel, dim3(a.B), dim3(HEAD_THREADS), 0, s, a));
+    if (a.B == 0) return 0;
+    GSL_CHECK_CUDA(launch_pdl(head_bwd_kernel, dim3((a.B + HEAD_IMGS - 1) / HEAD_IMGS), dim3(HEAD_THREADS), 0, s, a));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;

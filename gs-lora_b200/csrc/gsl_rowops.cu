@@ -11,49 +11,72 @@ namespace gsl {
 // Reference: einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (vit_pytorch_face/vit_face.py:530) and, for the
 // torchvision family, conv_proj's implicit (c p1 p2) patch vector.  Token 0 (cls slot) is a zero row so that the
 // patch-embedding GEMM's rows line up 1:1 with the [B, tokens, D] residual stream.
-// output-centric: one thread per pair of consecutive patch-vector elements (coalesced half2 stores; the gathers hit L1/L2)
 // T = float: the reference's loader output (transforms.ToTensor(): fp32 NCHW in [0, 1]).
 // T = uint8_t: raw pixels, NCHW (layout 0, transforms.PILToTensor()) or NHWC (layout 1, decoded image rows); ToTensor's `/ 255` and the optional
 // transforms.Normalize(mean, std) of the ImageNet configs (train_own_forget_cl.py:138-139) are applied on the fly with IEEE division, so
 // the fp32 value that gets rounded to fp16 is bit-identical to what the reference's transform pipeline would have produced on the host.
 struct PixelNorm { float mean[4]; float std[4]; int enabled; };
 
+// One CTA per (image, patch row): the C x patch x S strip of the image is read ONCE with coalesced loads into shared memory (converted to
+// fp32 there: the u8 arithmetic runs once per pixel), then the w patch vectors of that row leave as coalesced half2 stores; a per-CTA
+// table maps the patch-vector element e to its strip offset, so the scatter costs one shared-memory lookup per element instead of the
+// integer divisions.  HBM-bound: reads the image once, writes the patch matrix once.
 template <typename T>
-__global__ void patchify_kernel(const T* __restrict__ img, __half* __restrict__ out, int64_t ld, int B, int C, int S,
-                                int patch, int order, int layout, PixelNorm nrm) {
+__global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ img, __half* __restrict__ out, int64_t ld, int B, int C, int S,
+                                                       int patch, int order, int layout, PixelNorm nrm) {
     pdl_prologue();
-    const int w = S / patch;
-    const int P = w * w;
-    const int pd = C * patch * patch;
-    const int half_pd = pd >> 1;
-    const int64_t total = (int64_t)B * (P + 1) * half_pd;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int e0 = (int)(i % half_pd) * 2;
-        const int64_t row = i / half_pd;
-        const int tok = (int)(row % (P + 1));
-        const int b = (int)(row / (P + 1));
-        float v[2] = {0.f, 0.f};
-        if (tok > 0) {
-            const int ph = (tok - 1) / w, pw = (tok - 1) % w;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int e = e0 + k;
-                int c, p1, p2;
-                if (order == 0) { c = e % C; p2 = (e / C) % patch; p1 = e / (C * patch); }
-                else { p2 = e % patch; p1 = (e / patch) % patch; c = e / (patch * patch); }
-                const int y = ph * patch + p1, x = pw * patch + p2;
-                const int64_t idx = layout == 0 ? (((int64_t)b * C + c) * S + y) * S + x : (((int64_t)b * S + y) * S + x) * C + c;
-                if constexpr (sizeof(T) == 1) {
-                    float f = __fdiv_rn((float)__ldg(img + idx), 255.f);
-                    if (nrm.enabled) f = __fdiv_rn(f - nrm.mean[c & 3], nrm.std[c & 3]);
-                    v[k] = f;
-                } else {
-                    v[k] = __ldg(img + idx);
+    extern __shared__ __align__(16) uint8_t pf_smem[];
+    const int w = S / patch, P = w * w, pd = C * patch * patch, half_pd = pd >> 1;
+    const int plane = patch * S;                          // one channel of the strip: [patch rows][S pixels]
+    float* strip = reinterpret_cast<float*>(pf_smem);     // [C][patch][S]
+    int* lut = reinterpret_cast<int*>(strip + C * plane); // e -> c * plane + p1 * S + p2
+    const int b = blockIdx.x / w, ph = blockIdx.x % w;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < pd; e += blockDim.x) {
+        int c, p1, p2;
+        if (order == 0) { c = e % C; p2 = (e / C) % patch; p1 = e / (C * patch); }
+        else { p2 = e % patch; p1 = (e / patch) % patch; c = e / (patch * patch); }
+        lut[e] = c * plane + p1 * S + p2;
+    }
+    auto conv = [&](T v, int c) -> float {
+        if constexpr (sizeof(T) == 1) {
+            float f = __fdiv_rn((float)v, 255.f);
+            if (nrm.enabled) f = __fdiv_rn(f - nrm.mean[c & 3], nrm.std[c & 3]);
+            return f;
+        } else {
+            return v;
+        }
+    };
+    if (layout == 0) {          // NCHW: channel c contributes `patch` contiguous image rows = plane contiguous elements
+        for (int c = 0; c < C; ++c) {
+            const T* src = img + (((int64_t)b * C + c) * S + (int64_t)ph * patch) * S;
+            if constexpr (sizeof(T) == 4) {
+                if ((plane & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                    for (int i = tid; i < (plane >> 2); i += blockDim.x)
+                        reinterpret_cast<float4*>(strip + c * plane)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+                    continue;
                 }
             }
+            for (int i = tid; i < plane; i += blockDim.x) strip[c * plane + i] = conv(__ldg(src + i), c);
         }
-        *reinterpret_cast<__half2*>(out + row * ld + e0) = __floats2half2_rn(v[0], v[1]);
+    } else {                    // NHWC: `patch` contiguous image rows of S * C interleaved elements
+        const T* src = img + ((int64_t)b * S + (int64_t)ph * patch) * S * C;
+        const int n = plane * C;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const int c = i % C, px = i / C;               // px = p1 * S + x
+            strip[c * plane + px] = conv(__ldg(src + i), c);
+        }
     }
+    __syncthreads();
+    const int64_t row0 = (int64_t)b * (P + 1) + 1 + (int64_t)ph * w;
+    const int n_out = w * half_pd;
+    for (int i = tid; i < n_out; i += blockDim.x) {
+        const int pw = i / half_pd, e0 = (i - pw * half_pd) * 2;
+        const int off = pw * patch;
+        *reinterpret_cast<__half2*>(out + (row0 + pw) * ld + e0) = __floats2half2_rn(strip[lut[e0] + off], strip[lut[e0 + 1] + off]);
+    }
+    if (ph == 0)                // token 0 (cls slot) is a zero row
+        for (int i = tid; i < half_pd; i += blockDim.x) *reinterpret_cast<__half2*>(out + (int64_t)b * (P + 1) * ld + 2 * i) = __floats2half2_rn(0.f, 0.f);
 }
 
 template <typename T>
@@ -61,12 +84,17 @@ static int patchify_launch(const T* img, __half* out, int64_t ld, int B, int C, 
                            cudaStream_t s) {
     GSL_REQUIRE(S % patch == 0, "image size %d not divisible by patch %d", S, patch);
     GSL_REQUIRE((C * patch * patch) % 2 == 0 && ld % 2 == 0, "patchify: patch_dim and ld must be even");
-    const int64_t total = (int64_t)B * ((S / patch) * (S / patch) + 1) * (C * patch * patch / 2);
-    const int threads = 256;
-    int blocks = (int)((total + threads - 1) / threads);
-    const int cap = device_sm_count() * 32;
-    if (blocks > cap) blocks = cap;
-    GSL_CHECK_CUDA(launch_pdl(patchify_kernel<T>, dim3(blocks), dim3(threads), 0, s, img, out, ld, B, C, S, patch, order, layout, nrm));
+    if (B == 0) return 0;
+    const int w = S / patch;
+    const size_t smem = (size_t)C * patch * S * 4 + (size_t)C * patch * patch * 4;
+    GSL_REQUIRE(smem <= 200 * 1024, "patchify: a %d x %d x %d strip does not fit in shared memory", C, patch, S);
+    static size_t smem_set[2] = {0, 0};           // per instantiation (float / uint8)
+    size_t& cur = smem_set[sizeof(T) == 1 ? 1 : 0];
+    if (smem > cur) {
+        GSL_CHECK_CUDA(cudaFuncSetAttribute(patchify_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    GSL_CHECK_CUDA(launch_pdl(patchify_kernel<T>, dim3((unsigned)(B * w)), dim3(256), smem, s, img, out, ld, B, C, S, patch, order, layout, nrm));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -472,18 +500,42 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_tn_partial_kernel(const 
     }
 }
 
+// Reduction of the split partials in a FIXED order (deterministic, no atomics).  The partials were just written and sit in L2, so the
+// kernel is pure latency: RED_PARTS threads share one output (part p sums splits p, p + RED_PARTS, ...) with RED_DEPTH independent loads
+// in flight each, and the parts are combined through shared memory in part order.
+static constexpr int RED_PARTS = 4, RED_OUTS = 64, RED_DEPTH = 8;
 template <int R>
-__global__ void skinny_tn_reduce_kernel(const float* __restrict__ partial, int splits, int N, float scale, float* __restrict__ out, int64_t ldo,
-                                        int transpose_out, int r_out, int accumulate) {
+__global__ void __launch_bounds__(RED_PARTS * RED_OUTS) skinny_tn_reduce_kernel(const float* __restrict__ partial, int splits, int N, float scale,
+                                                                                float* __restrict__ out, int64_t ldo, int transpose_out, int r_out,
+                                                                                int accumulate) {
     pdl_prologue();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N * R) return;
-    const int n = i / R, j = i % R;
+    __shared__ float s_part[RED_PARTS][RED_OUTS];
+    const int lo = threadIdx.x % RED_OUTS, part = threadIdx.x / RED_OUTS;
+    const int i = blockIdx.x * RED_OUTS + lo;
+    const int64_t stride = (int64_t)N * R;
     float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * N * R + i];
-    if (j < r_out) {
-        float* o = transpose_out ? out + (int64_t)j * ldo + n : out + (int64_t)n * ldo + j;
-        *o = (accumulate ? *o : 0.f) + s * scale;
+    if (i < N * R) {
+        int k = part;
+        for (; k + (RED_DEPTH - 1) * RED_PARTS < splits; k += RED_DEPTH * RED_PARTS) {
+            float v[RED_DEPTH];
+#pragma unroll
+            for (int u = 0; u < RED_DEPTH; ++u) v[u] = partial[(int64_t)(k + u * RED_PARTS) * stride + i];
+#pragma unroll
+            for (int u = 0; u < RED_DEPTH; ++u) s += v[u];
+        }
+        for (; k < splits; k += RED_PARTS) s += partial[(int64_t)k * stride + i];
+    }
+    s_part[part][lo] = s;
+    __syncthreads();
+    if (part == 0 && i < N * R) {
+        float t = s_part[0][lo];
+#pragma unroll
+        for (int p = 1; p < RED_PARTS; ++p) t += s_part[p][lo];
+        const int n = i / R, j = i % R;
+        if (j < r_out) {
+            float* o = transpose_out ? out + (int64_t)j * ldo + n : out + (int64_t)n * ldo + j;
+            *o = (accumulate ? *o : 0.f) + t * scale;
+        }
     }
 }
 
@@ -520,12 +572,12 @@ int skinny_tn(const __half* L, int64_t ldl, const __half* Rm, int64_t ldr, float
     if (r <= 8) {
         GSL_CHECK_CUDA(launch_pdl(skinny_tn_partial_kernel<8>, dim3(grid), dim3(SK_THREADS), smem, s, L, ldl, Rm, ldr, workspace, M, N, rows_per_split));
         GSL_COUNT_LAUNCH(1);
-        GSL_CHECK_CUDA(launch_pdl(skinny_tn_reduce_kernel<8>, dim3((N * 8 + 255) / 256), dim3(256), 0, s, workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate));
+        GSL_CHECK_CUDA(launch_pdl(skinny_tn_reduce_kernel<8>, dim3((N * 8 + RED_OUTS - 1) / RED_OUTS), dim3(RED_PARTS * RED_OUTS), 0, s, workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate));
         GSL_COUNT_LAUNCH(1);
     } else {
         GSL_CHECK_CUDA(launch_pdl(skinny_tn_partial_kernel<16>, dim3(grid), dim3(SK_THREADS), smem, s, L, ldl, Rm, ldr, workspace, M, N, rows_per_split));
         GSL_COUNT_LAUNCH(1);
-        GSL_CHECK_CUDA(launch_pdl(skinny_tn_reduce_kernel<16>, dim3((N * 16 + 255) / 256), dim3(256), 0, s, workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate));
+        GSL_CHECK_CUDA(launch_pdl(skinny_tn_reduce_kernel<16>, dim3((N * 16 + RED_OUTS - 1) / RED_OUTS), dim3(RED_PARTS * RED_OUTS), 0, s, workspace, splits, N, scale, out, ldo, transpose_out, r, accumulate));
         GSL_COUNT_LAUNCH(1);
     }
     GSL_CHECK_CUDA(cudaGetLastError());
@@ -714,7 +766,7 @@ int lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __ha
     }
 #undef GSL_SP_CASE
     if (rc) return rc;
-    GSL_CHECK_CUDA(launch_pdl(skinny_tn_reduce_kernel<8>, dim3((N * 8 + 255) / 256), dim3(256), 0, s, workspace, ctas, N, scale, out, ldo, transpose_out, r, accumulate));
+    GSL_CHECK_CUDA(launch_pdl(skinny_tn_reduce_kernel<8>, dim3((N * 8 + RED_OUTS - 1) / RED_OUTS), dim3(RED_PARTS * RED_OUTS), 0, s, workspace, ctas, N, scale, out, ldo, transpose_out, r, accumulate));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;
