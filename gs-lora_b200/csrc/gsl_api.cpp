@@ -41,6 +41,7 @@ int gsl_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
     a.M = M; a.N = N; a.K = K; a.epi = epi; a.bias = bias;
     a.out0 = out0; a.ld0 = ld0; a.out1 = out1; a.ld1 = ld1;
     a.aux = aux; a.ldaux = ldaux; a.aux_period = aux_period;
+    if (epi == EPI_F16_ROWDOT) { a.rowdot = (float*)out1; a.out1 = nullptr; }
     a.cta_group = cta_group; a.block_n = block_n; a.drop_p = drop_p; a.drop_seed = drop_seed;
     return gemm_f16(a, (cudaStream_t)stream);
 }
@@ -53,6 +54,7 @@ int gsl_gemm_f16_split(const void* A, int64_t lda, const void* B, const void* B_
     a.M = M; a.N = N; a.K = K; a.epi = epi; a.bias = bias;
     a.out0 = out0; a.ld0 = ld0; a.out1 = out1; a.ld1 = ld1;
     a.aux = aux; a.ldaux = ldaux; a.aux_period = aux_period;
+    if (epi == EPI_F16_ROWDOT) { a.rowdot = (float*)out1; a.out1 = nullptr; }
     a.cta_group = cta_group; a.block_n = block_n; a.drop_p = drop_p; a.drop_seed = drop_seed;
     return gemm_f16(a, (cudaStream_t)stream);
 }
@@ -105,7 +107,13 @@ int gsl_attention_fwd(const void* qkv16, int64_t ld, void* out16, int64_t ldo, f
 int gsl_attention_bwd(const void* qkv16, int64_t ld, const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
                       void* dqkv16, int64_t lddqkv, int B, int N, int heads, float scale, void* stream) {
     return attention_bwd((const __half*)qkv16, ld, (const __half*)out16, ldo, (const __half*)dout16, lddo, lse, (__half*)dqkv16, lddqkv, B, N,
-                         heads, scale, ST(stream));
+                         heads, scale, ST(stream), nullptr);
+}
+int gsl_attention_bwd_rowdot(const void* qkv16, int64_t ld, const void* dout16, int64_t lddo, const float* lse, const float* rowdot,
+                             void* dqkv16, int64_t lddqkv, int B, int N, int heads, float scale, void* stream) {
+    if (rowdot == nullptr) { set_last_error("gsl_attention_bwd_rowdot: rowdot is null"); return -1; }
+    return attention_bwd((const __half*)qkv16, ld, nullptr, 0, (const __half*)dout16, lddo, lse, (__half*)dqkv16, lddqkv, B, N, heads, scale,
+                         ST(stream), rowdot);
 }
 int gsl_cast_f32_to_f16(const float* src, int64_t lds, void* dst16, int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose,
                         void* stream) {

@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV0, const __grid_constant__ CUtensorMap tmQKV1,
                         const __grid_constant__ CUtensorMap tmDO0, const __grid_constant__ CUtensorMap tmDO1,
                         const __grid_constant__ CUtensorMap tmDQKV, const __half* __restrict__ out, int64_t ldo, const __half* __restrict__ dout, int64_t lddo,
-                        const float* __restrict__ lse, __half* __restrict__ dqkv, int64_t lddqkv, int B, int N, int heads, float scale, int dbg) {
+                        const float* __restrict__ lse, const float* __restrict__ delta_parts, __half* __restrict__ dqkv, int64_t lddqkv, int B, int N, int heads,
+                        float scale, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sb = smem_u32(smem);
@@ -430,6 +431,21 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV0, const __grid
             float* st_lse = s_stat + p * 512;
             float* st_del = st_lse + 256;
             if (k >= 1) mbar_wait(bar(B_STATS_FREE + p), (k - 1) & 1);
+            if (delta_parts != nullptr) {
+                // delta arrives precomputed (EPI_F16_ROWDOT epilogue of the GEMM that produced dO) as two partial sums per row: coalesced
+                // fp32 reads.  (Computing it here from the O and dO rows made this warp pair the critical path of the whole kernel: 2 x 197
+                // strided 128-byte rows per pair with a few loads in flight = 0.13 of 0.63 ms per launch.)
+                const int64_t base = ((int64_t)b * heads + h) * N, part = (int64_t)B * heads * N;
+                for (int r = dt; r < 256; r += AB_DELTA_THREADS) {
+                    float d = 0.f, l = 0.f;
+                    if (r < N && !(dbg & 8)) {
+                        d = __ldg(delta_parts + base + r) + __ldg(delta_parts + part + base + r);
+                        l = lse[base + r] * 1.4426950408889634f;
+                    }
+                    st_del[r] = d;
+                    st_lse[r] = l;
+                }
+            } else
             for (int r = dt; r < 256; r += AB_DELTA_THREADS) {
                 float d = 0.f, l = 0.f;
                 if (r < N && !(dbg & 8)) {
@@ -464,9 +480,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV0, const __grid
 }
 
 int attention_bwd(const __half* qkv, int64_t ld, const __half* out, int64_t ldo, const __half* dout, int64_t lddo, const float* lse,
-                     __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s) {
+                     __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s, const float* delta_parts) {
     GSL_REQUIRE(N >= 1 && N <= AB_MAX_TOKENS, "attention_bwd: tokens=%d outside [1, %d]", N, AB_MAX_TOKENS);
     GSL_REQUIRE(ld % 8 == 0 && lddo % 8 == 0 && ldo % 8 == 0 && lddqkv % 8 == 0, "attention_bwd: pitches must be multiples of 8 halves");
+    GSL_REQUIRE(out != nullptr || delta_parts != nullptr, "attention_bwd: needs the forward output or precomputed delta parts");
     GSL_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0,
                 "attention_bwd: 16-byte alignment required");
     const int npad = (N + 15) & ~15;
@@ -490,7 +507,7 @@ int attention_bwd(const __half* qkv, int64_t ld, const __half* out, int64_t ldo,
     const int nwork = B * heads;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("GSL_ATTN_DBG"); dbg = e ? atoi(e) : 0; }       // dev switch: knock out stages to time the rest
-    GSL_CHECK_CUDA(launch_pdl(attention_bwd_tc_kernel, dim3(nwork < sms ? nwork : sms), dim3(AB_THREADS), smem, s, tq0, tq1, td0, td1, tout, out, ldo, dout, lddo, lse, dqkv, lddqkv, B, N,
+    GSL_CHECK_CUDA(launch_pdl(attention_bwd_tc_kernel, dim3(nwork < sms ? nwork : sms), dim3(AB_THREADS), smem, s, tq0, tq1, td0, td1, tout, out, ldo, dout, lddo, lse, delta_parts, dqkv, lddqkv, B, N,
                                                                                 heads, scale, dbg));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());

@@ -109,6 +109,7 @@ size_t Engine::carve(bool assign) {
     for (int i = 0; i < 4; ++i) t_tu[i] = (__half*)take((size_t)M * 16 * 2);
     auto* t_do = (__half*)take((size_t)M * inner * 2);
     auto* t_dqkv = (__half*)take((size_t)M * 3 * inner * 2);
+    auto* t_delta = (float*)take((size_t)2 * Bm * cfg.heads * tokens * 4);
     auto* t_dx32 = (float*)take((size_t)M * D * 4);
     auto* t_dxn32 = (float*)take((size_t)M * D * 4);
     auto* t_cdx = (float*)take((size_t)Bm * D * 4);
@@ -127,7 +128,7 @@ size_t Engine::carve(bool assign) {
     auto* t_pp = (void*)take((size_t)L * 8 * sizeof(void*));
     auto* t_mj = (void*)take((size_t)L * 3 * 128);
     if (assign) {
-        patches16 = t_patches; xn16 = t_xn; dy16 = t_dy; dh16 = t_dh; do16 = t_do; dqkv16 = t_dqkv;
+        patches16 = t_patches; xn16 = t_xn; dy16 = t_dy; dh16 = t_dh; do16 = t_do; dqkv16 = t_dqkv; attn_delta = t_delta;
         t1_16 = t_tu[0]; t2_16 = t_tu[1]; u1_16 = t_tu[2]; u2_16 = t_tu[3];
         dx32 = t_dx32; dxn32 = t_dxn32; skinny_ws = t_sk; skinny_ws_bytes = sk;
         cls_dx32 = t_cdx; cls_dxn32 = t_cdxn; cls_dy16 = t_cdy; cls_dh16 = t_cdh; cls_do16 = t_cdo;
@@ -632,13 +633,14 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
                                pdrop, dseed, s))) return rc;
         if (l == 0 && !attn_lora) break;      // nothing trainable below block 0's FFN
         // ---------------- attention: y = to_out(attn(to_qkv(LN1(x)))) + x
-        {   // dO = dY Wo
+        {   // dO = dY Wo; the epilogue also emits delta = rowsum(dO * O) per (image, head, token) for the attention backward
             GemmArgs g;
             g.A = dy16; g.lda = D; g.B = c.out_wT16.hi; g.B_lo = c.out_wT16.lo; g.ldb = D; g.M = M; g.N = inner; g.K = D;
-            g.epi = EPI_F16; g.out0 = do16; g.ld0 = inner;
+            g.epi = EPI_F16_ROWDOT; g.out0 = do16; g.ld0 = inner; g.aux = a.o16; g.ldaux = inner; g.aux_period = tokens; g.rowdot = attn_delta;
             if ((rc = gemm_f16(g, s))) return rc;
         }
-        if ((rc = attention_bwd(a.qkv16, 3 * inner, a.o16, inner, do16, inner, a.lse, dqkv16, 3 * inner, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
+        if ((rc = attention_bwd(a.qkv16, 3 * inner, a.o16, inner, do16, inner, a.lse, dqkv16, 3 * inner, B, tokens, cfg.heads, cfg.attn_scale, s,
+                                attn_delta))) return rc;
         if (attn_lora && (rc = attn_lora_grads(l, M, dqkv16, a.xn1_16, accumulate, s))) return rc;
         if (l == 0) break;      // block 0: to_qkv's LoRA is the last trainable thing on the way down
         {   // dLN1 = dQKV Wqkv

@@ -76,6 +76,7 @@ public:
     std::vector<Slot> slots;
     // transients (shared by all slots)
     __half *patches16, *xn16, *dy16, *dh16, *do16, *dqkv16;
+    float* attn_delta;      // [2][B, heads, tokens] partial sums of delta = rowsum(dO * O) (EPI_F16_ROWDOT -> attention_bwd)
     __half *t1_16, *t2_16, *u1_16, *u2_16;      // rank-r by-products [M, 16] of the block being back-propagated
     float *dx32, *dxn32, *skinny_ws;
     float *cls_dx32, *cls_dxn32; __half *cls_dy16, *cls_dh16, *cls_do16;

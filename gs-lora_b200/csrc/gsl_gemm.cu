@@ -43,6 +43,7 @@ struct GemmParams {
     const float* table;   // EPI_PERIODIC_F32: fp32 [period, ld_table]
     int period, ld_table;
     int has_out1;         // EPI_F32: also emit an fp16 copy through tmO1
+    float* rowdot;        // EPI_F16_ROWDOT: [2][M / period][N / 64][period]
     uint32_t drop_thresh; // round(p * 32768) (0 = no dropout)
     DropSeed drop_seed;
     float drop_scale;     // 1 / (1 - p)
@@ -57,6 +58,7 @@ template <> struct EpiTraits<EPI_GELU>         { static constexpr int O0 = 2, O1
 template <> struct EpiTraits<EPI_GELU_BWD>     { static constexpr int O0 = 2, O1 = 0, AUX = 2; };
 template <> struct EpiTraits<EPI_RES_F32>      { static constexpr int O0 = 4, O1 = 0, AUX = 4; };
 template <> struct EpiTraits<EPI_PERIODIC_F32> { static constexpr int O0 = 4, O1 = 0, AUX = 0; };
+template <> struct EpiTraits<EPI_F16_ROWDOT>   { static constexpr int O0 = 2, O1 = 0, AUX = 2; };
 
 static constexpr int EPI_GROUPS = 2;                      // two independent epilogue groups work on alternate stripes
 static constexpr int EPI_GROUP_WARPS = 8;                 // per group: two warps per TMEM lane quarter, each takes half of a stripe's columns
@@ -337,6 +339,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         v[4 * j + 3] = mul2(v[4 * j + 3], unpack_half2(h3));
                     }
                 }
+                if (EPI == EPI_F16_ROWDOT) {   // dot product of this thread's 32 accumulator columns with the aux stripe (fp16 [128 x 64]) -> rowdot part `half`
+                    const uint32_t aux_buf = aux_base + (aux_it % Cfg::AUX_DEPTH) * Cfg::AUX_BUF;
+                    mbar_wait(aux_bar(grp * 2 + (aux_it % Cfg::AUX_DEPTH)), (aux_it / Cfg::AUX_DEPTH) & 1);
+                    ++aux_it;
+                    float2 d = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t h0, h1, h2, h3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(aux_buf + sw128_off(row, half * 4 + j)));
+                        d = fma2(v[4 * j], unpack_half2(h0), d);
+                        d = fma2(v[4 * j + 1], unpack_half2(h1), d);
+                        d = fma2(v[4 * j + 2], unpack_half2(h2), d);
+                        d = fma2(v[4 * j + 3], unpack_half2(h3), d);
+                    }
+                    const int r = m_base + (int)row;
+                    if (r < p.M && n0 < p.N) {
+                        const int period = p.period > 0 ? p.period : p.M, nseg = p.N >> 6;
+                        p.rowdot[(size_t)half * p.M * nseg + ((size_t)(r / period) * nseg + (n0 >> 6)) * period + (r % period)] = d.x + d.y;
+                    }
+                }
                 if (EPI == EPI_PERIODIC_F32) {
                     const int r = m_base + (int)row;
                     if (r < p.M) {
@@ -526,6 +549,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.table = (EPI == EPI_PERIODIC_F32) ? reinterpret_cast<const float*>(a.aux) : nullptr;
     p.period = (int)a.aux_period; p.ld_table = (int)a.ldaux;
     p.has_out1 = has_o1 ? 1 : 0;
+    p.rowdot = a.rowdot;
     p.drop_thresh = drop_thresh15(a.drop_p);
     p.drop_seed = a.drop_seed;
     p.drop_scale = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
@@ -566,6 +590,7 @@ static int dispatch_epi(const GemmArgs& a, cudaStream_t s) {
         case EPI_GELU_BWD: return launch_gemm<CG, BN, EPI_GELU_BWD, SPLIT>(a, s);
         case EPI_RES_F32: return launch_gemm<CG, BN, EPI_RES_F32, SPLIT>(a, s);
         case EPI_PERIODIC_F32: return launch_gemm<CG, BN, EPI_PERIODIC_F32, SPLIT>(a, s);
+        case EPI_F16_ROWDOT: return launch_gemm<CG, BN, EPI_F16_ROWDOT, SPLIT>(a, s);
         default: set_last_error("unknown GEMM epilogue %d", a.epi); return -1;
     }
 }
@@ -579,7 +604,8 @@ int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
     GSL_REQUIRE(a.A && a.B && a.out0, "null GEMM operand");
     GSL_REQUIRE(a.drop_p >= 0.f && a.drop_p < 1.f && (a.drop_p == 0.f || a.M * a.N < (int64_t)4294967296LL), "bad dropout p / tensor too large for the 32-bit mask counter");
     if (a.epi == EPI_GELU) GSL_REQUIRE(a.out1 != nullptr, "EPI_GELU needs out1");
-    if (a.epi == EPI_GELU_BWD || a.epi == EPI_RES_F32 || a.epi == EPI_PERIODIC_F32) GSL_REQUIRE(a.aux != nullptr, "epilogue %d needs aux", a.epi);
+    if (a.epi == EPI_GELU_BWD || a.epi == EPI_RES_F32 || a.epi == EPI_PERIODIC_F32 || a.epi == EPI_F16_ROWDOT) GSL_REQUIRE(a.aux != nullptr, "epilogue %d needs aux", a.epi);
+    if (a.epi == EPI_F16_ROWDOT) GSL_REQUIRE(a.rowdot != nullptr && a.N % 64 == 0 && (a.aux_period == 0 || a.M % a.aux_period == 0), "EPI_F16_ROWDOT needs rowdot, N %% 64 == 0 and M %% aux_period == 0");
     if (a.epi == EPI_PERIODIC_F32) GSL_REQUIRE(a.aux_period > 0, "EPI_PERIODIC_F32 needs aux_period > 0");
     const int cg = a.cta_group ? a.cta_group : g_default_cta_group;
     const int bn = a.block_n ? a.block_n : ((a.N % 256 == 0 || a.N > 1024) ? 256 : 128);

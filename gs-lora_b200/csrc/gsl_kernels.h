@@ -17,6 +17,8 @@ enum GemmEpi {
     EPI_GELU_BWD = 3,      // out0(fp16) = acc * aux(fp16)                                  (dH = dG * [mask * gelu'(h)] saved by EPI_GELU)
     EPI_RES_F32 = 4,       // out0(fp32) = acc + bias + aux(fp32)                            (residual adds)
     EPI_PERIODIC_F32 = 5,  // out0(fp32) = acc + aux_table(fp32)[row % period]             (patch embed + pos/cls)
+    EPI_F16_ROWDOT = 6,    // out0(fp16) = acc ; rowdot = per-row, per-64-column dot products of acc with aux(fp16), as two 32-column partial
+                           // sums (dO = dY Wo with delta = rowsum(dO * O) per head for the attention backward)
 };
 
 struct GemmArgs {
@@ -29,6 +31,8 @@ struct GemmArgs {
     void* out0 = nullptr; int64_t ld0 = 0;
     void* out1 = nullptr; int64_t ld1 = 0;
     const void* aux = nullptr; int64_t ldaux = 0; int64_t aux_period = 0;
+    float* rowdot = nullptr;   // EPI_F16_ROWDOT: [2][M / period][N / 64][period] fp32 (period = aux_period, or M when 0): part h holds the dot products over
+                               // columns [64 c + 32 h, 64 c + 32 h + 32); the consumer adds the two parts
     int cta_group = 0;   // 0 = library default, 1 or 2
     int block_n = 0;     // 0 = auto, 128 or 256
     float drop_p = 0.f;  // dropout on the produced value (before the residual add; on both outputs of EPI_GELU)
@@ -79,7 +83,8 @@ int fill_zero(void* ptr, size_t bytes, cudaStream_t s);
 // ---- attention (gsl_attention_fwd.cu / gsl_attention_bwd.cu, tcgen05); qkv fp16 [B*N, ld] with q|k|v column blocks of heads*64
 int attention_fwd(const __half* qkv, int64_t ld, __half* out, int64_t ldo, float* lse, int B, int N, int heads, float scale, cudaStream_t s);
 int attention_bwd(const __half* qkv, int64_t ld, const __half* out, int64_t ldo, const __half* dout, int64_t lddo, const float* lse,
-                  __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s);
+                  __half* dqkv, int64_t lddqkv, int B, int N, int heads, float scale, cudaStream_t s,
+                  const float* delta_parts = nullptr);   // [2][B, heads, N]: delta = rowsum(dO * O) per head as the two partial sums of EPI_F16_ROWDOT (then `out` is unused)
 
 // ---- last-block shortcut: single (cls) query attention + cls-row gather / scatter (gsl_clsattn.cu)
 int cls_attention_fwd(const __half* qkv, int64_t ld, __half* o_cls, int64_t ldo, float* lse_cls, int B, int N, int heads, float scale, cudaStream_t s);

@@ -78,6 +78,7 @@ def _declare(L):
         "gsl_lora_side": [P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int, c_float, c_int, c_int64, c_int, c_int, P, c_size_t, P],
         "gsl_attention_fwd": [P, c_int64, P, c_int64, P, c_int, c_int, c_int, c_float, P],
         "gsl_attention_bwd": [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, c_int, c_int, c_float, P],
+        "gsl_attention_bwd_rowdot": [P, c_int64, P, c_int64, P, P, P, c_int64, c_int, c_int, c_int, c_float, P],
         "gsl_cast_f32_to_f16": [P, c_int64, P, c_int64, c_int64, c_int64, c_float, c_int, P],
         "gsl_grouplasso_adamw_step": [P, P, P, P, P, c_int, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P, P],
         "gsl_tensor_norms": [P, P, c_int, c_int, P, P],
@@ -117,7 +118,7 @@ def _declare(L):
 
 
 EXPORTS = ["gsl_last_error", "gsl_version", "gsl_launch_count", "gsl_set_gemm_cta_group", "gsl_gemm_f16", "gsl_patchify_f16", "gsl_layernorm_fwd",
-           "gsl_layernorm_bwd", "gsl_lora_down", "gsl_skinny_tn_workspace", "gsl_skinny_tn", "gsl_lora_side_workspace", "gsl_lora_side", "gsl_attention_fwd", "gsl_attention_bwd",
+           "gsl_layernorm_bwd", "gsl_lora_down", "gsl_skinny_tn_workspace", "gsl_skinny_tn", "gsl_lora_side_workspace", "gsl_lora_side", "gsl_attention_fwd", "gsl_attention_bwd", "gsl_attention_bwd_rowdot",
            "gsl_cast_f32_to_f16", "gsl_grouplasso_adamw_step", "gsl_tensor_norms", "gsl_engine_workspace_bytes", "gsl_engine_create",
            "gsl_engine_destroy", "gsl_engine_bind_params", "gsl_engine_refresh_frozen", "gsl_engine_refresh_lora", "gsl_engine_forward",
            "gsl_engine_backward", "gsl_engine_slot_ptr", "gsl_engine_lora_offset", "gsl_engine_lora_numel", "gsl_loss_sums",
@@ -151,7 +152,7 @@ def cur_stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-EPI_F16, EPI_F32, EPI_GELU, EPI_GELU_BWD, EPI_RES_F32, EPI_PERIODIC_F32 = range(6)
+EPI_F16, EPI_F32, EPI_GELU, EPI_GELU_BWD, EPI_RES_F32, EPI_PERIODIC_F32, EPI_F16_ROWDOT = range(7)
 
 
 def gemm_f16(A, B, *, epi=EPI_F16, bias=None, out0, out1=None, aux=None, aux_period=0, K=None, N=None, M=None,

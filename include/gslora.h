@@ -31,7 +31,9 @@ enum {
   GSL_EPI_GELU = 2,         /* h = acc + bias: out1 fp16 = Dropout(gelu_erf(h)), out0 fp16 = d out1/d h */
   GSL_EPI_GELU_BWD = 3,     /* out0 fp16 = acc * aux fp16  (aux = out0 of GSL_EPI_GELU)             */
   GSL_EPI_RES_F32 = 4,      /* out0 fp32 = acc + bias + aux fp32                                    */
-  GSL_EPI_PERIODIC_F32 = 5  /* out0 fp32 = acc + aux_table fp32[row % aux_period]                   */
+  GSL_EPI_PERIODIC_F32 = 5, /* out0 fp32 = acc + aux_table fp32[row % aux_period]                   */
+  GSL_EPI_F16_ROWDOT = 6    /* out0 fp16 = acc; out1 = fp32 [2][M / period][N / 64][period] (period = aux_period, M when 0): per row and per 64-column
+                               block the dot product of acc with aux fp16, as the partial sums over the block's two 32-column halves */
 };
 
 /* C[M,N] = epi(A[M,K] * B[N,K]^T), fp16 operands, fp32 accumulation on tcgen05 tensor cores.
@@ -96,6 +98,10 @@ int gsl_lora_side_split(const void* L16, int64_t ldl, const void* P32, int64_t l
 int gsl_attention_fwd(const void* qkv16, int64_t ld, void* out16, int64_t ldo, float* lse, int B, int N, int heads, float scale, void* stream);
 int gsl_attention_bwd(const void* qkv16, int64_t ld, const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
                       void* dqkv16, int64_t lddqkv, int B, int N, int heads, float scale, void* stream);
+/* The same with delta = rowsum(dO * O) per (image, head, token) precomputed: rowdot = out1 of the GSL_EPI_F16_ROWDOT GEMM that produced dO
+   (M = B*N rows, aux = the forward's attention output, aux_period = N), fp32 [2][B, heads, N]; the kernel adds the two parts. */
+int gsl_attention_bwd_rowdot(const void* qkv16, int64_t ld, const void* dout16, int64_t lddo, const float* lse, const float* rowdot,
+                             void* dqkv16, int64_t lddqkv, int B, int N, int heads, float scale, void* stream);
 /* fp32 -> fp16 cast (optional scale / transpose) used to build the frozen-weight operand caches. */
 int gsl_cast_f32_to_f16(const float* src, int64_t lds, void* dst16, int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose, void* stream);
 /* split form: dst16 = fp16(v), dst_lo16 = fp16(v - dst16), v = src * scale (the operand pair of gsl_gemm_f16_split) */

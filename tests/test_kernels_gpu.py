@@ -156,6 +156,42 @@ def test_attention_fwd_bwd(F, B, N, heads, scale):
         assert rel(dqkv[:, i * D:(i + 1) * D].float(), q32.grad[:, i * D:(i + 1) * D]) < 4e-3, name
 
 
+@pytest.mark.parametrize("B,N,heads,scale,split", [(3, 197, 8, 512 ** -0.5, True), (2, 26, 2, 128 ** -0.5, False), (5, 50, 4, 0.2, True)])
+def test_rowdot_epilogue_feeds_attention_bwd(F, B, N, heads, scale, split):
+    """EPI_F16_ROWDOT: dO = dY Wo^T with delta = rowsum(dO * O) per (image, head, token) as two partial sums; gsl_attention_bwd_rowdot with those
+    equals gsl_attention_bwd computing delta itself (autograd of Attention.forward, vit_face.py:358-379)."""
+    torch.manual_seed(11)
+    D = heads * 64
+    M = B * N
+    qkv = torch.randn(M, 3 * D, device="cuda").half()
+    out = torch.empty(M, D, device="cuda", dtype=torch.half); lse = torch.empty(B * heads * N, device="cuda")
+    F.check(F.lib().gsl_attention_fwd(F.ptr(qkv), 3 * D, F.ptr(out), D, F.ptr(lse), B, N, heads, scale, F.cur_stream()))
+    dy = (torch.randn(M, D, device="cuda") * 0.5).half()
+    w = torch.randn(D, D, device="cuda") * 0.05
+    w_hi = w.half(); w_lo = (w - w_hi.float()).half()
+    do16 = torch.empty(M, D, device="cuda", dtype=torch.half)
+    parts = torch.full((2, B, heads, N), float("nan"), device="cuda")
+    F.gemm_f16(dy, w_hi, B_lo=w_lo if split else None, epi=F.EPI_F16_ROWDOT, out0=do16, out1=parts, aux=out, aux_period=N)
+    do_ref = dy.float() @ (w if split else w_hi.float()).t()
+    assert rel(do16.float(), do_ref) < 1e-3
+    delta_ref = (do_ref * out.float()).view(B, N, heads, 64).sum(-1).permute(0, 2, 1)          # [B, heads, N]
+    assert not torch.isnan(parts).any()
+    assert rel(parts.sum(0), delta_ref) < 1e-4
+    half_ref = (do_ref * out.float()).view(B, N, heads, 2, 32).sum(-1).permute(3, 0, 2, 1)    # [2, B, heads, N]
+    assert rel(parts, half_ref) < 1e-4
+    dq_a = torch.empty(M, 3 * D, device="cuda", dtype=torch.half); dq_b = torch.empty_like(dq_a)
+    F.check(F.lib().gsl_attention_bwd(F.ptr(qkv), 3 * D, F.ptr(out), D, F.ptr(do16), D, F.ptr(lse), F.ptr(dq_a), 3 * D, B, N, heads, scale, F.cur_stream()))
+    F.check(F.lib().gsl_attention_bwd_rowdot(F.ptr(qkv), 3 * D, F.ptr(do16), D, F.ptr(lse), F.ptr(parts), F.ptr(dq_b), 3 * D, B, N, heads, scale,
+                                             F.cur_stream()))
+    assert rel(dq_b.float(), dq_a.float()) < 1e-3
+    q32 = qkv.float().requires_grad_(True)
+    q, k, v = [t.reshape(B, N, heads, 64).permute(0, 2, 1, 3) for t in q32.chunk(3, dim=-1)]
+    ref = torch.einsum("bhij,bhjd->bhid", (torch.einsum("bhid,bhjd->bhij", q, k) * scale).softmax(-1), v).permute(0, 2, 1, 3).reshape(M, D)
+    ref.backward(do16.float())
+    for i, name in enumerate("qkv"):
+        assert rel(dq_b[:, i * D:(i + 1) * D].float(), q32.grad[:, i * D:(i + 1) * D]) < 4e-3, name
+
+
 def test_grouplasso_adamw_matches_torch(F):
     torch.manual_seed(4)
     G, n_per = 6, 40960
