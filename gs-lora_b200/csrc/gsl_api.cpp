@@ -59,6 +59,20 @@ int gsl_gemm_f16_split(const void* A, int64_t lda, const void* B, const void* B_
     return gemm_f16(a, (cudaStream_t)stream);
 }
 
+int gsl_gemm_f16_split8(const void* A, int64_t lda, const void* B, const void* B_lo8, int shift, int64_t ldb, int64_t M, int64_t N, int64_t K, int epi,
+                        const float* bias, void* out0, int64_t ld0, void* out1, int64_t ld1, const void* aux, int64_t ldaux,
+                        int64_t aux_period, int block_n, float drop_p, uint32_t drop_seed, void* stream) {
+    if (B_lo8 == nullptr) { set_last_error("gsl_gemm_f16_split8: B_lo8 is null"); return -1; }
+    GemmArgs a;
+    a.A = (const __half*)A; a.lda = lda; a.B = (const __half*)B; a.B_lo8 = (const uint8_t*)B_lo8; a.lo8_shift = shift; a.ldb = ldb;
+    a.M = M; a.N = N; a.K = K; a.epi = epi; a.bias = bias;
+    a.out0 = out0; a.ld0 = ld0; a.out1 = out1; a.ld1 = ld1;
+    a.aux = aux; a.ldaux = ldaux; a.aux_period = aux_period;
+    if (epi == EPI_F16_ROWDOT) { a.rowdot = (float*)out1; a.out1 = nullptr; }
+    a.cta_group = 2; a.block_n = block_n; a.drop_p = drop_p; a.drop_seed = drop_seed;
+    return gemm_f16(a, (cudaStream_t)stream);
+}
+
 #define ST(x) ((cudaStream_t)(x))
 
 int gsl_patchify_f16(const float* img, void* out, int64_t ld, int B, int C, int S, int patch, int order, void* stream) {
@@ -118,6 +132,11 @@ int gsl_attention_bwd_rowdot(const void* qkv16, int64_t ld, const void* dout16, 
 int gsl_cast_f32_to_f16(const float* src, int64_t lds, void* dst16, int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose,
                         void* stream) {
     return cast_f32_to_f16(src, lds, (__half*)dst16, ldd, rows, cols, scale, transpose, ST(stream));
+}
+int gsl_cast_f32_to_f16_split8(const float* src, int64_t lds, void* dst16, void* dst_lo8, int64_t ldd, int64_t rows, int64_t cols, int shift,
+                               int transpose, void* stream) {
+    if (shift < 0 || shift > 24) { set_last_error("gsl_cast_f32_to_f16_split8: shift %d outside [0, 24]", shift); return -1; }
+    return cast_f32_to_f16(src, lds, (__half*)dst16, ldd, rows, cols, ldexpf(1.0f, shift), transpose, ST(stream), nullptr, (uint8_t*)dst_lo8);
 }
 int gsl_cast_f32_to_f16_split(const float* src, int64_t lds, void* dst16, void* dst_lo16, int64_t ldd, int64_t rows, int64_t cols, float scale,
                               int transpose, void* stream) {

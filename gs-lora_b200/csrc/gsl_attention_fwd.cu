@@ -62,7 +62,7 @@ __device__ long long g_af_trace[16 * 64 * 4];
 
 enum : uint32_t {   // mbarrier indices (+ parity / buffer)
     F_FULL_Q = 0, F_FREE_Q = 2, F_FULL_K = 4, F_FREE_K = 6, F_FULL_V = 8, F_FREE_V = 10,
-    F_S_FULL = 12, F_P_READY = 14, F_O_FULL = 16, F_O_FREE = 18, F_COUNT = 20
+    F_S_FULL = 12, F_P_READY = 14, F_O_FULL = 16, F_O_FREE = 18, F_STATS_READY = 20, F_STATS_FREE = 22, F_COUNT = 24
 };
 
 __device__ __forceinline__ uint64_t af_desc(uint32_t smem_addr) {      // 128-byte rows, 128B swizzle, 8-row atoms of 1024 bytes
@@ -175,7 +175,10 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
             tma_prefetch_desc(&tmQ0); tma_prefetch_desc(&tmQ1); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmO);
             for (uint32_t i = 0; i < F_COUNT; ++i) mbar_init(bar(i), 1);
             // worker / writer barriers count WARPS (one elected lane arrives after __syncwarp)
-            for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar(F_P_READY + i), AF_GROUP_WARPS); mbar_init(bar(F_O_FREE + i), AF_WRITER_WARPS); }
+            for (uint32_t i = 0; i < 2; ++i) {
+                mbar_init(bar(F_P_READY + i), AF_GROUP_WARPS); mbar_init(bar(F_O_FREE + i), AF_WRITER_WARPS);
+                mbar_init(bar(F_STATS_READY + i), AF_GROUP_WARPS); mbar_init(bar(F_STATS_FREE + i), AF_WRITER_WARPS);
+            }
             fence_mbar_init();
         }
         __syncwarp();
@@ -324,12 +327,15 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
                 }
                 af_st_wait();
                 AF_TRACE(warp, j, 3);
-                s_sum[g * 128 + rl] = sum;          // row statistics for the writers (their slots were released with O_FREE of item j - 2,
-                s_rowmax[g * 128 + rl] = mx;        //  which the issuer waited for before this item's scores existed)
+                // row statistics for the writers, handed over through their own barrier pair: the P_READY -> MMA -> tcgen05.commit -> O_FULL chain
+                // orders them too, but only through the tensor core's asynchronous arrival (compute-sanitizer racecheck cannot follow that)
+                if (u >= 1) mbar_wait(bar(F_STATS_FREE + g), (u - 1) & 1);
+                s_sum[g * 128 + rl] = sum;
+                s_rowmax[g * 128 + rl] = mx;
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(F_P_READY + g));         // (release: P and the statistics are ordered before the P V MMAs and O_FULL)
+            if (lane == 0) { mbar_arrive(bar(F_STATS_READY + g)); mbar_arrive(bar(F_P_READY + g)); }
         }
     } else if (warp < AF_W_PROD) {
         // ===================================================== output writers: thread = one row of the [128 x 64] O tile
@@ -349,9 +355,12 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_c
             mbar_wait(bar(F_O_FULL + pb), (jj >> 1) & 1);
             tcgen05_fence_after();
             AF_TRACE(warp, jj, 0);
+            mbar_wait(bar(F_STATS_READY + pb), (jj >> 1) & 1);
             const float sum = rows_on ? s_sum[pb * 128 + rl] : 1.f;
             const float mx = rows_on ? s_rowmax[pb * 128 + rl] : 0.f;
             const float inv = 1.0f / sum;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(F_STATS_FREE + pb));
             if (elected) tma_store_wait_read<1>();      // the store of item jj - 2 has finished reading this staging tile
             asm volatile("bar.sync 2, %0;" ::"n"(AF_WRITERS) : "memory");
 #pragma unroll

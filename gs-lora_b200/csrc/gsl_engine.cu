@@ -9,6 +9,7 @@
 //   transient gradient buffers shared by all slots.
 #include "gsl_engine.h"
 #include "gsl_common.cuh"
+#include <cuda_fp8.h>
 
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +17,11 @@
 namespace gsl {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline void set_b(GemmArgs& g, const WOp& w) { g.B = w.hi; g.B_lo = w.lo; g.B_lo8 = w.lo8; g.lo8_shift = w.lo8 ? GSL_LO8_SHIFT : 0; }
+// frozen weight -> cached operand in the engine's precision mode (optionally transposed)
+static int cast_w(const float* src, int64_t lds, const WOp& w, int64_t ldd, int64_t rows, int64_t cols, int transpose, cudaStream_t s) {
+    return cast_f32_to_f16(src, lds, w.hi, ldd, rows, cols, w.lo8 ? ldexpf(1.0f, GSL_LO8_SHIFT) : 1.f, transpose, s, w.lo, w.lo8);
+}
 
 int64_t Engine::lora_block_elems() const {
     const int64_t r = cfg.lora_rank, D = cfg.dim, H = cfg.mlp_dim, inner = (int64_t)cfg.heads * 64;
@@ -44,26 +50,28 @@ size_t Engine::carve(bool assign) {
     const int64_t D = cfg.dim, H = cfg.mlp_dim, L = cfg.depth, C = cfg.num_class, Bm = cfg.max_batch;
     const int64_t inner = (int64_t)cfg.heads * 64;
     const int64_t M = Bm * tokens;
-    const bool split = cfg.precision == 1;
-    auto take_w = [&](size_t elems) -> WOp {        // one cached B operand: hi [, lo]
+    auto take_w = [&](size_t elems, int precision) -> WOp {        // one cached B operand: hi [, lo | lo8]
         WOp w;
         w.hi = (__half*)take(elems * 2);
-        w.lo = split ? (__half*)take(elems * 2) : nullptr;
+        w.lo = precision == 1 ? (__half*)take(elems * 2) : nullptr;
+        w.lo8 = precision == 2 ? (uint8_t*)take(elems) : nullptr;
         return w;
     };
-    const WOp pw = take_w((size_t)D * patch_dim);
+    const int wprec = cfg.precision;
+    const WOp pw = take_w((size_t)D * patch_dim, wprec == 2 ? 1 : wprec);   // patch embedding: K = patch_dim may not be a multiple of 64 -> fp16 residual
     auto* pb = (float*)take((size_t)tokens * D * 4);
     if (assign) { patch_w16 = pw; posb = pb; cache.assign(L, BlockCache()); }
     for (int l = 0; l < L; ++l) {
         BlockCache c;
-        c.qkv_w16 = take_w((size_t)3 * inner * D);
-        c.qkv_wT16 = take_w((size_t)D * 3 * inner);
-        c.out_w16 = take_w((size_t)D * inner);
-        c.out_wT16 = take_w((size_t)inner * D);
-        c.fc1_w16 = take_w((size_t)H * D);
-        c.fc1T_w16 = take_w((size_t)D * H);
-        c.fc2_w16 = take_w((size_t)D * H);
-        c.fc2T_w16 = take_w((size_t)H * D);
+        c.qkv_w16 = take_w((size_t)3 * inner * D, wprec);
+        c.qkv_wT16 = take_w((size_t)D * 3 * inner, wprec);
+        c.out_w16 = take_w((size_t)D * inner, wprec);
+        c.out_wT16 = take_w((size_t)inner * D, wprec);
+        c.fc1_w16 = take_w((size_t)H * D, wprec == 2 ? 1 : wprec);     // split8: the fc1 GEMM is epilogue-bound (GELU, two outputs) and measured 4 % faster
+                                                                       // with the fp16 residual (no converter warps, 112 instead of 96 registers per thread)
+        c.fc1T_w16 = take_w((size_t)D * H, wprec);
+        c.fc2_w16 = take_w((size_t)D * H, wprec);
+        c.fc2T_w16 = take_w((size_t)H * D, wprec);
         c.A1h = (__half*)take((size_t)32 * D * 2);
         c.A2h = (__half*)take((size_t)32 * H * 2);
         c.B1T = (__half*)take((size_t)32 * H * 2);
@@ -145,7 +153,8 @@ static int validate(const GslConfig& c) {
     GSL_REQUIRE(c.heads * 64 == c.dim || c.heads > 0, "bad heads");
     GSL_REQUIRE(c.lora_rank >= 1 && c.lora_rank <= 16, "lora_rank=%d: the rank-r side kernels hold r <= 16 (args.py --lora_rank)", c.lora_rank);
     GSL_REQUIRE(c.lora_pos == 0 || c.lora_pos == 1, "lora_pos=%d: 0 (FFN) or 1 (Attention)", c.lora_pos);
-    GSL_REQUIRE(c.precision == 0 || c.precision == 1, "precision=%d: 0 (fast: fp16 weights) or 1 (split: fp16 hi + lo weights)", c.precision);
+    GSL_REQUIRE(c.precision >= 0 && c.precision <= 2, "precision=%d: 0 (fast: fp16 weights), 1 (split: fp16 hi + lo weights) or 2 (split8: fp16 hi + e4m3 lo)", c.precision);
+    GSL_REQUIRE(c.precision != 2 || c.mlp_dim % 64 == 0, "precision split8 needs every GEMM K (dim, mlp_dim, 3 * heads * 64) to be a multiple of 64");
     GSL_REQUIRE((c.channels * c.patch_size * c.patch_size) % 16 == 0, "patch_dim must be a multiple of 16");
     GSL_REQUIRE(c.max_batch >= 1 && c.num_slots >= 1 && c.depth >= 1, "bad max_batch / num_slots / depth");
     const int tokens = (c.image_size / c.patch_size) * (c.image_size / c.patch_size) + 1;
@@ -202,7 +211,9 @@ int Engine::init(const GslConfig& c, void* workspace, size_t bytes) {
 struct MergeJob {
     const float *W, *A, *B;
     __half *out, *outT, *out_lo, *outT_lo;
+    uint8_t *out_lo8, *outT_lo8;        // split8: e4m3 residual of the 2^shift-scaled value
     int R, C, groups;
+    float s_out, s_outT;                // power-of-two pre-scale of each output (2^GSL_LO8_SHIFT where that output carries an e4m3 residual, else 1)
 };
 static constexpr int MERGE_JOB_SLOT = 128;
 __global__ void __launch_bounds__(256) merge_weights_kernel(const uint8_t* __restrict__ jobs_raw, int r, float sc) {
@@ -222,19 +233,22 @@ __global__ void __launch_bounds__(256) merge_weights_kernel(const uint8_t* __res
             for (int k = 0; k < r; ++k) d = fmaf(j.B[(int64_t)row * r + k], j.A[(int64_t)(a0 + k) * j.C + col], d);
             v = fmaf(sc, d, v);
         }
+        tile[ty + 8 * i][tx] = v;
+        v *= j.s_out;               // 1, or 2^shift where this output carries an e4m3 residual (exact)
         const __half hv = __float2half_rn(v);
         j.out[(int64_t)row * j.C + col] = hv;
         if (j.out_lo) j.out_lo[(int64_t)row * j.C + col] = __float2half_rn(v - __half2float(hv));
-        tile[ty + 8 * i][tx] = v;
+        if (j.out_lo8) j.out_lo8[(int64_t)row * j.C + col] = (uint8_t)__nv_cvt_float_to_fp8(v - __half2float(hv), __NV_SATFINITE, __NV_E4M3);
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int col = c0 + ty + 8 * i, row = r0 + tx;
-        const float v = tile[tx][ty + 8 * i];
+        const float v = tile[tx][ty + 8 * i] * j.s_outT;
         const __half hv = __float2half_rn(v);
         j.outT[(int64_t)col * j.R + row] = hv;
         if (j.outT_lo) j.outT_lo[(int64_t)col * j.R + row] = __float2half_rn(v - __half2float(hv));
+        if (j.outT_lo8) j.outT_lo8[(int64_t)col * j.R + row] = (uint8_t)__nv_cvt_float_to_fp8(v - __half2float(hv), __NV_SATFINITE, __NV_E4M3);
     }
 }
 
@@ -282,17 +296,21 @@ int Engine::bind_params(const void* const* p, int n, float* lora, float* grads) 
             MergeJob jq;
             jq.W = frozen[l].qkv_w; jq.A = lora_flat + lora_offset(l, 0); jq.B = lora_flat + lora_offset(l, 1);
             jq.out = cache[l].qkv_w16.hi; jq.outT = cache[l].qkv_wT16.hi; jq.out_lo = cache[l].qkv_w16.lo; jq.outT_lo = cache[l].qkv_wT16.lo;
+            jq.out_lo8 = cache[l].qkv_w16.lo8; jq.outT_lo8 = cache[l].qkv_wT16.lo8;
             jq.R = 3 * cfg.heads * 64; jq.C = cfg.dim; jq.groups = 3;
             jobs.push_back(jq);
         }
         j1.W = frozen[l].fc1_w; j1.A = attn_lora ? nullptr : lora_flat + lora_offset(l, 0); j1.B = attn_lora ? nullptr : lora_flat + lora_offset(l, 1);
         j1.out = cache[l].fc1_w16.hi; j1.outT = cache[l].fc1T_w16.hi; j1.out_lo = cache[l].fc1_w16.lo; j1.outT_lo = cache[l].fc1T_w16.lo;
+        j1.out_lo8 = cache[l].fc1_w16.lo8; j1.outT_lo8 = cache[l].fc1T_w16.lo8;
         j1.R = cfg.mlp_dim; j1.C = cfg.dim;
         j2.W = frozen[l].fc2_w; j2.A = attn_lora ? nullptr : lora_flat + lora_offset(l, 2); j2.B = attn_lora ? nullptr : lora_flat + lora_offset(l, 3);
         j2.out = cache[l].fc2_w16.hi; j2.outT = cache[l].fc2T_w16.hi; j2.out_lo = cache[l].fc2_w16.lo; j2.outT_lo = cache[l].fc2T_w16.lo;
+        j2.out_lo8 = cache[l].fc2_w16.lo8; j2.outT_lo8 = cache[l].fc2T_w16.lo8;
         j2.R = cfg.dim; j2.C = cfg.mlp_dim;
         jobs.push_back(j1); jobs.push_back(j2);
     }
+    for (MergeJob& j : jobs) { j.s_out = j.out_lo8 ? ldexpf(1.0f, GSL_LO8_SHIFT) : 1.0f; j.s_outT = j.outT_lo8 ? ldexpf(1.0f, GSL_LO8_SHIFT) : 1.0f; }
     static_assert(sizeof(MergeJob) <= MERGE_JOB_SLOT, "MergeJob slot");
     std::vector<uint8_t> raw(jobs.size() * MERGE_JOB_SLOT, 0);
     for (size_t i = 0; i < jobs.size(); ++i) memcpy(raw.data() + i * MERGE_JOB_SLOT, &jobs[i], sizeof(MergeJob));
@@ -313,17 +331,17 @@ int Engine::refresh_frozen(cudaStream_t s) {
     GSL_REQUIRE(params_bound, "bind_params first");
     const int D = cfg.dim, H = cfg.mlp_dim, inner = cfg.heads * 64;
     int rc;
-    if ((rc = cast_f32_to_f16(patch_w, patch_dim, patch_w16.hi, patch_dim, D, patch_dim, 1.f, 0, s, patch_w16.lo))) return rc;
+    if ((rc = cast_w(patch_w, patch_dim, patch_w16, patch_dim, D, patch_dim, 0, s))) return rc;
     posb_kernel<<<(tokens * D + 255) / 256, 256, 0, s>>>(pos_embedding, cls_token, patch_b, posb, tokens, D);
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     for (int l = 0; l < cfg.depth; ++l) {
         const BlockFrozen& f = frozen[l];
         BlockCache& c = cache[l];
-        if ((rc = cast_f32_to_f16(f.qkv_w, D, c.qkv_w16.hi, D, 3 * inner, D, 1.f, 0, s, c.qkv_w16.lo))) return rc;
-        if ((rc = cast_f32_to_f16(f.qkv_w, D, c.qkv_wT16.hi, 3 * inner, 3 * inner, D, 1.f, 1, s, c.qkv_wT16.lo))) return rc;
-        if ((rc = cast_f32_to_f16(f.out_w, inner, c.out_w16.hi, inner, D, inner, 1.f, 0, s, c.out_w16.lo))) return rc;
-        if ((rc = cast_f32_to_f16(f.out_w, inner, c.out_wT16.hi, D, D, inner, 1.f, 1, s, c.out_wT16.lo))) return rc;
+        if ((rc = cast_w(f.qkv_w, D, c.qkv_w16, D, 3 * inner, D, 0, s))) return rc;
+        if ((rc = cast_w(f.qkv_w, D, c.qkv_wT16, 3 * inner, 3 * inner, D, 1, s))) return rc;
+        if ((rc = cast_w(f.out_w, inner, c.out_w16, inner, D, inner, 0, s))) return rc;
+        if ((rc = cast_w(f.out_w, inner, c.out_wT16, D, D, inner, 1, s))) return rc;
         if ((rc = fill_zero(c.A1h, (size_t)32 * D * 2, s))) return rc;
         if ((rc = fill_zero(c.A2h, (size_t)32 * H * 2, s))) return rc;
         if ((rc = fill_zero(c.B1T, (size_t)32 * H * 2, s))) return rc;
@@ -385,9 +403,9 @@ int Engine::refresh_lora(cudaStream_t s) {
     const int per_block = (int)lora_block_elems();
     dim3 grid((per_block + 255) / 256, cfg.depth);
     if (cfg.lora_pos == 1)
-        lora_pack_attn_kernel<<<grid, 256, 0, s>>>(lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.heads * 64, cfg.lora_rank, per_block, cfg.precision == 1 ? 1 : 0);
+        lora_pack_attn_kernel<<<grid, 256, 0, s>>>(lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.heads * 64, cfg.lora_rank, per_block, cfg.precision >= 1 ? 1 : 0);
     else
-        GSL_CHECK_CUDA(launch_pdl(lora_pack_kernel, dim3(grid), dim3(256), 0, s, lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, per_block, cfg.precision == 1 ? 1 : 0));
+        GSL_CHECK_CUDA(launch_pdl(lora_pack_kernel, dim3(grid), dim3(256), 0, s, lora_flat, (const LoraPackPtrs*)pack_ptrs_dev, cfg.dim, cfg.mlp_dim, cfg.lora_rank, per_block, cfg.precision >= 1 ? 1 : 0));
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     if (ffn_cache_mode == 1) ffn_cache_mode = -1;       // W + s B A is stale
@@ -422,14 +440,14 @@ int Engine::ffn_forward(int l, int64_t M, __half* xn2, float* ln_mean, float* ln
     if ((rc = layernorm_fwd(x_mid, D, f.ln2_w, f.ln2_b, cfg.ln_eps, xn2, D, ln_mean, ln_rstd, M, D, s))) return rc;
     {
         GemmArgs g;
-        g.A = xn2; g.lda = D; g.B = c.fc1_w16.hi; g.B_lo = c.fc1_w16.lo; g.ldb = D; g.M = M; g.N = H; g.K = D;
+        g.A = xn2; g.lda = D; set_b(g, c.fc1_w16); g.ldb = D; g.M = M; g.N = H; g.K = D;
         g.epi = EPI_GELU; g.bias = f.fc1_b; g.out0 = gp16; g.ld0 = H; g.out1 = g16; g.ld1 = H;
         g.drop_p = pdrop; g.drop_seed = site(dseed, l, 2);
         if ((rc = gemm_f16(g, s))) return rc;
     }
     {
         GemmArgs g;
-        g.A = g16; g.lda = H; g.B = c.fc2_w16.hi; g.B_lo = c.fc2_w16.lo; g.ldb = H; g.M = M; g.N = D; g.K = H;
+        g.A = g16; g.lda = H; set_b(g, c.fc2_w16); g.ldb = H; g.M = M; g.N = D; g.K = H;
         g.epi = EPI_RES_F32; g.bias = f.fc2_b; g.out0 = x_out; g.ld0 = D; g.aux = x_mid; g.ldaux = D;
         g.drop_p = pdrop; g.drop_seed = site(dseed, l, 3);
         if ((rc = gemm_f16(g, s))) return rc;
@@ -457,7 +475,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
     if (rc) return rc;
     {   // patch_to_embedding + cls token + pos_embedding (vit_face.py:531-536)
         GemmArgs g;
-        g.A = patches16; g.lda = patch_dim; g.B = patch_w16.hi; g.B_lo = patch_w16.lo; g.ldb = patch_dim; g.M = M; g.N = D; g.K = patch_dim;
+        g.A = patches16; g.lda = patch_dim; set_b(g, patch_w16); g.ldb = patch_dim; g.M = M; g.N = D; g.K = patch_dim;
         g.epi = EPI_PERIODIC_F32; g.out0 = S.x[0]; g.ld0 = D; g.aux = posb; g.ldaux = D; g.aux_period = tokens;
         g.drop_p = pemb; g.drop_seed = site(dropout_seed, L, 0);
         if ((rc = gemm_f16(g, s))) return rc;
@@ -472,7 +490,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
         if ((rc = layernorm_fwd(x_in, D, f.ln1_w, f.ln1_b, cfg.ln_eps, xn1, D, a.ln1_mean, a.ln1_rstd, M, D, s))) return rc;
         {
             GemmArgs g;
-            g.A = xn1; g.lda = D; g.B = c.qkv_w16.hi; g.B_lo = c.qkv_w16.lo; g.ldb = D; g.M = M; g.N = 3 * inner; g.K = D;
+            g.A = xn1; g.lda = D; set_b(g, c.qkv_w16); g.ldb = D; g.M = M; g.N = 3 * inner; g.K = D;
             g.epi = EPI_F16; g.bias = f.qkv_b; g.out0 = a.qkv16; g.ld0 = 3 * inner;
             if ((rc = gemm_f16(g, s))) return rc;
         }
@@ -481,7 +499,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
             float* x_out = S.x[2 * l + 2];
             if ((rc = attention_fwd(a.qkv16, 3 * inner, a.o16, inner, a.lse, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
             GemmArgs g;
-            g.A = a.o16; g.lda = inner; g.B = c.out_w16.hi; g.B_lo = c.out_w16.lo; g.ldb = inner; g.M = M; g.N = D; g.K = inner;
+            g.A = a.o16; g.lda = inner; set_b(g, c.out_w16); g.ldb = inner; g.M = M; g.N = D; g.K = inner;
             g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = x_mid; g.ld0 = D; g.aux = x_in; g.ldaux = D;
             g.drop_p = pdrop; g.drop_seed = site(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
@@ -494,7 +512,7 @@ int Engine::forward(int slot, const void* img, int img_kind, const float* mean, 
             if ((rc = cls_attention_fwd(a.qkv16, 3 * inner, k.o16, inner, k.lse, B, tokens, cfg.heads, cfg.attn_scale, s))) return rc;
             if ((rc = copy_cls_rows(x_in, (int64_t)tokens * D * 4, k.xin32, (int64_t)D * 4, B, (int64_t)D * 4, s))) return rc;
             GemmArgs g;
-            g.A = k.o16; g.lda = inner; g.B = c.out_w16.hi; g.B_lo = c.out_w16.lo; g.ldb = inner; g.M = B; g.N = D; g.K = inner;
+            g.A = k.o16; g.lda = inner; set_b(g, c.out_w16); g.ldb = inner; g.M = B; g.N = D; g.K = inner;
             g.epi = EPI_RES_F32; g.bias = f.out_b; g.out0 = k.xmid32; g.ld0 = D; g.aux = k.xin32; g.ldaux = D;
             g.drop_p = pdrop; g.drop_seed = site(dropout_seed, l, 1);
             if ((rc = gemm_f16(g, s))) return rc;
@@ -525,7 +543,7 @@ int Engine::ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, fl
     float* gA2 = grad_flat + lora_offset(l, 2);
     float* gB2 = grad_flat + lora_offset(l, 3);
     int rc;
-    const int fold = cfg.precision == 1 ? 1 : 0;                // split mode: the rank-r operands carry their rounding residual too
+    const int fold = cfg.precision >= 1 ? 1 : 0;                // split mode: the rank-r operands carry their rounding residual too
     const bool ffn_lora = cfg.lora_pos == 0;
     if (ffn_lora) {
     if ((rc = lora_down(dy, D, c.B2T, D, u2_16, 16, M, D, r, s, fold))) return rc;                                                        // U2 = dY2 B2
@@ -534,7 +552,7 @@ int Engine::ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, fl
     }
     {   // dH = (dY2 W2') * d[Dropout(gelu(h))] / dh
         GemmArgs g;
-        g.A = dy; g.lda = D; g.B = c.fc2T_w16.hi; g.B_lo = c.fc2T_w16.lo; g.ldb = D; g.M = M; g.N = H; g.K = D;
+        g.A = dy; g.lda = D; set_b(g, c.fc2T_w16); g.ldb = D; g.M = M; g.N = H; g.K = D;
         g.epi = EPI_GELU_BWD; g.out0 = dh; g.ld0 = H; g.aux = gp16; g.ldaux = H;
         if ((rc = gemm_f16(g, s))) return rc;
     }
@@ -546,7 +564,7 @@ int Engine::ffn_backward(int l, int64_t M, __half* dy, float* dx, __half* dh, fl
     if (l == 0 && ffn_lora) return 0;       // nothing trainable below block 0's FFN (with LoRA on to_qkv block 0's attention still is)
     {   // dLN2 = dH W1'
         GemmArgs g;
-        g.A = dh; g.lda = H; g.B = c.fc1T_w16.hi; g.B_lo = c.fc1T_w16.lo; g.ldb = H; g.M = M; g.N = D; g.K = H;
+        g.A = dh; g.lda = H; set_b(g, c.fc1T_w16); g.ldb = H; g.M = M; g.N = D; g.K = H;
         g.epi = dxn_fp32() ? EPI_F32 : EPI_F16; g.out0 = dxn; g.ld0 = D;            // fp16: halves the traffic of the LayerNorm-backward pass that consumes it
         if ((rc = gemm_f16(g, s))) return rc;
     }
@@ -560,7 +578,7 @@ int Engine::attn_lora_grads(int l, int64_t M, const __half* dqkv, const __half* 
     const int D = cfg.dim, inner = cfg.heads * 64, r = cfg.lora_rank;
     const BlockCache& c = cache[l];
     const float wscale = cfg.lora_scaling / cfg.grad_scale;
-    const int fold = cfg.precision == 1 ? 1 : 0;
+    const int fold = cfg.precision >= 1 ? 1 : 0;
     float* gA = grad_flat + lora_offset(l, 0);      // [3r, D]
     float* gB = grad_flat + lora_offset(l, 1);      // [3 inner, r]
     int rc;
@@ -607,7 +625,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         if (l == 0 && !attn_lora) return 0;
         {   // dO (cls rows) = dY Wo
             GemmArgs g;
-            g.A = cls_dy16; g.lda = D; g.B = c.out_wT16.hi; g.B_lo = c.out_wT16.lo; g.ldb = D; g.M = B; g.N = inner; g.K = D;
+            g.A = cls_dy16; g.lda = D; set_b(g, c.out_wT16); g.ldb = D; g.M = B; g.N = inner; g.K = D;
             g.epi = EPI_F16; g.out0 = cls_do16; g.ld0 = inner;
             if ((rc = gemm_f16(g, s))) return rc;
         }
@@ -616,7 +634,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         if (l == 0) return 0;
         {   // dLN1 = dQKV Wqkv  (dense: dK / dV reach every token)
             GemmArgs g;
-            g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16.hi; g.B_lo = c.qkv_wT16.lo; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
+            g.A = dqkv16; g.lda = 3 * inner; set_b(g, c.qkv_wT16); g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
             g.epi = dxn_fp32() ? EPI_F32 : EPI_F16; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }
@@ -635,7 +653,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         // ---------------- attention: y = to_out(attn(to_qkv(LN1(x)))) + x
         {   // dO = dY Wo; the epilogue also emits delta = rowsum(dO * O) per (image, head, token) for the attention backward
             GemmArgs g;
-            g.A = dy16; g.lda = D; g.B = c.out_wT16.hi; g.B_lo = c.out_wT16.lo; g.ldb = D; g.M = M; g.N = inner; g.K = D;
+            g.A = dy16; g.lda = D; set_b(g, c.out_wT16); g.ldb = D; g.M = M; g.N = inner; g.K = D;
             g.epi = EPI_F16_ROWDOT; g.out0 = do16; g.ld0 = inner; g.aux = a.o16; g.ldaux = inner; g.aux_period = tokens; g.rowdot = attn_delta;
             if ((rc = gemm_f16(g, s))) return rc;
         }
@@ -645,7 +663,7 @@ int Engine::backward(int slot, const float* dlogits, const float* demb, int accu
         if (l == 0) break;      // block 0: to_qkv's LoRA is the last trainable thing on the way down
         {   // dLN1 = dQKV Wqkv
             GemmArgs g;
-            g.A = dqkv16; g.lda = 3 * inner; g.B = c.qkv_wT16.hi; g.B_lo = c.qkv_wT16.lo; g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
+            g.A = dqkv16; g.lda = 3 * inner; set_b(g, c.qkv_wT16); g.ldb = 3 * inner; g.M = M; g.N = D; g.K = 3 * inner;
             g.epi = dxn_fp32() ? EPI_F32 : EPI_F16; g.out0 = dxn32; g.ld0 = D;
             if ((rc = gemm_f16(g, s))) return rc;
         }

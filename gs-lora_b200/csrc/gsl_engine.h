@@ -13,10 +13,14 @@ struct BlockFrozen {            // fp32 parameters of one Transformer block (cal
 };
 
 // A cached GEMM B operand: `hi` = fp16(W); `lo` = fp16(W - hi) in precision mode "split" (cfg.precision = 1), else null.
-struct WOp {
-    __half* hi = nullptr;
-    __half* lo = nullptr;
+struct WOp {                    // one cached B operand of the GEMM family
+    __half* hi = nullptr;       // fp16(W)  (precision "split8": fp16(W * 2^GSL_LO8_SHIFT))
+    __half* lo = nullptr;       // precision "split": fp16(W - hi)
+    uint8_t* lo8 = nullptr;     // precision "split8": e4m3(W * 2^GSL_LO8_SHIFT - hi)
 };
+// split8: power-of-two pre-scale of the (hi, lo8) pair.  The residual of a weight in the binade 2^e is <= 2^(e - 11): with the shift it lands
+// in e4m3's normal range [2^-6, 448] for |W| from 2^-7 up to 16, and hi stays inside fp16 for |W| < 16 (ViT weights are O(0.01 .. 1)).
+static constexpr int GSL_LO8_SHIFT = 12;
 
 struct BlockCache {             // fp16 operand caches (engine workspace)
     WOp qkv_w16, qkv_wT16, out_w16, out_wT16;

@@ -15,6 +15,17 @@
 // (identical for every token of every step); with them exact to 2^-22 the LoRA gradients meet the 1e-3 parity bar
 // (DESIGN.md section 2), for +1 B tile of shared memory per stage and 2x the tensor-pipe work.
 //
+// SPLIT = 2 (precision mode "split8"): the residual term runs on the FP8 tensor path at twice the rate.  B_hi = fp16(W * 2^s) and
+// B_lo8 = e4m3(W * 2^s - B_hi) (the power-of-two pre-scale puts the residual, ~2^-12 |W|, into e4m3's range; the epilogue multiplies the
+// accumulator by 2^-s); two converter warps per CTA turn every fp16 A tile that lands in shared memory into an e5m2 copy (64-byte rows,
+// 64B swizzle), and each 64-wide k-block issues 4 x kind::f16 (A * B_hi^T, K = 16) + 2 x kind::f8f6f4 (A8 * B_lo8^T, K = 32) into the same
+// fp32 accumulator: 1.5x the tensor work of the plain GEMM instead of 2x.  The weight keeps ~15 significant bits (11 + e4m3's 4), the
+// error of the e5m2 activation copy only touches the 2^-12-sized residual term (2^-15 relative, random per element).
+// Measured (B200, M = 201 728): the K = 1536 / 2048 GEMMs with the light fp16 epilogue (4-stage operand ring) run 10-16 % faster than with
+// the fp16 residual and are tensor-bound again (90-92 % active); the GEMMs whose epilogue staging leaves 3 stages (fc2, dH) gain 1-3 %
+// (the TMA -> convert -> MMA chain is one hop longer), the epilogue-bound fc1 loses 4 % (the engine keeps the fp16 residual there).
+// Shared-memory bandwidth (TMA writes + converter + MMA operand reads = 112 KB per k-block) sits at ~85 % of its peak in both modes.
+//
 // Structure (persistent, warp specialised, 576 threads):
 //   warp 0    TMA producer      cp.async.bulk.tensor 128B-swizzled A/B tiles -> smem ring (mbarrier full/empty)
 //   warp 1    MMA issuer        one lane issues tcgen05.mma (cta_group::1 or ::2), accumulators in TMEM,
@@ -44,6 +55,7 @@ struct GemmParams {
     int period, ld_table;
     int has_out1;         // EPI_F32: also emit an fp16 copy through tmO1
     float* rowdot;        // EPI_F16_ROWDOT: [2][M / period][N / 64][period]
+    float acc_scale;      // split8: 2^-s, undoes the pre-scale of the (B_hi, B_lo8) pair on the accumulator
     uint32_t drop_thresh; // round(p * 32768) (0 = no dropout)
     DropSeed drop_seed;
     float drop_scale;     // 1 / (1 - p)
@@ -63,15 +75,19 @@ template <> struct EpiTraits<EPI_F16_ROWDOT>   { static constexpr int O0 = 2, O1
 static constexpr int EPI_GROUPS = 2;                      // two independent epilogue groups work on alternate stripes
 static constexpr int EPI_GROUP_WARPS = 8;                 // per group: two warps per TMEM lane quarter, each takes half of a stripe's columns
 static constexpr int EPI_WARPS = EPI_GROUPS * EPI_GROUP_WARPS;
-static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 
-template <int CG, int BN, int EPI, bool SPLIT = false>
+template <int CG, int BN, int EPI, int SPLIT = 0>
 struct GemmCfg {
     using T = EpiTraits<EPI>;
     static constexpr int A_STAGE = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_STAGE = (BN / CG) * BLOCK_K * 2;
-    static constexpr int NB = SPLIT ? 2 : 1;             // B tiles per stage: B_hi [, B_lo]
-    static constexpr int STAGE = A_STAGE + NB * B_STAGE;
+    static constexpr int A8_STAGE = SPLIT == 2 ? BLOCK_M * BLOCK_K : 0;                            // e5m2 copy of the A tile (split8)
+    static constexpr int B2_STAGE = SPLIT == 1 ? B_STAGE : SPLIT == 2 ? (BN / CG) * BLOCK_K : 0;   // B_lo tile: fp16, or e4m3 (split8)
+    static constexpr int A_STRIDE = A_STAGE + A8_STAGE;  // per stage: A tile [, A8 tile]
+    static constexpr int B_STRIDE = B_STAGE + B2_STAGE;  // per stage: B_hi tile [, B_lo tile]
+    static constexpr int STAGE = A_STRIDE + B_STRIDE;
+    static constexpr int CONV_WARPS = SPLIT == 2 ? 2 : 0;                                          // fp16 -> e5m2 converters of the A tiles
+    static constexpr int THREADS = 64 + EPI_WARPS * 32 + CONV_WARPS * 32;
     // the epilogue works on stripes of the 128 x BN accumulator: 64 columns when every output is fp16, 32 columns when
     // the main output is fp32 -- either way one 128-byte swizzle row per accumulator row, one TMA store per stripe.
     static constexpr int STRIPE = T::O0 == 2 ? 64 : 32;
@@ -88,6 +104,8 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE + EPI_TOTAL + BAR_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
     static_assert(STAGES >= (SPLIT ? 2 : 3), "not enough shared memory for the operand ring");
+    static_assert(SPLIT != 2 || CG == 2, "split8 is built for cta_group::2 only");
+    static_assert(A8_STAGE % 1024 == 0 && B2_STAGE % 1024 == 0, "operand tiles must stay 1024-byte aligned");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
     static_assert(O0_BUF % 1024 == 0 && (O1_BUF % 1024 == 0) && (AUX_BUF % 1024 == 0), "staging must keep 1024-byte alignment");
 };
@@ -116,8 +134,43 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float2 (&f)[CW / 2]
     }
 }
 
-template <int CG, int BN, int EPI, bool SPLIT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// fp16 -> e5m2 pairs (split8 converter warps)
+__device__ __forceinline__ uint32_t cvt_e5m2x4(uint32_t h01, uint32_t h23) {
+    uint16_t a, b;
+    asm("cvt.rn.satfinite.e5m2x2.f16x2 %0, %1;" : "=h"(a) : "r"(h01));
+    asm("cvt.rn.satfinite.e5m2x2.f16x2 %0, %1;" : "=h"(b) : "r"(h23));
+    return (uint32_t)a | ((uint32_t)b << 16);
+}
+// K-major operand tile with 64-byte rows (64 one-byte elements), 64B swizzle, 8-row atoms of 512 bytes
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+// instruction descriptor, kind::f8f6f4: D = F32, A = E5M2, B = E4M3, both K-major
+__device__ __host__ constexpr uint32_t umma_idesc_f8(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+template <int CTA_GROUP>
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CTA_GROUP == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+
+template <int CG, int BN, int EPI, int SPLIT>
+__global__ void __launch_bounds__((GemmCfg<CG, BN, EPI, SPLIT>::THREADS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
                     const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                     const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
@@ -129,15 +182,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t sA = smem_base;
-    const uint32_t sB = sA + S * Cfg::A_STAGE;              // per stage: B_hi tile [, B_lo tile]
-    const uint32_t sEpi = sB + S * Cfg::NB * Cfg::B_STAGE;
+    const uint32_t sB = sA + S * Cfg::A_STRIDE;             // sA: per stage A tile [, e5m2 copy]; sB: per stage B_hi tile [, B_lo tile]
+    const uint32_t sEpi = sB + S * Cfg::B_STRIDE;
     const uint32_t sBar = sEpi + Cfg::EPI_TOTAL;
     auto full_bar = [&](int i) { return sBar + 8u * i; };
     auto empty_bar = [&](int i) { return sBar + 8u * (S + i); };
     auto tfull_bar = [&](int i) { return sBar + 8u * (2 * S + i); };
     auto tempty_bar = [&](int i) { return sBar + 8u * (2 * S + 2 + i); };
     auto aux_bar = [&](int i) { return sBar + 8u * (2 * S + 4 + i); };      // [group][slot]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (sBar - smem_base) + 8 * (2 * S + 4 + 4));
+    auto afull_bar = [&](int i) { return sBar + 8u * (2 * S + 8 + i); };    // split8: this CTA's A tile of stage i has landed (local)
+    auto conv_bar = [&](int i) { return sBar + 8u * (3 * S + 8 + i); };     // split8: both CTAs' e5m2 copies of stage i are written (leader)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (sBar - smem_base) + 8 * (4 * S + 8));
+    static_assert(8 * (4 * S + 8) + 4 <= Cfg::BAR_BYTES, "barrier block");
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
@@ -165,6 +221,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_init(tempty_bar(i), CG * EPI_WARPS);          // one elected lane per epilogue warp of the pair
             }
             for (int i = 0; i < 4; ++i) mbar_init(aux_bar(i), 1);
+            if (SPLIT == 2)
+                for (int i = 0; i < S; ++i) { mbar_init(afull_bar(i), 1); mbar_init(conv_bar(i), CG * Cfg::CONV_WARPS); }
             fence_mbar_init();
         }
         __syncwarp();
@@ -192,10 +250,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int n_base = nt * BN + (int)cta_rank * (BN / CG);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    if (leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE * CG);
-                    tma_load_2d<CG>(&tmA, full_bar(stage), sA + stage * Cfg::A_STAGE, kb * BLOCK_K, m_base);
-                    tma_load_2d<CG>(&tmB, full_bar(stage), sB + stage * Cfg::NB * Cfg::B_STAGE, kb * BLOCK_K, n_base);
-                    if (SPLIT) tma_load_2d<CG>(&tmB2, full_bar(stage), sB + stage * Cfg::NB * Cfg::B_STAGE + Cfg::B_STAGE, kb * BLOCK_K, n_base);
+                    if (SPLIT == 2) {
+                        // the A tile reports to THIS CTA's barrier (its converter warps wait for it); the B tiles to the leader's
+                        mbar_arrive_expect_tx(afull_bar(stage), Cfg::A_STAGE);
+                        tma_load_2d<1>(&tmA, afull_bar(stage), sA + stage * Cfg::A_STRIDE, kb * BLOCK_K, m_base);
+                        if (leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::B_STRIDE * CG);
+                    } else {
+                        if (leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE * CG);
+                        tma_load_2d<CG>(&tmA, full_bar(stage), sA + stage * Cfg::A_STRIDE, kb * BLOCK_K, m_base);
+                    }
+                    tma_load_2d<CG>(&tmB, full_bar(stage), sB + stage * Cfg::B_STRIDE, kb * BLOCK_K, n_base);
+                    if (SPLIT) tma_load_2d<CG>(&tmB2, full_bar(stage), sB + stage * Cfg::B_STRIDE + Cfg::B_STAGE, kb * BLOCK_K, n_base);
                     if (!leader) mbar_arrive_cluster(full_bar(stage), 0);
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
@@ -216,24 +281,69 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
+                    if (SPLIT == 2) mbar_wait_cluster(conv_bar(stage), phase);   // A tiles landed in both CTAs and their e5m2 copies are written
                     tcgen05_fence_after();
                     if (lane == 0) {
-                        const uint64_t da = umma_desc_sw128(sA + stage * Cfg::A_STAGE);
-                        const uint64_t db = umma_desc_sw128(sB + stage * Cfg::NB * Cfg::B_STAGE);
-                        const uint64_t db2 = umma_desc_sw128(sB + stage * Cfg::NB * Cfg::B_STAGE + Cfg::B_STAGE);
+                        const uint64_t da = umma_desc_sw128(sA + stage * Cfg::A_STRIDE);
+                        const uint64_t db = umma_desc_sw128(sB + stage * Cfg::B_STRIDE);
                         const int krem = p.K - kb * BLOCK_K;
                         const int nk = krem >= BLOCK_K ? BLOCK_K / 16 : (krem + 15) / 16;   // ragged last k-block (K % 64 != 0)
+                        if (SPLIT == 2) {
+                            constexpr uint32_t idesc8 = umma_idesc_f8(BLOCK_M * CG, BN);
+                            const uint64_t da8 = umma_desc_sw64(sA + stage * Cfg::A_STRIDE + Cfg::A_STAGE);
+                            const uint64_t db8 = umma_desc_sw64(sB + stage * Cfg::B_STRIDE + Cfg::B_STAGE);
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 16; ++k) {
-                            if (k < nk) {
-                                umma_f16<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                                if (SPLIT) umma_f16<CG>(d_tmem, da + 2 * k, db2 + 2 * k, idesc, 1u);     // + A * B_lo^T on the same A tile
+                            for (int k = 0; k < BLOCK_K / 16; ++k) umma_f16<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 32; ++k) umma_f8<CG>(d_tmem, da8 + 2 * k, db8 + 2 * k, idesc8, 1u);    // + A8 * B_lo8^T (K = 32 per MMA)
+                        } else {
+                            const uint64_t db2 = umma_desc_sw128(sB + stage * Cfg::B_STRIDE + Cfg::B_STAGE);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                if (k < nk) {
+                                    umma_f16<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                    if (SPLIT == 1) umma_f16<CG>(d_tmem, da + 2 * k, db2 + 2 * k, idesc, 1u);     // + A * B_lo^T on the same A tile
+                                }
                             }
                         }
                         umma_commit<CG>(empty_bar(stage));                 // smem stage free once these MMAs retire
                         if (kb == num_kb - 1) umma_commit<CG>(tfull_bar(acc));   // accumulator complete
                     }
                     __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 2 + EPI_WARPS) {
+        // ===================================================== split8 converter warps: fp16 A tile -> e5m2 copy, stage by stage
+        // task = (row, 16-byte output chunk): 32 bytes of fp16 (two 16-byte chunks of the 128B-swizzled row) -> 16 e5m2 bytes of the
+        // 64B-swizzled row; lanes 4 r .. 4 r + 3 cover one row, so a warp reads 1 KB of contiguous rows per pass
+        if constexpr (SPLIT == 2) {
+            const int ct = (int)(warp - (2 + EPI_WARPS)) * 32 + (int)lane;         // 0 .. 63
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(afull_bar(stage), phase);
+                    const uint32_t src = sA + stage * Cfg::A_STRIDE, dst = src + Cfg::A_STAGE;
+                    constexpr int NTASK = (BLOCK_M * 4) / (Cfg::CONV_WARPS * 32);
+                    uint32_t q[NTASK][8];
+#pragma unroll
+                    for (int i = 0; i < NTASK; ++i) {       // all loads first: issued one task at a time the ld -> cvt -> st chains run serially
+                        const uint32_t task = (uint32_t)(i * Cfg::CONV_WARPS * 32 + ct), row = task >> 2, oc = task & 3;    // (~500 clk per tile: +40 % GEMM time)
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q[i][0]), "=r"(q[i][1]), "=r"(q[i][2]), "=r"(q[i][3]) : "r"(src + sw128_off(row, 2 * oc)));
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q[i][4]), "=r"(q[i][5]), "=r"(q[i][6]), "=r"(q[i][7]) : "r"(src + sw128_off(row, 2 * oc + 1)));
+                    }
+#pragma unroll
+                    for (int i = 0; i < NTASK; ++i) {
+                        const uint32_t task = (uint32_t)(i * Cfg::CONV_WARPS * 32 + ct), row = task >> 2, oc = task & 3;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + sw64_off(row, oc)),
+                                     "r"(cvt_e5m2x4(q[i][0], q[i][1])), "r"(cvt_e5m2x4(q[i][2], q[i][3])), "r"(cvt_e5m2x4(q[i][4], q[i][5])),
+                                     "r"(cvt_e5m2x4(q[i][6], q[i][7])) : "memory");
+                    }
+                    fence_proxy_async_smem();       // generic-proxy writes -> visible to the tensor core's reads
+                    __syncwarp();
+                    if (lane == 0) { if (leader) mbar_arrive(conv_bar(stage)); else mbar_arrive_cluster(conv_bar(stage), 0); }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
@@ -295,6 +405,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 if (!tile_live) continue;
                 const uint32_t e0 = (uint32_t)(m_base + (int)row) * (uint32_t)p.N + (uint32_t)n0;     // dropout counter of column n0
+                if (SPLIT == 2) {               // undo the 2^s pre-scale of the weight pair
+                    const float2 sc = make_float2(p.acc_scale, p.acc_scale);
+#pragma unroll
+                    for (int j = 0; j < CW / 2; ++j) v[j] = mul2(v[j], sc);
+                }
 
                 if (p.bias != nullptr) {
 #pragma unroll
@@ -490,7 +605,7 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int64_t rows
     else if (inner_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
     else if (inner_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
     else { set_last_error("unsupported TMA box width %d bytes", inner_bytes); return -1; }
-    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)(ld * elem_bytes)};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
@@ -527,7 +642,7 @@ int device_sm_count() {
     return sms;
 }
 
-template <int CG, int BN, int EPI, bool SPLIT>
+template <int CG, int BN, int EPI, int SPLIT>
 static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     using Cfg = GemmCfg<CG, BN, EPI, SPLIT>;
     using T = EpiTraits<EPI>;
@@ -535,7 +650,8 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     int rc;
     if ((rc = make_tmap_2d(&tmA, a.A, 2, a.M, a.K, a.lda, BLOCK_M, BLOCK_K))) return rc;
     if ((rc = make_tmap_2d(&tmB, a.B, 2, a.N, a.K, a.ldb, BN / CG, BLOCK_K))) return rc;
-    if (SPLIT) { if ((rc = make_tmap_2d(&tmB2, a.B_lo, 2, a.N, a.K, a.ldb, BN / CG, BLOCK_K))) return rc; } else tmB2 = tmB;
+    if (SPLIT == 2) { if ((rc = make_tmap_2d(&tmB2, a.B_lo8, 1, a.N, a.K, a.ldb, BN / CG, BLOCK_K))) return rc; }
+    else if (SPLIT == 1) { if ((rc = make_tmap_2d(&tmB2, a.B_lo, 2, a.N, a.K, a.ldb, BN / CG, BLOCK_K))) return rc; } else tmB2 = tmB;
     if ((rc = make_tmap_2d(&tmO0, a.out0, T::O0, a.M, a.N, a.ld0, BLOCK_M, Cfg::STRIPE))) return rc;
     const bool has_o1 = (EPI == EPI_GELU) || (T::O1 && a.out1 != nullptr);
     if (has_o1) { if ((rc = make_tmap_2d(&tmO1, a.out1, 2, a.M, a.N, a.ld1, BLOCK_M, Cfg::STRIPE))) return rc; } else tmO1 = tmO0;
@@ -550,6 +666,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.period = (int)a.aux_period; p.ld_table = (int)a.ldaux;
     p.has_out1 = has_o1 ? 1 : 0;
     p.rowdot = a.rowdot;
+    p.acc_scale = SPLIT == 2 ? ldexpf(1.0f, -a.lo8_shift) : 1.0f;
     p.drop_thresh = drop_thresh15(a.drop_p);
     p.drop_seed = a.drop_seed;
     p.drop_scale = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
@@ -567,7 +684,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     if (clusters > total) clusters = total;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * CG);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -581,7 +698,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     return 0;
 }
 
-template <int CG, int BN, bool SPLIT>
+template <int CG, int BN, int SPLIT>
 static int dispatch_epi(const GemmArgs& a, cudaStream_t s) {
     switch (a.epi) {
         case EPI_F16: return launch_gemm<CG, BN, EPI_F16, SPLIT>(a, s);
@@ -609,12 +726,18 @@ int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
     if (a.epi == EPI_PERIODIC_F32) GSL_REQUIRE(a.aux_period > 0, "EPI_PERIODIC_F32 needs aux_period > 0");
     const int cg = a.cta_group ? a.cta_group : g_default_cta_group;
     const int bn = a.block_n ? a.block_n : ((a.N % 256 == 0 || a.N > 1024) ? 256 : 128);
-    if (a.B_lo != nullptr) {
-        if (cg == 2) return bn == 256 ? dispatch_epi<2, 256, true>(a, stream) : dispatch_epi<2, 128, true>(a, stream);
-        return bn == 256 ? dispatch_epi<1, 256, true>(a, stream) : dispatch_epi<1, 128, true>(a, stream);
+    if (a.B_lo8 != nullptr) {
+        GSL_REQUIRE(a.B_lo == nullptr, "pass either B_lo (fp16 residual) or B_lo8 (e4m3 residual of the 2^shift-scaled weight), not both");
+        GSL_REQUIRE(cg == 2 && a.K % 64 == 0 && a.ldb % 16 == 0 && a.lo8_shift >= 0 && a.lo8_shift <= 24,
+                    "split8 GEMM needs cta_group 2, K %% 64 == 0, ldb %% 16 == 0 (K=%lld ldb=%lld)", (long long)a.K, (long long)a.ldb);
+        return bn == 256 ? dispatch_epi<2, 256, 2>(a, stream) : dispatch_epi<2, 128, 2>(a, stream);
     }
-    if (cg == 2) return bn == 256 ? dispatch_epi<2, 256, false>(a, stream) : dispatch_epi<2, 128, false>(a, stream);
-    return bn == 256 ? dispatch_epi<1, 256, false>(a, stream) : dispatch_epi<1, 128, false>(a, stream);
+    if (a.B_lo != nullptr) {
+        if (cg == 2) return bn == 256 ? dispatch_epi<2, 256, 1>(a, stream) : dispatch_epi<2, 128, 1>(a, stream);
+        return bn == 256 ? dispatch_epi<1, 256, 1>(a, stream) : dispatch_epi<1, 128, 1>(a, stream);
+    }
+    if (cg == 2) return bn == 256 ? dispatch_epi<2, 256, 0>(a, stream) : dispatch_epi<2, 128, 0>(a, stream);
+    return bn == 256 ? dispatch_epi<1, 256, 0>(a, stream) : dispatch_epi<1, 128, 0>(a, stream);
 }
 
 }  // namespace gsl

@@ -25,6 +25,8 @@ struct GemmArgs {
     const __half* A = nullptr; int64_t lda = 0;     // [M, K] row-major
     const __half* B = nullptr; int64_t ldb = 0;     // [N, K] row-major (a torch Linear weight)
     const __half* B_lo = nullptr;                   // optional second term of a split weight: C = epi(A (B + B_lo)^T), same shape / ldb as B
+    const uint8_t* B_lo8 = nullptr; int lo8_shift = 0;   // split8: B = fp16(W * 2^shift), B_lo8 = e4m3(W * 2^shift - B) [N, K] bytes (pitch ldb):
+                                                    // C = epi(2^-shift (A B^T + e5m2(A) B_lo8^T)), the residual term on the FP8 tensor path
     int64_t M = 0, N = 0, K = 0;
     int epi = EPI_F16;
     const float* bias = nullptr;
@@ -77,7 +79,8 @@ int lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __ha
 size_t lora_side_workspace(int64_t M, int N, int r);
 // fp32 -> fp16 casts with optional scale / transpose / column placement (weight cache building, LoRA operand packing)
 int cast_f32_to_f16(const float* src, int64_t lds, __half* dst, int64_t ldd, int64_t rows, int64_t cols, float scale,
-                    int transpose, cudaStream_t s, __half* dst_lo = nullptr);     // dst_lo: fp16(v - fp16(v)), same layout as dst
+                    int transpose, cudaStream_t s, __half* dst_lo = nullptr,     // dst_lo: fp16(v - dst), the second term of a split operand
+                    uint8_t* dst_lo8 = nullptr);                                  // dst_lo8: e4m3(v - dst) (split8; pass scale = 2^shift)     // dst_lo: fp16(v - fp16(v)), same layout as dst
 int fill_zero(void* ptr, size_t bytes, cudaStream_t s);
 
 // ---- attention (gsl_attention_fwd.cu / gsl_attention_bwd.cu, tcgen05); qkv fp16 [B*N, ld] with q|k|v column blocks of heads*64

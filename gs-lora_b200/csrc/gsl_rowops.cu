@@ -4,6 +4,7 @@
 // loads, one warp per row (or per 16 rows for the mma-based skinny products), fp32 arithmetic.
 #include "gsl_common.cuh"
 #include "gsl_kernels.h"
+#include <cuda_fp8.h>
 
 namespace gsl {
 
@@ -773,9 +774,10 @@ int lora_side(const __half* L, int64_t ldl, const __half* P16, int64_t ldp, __ha
 }
 
 // ------------------------------------------------------------------------------------------------ casts
-// dst = fp16(v), v = src * scale; dst_lo (optional, same layout) = fp16(v - dst): the second term of a split operand (hi + lo = v to ~2^-22)
-__global__ void cast_kernel(const float* __restrict__ src, int64_t lds, __half* __restrict__ dst, __half* __restrict__ dst_lo, int64_t ldd,
-                            int64_t rows, int64_t cols, float scale, int transpose) {
+// dst = fp16(v), v = src * scale; dst_lo (optional, same layout) = fp16(v - dst): the second term of a split operand (hi + lo = v to ~2^-22);
+// dst_lo8 (optional, same layout, one byte per element) = e4m3(v - dst): the FP8 residual of precision mode "split8" (scale = 2^shift there)
+__global__ void cast_kernel(const float* __restrict__ src, int64_t lds, __half* __restrict__ dst, __half* __restrict__ dst_lo, uint8_t* __restrict__ dst_lo8,
+                            int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose) {
     const int64_t total = rows * cols;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / cols, c = i % cols;
@@ -784,17 +786,18 @@ __global__ void cast_kernel(const float* __restrict__ src, int64_t lds, __half* 
         const int64_t o = transpose ? c * ldd + r : r * ldd + c;
         dst[o] = h;
         if (dst_lo) dst_lo[o] = __float2half_rn(v - __half2float(h));
+        if (dst_lo8) dst_lo8[o] = (uint8_t)__nv_cvt_float_to_fp8(v - __half2float(h), __NV_SATFINITE, __NV_E4M3);
     }
 }
 
 int cast_f32_to_f16(const float* src, int64_t lds, __half* dst, int64_t ldd, int64_t rows, int64_t cols, float scale, int transpose,
-                    cudaStream_t s, __half* dst_lo) {
+                    cudaStream_t s, __half* dst_lo, uint8_t* dst_lo8) {
     const int64_t total = rows * cols;
     if (total == 0) return 0;
     int blocks = (int)((total + 255) / 256);
     const int cap = device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    cast_kernel<<<blocks, 256, 0, s>>>(src, lds, dst, dst_lo, ldd, rows, cols, scale, transpose);
+    cast_kernel<<<blocks, 256, 0, s>>>(src, lds, dst, dst_lo, dst_lo8, ldd, rows, cols, scale, transpose);
     GSL_COUNT_LAUNCH(1);
     GSL_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -35,15 +35,17 @@ class GslConfig(ctypes.Structure):
                [("head_type", ctypes.c_int32), ("precision", ctypes.c_int32), ("lora_pos", ctypes.c_int32)]
 
 
-PRECISION_FAST, PRECISION_SPLIT = 0, 1
+PRECISION_FAST, PRECISION_SPLIT, PRECISION_SPLIT8 = 0, 1, 2
+PRECISION_BY_NAME = {"fast": PRECISION_FAST, "split": PRECISION_SPLIT, "split8": PRECISION_SPLIT8}
 
 
 def default_precision() -> int:
-    """GSLORA_PRECISION = split (default: fp16 hi + lo weights, LoRA gradients within the 1e-3 parity bar) | fast (one fp16 rounding per weight)."""
-    v = os.environ.get("GSLORA_PRECISION", "split").lower()
-    if v not in ("split", "fast"):
-        raise GslError(f"GSLORA_PRECISION={v!r}: expected 'split' or 'fast'")
-    return PRECISION_SPLIT if v == "split" else PRECISION_FAST
+    """GSLORA_PRECISION = split8 (default: fp16 hi + e4m3 lo weights, the lo term on the FP8 tensor path; LoRA gradients within the 1e-3 parity
+    bar) | split (fp16 hi + fp16 lo: two fp16 MMAs per k-step, same accuracy, 5 % slower) | fast (one fp16 rounding per weight: misses the bar)."""
+    v = os.environ.get("GSLORA_PRECISION", "split8").lower()
+    if v not in PRECISION_BY_NAME:
+        raise GslError(f"GSLORA_PRECISION={v!r}: expected one of {sorted(PRECISION_BY_NAME)}")
+    return PRECISION_BY_NAME[v]
 
 
 SLOT_EMB, SLOT_LOGITS, SLOT_CE, SLOT_CORRECT, SLOT_XFINAL = range(5)
@@ -61,6 +63,9 @@ def _declare(L):
     L.gsl_gemm_f16_split.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p,
                                      c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_float, ctypes.c_uint32, c_void_p]
     L.gsl_gemm_f16_split.restype = c_int
+    L.gsl_gemm_f16_split8.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p,
+                                      c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float, ctypes.c_uint32, c_void_p]
+    L.gsl_gemm_f16_split8.restype = c_int
     P = c_void_p
     sigs = {
         "gsl_patchify_f16": [P, P, c_int64, c_int, c_int, c_int, c_int, c_int, P],
@@ -74,6 +79,7 @@ def _declare(L):
         "gsl_lora_down_split": [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int, c_int, P],
         "gsl_lora_side_split": [P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int, c_float, c_int, c_int64, c_int, c_int, P, c_size_t, P],
         "gsl_cast_f32_to_f16_split": [P, c_int64, P, P, c_int64, c_int64, c_int64, c_float, c_int, P],
+        "gsl_cast_f32_to_f16_split8": [P, c_int64, P, P, c_int64, c_int64, c_int64, c_int, c_int, P],
         "gsl_skinny_tn": [P, c_int64, P, c_int64, P, c_int64, c_int, c_float, c_int, c_int64, c_int, c_int, P, c_size_t, P],
         "gsl_lora_side": [P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int, c_float, c_int, c_int64, c_int, c_int, P, c_size_t, P],
         "gsl_attention_fwd": [P, c_int64, P, c_int64, P, c_int, c_int, c_int, c_float, P],
@@ -123,7 +129,7 @@ EXPORTS = ["gsl_last_error", "gsl_version", "gsl_launch_count", "gsl_set_gemm_ct
            "gsl_engine_destroy", "gsl_engine_bind_params", "gsl_engine_refresh_frozen", "gsl_engine_refresh_lora", "gsl_engine_forward",
            "gsl_engine_backward", "gsl_engine_slot_ptr", "gsl_engine_lora_offset", "gsl_engine_lora_numel", "gsl_loss_sums",
            "gsl_unlearn_ce_grad", "gsl_prototype_kl_fwd", "gsl_prototype_kl_grad", "gsl_patchify_u8_f16", "gsl_engine_forward_u8",
-           "gsl_class_sums", "gsl_class_means", "gsl_gemm_f16_split", "gsl_lora_down_split", "gsl_lora_side_split", "gsl_cast_f32_to_f16_split",
+           "gsl_class_sums", "gsl_class_means", "gsl_gemm_f16_split", "gsl_lora_down_split", "gsl_lora_side_split", "gsl_cast_f32_to_f16_split", "gsl_cast_f32_to_f16_split8", "gsl_gemm_f16_split8",
            "gsl_engine_forward_dev", "gsl_grouplasso_adamw_step_dev", "gsl_count_launches"]
 
 
@@ -156,11 +162,19 @@ EPI_F16, EPI_F32, EPI_GELU, EPI_GELU_BWD, EPI_RES_F32, EPI_PERIODIC_F32, EPI_F16
 
 
 def gemm_f16(A, B, *, epi=EPI_F16, bias=None, out0, out1=None, aux=None, aux_period=0, K=None, N=None, M=None,
-             cta_group=0, block_n=0, drop_p=0.0, drop_seed=0, B_lo=None):
+             cta_group=0, block_n=0, drop_p=0.0, drop_seed=0, B_lo=None, B_lo8=None, lo8_shift=0):
     """out = epi(A[:, :K] @ (B [+ B_lo])[:, :K].T); A, B fp16 row-major 2-D (possibly column-sliced views); B_lo: split-weight residual."""
     M = A.shape[0] if M is None else M
     K = A.shape[1] if K is None else K
     N = B.shape[0] if N is None else N
+    if B_lo8 is not None:       # split8: B = fp16(W * 2^shift), B_lo8 = e4m3 residual bytes (cast_split8)
+        assert B_lo8.shape == B.shape and B_lo8.stride(0) == B.stride(0) and B_lo8.dtype == torch.uint8
+        rc = lib().gsl_gemm_f16_split8(ptr(A), A.stride(0), ptr(B), ptr(B_lo8), int(lo8_shift), B.stride(0), M, N, K, epi, ptr(bias),
+                                       ptr(out0), out0.stride(0), ptr(out1), out1.stride(0) if out1 is not None else 0,
+                                       ptr(aux), aux.stride(0) if aux is not None else 0, aux_period, block_n, float(drop_p), int(drop_seed),
+                                       cur_stream())
+        check(rc, "gsl_gemm_f16_split8")
+        return
     if B_lo is not None:
         assert B_lo.shape == B.shape and B_lo.stride(0) == B.stride(0)
         rc = lib().gsl_gemm_f16_split(ptr(A), A.stride(0), ptr(B), ptr(B_lo), B.stride(0), M, N, K, epi, ptr(bias),

@@ -105,7 +105,7 @@ class EngineBackedModel(nn.Module):
     def _spec(self) -> EngineSpec:
         spec = self.engine_spec()
         if self.gsl_precision is not None:
-            spec.precision = {"fast": F.PRECISION_FAST, "split": F.PRECISION_SPLIT}[self.gsl_precision]
+            spec.precision = F.PRECISION_BY_NAME[self.gsl_precision]
         return spec
 
     def ensure_engine(self, batch: int, slots: Optional[int] = None) -> VitEngine:

@@ -54,6 +54,12 @@ int gsl_gemm_f16_split(const void* A, int64_t lda, const void* B, const void* B_
                        int epi, const float* bias, void* out0, int64_t ld0, void* out1, int64_t ld1,
                        const void* aux, int64_t ldaux, int64_t aux_period, int cta_group, int block_n, float drop_p, uint32_t drop_seed,
                        void* stream);
+/* Precision mode "split8": B = fp16(W * 2^shift), B_lo8 = e4m3(W * 2^shift - B) [N, K] bytes with the same pitch ldb (gsl_cast_f32_to_f16_split8):
+   C = epi(2^-shift (A B^T + e5m2(A) B_lo8^T)).  The residual term runs on the FP8 tensor path (kind::f8f6f4) at twice the fp16 rate, the e5m2 copy
+   of every A tile is made inside the kernel: 1.5x the tensor work of gsl_gemm_f16 instead of 2x.  Needs K % 64 == 0, ldb % 16 == 0; cta_group 2. */
+int gsl_gemm_f16_split8(const void* A, int64_t lda, const void* B, const void* B_lo8, int shift, int64_t ldb, int64_t M, int64_t N, int64_t K, int epi,
+                        const float* bias, void* out0, int64_t ld0, void* out1, int64_t ld1, const void* aux, int64_t ldaux,
+                        int64_t aux_period, int block_n, float drop_p, uint32_t drop_seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Op-level entry points (each one kernel family; used by the engine and by the parity tests)
@@ -107,6 +113,9 @@ int gsl_cast_f32_to_f16(const float* src, int64_t lds, void* dst16, int64_t ldd,
 /* split form: dst16 = fp16(v), dst_lo16 = fp16(v - dst16), v = src * scale (the operand pair of gsl_gemm_f16_split) */
 int gsl_cast_f32_to_f16_split(const float* src, int64_t lds, void* dst16, void* dst_lo16, int64_t ldd, int64_t rows, int64_t cols, float scale,
                               int transpose, void* stream);
+/* dst16 = fp16(src * 2^shift), dst_lo8 = e4m3(src * 2^shift - dst16): the operand pair of gsl_gemm_f16_split8 */
+int gsl_cast_f32_to_f16_split8(const float* src, int64_t lds, void* dst16, void* dst_lo8, int64_t ldd, int64_t rows, int64_t cols, int shift,
+                               int transpose, void* stream);
 
 /* Fused group-Lasso + AdamW (engine_cl.get_structure_loss engine_cl.py:349-432 + torch.optim.AdamW as built by
  * timm create_optimizer, train_own_forget_cl.py:811-813).  group_offsets: device int32 [G+1] element offsets.

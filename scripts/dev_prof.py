@@ -65,6 +65,33 @@ if "split" in what:
     timeit(lambda: F.gemm_f16(A, Wo, B_lo=Wol, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=x), "SPLIT out-proj RES gemm (K=512)", flops=2.0 * M * D * D)
     timeit(lambda: F.gemm_f16(A, Wo, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=x), "plain out-proj RES gemm (K=512)", flops=2.0 * M * D * D)
     del A, W, Wl, o0, o1, W2, W2l, x, y, y16
+if "split8" in what:
+    # precision mode "split8": fp16(W 2^12) + e4m3 residual, the residual term on the FP8 tensor path
+    def pair8(n, k, std=0.05):
+        w = torch.randn(n, k, device=dev) * std
+        hi = torch.empty(n, k, device=dev, dtype=torch.half); lo8 = torch.empty(n, k, device=dev, dtype=torch.uint8)
+        F.check(F.lib().gsl_cast_f32_to_f16_split8(F.ptr(w), k, F.ptr(hi), F.ptr(lo8), k, n, k, 12, 0, F.cur_stream()))
+        return hi, lo8
+    A = (torch.randn(M, D, device=dev) * 0.5).half(); bias = torch.randn(H, device=dev)
+    W, Wl = pair8(H, D)
+    o0 = torch.empty(M, H, device=dev, dtype=torch.half); o1 = torch.empty(M, H, device=dev, dtype=torch.half)
+    kw = dict(lo8_shift=12)
+    timeit(lambda: F.gemm_f16(A, W, B_lo8=Wl, epi=F.EPI_GELU, bias=bias, out0=o0, out1=o1, drop_p=0.1, drop_seed=1234, **kw), "SPLIT8 fc1 GELU gemm, dropout 0.1", flops=2.0 * M * H * D)
+    timeit(lambda: F.gemm_f16(A, W, B_lo8=Wl, epi=F.EPI_GELU_BWD, out0=o1, aux=o0, **kw), "SPLIT8 dH gemm (x saved gelu')", flops=2.0 * M * H * D)
+    Wq, Wql = pair8(3 * D, D)
+    qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.half)
+    timeit(lambda: F.gemm_f16(A, Wq, B_lo8=Wql, epi=F.EPI_F16, out0=qkv, **kw), "SPLIT8 QKV F16 gemm", flops=2.0 * M * 3 * D * D)
+    WqT, WqlT = pair8(D, 3 * D)
+    timeit(lambda: F.gemm_f16(qkv, WqT, B_lo8=WqlT, epi=F.EPI_F16, out0=A, **kw), "SPLIT8 dLN1 F16 gemm (K=1536)", flops=2.0 * M * 3 * D * D)
+    del qkv, Wq, Wql, WqT, WqlT
+    W2, W2l = pair8(D, H)
+    x = torch.randn(M, D, device=dev); y = torch.empty(M, D, device=dev); b2 = torch.randn(D, device=dev)
+    timeit(lambda: F.gemm_f16(o1, W2, B_lo8=W2l, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=x, drop_p=0.1, drop_seed=99, **kw), "SPLIT8 fc2 RES gemm, dropout 0.1", flops=2.0 * M * D * H)
+    y16 = torch.empty(M, D, device=dev, dtype=torch.half)
+    timeit(lambda: F.gemm_f16(o1, W2, B_lo8=W2l, epi=F.EPI_F16, out0=y16, **kw), "SPLIT8 dXn F16 gemm (K=2048)", flops=2.0 * M * D * H)
+    Wo, Wol = pair8(D, D)
+    timeit(lambda: F.gemm_f16(A, Wo, B_lo8=Wol, epi=F.EPI_RES_F32, bias=b2, out0=y, aux=x, **kw), "SPLIT8 out-proj RES gemm (K=512)", flops=2.0 * M * D * D)
+    del A, W, Wl, o0, o1, W2, W2l, x, y, y16
 if "attn" in what:
     qkv = torch.randn(M, 3 * D, device=dev).half(); out = torch.empty(M, D, device=dev, dtype=torch.half); lse = torch.empty(B * heads * N, device=dev)
     sc = 512 ** -0.5

@@ -7,13 +7,13 @@ import csv
 import re
 import sys
 
-EPI = {0: "F16", 1: "F32", 2: "GELU", 3: "GELU_BWD", 4: "RES_F32", 5: "PERIODIC_F32", 6: "LN_F16"}
+EPI = {0: "F16", 1: "F32", 2: "GELU", 3: "GELU_BWD", 4: "RES_F32", 5: "PERIODIC_F32", 6: "F16_ROWDOT"}
 
 
 def short(name):
     m = re.search(r"gemm_tcgen05_kernel<(?:\(int\))?(\d), (?:\(int\))?(\d+), (?:\(int\))?(\d)(?:, (?:\(bool\))?(\w+))?>", name)
     if m:
-        split = ", SPLIT" if m.group(4) in ("1", "true") else ""
+        split = {"1": ", SPLIT", "true": ", SPLIT", "2": ", SPLIT8"}.get(m.group(4), "")
         return f"gsl::gemm_tcgen05_kernel<cg{m.group(1)}, bn{m.group(2)}, {EPI.get(int(m.group(3)), m.group(3))}{split}>"
     return re.sub(r"\(.*", "", name).replace("void ", "")
 

@@ -86,6 +86,59 @@ def test_layernorm_fwd_bwd(F, M, D):
     assert rel(dx16[:, :D].float(), want) < 1e-3
 
 
+def _e4m3_decode(b):
+    """uint8 tensor of e4m3 codes -> fp32 (bias 7, no infinities)."""
+    b = b.to(torch.int32)
+    sign = torch.where((b & 0x80) != 0, -1.0, 1.0)
+    e = (b >> 3) & 0xF
+    m = (b & 7).float()
+    val = torch.where(e == 0, m / 8 * 2.0 ** -6, (1 + m / 8) * torch.pow(2.0, (e - 7).float()))
+    return sign * val
+
+
+@pytest.mark.parametrize("M,N,K,epi,bn", [(512, 512, 512, 1, 256), (1000, 1536, 576, 1, 256), (777, 512, 2048, 4, 256), (300, 384, 192, 1, 128),
+                                          (9456, 512, 2048, 4, 0), (9456, 2048, 512, 2, 0), (9456, 512, 1536, 0, 0)])
+def test_gemm_split8_fp8_residual(F, M, N, K, epi, bn):
+    """Precision mode split8: B = fp16(W 2^s), B_lo8 = e4m3(W 2^s - B); the kernel adds e5m2(A) B_lo8^T on the FP8 tensor path and un-scales.
+    The product must sit far below the single-rounding floor (the fp16 weight error 2^-12 shrinks by the e4m3 / e5m2 precision, ~2^-4)."""
+    torch.manual_seed(M + N + K + 1)
+    shift = 12
+    A = (torch.randn(M, K, device="cuda") * 0.5).half()
+    W = torch.randn(N, K, device="cuda") * 0.05
+    hi = torch.empty(N, K, device="cuda", dtype=torch.half); lo8 = torch.empty(N, K, device="cuda", dtype=torch.uint8)
+    F.check(F.lib().gsl_cast_f32_to_f16_split8(F.ptr(W), K, F.ptr(hi), F.ptr(lo8), K, N, K, shift, 0, F.cur_stream()))
+    assert torch.equal(hi, (W * 2.0 ** shift).half())
+    recon = (hi.float() + _e4m3_decode(lo8)) * 2.0 ** -shift
+    assert rel(recon, W) < 2.5e-5 and rel(hi.float() * 2.0 ** -shift, W) > 1.5e-4       # ~15 significant bits vs 11
+    hiT = torch.empty(K, N, device="cuda", dtype=torch.half); lo8T = torch.empty(K, N, device="cuda", dtype=torch.uint8)
+    F.check(F.lib().gsl_cast_f32_to_f16_split8(F.ptr(W), K, F.ptr(hiT), F.ptr(lo8T), N, N, K, shift, 1, F.cur_stream()))
+    assert torch.equal(hiT, hi.t().contiguous()) and torch.equal(lo8T, lo8.t().contiguous())
+    bias = torch.randn(N, device="cuda")
+    exact = (A.double() @ W.double().t()).float() + bias
+    one_w = W.half()
+    if epi == F.EPI_F32:
+        out0 = torch.empty(M, N, device="cuda"); one = torch.empty(M, N, device="cuda")
+        F.gemm_f16(A, hi, B_lo8=lo8, lo8_shift=shift, epi=epi, bias=bias, out0=out0, block_n=bn)
+        F.gemm_f16(A, one_w, epi=epi, bias=bias, out0=one, block_n=bn)
+        print(f"split8 {M}x{N}x{K}: {rel(out0, exact):.2e} (single rounding {rel(one, exact):.2e})")
+        assert rel(out0, exact) < 3e-5
+        assert rel(one, exact) > 5 * rel(out0, exact)
+    elif epi == F.EPI_RES_F32:
+        res = torch.randn(M, N, device="cuda"); out0 = torch.empty(M, N, device="cuda")
+        F.gemm_f16(A, hi, B_lo8=lo8, lo8_shift=shift, epi=epi, bias=bias, out0=out0, aux=res, block_n=bn)
+        assert rel(out0, exact + res) < 3e-5
+    elif epi == F.EPI_F16:
+        out0 = torch.empty(M, N, device="cuda", dtype=torch.half)
+        F.gemm_f16(A, hi, B_lo8=lo8, lo8_shift=shift, epi=epi, bias=bias, out0=out0, block_n=bn)
+        assert rel(out0.float(), exact) < 4e-4      # fp16 output rounding
+    else:       # GELU: fp16 outputs, checked to fp16 rounding
+        gp = torch.empty(M, N, device="cuda", dtype=torch.half); g = torch.empty(M, N, device="cuda", dtype=torch.half)
+        F.gemm_f16(A, hi, B_lo8=lo8, lo8_shift=shift, epi=epi, bias=bias, out0=gp, out1=g, block_n=bn)
+        want = torch.nn.functional.gelu(exact)
+        assert (g.float() - want).abs().max() <= 1e-3 * want.abs().max() + 1e-4
+
+
+
 @pytest.mark.parametrize("M,K,r", [(1000, 512, 8), (197 * 5, 2048, 8), (333, 1024, 16), (50, 128, 8), (100, 272 - 16, 8)])
 def test_lora_down(F, M, K, r):
     torch.manual_seed(1)

@@ -355,7 +355,7 @@ def test_attention_lora_matches_unmodified_reference_golden(golden_dir):
     assert rel(le, lt) < 1e-3 and rel(lt2, lt) < 1e-4 and rel(le, g["eval_logits_r"].cuda()) < 5e-2
 
 
-@pytest.mark.parametrize("mode", ["split", "fast"])
+@pytest.mark.parametrize("mode", ["split8", "split", "fast"])
 def test_attention_lora_p8s8_vs_oracle_fp32(mode):
     """Config-2 widths with LoRA r = 8 on to_qkv, bs 32+32: logits and the 12 to_qkv LoRA gradients against the oracle in FP32 on the same GPU."""
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -377,4 +377,4 @@ def test_attention_lora_p8s8_vs_oracle_fp32(mode):
     allrel = rel(torch.cat([model.get_parameter(n).grad.flatten() for n in names]), torch.cat([ref_grads[n].flatten() for n in names]))
     print(f"attention LoRA P8S8 bs32 [{mode}]: logits {rel(out_r, ref['logits_r']):.2e} grads all {allrel:.2e} worst {max(per.values()):.2e}")
     assert rel(out_r, ref["logits_r"]) < 1e-3 and rel(out_f, ref["logits_f"]) < 1e-3
-    assert allrel < (1e-3 if mode == "split" else 3e-3) and max(per.values()) < (1.25e-3 if mode == "split" else 5e-3)
+    assert allrel < (1e-3 if mode != "fast" else 3e-3) and max(per.values()) < (1.5e-3 if mode != "fast" else 5e-3)

@@ -41,7 +41,7 @@ def _check(tag, dev, env, ref_dev):
         assert dev["first_cross"] is not None and lo <= dev["first_cross"] <= hi
 
 
-@pytest.mark.parametrize("mode", ["split", "fast"])
+@pytest.mark.parametrize("mode", ["split8", "split", "fast"])
 def test_tiny6_epoch_loop_free_running_vs_unmodified_reference_records(golden_dir, mode):
     import engine
     import engine_cl
@@ -85,7 +85,7 @@ def test_tiny6_epoch_loop_free_running_vs_unmodified_reference_records(golden_di
     assert collapsed == ref_dev["collapsed"] == [n1 < COLLAPSED * n0 for n0, n1 in zip(*g["group_norms"])] and any(collapsed) and not all(collapsed)
 
 
-@pytest.mark.parametrize("mode", ["split", "fast"])
+@pytest.mark.parametrize("mode", ["split8", "split", "fast"])
 def test_p8s8_bs32_free_running_steps_vs_oracle(mode):
     import engine_cl
     torch.backends.cuda.matmul.allow_tf32 = False
