@@ -76,7 +76,7 @@ static constexpr int EPI_GROUPS = 2;                      // two independent epi
 static constexpr int EPI_GROUP_WARPS = 8;                 // per group: two warps per TMEM lane quarter, each takes half of a stripe's columns
 static constexpr int EPI_WARPS = EPI_GROUPS * EPI_GROUP_WARPS;
 
-template <int CG, int BN, int EPI, int SPLIT = 0>
+template <int CG, int BN, int EPI, int SPLIT = 0, int EG = EPI_GROUPS>
 struct GemmCfg {
     using T = EpiTraits<EPI>;
     static constexpr int A_STAGE = BLOCK_M * BLOCK_K * 2;
@@ -96,8 +96,11 @@ struct GemmCfg {
     static constexpr int O1_BUF = BLOCK_M * STRIPE * T::O1;
     static constexpr int AUX_BUF = BLOCK_M * STRIPE * T::AUX;
     // aux stripes in flight per group: a TMA round trip is ~3x a stripe's epilogue time, so two when the operand ring keeps >= 4 stages
-    static constexpr int AUX_DEPTH = (SMEM_LIMIT - 1024 - EPI_GROUPS * (O0_BUF + O1_BUF + 2 * AUX_BUF) - 1024) / STAGE >= 4 ? 2 : 1;
-    static constexpr int EPI_TOTAL = EPI_GROUPS * (O0_BUF + O1_BUF + AUX_DEPTH * AUX_BUF);   // one staging set per group (the groups alternate)
+    // EG = epilogue groups that WORK (1 or 2; the warps of an idle group only hand the accumulator back).  With a long K loop the epilogue
+    // of a tile is a fraction of its MMA time, and one group's staging instead of two buys the split8 operand ring its 4th stage -- which
+    // the TMA -> convert -> MMA chain of that mode needs (3 stages: tensor pipe 67 % active on fc2 / dH, 4 stages: 90 %).
+    static constexpr int AUX_DEPTH = (SMEM_LIMIT - 1024 - EG * (O0_BUF + O1_BUF + 2 * AUX_BUF) - 1024) / STAGE >= 4 ? 2 : 1;
+    static constexpr int EPI_TOTAL = EG * (O0_BUF + O1_BUF + AUX_DEPTH * AUX_BUF);   // one staging set per working group (the groups alternate)
     static constexpr int BAR_BYTES = 1024;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - EPI_TOTAL - BAR_BYTES) / STAGE;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -169,12 +172,12 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64
     }
 }
 
-template <int CG, int BN, int EPI, int SPLIT>
-__global__ void __launch_bounds__((GemmCfg<CG, BN, EPI, SPLIT>::THREADS), 1)
+template <int CG, int BN, int EPI, int SPLIT, int EG>
+__global__ void __launch_bounds__((GemmCfg<CG, BN, EPI, SPLIT, EG>::THREADS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
                     const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                     const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
-    using Cfg = GemmCfg<CG, BN, EPI, SPLIT>;
+    using Cfg = GemmCfg<CG, BN, EPI, SPLIT, EG>;
     using T = EpiTraits<EPI>;
     constexpr int S = Cfg::STAGES;
 
@@ -374,10 +377,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int nstripes = ((n_rem >= BN ? BN : n_rem) + STRIPE - 1) / STRIPE;
             const bool tile_live = m_base < p.M;     // CTA-uniform (the second CTA of a pair can be past the M tail)
 
-            if (T::AUX && tile_live && elected) {       // this group's first two aux stripes of the tile
+            if (T::AUX && tile_live && elected && grp < (uint32_t)EG) {       // this group's first two aux stripes of the tile
 #pragma unroll
                 for (int q = 0; q < Cfg::AUX_DEPTH; ++q) {
-                    const int sq = (int)grp + q * EPI_GROUPS;
+                    const int sq = (int)grp + q * EG;
                     if (sq < nstripes) {
                         const uint32_t slot = (aux_it + q) % Cfg::AUX_DEPTH;
                         mbar_arrive_expect_tx(aux_bar(grp * 2 + slot), Cfg::AUX_BUF);
@@ -387,17 +390,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
-            if ((int)grp >= nstripes) {              // nothing to do for this group in a narrow tile: just release the accumulator
+            if ((int)grp >= nstripes || grp >= (uint32_t)EG) {      // nothing to do for this group (narrow tile, or an idle group): just release the accumulator
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) { if (CG == 2 && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
             }
 
-            for (int sidx = grp; sidx < nstripes; sidx += EPI_GROUPS) {
+            for (int sidx = grp; sidx < (grp < (uint32_t)EG ? nstripes : 0); sidx += EG) {
                 const int n0 = n_base + sidx * STRIPE + (int)half * CW;      // first column of this warp
                 float2 v[CW / 2];                                            // this thread's CW accumulator columns, as pairs
                 tmem_ld_cols<CW>(tmem_base + ((quarter * 32u) << 16) + acc * BN + sidx * STRIPE + half * CW, v);
-                if (sidx + EPI_GROUPS >= nstripes) {
+                if (sidx + EG >= nstripes) {
                     // this warp's last TMEM read of the accumulator (tcgen05.wait::ld is warp-wide): hand the buffer back to the MMA warp
                     tcgen05_fence_before();
                     __syncwarp();
@@ -526,10 +529,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // has consumed the aux stripe by the time it reaches the barrier
                 if (elected) tma_store_wait_read<0>();
                 epi_bar_sync(grp);
-                if (T::AUX && elected && sidx + Cfg::AUX_DEPTH * EPI_GROUPS < nstripes) {     // refill the slot just consumed: two stripes ahead
+                if (T::AUX && elected && sidx + Cfg::AUX_DEPTH * EG < nstripes) {     // refill the slot just consumed: two stripes ahead
                     const uint32_t slot = (aux_it - 1) % Cfg::AUX_DEPTH;      // (aux_it was advanced when this stripe's aux was consumed)
                     mbar_arrive_expect_tx(aux_bar(grp * 2 + slot), Cfg::AUX_BUF);
-                    tma_load_2d<1>(&tmAux, aux_bar(grp * 2 + slot), aux_base + slot * Cfg::AUX_BUF, n_base + (sidx + Cfg::AUX_DEPTH * EPI_GROUPS) * STRIPE, m_base);
+                    tma_load_2d<1>(&tmAux, aux_bar(grp * 2 + slot), aux_base + slot * Cfg::AUX_BUF, n_base + (sidx + Cfg::AUX_DEPTH * EG) * STRIPE, m_base);
                 }
 
                 if (T::O0 == 4) {   // fp32 [128 x 32] stripe: this warp's 16 columns = 16-byte chunks half*4 .. +3
@@ -642,9 +645,9 @@ int device_sm_count() {
     return sms;
 }
 
-template <int CG, int BN, int EPI, int SPLIT>
+template <int CG, int BN, int EPI, int SPLIT, int EG = EPI_GROUPS>
 static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
-    using Cfg = GemmCfg<CG, BN, EPI, SPLIT>;
+    using Cfg = GemmCfg<CG, BN, EPI, SPLIT, EG>;
     using T = EpiTraits<EPI>;
     CUtensorMap tmA, tmB, tmB2, tmO0, tmO1, tmAux;
     int rc;
@@ -672,7 +675,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.drop_scale = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
     p.gelu = make_gelu_consts(p.drop_thresh ? p.drop_scale : 1.0f);
 
-    auto kern = gemm_tcgen05_kernel<CG, BN, EPI, SPLIT>;
+    auto kern = gemm_tcgen05_kernel<CG, BN, EPI, SPLIT, EG>;
     static bool attr_set = false;
     if (!attr_set) {
         GSL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -704,8 +707,11 @@ static int dispatch_epi(const GemmArgs& a, cudaStream_t s) {
         case EPI_F16: return launch_gemm<CG, BN, EPI_F16, SPLIT>(a, s);
         case EPI_F32: return launch_gemm<CG, BN, EPI_F32, SPLIT>(a, s);
         case EPI_GELU: return launch_gemm<CG, BN, EPI_GELU, SPLIT>(a, s);
-        case EPI_GELU_BWD: return launch_gemm<CG, BN, EPI_GELU_BWD, SPLIT>(a, s);
-        case EPI_RES_F32: return launch_gemm<CG, BN, EPI_RES_F32, SPLIT>(a, s);
+        // split8 with a long K loop: one working epilogue group (its staging alone leaves room for the ring's 4th stage, see GemmCfg)
+        case EPI_GELU_BWD: if (SPLIT == 2 && a.K >= 1024) return launch_gemm<CG, BN, EPI_GELU_BWD, SPLIT, 1>(a, s);
+                           return launch_gemm<CG, BN, EPI_GELU_BWD, SPLIT>(a, s);
+        case EPI_RES_F32: if (SPLIT == 2 && a.K >= 1024) return launch_gemm<CG, BN, EPI_RES_F32, SPLIT, 1>(a, s);
+                          return launch_gemm<CG, BN, EPI_RES_F32, SPLIT>(a, s);
         case EPI_PERIODIC_F32: return launch_gemm<CG, BN, EPI_PERIODIC_F32, SPLIT>(a, s);
         case EPI_F16_ROWDOT: return launch_gemm<CG, BN, EPI_F16_ROWDOT, SPLIT>(a, s);
         default: set_last_error("unknown GEMM epilogue %d", a.epi); return -1;
