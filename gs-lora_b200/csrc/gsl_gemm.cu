@@ -708,7 +708,7 @@ static int dispatch_epi(const GemmArgs& a, cudaStream_t s) {
         case EPI_F32: return launch_gemm<CG, BN, EPI_F32, SPLIT>(a, s);
         case EPI_GELU: return launch_gemm<CG, BN, EPI_GELU, SPLIT>(a, s);
         // split8 with a long K loop: one working epilogue group (its staging alone leaves room for the ring's 4th stage, see GemmCfg)
-        case EPI_GELU_BWD: if (SPLIT == 2 && a.K >= 1024) return launch_gemm<CG, BN, EPI_GELU_BWD, SPLIT, 1>(a, s);
+        case EPI_GELU_BWD: if (SPLIT == 2 && a.K >= 512) return launch_gemm<CG, BN, EPI_GELU_BWD, SPLIT, 1>(a, s);
                            return launch_gemm<CG, BN, EPI_GELU_BWD, SPLIT>(a, s);
         case EPI_RES_F32: if (SPLIT == 2 && a.K >= 1024) return launch_gemm<CG, BN, EPI_RES_F32, SPLIT, 1>(a, s);
                           return launch_gemm<CG, BN, EPI_RES_F32, SPLIT>(a, s);
