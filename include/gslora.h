@@ -152,7 +152,10 @@ typedef struct GslConfig {
   int32_t head_type;     /* 0 = CosFace on LN(cls) (ViT_face), 1 = Linear + bias on LN(cls) (torchvision heads.head, modified_VIT.py:23-39) */
   int32_t precision;     /* 0 = "fast": every frozen weight rounded to fp16 once (LoRA gradients ~1-2e-3 of the FP32 reference);
                             1 = "split": weights and LoRA factors enter the GEMMs as fp16 hi + lo pairs (22 significand bits; gradients <= 1e-3,
-                            the north-star parity bar) at 2x the tensor-pipe work.  Activations are fp16 with fp32 accumulation in both. */
+                            the north-star parity bar) at 2x the tensor-pipe work;
+                            2 = "split8" (the Python surface's default): frozen weights as fp16(W 2^12) + e4m3 residual, the residual term on the FP8 tensor
+                            path against an in-kernel e5m2 copy of the activation tile (~15 significand bits; gradients <= 1e-3) at 1.5x the tensor-pipe
+                            work; LoRA factors as fp16 hi + lo pairs; needs mlp_dim % 64 == 0.  Activations are fp16 with fp32 accumulation in all three. */
   int32_t lora_pos;      /* 0 = "FFN": lora.Linear on net.0 / net.3 (every GS-LoRA script); 1 = "Attention": lora.MergedLinear(r, enable_lora = [T, T, T]) on
                             to_qkv and plain FFN Linears (vit_face.py:349-355, 405-425; engine.py:650-656) */
 } GslConfig;

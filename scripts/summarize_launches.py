@@ -11,10 +11,11 @@ EPI = {0: "F16", 1: "F32", 2: "GELU", 3: "GELU_BWD", 4: "RES_F32", 5: "PERIODIC_
 
 
 def short(name):
-    m = re.search(r"gemm_tcgen05_kernel<(?:\(int\))?(\d), (?:\(int\))?(\d+), (?:\(int\))?(\d)(?:, (?:\(bool\))?(\w+))?>", name)
+    m = re.search(r"gemm_tcgen05_kernel<(?:\(int\))?(\d), (?:\(int\))?(\d+), (?:\(int\))?(\d)(?:, (?:\((?:bool|int)\))?(\w+))?(?:, (?:\(int\))?(\d))?>", name)
     if m:
         split = {"1": ", SPLIT", "true": ", SPLIT", "2": ", SPLIT8"}.get(m.group(4), "")
-        return f"gsl::gemm_tcgen05_kernel<cg{m.group(1)}, bn{m.group(2)}, {EPI.get(int(m.group(3)), m.group(3))}{split}>"
+        eg = ", 1 epilogue group" if m.group(5) == "1" else ""
+        return f"gsl::gemm_tcgen05_kernel<cg{m.group(1)}, bn{m.group(2)}, {EPI.get(int(m.group(3)), m.group(3))}{split}{eg}>"
     return re.sub(r"\(.*", "", name).replace("void ", "")
 
 
