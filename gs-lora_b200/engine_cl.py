@@ -201,8 +201,9 @@ class StepResult:
             c = self._c
             s_ce_r, n_r, s_ce_f, n_f, hit_r, hit_f, s_kl_r, s_kl_f, structure = host[:9]
             if structure != structure:       # NaN: gsl_grouplasso_adamw_step found inf / NaN in a group's gradient and skipped that group
-                raise FloatingPointError("unlearn_step: the loss-scaled fp16 gradient stream overflowed (non-finite LoRA gradient); the affected "
-                                         "groups were not updated -- lower GSLORA_GRAD_SCALE (default 1024)")
+                raise FloatingPointError("unlearn_step: non-finite LoRA gradient; the affected groups were not updated.  Either the loss-scaled fp16 "
+                                         "gradient stream overflowed -- lower GSLORA_GRAD_SCALE (default 1024) -- or, in precision mode split8, a frozen "
+                                         "weight reaches |W| >= 16 and its 2^12-scaled fp16 operand overflowed -- use GSLORA_PRECISION=split")
             if self._n > 9 and host[9] != 0.0:
                 raise KeyError("unlearn_step: a label of this step's batch has no entry in prototype_dict (engine_cl.py:571-603 looks every "
                                "label up in the dict)")

@@ -45,6 +45,22 @@ def make_model(cfg=O.TINY, **kw):
                     dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp_dim=cfg.mlp_dim, lora_rank=cfg.lora_rank, **kw)
 
 
+def test_precision_modes_by_name_and_default(monkeypatch):
+    """GslConfig.precision values behind the Python surface (include/gslora.h): split8 is the default, the environment can select any mode,
+    an unknown name fails loudly instead of falling back."""
+    import pytest
+    from gslora import _ffi as F
+    assert F.PRECISION_BY_NAME == {"fast": 0, "split": 1, "split8": 2}
+    monkeypatch.delenv("GSLORA_PRECISION", raising=False)
+    assert F.default_precision() == F.PRECISION_SPLIT8
+    for name, val in F.PRECISION_BY_NAME.items():
+        monkeypatch.setenv("GSLORA_PRECISION", name.upper())
+        assert F.default_precision() == val
+    monkeypatch.setenv("GSLORA_PRECISION", "bf16")
+    with pytest.raises(F.GslError):
+        F.default_precision()
+
+
 def test_state_dict_names_and_counts_match_reference_surface():
     import loralib as lora
     m = make_model(O.P8S8, dropout=0.1, emb_dropout=0.1)

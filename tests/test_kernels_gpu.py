@@ -108,6 +108,8 @@ def test_gemm_split8_fp8_residual(F, M, N, K, epi, bn):
     hi = torch.empty(N, K, device="cuda", dtype=torch.half); lo8 = torch.empty(N, K, device="cuda", dtype=torch.uint8)
     F.check(F.lib().gsl_cast_f32_to_f16_split8(F.ptr(W), K, F.ptr(hi), F.ptr(lo8), K, N, K, shift, 0, F.cur_stream()))
     assert torch.equal(hi, (W * 2.0 ** shift).half())
+    want8 = (W * 2.0 ** shift - hi.float()).to(torch.float8_e4m3fn).view(torch.uint8)      # torch's round-to-nearest-even e4m3 cast of the same residual
+    assert (lo8 == want8).float().mean() > 0.9999 and ((lo8 & 0x7F).int() - (want8 & 0x7F).int()).abs().max() <= 1
     recon = (hi.float() + _e4m3_decode(lo8)) * 2.0 ** -shift
     assert rel(recon, W) < 2.5e-5 and rel(hi.float() * 2.0 ** -shift, W) > 1.5e-4       # ~15 significant bits vs 11
     hiT = torch.empty(K, N, device="cuda", dtype=torch.half); lo8T = torch.empty(K, N, device="cuda", dtype=torch.uint8)
