@@ -730,12 +730,12 @@ int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
     if (a.epi == EPI_GELU_BWD || a.epi == EPI_RES_F32 || a.epi == EPI_PERIODIC_F32 || a.epi == EPI_F16_ROWDOT) GSL_REQUIRE(a.aux != nullptr, "epilogue %d needs aux", a.epi);
     if (a.epi == EPI_F16_ROWDOT) GSL_REQUIRE(a.rowdot != nullptr && a.N % 64 == 0 && (a.aux_period == 0 || a.M % a.aux_period == 0), "EPI_F16_ROWDOT needs rowdot, N %% 64 == 0 and M %% aux_period == 0");
     if (a.epi == EPI_PERIODIC_F32) GSL_REQUIRE(a.aux_period > 0, "EPI_PERIODIC_F32 needs aux_period > 0");
-    const int cg = a.cta_group ? a.cta_group : g_default_cta_group;
+    const int cg = a.B_lo8 ? 2 : a.cta_group ? a.cta_group : g_default_cta_group;      // (split8 exists for cta_group::2 only)
     const int bn = a.block_n ? a.block_n : ((a.N % 256 == 0 || a.N > 1024) ? 256 : 128);
     if (a.B_lo8 != nullptr) {
         GSL_REQUIRE(a.B_lo == nullptr, "pass either B_lo (fp16 residual) or B_lo8 (e4m3 residual of the 2^shift-scaled weight), not both");
-        GSL_REQUIRE(cg == 2 && a.K % 64 == 0 && a.ldb % 16 == 0 && a.lo8_shift >= 0 && a.lo8_shift <= 24,
-                    "split8 GEMM needs cta_group 2, K %% 64 == 0, ldb %% 16 == 0 (K=%lld ldb=%lld)", (long long)a.K, (long long)a.ldb);
+        GSL_REQUIRE(a.K % 64 == 0 && a.ldb % 16 == 0 && a.lo8_shift >= 0 && a.lo8_shift <= 24,
+                    "split8 GEMM needs K %% 64 == 0, ldb %% 16 == 0, shift in [0, 24] (K=%lld ldb=%lld shift=%d)", (long long)a.K, (long long)a.ldb, a.lo8_shift);
         return bn == 256 ? dispatch_epi<2, 256, 2>(a, stream) : dispatch_epi<2, 128, 2>(a, stream);
     }
     if (a.B_lo != nullptr) {
