@@ -122,7 +122,11 @@ def test_gemm_split8_fp8_residual(F, M, N, K, epi, bn):
         out0 = torch.empty(M, N, device="cuda"); one = torch.empty(M, N, device="cuda")
         F.gemm_f16(A, hi, B_lo8=lo8, lo8_shift=shift, epi=epi, bias=bias, out0=out0, block_n=bn)
         F.gemm_f16(A, one_w, epi=epi, bias=bias, out0=one, block_n=bn)
-        print(f"split8 {M}x{N}x{K}: {rel(out0, exact):.2e} (single rounding {rel(one, exact):.2e})")
+        # the oracle's restatement of this arithmetic (fp16 x fp16 + e5m2 x e4m3, exact products, fp64 accumulation): agreement to accumulation order
+        from oracle import operand_emul as E
+        emul = E.gemm(A.cpu(), "split8", W.cpu(), shift).float().cuda() + bias
+        print(f"split8 {M}x{N}x{K}: {rel(out0, exact):.2e} vs FP32 (single rounding {rel(one, exact):.2e}), {rel(out0, emul):.2e} vs the operand emulation")
+        assert rel(out0, emul) < 2e-6
         assert rel(out0, exact) < 3e-5
         assert rel(one, exact) > 5 * rel(out0, exact)
     elif epi == F.EPI_RES_F32:
