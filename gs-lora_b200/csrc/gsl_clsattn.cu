@@ -42,36 +42,44 @@ __global__ void __launch_bounds__(128) cls_attention_fwd_kernel(const __half* __
     const int iters = (N + 3) >> 2;
     float s[CLS_ITERS];
     float mx = -INFINITY;
+    // Branch-free in chunks of 8 iterations: rows past the end are CLAMPED (a valid address, the value is masked afterwards), so the eight
+    // 16-byte loads of a chunk are independent straight-line code and go out together.  (With a per-lane `if (j < N)` around each load the
+    // compiler emitted load -> dot -> shuffles strictly one key group after the other: 0.20 ms for 413 MB, pure latency.)
 #pragma unroll
-    for (int i = 0; i < CLS_ITERS; ++i) {
-        s[i] = -INFINITY;
-        if (i < iters) {
-            const int j = 4 * i + g;
-            float acc = 0.f;
-            if (j < N) {
-                float k[8];
-                load8(base + (int64_t)j * ld + D, k);
+    for (int c8 = 0; c8 < CLS_ITERS; c8 += 8) {
+        if (c8 < iters) {                                       // warp-uniform
+            float kk[8][8];
 #pragma unroll
-                for (int d = 0; d < 8; ++d) acc = fmaf(k[d], q[d], acc);
+            for (int u = 0; u < 8; ++u) load8(base + (int64_t)min(4 * (c8 + u) + g, N - 1) * ld + D, kk[u]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = 4 * (c8 + u) + g;
+                float acc = 0.f;
+#pragma unroll
+                for (int d = 0; d < 8; ++d) acc = fmaf(kk[u][d], q[d], acc);
+                acc = group_sum8(acc);
+                s[c8 + u] = j < N ? acc * scale : -INFINITY;
+                mx = fmaxf(mx, s[c8 + u]);
             }
-            acc = group_sum8(acc);
-            s[i] = j < N ? acc * scale : -INFINITY;
-            mx = fmaxf(mx, s[i]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[c8 + u] = -INFINITY;
         }
     }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
     float sum = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < CLS_ITERS; ++i) {
-        if (i < iters) {
-            const int j = 4 * i + g;
-            if (j < N) {
-                const float p = __expf(s[i] - mx);
-                sum += p;
-                float v[8];
-                load8(base + (int64_t)j * ld + 2 * D, v);
+    for (int c8 = 0; c8 < CLS_ITERS; c8 += 8) {
+        if (c8 < iters) {
+            float vv[8][8];
 #pragma unroll
-                for (int d = 0; d < 8; ++d) o[d] = fmaf(p, v[d], o[d]);
+            for (int u = 0; u < 8; ++u) load8(base + (int64_t)min(4 * (c8 + u) + g, N - 1) * ld + 2 * D, vv[u]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float p = __expf(s[c8 + u] - mx);         // masked keys: s = -inf -> p = 0
+                sum += p;
+#pragma unroll
+                for (int d = 0; d < 8; ++d) o[d] = fmaf(p, vv[u][d], o[d]);
             }
         }
     }
