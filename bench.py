@@ -447,8 +447,10 @@ def kernel_roofline(dev, cfg, peaks, BATCH=BATCH, DROPOUT=DROPOUT, mode="split")
         traffic = traffic_src = None                                   # the committed ncu capture is of the P8S8 shape
     # tensor-pipe time really issued, in fp16-MMA units: split = two fp16 MMAs per k-step, split8 = one fp16 MMA + one FP8 MMA at twice the rate
     mma = 2.0 * M * D * H * 2 * {"fast": 1.0, "split": 2.0, "split8": 1.75}[mode]      # (split8: fc1 at 2.0, fc2 at 1.5)
-    return dict(bound="tensor", kernel=f"gemm_tcgen05_kernel<2,256,EPI_GELU,{mode}> + <2,256,EPI_RES_F32,...> (FFN+LoRA pair, "
-                       f"precision {mode}, dropout {DROPOUT})",
+    kname = {"fast": "gemm_tcgen05_kernel<2,256,EPI_GELU,0,2> + <2,256,EPI_RES_F32,0,2>",
+             "split": "gemm_tcgen05_kernel<2,256,EPI_GELU,SPLIT,2> + <2,256,EPI_RES_F32,SPLIT,2>",
+             "split8": "gemm_tcgen05_kernel<2,256,EPI_GELU,SPLIT,2> [fc1 keeps the fp16 residual] + <2,256,EPI_RES_F32,SPLIT8,1> [e4m3 residual, one epilogue group]"}[mode]
+    return dict(bound="tensor", kernel=f"{kname} (FFN+LoRA pair, precision {mode}, dropout {DROPOUT})",
                 achieved=round(ach, 1), peak=peaks["burst"], unit="TFLOP/s", frac=round(ach / peaks["burst"], 4),
                 executed_frac=round(mma / ms / 1e9 / peaks["burst"], 4), traffic=traffic,
                 traffic_source=traffic_src, algorithmic_bytes=int(alg_bytes), ms_per_launch_pair=round(ms, 4),
